@@ -1,0 +1,170 @@
+"""Synthetic workloads for the BASELINE.json configs.
+
+Host-side numpy only; nothing here is on the hot path.  The same arrays are handed to the
+CUDA path and to the CPU oracle, so the generator's RNG only has to be seeded, not bit-stable
+across numpy versions.
+"""
+import numpy as np
+
+
+def triangle_aabbs(n, seed=12345, shift=(0.0, 0.0, 0.0), ndims=3):
+    """C1/C3: n triangle AABBs; centres uniform in [0,1)^D, vertices = centre + h*U(-1/2,1/2)^D,
+    h = n^(-1/D).  Returns (n, 2*D) float64 [min..., max...] (the primal::BoundingBox layout)."""
+    rng = np.random.default_rng(seed)
+    h = float(n) ** (-1.0 / ndims)
+    c = rng.random((n, 1, ndims))
+    v = c + h * (rng.random((n, 3, ndims)) - 0.5)
+    v = v + np.asarray(shift, np.float64)[:ndims]
+    return np.ascontiguousarray(np.concatenate([v.min(axis=1), v.max(axis=1)], axis=1))
+
+
+def random_points(q, seed=12345 + 1, lo=0.0, hi=1.0, ndims=3):
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(lo + (hi - lo) * rng.random((q, ndims)))
+
+
+def random_rays(q, seed=777, lo=-1.0, hi=1.0, ndims=3):
+    """C4: origins uniform in [lo,hi]^D, directions uniform on the sphere (normalised Gaussian)."""
+    rng = np.random.default_rng(seed)
+    o = lo + (hi - lo) * rng.random((q, ndims))
+    d = rng.standard_normal((q, ndims))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.ascontiguousarray(o), np.ascontiguousarray(d)
+
+
+_ICO_FACES = None
+
+
+def _icosahedron():
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                  [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5],
+                  [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], np.int64)
+    return v, f
+
+
+def icosphere(freq, radius=0.5, center=(0.0, 0.0, 0.0)):
+    """Geodesic icosphere of frequency `freq`: 20*freq^2 triangles, 10*freq^2+2 welded vertices,
+    consistent outward (CCW from outside) winding.  C2 uses freq=316 (1 997 120 triangles),
+    C4 freq=1000 (20 000 000 triangles).
+    Returns x, y, z (float64) and conn (ntri,3) int32."""
+    n = int(freq)
+    V, F = _icosahedron()
+    # global vertex ids: 12 corners | 30 edges x (n-1) | 20 faces x (n-1)(n-2)/2
+    edges = {}
+    for f in F:
+        for a, b in ((f[0], f[1]), (f[1], f[2]), (f[2], f[0])):
+            key = (min(a, b), max(a, b))
+            if key not in edges:
+                edges[key] = len(edges)
+    n_edge_pts = n - 1
+    n_face_pts = (n - 1) * (n - 2) // 2
+    nverts = 12 + 30 * n_edge_pts + 20 * n_face_pts
+    P = np.empty((nverts, 3), np.float64)
+    P[:12] = V
+    ts = np.arange(1, n, dtype=np.float64)[:, None]
+    for (a, b), e in edges.items():
+        base = 12 + e * n_edge_pts
+        P[base:base + n_edge_pts] = ((n - ts) * V[a] + ts * V[b]) / n
+
+    # per-face barycentric lattice: point (i,j) with i+j<=n is ((n-i-j)*A + i*B + j*C)/n
+    ii, jj = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    lattice_valid = (ii + jj) <= n
+    # interior numbering (i>=1, j>=1, i+j<=n-1), row-major in i then j
+    interior = (ii >= 1) & (jj >= 1) & ((ii + jj) <= n - 1)
+    interior_id = -np.ones((n + 1, n + 1), np.int64)
+    interior_id[interior] = np.arange(n_face_pts)
+
+    def edge_point(a, b, t):
+        """id of the point at parameter t (from a towards b) on edge (a,b), t in 0..n (vectorised)"""
+        key = (min(a, b), max(a, b))
+        e = edges[key]
+        tt = t if a < b else n - t
+        out = 12 + e * n_edge_pts + (tt - 1)
+        out = np.where(tt == 0, key[0], out)
+        out = np.where(tt == n, key[1], out)
+        return out
+
+    conn_all = []
+    for fi, (A, B, C) in enumerate(F):
+        gid = -np.ones((n + 1, n + 1), np.int64)
+        fbase = 12 + 30 * n_edge_pts + fi * n_face_pts
+        gid[interior] = fbase + interior_id[interior]
+        if n_face_pts:
+            i_in, j_in = ii[interior].astype(np.float64)[:, None], jj[interior].astype(np.float64)[:, None]
+            P[fbase:fbase + n_face_pts] = ((n - i_in - j_in) * V[A] + i_in * V[B] + j_in * V[C]) / n
+        t = np.arange(n + 1)
+        gid[t, 0] = edge_point(A, B, t)          # j == 0: from A (i=0) to B (i=n)
+        gid[0, t] = edge_point(A, C, t)          # i == 0: from A (j=0) to C (j=n)
+        gid[t, n - t] = edge_point(C, B, t)      # i + j == n: from C (i=0) to B (i=n)
+        # upward triangles (i,j),(i+1,j),(i,j+1) for i+j<=n-1; downward (i+1,j),(i+1,j+1),(i,j+1) for i+j<=n-2
+        iu, ju = np.nonzero((ii + jj) <= n - 1)
+        up = np.stack([gid[iu, ju], gid[iu + 1, ju], gid[iu, ju + 1]], axis=1)
+        idn, jdn = np.nonzero((ii + jj) <= n - 2)
+        dn = np.stack([gid[idn + 1, jdn], gid[idn + 1, jdn + 1], gid[idn, jdn + 1]], axis=1)
+        conn_all.append(up)
+        conn_all.append(dn)
+        assert lattice_valid[iu, ju].all()
+    conn = np.concatenate(conn_all, axis=0)
+    P /= np.linalg.norm(P, axis=1, keepdims=True)
+    P = P * radius + np.asarray(center, np.float64)
+    # make sure the winding is outward
+    a, b, c = P[conn[:, 0]], P[conn[:, 1]], P[conn[:, 2]]
+    nrm = np.cross(b - a, c - a)
+    flip = (nrm * (a + b + c - 3 * np.asarray(center))).sum(axis=1) < 0
+    conn[flip] = conn[flip][:, [0, 2, 1]]
+    return (np.ascontiguousarray(P[:, 0]), np.ascontiguousarray(P[:, 1]), np.ascontiguousarray(P[:, 2]),
+            np.ascontiguousarray(conn.astype(np.int32)))
+
+
+def latlong_sphere(radius=0.5, theta_res=25, phi_res=25, center=(0.0, 0.0, 0.0)):
+    """The reference test's sphere mesh (quest/tests/quest_test_utilities.hpp:51-151), restated:
+    same node order, same connectivity (including its seam/pole quirks), so the golden norms of
+    quest/tests/quest_signed_distance.cpp:88-91 apply."""
+    deg = np.pi / 180.0
+    cx, cy, cz = center
+    xs, ys, zs = [cx, cx], [cy, cy], [cz + radius, cz - radius]
+    dphi = (180 * deg) / float(phi_res - 1)
+    dtheta = (360 * deg) / float(theta_res - 1)
+    for i in range(theta_res):
+        theta = i * dtheta
+        for j in range(phi_res - 2):
+            phi = j * dphi
+            r = radius * np.sin(phi)
+            xs.append(r * np.cos(theta) + cx)
+            ys.append(r * np.sin(theta) + cy)
+            zs.append(radius * np.cos(phi) + cz)
+    pr = phi_res - 2
+    stride = pr * theta_res
+    cells = []
+    for i in range(theta_res):
+        cells.append([0, (pr * (i + 1) % stride) + 2, pr * i + 2])
+    off = phi_res - 1
+    for i in range(theta_res):
+        cells.append([1, (pr * (i + 1) % stride) + off, pr * i + off])
+    for i in range(theta_res):
+        for j in range(phi_res - 3):
+            c0 = pr * i + j + 2
+            c2 = ((pr * (i + 1) + j) % stride) + 3
+            cells.append([c0, c0 + 1, c2])
+            cells.append([c0, c2, c2 - 1])
+    return (np.array(xs, np.float64), np.array(ys, np.float64), np.array(zs, np.float64), np.array(cells, np.int32))
+
+
+def uniform_grid_points(lo, hi, n):
+    """n^3 (or nx,ny,nz) lattice nodes spanning [lo,hi], x fastest (mint::UniformMesh node order)."""
+    lo = np.broadcast_to(np.asarray(lo, np.float64), (3,))
+    hi = np.broadcast_to(np.asarray(hi, np.float64), (3,))
+    nn = np.broadcast_to(np.asarray(n, np.int64), (3,))
+    axes = [lo[d] + np.arange(nn[d], dtype=np.float64) * ((hi[d] - lo[d]) / (nn[d] - 1)) for d in range(3)]
+    zz, yy, xx = np.meshgrid(axes[2], axes[1], axes[0], indexing="ij")
+    return np.ascontiguousarray(np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1))
+
+
+def mesh_cell_boxes(x, y, z, conn):
+    """per-cell AABB over the cell's nodes (quest/SignedDistance.hpp:608-633), (ncells, 6)."""
+    P = np.stack([x, y, z], axis=1)[conn]
+    return np.ascontiguousarray(np.concatenate([P.min(axis=1), P.max(axis=1)], axis=1))

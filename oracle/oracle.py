@@ -1,0 +1,185 @@
+"""ctypes wrapper over the CPU oracle libraries.  TEST INFRASTRUCTURE ONLY.
+
+Two back ends share one interface (same entry points, different prefix):
+  kind="port"       oracle/liboracle.so          -- our restatement (axb_oracle.cpp)
+  kind="reference"  oracle/_ref/libaxom_ref.so   -- the real LLNL/axom SEQ_EXEC path (ref_driver.cpp)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (axom_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT = os.path.join(HERE, "liboracle.so")
+_REF = os.path.join(HERE, "_ref", "libaxom_ref.so")
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def build_port():
+    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"])
+
+
+def have_reference():
+    return os.path.exists(_REF)
+
+
+class _Lib:
+    def __init__(self, kind):
+        self.kind = kind
+        if kind == "port":
+            if not os.path.exists(_PORT):
+                build_port()
+            self.lib = C.CDLL(_PORT)
+            self.pfx = "axo_"
+        elif kind == "reference":
+            if not os.path.exists(_REF):
+                raise FileNotFoundError(_REF + " (run python oracle/build_ref.py where /root/reference exists)")
+            self.lib = C.CDLL(_REF)
+            self.pfx = "axref_"
+        else:
+            raise ValueError(kind)
+        f = self.fn
+        f("bvh_create").restype = C.c_void_p
+        f("bvh_create").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double]
+        f("bvh_destroy").argtypes = [C.c_void_p]
+        f("bvh_num_leaves").argtypes = [C.c_void_p]
+        f("bvh_get").argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        f("free").argtypes = [C.c_void_p]
+        for name in ("bvh_find_points", "bvh_find_boxes"):
+            f(name).restype = C.c_int64
+            f(name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        f("bvh_find_rays").restype = C.c_int64
+        f("bvh_find_rays").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_void_p)]
+        f("bvh_count_points_omp").restype = C.c_int64
+        f("bvh_count_points_omp").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        f("sd_create").restype = C.c_void_p
+        f("sd_create").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        f("sd_destroy").argtypes = [C.c_void_p]
+        f("sd_compute").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f("max_threads").restype = C.c_int
+
+    def fn(self, name):
+        return getattr(self.lib, self.pfx + name)
+
+
+_libs = {}
+
+
+def lib(kind="port"):
+    if kind not in _libs:
+        _libs[kind] = _Lib(kind)
+    return _libs[kind]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Bvh:
+    """spin::BVH<D, SEQ_EXEC, double> on the CPU (port or real reference)."""
+
+    def __init__(self, boxes, ndims=3, scale=-1.0, tol=-1.0, kind="port"):
+        self.L = lib(kind)
+        self.ndims = ndims
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 2 * ndims)
+        self.n_in = boxes.shape[0]
+        self.h = self.L.fn("bvh_create")(ndims, _ptr(boxes), self.n_in, float(scale), float(tol))
+        self.n = self.L.fn("bvh_num_leaves")(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.fn("bvh_destroy")(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def arrays(self):
+        n, inner, D = self.n, self.n - 1, self.ndims
+        out = dict(
+            mcodes=np.empty(n, np.uint32), leafs=np.empty(n, np.int32), lchild=np.empty(inner, np.int32),
+            rchild=np.empty(inner, np.int32), parents=np.empty(inner + n, np.int32),
+            inner_nodes=np.empty((2 * inner, 2 * D), np.float64), inner_children=np.empty(2 * inner, np.int32),
+            bounds=np.empty(2 * D, np.float64))
+        self.L.fn("bvh_get")(self.h, *[_ptr(out[k]) for k in
+                                       ("mcodes", "leafs", "lchild", "rchild", "parents", "inner_nodes", "inner_children", "bounds")])
+        return out
+
+    def _collect(self, total, cand_p):
+        cand = np.ctypeslib.as_array(C.cast(cand_p, C.POINTER(C.c_int32)), shape=(max(int(total), 1),))[:int(total)].copy()
+        self.L.fn("free")(cand_p)
+        return cand
+
+    def find_points(self, pts):
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, self.ndims)
+        q = pts.shape[0]
+        off, cnt = np.empty(q, np.int32), np.empty(q, np.int32)
+        cp = C.c_void_p()
+        tot = self.L.fn("bvh_find_points")(self.h, _ptr(pts), q, _ptr(off), _ptr(cnt), C.byref(cp))
+        return off, cnt, self._collect(tot, cp)
+
+    def find_boxes(self, qboxes):
+        qb = np.ascontiguousarray(qboxes, np.float64).reshape(-1, 2 * self.ndims)
+        q = qb.shape[0]
+        off, cnt = np.empty(q, np.int32), np.empty(q, np.int32)
+        cp = C.c_void_p()
+        tot = self.L.fn("bvh_find_boxes")(self.h, _ptr(qb), q, _ptr(off), _ptr(cnt), C.byref(cp))
+        return off, cnt, self._collect(tot, cp)
+
+    def find_rays(self, origins, dirs, normalize=True):
+        o = np.ascontiguousarray(origins, np.float64).reshape(-1, self.ndims)
+        d = np.ascontiguousarray(dirs, np.float64).reshape(-1, self.ndims)
+        q = o.shape[0]
+        off, cnt = np.empty(q, np.int32), np.empty(q, np.int32)
+        cp = C.c_void_p()
+        tot = self.L.fn("bvh_find_rays")(self.h, _ptr(o), _ptr(d), q, int(bool(normalize)), _ptr(off), _ptr(cnt), C.byref(cp))
+        return off, cnt, self._collect(tot, cp)
+
+    def count_points_omp(self, pts, nthreads=0):
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, self.ndims)
+        cnt = np.empty(pts.shape[0], np.int32)
+        tot = self.L.fn("bvh_count_points_omp")(self.h, _ptr(pts), pts.shape[0], _ptr(cnt), int(nthreads))
+        return int(tot), cnt
+
+
+class SignedDistance:
+    """quest::SignedDistance<3, SEQ_EXEC> on the CPU (port or real reference)."""
+
+    def __init__(self, x, y, z, conn, nodes_per_cell=3, watertight=True, compute_sign=True, kind="port"):
+        self.L = lib(kind)
+        self.x = np.ascontiguousarray(x, np.float64)
+        self.y = np.ascontiguousarray(y, np.float64)
+        self.z = np.ascontiguousarray(z, np.float64)
+        self.conn = np.ascontiguousarray(conn, np.int32).reshape(-1)
+        ncells = self.conn.size // nodes_per_cell
+        self.h = self.L.fn("sd_create")(_ptr(self.x), _ptr(self.y), _ptr(self.z), self.x.size, _ptr(self.conn), ncells,
+                                        nodes_per_cell, int(watertight), int(compute_sign))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.fn("sd_destroy")(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def compute(self, qpts, want_cp=False, want_normals=False, nthreads=1):
+        q = np.ascontiguousarray(qpts, np.float64).reshape(-1, 3)
+        n = q.shape[0]
+        phi = np.empty(n, np.float64)
+        cp = np.empty((n, 3), np.float64) if want_cp else None
+        nr = np.empty((n, 3), np.float64) if want_normals else None
+        self.L.fn("sd_compute")(self.h, _ptr(q), n, _ptr(phi), _ptr(cp), _ptr(nr), int(nthreads))
+        return phi, cp, nr
+
+
+def max_threads(kind="port"):
+    return lib(kind).fn("max_threads")()

@@ -1,0 +1,357 @@
+// ref_driver.cpp -- thin C ABI over the UNMODIFIED reference (LLNL/axom v0.11.0) so that
+// tests and bench.py can run the reference's own SEQ_EXEC path from Python/ctypes.
+//
+// TEST INFRASTRUCTURE ONLY (see oracle/build_ref.py).  This file contains no algorithm:
+// every entry point forwards to the reference's public API
+//   spin::BVH<D,SEQ_EXEC,double>           (spin/BVH.hpp:129)
+//   lbvh::build_radix_tree<SEQ_EXEC>       (spin/internal/linear_bvh/build_radix_tree.hpp:579)
+//   quest::SignedDistance<3,SEQ_EXEC>      (quest/SignedDistance.hpp:147)
+// The entry points mirror oracle/axb_oracle.cpp one to one (axref_* vs axo_*), so the same
+// Python wrapper drives both.
+#include "axom/config.hpp"
+#include "axom/core/Array.hpp"
+#include "axom/core/ArrayView.hpp"
+#include "axom/core/execution/execution_space.hpp"
+#include "axom/slic/interface/slic.hpp"
+#include "axom/slic/core/SimpleLogger.hpp"
+#include "axom/primal/geometry/BoundingBox.hpp"
+#include "axom/primal/geometry/Point.hpp"
+#include "axom/primal/geometry/Ray.hpp"
+#include "axom/primal/geometry/Vector.hpp"
+#include "axom/spin/BVH.hpp"
+#include "axom/mint/mesh/UnstructuredMesh.hpp"
+#include "axom/quest/SignedDistance.hpp"
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#ifdef _OPENMP
+  #include <omp.h>
+#endif
+
+namespace
+{
+using axom::SEQ_EXEC;
+namespace lbvh = axom::spin::internal::linear_bvh;
+
+void ensure_slic()
+{
+  if(!axom::slic::isInitialized())
+  {
+    axom::slic::initialize();
+    axom::slic::setLoggingMsgLevel(axom::slic::message::Warning);
+    axom::slic::addStreamToAllMsgLevels(new axom::slic::GenericOutputStream(&std::cerr));
+  }
+}
+
+// LinearBVHTraverser (spin/policy/LinearBVH.hpp:57-109) keeps its three ArrayViews private;
+// this mirror has the same members in the same order so the arrays can be read out.
+template <int D>
+struct TraverserMirror
+{
+  axom::ArrayView<const axom::primal::BoundingBox<double, D>> inner_nodes;
+  axom::ArrayView<const std::int32_t> inner_children;
+  axom::ArrayView<const std::int32_t> leaf_nodes;
+};
+
+template <int D>
+struct RefBvh
+{
+  using BVHType = axom::spin::BVH<D, SEQ_EXEC, double>;
+  using BoxType = axom::primal::BoundingBox<double, D>;
+  BVHType bvh;
+  int n_in = 0;
+  // radix-tree internals, from a second (identical) call of build_radix_tree
+  lbvh::RadixTree<double, D> radix;
+};
+
+template <int D>
+RefBvh<D>* create(const double* boxes_aos, int n, double scale, double tol)
+{
+  using BoxType = typename RefBvh<D>::BoxType;
+  static_assert(sizeof(BoxType) == sizeof(double) * 2 * D, "BoundingBox is min[D],max[D]");
+  ensure_slic();
+  RefBvh<D>* r = new RefBvh<D>();
+  r->n_in = n;
+  if(scale > 0) r->bvh.setScaleFactor(scale);
+  if(tol >= 0) r->bvh.setTolerance(tol);
+  const BoxType* boxes = reinterpret_cast<const BoxType*>(boxes_aos);
+  r->bvh.initialize(boxes, n);
+  // internals: same padding as BVH::initialize (spin/BVH.hpp:439-464)
+  std::vector<BoxType> tmp;
+  int m = n;
+  if(n <= 1)
+  {
+    tmp.resize(2);
+    tmp[0].clear();
+    tmp[1].clear();
+    if(n == 1) tmp[0] = boxes[0];
+    boxes = tmp.data();
+    m = 2;
+  }
+  BoxType bounds;
+  lbvh::build_radix_tree<SEQ_EXEC>(boxes, m, bounds, r->radix, r->bvh.getScaleFactor(), r->bvh.getAllocatorID());
+  return r;
+}
+
+template <int D>
+void get_arrays(const RefBvh<D>& r, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
+                double* inner_nodes, int32_t* inner_children, double* bounds)
+{
+  using BoxType = typename RefBvh<D>::BoxType;
+  const int n = r.radix.m_size, inner = n - 1;
+  if(mcodes) memcpy(mcodes, r.radix.m_mcodes.data(), sizeof(uint32_t) * n);
+  if(leafs) memcpy(leafs, r.radix.m_leafs.data(), sizeof(int32_t) * n);
+  if(lchild) memcpy(lchild, r.radix.m_left_children.data(), sizeof(int32_t) * inner);
+  if(rchild) memcpy(rchild, r.radix.m_right_children.data(), sizeof(int32_t) * inner);
+  if(parents) memcpy(parents, r.radix.m_parents.data(), sizeof(int32_t) * (inner + n));
+  auto trav = r.bvh.getTraverser();
+  static_assert(sizeof(trav) == sizeof(TraverserMirror<D>), "traverser layout changed");
+  TraverserMirror<D> tm;
+  memcpy((void*)&tm, (const void*)&trav, sizeof(tm));
+  if(inner_nodes) memcpy(inner_nodes, tm.inner_nodes.data(), sizeof(BoxType) * 2 * inner);
+  if(inner_children) memcpy(inner_children, tm.inner_children.data(), sizeof(int32_t) * 2 * inner);
+  if(leafs)
+  {
+    // the final leaf_nodes array must equal the radix tree's permutation
+    if(memcmp(leafs, tm.leaf_nodes.data(), sizeof(int32_t) * n) != 0) abort();
+  }
+  if(bounds)
+  {
+    BoxType b = r.bvh.getBounds();
+    memcpy(bounds, &b, sizeof(BoxType));
+  }
+}
+
+int32_t* to_malloc(const axom::Array<axom::IndexType>& a)
+{
+  const size_t n = a.size();
+  int32_t* p = (int32_t*)malloc(sizeof(int32_t) * (n ? n : 1));
+  if(n) memcpy(p, a.data(), sizeof(int32_t) * n);
+  return p;
+}
+
+template <int D>
+int64_t find_points(const RefBvh<D>& r, const double* pts, int q, int32_t* off, int32_t* cnt, int32_t** cand)
+{
+  using PointType = axom::primal::Point<double, D>;
+  axom::Array<axom::IndexType> c;
+  r.bvh.findPoints(axom::ArrayView<axom::IndexType>(off, q), axom::ArrayView<axom::IndexType>(cnt, q), c, q,
+                   reinterpret_cast<const PointType*>(pts));
+  *cand = to_malloc(c);
+  return c.size();
+}
+
+template <int D>
+int64_t find_boxes(const RefBvh<D>& r, const double* bx, int q, int32_t* off, int32_t* cnt, int32_t** cand)
+{
+  using BoxType = typename RefBvh<D>::BoxType;
+  axom::Array<axom::IndexType> c;
+  r.bvh.findBoundingBoxes(axom::ArrayView<axom::IndexType>(off, q), axom::ArrayView<axom::IndexType>(cnt, q), c, q,
+                          reinterpret_cast<const BoxType*>(bx));
+  *cand = to_malloc(c);
+  return c.size();
+}
+
+template <int D>
+int64_t find_rays(const RefBvh<D>& r, const double* orig, const double* dirs, int q, int normalize, int32_t* off, int32_t* cnt,
+                  int32_t** cand)
+{
+  using RayType = axom::primal::Ray<double, D>;
+  using PointType = axom::primal::Point<double, D>;
+  using VectorType = axom::primal::Vector<double, D>;
+  std::vector<RayType> rays;
+  rays.reserve(q);
+  for(int i = 0; i < q; ++i)
+  {
+    PointType o(orig + (size_t)i * D, D);
+    VectorType d(dirs + (size_t)i * D, D);
+    RayType ray(o, d);  // normalises (Ray.hpp:122-127)
+    if(!normalize)
+    {
+      // store the direction verbatim, as a caller holding already-built Ray objects would
+      struct Raw
+      {
+        PointType o;
+        VectorType d;
+      } raw {o, d};
+      static_assert(sizeof(Raw) == sizeof(RayType), "Ray is origin,direction");
+      memcpy((void*)&ray, &raw, sizeof(ray));
+    }
+    rays.push_back(ray);
+  }
+  axom::Array<axom::IndexType> c;
+  r.bvh.findRays(axom::ArrayView<axom::IndexType>(off, q), axom::ArrayView<axom::IndexType>(cnt, q), c, q, rays.data());
+  *cand = to_malloc(c);
+  return c.size();
+}
+
+struct RefSurface
+{
+  using Mesh = axom::mint::UnstructuredMesh<axom::mint::SINGLE_SHAPE>;
+  using SD = axom::quest::SignedDistance<3, SEQ_EXEC>;
+  Mesh* mesh = nullptr;
+  SD* sd = nullptr;
+  ~RefSurface()
+  {
+    delete sd;
+    delete mesh;
+  }
+};
+
+}  // namespace
+
+struct AxrefBvh
+{
+  int ndims;
+  void* impl;
+};
+
+extern "C" {
+
+AxrefBvh* axref_bvh_create(int ndims, const double* boxes_aos, int n, double scale, double tol)
+{
+  AxrefBvh* h = new AxrefBvh {ndims, nullptr};
+  h->impl = ndims == 2 ? (void*)create<2>(boxes_aos, n, scale, tol) : (void*)create<3>(boxes_aos, n, scale, tol);
+  return h;
+}
+
+void axref_bvh_destroy(AxrefBvh* h)
+{
+  if(!h) return;
+  if(h->ndims == 2)
+    delete(RefBvh<2>*)h->impl;
+  else
+    delete(RefBvh<3>*)h->impl;
+  delete h;
+}
+
+int axref_bvh_num_leaves(const AxrefBvh* h)
+{
+  return h->ndims == 2 ? ((RefBvh<2>*)h->impl)->radix.m_size : ((RefBvh<3>*)h->impl)->radix.m_size;
+}
+
+void axref_bvh_get(const AxrefBvh* h, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
+                   double* inner_nodes, int32_t* inner_children, double* bounds)
+{
+  if(h->ndims == 2)
+    get_arrays(*(RefBvh<2>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
+  else
+    get_arrays(*(RefBvh<3>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
+}
+
+void axref_free(void* p) { free(p); }
+
+int64_t axref_bvh_find_points(const AxrefBvh* h, const double* pts_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
+{
+  return h->ndims == 2 ? find_points(*(RefBvh<2>*)h->impl, pts_aos, q, offsets, counts, cand)
+                       : find_points(*(RefBvh<3>*)h->impl, pts_aos, q, offsets, counts, cand);
+}
+
+int64_t axref_bvh_find_boxes(const AxrefBvh* h, const double* boxes_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
+{
+  return h->ndims == 2 ? find_boxes(*(RefBvh<2>*)h->impl, boxes_aos, q, offsets, counts, cand)
+                       : find_boxes(*(RefBvh<3>*)h->impl, boxes_aos, q, offsets, counts, cand);
+}
+
+int64_t axref_bvh_find_rays(const AxrefBvh* h, const double* origins_aos, const double* dirs_aos, int q, int normalize,
+                            int32_t* offsets, int32_t* counts, int32_t** cand)
+{
+  return h->ndims == 2 ? find_rays(*(RefBvh<2>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand)
+                       : find_rays(*(RefBvh<3>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand);
+}
+
+// Reference traversal (getTraverser().traverse_tree, policy/LinearBVH.hpp:92-103) driven by an
+// external OpenMP loop: RAJA is absent here so OMP_EXEC cannot be instantiated.
+int64_t axref_bvh_count_points_omp(const AxrefBvh* h, const double* pts_aos, int q, int32_t* counts, int nthreads)
+{
+  if(h->ndims != 3) return -1;
+  using PointType = axom::primal::Point<double, 3>;
+  using BoxType = axom::primal::BoundingBox<double, 3>;
+  const auto trav = ((RefBvh<3>*)h->impl)->bvh.getTraverser();
+  const PointType* pts = reinterpret_cast<const PointType*>(pts_aos);
+  int64_t total = 0;
+#ifdef _OPENMP
+  if(nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : total)
+  for(int i = 0; i < q; ++i)
+  {
+    int c = 0;
+    const PointType p = pts[i];
+    auto leafAction = [&c](std::int32_t, const std::int32_t*) { ++c; };
+    auto pred = [](const PointType& pp, const BoxType& bb) { return bb.contains(pp); };
+    // generic (non-point) overload has no child ordering, like findCandidatesImpl
+    struct Wrap
+    {
+      PointType p;
+    } w {p};
+    auto pred2 = [](const Wrap& ww, const BoxType& bb) { return bb.contains(ww.p); };
+    (void)pred;
+    trav.traverse_tree(w, leafAction, pred2);
+    counts[i] = c;
+    total += c;
+  }
+  return total;
+}
+
+void* axref_sd_create(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, int ncells,
+                      int nodes_per_cell, int watertight, int compute_sign)
+{
+  ensure_slic();
+  RefSurface* s = new RefSurface();
+  const axom::mint::CellType ct = nodes_per_cell == 3 ? axom::mint::TRIANGLE : axom::mint::QUAD;
+  s->mesh = new RefSurface::Mesh(3, ct, nnodes, ncells);
+  for(int i = 0; i < nnodes; ++i) s->mesh->appendNode(x[i], y[i], z[i]);
+  for(int c = 0; c < ncells; ++c)
+  {
+    axom::IndexType ids[4];
+    for(int k = 0; k < nodes_per_cell; ++k) ids[k] = conn[(size_t)c * nodes_per_cell + k];
+    s->mesh->appendCell(ids);
+  }
+  s->sd = new RefSurface::SD(s->mesh, watertight != 0, compute_sign != 0);
+  return s;
+}
+
+void axref_sd_destroy(void* h) { delete(RefSurface*)h; }
+
+void axref_sd_compute(void* h, const double* qpts_aos, int npts, double* phi, double* cp, double* normals, int nthreads)
+{
+  using PointType = axom::primal::Point<double, 3>;
+  using VectorType = axom::primal::Vector<double, 3>;
+  const RefSurface& s = *(RefSurface*)h;
+  const PointType* q = reinterpret_cast<const PointType*>(qpts_aos);
+  PointType* cps = reinterpret_cast<PointType*>(cp);
+  VectorType* nrm = reinterpret_cast<VectorType*>(normals);
+  if(nthreads == 1)
+  {
+    s.sd->computeDistances(npts, q, phi, cps, nrm);
+    return;
+  }
+  // chunked computeDistances from an external OpenMP loop (method is const)
+#ifdef _OPENMP
+  if(nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  const int chunk = 64;
+  const int nchunks = (npts + chunk - 1) / chunk;
+#pragma omp parallel for schedule(dynamic, 1)
+  for(int c = 0; c < nchunks; ++c)
+  {
+    const int b = c * chunk;
+    const int m = (b + chunk <= npts) ? chunk : npts - b;
+    s.sd->computeDistances(m, q + b, phi + b, cps ? cps + b : nullptr, nrm ? nrm + b : nullptr);
+  }
+}
+
+int axref_max_threads()
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"
