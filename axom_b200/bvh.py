@@ -1,0 +1,244 @@
+"""Host-side mirror of axom::spin::BVH (spin/BVH.hpp:129-419) over the C ABI.
+
+Method names and argument meaning follow the reference class so the parity tests read like
+spin/tests/spin_bvh.cpp.  Inputs may be
+  * numpy float64 arrays (host)  -> staged by the library, results come back as numpy arrays;
+  * torch CUDA float64 tensors   -> used in place, results come back as torch tensors
+    (torch is only the device-memory container here);
+  * a tuple/list of per-component 1-D arrays/tensors (the primal::ZipIndexable SoA form).
+Everything is executed by libaxb200.so; nothing is computed in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MEM_DEVICE, MEM_HOST, ArrayDesc, Traverser, check
+
+BVH_BUILD_OK = 0
+DEFAULT_SCALE_FACTOR = 1.000123
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+class _Keep:
+    """descriptor + the arrays it points into (kept alive for the duration of the call)"""
+
+    def __init__(self, desc, refs, count, device):
+        self.desc, self.refs, self.count, self.device = desc, refs, count, device
+
+
+def make_desc(data, ncomp):
+    """Build an axb_array_desc for AoS (n, ncomp) or SoA (ncomp x (n,)) input on host or device."""
+    d = ArrayDesc()
+    d.ncomp = ncomp
+    if isinstance(data, (tuple, list)):
+        if len(data) != ncomp:
+            raise ValueError("expected %d component arrays, got %d" % (ncomp, len(data)))
+        if all(_is_torch(a) for a in data):
+            comps = [a.contiguous() for a in data]
+            for a in comps:
+                if not a.is_cuda or str(a.dtype) != "torch.float64" or a.dim() != 1:
+                    raise ValueError("SoA components must be 1-D CUDA float64 tensors")
+            n = comps[0].numel()
+            for c, a in enumerate(comps):
+                d.comp[c] = a.data_ptr()
+            d.stride_bytes, d.memspace = 8, MEM_DEVICE
+            return _Keep(d, comps, n, True)
+        comps = [np.ascontiguousarray(a, np.float64).reshape(-1) for a in data]
+        n = comps[0].size
+        for c, a in enumerate(comps):
+            if a.size != n:
+                raise ValueError("SoA components differ in length")
+            d.comp[c] = a.ctypes.data
+        d.stride_bytes, d.memspace = 8, MEM_HOST
+        return _Keep(d, comps, n, False)
+    if _is_torch(data):
+        if not data.is_cuda or str(data.dtype) != "torch.float64":
+            raise ValueError("device input must be a CUDA float64 tensor")
+        a = data.contiguous().reshape(-1, ncomp)
+        base = a.data_ptr()
+        for c in range(ncomp):
+            d.comp[c] = base + 8 * c
+        d.stride_bytes, d.memspace = 8 * ncomp, MEM_DEVICE
+        return _Keep(d, [a], a.shape[0], True)
+    a = np.ascontiguousarray(data, np.float64).reshape(-1, ncomp)
+    base = a.ctypes.data
+    for c in range(ncomp):
+        d.comp[c] = base + 8 * c
+    d.stride_bytes, d.memspace = 8 * ncomp, MEM_HOST
+    return _Keep(d, [a], a.shape[0], False)
+
+
+class BVH:
+    """spin::BVH<NDIMS, B200, double>."""
+
+    def __init__(self, ndims=3, device=0, _borrowed=None):
+        self._L = _lib.lib()
+        self.ndims = ndims
+        self.device = device
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = C.c_void_p()
+            check(self._L.axb_bvh_create(C.byref(h), ndims, 8, device))
+            self._h = h
+        else:
+            self._h = _borrowed
+
+    def __del__(self):
+        try:
+            if getattr(self, "_owned", False) and getattr(self, "_h", None):
+                self._L.axb_bvh_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- configuration (spin/BVH.hpp:255-289) ----
+    def setScaleFactor(self, s):
+        check(self._L.axb_bvh_set_scale_factor(self._h, float(s)))
+
+    def getScaleFactor(self):
+        v = C.c_double()
+        check(self._L.axb_bvh_get_scale_factor(self._h, C.byref(v)))
+        return v.value
+
+    def setTolerance(self, t):
+        check(self._L.axb_bvh_set_tolerance(self._h, float(t)))
+
+    def getTolerance(self):
+        v = C.c_double()
+        check(self._L.axb_bvh_get_tolerance(self._h, C.byref(v)))
+        return v.value
+
+    def setStream(self, cuda_stream_ptr):
+        check(self._L.axb_bvh_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def setAsync(self, enabled):
+        check(self._L.axb_bvh_set_async(self._h, int(bool(enabled))))
+
+    def synchronize(self):
+        check(self._L.axb_bvh_synchronize(self._h))
+
+    def setProfiling(self, enabled):
+        check(self._L.axb_bvh_set_profiling(self._h, int(bool(enabled))))
+
+    def phase_ms(self, name):
+        v = C.c_double()
+        check(self._L.axb_bvh_get_phase_ms(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        v = C.c_int64()
+        check(self._L.axb_bvh_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # ---- build (spin/BVH.hpp:424-477) ----
+    def initialize(self, boxes, numItems=None):
+        k = make_desc(boxes, 2 * self.ndims)
+        n = k.count if numItems is None else int(numItems)
+        if n > k.count:
+            raise ValueError("numItems exceeds the supplied boxes")
+        st = self._L.axb_bvh_initialize(self._h, C.byref(k.desc), n)
+        if st < 0:
+            check(st)
+        return st
+
+    def isInitialized(self):
+        return bool(self._L.axb_bvh_is_initialized(self._h))
+
+    def getBounds(self):
+        lo = np.empty(self.ndims, np.float64)
+        hi = np.empty(self.ndims, np.float64)
+        check(self._L.axb_bvh_get_bounds(self._h, lo.ctypes.data, hi.ctypes.data))
+        return lo, hi
+
+    def numLeaves(self):
+        v = C.c_int32()
+        check(self._L.axb_bvh_num_leaves(self._h, C.byref(v)))
+        return v.value
+
+    # ---- queries (spin/BVH.hpp:341-398) ----
+    def _find(self, which, k, nq, extra=()):
+        import_torch = k.device
+        total = C.c_int64()
+        cand = C.c_void_p()
+        if import_torch:
+            import torch
+            dev = torch.device("cuda", self.device)
+            offsets = torch.empty(nq, dtype=torch.int32, device=dev)
+            counts = torch.empty(nq, dtype=torch.int32, device=dev)
+            po, pc, space = offsets.data_ptr(), counts.data_ptr(), MEM_DEVICE
+        else:
+            offsets = np.empty(nq, np.int32)
+            counts = np.empty(nq, np.int32)
+            po, pc, space = offsets.ctypes.data, counts.ctypes.data, MEM_HOST
+        fn = getattr(self._L, "axb_bvh_find_" + which)
+        check(fn(self._h, C.byref(k.desc), *extra, nq, po, pc, space, C.byref(cand), C.byref(total)))
+        t = int(total.value)
+        if import_torch:
+            import torch
+            candidates = torch.empty(t, dtype=torch.int32, device=dev)
+            if t:
+                # device-to-device copy into a tensor torch owns, then release the library buffer
+                _cudart_memcpy_d2d(candidates.data_ptr(), cand.value, 4 * t, self)
+        else:
+            candidates = np.ctypeslib.as_array(C.cast(cand, C.POINTER(C.c_int32)), shape=(max(t, 1),))[:t].copy()
+        check(self._L.axb_bvh_free_candidates(self._h, cand, space))
+        return offsets, counts, candidates
+
+    def findPoints(self, points, numPts=None):
+        k = make_desc(points, self.ndims)
+        return self._find("points", k, k.count if numPts is None else int(numPts))
+
+    def findBoundingBoxes(self, boxes, numBoxes=None):
+        k = make_desc(boxes, 2 * self.ndims)
+        return self._find("boxes", k, k.count if numBoxes is None else int(numBoxes))
+
+    def findRays(self, origins, directions=None, numRays=None, normalized=False):
+        """rays as (origins, directions) AoS pairs or a 2*D-tuple of SoA components.
+        normalized=False applies the primal::Ray constructor's normalisation."""
+        D = self.ndims
+        if directions is None:
+            k = make_desc(origins, 2 * D)
+        elif _is_torch(origins):
+            import torch
+            k = make_desc(torch.cat([origins.reshape(-1, D), directions.reshape(-1, D)], dim=1), 2 * D)
+        else:
+            k = make_desc(np.concatenate([np.asarray(origins, np.float64).reshape(-1, D),
+                                          np.asarray(directions, np.float64).reshape(-1, D)], axis=1), 2 * D)
+        return self._find("rays", k, k.count if numRays is None else int(numRays), extra=(int(bool(normalized)),))
+
+    # ---- traverser / parity views ----
+    def getTraverser(self):
+        t = Traverser()
+        check(self._L.axb_bvh_get_traverser(self._h, C.byref(t)))
+        return t
+
+    def arrays(self):
+        """host copies of the build artefacts in the reference's layout (parity tests)"""
+        n = self.numLeaves()
+        inner, D = n - 1, self.ndims
+        out = dict(mcodes=np.empty(n, np.uint32), leafs=np.empty(n, np.int32),
+                   inner_nodes=np.empty((2 * inner, 2 * D), np.float64), inner_children=np.empty(2 * inner, np.int32))
+        check(self._L.axb_bvh_copy_arrays(self._h, out["mcodes"].ctypes.data, out["leafs"].ctypes.data,
+                                          out["inner_nodes"].ctypes.data, out["inner_children"].ctypes.data))
+        lo, hi = self.getBounds()
+        out["bounds"] = np.concatenate([lo, hi])
+        return out
+
+
+def _cudart_memcpy_d2d(dst, src, nbytes, bvh):
+    import torch
+    bvh.synchronize()
+    # view the library buffer through the CUDA array interface and let torch copy it
+    class _Raw:
+        pass
+    raw = _Raw()
+    raw.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (int(src), False), "version": 3}
+    src_t = torch.as_tensor(raw, device=torch.device("cuda", bvh.device))
+    dst_t_raw = _Raw()
+    dst_t_raw.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (int(dst), False), "version": 3}
+    torch.as_tensor(dst_t_raw, device=torch.device("cuda", bvh.device)).copy_(src_t)
+    torch.cuda.synchronize(bvh.device)

@@ -1,0 +1,958 @@
+// api.cu -- host side of libaxb200: handles, device memory, staging, kernel launches and
+// the extern "C" entry points declared in include/axb200.h.
+//
+// There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA
+// device and fails with AXB_ERR_NO_DEVICE / AXB_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "build.cuh"
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "sd.cuh"
+#include "traverse.cuh"
+
+namespace axb
+{
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+static int fail(int status, const std::string& msg)
+{
+  set_last_error(msg);
+  return status;
+}
+
+//------------------------------------------------------------------------------------------
+// stream-ordered device buffer (grow-only, reused across calls)
+//------------------------------------------------------------------------------------------
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes, cudaStream_t s)
+  {
+    if(bytes <= cap && p) return AXB_OK;
+    if(p) AXB_CUDA_TRY(cudaFreeAsync(p, s));
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes ? bytes : 16;
+    AXB_CUDA_TRY(cudaMallocAsync(&p, want, s));
+    cap = want;
+    return AXB_OK;
+  }
+  void release(cudaStream_t s)
+  {
+    if(p) cudaFreeAsync(p, s);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename U>
+  U* as() const
+  {
+    return reinterpret_cast<U*>(p);
+  }
+};
+
+//------------------------------------------------------------------------------------------
+// per-handle execution context: stream, profiling events, launch counter
+//------------------------------------------------------------------------------------------
+struct Phase
+{
+  std::string name;
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+struct Ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool async = false;
+  bool profiling = false;
+  int64_t launches = 0;
+  std::vector<Phase> phases;           // events of the last call
+  std::map<std::string, double> ms;    // resolved times
+  std::vector<cudaEvent_t> event_pool;
+
+  int init(int dev)
+  {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if(e != cudaSuccess || count <= 0)
+    {
+      cudaGetLastError();
+      return fail(AXB_ERR_NO_DEVICE, "no CUDA device available (libaxb200 has no CPU fallback)");
+    }
+    if(dev < 0 || dev >= count) return fail(AXB_ERR_BAD_ARG, "device ordinal out of range");
+    device = dev;
+    AXB_CUDA_TRY(cudaSetDevice(device));
+    AXB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+    return AXB_OK;
+  }
+  void destroy()
+  {
+    for(auto& ev : event_pool) cudaEventDestroy(ev);
+    event_pool.clear();
+    if(own_stream && stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+  int bind() { AXB_CUDA_TRY(cudaSetDevice(device)); return AXB_OK; }
+  cudaEvent_t new_event()
+  {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    event_pool.push_back(ev);
+    return ev;
+  }
+  void begin_call()
+  {
+    for(auto& ev : event_pool) cudaEventDestroy(ev);
+    event_pool.clear();
+    phases.clear();
+  }
+  int phase_begin(const char* name)
+  {
+    if(!profiling) return -1;
+    Phase ph;
+    ph.name = name;
+    ph.a = new_event();
+    ph.b = new_event();
+    cudaEventRecord(ph.a, stream);
+    phases.push_back(ph);
+    return (int)phases.size() - 1;
+  }
+  void phase_end(int id)
+  {
+    if(id >= 0) cudaEventRecord(phases[id].b, stream);
+  }
+  // resolve event pairs into ms (requires the stream to be idle)
+  void resolve()
+  {
+    if(!profiling) return;
+    cudaStreamSynchronize(stream);
+    for(auto& ph : phases)
+    {
+      float t = 0.f;
+      if(ph.a && ph.b && cudaEventElapsedTime(&t, ph.a, ph.b) == cudaSuccess) ms[ph.name] = t;
+    }
+    cudaGetLastError();
+  }
+  int sync() { AXB_CUDA_TRY(cudaStreamSynchronize(stream)); return AXB_OK; }
+  int finish_call()
+  {
+    if(!async) AXB_TRY(sync());
+    if(profiling) resolve();
+    return AXB_OK;
+  }
+};
+
+struct ScopedPhase
+{
+  Ctx& c;
+  int id;
+  ScopedPhase(Ctx& ctx, const char* name) : c(ctx), id(ctx.phase_begin(name)) { }
+  ~ScopedPhase() { c.phase_end(id); }
+};
+
+#define AXB_LAUNCH(ctx, kernel, grid, block, ...)                    \
+  do                                                                 \
+  {                                                                  \
+    kernel<<<(grid), (block), 0, (ctx).stream>>>(__VA_ARGS__);       \
+    ++(ctx).launches;                                                \
+    AXB_CUDA_TRY(cudaGetLastError());                                \
+  } while(0)
+
+static inline int blocks_for(long long n, int block) { return (int)std::max<long long>(1, (n + block - 1) / block); }
+static inline int capped_grid(long long n, int block, int per_sm = 8)
+{
+  return (int)std::min<long long>(blocks_for(n, block), (long long)kNumSMsB200 * per_sm);
+}
+
+//------------------------------------------------------------------------------------------
+// staging of "Indexable" inputs: host arrays are copied to the device (AoS block or one
+// array per component), device arrays are used in place.
+//------------------------------------------------------------------------------------------
+template <int NC>
+static int stage_desc(Ctx& ctx, const axb_array_desc* in, long long count, size_t elem, DevBuf& stage, Desc<NC>& out)
+{
+  if(!in) return fail(AXB_ERR_BAD_ARG, "null array descriptor");
+  if(in->ncomp != NC) return fail(AXB_ERR_BAD_ARG, "array descriptor has the wrong number of components for this dimension");
+  for(int c = 0; c < NC; ++c)
+    if(count > 0 && in->comp[c] == nullptr) return fail(AXB_ERR_BAD_ARG, "null component pointer in array descriptor");
+  if(count > 0 && in->stride_bytes < (int64_t)elem) return fail(AXB_ERR_BAD_ARG, "array descriptor stride smaller than the element size");
+  if(in->memspace == AXB_MEM_DEVICE || count == 0)
+  {
+    for(int c = 0; c < NC; ++c) out.comp[c] = reinterpret_cast<const char*>(in->comp[c]);
+    out.stride = in->stride_bytes;
+    return AXB_OK;
+  }
+  if(in->memspace != AXB_MEM_HOST) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  const char* base = reinterpret_cast<const char*>(in->comp[0]);
+  bool aos = (in->stride_bytes == (int64_t)(NC * elem));
+  for(int c = 0; c < NC && aos; ++c) aos = (reinterpret_cast<const char*>(in->comp[c]) == base + c * elem);
+  if(aos)
+  {
+    const size_t bytes = (size_t)count * NC * elem;
+    AXB_TRY(stage.reserve(bytes, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(stage.p, base, bytes, cudaMemcpyHostToDevice, ctx.stream));
+    for(int c = 0; c < NC; ++c) out.comp[c] = stage.as<char>() + c * elem;
+    out.stride = (long long)(NC * elem);
+    return AXB_OK;
+  }
+  // component-wise (ZipIndexable SoA or a general strided view): one dense device array each
+  const size_t comp_bytes = (size_t)count * elem;
+  const size_t comp_pitch = (comp_bytes + 255) & ~(size_t)255;
+  AXB_TRY(stage.reserve(comp_pitch * NC, ctx.stream));
+  for(int c = 0; c < NC; ++c)
+  {
+    char* dst = stage.as<char>() + c * comp_pitch;
+    if(in->stride_bytes == (int64_t)elem)
+      AXB_CUDA_TRY(cudaMemcpyAsync(dst, in->comp[c], comp_bytes, cudaMemcpyHostToDevice, ctx.stream));
+    else
+      AXB_CUDA_TRY(cudaMemcpy2DAsync(dst, elem, in->comp[c], (size_t)in->stride_bytes, elem, (size_t)count, cudaMemcpyHostToDevice,
+                                     ctx.stream));
+    out.comp[c] = dst;
+  }
+  out.stride = (long long)elem;
+  return AXB_OK;
+}
+
+}  // namespace axb
+
+using namespace axb;
+
+//==========================================================================================
+// spin::BVH
+//==========================================================================================
+struct axb_bvh
+{
+  Ctx ctx;
+  int ndims = 3;
+  int fp_bytes = 8;
+  double scale = 1.000123;      // DEFAULT_SCALE_FACTOR, spin/BVH.hpp:410
+  double tol = DBL_EPSILON;     // DEFAULT_TOLERANCE, spin/BVH.hpp:411-412
+  bool built = false;
+  int n = 0;       // leaves after padding
+  int n_in = 0;    // boxes supplied by the caller
+  double bounds_lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
+  double bounds_hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+
+  DevBuf nodes, leaf_nodes, leaf_parent, keys_a, keys_b, state, sort_scratch, stage_in;
+  unsigned long long* sorted_keys = nullptr;  // points into keys_a or keys_b
+  DevBuf ref_inner_nodes, ref_children;       // reference-layout view, built lazily
+  bool ref_view_valid = false;
+  DevBuf q_stage, q_counts, q_offsets, q_tiles, q_total;
+
+  void release_all()
+  {
+    cudaStream_t s = ctx.stream;
+    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &ref_inner_nodes,
+                     &ref_children, &q_stage, &q_counts, &q_offsets, &q_tiles, &q_total})
+      b->release(s);
+  }
+};
+
+namespace
+{
+// LSD radix sort of the 64-bit keys on bits [32, 64): 4 onesweep passes.
+int sort_keys(axb_bvh* h, int n, uint32_t* ghist /* 4*256, filled */, uint32_t* tile_counters, uint32_t* lookback)
+{
+  Ctx& ctx = h->ctx;
+  const int tiles = rsort::num_tiles(n);
+  unsigned long long* src = h->keys_a.as<unsigned long long>();
+  unsigned long long* dst = h->keys_b.as<unsigned long long>();
+  for(int p = 0; p < rsort::MAX_PASSES; ++p)
+  {
+    AXB_LAUNCH(ctx, rsort::onesweep_kernel, tiles, rsort::BLOCK, src, dst, (long long)n, 32 + p * rsort::RADIX_BITS,
+               ghist + p * rsort::RADIX, lookback + (size_t)p * tiles * rsort::RADIX, tile_counters + p);
+    std::swap(src, dst);
+  }
+  h->sorted_keys = src;
+  return AXB_OK;
+}
+
+template <int D>
+int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
+{
+  using T = double;
+  Ctx& ctx = h->ctx;
+  AXB_TRY(ctx.bind());
+  ctx.begin_call();
+  const int tot = ctx.phase_begin("build.total");
+  h->built = false;
+  h->ref_view_valid = false;
+  h->n_in = num_boxes;
+  const int n = num_boxes <= 1 ? 2 : num_boxes;  // spin/BVH.hpp:439-464
+  h->n = n;
+  const int inner = n - 1;
+  const T half_scale = static_cast<T>(h->scale * 0.5);
+
+  Desc<2 * D> in;
+  AXB_TRY(stage_desc<2 * D>(ctx, boxes, num_boxes, sizeof(T), h->stage_in, in));
+  if(num_boxes == 0)
+    for(int c = 0; c < 2 * D; ++c) in.comp[c] = nullptr;
+
+  AXB_TRY(h->nodes.reserve(sizeof(Node<T, D>) * (size_t)inner, ctx.stream));
+  AXB_TRY(h->leaf_nodes.reserve(sizeof(int32_t) * (size_t)n, ctx.stream));
+  AXB_TRY(h->leaf_parent.reserve(sizeof(int32_t) * (size_t)n, ctx.stream));
+  AXB_TRY(h->keys_a.reserve(sizeof(unsigned long long) * (size_t)n, ctx.stream));
+  AXB_TRY(h->keys_b.reserve(sizeof(unsigned long long) * (size_t)n, ctx.stream));
+  AXB_TRY(h->state.reserve(sizeof(BuildState<T, D>), ctx.stream));
+  const size_t scratch = rsort::scratch_bytes(n);
+  AXB_TRY(h->sort_scratch.reserve(scratch, ctx.stream));
+  AXB_CUDA_TRY(cudaMemsetAsync(h->sort_scratch.p, 0, scratch, ctx.stream));
+  uint32_t* ghist = h->sort_scratch.as<uint32_t>();
+  uint32_t* tile_counters = ghist + rsort::MAX_PASSES * rsort::RADIX;
+  uint32_t* lookback = tile_counters + 64;
+  auto* st = h->state.as<BuildState<T, D>>();
+
+  {
+    ScopedPhase ph(ctx, "build.bounds");
+    AXB_LAUNCH(ctx, (init_state_kernel<T, D>), 1, 32, st);
+    AXB_LAUNCH(ctx, (bounds_kernel<T, D>), capped_grid(n, 256), 256, in, n, num_boxes, half_scale, st);
+    AXB_LAUNCH(ctx, (finalize_bounds_kernel<T, D>), 1, 32, st);
+  }
+  {
+    ScopedPhase ph(ctx, "build.morton");
+    AXB_LAUNCH(ctx, (morton_kernel<T, D>), capped_grid(n, 256), 256, in, n, num_boxes, half_scale, st,
+               h->keys_a.as<unsigned long long>(), ghist);
+  }
+  {
+    ScopedPhase ph(ctx, "build.sort");
+    AXB_TRY(sort_keys(h, n, ghist, tile_counters, lookback));
+  }
+  {
+    ScopedPhase ph(ctx, "build.tree");
+    AXB_LAUNCH(ctx, (tree_kernel<T, D>), blocks_for(inner, 256), 256, h->sorted_keys, n, h->nodes.as<Node<T, D>>(),
+               h->leaf_parent.as<int32_t>());
+  }
+  {
+    ScopedPhase ph(ctx, "build.refit");
+    AXB_LAUNCH(ctx, (refit_kernel<T, D>), blocks_for(n, 256), 256, in, n, num_boxes, half_scale, h->sorted_keys,
+               h->leaf_parent.as<int32_t>(), h->nodes.as<Node<T, D>>(), h->leaf_nodes.as<int32_t>());
+  }
+  ctx.phase_end(tot);
+  // bounds come back to the host (getBounds() is a host query); this is also the build's sync point
+  BuildState<T, D> hst;
+  AXB_CUDA_TRY(cudaMemcpyAsync(&hst, st, sizeof(hst), cudaMemcpyDeviceToHost, ctx.stream));
+  AXB_TRY(ctx.sync());
+  for(int d = 0; d < 3; ++d)
+  {
+    h->bounds_lo[d] = d < D ? (double)hst.bmin[d] : 0.0;
+    h->bounds_hi[d] = d < D ? (double)hst.bmax[d] : 0.0;
+  }
+  h->built = true;
+  if(ctx.profiling) ctx.resolve();
+  return AXB_BVH_BUILD_OK;
+}
+
+template <int D>
+int ensure_ref_view(axb_bvh* h)
+{
+  using T = double;
+  if(h->ref_view_valid) return AXB_OK;
+  Ctx& ctx = h->ctx;
+  const int inner = h->n - 1;
+  AXB_TRY(h->ref_inner_nodes.reserve(sizeof(Box<T, D>) * 2 * (size_t)inner, ctx.stream));
+  AXB_TRY(h->ref_children.reserve(sizeof(int32_t) * 2 * (size_t)inner, ctx.stream));
+  AXB_LAUNCH(ctx, (export_kernel<T, D>), blocks_for(inner, 256), 256, h->nodes.as<Node<T, D>>(), inner,
+             h->ref_inner_nodes.as<Box<T, D>>(), h->ref_children.as<int32_t>());
+  AXB_TRY(ctx.sync());
+  h->ref_view_valid = true;
+  return AXB_OK;
+}
+
+int exclusive_scan(axb_bvh* h, const int32_t* counts, int nq, int32_t* offsets, long long* d_total)
+{
+  Ctx& ctx = h->ctx;
+  const int tiles = blocks_for(nq, SCAN_TILE);
+  AXB_TRY(h->q_tiles.reserve(sizeof(long long) * (size_t)tiles, ctx.stream));
+  long long* tsum = h->q_tiles.as<long long>();
+  AXB_LAUNCH(ctx, scan_tile_sums_kernel, tiles, SCAN_BLOCK, counts, nq, tsum);
+  AXB_LAUNCH(ctx, scan_spine_kernel, 1, 1024, tsum, tiles, d_total);
+  AXB_LAUNCH(ctx, scan_apply_kernel, tiles, SCAN_BLOCK, counts, nq, tsum, offsets);
+  return AXB_OK;
+}
+
+// LinearBVH::findCandidatesImpl (policy/LinearBVH.hpp:271-402): count -> scan -> allocate -> fill
+template <int D, class Query>
+int find_impl(axb_bvh* h, const axb_array_desc* prims, int flags, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
+              int32_t** candidates, int64_t* total)
+{
+  using T = double;
+  if(!h->built) return fail(AXB_ERR_NOT_BUILT, "BVH query before initialize()");
+  if(nq < 0) return fail(AXB_ERR_BAD_ARG, "negative query count");
+  if(!candidates || !total) return fail(AXB_ERR_BAD_ARG, "null output pointer");
+  if(nq > 0 && (!offsets || !counts)) return fail(AXB_ERR_BAD_ARG, "offsets/counts must hold num_queries entries");
+  if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown output memspace");
+  Ctx& ctx = h->ctx;
+  AXB_TRY(ctx.bind());
+  ctx.begin_call();
+  *candidates = nullptr;
+  *total = 0;
+  if(nq == 0) return AXB_OK;
+  const int tot = ctx.phase_begin("find.total");
+
+  Desc<Query::NCOMP> q;
+  AXB_TRY(stage_desc<Query::NCOMP>(ctx, prims, nq, sizeof(T), h->q_stage, q));
+  int32_t* d_counts = counts;
+  int32_t* d_offsets = offsets;
+  if(out_memspace == AXB_MEM_HOST)
+  {
+    AXB_TRY(h->q_counts.reserve(sizeof(int32_t) * (size_t)nq, ctx.stream));
+    AXB_TRY(h->q_offsets.reserve(sizeof(int32_t) * (size_t)nq, ctx.stream));
+    d_counts = h->q_counts.as<int32_t>();
+    d_offsets = h->q_offsets.as<int32_t>();
+  }
+  AXB_TRY(h->q_total.reserve(sizeof(long long), ctx.stream));
+  long long* d_total = h->q_total.as<long long>();
+  const Node<T, D>* nodes = h->nodes.as<Node<T, D>>();
+  const T tol = (T)h->tol;
+  {
+    ScopedPhase ph(ctx, "find.count");
+    AXB_LAUNCH(ctx, (count_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, q, nq, tol, flags, (const int32_t*)nullptr, d_counts);
+  }
+  {
+    ScopedPhase ph(ctx, "find.scan");
+    AXB_TRY(exclusive_scan(h, d_counts, nq, d_offsets, d_total));
+  }
+  long long htotal = 0;
+  AXB_CUDA_TRY(cudaMemcpyAsync(&htotal, d_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx.stream));
+  AXB_TRY(ctx.sync());
+  if(htotal > 2147483647LL)
+    return fail(AXB_ERR_OVERFLOW, "candidate total " + std::to_string(htotal) + " overflows int32 offsets: split the query batch");
+  int32_t* d_cand = nullptr;
+  AXB_CUDA_TRY(cudaMallocAsync((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+  {
+    ScopedPhase ph(ctx, "find.fill");
+    AXB_LAUNCH(ctx, (fill_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, h->leaf_nodes.as<int32_t>(), q, nq, tol, flags,
+               (const int32_t*)nullptr, d_offsets, d_cand);
+  }
+  ctx.phase_end(tot);
+  if(out_memspace == AXB_MEM_HOST)
+  {
+    int32_t* hc = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1));
+    if(!hc) return fail(AXB_ERR_BAD_ARG, "host allocation of the candidate array failed");
+    AXB_CUDA_TRY(cudaMemcpyAsync(hc, d_cand, sizeof(int32_t) * (size_t)htotal, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(counts, d_counts, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(offsets, d_offsets, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaFreeAsync(d_cand, ctx.stream));
+    AXB_TRY(ctx.sync());
+    *candidates = hc;
+  }
+  else
+  {
+    *candidates = d_cand;
+  }
+  *total = htotal;
+  return ctx.finish_call();
+}
+
+bool valid_bvh(const axb_bvh* b) { return b != nullptr; }
+
+}  // namespace
+
+extern "C" {
+
+const char* axb_version(void) { return AXB_VERSION_STRING; }
+const char* axb_last_error(void) { return g_last_error.c_str(); }
+
+int axb_device_count(void)
+{
+  int c = 0;
+  if(cudaGetDeviceCount(&c) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return c;
+}
+
+const char* axb_status_string(int s)
+{
+  switch(s)
+  {
+  case AXB_OK: return "AXB_OK";
+  case AXB_ERR_BAD_ARG: return "AXB_ERR_BAD_ARG";
+  case AXB_ERR_CUDA: return "AXB_ERR_CUDA";
+  case AXB_ERR_OVERFLOW: return "AXB_ERR_OVERFLOW";
+  case AXB_ERR_NOT_BUILT: return "AXB_ERR_NOT_BUILT";
+  case AXB_ERR_NO_DEVICE: return "AXB_ERR_NO_DEVICE";
+  case AXB_ERR_UNSUPPORTED: return "AXB_ERR_UNSUPPORTED";
+  default: return "AXB_ERR_UNKNOWN";
+  }
+}
+
+int axb_bvh_create(axb_bvh** out, int ndims, int fp_bytes, int device)
+{
+  if(!out) return fail(AXB_ERR_BAD_ARG, "null output handle");
+  *out = nullptr;
+  if(ndims != 2 && ndims != 3) return fail(AXB_ERR_BAD_ARG, "The BVH class may be used only in 2D or 3D.");
+  if(fp_bytes == 4) return fail(AXB_ERR_UNSUPPORTED, "float BVH is not built in this version (double only)");
+  if(fp_bytes != 8) return fail(AXB_ERR_BAD_ARG, "fp_bytes must be 8");
+  axb_bvh* h = new axb_bvh();
+  h->ndims = ndims;
+  h->fp_bytes = fp_bytes;
+  int s = h->ctx.init(device);
+  if(s != AXB_OK)
+  {
+    delete h;
+    return s;
+  }
+  *out = h;
+  return AXB_OK;
+}
+
+int axb_bvh_destroy(axb_bvh* h)
+{
+  if(!h) return AXB_OK;
+  cudaSetDevice(h->ctx.device);
+  h->release_all();
+  cudaStreamSynchronize(h->ctx.stream);
+  h->ctx.destroy();
+  delete h;
+  return AXB_OK;
+}
+
+int axb_bvh_set_stream(axb_bvh* h, void* s)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  AXB_TRY(h->ctx.sync());
+  if(h->ctx.own_stream && h->ctx.stream) cudaStreamDestroy(h->ctx.stream);
+  h->ctx.stream = (cudaStream_t)s;
+  h->ctx.own_stream = false;
+  return AXB_OK;
+}
+int axb_bvh_set_async(axb_bvh* h, int e)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  h->ctx.async = e != 0;
+  return AXB_OK;
+}
+int axb_bvh_synchronize(axb_bvh* h)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  return h->ctx.sync();
+}
+int axb_bvh_set_scale_factor(axb_bvh* h, double s)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  h->scale = s;
+  return AXB_OK;
+}
+int axb_bvh_get_scale_factor(const axb_bvh* h, double* s)
+{
+  if(!valid_bvh(h) || !s) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *s = h->scale;
+  return AXB_OK;
+}
+int axb_bvh_set_tolerance(axb_bvh* h, double t)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  h->tol = t;
+  return AXB_OK;
+}
+int axb_bvh_get_tolerance(const axb_bvh* h, double* t)
+{
+  if(!valid_bvh(h) || !t) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *t = h->tol;
+  return AXB_OK;
+}
+
+int axb_bvh_initialize(axb_bvh* h, const axb_array_desc* boxes, int32_t n)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(n < 0) return fail(AXB_ERR_BAD_ARG, "negative box count");
+  if(n > (1 << 30)) return fail(AXB_ERR_BAD_ARG, "more than 2^30 boxes: int32 node ids would overflow");
+  if(n > 0 && !boxes) return fail(AXB_ERR_BAD_ARG, "null boxes");
+  axb_array_desc empty;
+  memset(&empty, 0, sizeof(empty));
+  empty.ncomp = 2 * h->ndims;
+  empty.stride_bytes = 8;
+  empty.memspace = AXB_MEM_DEVICE;
+  const axb_array_desc* d = (n == 0 && !boxes) ? &empty : boxes;
+  return h->ndims == 2 ? build_impl<2>(h, d, n) : build_impl<3>(h, d, n);
+}
+
+int axb_bvh_is_initialized(const axb_bvh* h) { return (h && h->built) ? 1 : 0; }
+
+int axb_bvh_get_bounds(const axb_bvh* h, double* lo, double* hi)
+{
+  if(!valid_bvh(h) || !lo || !hi) return fail(AXB_ERR_BAD_ARG, "null argument");
+  for(int d = 0; d < h->ndims; ++d)
+  {
+    lo[d] = h->built ? h->bounds_lo[d] : DBL_MAX;   // invalid box when unbuilt, spin/BVH.hpp:303-307
+    hi[d] = h->built ? h->bounds_hi[d] : -DBL_MAX;
+  }
+  return AXB_OK;
+}
+
+int axb_bvh_get_traverser(axb_bvh* h, axb_traverser* out)
+{
+  if(!valid_bvh(h) || !out) return fail(AXB_ERR_BAD_ARG, "null argument");
+  if(!h->built) return fail(AXB_ERR_NOT_BUILT, "getTraverser() before initialize()");
+  AXB_TRY(h->ctx.bind());
+  AXB_TRY(h->ndims == 2 ? ensure_ref_view<2>(h) : ensure_ref_view<3>(h));
+  out->inner_nodes = h->ref_inner_nodes.p;
+  out->inner_node_children = h->ref_children.as<int32_t>();
+  out->leaf_nodes = h->leaf_nodes.as<int32_t>();
+  out->num_leaves = h->n;
+  out->ndims = h->ndims;
+  out->fp_bytes = h->fp_bytes;
+  return AXB_OK;
+}
+
+int axb_bvh_find_points(axb_bvh* h, const axb_array_desc* pts, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
+                        int32_t** candidates, int64_t* total)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  return h->ndims == 2 ? find_impl<2, PointQuery<double, 2>>(h, pts, 0, nq, offsets, counts, out_memspace, candidates, total)
+                       : find_impl<3, PointQuery<double, 3>>(h, pts, 0, nq, offsets, counts, out_memspace, candidates, total);
+}
+
+int axb_bvh_find_boxes(axb_bvh* h, const axb_array_desc* boxes, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
+                       int32_t** candidates, int64_t* total)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  return h->ndims == 2 ? find_impl<2, BoxQuery<double, 2>>(h, boxes, 0, nq, offsets, counts, out_memspace, candidates, total)
+                       : find_impl<3, BoxQuery<double, 3>>(h, boxes, 0, nq, offsets, counts, out_memspace, candidates, total);
+}
+
+int axb_bvh_find_rays(axb_bvh* h, const axb_array_desc* rays, int rays_normalized, int32_t nq, int32_t* offsets, int32_t* counts,
+                      int out_memspace, int32_t** candidates, int64_t* total)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  const int f = rays_normalized ? 1 : 0;
+  return h->ndims == 2 ? find_impl<2, RayQuery<double, 2>>(h, rays, f, nq, offsets, counts, out_memspace, candidates, total)
+                       : find_impl<3, RayQuery<double, 3>>(h, rays, f, nq, offsets, counts, out_memspace, candidates, total);
+}
+
+int axb_bvh_free_candidates(axb_bvh* h, int32_t* candidates, int memspace)
+{
+  if(!candidates) return AXB_OK;
+  if(memspace == AXB_MEM_HOST)
+  {
+    free(candidates);
+    return AXB_OK;
+  }
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  AXB_TRY(h->ctx.bind());
+  AXB_CUDA_TRY(cudaFreeAsync(candidates, h->ctx.stream));
+  return AXB_OK;
+}
+
+int axb_bvh_num_leaves(const axb_bvh* h, int32_t* n)
+{
+  if(!valid_bvh(h) || !n) return fail(AXB_ERR_BAD_ARG, "null argument");
+  if(!h->built) return fail(AXB_ERR_NOT_BUILT, "BVH not initialized");
+  *n = h->n;
+  return AXB_OK;
+}
+
+int axb_bvh_copy_arrays(axb_bvh* h, uint32_t* mcodes, int32_t* leaf_nodes, double* inner_nodes, int32_t* inner_children)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(!h->built) return fail(AXB_ERR_NOT_BUILT, "BVH not initialized");
+  Ctx& ctx = h->ctx;
+  AXB_TRY(ctx.bind());
+  const int n = h->n, inner = n - 1, D = h->ndims;
+  if(mcodes)
+  {
+    DevBuf tmp;
+    AXB_TRY(tmp.reserve(sizeof(uint32_t) * (size_t)n, ctx.stream));
+    AXB_LAUNCH(ctx, extract_mcodes_kernel, blocks_for(n, 256), 256, h->sorted_keys, n, tmp.as<uint32_t>());
+    AXB_CUDA_TRY(cudaMemcpyAsync(mcodes, tmp.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_TRY(ctx.sync());
+    tmp.release(ctx.stream);
+  }
+  if(leaf_nodes)
+    AXB_CUDA_TRY(cudaMemcpyAsync(leaf_nodes, h->leaf_nodes.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx.stream));
+  if(inner_nodes || inner_children)
+  {
+    AXB_TRY(D == 2 ? ensure_ref_view<2>(h) : ensure_ref_view<3>(h));
+    if(inner_nodes)
+      AXB_CUDA_TRY(cudaMemcpyAsync(inner_nodes, h->ref_inner_nodes.p, sizeof(double) * 2 * D * 2 * (size_t)inner, cudaMemcpyDeviceToHost,
+                                   ctx.stream));
+    if(inner_children)
+      AXB_CUDA_TRY(cudaMemcpyAsync(inner_children, h->ref_children.p, sizeof(int32_t) * 2 * (size_t)inner, cudaMemcpyDeviceToHost,
+                                   ctx.stream));
+  }
+  return ctx.sync();
+}
+
+int axb_bvh_set_profiling(axb_bvh* h, int e)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  h->ctx.profiling = e != 0;
+  return AXB_OK;
+}
+int axb_bvh_get_phase_ms(const axb_bvh* h, const char* name, double* ms)
+{
+  if(!valid_bvh(h) || !name || !ms) return fail(AXB_ERR_BAD_ARG, "null argument");
+  auto it = h->ctx.ms.find(name);
+  if(it == h->ctx.ms.end()) return fail(AXB_ERR_BAD_ARG, std::string("no timing recorded for phase ") + name);
+  *ms = it->second;
+  return AXB_OK;
+}
+int axb_bvh_launch_count(const axb_bvh* h, int64_t* n)
+{
+  if(!valid_bvh(h) || !n) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *n = h->ctx.launches;
+  return AXB_OK;
+}
+
+}  // extern "C"
+
+//==========================================================================================
+// quest::SignedDistance
+//==========================================================================================
+struct axb_sd
+{
+  axb_bvh* bvh = nullptr;  // owns; shares nothing else
+  int nv = 3;              // vertices per cell
+  int ncells = 0;
+  int nnodes = 0;
+  int mode = 0;
+  SdParams prm;
+  DevBuf x, y, z, conn, soup, cell_boxes, obounds, q_stage, out_phi, out_cp, out_n, work;
+  int64_t last_leaf_tests = 0, last_inner_visits = 0;
+  Ctx& ctx() { return bvh->ctx; }
+};
+
+extern "C" {
+
+int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, const double* z, int32_t nnodes, const int32_t* conn,
+                  const int32_t* cell_node_offsets, int32_t ncells, int32_t nodes_per_cell, int mesh_memspace, int is_watertight,
+                  int compute_sign)
+{
+  if(!out) return fail(AXB_ERR_BAD_ARG, "null output handle");
+  *out = nullptr;
+  if(cell_node_offsets) return fail(AXB_ERR_UNSUPPORTED, "mixed-shape surface meshes are not built in this version");
+  if(nodes_per_cell != 3 && nodes_per_cell != 4) return fail(AXB_ERR_BAD_ARG, "surface cells must be triangles (3) or quads (4)");
+  if(nnodes < 0 || ncells < 0) return fail(AXB_ERR_BAD_ARG, "negative mesh size");
+  if((nnodes > 0 && (!x || !y || !z)) || (ncells > 0 && !conn)) return fail(AXB_ERR_BAD_ARG, "null mesh array");
+  if(mesh_memspace != AXB_MEM_HOST && mesh_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  axb_sd* s = new axb_sd();
+  int st = axb_bvh_create(&s->bvh, 3, 8, device);
+  if(st != AXB_OK)
+  {
+    delete s;
+    return st;
+  }
+  Ctx& ctx = s->ctx();
+  s->nv = nodes_per_cell;
+  s->ncells = ncells;
+  s->nnodes = nnodes;
+  s->prm.watertight = is_watertight != 0;
+  s->prm.compute_sign = compute_sign != 0;
+  auto body = [&]() -> int {
+    ctx.begin_call();
+    const cudaMemcpyKind kind = mesh_memspace == AXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const size_t nb = sizeof(double) * (size_t)nnodes, cb = sizeof(int32_t) * (size_t)ncells * nodes_per_cell;
+    AXB_TRY(s->x.reserve(nb, ctx.stream));
+    AXB_TRY(s->y.reserve(nb, ctx.stream));
+    AXB_TRY(s->z.reserve(nb, ctx.stream));
+    AXB_TRY(s->conn.reserve(cb, ctx.stream));
+    if(nnodes)
+    {
+      AXB_CUDA_TRY(cudaMemcpyAsync(s->x.p, x, nb, kind, ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(s->y.p, y, nb, kind, ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(s->z.p, z, nb, kind, ctx.stream));
+    }
+    if(ncells) AXB_CUDA_TRY(cudaMemcpyAsync(s->conn.p, conn, cb, kind, ctx.stream));
+    // mesh node bounds (m_boxDomain)
+    AXB_TRY(s->obounds.reserve(sizeof(unsigned long long) * 6, ctx.stream));
+    unsigned long long init[6];
+    for(int d = 0; d < 3; ++d)
+    {
+      init[d] = f64_to_ordered(DBL_MAX);
+      init[3 + d] = f64_to_ordered(-DBL_MAX);
+    }
+    AXB_CUDA_TRY(cudaMemcpyAsync(s->obounds.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+    if(nnodes)
+      AXB_LAUNCH(ctx, node_bounds_kernel, capped_grid(nnodes, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(), nnodes,
+                 s->obounds.as<unsigned long long>());
+    unsigned long long hb[6];
+    AXB_CUDA_TRY(cudaMemcpyAsync(hb, s->obounds.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx.stream));
+    // per-cell AABBs
+    AXB_TRY(s->cell_boxes.reserve(sizeof(Box<double, 3>) * (size_t)std::max(ncells, 1), ctx.stream));
+    if(ncells)
+    {
+      if(s->nv == 3)
+        AXB_LAUNCH(ctx, cell_boxes_kernel<3>, blocks_for(ncells, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
+                   s->conn.as<int32_t>(), ncells, s->cell_boxes.as<Box<double, 3>>());
+      else
+        AXB_LAUNCH(ctx, cell_boxes_kernel<4>, blocks_for(ncells, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
+                   s->conn.as<int32_t>(), ncells, s->cell_boxes.as<Box<double, 3>>());
+    }
+    AXB_TRY(ctx.sync());
+    for(int d = 0; d < 3; ++d)
+    {
+      s->prm.dom_lo[d] = ordered_to_f64(hb[d]);
+      s->prm.dom_hi[d] = ordered_to_f64(hb[3 + d]);
+    }
+    // BVH over the cell boxes with the default scale factor (quest/SignedDistance.hpp:499-500)
+    axb_array_desc bd;
+    memset(&bd, 0, sizeof(bd));
+    for(int c = 0; c < 6; ++c) bd.comp[c] = s->cell_boxes.as<char>() + 8 * c;
+    bd.stride_bytes = 48;
+    bd.ncomp = 6;
+    bd.memspace = AXB_MEM_DEVICE;
+    const bool prof = ctx.profiling;
+    AXB_TRY(axb_bvh_initialize(s->bvh, &bd, ncells));
+    ctx.profiling = prof;
+    // leaf geometry in sorted-leaf order
+    const int nl = s->bvh->n;
+    AXB_TRY(s->soup.reserve(sizeof(double) * 3 * s->nv * (size_t)nl, ctx.stream));
+    if(s->nv == 3)
+      AXB_LAUNCH(ctx, gather_soup_kernel<3>, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
+                 s->conn.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
+    else
+      AXB_LAUNCH(ctx, gather_soup_kernel<4>, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
+                 s->conn.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
+    s->cell_boxes.release(ctx.stream);
+    return ctx.sync();
+  };
+  st = body();
+  if(st != AXB_OK)
+  {
+    axb_sd_destroy(s);
+    return st;
+  }
+  *out = s;
+  return AXB_OK;
+}
+
+int axb_sd_destroy(axb_sd* s)
+{
+  if(!s) return AXB_OK;
+  if(s->bvh)
+  {
+    cudaSetDevice(s->ctx().device);
+    cudaStream_t st = s->ctx().stream;
+    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->soup, &s->cell_boxes, &s->obounds, &s->q_stage, &s->out_phi, &s->out_cp,
+                     &s->out_n, &s->work})
+      b->release(st);
+    axb_bvh_destroy(s->bvh);
+  }
+  delete s;
+  return AXB_OK;
+}
+
+int axb_sd_set_stream(axb_sd* s, void* st) { return s ? axb_bvh_set_stream(s->bvh, st) : fail(AXB_ERR_BAD_ARG, "null handle"); }
+int axb_sd_set_async(axb_sd* s, int e) { return s ? axb_bvh_set_async(s->bvh, e) : fail(AXB_ERR_BAD_ARG, "null handle"); }
+int axb_sd_synchronize(axb_sd* s) { return s ? axb_bvh_synchronize(s->bvh) : fail(AXB_ERR_BAD_ARG, "null handle"); }
+int axb_sd_set_profiling(axb_sd* s, int e) { return s ? axb_bvh_set_profiling(s->bvh, e) : fail(AXB_ERR_BAD_ARG, "null handle"); }
+int axb_sd_get_phase_ms(const axb_sd* s, const char* name, double* ms)
+{
+  return s ? axb_bvh_get_phase_ms(s->bvh, name, ms) : fail(AXB_ERR_BAD_ARG, "null handle");
+}
+int axb_sd_launch_count(const axb_sd* s, int64_t* n) { return s ? axb_bvh_launch_count(s->bvh, n) : fail(AXB_ERR_BAD_ARG, "null handle"); }
+
+int axb_sd_get_bvh(axb_sd* s, axb_bvh** b)
+{
+  if(!s || !b) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *b = s->bvh;
+  return AXB_OK;
+}
+
+int axb_sd_get_mesh_bounds(const axb_sd* s, double* lo, double* hi)
+{
+  if(!s || !lo || !hi) return fail(AXB_ERR_BAD_ARG, "null argument");
+  for(int d = 0; d < 3; ++d)
+  {
+    lo[d] = s->prm.dom_lo[d];
+    hi[d] = s->prm.dom_hi[d];
+  }
+  return AXB_OK;
+}
+
+int axb_sd_set_mode(axb_sd* s, int mode)
+{
+  if(!s) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(mode != 0) return fail(AXB_ERR_UNSUPPORTED, "only mode 0 (reference visiting order) is built in this version");
+  s->mode = mode;
+  return AXB_OK;
+}
+
+int axb_sd_get_work_counters(const axb_sd* s, int64_t* leaf_tests, int64_t* inner_visits)
+{
+  if(!s || !leaf_tests || !inner_visits) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *leaf_tests = s->last_leaf_tests;
+  *inner_visits = s->last_inner_visits;
+  return AXB_OK;
+}
+
+int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts, double* phi, double* cps, double* nrms, int out_memspace)
+{
+  if(!s) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(npts < 0) return fail(AXB_ERR_BAD_ARG, "negative point count");
+  if(npts > 0 && !phi) return fail(AXB_ERR_BAD_ARG, "outSgnDist != nullptr");
+  if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown output memspace");
+  if(!s->bvh->built) return fail(AXB_ERR_NOT_BUILT, "SignedDistance query before setMesh()");
+  Ctx& ctx = s->ctx();
+  AXB_TRY(ctx.bind());
+  ctx.begin_call();
+  if(npts == 0) return AXB_OK;
+  const int tot = ctx.phase_begin("query.total");
+  Desc<3> q;
+  AXB_TRY(stage_desc<3>(ctx, qpts, npts, sizeof(double), s->q_stage, q));
+  double *d_phi = phi, *d_cp = cps, *d_n = nrms;
+  if(out_memspace == AXB_MEM_HOST)
+  {
+    AXB_TRY(s->out_phi.reserve(sizeof(double) * (size_t)npts, ctx.stream));
+    d_phi = s->out_phi.as<double>();
+    if(cps)
+    {
+      AXB_TRY(s->out_cp.reserve(sizeof(double) * 3 * (size_t)npts, ctx.stream));
+      d_cp = s->out_cp.as<double>();
+    }
+    if(nrms)
+    {
+      AXB_TRY(s->out_n.reserve(sizeof(double) * 3 * (size_t)npts, ctx.stream));
+      d_n = s->out_n.as<double>();
+    }
+  }
+  unsigned long long* d_work = nullptr;
+  if(ctx.profiling)
+  {
+    AXB_TRY(s->work.reserve(sizeof(unsigned long long) * 2, ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(s->work.p, 0, sizeof(unsigned long long) * 2, ctx.stream));
+    d_work = s->work.as<unsigned long long>();
+  }
+  const Node<double, 3>* nodes = s->bvh->nodes.as<Node<double, 3>>();
+  {
+    ScopedPhase ph(ctx, "query.kernel");
+    if(s->nv == 3)
+      AXB_LAUNCH(ctx, sd_reference_order_kernel<3>, blocks_for(npts, 128), 128, nodes, s->soup.as<double>(), s->prm, q, npts,
+                 (const int32_t*)nullptr, d_phi, d_cp, d_n, d_work);
+    else
+      AXB_LAUNCH(ctx, sd_reference_order_kernel<4>, blocks_for(npts, 128), 128, nodes, s->soup.as<double>(), s->prm, q, npts,
+                 (const int32_t*)nullptr, d_phi, d_cp, d_n, d_work);
+  }
+  ctx.phase_end(tot);
+  if(out_memspace == AXB_MEM_HOST)
+  {
+    AXB_CUDA_TRY(cudaMemcpyAsync(phi, d_phi, sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
+    if(cps) AXB_CUDA_TRY(cudaMemcpyAsync(cps, d_cp, sizeof(double) * 3 * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
+    if(nrms) AXB_CUDA_TRY(cudaMemcpyAsync(nrms, d_n, sizeof(double) * 3 * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_TRY(ctx.sync());
+  }
+  if(d_work)
+  {
+    unsigned long long hw[2];
+    AXB_CUDA_TRY(cudaMemcpyAsync(hw, d_work, sizeof(hw), cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_TRY(ctx.sync());
+    s->last_leaf_tests = (int64_t)hw[0];
+    s->last_inner_visits = (int64_t)hw[1];
+  }
+  return ctx.finish_call();
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+/* axb200.h -- C ABI of the B200-native spin::BVH / quest::SignedDistance engine.
+ *
+ * Plain C: opaque handles, raw pointers and sizes, int status codes.  No torch / CUDA
+ * types appear in any signature (a stream is passed as void*).  This is the boundary a
+ * host code binds against; include/axom_b200/BVH.hpp and SignedDistance.hpp are the C++
+ * header shims that keep the reference's class / method names on top of it, and
+ * axom_b200/bvh.py is the ctypes mirror the tests use.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/src/axom):
+ *   spin/BVH.hpp:129-419                    class BVH<NDIMS,ExecSpace,FloatType>
+ *   spin/policy/LinearBVH.hpp:57-109        LinearBVHTraverser (device arrays)
+ *   quest/SignedDistance.hpp:147-397        class SignedDistance<NDIMS,ExecSpace>
+ *   quest/interface/signed_distance.hpp:117-319  (process-global C-style API)
+ *
+ * Conventions
+ *   - every function returns AXB_OK (0) or a negative axb_status; nothing throws or exits.
+ *     axb_last_error() returns a thread-local message for the last failure.
+ *   - IndexType is int32_t (reference default, core/Types.hpp:63-65); totals are int64_t.
+ *   - calls are synchronous (results complete on return), like CUDA_EXEC<256>
+ *     (core/execution/internal/cuda_exec.hpp:38-76), unless axb_*_set_async(h,1) was
+ *     called: then work is only enqueued on the handle's stream.
+ *   - "Indexable" inputs (raw AoS pointer or primal::ZipIndexable SoA) are described by an
+ *     axb_array_desc: component c of item i lives at (char*)comp[c] + i*stride_bytes.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     AXB_ERR_NO_DEVICE.
+ */
+#ifndef AXB200_H_
+#define AXB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AXB_VERSION_STRING "0.1.0"
+
+typedef enum axb_status
+{
+  AXB_OK = 0,
+  AXB_ERR_BAD_ARG = -1,     /* null pointer, wrong size, wrong dimension ...               */
+  AXB_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed (see axb_last_error)    */
+  AXB_ERR_OVERFLOW = -3,    /* candidate total does not fit the reference's int32 offsets   */
+  AXB_ERR_NOT_BUILT = -4,   /* query before initialize() / setMesh()                        */
+  AXB_ERR_NO_DEVICE = -5,   /* no CUDA device: there is no CPU fallback                     */
+  AXB_ERR_UNSUPPORTED = -6  /* valid request this build does not implement                  */
+} axb_status;
+
+typedef enum axb_memspace
+{
+  AXB_MEM_HOST = 0,  /* pageable or pinned host memory: staged through the handle's stream */
+  AXB_MEM_DEVICE = 1 /* device (or managed) memory on the handle's device: used in place   */
+} axb_memspace;
+
+/* BVH_BUILD_OK of spin/BVH.hpp:39-43 */
+#define AXB_BVH_BUILD_OK 0
+
+/* Layout descriptor for an Indexable of primitives.
+ *   boxes : ncomp = 2*D  -> min[0..D), max[0..D)          (primal::BoundingBox / ZipBoundingBox)
+ *   points: ncomp = D                                      (primal::Point / ZipPoint)
+ *   rays  : ncomp = 2*D  -> origin[0..D), direction[0..D)  (primal::Ray / ZipRay)
+ * AoS array of T[ncomp]:  comp[c] = base + c*sizeof(T), stride_bytes = ncomp*sizeof(T).
+ * SoA (ZipIndexable):     comp[c] = array c,            stride_bytes = sizeof(T).       */
+typedef struct axb_array_desc
+{
+  const void* comp[6];
+  int64_t stride_bytes;
+  int32_t ncomp;
+  int32_t memspace; /* axb_memspace */
+} axb_array_desc;
+
+/* The three arrays of LinearBVHTraverser (spin/policy/LinearBVH.hpp:105-108), device
+ * pointers in the reference's exact layout (policy/LinearBVH.hpp:226-263):
+ *   inner_nodes[2i+{0,1}]          = AABB of the left/right child of inner node i, as
+ *                                    FloatType min[D],max[D] (primal::BoundingBox layout)
+ *   inner_node_children[2i+{0,1}]  = 2*child (inner) or -(sorted_pos+1) (leaf)
+ *   leaf_nodes[sorted_pos]         = original box id                                      */
+typedef struct axb_traverser
+{
+  const void* inner_nodes;
+  const int32_t* inner_node_children;
+  const int32_t* leaf_nodes;
+  int32_t num_leaves; /* after the N<=1 padding of spin/BVH.hpp:439-464 */
+  int32_t ndims;
+  int32_t fp_bytes;
+} axb_traverser;
+
+typedef struct axb_bvh axb_bvh;
+typedef struct axb_sd axb_sd;
+
+/* ---- library ------------------------------------------------------------------------ */
+const char* axb_version(void);
+const char* axb_last_error(void);
+int axb_device_count(void);
+const char* axb_status_string(int status);
+
+/* ---- spin::BVH ---------------------------------------------------------------------- */
+/* BVH() (spin/BVH.hpp:185).  ndims 2|3, fp_bytes 8 (double; 4 = float is AXB_ERR_UNSUPPORTED
+ * in this build), device = CUDA ordinal.  Defaults: scale 1.000123, tolerance DBL_EPSILON
+ * (spin/BVH.hpp:410-412). */
+int axb_bvh_create(axb_bvh** out, int ndims, int fp_bytes, int device);
+int axb_bvh_destroy(axb_bvh* bvh);
+int axb_bvh_set_stream(axb_bvh* bvh, void* cuda_stream); /* optional: run on the caller's stream */
+int axb_bvh_set_async(axb_bvh* bvh, int enabled);
+int axb_bvh_synchronize(axb_bvh* bvh);
+int axb_bvh_set_scale_factor(axb_bvh* bvh, double scale); /* setScaleFactor :269 */
+int axb_bvh_get_scale_factor(const axb_bvh* bvh, double* scale);
+int axb_bvh_set_tolerance(axb_bvh* bvh, double tol); /* setTolerance :283 */
+int axb_bvh_get_tolerance(const axb_bvh* bvh, double* tol);
+/* initialize(boxes, numItems) :424-477.  Input boxes are copied, never reordered; may be
+ * called again to rebuild.  Returns AXB_BVH_BUILD_OK. */
+int axb_bvh_initialize(axb_bvh* bvh, const axb_array_desc* boxes, int32_t num_boxes);
+int axb_bvh_is_initialized(const axb_bvh* bvh); /* 1 / 0 */
+/* getBounds() :297-308: bounds of the *scaled* boxes; invalid box (DBL_MAX,-DBL_MAX) if unbuilt */
+int axb_bvh_get_bounds(const axb_bvh* bvh, double* lo, double* hi);
+/* getTraverser() :319 */
+int axb_bvh_get_traverser(axb_bvh* bvh, axb_traverser* out);
+
+/* findPoints / findBoundingBoxes / findRays (:341-398).  offsets and counts are caller
+ * arrays of length num_queries in `out_memspace`; *candidates is allocated by the library in
+ * `out_memspace` (release with axb_bvh_free_candidates) and *total receives its length.
+ * Per-query candidate order is the reference's DFS visit order (bvh_traverse.hpp:66-154).
+ * rays_normalized = 0 applies the primal::Ray constructor's normalisation (Ray.hpp:122-127),
+ * 1 uses the directions verbatim (an array of already constructed Ray objects). */
+int axb_bvh_find_points(axb_bvh* bvh, const axb_array_desc* points, int32_t num_queries, int32_t* offsets, int32_t* counts,
+                        int out_memspace, int32_t** candidates, int64_t* total);
+int axb_bvh_find_boxes(axb_bvh* bvh, const axb_array_desc* boxes, int32_t num_queries, int32_t* offsets, int32_t* counts,
+                       int out_memspace, int32_t** candidates, int64_t* total);
+int axb_bvh_find_rays(axb_bvh* bvh, const axb_array_desc* rays, int rays_normalized, int32_t num_queries, int32_t* offsets,
+                      int32_t* counts, int out_memspace, int32_t** candidates, int64_t* total);
+int axb_bvh_free_candidates(axb_bvh* bvh, int32_t* candidates, int memspace);
+
+/* Parity / debugging: copy the build artefacts to HOST buffers (any may be NULL).
+ *   mcodes[n]          sorted 32-bit Morton codes        (RadixTree::m_mcodes)
+ *   leaf_nodes[n]      sort permutation                  (RadixTree::m_leafs)
+ *   inner_nodes[2(n-1)*2D], inner_children[2(n-1)]       (LinearBVH arrays, reference layout) */
+int axb_bvh_num_leaves(const axb_bvh* bvh, int32_t* n);
+int axb_bvh_copy_arrays(axb_bvh* bvh, uint32_t* mcodes, int32_t* leaf_nodes, double* inner_nodes, int32_t* inner_children);
+
+/* Device time (ms, CUDA events on the handle's stream) of the phases of the last call.
+ * names: "build.total" "build.bounds" "build.morton" "build.sort" "build.tree" "build.refit"
+ *        "find.total" "find.count" "find.scan" "find.fill" "find.sortq"                   */
+int axb_bvh_set_profiling(axb_bvh* bvh, int enabled);
+int axb_bvh_get_phase_ms(const axb_bvh* bvh, const char* name, double* ms);
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int axb_bvh_launch_count(const axb_bvh* bvh, int64_t* n);
+
+/* ---- quest::SignedDistance ---------------------------------------------------------- */
+/* SignedDistance(mesh, isWatertight, computeSign) + setMesh (quest/SignedDistance.hpp:410-504).
+ * The mint::Mesh is reduced to what SD_GetUcdMeshData extracts (quest/SignedDistance.cpp:15-45):
+ * SoA node coordinates and int32 connectivity.  nodes_per_cell 3 (triangles) or 4 (quads,
+ * split (0,1,2),(0,2,3)); cell_node_offsets != NULL selects a mixed-shape mesh
+ * (AXB_ERR_UNSUPPORTED in this build).  The mesh is copied and re-laid-out on the device. */
+int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, const double* z, int32_t num_nodes,
+                  const int32_t* cells_to_nodes, const int32_t* cell_node_offsets, int32_t num_cells, int32_t nodes_per_cell,
+                  int mesh_memspace, int is_watertight, int compute_sign);
+int axb_sd_destroy(axb_sd* sd);
+int axb_sd_set_stream(axb_sd* sd, void* cuda_stream);
+int axb_sd_set_async(axb_sd* sd, int enabled);
+int axb_sd_synchronize(axb_sd* sd);
+/* computeDistances(npts, queryPts, outSgnDist, outClosestPts, outNormals) :527-605.
+ * phi[npts]; closest_pts / normals are AoS double[3*npts] or NULL. */
+int axb_sd_compute_distances(axb_sd* sd, const axb_array_desc* query_pts, int32_t npts, double* phi, double* closest_pts,
+                             double* normals, int out_memspace);
+/* getBVHTree() :337 -- borrowed handle, owned by the axb_sd */
+int axb_sd_get_bvh(axb_sd* sd, axb_bvh** bvh);
+/* bounding box of the mesh nodes (m_boxDomain; quest::signed_distance_get_mesh_bounds) */
+int axb_sd_get_mesh_bounds(const axb_sd* sd, double* lo, double* hi);
+/* traversal strategy: 0 = reference visiting order, one thread per query (bit-identical
+ * closest points and normals); 1 = warp-cooperative packets (default; distances and closest
+ * points bit-identical, normals may differ in the last ulp by summation order) */
+int axb_sd_set_mode(axb_sd* sd, int mode);
+int axb_sd_set_profiling(axb_sd* sd, int enabled);
+int axb_sd_get_phase_ms(const axb_sd* sd, const char* name, double* ms); /* "setmesh.total" "query.total" "query.kernel" "query.sortq" */
+int axb_sd_launch_count(const axb_sd* sd, int64_t* n);
+/* work counters of the last query when profiling is enabled (device-side atomics in a
+ * profiling build of the kernel): leaf tests and inner nodes visited */
+int axb_sd_get_work_counters(const axb_sd* sd, int64_t* leaf_tests, int64_t* inner_visits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AXB200_H_ */

@@ -425,8 +425,8 @@ inline bool ray_hits(const double* o, const double* dir, const Box<D>& bb, doubl
       double t1 = (bb.lo[d] - o[d]) * inv;
       double t2 = (bb.hi[d] - o[d]) * inv;
       if(t1 > t2) std::swap(t1, t2);
-      tmin = tmin > t1 ? tmin : t1;  // utilities::max(a,b) = (a > b) ? a : b
-      tmax = tmax < t2 ? tmax : t2;  // utilities::min(a,b) = (a < b) ? a : b
+      tmin = (t1 < tmin) ? tmin : t1;  // utilities::max(x,y) = (y < x) ? x : y  (core/utilities/Utilities.hpp:80-83)
+      tmax = (t2 < tmax) ? t2 : tmax;  // utilities::min(x,y) = (y < x) ? y : x  (:93-96)
       if(tmin > tmax) return false;
     }
   }

@@ -1,0 +1,86 @@
+"""GPU parity tests for quest::SignedDistance through the C ABI, against the CPU oracle.
+Distances and closest points must be bit-identical (tolerance stated by north_star: 1e-12
+relative); signs equal; unit normals to 1e-12 (acos of libm vs CUDA differs in the last ulp)."""
+import numpy as np
+import pytest
+
+from axom_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(oracle, x, y, z, conn, q, npc=3, wt=True, cs=True):
+    from axom_b200 import SignedDistance
+    ref = oracle.SignedDistance(x, y, z, conn, npc, wt, cs)
+    gpu = SignedDistance(x, y, z, conn, npc, wt, cs)
+    rphi, rcp, rn = ref.compute(q, True, True)
+    gphi, gcp, gn = gpu.computeDistances(q, True, True)
+    assert np.array_equal(rphi, gphi), np.abs(rphi - gphi).max()
+    assert np.array_equal(rcp, gcp)
+    assert np.allclose(rn, gn, rtol=0, atol=1e-12)
+    lo, hi = gpu.getMeshBounds()
+    assert lo[0] == x.min() and hi[2] == z.max()
+    return gphi
+
+
+def test_reference_sphere_golden_norms(oracle):
+    # quest/tests/quest_signed_distance.cpp:88-163
+    x, y, z, conn = synth.latlong_sphere(0.5, 25, 25)
+    lo = np.array([x.min(), y.min(), z.min()]) - 2.0
+    hi = np.array([x.max(), y.max(), z.max()]) + 2.0
+    q = synth.uniform_grid_points(lo, hi, 16)
+    phi = _cmp(oracle, x, y, z, conn, q)
+    d = phi - (np.linalg.norm(q, axis=1) - 0.5)
+    assert np.abs(d).max() < 1e-2
+    assert abs(np.abs(d).sum() - 6.7051997372579715) < 1e-3
+    assert abs(np.sqrt(d.sum()) - 2.5894400431865519) < 1e-3
+    assert abs(np.abs(d).max() - 0.00532092) < 1e-3
+
+
+def test_icosphere_grid_and_features(oracle):
+    x, y, z, conn = synth.icosphere(12)
+    _cmp(oracle, x, y, z, conn, synth.uniform_grid_points(-1, 1, 24))
+    rng = np.random.default_rng(5)
+    P = np.stack([x, y, z], 1)
+    qv = P[rng.integers(0, len(x), 500)] * rng.choice([1.0, 0.9, 1.1, 1.0000001], 500)[:, None]
+    e = 0.5 * (P[conn[:, 0]] + P[conn[:, 1]])
+    qe = e[rng.integers(0, len(e), 500)] * rng.choice([1.0, 0.7, 1.3], 500)[:, None]
+    q = np.concatenate([qv, qe])
+    _cmp(oracle, x, y, z, conn, q)
+    _cmp(oracle, x, y, z, conn, q, wt=False)
+    _cmp(oracle, x, y, z, conn, q, cs=False)
+
+
+def test_quads_and_plane(oracle):
+    g = np.linspace(-1, 1, 9)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    xs, ys = X.ravel(), Y.ravel()
+    zs = 0.1 * np.sin(3 * xs) * np.cos(2 * ys)
+    idx = lambda i, j: i * 9 + j
+    quads = np.array([[idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)] for i in range(8) for j in range(8)], np.int32)
+    _cmp(oracle, xs, ys, zs, quads, synth.uniform_grid_points(-1.5, 1.5, 12), npc=4, wt=False)
+    # 4-triangle z=0 plane, non-watertight: phi == z exactly (quest_signed_distance_interface.cpp:186-237)
+    px = np.array([-5.0, 5.0, 5.0, -5.0, 0.0])
+    py = np.array([-5.0, -5.0, 5.0, 5.0, 0.0])
+    pz = np.zeros(5)
+    tris = np.array([[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]], np.int32)
+    q = synth.uniform_grid_points(-4, 4, 16)
+    phi = _cmp(oracle, px, py, pz, tris, q, wt=False)
+    assert np.array_equal(phi, q[:, 2])
+
+
+def test_medium_icosphere_device_queries(oracle):
+    import torch
+    from axom_b200 import SignedDistance
+    x, y, z, conn = synth.icosphere(40)  # 32 000 triangles
+    q = synth.uniform_grid_points(-1, 1, 20)
+    ref = oracle.SignedDistance(x, y, z, conn).compute(q, True, False, nthreads=0)
+    gpu = SignedDistance(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(z).cuda(),
+                         torch.from_numpy(conn).cuda())
+    qd = torch.from_numpy(q).cuda()
+    phi, cp, _ = gpu.computeDistances(qd, True, False)
+    assert np.array_equal(ref[0], phi.cpu().numpy())
+    assert np.array_equal(ref[1], cp.cpu().numpy())
+    # SoA (ZipIndexable) queries give the same answer
+    phi2, _, _ = gpu.computeDistances(tuple(qd[:, c].contiguous() for c in range(3)))
+    assert torch.equal(phi, phi2)
