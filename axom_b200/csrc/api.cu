@@ -75,9 +75,14 @@ struct Ctx
   bool async = false;
   bool profiling = false;
   int64_t launches = 0;
-  std::vector<Phase> phases;           // events of the last call
-  std::map<std::string, double> ms;    // resolved times
-  std::vector<cudaEvent_t> event_pool;
+  std::vector<Phase> phases;  // recorded, not yet resolved (events pending)
+  struct Acc
+  {
+    double sum = 0.0;
+    long long calls = 0;
+    double last = 0.0;
+  };
+  std::map<std::string, Acc> acc;  // resolved times since profiling was (re-)enabled
 
   int init(int dev)
   {
@@ -95,34 +100,36 @@ struct Ctx
     own_stream = true;
     return AXB_OK;
   }
+  void drop_phases()
+  {
+    for(auto& ph : phases)
+    {
+      if(ph.a) cudaEventDestroy(ph.a);
+      if(ph.b) cudaEventDestroy(ph.b);
+    }
+    phases.clear();
+  }
   void destroy()
   {
-    for(auto& ev : event_pool) cudaEventDestroy(ev);
-    event_pool.clear();
+    drop_phases();
     if(own_stream && stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
   int bind() { AXB_CUDA_TRY(cudaSetDevice(device)); return AXB_OK; }
-  cudaEvent_t new_event()
+  void set_profiling(bool on)
   {
-    cudaEvent_t ev;
-    cudaEventCreate(&ev);
-    event_pool.push_back(ev);
-    return ev;
+    drop_phases();
+    acc.clear();
+    profiling = on;
   }
-  void begin_call()
-  {
-    for(auto& ev : event_pool) cudaEventDestroy(ev);
-    event_pool.clear();
-    phases.clear();
-  }
+  void begin_call() { }
   int phase_begin(const char* name)
   {
     if(!profiling) return -1;
     Phase ph;
     ph.name = name;
-    ph.a = new_event();
-    ph.b = new_event();
+    cudaEventCreate(&ph.a);
+    cudaEventCreate(&ph.b);
     cudaEventRecord(ph.a, stream);
     phases.push_back(ph);
     return (int)phases.size() - 1;
@@ -131,23 +138,33 @@ struct Ctx
   {
     if(id >= 0) cudaEventRecord(phases[id].b, stream);
   }
-  // resolve event pairs into ms (requires the stream to be idle)
+  // turn pending event pairs into milliseconds (synchronises the stream)
   void resolve()
   {
-    if(!profiling) return;
+    if(phases.empty()) return;
     cudaStreamSynchronize(stream);
     for(auto& ph : phases)
     {
       float t = 0.f;
-      if(ph.a && ph.b && cudaEventElapsedTime(&t, ph.a, ph.b) == cudaSuccess) ms[ph.name] = t;
+      if(ph.a && ph.b && cudaEventElapsedTime(&t, ph.a, ph.b) == cudaSuccess)
+      {
+        Acc& a = acc[ph.name];
+        a.sum += t;
+        a.calls += 1;
+        a.last = t;
+      }
     }
     cudaGetLastError();
+    drop_phases();
   }
   int sync() { AXB_CUDA_TRY(cudaStreamSynchronize(stream)); return AXB_OK; }
   int finish_call()
   {
-    if(!async) AXB_TRY(sync());
-    if(profiling) resolve();
+    if(!async)
+    {
+      AXB_TRY(sync());
+      if(profiling) resolve();
+    }
     return AXB_OK;
   }
 };
@@ -348,7 +365,7 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
     h->bounds_hi[d] = d < D ? (double)hst.bmax[d] : 0.0;
   }
   h->built = true;
-  if(ctx.profiling) ctx.resolve();
+  if(ctx.profiling && !ctx.async) ctx.resolve();
   return AXB_BVH_BUILD_OK;
 }
 
@@ -689,15 +706,18 @@ int axb_bvh_copy_arrays(axb_bvh* h, uint32_t* mcodes, int32_t* leaf_nodes, doubl
 int axb_bvh_set_profiling(axb_bvh* h, int e)
 {
   if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
-  h->ctx.profiling = e != 0;
+  h->ctx.set_profiling(e != 0);
   return AXB_OK;
 }
-int axb_bvh_get_phase_ms(const axb_bvh* h, const char* name, double* ms)
+int axb_bvh_get_phase_ms(const axb_bvh* hc, const char* name, double* ms)
 {
+  axb_bvh* h = const_cast<axb_bvh*>(hc);
   if(!valid_bvh(h) || !name || !ms) return fail(AXB_ERR_BAD_ARG, "null argument");
-  auto it = h->ctx.ms.find(name);
-  if(it == h->ctx.ms.end()) return fail(AXB_ERR_BAD_ARG, std::string("no timing recorded for phase ") + name);
-  *ms = it->second;
+  h->ctx.resolve();
+  auto it = h->ctx.acc.find(name);
+  if(it == h->ctx.acc.end() || it->second.calls == 0)
+    return fail(AXB_ERR_BAD_ARG, std::string("no timing recorded for phase ") + name);
+  *ms = it->second.sum / (double)it->second.calls;  // mean over the calls since profiling was enabled
   return AXB_OK;
 }
 int axb_bvh_launch_count(const axb_bvh* h, int64_t* n)
@@ -719,6 +739,7 @@ struct axb_sd
   int ncells = 0;
   int nnodes = 0;
   int mode = 0;
+  bool count_work = false;
   SdParams prm;
   DevBuf x, y, z, conn, soup, cell_boxes, obounds, q_stage, out_phi, out_cp, out_n, work;
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
@@ -804,9 +825,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
     bd.stride_bytes = 48;
     bd.ncomp = 6;
     bd.memspace = AXB_MEM_DEVICE;
-    const bool prof = ctx.profiling;
     AXB_TRY(axb_bvh_initialize(s->bvh, &bd, ncells));
-    ctx.profiling = prof;
     // leaf geometry in sorted-leaf order
     const int nl = s->bvh->n;
     AXB_TRY(s->soup.reserve(sizeof(double) * 3 * s->nv * (size_t)nl, ctx.stream));
@@ -848,7 +867,12 @@ int axb_sd_destroy(axb_sd* s)
 int axb_sd_set_stream(axb_sd* s, void* st) { return s ? axb_bvh_set_stream(s->bvh, st) : fail(AXB_ERR_BAD_ARG, "null handle"); }
 int axb_sd_set_async(axb_sd* s, int e) { return s ? axb_bvh_set_async(s->bvh, e) : fail(AXB_ERR_BAD_ARG, "null handle"); }
 int axb_sd_synchronize(axb_sd* s) { return s ? axb_bvh_synchronize(s->bvh) : fail(AXB_ERR_BAD_ARG, "null handle"); }
-int axb_sd_set_profiling(axb_sd* s, int e) { return s ? axb_bvh_set_profiling(s->bvh, e) : fail(AXB_ERR_BAD_ARG, "null handle"); }
+int axb_sd_set_profiling(axb_sd* s, int e)
+{
+  if(!s) return fail(AXB_ERR_BAD_ARG, "null handle");
+  s->count_work = (e >= 2);  // level 2 also counts leaf tests / inner visits (adds a sync per query call)
+  return axb_bvh_set_profiling(s->bvh, e);
+}
 int axb_sd_get_phase_ms(const axb_sd* s, const char* name, double* ms)
 {
   return s ? axb_bvh_get_phase_ms(s->bvh, name, ms) : fail(AXB_ERR_BAD_ARG, "null handle");
@@ -920,7 +944,7 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
     }
   }
   unsigned long long* d_work = nullptr;
-  if(ctx.profiling)
+  if(s->count_work)
   {
     AXB_TRY(s->work.reserve(sizeof(unsigned long long) * 2, ctx.stream));
     AXB_CUDA_TRY(cudaMemsetAsync(s->work.p, 0, sizeof(unsigned long long) * 2, ctx.stream));

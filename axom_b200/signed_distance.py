@@ -63,7 +63,7 @@ class SignedDistance:
         check(self._L.axb_sd_synchronize(self._h))
 
     def setProfiling(self, e):
-        check(self._L.axb_sd_set_profiling(self._h, int(bool(e))))
+        check(self._L.axb_sd_set_profiling(self._h, int(e)))
 
     def phase_ms(self, name):
         v = C.c_double()

@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native spin::BVH / quest::SignedDistance path.
+
+Workload (BASELINE.json configs[1], "C2"): quest::SignedDistance on a synthetic 2M-triangle
+icosphere (geodesic frequency 316 -> 1 997 120 triangles, radius 0.5, watertight, signs on)
+evaluated on the 256^3 uniform grid spanning [-1,1]^3.  With N GPUs the grid is sharded by
+contiguous z-slabs (one process per GPU, surface BVH replicated and built per GPU, no data-path
+collective); total work is fixed, so scaling is "strong".
+
+A "step" is one computeDistances() pass over the rank's shard.
+  value : whole-job points/s with queries and results resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the C ABI with HOST buffers (pinned), H2D and D2H inside the timed region
+  roofline     : the dominant kernel (the distance kernel) against the measured HBM peak
+  cpu_baseline : the reference's CPU path (oracle/_ref if present, else the oracle port) on the
+                 box's host cores, on a bounded sample of the same workload
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SignedDistance query points/s (2M-triangle icosphere, 256^3 grid); BVH build ms reported beside it"
+UNIT = "points/s"
+FREQ = 316
+GRID = 256
+WORKLOAD = "C2: quest::SignedDistance, icosphere freq=%d (%d triangles), %d^3 grid on [-1,1]^3" % (FREQ, 20 * FREQ * FREQ, GRID)
+
+
+def grid_axis():
+    lo, hi, n = -1.0, 1.0, GRID
+    return lo + np.arange(n, dtype=np.float64) * ((hi - lo) / (n - 1))
+
+
+def sublattice(step):
+    """query points of the sub-lattice i,j,k = 0 (mod step): bit-identical coordinates to the full grid"""
+    ax = grid_axis()[::step]
+    zz, yy, xx = np.meshgrid(ax, ax, ax, indexing="ij")
+    return np.ascontiguousarray(np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(x, y, z, conn, step, repeats=1, warm=0):
+    """reference CPU path on all host cores over the sub-lattice `step`; returns (points/s, info)"""
+    from oracle import oracle as O
+    kind = "reference" if O.have_reference() else "port"
+    sd = O.SignedDistance(x, y, z, conn, 3, True, True, kind=kind)
+    q = sublattice(step)
+    cores = O.max_threads(kind)
+    for _ in range(warm):
+        sd.compute(q, nthreads=0)
+    ts = []
+    phi = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        phi, _, _ = sd.compute(q, nthreads=0)
+        ts.append(time.perf_counter() - t)
+    return len(q) / (sum(ts) / len(ts)), dict(kind=kind, cores=cores, npts=len(q), seconds=ts, phi=phi, q=q)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from axom_b200 import synth
+    x, y, z, conn = synth.icosphere(FREQ)
+    step = 4  # 64^3 sub-lattice per step: ~1-3 s of CPU work on 16 cores
+    rate, info = cpu_reference_rate(x, y, z, conn, step, repeats=args.steps, warm=args.warmup)
+    ms = 1e3 * sum(info["seconds"]) / len(info["seconds"])
+    sample = "%d^3 sub-lattice (i,j,k = 0 mod %d) of the %d^3 grid per step, OpenMP over queries on %d host threads" % (
+        GRID // step, step, GRID, info["cores"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from axom_b200 import SignedDistance, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- surface + BVH (replicated per GPU) ----
+    x, y, z, conn = synth.icosphere(FREQ)
+    ntri = len(conn)
+    t0 = time.perf_counter()
+    sd = SignedDistance(x, y, z, conn, 3, True, True, device=local)
+    setmesh_wall_ms = (time.perf_counter() - t0) * 1e3
+    bvh = sd.getBVHTree()
+    # BVH build time (device): rebuild from the device-resident cell boxes a few times
+    boxes_d = torch.from_numpy(synth.mesh_cell_boxes(x, y, z, conn)).to(dev)
+    from axom_b200 import BVH
+    tb = BVH(3, device=local)
+    tb.initialize(boxes_d)
+    tb.setProfiling(True)
+    for _ in range(5):
+        tb.initialize(boxes_d)
+    build_ms = tb.phase_ms("build.total")
+    build_phases = {k: tb.phase_ms("build." + k) for k in ("bounds", "morton", "sort", "tree", "refit")}
+    del tb, boxes_d
+
+    # ---- this rank's z-slab of the 256^3 grid, generated on the device ----
+    ax = torch.from_numpy(grid_axis()).to(dev)
+    k0, k1 = (GRID * rank) // world, (GRID * (rank + 1)) // world
+    zz, yy, xx = torch.meshgrid(ax[k0:k1], ax, ax, indexing="ij")
+    q_d = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=1).contiguous()
+    del zz, yy, xx
+    nq_local = q_d.shape[0]
+    nq_total = GRID ** 3
+    phi_d = torch.empty(nq_local, dtype=torch.float64, device=dev)
+
+    stream = torch.cuda.current_stream()
+    sd.setStream(stream.cuda_stream)
+
+    # ---- value: device-resident, K steps back to back, CUDA events on the launching stream ----
+    sd.setAsync(True)
+    for _ in range(args.warmup):
+        sd.computeDistances(q_d, out=phi_d)
+    sd.setProfiling(1)
+    launches0 = sd.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        sd.computeDistances(q_d, out=phi_d)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = sd.launch_count() - launches0
+    kernel_ms = sd.phase_ms("query.kernel")  # mean over the K timed steps (events around the kernel)
+    sd.setProfiling(0)
+    sd.setAsync(False)
+    value = nq_total / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI (H2D of the queries + D2H of phi inside the timed region) ----
+    q_h = torch.empty((nq_local, 3), dtype=torch.float64, pin_memory=True)
+    q_h.copy_(q_d)
+    phi_h = torch.empty(nq_local, dtype=torch.float64, pin_memory=True)
+    qn, pn = q_h.numpy(), phi_h.numpy()
+    e2e_steps = max(1, min(args.steps, 5))
+    sd.computeDistances(qn, out=pn)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sd.computeDistances(qn, out=pn)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    e2e_value = nq_total / (e2e_ms * 1e-3)
+    same = bool(np.array_equal(pn, phi_d.cpu().numpy()))
+
+    # ---- work counters (profiling level 2; outside every timed region) ----
+    sd.setProfiling(2)
+    sd.computeDistances(q_d, out=phi_d)
+    leaf_tests, inner_visits = sd.work_counters()
+    sd.setProfiling(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    # algorithmic bytes of one distance-kernel launch: 24 B in + 8 B out per query,
+    # plus the node array and the leaf geometry once
+    alg_bytes = nq_local * 32 + 128 * (ntri - 1) + 72 * ntri
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": None, "kernel": "signed-distance query kernel", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "note": "latency/FP64-pipe bound traversal: see fp64 for the arithmetic side"}
+    flops = 80.0 * leaf_tests + 50.0 * inner_visits  # SURVEY.md 8(d) convention
+    fp64 = {"leaf_tests_per_query": leaf_tests / nq_local, "inner_visits_per_query": inner_visits / nq_local,
+            "gflops_survey_convention": flops / (kernel_ms * 1e-3) / 1e9}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample, checked against the GPU result ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        step = 2 if args.cpu_sample == "large" else 4
+        rate, info = cpu_reference_rate(x, y, z, conn, step)
+        sub = phi_d.reshape(GRID, GRID, GRID)[::step, ::step, ::step].reshape(-1).cpu().numpy()
+        cpu = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+               "sample": "%d^3 sub-lattice (i,j,k = 0 mod %d) of the %d^3 grid, %d points, OpenMP over queries, %.1f s" % (
+                   GRID // step, step, GRID, info["npts"], info["seconds"][0]),
+               "matches_gpu_bit_exact": bool(np.array_equal(sub, info["phi"]))}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "queries_total": nq_total, "queries_per_gpu": nq_local, "sharding": "z-slabs, BVH replicated",
+                   "l2_policy": "inputs larger than L2 (403 MB of queries per pass)", "mode": "reference-order traversal"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq_local * 24, "d2h_bytes_per_step": nq_local * 8,
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "fp64": fp64,
+        "cpu_baseline": cpu,
+        "build_ms": build_ms, "build_phases_ms": build_phases, "setmesh_wall_ms": setmesh_wall_ms,
+        "build_roofline": {"bound": "hbm", "achieved": 156.0 * ntri / (build_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": 156.0 * ntri / (build_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_box": 156},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", default="small", choices=["small", "large"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

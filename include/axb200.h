@@ -137,7 +137,8 @@ int axb_bvh_free_candidates(axb_bvh* bvh, int32_t* candidates, int memspace);
 int axb_bvh_num_leaves(const axb_bvh* bvh, int32_t* n);
 int axb_bvh_copy_arrays(axb_bvh* bvh, uint32_t* mcodes, int32_t* leaf_nodes, double* inner_nodes, int32_t* inner_children);
 
-/* Device time (ms, CUDA events on the handle's stream) of the phases of the last call.
+/* Device time (ms, CUDA events on the handle's stream) of the phases of the calls made since
+ * profiling was (re-)enabled: the MEAN over those calls.  Enabling profiling resets the record.
  * names: "build.total" "build.bounds" "build.morton" "build.sort" "build.tree" "build.refit"
  *        "find.total" "find.count" "find.scan" "find.fill" "find.sortq"                   */
 int axb_bvh_set_profiling(axb_bvh* bvh, int enabled);
@@ -170,7 +171,7 @@ int axb_sd_get_mesh_bounds(const axb_sd* sd, double* lo, double* hi);
  * closest points and normals); 1 = warp-cooperative packets (default; distances and closest
  * points bit-identical, normals may differ in the last ulp by summation order) */
 int axb_sd_set_mode(axb_sd* sd, int mode);
-int axb_sd_set_profiling(axb_sd* sd, int enabled);
+int axb_sd_set_profiling(axb_sd* sd, int level); /* 0 off, 1 phase timers, 2 + work counters (adds a sync per call) */
 int axb_sd_get_phase_ms(const axb_sd* sd, const char* name, double* ms); /* "setmesh.total" "query.total" "query.kernel" "query.sortq" */
 int axb_sd_launch_count(const axb_sd* sd, int64_t* n);
 /* work counters of the last query when profiling is enabled (device-side atomics in a

@@ -1,0 +1,53 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in this directory from the REAL reference (LLNL/axom v0.11.0,
+SEQ_EXEC) compiled by oracle/build_ref.py.  Run where /root/reference exists:
+
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+
+The fixtures hold seeded inputs and the reference's outputs; tests/test_oracle_golden.py pins the
+oracle port (oracle/axb_oracle.cpp) to them, and the GPU tests compare against the same files."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from axom_b200 import synth  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def bvh_case(name, n, ndims, seed):
+    boxes = synth.triangle_aabbs(n, seed=seed, ndims=ndims)
+    boxes[3] = boxes[4]  # tied Morton codes
+    b = O.Bvh(boxes, ndims=ndims, kind="reference")
+    A = b.arrays()
+    pts = synth.random_points(400, seed=seed + 1, ndims=ndims)
+    qb = synth.triangle_aabbs(300, seed=seed + 2, ndims=ndims)
+    ro, rd = synth.random_rays(200, seed=seed + 3, lo=-0.5, hi=1.5, ndims=ndims)
+    p = b.find_points(pts)
+    x = b.find_boxes(qb)
+    r = b.find_rays(ro, rd * 1.3, True)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), boxes=boxes, ndims=ndims, pts=pts, qboxes=qb, ray_o=ro, ray_d=rd * 1.3,
+                        p_off=p[0], p_cnt=p[1], p_cand=p[2], b_off=x[0], b_cnt=x[1], b_cand=x[2], r_off=r[0], r_cnt=r[1],
+                        r_cand=r[2], **{"a_" + k: v for k, v in A.items()})
+
+
+def sd_case(name, freq, grid):
+    x, y, z, conn = synth.icosphere(freq)
+    rng = np.random.default_rng(11)
+    P = np.stack([x, y, z], 1)
+    qv = P[rng.integers(0, len(x), 60)] * rng.choice([1.0, 0.9, 1.1], 60)[:, None]
+    e = 0.5 * (P[conn[:, 0]] + P[conn[:, 1]])
+    qe = e[rng.integers(0, len(e), 60)] * rng.choice([1.0, 0.7, 1.3], 60)[:, None]
+    q = np.concatenate([synth.uniform_grid_points(-1, 1, grid), qv, qe])
+    phi, cp, nrm = O.SignedDistance(x, y, z, conn, kind="reference").compute(q, True, True)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, y=y, z=z, conn=conn, q=q, phi=phi, cp=cp, nrm=nrm)
+
+
+if __name__ == "__main__":
+    assert O.have_reference(), "build the reference first: python oracle/build_ref.py"
+    bvh_case("bvh3d_n600", 600, 3, 41)
+    bvh_case("bvh2d_n400", 400, 2, 43)
+    sd_case("sd_icosphere5", 5, 9)
+    print("golden fixtures written to", HERE)

@@ -55,7 +55,7 @@ def run_sd(freq, grid):
     rphi, rcp, rn = ref.compute(q, True, True, nthreads=0)
     tc = time.time() - t
     g = SignedDistance(x, y, z, conn)
-    g.setProfiling(True)
+    g.setProfiling(2)
     t = time.time()
     gphi, gcp, gn = g.computeDistances(q, True, True)
     tg = time.time() - t

@@ -107,3 +107,65 @@ def test_query_before_build_fails():
     with pytest.raises(AxbError) as e:
         b.findPoints(np.zeros((1, 3)))
     assert e.value.status == AXB_ERR_NOT_BUILT
+
+
+class _Adapter:
+    """gives axom_b200.BVH the oracle.Bvh query interface so tests/kats.py runs on the GPU path"""
+
+    def __init__(self, boxes, ndims, scale):
+        self.b = _gpu_bvh(boxes, ndims, scale)
+
+    def find_points(self, p):
+        return self.b.findPoints(p)
+
+    def find_boxes(self, q):
+        return self.b.findBoundingBoxes(q)
+
+    def find_rays(self, o, d, normalize=True):
+        return self.b.findRays(o, d, normalized=not normalize)
+
+
+def test_reference_kats_on_gpu():
+    import kats
+    b3 = kats.unit_cells(3, 3)
+    g = _Adapter(b3, 3, 1.0)
+    A = g.b.arrays()
+    assert A["mcodes"].tolist() == kats.KAT_MCODES and A["leafs"].tolist() == kats.KAT_LEAFS
+    l, r = kats.children_to_lr(A["inner_children"], 27)
+    assert l.tolist() == kats.KAT_LCHILD and r.tolist() == kats.KAT_RCHILD
+    kats.check_boxes_3d(g)
+    kats.check_rays_3d(g)
+    kats.check_points(g, b3, 3)
+    b2 = kats.unit_cells(3, 2)
+    g2 = _Adapter(b2, 2, 1.0)
+    kats.check_boxes_2d(g2)
+    kats.check_rays_2d(g2)
+    kats.check_points(g2, b2, 2)
+    lo, hi = _gpu_bvh(b3, 3).getBounds()  # default scale 1.000123 inflates the bounds
+    assert lo[0] == -6.1500000000047628e-05 and hi[0] == 3.0000615000000002
+
+
+@pytest.mark.parametrize("name", ["bvh3d_n600", "bvh2d_n400"])
+def test_golden_fixtures_on_gpu(name):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    nd = int(g["ndims"])
+    b = _gpu_bvh(g["boxes"], nd)
+    A = b.arrays()
+    for k in ("mcodes", "leafs", "inner_children", "inner_nodes", "bounds"):
+        assert np.array_equal(A[k], g["a_" + k]), k
+    assert _same(b.findPoints(g["pts"]), (g["p_off"], g["p_cnt"], g["p_cand"]))
+    assert _same(b.findBoundingBoxes(g["qboxes"]), (g["b_off"], g["b_cnt"], g["b_cand"]))
+    assert _same(b.findRays(g["ray_o"], g["ray_d"]), (g["r_off"], g["r_cnt"], g["r_cand"]))
+
+
+def test_rebuild_and_traverser_view():
+    import torch
+    from axom_b200 import BVH
+    b = BVH(3)
+    b.initialize(synth.triangle_aabbs(100, seed=1))
+    boxes = synth.triangle_aabbs(7000, seed=2)
+    b.initialize(boxes)  # initialize() may be called again (spin/BVH.hpp:437)
+    t = b.getTraverser()
+    assert t.num_leaves == 7000 and t.ndims == 3 and t.fp_bytes == 8
+    assert t.inner_nodes and t.inner_node_children and t.leaf_nodes

