@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "sd.cuh"
+#include "sd_fast.cuh"
 #include "traverse.cuh"
 
 namespace axb
@@ -260,7 +261,7 @@ struct axb_bvh
   double bounds_lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
   double bounds_hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
 
-  DevBuf nodes, leaf_nodes, leaf_parent, keys_a, keys_b, state, sort_scratch, stage_in;
+  DevBuf nodes, leaf_nodes, leaf_parent, node_range, keys_a, keys_b, state, sort_scratch, stage_in;
   unsigned long long* sorted_keys = nullptr;  // points into keys_a or keys_b
   DevBuf ref_inner_nodes, ref_children;       // reference-layout view, built lazily
   bool ref_view_valid = false;
@@ -269,7 +270,7 @@ struct axb_bvh
   void release_all()
   {
     cudaStream_t s = ctx.stream;
-    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &ref_inner_nodes,
+    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &node_range, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &ref_inner_nodes,
                      &ref_children, &q_stage, &q_counts, &q_offsets, &q_tiles, &q_total})
       b->release(s);
   }
@@ -278,20 +279,24 @@ struct axb_bvh
 namespace
 {
 // LSD radix sort of the 64-bit keys on bits [32, 64): 4 onesweep passes.
-int sort_keys(axb_bvh* h, int n, uint32_t* ghist /* 4*256, filled */, uint32_t* tile_counters, uint32_t* lookback)
+int sort_keys_generic(Ctx& ctx, unsigned long long* src, unsigned long long* dst, int n, uint32_t* ghist /* 4*256, filled */,
+                      uint32_t* tile_counters, uint32_t* lookback, unsigned long long** sorted)
 {
-  Ctx& ctx = h->ctx;
   const int tiles = rsort::num_tiles(n);
-  unsigned long long* src = h->keys_a.as<unsigned long long>();
-  unsigned long long* dst = h->keys_b.as<unsigned long long>();
   for(int p = 0; p < rsort::MAX_PASSES; ++p)
   {
     AXB_LAUNCH(ctx, rsort::onesweep_kernel, tiles, rsort::BLOCK, src, dst, (long long)n, 32 + p * rsort::RADIX_BITS,
                ghist + p * rsort::RADIX, lookback + (size_t)p * tiles * rsort::RADIX, tile_counters + p);
     std::swap(src, dst);
   }
-  h->sorted_keys = src;
+  *sorted = src;
   return AXB_OK;
+}
+
+int sort_keys(axb_bvh* h, int n, uint32_t* ghist, uint32_t* tile_counters, uint32_t* lookback)
+{
+  return sort_keys_generic(h->ctx, h->keys_a.as<unsigned long long>(), h->keys_b.as<unsigned long long>(), n, ghist, tile_counters,
+                           lookback, &h->sorted_keys);
 }
 
 template <int D>
@@ -318,6 +323,7 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
   AXB_TRY(h->nodes.reserve(sizeof(Node<T, D>) * (size_t)inner, ctx.stream));
   AXB_TRY(h->leaf_nodes.reserve(sizeof(int32_t) * (size_t)n, ctx.stream));
   AXB_TRY(h->leaf_parent.reserve(sizeof(int32_t) * (size_t)n, ctx.stream));
+  AXB_TRY(h->node_range.reserve(sizeof(int2) * (size_t)inner, ctx.stream));
   AXB_TRY(h->keys_a.reserve(sizeof(unsigned long long) * (size_t)n, ctx.stream));
   AXB_TRY(h->keys_b.reserve(sizeof(unsigned long long) * (size_t)n, ctx.stream));
   AXB_TRY(h->state.reserve(sizeof(BuildState<T, D>), ctx.stream));
@@ -347,7 +353,7 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
   {
     ScopedPhase ph(ctx, "build.tree");
     AXB_LAUNCH(ctx, (tree_kernel<T, D>), blocks_for(inner, 256), 256, h->sorted_keys, n, h->nodes.as<Node<T, D>>(),
-               h->leaf_parent.as<int32_t>());
+               h->leaf_parent.as<int32_t>(), h->node_range.as<int2>());
   }
   {
     ScopedPhase ph(ctx, "build.refit");
@@ -738,10 +744,11 @@ struct axb_sd
   int nv = 3;              // vertices per cell
   int ncells = 0;
   int nnodes = 0;
-  int mode = 0;
+  int mode = 1;  // 1 = OBB-accelerated, Morton-ordered queries (default); 0 = reference visiting order
   bool count_work = false;
   SdParams prm;
   DevBuf x, y, z, conn, soup, cell_boxes, obounds, q_stage, out_phi, out_cp, out_n, work;
+  DevBuf obb, qkeys_a, qkeys_b, qscratch, qperm, qbounds;
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
   Ctx& ctx() { return bvh->ctx; }
 };
@@ -836,6 +843,16 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       AXB_LAUNCH(ctx, gather_soup_kernel<4>, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
                  s->conn.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
     s->cell_boxes.release(ctx.stream);
+    // oriented-bound overlay for the fast query mode (sd_fast.cuh): one warp per tree entity
+    {
+      const long long entities = 2LL * nl - 1;
+      AXB_TRY(s->obb.reserve(sizeof(Obb) * (size_t)entities, ctx.stream));
+      const int blocks = blocks_for(entities * 32, 256);
+      if(s->nv == 3)
+        AXB_LAUNCH(ctx, obb_build_kernel<3>, blocks, 256, s->soup.as<double>(), s->bvh->node_range.as<int2>(), nl, s->obb.as<Obb>());
+      else
+        AXB_LAUNCH(ctx, obb_build_kernel<4>, blocks, 256, s->soup.as<double>(), s->bvh->node_range.as<int2>(), nl, s->obb.as<Obb>());
+    }
     return ctx.sync();
   };
   st = body();
@@ -856,7 +873,7 @@ int axb_sd_destroy(axb_sd* s)
     cudaSetDevice(s->ctx().device);
     cudaStream_t st = s->ctx().stream;
     for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->soup, &s->cell_boxes, &s->obounds, &s->q_stage, &s->out_phi, &s->out_cp,
-                     &s->out_n, &s->work})
+                     &s->out_n, &s->work, &s->obb, &s->qkeys_a, &s->qkeys_b, &s->qscratch, &s->qperm, &s->qbounds})
       b->release(st);
     axb_bvh_destroy(s->bvh);
   }
@@ -900,7 +917,7 @@ int axb_sd_get_mesh_bounds(const axb_sd* s, double* lo, double* hi)
 int axb_sd_set_mode(axb_sd* s, int mode)
 {
   if(!s) return fail(AXB_ERR_BAD_ARG, "null handle");
-  if(mode != 0) return fail(AXB_ERR_UNSUPPORTED, "only mode 0 (reference visiting order) is built in this version");
+  if(mode != 0 && mode != 1) return fail(AXB_ERR_BAD_ARG, "mode must be 0 (reference visiting order) or 1 (fast)");
   s->mode = mode;
   return AXB_OK;
 }
@@ -951,6 +968,49 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
     d_work = s->work.as<unsigned long long>();
   }
   const Node<double, 3>* nodes = s->bvh->nodes.as<Node<double, 3>>();
+  if(s->mode == 1)
+  {
+    const int32_t* perm = nullptr;
+    if(npts >= 4096)
+    {
+      // Morton order of the query points: neighbouring threads walk the same nodes
+      ScopedPhase ph(ctx, "query.sortq");
+      const size_t kb = sizeof(unsigned long long) * (size_t)npts;
+      AXB_TRY(s->qkeys_a.reserve(kb, ctx.stream));
+      AXB_TRY(s->qkeys_b.reserve(kb, ctx.stream));
+      AXB_TRY(s->qperm.reserve(sizeof(int32_t) * (size_t)npts, ctx.stream));
+      AXB_TRY(s->qbounds.reserve(sizeof(unsigned long long) * 6, ctx.stream));
+      const size_t scratch = rsort::scratch_bytes(npts);
+      AXB_TRY(s->qscratch.reserve(scratch, ctx.stream));
+      AXB_CUDA_TRY(cudaMemsetAsync(s->qscratch.p, 0, scratch, ctx.stream));
+      uint32_t* ghist = s->qscratch.as<uint32_t>();
+      uint32_t* tile_counters = ghist + rsort::MAX_PASSES * rsort::RADIX;
+      uint32_t* lookback = tile_counters + 64;
+      unsigned long long init[6];
+      for(int d = 0; d < 3; ++d)
+      {
+        init[d] = f64_to_ordered(DBL_MAX);
+        init[3 + d] = f64_to_ordered(-DBL_MAX);
+      }
+      AXB_CUDA_TRY(cudaMemcpyAsync(s->qbounds.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+      AXB_LAUNCH(ctx, query_bounds_kernel, capped_grid(npts, 256), 256, q, npts, s->qbounds.as<unsigned long long>());
+      AXB_LAUNCH(ctx, query_keys_kernel, capped_grid(npts, 256), 256, q, npts, s->qbounds.as<unsigned long long>(),
+                 s->qkeys_a.as<unsigned long long>(), ghist);
+      unsigned long long* sorted = nullptr;
+      AXB_TRY(sort_keys_generic(ctx, s->qkeys_a.as<unsigned long long>(), s->qkeys_b.as<unsigned long long>(), npts, ghist,
+                                tile_counters, lookback, &sorted));
+      AXB_LAUNCH(ctx, keys_to_perm_kernel, blocks_for(npts, 256), 256, sorted, npts, s->qperm.as<int32_t>());
+      perm = s->qperm.as<int32_t>();
+    }
+    ScopedPhase ph(ctx, "query.kernel");
+    if(s->nv == 3)
+      AXB_LAUNCH(ctx, sd_fast_kernel<3>, blocks_for(npts, 128), 128, nodes, s->obb.as<Obb>(), s->soup.as<double>(), s->bvh->n, s->prm, q,
+                 npts, perm, d_phi, d_cp, d_n, d_work);
+    else
+      AXB_LAUNCH(ctx, sd_fast_kernel<4>, blocks_for(npts, 128), 128, nodes, s->obb.as<Obb>(), s->soup.as<double>(), s->bvh->n, s->prm, q,
+                 npts, perm, d_phi, d_cp, d_n, d_work);
+  }
+  else
   {
     ScopedPhase ph(ctx, "query.kernel");
     if(s->nv == 3)

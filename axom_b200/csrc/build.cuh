@@ -222,7 +222,7 @@ __device__ __forceinline__ int karras_delta(const unsigned long long* __restrict
 // node i gets child ids in traversal encoding; each child records (parent<<1)|side.
 template <typename T, int D>
 __global__ void __launch_bounds__(256) tree_kernel(const unsigned long long* __restrict__ keys, int n, Node<T, D>* __restrict__ nodes,
-                                                    int32_t* __restrict__ leaf_parent)
+                                                    int32_t* __restrict__ leaf_parent, int2* __restrict__ node_range)
 {
   const int inner_size = n - 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(256) tree_kernel(const unsigned long long* __r
     nodes[split + 1].parent = (i << 1) | 1;
     rchild = split + 1;
   }
+  node_range[i] = make_int2(lo, hi);  // sorted-leaf range covered by inner node i (inclusive)
   nodes[i].child[0] = lchild;
   nodes[i].child[1] = rchild;
   nodes[i].counter = 0u;

@@ -55,20 +55,26 @@ def run_sd(freq, grid):
     rphi, rcp, rn = ref.compute(q, True, True, nthreads=0)
     tc = time.time() - t
     g = SignedDistance(x, y, z, conn)
-    g.setProfiling(2)
-    t = time.time()
-    gphi, gcp, gn = g.computeDistances(q, True, True)
-    tg = time.time() - t
-    ok = diff("phi", rphi, gphi) & diff("cp", rcp, gcp)
-    nerr = np.abs(rn - gn).max()
-    leaf, inner = g.work_counters()
-    print("sd tris=%d q=%d %s normals maxdiff %.2e cpu(omp) %.2fs gpu host %.3fs kernel %.3f ms leaf/q %.1f inner/q %.1f" % (
-        len(conn), len(q), "OK" if ok else "FAIL", nerr, tc, tg, g.phase_ms("query.kernel"), leaf / len(q), inner / len(q)), flush=True)
+    ok = True
+    for mode in (0, 1):
+        g.setMode(mode)
+        g.setProfiling(2)
+        t = time.time()
+        gphi, gcp, gn = g.computeDistances(q, True, True)
+        tg = time.time() - t
+        okm = diff("phi", rphi, gphi)
+        cperr = np.abs(rcp - gcp).max()
+        okm &= cperr <= 1e-12
+        nerr = np.abs(rn - gn).max()
+        leaf, inner = g.work_counters()
+        print("sd mode %d tris=%d q=%d %s cp maxdiff %.1e normals maxdiff %.2e cpu(omp) %.2fs gpu host %.3fs kernel %.3f ms leaf/q %.1f inner/q %.1f" % (
+            mode, len(conn), len(q), "OK" if okm else "FAIL", cperr, nerr, tc, tg, g.phase_ms("query.kernel"), leaf / len(q), inner / len(q)), flush=True)
+        ok &= okm
     return ok
 
 
 if __name__ == "__main__":
-    sizes = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 27, 1000, 4097, 50000]
+    sizes = [int(a) for a in sys.argv[1:] if not a.startswith('-')] or [0, 1, 2, 3, 27, 1000, 4097, 50000]
     ok = True
     for n in sizes:
         ok &= run(n, 3)
@@ -76,5 +82,7 @@ if __name__ == "__main__":
             ok &= run(n, 2)
     ok &= run_sd(8, 12)
     ok &= run_sd(40, 24)
+    if "--big" in sys.argv:
+        ok &= run_sd(316, 64)
     print("ALL OK" if ok else "SOME FAILED")
     sys.exit(0 if ok else 1)

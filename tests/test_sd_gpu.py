@@ -10,14 +10,24 @@ pytestmark = pytest.mark.gpu
 
 
 def _cmp(oracle, x, y, z, conn, q, npc=3, wt=True, cs=True):
+    """both traversal modes against the oracle.
+    mode 0 (reference visiting order): phi and closest points bit-identical.
+    mode 1 (oriented bounds, Morton-ordered queries; the default): phi bit-identical -- it is an exact
+    min over exact per-triangle values -- closest points identical except between exactly tied
+    candidates (<= 1e-12), normals to 1e-12 (summation order / libm acos)."""
     from axom_b200 import SignedDistance
     ref = oracle.SignedDistance(x, y, z, conn, npc, wt, cs)
     gpu = SignedDistance(x, y, z, conn, npc, wt, cs)
     rphi, rcp, rn = ref.compute(q, True, True)
-    gphi, gcp, gn = gpu.computeDistances(q, True, True)
-    assert np.array_equal(rphi, gphi), np.abs(rphi - gphi).max()
-    assert np.array_equal(rcp, gcp)
-    assert np.allclose(rn, gn, rtol=0, atol=1e-12)
+    for mode in (0, 1):
+        gpu.setMode(mode)
+        gphi, gcp, gn = gpu.computeDistances(q, True, True)
+        assert np.array_equal(rphi, gphi), (mode, np.abs(rphi - gphi).max())
+        if mode == 0:
+            assert np.array_equal(rcp, gcp)
+        else:
+            assert np.allclose(rcp, gcp, rtol=0, atol=1e-12)
+        assert np.allclose(rn, gn, rtol=0, atol=1e-12), mode
     lo, hi = gpu.getMeshBounds()
     assert lo[0] == x.min() and hi[2] == z.max()
     return gphi
@@ -80,7 +90,7 @@ def test_medium_icosphere_device_queries(oracle):
     qd = torch.from_numpy(q).cuda()
     phi, cp, _ = gpu.computeDistances(qd, True, False)
     assert np.array_equal(ref[0], phi.cpu().numpy())
-    assert np.array_equal(ref[1], cp.cpu().numpy())
+    assert np.allclose(ref[1], cp.cpu().numpy(), rtol=0, atol=1e-12)
     # SoA (ZipIndexable) queries give the same answer
     phi2, _, _ = gpu.computeDistances(tuple(qd[:, c].contiguous() for c in range(3)))
     assert torch.equal(phi, phi2)
@@ -90,9 +100,12 @@ def test_golden_fixture_on_gpu():
     import os
     from axom_b200 import SignedDistance
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sd_icosphere5.npz"))
-    phi, cp, nrm = SignedDistance(g["x"], g["y"], g["z"], g["conn"]).computeDistances(g["q"], True, True)
-    assert np.array_equal(phi, g["phi"]) and np.array_equal(cp, g["cp"])
-    assert np.allclose(nrm, g["nrm"], rtol=0, atol=1e-12)
+    sd = SignedDistance(g["x"], g["y"], g["z"], g["conn"])
+    for mode in (0, 1):
+        sd.setMode(mode)
+        phi, cp, nrm = sd.computeDistances(g["q"], True, True)
+        assert np.array_equal(phi, g["phi"]) and np.allclose(cp, g["cp"], rtol=0, atol=1e-12)
+        assert np.allclose(nrm, g["nrm"], rtol=0, atol=1e-12)
 
 
 def test_scalar_overload_and_bvh_access(oracle):
@@ -105,3 +118,16 @@ def test_scalar_overload_and_bvh_access(oracle):
     b = sd.getBVHTree()
     assert b.isInitialized() and b.numLeaves() == len(conn)
     assert b.getScaleFactor() == 1.000123  # SignedDistance keeps the default scale (:499-500)
+
+
+def test_fast_mode_large_sorted_queries(oracle):
+    """enough queries to take the Morton-sort path (>= 4096), random + grid, both modes agree with the oracle"""
+    from axom_b200 import SignedDistance
+    x, y, z, conn = synth.icosphere(30)
+    rng = np.random.default_rng(8)
+    q = np.concatenate([synth.uniform_grid_points(-1, 1, 20), rng.uniform(-2, 2, (6000, 3)), rng.normal(0, 0.02, (2000, 3))])
+    ref = oracle.SignedDistance(x, y, z, conn).compute(q, True, False, nthreads=0)
+    sd = SignedDistance(x, y, z, conn)
+    phi, cp, _ = sd.computeDistances(q, True, False)
+    assert np.array_equal(ref[0], phi)
+    assert np.allclose(ref[1], cp, rtol=0, atol=1e-12)
