@@ -196,6 +196,20 @@ static inline int capped_grid(long long n, int block, int per_sm = 8)
 // staging of "Indexable" inputs: host arrays are copied to the device (AoS block or one
 // array per component), device arrays are used in place.
 //------------------------------------------------------------------------------------------
+// AXB_MEM_AUTO -> AXB_MEM_HOST | AXB_MEM_DEVICE by asking the driver about the pointer
+static int resolve_memspace(int memspace, const void* p)
+{
+  if(memspace != AXB_MEM_AUTO) return memspace;
+  if(!p) return AXB_MEM_HOST;
+  cudaPointerAttributes a;
+  if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return AXB_MEM_HOST;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? AXB_MEM_DEVICE : AXB_MEM_HOST;
+}
+
 template <int NC>
 static int stage_desc(Ctx& ctx, const axb_array_desc* in, long long count, size_t elem, DevBuf& stage, Desc<NC>& out)
 {
@@ -204,13 +218,14 @@ static int stage_desc(Ctx& ctx, const axb_array_desc* in, long long count, size_
   for(int c = 0; c < NC; ++c)
     if(count > 0 && in->comp[c] == nullptr) return fail(AXB_ERR_BAD_ARG, "null component pointer in array descriptor");
   if(count > 0 && in->stride_bytes < (int64_t)elem) return fail(AXB_ERR_BAD_ARG, "array descriptor stride smaller than the element size");
-  if(in->memspace == AXB_MEM_DEVICE || count == 0)
+  const int space = resolve_memspace(in->memspace, in->comp[0]);
+  if(space == AXB_MEM_DEVICE || count == 0)
   {
     for(int c = 0; c < NC; ++c) out.comp[c] = reinterpret_cast<const char*>(in->comp[c]);
     out.stride = in->stride_bytes;
     return AXB_OK;
   }
-  if(in->memspace != AXB_MEM_HOST) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  if(space != AXB_MEM_HOST) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
   const char* base = reinterpret_cast<const char*>(in->comp[0]);
   bool aos = (in->stride_bytes == (int64_t)(NC * elem));
   for(int c = 0; c < NC && aos; ++c) aos = (reinterpret_cast<const char*>(in->comp[c]) == base + c * elem);
@@ -413,6 +428,7 @@ int find_impl(axb_bvh* h, const axb_array_desc* prims, int flags, int32_t nq, in
   if(nq < 0) return fail(AXB_ERR_BAD_ARG, "negative query count");
   if(!candidates || !total) return fail(AXB_ERR_BAD_ARG, "null output pointer");
   if(nq > 0 && (!offsets || !counts)) return fail(AXB_ERR_BAD_ARG, "offsets/counts must hold num_queries entries");
+  out_memspace = resolve_memspace(out_memspace, offsets);
   if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown output memspace");
   Ctx& ctx = h->ctx;
   AXB_TRY(ctx.bind());
@@ -659,6 +675,7 @@ int axb_bvh_find_rays(axb_bvh* h, const axb_array_desc* rays, int rays_normalize
 int axb_bvh_free_candidates(axb_bvh* h, int32_t* candidates, int memspace)
 {
   if(!candidates) return AXB_OK;
+  memspace = resolve_memspace(memspace, candidates);
   if(memspace == AXB_MEM_HOST)
   {
     free(candidates);
@@ -765,6 +782,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
   if(nodes_per_cell != 3 && nodes_per_cell != 4) return fail(AXB_ERR_BAD_ARG, "surface cells must be triangles (3) or quads (4)");
   if(nnodes < 0 || ncells < 0) return fail(AXB_ERR_BAD_ARG, "negative mesh size");
   if((nnodes > 0 && (!x || !y || !z)) || (ncells > 0 && !conn)) return fail(AXB_ERR_BAD_ARG, "null mesh array");
+  mesh_memspace = resolve_memspace(mesh_memspace, x);
   if(mesh_memspace != AXB_MEM_HOST && mesh_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
   axb_sd* s = new axb_sd();
   int st = axb_bvh_create(&s->bvh, 3, 8, device);
@@ -935,6 +953,7 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
   if(!s) return fail(AXB_ERR_BAD_ARG, "null handle");
   if(npts < 0) return fail(AXB_ERR_BAD_ARG, "negative point count");
   if(npts > 0 && !phi) return fail(AXB_ERR_BAD_ARG, "outSgnDist != nullptr");
+  out_memspace = resolve_memspace(out_memspace, phi);
   if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown output memspace");
   if(!s->bvh->built) return fail(AXB_ERR_NOT_BUILT, "SignedDistance query before setMesh()");
   Ctx& ctx = s->ctx();

@@ -10,11 +10,16 @@
 // lower bound on the distance to anything in the subtree, so only the few nodes actually under the query
 // survive.  Leaves that survive are evaluated with exactly the reference arithmetic (check_triangle in
 // sd.cuh), and the running minimum is an exact min over exact per-triangle values, so
-//   * distances and closest points are bit-identical to the reference,
+//   * distances are bit-identical to the reference,
 //   * every candidate the reference's pseudo-normal state machine would have used is still visited:
 //     the prune threshold is widened by the machine's own tie window (closest points within 1e-6,
-//     quest/SignedDistance.hpp:690,709), so signs are identical and normals differ only by summation
-//     order (last ulp).
+//     quest/SignedDistance.hpp:690,709),
+//   * children are entered in the reference's order (nearer AABB centroid first), so the evaluated
+//     leaves are a subsequence of the reference's visiting order and every skipped leaf is a no-op of
+//     the state machine: strict-< tie-breaks between equidistant triangles (closest point, minElem)
+//     and the summation order of the pseudo-normal are the reference's.  (The only inputs on which
+//     the two can differ are meshes with DISTINCT features closer than 1e-6 to each other, where the
+//     reference's own answer already depends on its visiting order.)
 // Queries are processed in Morton order of their position (one thread per query), so the threads of a
 // warp walk the same few nodes and their loads coalesce into L1-resident lines.
 #pragma once
@@ -201,7 +206,7 @@ __device__ __forceinline__ double prune_threshold(double minSq)
   return d * d * (1.0 + 1e-12) + 1e-300;
 }
 
-// MODE 1 kernel: one thread per query, queries taken in Morton order (perm), nearest-child-first DFS
+// MODE 1 kernel: one thread per query, queries taken in Morton order (perm), reference-ordered DFS
 // with a (node, lower bound) stack so stale entries are dropped without touching memory.
 template <int NV>
 __global__ void __launch_bounds__(128) sd_fast_kernel(const Node<double, 3>* __restrict__ nodes, const Obb* __restrict__ obb,
@@ -232,75 +237,80 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const Node<double, 3>* __r
   int32_t cur = 0;  // root
   while(true)
   {
-    // ---- visit inner node `cur` ----
-    ++ninner;
-    const Node<double, 3>& nd = nodes[cur];
-    int32_t child[2] = {nd.child[0], nd.child[1]};
-    double d2[2];
-#pragma unroll
-    for(int s = 0; s < 2; ++s)
-    {
-      const Box<double, 3> bb = nd.box[s];
-      double v = DBL_MAX;
-      if(box_valid(bb))
-      {
-        v = sqdist_point_box(qp, bb);
-        if(v <= thr)
-        {
-          const int e = child[s] >= 0 ? child[s] : inner + (-child[s] - 1);
-          v = fmax(v, obb_sqdist(obb + e, qp));
-        }
-      }
-      d2[s] = v;
-    }
-    // nearer child first
-    if(d2[1] < d2[0])
-    {
-      const double td = d2[0];
-      d2[0] = d2[1];
-      d2[1] = td;
-      const int32_t tc = child[0];
-      child[0] = child[1];
-      child[1] = tc;
-    }
     int32_t next = kBarrier;
+    if(cur < 0)
+    {
+      // ---- leaf: the reference's checkCandidate, then tighten the threshold ----
+      ++nleaf;
+      check_leaf<NV>(soup, q, m, -cur - 1, cn);
+      thr = prune_threshold(m.minSq);
+    }
+    else
+    {
+      // ---- inner node ----
+      ++ninner;
+      const Node<double, 3>& nd = nodes[cur];
+      int32_t child[2] = {nd.child[0], nd.child[1]};
+      const Box<double, 3> bx[2] = {nd.box[0], nd.box[1]};
+      double d2[2];
+      bool in[2];
 #pragma unroll
-    for(int s = 0; s < 2; ++s)
-    {
-      if(d2[s] <= thr)
+      for(int s = 0; s < 2; ++s)
       {
-        if(child[s] < 0)
+        double v = DBL_MAX;
+        bool ok = box_valid(bx[s]);  // bvh_traverse.hpp:95-96: invalid boxes are never entered
+        if(ok)
         {
-          ++nleaf;
-          check_leaf<NV>(soup, q, m, -child[s] - 1, cn);
-          thr = prune_threshold(m.minSq);
+          v = sqdist_point_box(qp, bx[s]);
+          ok = v <= thr;
+          if(ok)
+          {
+            const int e = child[s] >= 0 ? child[s] : inner + (-child[s] - 1);
+            v = fmax(v, obb_sqdist(obb + e, qp));
+            ok = v <= thr;
+          }
         }
-        else if(next == kBarrier)
+        d2[s] = v;
+        in[s] = ok;
+      }
+      // Child order = the reference's (LinearBVH.hpp:72-85): when both children are entered, the one whose
+      // AABB centroid is nearer goes first and the other waits on the stack -- leaf or not -- until
+      // everything below the first is done.  The leaves this kernel evaluates are then a SUBSEQUENCE of
+      // the reference's own visiting order, so strict-< tie-breaks between equidistant triangles and the
+      // summation order of the pseudo-normal are the reference's.
+      if(in[0] && in[1])
+      {
+        double dl = 0.0, dr = 0.0;
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
         {
-          next = child[s];
+          const double cl = 0.5 * (bx[0].lo[d] + bx[0].hi[d]) - qp[d];
+          dl += cl * cl;
+          const double cr = 0.5 * (bx[1].lo[d] + bx[1].hi[d]) - qp[d];
+          dr += cr * cr;
         }
-        else
-        {
-          st_node[sp] = child[s];
-          st_d2[sp] = __double2float_rd(d2[s]);
-          ++sp;
-        }
+        const int first = dl > dr ? 1 : 0;
+        next = child[first];
+        st_node[sp] = child[first ^ 1];
+        st_d2[sp] = __double2float_rd(d2[first ^ 1]);
+        ++sp;
+      }
+      else if(in[0])
+      {
+        next = child[0];
+      }
+      else if(in[1])
+      {
+        next = child[1];
       }
     }
-    // ---- next node: the near inner child, else pop until an entry still beats the threshold ----
-    if(next == kBarrier)
+    // ---- pop until an entry still beats the threshold (stale entries cost no memory access) ----
+    while(next == kBarrier && sp > 0)
     {
-      while(sp > 0)
-      {
-        --sp;
-        if((double)st_d2[sp] <= thr)
-        {
-          next = st_node[sp];
-          break;
-        }
-      }
-      if(next == kBarrier) break;
+      --sp;
+      if((double)st_d2[sp] <= thr) next = st_node[sp];
     }
+    if(next == kBarrier) break;
     cur = next;
   }
   sd_finish<NV>(soup, prm, q, m, qi, phi, cps, nrms);

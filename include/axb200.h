@@ -49,7 +49,11 @@ typedef enum axb_status
 typedef enum axb_memspace
 {
   AXB_MEM_HOST = 0,  /* pageable or pinned host memory: staged through the handle's stream */
-  AXB_MEM_DEVICE = 1 /* device (or managed) memory on the handle's device: used in place   */
+  AXB_MEM_DEVICE = 1, /* device (or managed) memory on the handle's device: used in place  */
+  AXB_MEM_AUTO = 2    /* ask the driver (cudaPointerGetAttributes): device / managed pointers are
+                         used in place, everything else is treated as host memory.  This is what
+                         the C++ shims pass, so that -- like the reference (spin/BVH.hpp:198-203) --
+                         the caller simply hands over pointers valid in its execution space.  */
 } axb_memspace;
 
 /* BVH_BUILD_OK of spin/BVH.hpp:39-43 */

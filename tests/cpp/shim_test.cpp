@@ -1,0 +1,254 @@
+// shim_test.cpp -- exercises the C++ header shims (include/axom_b200/*.hpp) the way the reference's
+// own unit tests drive spin::BVH and quest::SignedDistance:
+//   spin/tests/spin_bvh.cpp:279-404  (3-D box query, 18 hits)        :519-646 (3-D rays, 15 hits)
+//   spin/tests/spin_bvh.cpp:792-999  (cell centroids -> one candidate each)
+//   spin/tests/spin_bvh.cpp:1064-1076, :1526-1531 (single box / zero boxes)
+//   quest/tests/quest_signed_distance_interface.cpp:186-237 (z=0 plane, phi == z exactly)
+// Built by __graft_entry__.build() with plain g++ (no CUDA headers needed) and run on the GPU box by
+// tests/test_cpp_shim.py.  `shim_test --no-device` only checks the error path (there is no CPU fallback).
+#define AXOM_B200_ALIAS_AXOM
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "axom_b200/BVH.hpp"
+#include "axom_b200/SignedDistance.hpp"
+
+namespace primal = axom::primal;
+using axom::IndexType;
+
+static int g_failures = 0;
+#define EXPECT(cond)                                                                  \
+  do                                                                                  \
+  {                                                                                   \
+    if(!(cond))                                                                       \
+    {                                                                                 \
+      std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);          \
+      ++g_failures;                                                                   \
+    }                                                                                 \
+  } while(0)
+
+static void throwing_handler(int status, const char* msg)
+{
+  throw std::runtime_error(std::string(axb_status_string(status)) + ": " + msg);
+}
+
+using Box3 = primal::BoundingBox<double, 3>;
+using Pt3 = primal::Point<double, 3>;
+using Vec3 = primal::Vector<double, 3>;
+using Ray3 = primal::Ray<double, 3>;
+
+// AABBs of the cells of a uniform mesh [0,n]^3 with unit cells, x fastest (spin_bvh.cpp:90-122)
+static std::vector<Box3> unit_cells(int n)
+{
+  std::vector<Box3> b;
+  for(int k = 0; k < n; ++k)
+    for(int j = 0; j < n; ++j)
+      for(int i = 0; i < n; ++i) b.emplace_back(Pt3 {double(i), double(j), double(k)}, Pt3 {i + 1., j + 1., k + 1.});
+  return b;
+}
+
+static std::vector<IndexType> sorted_hits(const std::vector<IndexType>& off, const std::vector<IndexType>& cnt,
+                                          const axom::Array<IndexType>& cand, int q)
+{
+  std::vector<IndexType> h(cand.data() + off[q], cand.data() + off[q] + cnt[q]);
+  std::sort(h.begin(), h.end());
+  return h;
+}
+
+static void test_bvh()
+{
+  const int N = 3;
+  std::vector<Box3> cells = unit_cells(N);
+  axom::spin::BVH<3, axom::B200_EXEC, double> bvh;
+  bvh.setScaleFactor(1.0);  // spin_bvh.cpp:218
+  EXPECT(!bvh.isInitialized());
+  EXPECT(!bvh.getBounds().isValid());
+  EXPECT(bvh.initialize(cells.data(), (IndexType)cells.size()) == axom::spin::BVH_BUILD_OK);
+  EXPECT(bvh.isInitialized());
+  const Box3 bounds = bvh.getBounds();
+  for(int d = 0; d < 3; ++d) EXPECT(bounds.getMin()[d] == 0.0 && bounds.getMax()[d] == 3.0);
+
+  // boxes: 18 hits = cells 0..17, second box none
+  {
+    std::vector<Box3> q = {Box3(Pt3 {-1, -1, -1}, Pt3 {2.5, 2.5, 1.5}), Box3(Pt3 {-1, -1, -1}, Pt3 {-0.5, -0.5, -0.5})};
+    std::vector<IndexType> off(2), cnt(2);
+    axom::Array<IndexType> cand;
+    bvh.findBoundingBoxes(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, 2, q.data());
+    EXPECT(cnt[0] == 18 && cnt[1] == 0 && off[0] == 0 && off[1] == 18 && cand.size() == 18);
+    const auto h = sorted_hits(off, cnt, cand, 0);
+    for(int i = 0; i < 18; ++i) EXPECT(h[i] == i);
+  }
+  // rays (array of constructed, i.e. normalised, Ray objects): 15 hits
+  {
+    std::vector<Ray3> q = {Ray3(Pt3 {-1, -1, -1}, Vec3 {1, 1, 1}), Ray3(Pt3 {-1, -1, -1}, Vec3 {-1, -1, -1})};
+    std::vector<IndexType> off(2), cnt(2);
+    axom::Array<IndexType> cand;
+    bvh.findRays(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, 2, q.data());
+    const IndexType expect[15] = {0, 1, 3, 4, 9, 10, 12, 13, 14, 16, 17, 22, 23, 25, 26};
+    EXPECT(cnt[0] == 15 && cnt[1] == 0);
+    const auto h = sorted_hits(off, cnt, cand, 0);
+    for(int i = 0; i < 15 && i < (int)h.size(); ++i) EXPECT(h[i] == expect[i]);
+    // the same rays as an SoA ZipIndexable with unnormalised directions: the library applies the Ray ctor
+    const double ox[2] = {-1, -1}, oy[2] = {-1, -1}, oz[2] = {-1, -1};
+    const double dx[2] = {1, -1}, dy[2] = {1, -1}, dz[2] = {1, -1};
+    const double* o[3] = {ox, oy, oz};
+    const double* dd[3] = {dx, dy, dz};
+    primal::ZipIndexable<Ray3> zip(o, dd);
+    axom::Array<IndexType> cand2;
+    std::vector<IndexType> off2(2), cnt2(2);
+    bvh.findRays(axom::ArrayView<IndexType>(off2), axom::ArrayView<IndexType>(cnt2), cand2, 2, zip);
+    EXPECT(cnt2 == cnt && cand2.size() == cand.size());
+    for(IndexType i = 0; i < cand.size() && i < cand2.size(); ++i) EXPECT(cand[i] == cand2[i]);
+  }
+  // points: centroids -> exactly their own cell; as AoS, as ZipIndexable, and as a generic Indexable
+  {
+    std::vector<Pt3> c;
+    std::vector<double> cx, cy, cz;
+    for(const Box3& b : cells)
+    {
+      c.push_back(Pt3 {0.5 * (b.getMin()[0] + b.getMax()[0]), 0.5 * (b.getMin()[1] + b.getMax()[1]), 0.5 * (b.getMin()[2] + b.getMax()[2])});
+      cx.push_back(c.back()[0]);
+      cy.push_back(c.back()[1]);
+      cz.push_back(c.back()[2]);
+    }
+    const IndexType n = (IndexType)c.size();
+    const double* arrs[3] = {cx.data(), cy.data(), cz.data()};
+    primal::ZipIndexable<Pt3> zip(arrs);
+    for(int variant = 0; variant < 3; ++variant)
+    {
+      std::vector<IndexType> off(n), cnt(n);
+      axom::Array<IndexType> cand;
+      if(variant == 0)
+        bvh.findPoints(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, n, c.data());
+      else if(variant == 1)
+        bvh.findPoints(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, n, zip);
+      else
+        bvh.findPoints(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, n, c);  // std::vector: generic operator[]
+      EXPECT(cand.size() == n);
+      for(IndexType i = 0; i < n; ++i) EXPECT(cnt[i] == 1 && cand[off[i]] == i);
+    }
+    // size mismatch -> the reference's SLIC_ERROR (policy/LinearBVH.hpp:284-285)
+    bool threw = false;
+    try
+    {
+      std::vector<IndexType> off(n - 1), cnt(n);
+      axom::Array<IndexType> cand;
+      bvh.findPoints(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, n, c.data());
+    }
+    catch(const std::runtime_error&)
+    {
+      threw = true;
+    }
+    EXPECT(threw);
+  }
+  // single box and zero boxes (spin_bvh.cpp:1064-1076, :1526-1531)
+  {
+    axom::spin::BVH<3> one(cells.data(), 1);
+    Pt3 q[2] = {Pt3 {0.5, 0.5, 0.5}, Pt3 {2.5, 2.5, 2.5}};
+    std::vector<IndexType> off(2), cnt(2);
+    axom::Array<IndexType> cand;
+    one.findPoints(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, 2, q);
+    EXPECT(cnt[0] == 1 && cnt[1] == 0 && cand.size() == 1 && cand[0] == 0);
+    axom::spin::BVH<3> none(cells.data(), 0);
+    none.findPoints(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, 2, q);
+    EXPECT(cnt[0] == 0 && cnt[1] == 0 && cand.size() == 0);
+    const auto tr = none.getTraverser();
+    EXPECT(tr.m_num_leaves == 2 && tr.m_inner_nodes != nullptr);
+  }
+  // 2-D
+  {
+    using Box2 = primal::BoundingBox<double, 2>;
+    using Pt2 = primal::Point<double, 2>;
+    std::vector<Box2> c2;
+    for(int j = 0; j < 3; ++j)
+      for(int i = 0; i < 3; ++i) c2.emplace_back(Pt2 {double(i), double(j)}, Pt2 {i + 1., j + 1.});
+    axom::spin::BVH<2> b2;
+    b2.setScaleFactor(1.0);
+    b2.initialize(c2.data(), 9);
+    std::vector<Box2> q = {Box2(Pt2 {-1, -1}, Pt2 {2.5, 1.5}), Box2(Pt2 {-1, -1}, Pt2 {-0.1, -0.1})};
+    std::vector<IndexType> off(2), cnt(2);
+    axom::Array<IndexType> cand;
+    b2.findBoundingBoxes(axom::ArrayView<IndexType>(off), axom::ArrayView<IndexType>(cnt), cand, 2, q.data());
+    EXPECT(cnt[0] == 6 && cnt[1] == 0);  // spin_bvh.cpp:408-516
+  }
+}
+
+static void test_signed_distance()
+{
+  // 4-triangle z=0 plane, not watertight: phi == z exactly (quest_signed_distance_interface.cpp:186-237)
+  const double px[5] = {-5, 5, 5, -5, 0}, py[5] = {-5, -5, 5, 5, 0}, pz[5] = {0, 0, 0, 0, 0};
+  const IndexType tris[12] = {0, 1, 4, 1, 2, 4, 2, 3, 4, 3, 0, 4};
+  axom::quest::SurfaceMesh mesh;
+  mesh.x = px;
+  mesh.y = py;
+  mesh.z = pz;
+  mesh.num_nodes = 5;
+  mesh.cells_to_nodes = tris;
+  mesh.num_cells = 4;
+  mesh.nodes_per_cell = 3;
+  axom::quest::SignedDistance<3> sd(&mesh, /*isWatertight*/ false, /*computeSign*/ true);
+  EXPECT(sd.getBVHTree().isInitialized());
+  EXPECT(sd.getBVHTree().getScaleFactor() == 1.000123);  // quest/SignedDistance.hpp:499-500
+  std::vector<Pt3> q;
+  for(int k = 0; k < 9; ++k)
+    for(int j = 0; j < 9; ++j)
+      for(int i = 0; i < 9; ++i) q.push_back(Pt3 {-4. + i, -4. + j, -4. + k});
+  std::vector<double> phi(q.size());
+  std::vector<Pt3> cp(q.size());
+  std::vector<Vec3> nrm(q.size());
+  sd.computeDistances((int)q.size(), q.data(), phi.data(), cp.data(), nrm.data());
+  for(std::size_t i = 0; i < q.size(); ++i)
+  {
+    EXPECT(phi[i] == q[i][2]);
+    EXPECT(cp[i][0] == q[i][0] && cp[i][1] == q[i][1] && cp[i][2] == 0.0);
+    EXPECT(nrm[i][0] == 0.0 && nrm[i][1] == 0.0 && nrm[i][2] == 1.0);
+  }
+  EXPECT(sd.computeDistance(1.0, 2.0, -3.0) == -3.0);
+  Pt3 c;
+  Vec3 n;
+  EXPECT(sd.computeDistance(Pt3 {0.25, 0.5, 2.0}, c, n) == 2.0);
+  EXPECT(c[2] == 0.0 && n[2] == 1.0);
+  const Box3 mb = sd.getMeshBounds();
+  EXPECT(mb.getMin()[0] == -5.0 && mb.getMax()[1] == 5.0 && mb.getMax()[2] == 0.0);
+}
+
+int main(int argc, char** argv)
+{
+  axom::error_handler() = throwing_handler;
+  if(argc > 1 && std::strcmp(argv[1], "--no-device") == 0)
+  {
+    // without a GPU every compute entry point must fail loudly: there is no CPU fallback
+    if(axb_device_count() > 0)
+    {
+      std::printf("shim_test --no-device: a device is present, nothing to check\n");
+      return 0;
+    }
+    bool threw = false;
+    try
+    {
+      std::vector<Box3> cells = unit_cells(2);
+      axom::spin::BVH<3> bvh;
+      bvh.initialize(cells.data(), (IndexType)cells.size());
+    }
+    catch(const std::runtime_error& e)
+    {
+      threw = std::strstr(e.what(), "AXB_ERR_NO_DEVICE") != nullptr;
+    }
+    std::printf("shim_test --no-device: %s\n", threw ? "OK (AXB_ERR_NO_DEVICE raised)" : "FAILED");
+    return threw ? 0 : 1;
+  }
+  try
+  {
+    test_bvh();
+    test_signed_distance();
+  }
+  catch(const std::exception& e)
+  {
+    std::fprintf(stderr, "unexpected error: %s\n", e.what());
+    return 2;
+  }
+  std::printf("shim_test: %s (%d failures)\n", g_failures == 0 ? "OK" : "FAILED", g_failures);
+  return g_failures == 0 ? 0 : 1;
+}
