@@ -765,7 +765,8 @@ struct axb_sd
   bool count_work = false;
   SdParams prm;
   DevBuf x, y, z, conn, soup, cell_boxes, obounds, q_stage, out_phi, out_cp, out_n, work;
-  DevBuf obb, qkeys_a, qkeys_b, qscratch, qperm, qbounds;
+  DevBuf sdnodes, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor;
+  int fast_blocks_per_sm = 0;  // occupancy of the persistent query kernel (queried once)
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
   Ctx& ctx() { return bvh->ctx; }
 };
@@ -853,7 +854,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
     AXB_TRY(axb_bvh_initialize(s->bvh, &bd, ncells));
     // leaf geometry in sorted-leaf order
     const int nl = s->bvh->n;
-    AXB_TRY(s->soup.reserve(sizeof(double) * 3 * s->nv * (size_t)nl, ctx.stream));
+    AXB_TRY(s->soup.reserve(sizeof(double) * kLeafDoubles * (size_t)nl, ctx.stream));
     if(s->nv == 3)
       AXB_LAUNCH(ctx, gather_soup_kernel<3>, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
                  s->conn.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
@@ -861,15 +862,26 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       AXB_LAUNCH(ctx, gather_soup_kernel<4>, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
                  s->conn.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
     s->cell_boxes.release(ctx.stream);
-    // oriented-bound overlay for the fast query mode (sd_fast.cuh): one warp per tree entity
+    // traversal records of the fast query mode (sd_fast.cuh): child AABBs + oriented bounds + ids,
+    // one warp per tree entity
     {
       const long long entities = 2LL * nl - 1;
-      AXB_TRY(s->obb.reserve(sizeof(Obb) * (size_t)entities, ctx.stream));
+      AXB_TRY(s->sdnodes.reserve(sizeof(SdNode) * (size_t)(nl - 1), ctx.stream));
       const int blocks = blocks_for(entities * 32, 256);
+      const Node<double, 3>* bn = s->bvh->nodes.as<Node<double, 3>>();
       if(s->nv == 3)
-        AXB_LAUNCH(ctx, obb_build_kernel<3>, blocks, 256, s->soup.as<double>(), s->bvh->node_range.as<int2>(), nl, s->obb.as<Obb>());
+        AXB_LAUNCH(ctx, obb_build_kernel<3>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>());
       else
-        AXB_LAUNCH(ctx, obb_build_kernel<4>, blocks, 256, s->soup.as<double>(), s->bvh->node_range.as<int2>(), nl, s->obb.as<Obb>());
+        AXB_LAUNCH(ctx, obb_build_kernel<4>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>());
+      AXB_TRY(s->cursor.reserve(sizeof(unsigned int), ctx.stream));
+      int bps = 0;
+      if(s->nv == 3)
+        AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_fast_kernel<3>, 128, 0));
+      else
+        AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_fast_kernel<4>, 128, 0));
+      s->fast_blocks_per_sm = std::max(1, bps);
     }
     return ctx.sync();
   };
@@ -891,7 +903,7 @@ int axb_sd_destroy(axb_sd* s)
     cudaSetDevice(s->ctx().device);
     cudaStream_t st = s->ctx().stream;
     for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->soup, &s->cell_boxes, &s->obounds, &s->q_stage, &s->out_phi, &s->out_cp,
-                     &s->out_n, &s->work, &s->obb, &s->qkeys_a, &s->qkeys_b, &s->qscratch, &s->qperm, &s->qbounds})
+                     &s->out_n, &s->work, &s->sdnodes, &s->qkeys_a, &s->qkeys_b, &s->qscratch, &s->qperm, &s->qbounds, &s->cursor})
       b->release(st);
     axb_bvh_destroy(s->bvh);
   }
@@ -1022,12 +1034,17 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
       perm = s->qperm.as<int32_t>();
     }
     ScopedPhase ph(ctx, "query.kernel");
+    // persistent warps: one resident wave, queries pulled from a device-side cursor
+    AXB_CUDA_TRY(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned int), ctx.stream));
+    int sms = kNumSMsB200;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
+    const int grid = (int)std::min<long long>(blocks_for(npts, 128), (long long)sms * s->fast_blocks_per_sm);
     if(s->nv == 3)
-      AXB_LAUNCH(ctx, sd_fast_kernel<3>, blocks_for(npts, 128), 128, nodes, s->obb.as<Obb>(), s->soup.as<double>(), s->bvh->n, s->prm, q,
-                 npts, perm, d_phi, d_cp, d_n, d_work);
+      AXB_LAUNCH(ctx, sd_fast_kernel<3>, grid, 128, s->sdnodes.as<SdNode>(), s->soup.as<double>(), s->prm, q, npts, perm, d_phi, d_cp,
+                 d_n, d_work, s->cursor.as<unsigned int>());
     else
-      AXB_LAUNCH(ctx, sd_fast_kernel<4>, blocks_for(npts, 128), 128, nodes, s->obb.as<Obb>(), s->soup.as<double>(), s->bvh->n, s->prm, q,
-                 npts, perm, d_phi, d_cp, d_n, d_work);
+      AXB_LAUNCH(ctx, sd_fast_kernel<4>, grid, 128, s->sdnodes.as<SdNode>(), s->soup.as<double>(), s->prm, q, npts, perm, d_phi, d_cp,
+                 d_n, d_work, s->cursor.as<unsigned int>());
   }
   else
   {

@@ -211,6 +211,20 @@ __host__ __device__ __forceinline__ double ordered_to_f64(unsigned long long o)
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
+// 256-bit read-only global load (sm_100: LDG.E.256).  A lane that reads a record of its own
+// (nothing to coalesce with) pays one L1 wavefront per load instruction, so the traversal records are
+// laid out in 32-byte units and fetched with the widest load the machine has.
+struct alignas(32) D4
+{
+  double x, y, z, w;
+};
+__device__ __forceinline__ D4 ldg256(const void* p)
+{
+  D4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+
 constexpr int kNumSMsB200 = 148;
 
 }  // namespace axb

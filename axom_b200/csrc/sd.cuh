@@ -103,12 +103,15 @@ __device__ __forceinline__ V3 closest_point_tri(const V3& P, const V3& A, const 
   return v3add(A, v3add(v3mul(ab, v), v3mul(ac, w)));
 }
 
-// Triangle::angle (Triangle.hpp:384-400)
+// Triangle::angle (Triangle.hpp:384-400); idx in {0,1,2}, selected without indexing so the
+// triangle stays in registers
 __device__ __forceinline__ double tri_angle(const V3* t, int idx)
 {
-  const V3 pt = t[idx];
-  const V3 v1 = v3unit(v3sub(t[(idx + 1) % 3], pt));
-  const V3 v2 = v3unit(v3sub(t[(idx + 2) % 3], pt));
+  const V3 pt = idx == 0 ? t[0] : (idx == 1 ? t[1] : t[2]);
+  const V3 p1 = idx == 0 ? t[1] : (idx == 1 ? t[2] : t[0]);
+  const V3 p2 = idx == 0 ? t[2] : (idx == 1 ? t[0] : t[1]);
+  const V3 v1 = v3unit(v3sub(p1, pt));
+  const V3 v2 = v3unit(v3sub(p2, pt));
   const double dp = v3dot(v1, v2);
   return acos(dp < -1.0 ? -1.0 : (dp > 1.0 ? 1.0 : dp));
 }
@@ -129,13 +132,26 @@ __device__ __forceinline__ int loc_type(int loc) { return loc < 0 ? 1 : (loc <= 
 
 // Leaf geometry, gathered at setMesh time into sorted-leaf order so a leaf visit is one
 // contiguous read instead of the reference's leaf_nodes -> connectivity -> 3 coordinate arrays
-// pointer chase: NV vertices x 3 doubles per leaf (NV = 3 triangles, 4 quads).
+// pointer chase.  One 96-byte record per leaf (3 x 32 B: 4 vertices x 3 doubles, the 4th unused for
+// triangles), read with three 256-bit loads.
+constexpr int kLeafDoubles = 12;
 template <int NV>
 __device__ __forceinline__ void load_leaf(const double* __restrict__ soup, int pos, V3* v)
 {
-  const double* p = soup + (size_t)pos * (NV * 3);
-#pragma unroll
-  for(int k = 0; k < NV; ++k) v[k] = {__ldg(p + 3 * k), __ldg(p + 3 * k + 1), __ldg(p + 3 * k + 2)};
+  const D4* p = reinterpret_cast<const D4*>(soup + (size_t)pos * kLeafDoubles);
+  const D4 a = ldg256(p), b = ldg256(p + 1);
+  v[0] = {a.x, a.y, a.z};
+  v[1] = {a.w, b.x, b.y};
+  if(NV == 4)
+  {
+    const D4 c = ldg256(p + 2);
+    v[2] = {b.z, b.w, c.x};
+    v[NV - 1] = {c.y, c.z, c.w};
+  }
+  else
+  {
+    v[2] = {b.z, b.w, __ldg(soup + (size_t)pos * kLeafDoubles + 8)};
+  }
 }
 
 // checkCandidate (:636-737) for one (sub-)triangle T
@@ -400,13 +416,10 @@ __global__ void __launch_bounds__(256) gather_soup_kernel(const double* __restri
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if(pos >= nleaves) return;
   const int cell = leaf_nodes[pos];
-  double* o = soup + (size_t)pos * (NV * 3);
-  if(cell >= ncells)
-  {
-    // padding leaf of the N<=1 case: never reached (its box is invalid), keep it finite
-    for(int k = 0; k < NV * 3; ++k) o[k] = 0.0;
-    return;
-  }
+  double* o = soup + (size_t)pos * kLeafDoubles;
+  for(int k = 0; k < kLeafDoubles; ++k) o[k] = 0.0;
+  // a padding leaf of the N<=1 case is never reached (its box is invalid); it stays zero
+  if(cell >= ncells) return;
 #pragma unroll
   for(int k = 0; k < NV; ++k)
   {

@@ -28,16 +28,30 @@
 
 namespace axb
 {
-// oriented bound of one child: rows of `axis` are (nearly) orthonormal; the subtree's vertices satisfy
-// lo[k] <= axis[k] . x <= hi[k].  128 bytes = one L2 line.
-struct alignas(32) Obb
+// What the fast traversal keeps per CHILD of an inner node: the centroid of the child's AABB (the
+// reference orders children by it, LinearBVH.hpp:72-85; precomputed with the reference's own
+// 0.5*(min+max)) and an oriented bound: unit axes n, t1 (t2 = n x t1 is recomputed), and the extent
+// lo[k] <= axis_k . x <= hi[k] of every vertex below the child.  Large subtrees (no useful
+// orientation) and invalid boxes use the coordinate axes, i.e. the oriented bound IS the AABB.
+struct ChildBound
 {
-  double axis[3][3];
+  double cen[3];
+  double n[3];
+  double t1[3];
   double lo[3];
   double hi[3];
-  double pad_;
 };
-static_assert(sizeof(Obb) == 128, "Obb must be one 128-byte line");
+
+// Traversal record of the fast path: everything one inner-node visit needs in ONE aligned 256-byte
+// read (8 x LDG.256 per lane).  The reference-layout view for getTraverser() and the reference-order
+// kernel keep using Node<>.
+struct alignas(32) SdNode
+{
+  int32_t child[2];  // >= 0 inner node, < 0 leaf -(sorted_pos+1)
+  double pad_;
+  ChildBound cb[2];  // 2 x 120 B
+};
+static_assert(sizeof(SdNode) == 256, "SdNode is 8 x 32 B");
 
 constexpr int kObbMaxRange = 4096;  // subtrees with more leaves keep only their AABB (top ~9 levels)
 
@@ -61,40 +75,45 @@ __device__ __forceinline__ double warp_max(double v)
 }
 
 // One warp per tree entity e: e < inner -> inner node e (leaves node_range[e]), else leaf e - inner.
-// obb[e] bounds everything below entity e.
+// The oriented bound of entity e is stored in its PARENT's record (slot = which child it is); the warp
+// of an inner entity also copies that node's child AABBs and ids into its own record.
 template <int NV>
-__global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict__ soup, const int2* __restrict__ node_range, int nleaves,
-                                                         Obb* __restrict__ obb)
+__global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
+                                                         const int32_t* __restrict__ leaf_parent, const int2* __restrict__ node_range,
+                                                         int nleaves, SdNode* __restrict__ sdn)
 {
   const int inner = nleaves - 1;
   const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if(e >= inner + nleaves) return;
   const int lane = (int)lane_id();
-  int first, last;
+  int first, last, link;
   if(e < inner)
   {
     const int2 r = node_range[e];
     first = r.x;
     last = r.y;
+    link = nodes[e].parent;
+    if(lane < 2) sdn[e].child[lane] = nodes[e].child[lane];
   }
   else
   {
     first = last = e - inner;
+    link = leaf_parent[first];
   }
-  Obb o;
-  if(last - first + 1 > kObbMaxRange)
+  if(link < 0) return;  // the root is nobody's child
+  ChildBound* out = &sdn[link >> 1].cb[link & 1];
+  const Box<double, 3> bb = nodes[link >> 1].box[link & 1];  // this entity's AABB as the reference has it
+  const bool valid = box_valid(bb);
+  if(lane < 3) out->cen[lane] = 0.5 * (bb.lo[lane] + bb.hi[lane]);
+  if(!valid || last - first + 1 > kObbMaxRange)
   {
-    // no oriented bound: gaps evaluate to 0, the AABB decides
-    if(lane == 0)
+    // coordinate axes: the bound is the AABB itself (an invalid box is (max, lowest): infinitely far)
+    if(lane < 3)
     {
-      for(int k = 0; k < 3; ++k)
-      {
-        for(int c = 0; c < 3; ++c) o.axis[k][c] = 0.0;
-        o.lo[k] = -DBL_MAX;
-        o.hi[k] = DBL_MAX;
-      }
-      o.pad_ = 0.0;
-      obb[e] = o;
+      out->n[lane] = lane == 0 ? 1.0 : 0.0;
+      out->t1[lane] = lane == 1 ? 1.0 : 0.0;
+      out->lo[lane] = bb.lo[lane];
+      out->hi[lane] = bb.hi[lane];
     }
     return;
   }
@@ -160,38 +179,36 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
   }
   if(lane == 0)
   {
+    out->n[0] = n.x;
+    out->n[1] = n.y;
+    out->n[2] = n.z;
+    out->t1[0] = t1.x;
+    out->t1[1] = t1.y;
+    out->t1[2] = t1.z;
 #pragma unroll
     for(int k = 0; k < 3; ++k)
     {
-      o.axis[k][0] = A[k].x;
-      o.axis[k][1] = A[k].y;
-      o.axis[k][2] = A[k].z;
       // pad by the rounding of the projections (a few ulp of the coordinate magnitude)
       const double pad = 1e-14 * (fabs(lo[k]) + fabs(hi[k])) + 1e-300;
-      o.lo[k] = lo[k] - pad;
-      o.hi[k] = hi[k] + pad;
+      out->lo[k] = lo[k] - pad;
+      out->hi[k] = hi[k] + pad;
     }
-    o.pad_ = 0.0;
-    obb[e] = o;
   }
 }
 
-// squared distance lower bound from q to the oriented box (FMA is fine here: it only has to be a bound)
-__device__ __forceinline__ double obb_sqdist(const Obb* __restrict__ ob, const double* q)
+// squared distance lower bound from q to the oriented box of a child, c = the 15 doubles of its
+// ChildBound (FMA is fine here: it only has to be a bound; t2 must be the build's n x t1, bit for bit)
+__device__ __forceinline__ double obb_sqdist(const double* c, const double* q)
 {
+  const V3 n {c[3], c[4], c[5]}, t1 {c[6], c[7], c[8]};
+  const V3 t2 = v3cross(n, t1);
+  const V3 A[3] = {n, t1, t2};
   double s = 0.0;
-  const double2* p = reinterpret_cast<const double2*>(ob);
-  // 15 doubles as 8 x 16-byte loads: axis[0..2][0..2], lo[0..2], hi[0..2]
-  const double2 a0 = __ldg(p + 0), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3), a4 = __ldg(p + 4), a5 = __ldg(p + 5),
-                a6 = __ldg(p + 6), a7 = __ldg(p + 7);
-  const double ax[3][3] = {{a0.x, a0.y, a1.x}, {a1.y, a2.x, a2.y}, {a3.x, a3.y, a4.x}};
-  const double lo[3] = {a4.y, a5.x, a5.y};
-  const double hi[3] = {a6.x, a6.y, a7.x};
 #pragma unroll
   for(int k = 0; k < 3; ++k)
   {
-    const double d = fma(ax[k][0], q[0], fma(ax[k][1], q[1], ax[k][2] * q[2]));
-    const double g = fmax(fmax(lo[k] - d, d - hi[k]), 0.0);
+    const double d = fma(A[k].x, q[0], fma(A[k].y, q[1], A[k].z * q[2]));
+    const double g = fmax(fmax(c[9 + k] - d, d - c[12 + k]), 0.0);
     s = fma(g, g, s);
   }
   return s;
@@ -206,118 +223,356 @@ __device__ __forceinline__ double prune_threshold(double minSq)
   return d * d * (1.0 + 1e-12) + 1e-300;
 }
 
-// MODE 1 kernel: one thread per query, queries taken in Morton order (perm), reference-ordered DFS
-// with a (node, lower bound) stack so stale entries are dropped without touching memory.
-template <int NV>
-__global__ void __launch_bounds__(128) sd_fast_kernel(const Node<double, 3>* __restrict__ nodes, const Obb* __restrict__ obb,
-                                                       const double* __restrict__ soup, int nleaves, SdParams prm, Desc<3> qpts, int npts,
-                                                       const int32_t* __restrict__ perm, double* __restrict__ phi, double* __restrict__ cps,
-                                                       double* __restrict__ nrms, unsigned long long* __restrict__ work)
-{
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if(t >= npts) return;
-  const int qi = perm ? perm[t] : t;
-  const double qp[3] = {ld_comp<double>(qpts, 0, qi), ld_comp<double>(qpts, 1, qi), ld_comp<double>(qpts, 2, qi)};
-  const V3 q {qp[0], qp[1], qp[2]};
-  MinCand m;
-  m.minSq = DBL_MAX;
-  m.minPt = {0.0, 0.0, 0.0};
-  m.sumN = {0.0, 0.0, 0.0};
-  m.minType = -1;
-  m.minPos = 0;
-  m.minSub = 0;
-  const bool cn = prm.compute_sign != 0;
-  const int inner = nleaves - 1;
-  double thr = DBL_MAX;
-  unsigned nleaf = 0, ninner = 0;
+//------------------------------------------------------------------------------------------
+// Lazy pseudo-normal: checkCandidate (:636-737) adds a normal contribution whenever a candidate on a
+// shared feature becomes (or ties with) the minimum; every later new minimum usually clears the sum
+// again.  The contributions cost a sqrt, a division and (vertices) an acos each, so the traversal only
+// RECORDS who contributed since the last clear, in order, and the sum is formed once at the end --
+// same terms, same order, same rounding as the reference's running sum.
+//------------------------------------------------------------------------------------------
+constexpr int kContribCap = 8;
 
-  int32_t st_node[kStackSize];
-  float st_d2[kStackSize];
-  int sp = 0;
-  int32_t cur = 0;  // root
-  while(true)
+struct Contribs
+{
+  int32_t pos[kContribCap];
+  int8_t code[kContribCap];  // (sub << 3) | (loc + 3)
+  int n;
+};
+
+template <int NV>
+__device__ __noinline__ V3 contrib_flush(const double* __restrict__ soup, Contribs& cl, V3 sumN)
+{
+  for(int i = 0; i < cl.n; ++i)
   {
-    int32_t next = kBarrier;
-    if(cur < 0)
+    V3 v[NV];
+    load_leaf<NV>(soup, cl.pos[i], v);
+    const int sub = cl.code[i] >> 3, loc = (cl.code[i] & 7) - 3;
+    const V3 T[3] = {v[0], sub == 0 ? v[1] : v[2], sub == 0 ? v[2] : v[NV - 1]};
+    const V3 n = v3cross(v3sub(T[1], T[0]), v3sub(T[2], T[0]));  // Triangle::normal :98-102
+    if(loc < 0)
     {
-      // ---- leaf: the reference's checkCandidate, then tighten the threshold ----
-      ++nleaf;
-      check_leaf<NV>(soup, q, m, -cur - 1, cn);
-      thr = prune_threshold(m.minSq);
+      sumN = v3add(sumN, v3unit(n));  // edge: += normal().unitVector() (:703)
     }
     else
     {
-      // ---- inner node ----
-      ++ninner;
-      const Node<double, 3>& nd = nodes[cur];
-      int32_t child[2] = {nd.child[0], nd.child[1]};
-      const Box<double, 3> bx[2] = {nd.box[0], nd.box[1]};
-      double d2[2];
-      bool in[2];
-#pragma unroll
-      for(int s = 0; s < 2; ++s)
+      const double area = 0.5 * sqrt(v3dot(n, n));  // Triangle::area :105-109
+      if(!nearly_eq(area, 0.0, 1.0e-12))            // !degenerate() :326-330
       {
-        double v = DBL_MAX;
-        bool ok = box_valid(bx[s]);  // bvh_traverse.hpp:95-96: invalid boxes are never entered
-        if(ok)
-        {
-          v = sqdist_point_box(qp, bx[s]);
-          ok = v <= thr;
-          if(ok)
-          {
-            const int e = child[s] >= 0 ? child[s] : inner + (-child[s] - 1);
-            v = fmax(v, obb_sqdist(obb + e, qp));
-            ok = v <= thr;
-          }
-        }
-        d2[s] = v;
-        in[s] = ok;
-      }
-      // Child order = the reference's (LinearBVH.hpp:72-85): when both children are entered, the one whose
-      // AABB centroid is nearer goes first and the other waits on the stack -- leaf or not -- until
-      // everything below the first is done.  The leaves this kernel evaluates are then a SUBSEQUENCE of
-      // the reference's own visiting order, so strict-< tie-breaks between equidistant triangles and the
-      // summation order of the pseudo-normal are the reference's.
-      if(in[0] && in[1])
-      {
-        double dl = 0.0, dr = 0.0;
-#pragma unroll
-        for(int d = 0; d < 3; ++d)
-        {
-          const double cl = 0.5 * (bx[0].lo[d] + bx[0].hi[d]) - qp[d];
-          dl += cl * cl;
-          const double cr = 0.5 * (bx[1].lo[d] + bx[1].hi[d]) - qp[d];
-          dr += cr * cr;
-        }
-        const int first = dl > dr ? 1 : 0;
-        next = child[first];
-        st_node[sp] = child[first ^ 1];
-        st_d2[sp] = __double2float_rd(d2[first ^ 1]);
-        ++sp;
-      }
-      else if(in[0])
-      {
-        next = child[0];
-      }
-      else if(in[1])
-      {
-        next = child[1];
+        const double alpha = tri_angle(T, loc);
+        sumN = v3add(sumN, v3mul(v3unit(n), alpha));  // vertex: += angle(loc)*normal().unitVector() (:722-728)
       }
     }
-    // ---- pop until an entry still beats the threshold (stale entries cost no memory access) ----
-    while(next == kBarrier && sp > 0)
+  }
+  cl.n = 0;
+  return sumN;
+}
+
+// checkCandidate (:636-737) for one (sub-)triangle with the normal contribution deferred
+template <int NV>
+__device__ __forceinline__ void check_triangle_lazy(const double* __restrict__ soup, const V3& q, MinCand& m, Contribs& cl, const V3* T,
+                                                     int pos, int sub, bool computeNormal)
+{
+  constexpr double EPS = 1e-12;
+  int loc;
+  const V3 cp = closest_point_tri(q, T[0], T[1], T[2], loc, EPS);
+  const V3 dq = v3sub(cp, q);
+  const double sq = v3dot(dq, dq);
+  const int type = loc_type(loc);
+  const bool shared = (type != 2);
+  const V3 dm = v3sub(m.minPt, cp);
+  const bool same_spot = (m.minType == type) && nearly_eq(v3dot(dm, dm), 0., EPS);
+  bool upd;
+  if(sq < m.minSq)
+  {
+    const bool clear = !shared || !same_spot;
+    m.minSq = sq;
+    m.minPt = cp;
+    m.minType = type;
+    m.minPos = pos;
+    m.minSub = sub;
+    if(computeNormal && clear)
+    {
+      m.sumN = {0.0, 0.0, 0.0};
+      cl.n = 0;
+    }
+    upd = computeNormal && shared;
+  }
+  else
+  {
+    upd = computeNormal && shared && same_spot;
+  }
+  if(upd)
+  {
+    if(cl.n == kContribCap) m.sumN = contrib_flush<NV>(soup, cl, m.sumN);
+    cl.pos[cl.n] = pos;
+    cl.code[cl.n] = (int8_t)((sub << 3) | (loc + 3));
+    ++cl.n;
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void check_leaf_lazy(const double* __restrict__ soup, const V3& q, MinCand& m, Contribs& cl, int pos,
+                                                 bool computeNormal)
+{
+  V3 v[NV];
+  load_leaf<NV>(soup, pos, v);
+  {
+    const V3 T[3] = {v[0], v[1], v[2]};
+    check_triangle_lazy<NV>(soup, q, m, cl, T, pos, 0, computeNormal);
+  }
+  if(NV == 4)
+  {
+    const V3 T[3] = {v[0], v[2], v[NV - 1]};  // quads split (0,1,2),(0,2,3) :652-658
+    check_triangle_lazy<NV>(soup, q, m, cl, T, pos, 1, computeNormal);
+  }
+}
+
+//------------------------------------------------------------------------------------------
+// MODE 1 kernel.  One query per LANE, but the warp is scheduled as a unit:
+//   * persistent warps pull Morton-ordered queries from a global cursor and a lane that finishes its
+//     query is refilled at once, so no lane idles behind the slowest query of its warp;
+//   * a lane that reaches a leaf does not evaluate it on the spot: it queues it (FIFO, so the leaf ORDER
+//     of the lane is unchanged) and keeps walking inner nodes; the warp switches to "leaf steps" when
+//     enough lanes have a leaf waiting, so closest_point() runs with most lanes active instead of 2-3;
+//   * finished lanes are finalised (pseudo-normal, sign, stores) a few at a time for the same reason.
+// Each lane still walks the tree in the reference's child order with a (node, lower bound) stack, so
+// everything said in the header about bit-identical results holds.
+//------------------------------------------------------------------------------------------
+constexpr int kPend = 4;         // queued leaves per lane
+constexpr int kLeafVote = 16;    // lanes with a queued leaf that trigger a leaf step
+constexpr int kFinishVote = 4;   // finished lanes that trigger a finalisation step
+constexpr int kQueryChunk = 32;  // queries a warp takes from the cursor at a time
+
+template <int NV>
+__global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup, SdParams prm,
+                                                       Desc<3> qpts, int npts, const int32_t* __restrict__ perm, double* __restrict__ phi,
+                                                       double* __restrict__ cps, double* __restrict__ nrms,
+                                                       unsigned long long* __restrict__ work, unsigned int* __restrict__ cursor)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  const unsigned lane = lane_id();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const bool cn = prm.compute_sign != 0;
+
+  // ---- per-lane query state ----
+  int qi = -1;  // original index of the lane's query, -1 = lane is free
+  double qp[3] = {0.0, 0.0, 0.0};
+  MinCand m;
+  Contribs cl;
+  cl.n = 0;
+  double thr = DBL_MAX;
+  unsigned long long st[kStackSize];  // (lower bound as float bits) << 32 | node id: one 8-byte access per push / pop
+  int sp = 0;
+  int32_t cur = kBarrier;  // node in hand: >= 0 inner, < 0 leaf, kBarrier = traversal finished
+  float cur_lb = 0.f;
+  int32_t pend_id[kPend];
+  float pend_lb[kPend];
+  int npend = 0;
+  unsigned nleaf = 0, ninner = 0;
+
+  // ---- the warp's share of the query stream ----
+  unsigned wbase = 0, wcount = 0;
+  bool exhausted = false;
+
+  auto pop = [&]() {
+    cur = kBarrier;
+    while(sp > 0)
     {
       --sp;
-      if((double)st_d2[sp] <= thr) next = st_node[sp];
+      const unsigned long long e = st[sp];
+      const float lb = __uint_as_float((unsigned)(e >> 32));
+      if((double)lb <= thr)
+      {
+        cur = (int32_t)(unsigned)(e & 0xffffffffull);
+        cur_lb = lb;
+        break;
+      }
     }
-    if(next == kBarrier) break;
-    cur = next;
+  };
+
+  while(true)
+  {
+    // ---- refill free lanes ----
+    const unsigned freem = __ballot_sync(FULL, qi < 0);
+    if(freem != 0u && !exhausted)
+    {
+      if(wcount == 0u)
+      {
+        unsigned b = 0;
+        if(lane == 0) b = atomicAdd(cursor, (unsigned)kQueryChunk);
+        wbase = __shfl_sync(FULL, b, 0);
+        wcount = wbase < (unsigned)npts ? min((unsigned)kQueryChunk, (unsigned)npts - wbase) : 0u;
+        exhausted = (wcount == 0u);
+      }
+      if(wcount != 0u)
+      {
+        const unsigned rank = __popc(freem & lt_mask);
+        if(qi < 0 && rank < wcount)
+        {
+          const unsigned t = wbase + rank;
+          qi = perm ? perm[t] : (int)t;
+          qp[0] = ld_comp<double>(qpts, 0, qi);
+          qp[1] = ld_comp<double>(qpts, 1, qi);
+          qp[2] = ld_comp<double>(qpts, 2, qi);
+          m.minSq = DBL_MAX;
+          m.minPt = {0.0, 0.0, 0.0};
+          m.sumN = {0.0, 0.0, 0.0};
+          m.minType = -1;
+          m.minPos = 0;
+          m.minSub = 0;
+          cl.n = 0;
+          thr = DBL_MAX;
+          sp = 0;
+          cur = 0;  // root
+          cur_lb = 0.f;
+          npend = 0;
+        }
+        const unsigned taken = min((unsigned)__popc(freem), wcount);
+        wbase += taken;
+        wcount -= taken;
+      }
+    }
+    const bool busy = qi >= 0;
+    const unsigned busym = __ballot_sync(FULL, busy);
+    if(busym == 0u)
+    {
+      if(exhausted) break;
+      continue;
+    }
+    const bool finished = busy && cur == kBarrier && npend == 0;
+    const bool want_inner = busy && cur != kBarrier && !(cur < 0 && npend == kPend);
+    const bool want_leaf = busy && npend > 0;
+    const unsigned mfin = __ballot_sync(FULL, finished);
+    const unsigned minner = __ballot_sync(FULL, want_inner);
+    const unsigned mleaf = __ballot_sync(FULL, want_leaf);
+    const unsigned mfull = __ballot_sync(FULL, busy && npend == kPend);
+
+    if(__popc(mfin) >= kFinishVote || (mfin != 0u && minner == 0u && mleaf == 0u))
+    {
+      // ---- finalisation step: pseudo-normal, sign, distance, outputs ----
+      if(finished)
+      {
+        if(cl.n) m.sumN = contrib_flush<NV>(soup, cl, m.sumN);
+        const V3 q {qp[0], qp[1], qp[2]};
+        sd_finish<NV>(soup, prm, q, m, qi, phi, cps, nrms);
+        qi = -1;
+      }
+      continue;
+    }
+    if(__popc(mleaf) >= kLeafVote || mfull != 0u || minner == 0u)
+    {
+      // ---- leaf step: every lane with a queued leaf evaluates its oldest one ----
+      if(want_leaf)
+      {
+        const int32_t id = pend_id[0];
+        const float lb = pend_lb[0];
+#pragma unroll
+        for(int k = 0; k + 1 < kPend; ++k)
+        {
+          pend_id[k] = pend_id[k + 1];
+          pend_lb[k] = pend_lb[k + 1];
+        }
+        --npend;
+        if((double)lb <= thr)
+        {
+          ++nleaf;
+          const V3 q {qp[0], qp[1], qp[2]};
+          check_leaf_lazy<NV>(soup, q, m, cl, -id - 1, cn);
+          thr = prune_threshold(m.minSq);
+        }
+      }
+      continue;
+    }
+    // ---- inner step ----
+    if(want_inner)
+    {
+      // a leaf in hand joins the queue; what follows it on the stack comes into hand
+      while(cur < 0 && cur != kBarrier && npend < kPend)
+      {
+#pragma unroll
+        for(int k = 0; k < kPend; ++k)
+          if(k == npend)
+          {
+            pend_id[k] = cur;
+            pend_lb[k] = cur_lb;
+          }
+        ++npend;
+        pop();
+      }
+      if(cur >= 0)
+      {
+        ++ninner;
+        const D4* rec = reinterpret_cast<const D4*>(nodes + cur);
+        double a[32];
+#pragma unroll
+        for(int k = 0; k < 8; ++k)
+        {
+          const D4 r = ldg256(rec + k);
+          a[4 * k + 0] = r.x;
+          a[4 * k + 1] = r.y;
+          a[4 * k + 2] = r.z;
+          a[4 * k + 3] = r.w;
+        }
+        const long long ids = __double_as_longlong(a[0]);
+        const int32_t child0 = (int32_t)(ids & 0xffffffffll), child1 = (int32_t)(ids >> 32);
+        // an invalid box is infinitely far (bvh_traverse.hpp:95-96)
+        const double d20 = obb_sqdist(a + 2, qp), d21 = obb_sqdist(a + 17, qp);
+        const bool in0 = d20 <= thr, in1 = d21 <= thr;
+        // Child order = the reference's (LinearBVH.hpp:72-85): when both children are entered, the one whose
+        // AABB centroid is nearer goes first and the other waits on the stack -- leaf or not -- until
+        // everything below the first is done.  The leaves a lane evaluates are then a SUBSEQUENCE of the
+        // reference's own visiting order, so strict-< tie-breaks between equidistant triangles and the
+        // summation order of the pseudo-normal are the reference's.
+        if(in0 && in1)
+        {
+          double dl = 0.0, dr = 0.0;
+#pragma unroll
+          for(int d = 0; d < 3; ++d)
+          {
+            const double cl_ = a[2 + d] - qp[d];
+            dl += cl_ * cl_;
+            const double cr_ = a[17 + d] - qp[d];
+            dr += cr_ * cr_;
+          }
+          const bool right_first = dl > dr;
+          const int32_t c_second = right_first ? child0 : child1;
+          const double d_second = right_first ? d20 : d21;
+          st[sp] = ((unsigned long long)__float_as_uint(__double2float_rd(d_second)) << 32) | (unsigned)c_second;
+          ++sp;
+          cur = right_first ? child1 : child0;
+          cur_lb = __double2float_rd(right_first ? d21 : d20);
+        }
+        else if(in0)
+        {
+          cur = child0;
+          cur_lb = __double2float_rd(d20);
+        }
+        else if(in1)
+        {
+          cur = child1;
+          cur_lb = __double2float_rd(d21);
+        }
+        else
+        {
+          pop();
+        }
+      }
+    }
   }
-  sd_finish<NV>(soup, prm, q, m, qi, phi, cps, nrms);
   if(work)
   {
-    atomicAdd(&work[0], (unsigned long long)nleaf);
-    atomicAdd(&work[1], (unsigned long long)ninner);
+    unsigned long long a = nleaf, b = ninner;
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+      a += __shfl_xor_sync(FULL, a, o);
+      b += __shfl_xor_sync(FULL, b, o);
+    }
+    if(lane == 0)
+    {
+      atomicAdd(&work[0], a);
+      atomicAdd(&work[1], b);
+    }
   }
 }
 

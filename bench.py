@@ -283,7 +283,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "queries_total": nq_total, "queries_per_gpu": nq_local, "sharding": "z-slabs, BVH replicated",
-                   "l2_policy": "inputs larger than L2 (403 MB of queries per pass)", "mode": "reference-order traversal"},
+                   "l2_policy": "inputs larger than L2 (403 MB of queries per pass)", "mode": "fast mode 1: oriented-bound overlay, Morton-ordered queries, persistent warp-scheduled traversal"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq_local * 24, "d2h_bytes_per_step": nq_local * 8,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
         "gpu_launches": int(launches),
