@@ -58,6 +58,7 @@ SYMBOLS = [
     ("axb_bvh_find_boxes", C.c_int, [_P, _DESC, C.c_int32, _P, _P, C.c_int, _PP, C.POINTER(C.c_int64)]),
     ("axb_bvh_find_rays", C.c_int, [_P, _DESC, C.c_int, C.c_int32, _P, _P, C.c_int, _PP, C.POINTER(C.c_int64)]),
     ("axb_bvh_free_candidates", C.c_int, [_P, _P, C.c_int]),
+    ("axb_bvh_set_find_strategy", C.c_int, [_P, C.c_int]),
     ("axb_bvh_num_leaves", C.c_int, [_P, C.POINTER(C.c_int32)]),
     ("axb_bvh_copy_arrays", C.c_int, [_P, _P, _P, _P, _P]),
     ("axb_bvh_set_profiling", C.c_int, [_P, C.c_int]),

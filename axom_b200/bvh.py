@@ -124,6 +124,10 @@ class BVH:
     def setProfiling(self, enabled):
         check(self._L.axb_bvh_set_profiling(self._h, int(bool(enabled))))
 
+    def setFindStrategy(self, strategy):
+        """0 = one traversal + scatter (default), 1 = count/fill double traversal, 2 = force the overflow path"""
+        check(self._L.axb_bvh_set_find_strategy(self._h, int(strategy)))
+
     def phase_ms(self, name):
         v = C.c_double()
         check(self._L.axb_bvh_get_phase_ms(self._h, name.encode(), C.byref(v)))

@@ -99,6 +99,16 @@ struct Ctx
     AXB_CUDA_TRY(cudaSetDevice(device));
     AXB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     own_stream = true;
+    // keep freed blocks in the device's stream-ordered pool: by default the pool hands memory back to the
+    // driver at every synchronisation, which turns the per-call candidate array into a fresh
+    // multi-hundred-MB allocation each time
+    cudaMemPool_t pool = nullptr;
+    if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool)
+    {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     return AXB_OK;
   }
   void drop_phases()
@@ -281,12 +291,17 @@ struct axb_bvh
   DevBuf ref_inner_nodes, ref_children;       // reference-layout view, built lazily
   bool ref_view_valid = false;
   DevBuf q_stage, q_counts, q_offsets, q_tiles, q_total;
+  DevBuf f_keys_a, f_keys_b, f_scratch, f_perm, f_pairs, f_unused, f_cursor;
+  long long pair_hint[3] = {0, 0, 0};  // candidates found by the last find* call of each kind (sizes the pair buffer)
+  int walk_blocks_per_sm = 0;
+  int find_strategy = 0;  // 0 = single traversal + scatter (default), 1 = the reference's count / fill double traversal
 
   void release_all()
   {
     cudaStream_t s = ctx.stream;
     for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &node_range, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &ref_inner_nodes,
-                     &ref_children, &q_stage, &q_counts, &q_offsets, &q_tiles, &q_total})
+                     &ref_children, &q_stage, &q_counts, &q_offsets, &q_tiles, &q_total, &f_keys_a, &f_keys_b, &f_scratch, &f_perm, &f_pairs,
+                     &f_unused, &f_cursor})
       b->release(s);
   }
 };
@@ -420,7 +435,7 @@ int exclusive_scan(axb_bvh* h, const int32_t* counts, int nq, int32_t* offsets, 
 
 // LinearBVH::findCandidatesImpl (policy/LinearBVH.hpp:271-402): count -> scan -> allocate -> fill
 template <int D, class Query>
-int find_impl(axb_bvh* h, const axb_array_desc* prims, int flags, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
+int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
               int32_t** candidates, int64_t* total)
 {
   using T = double;
@@ -453,25 +468,109 @@ int find_impl(axb_bvh* h, const axb_array_desc* prims, int flags, int32_t nq, in
   long long* d_total = h->q_total.as<long long>();
   const Node<T, D>* nodes = h->nodes.as<Node<T, D>>();
   const T tol = (T)h->tol;
-  {
-    ScopedPhase ph(ctx, "find.count");
-    AXB_LAUNCH(ctx, (count_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, q, nq, tol, flags, (const int32_t*)nullptr, d_counts);
-  }
-  {
-    ScopedPhase ph(ctx, "find.scan");
-    AXB_TRY(exclusive_scan(h, d_counts, nq, d_offsets, d_total));
-  }
   long long htotal = 0;
-  AXB_CUDA_TRY(cudaMemcpyAsync(&htotal, d_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx.stream));
-  AXB_TRY(ctx.sync());
-  if(htotal > 2147483647LL)
-    return fail(AXB_ERR_OVERFLOW, "candidate total " + std::to_string(htotal) + " overflows int32 offsets: split the query batch");
   int32_t* d_cand = nullptr;
-  AXB_CUDA_TRY(cudaMallocAsync((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+  if(h->find_strategy == 1)
   {
+    // the reference's shape: count -> scan -> fill, one thread per query (LinearBVH.hpp:302-364)
+    {
+      ScopedPhase ph(ctx, "find.count");
+      AXB_LAUNCH(ctx, (count_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, q, nq, tol, flags, (const int32_t*)nullptr, d_counts);
+    }
+    {
+      ScopedPhase ph(ctx, "find.scan");
+      AXB_TRY(exclusive_scan(h, d_counts, nq, d_offsets, d_total));
+    }
+    AXB_CUDA_TRY(cudaMemcpyAsync(&htotal, d_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_TRY(ctx.sync());
+    if(htotal > 2147483647LL)
+      return fail(AXB_ERR_OVERFLOW, "candidate total " + std::to_string(htotal) + " overflows int32 offsets: split the query batch");
+    AXB_CUDA_TRY(cudaMallocAsync((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+    {
+      ScopedPhase ph(ctx, "find.fill");
+      AXB_LAUNCH(ctx, (fill_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, h->leaf_nodes.as<int32_t>(), q, nq, tol, flags,
+                 (const int32_t*)nullptr, d_offsets, d_cand);
+    }
+  }
+  else
+  {
+    // ---- Morton order of the queries (processing order only) ----
+    const int32_t* perm = nullptr;
+    if(nq >= 8192)
+    {
+      ScopedPhase ph(ctx, "find.sortq");
+      const size_t kb = sizeof(unsigned long long) * (size_t)nq;
+      AXB_TRY(h->f_keys_a.reserve(kb, ctx.stream));
+      AXB_TRY(h->f_keys_b.reserve(kb, ctx.stream));
+      AXB_TRY(h->f_perm.reserve(sizeof(int32_t) * (size_t)nq, ctx.stream));
+      const size_t scratch = rsort::scratch_bytes(nq);
+      AXB_TRY(h->f_scratch.reserve(scratch, ctx.stream));
+      AXB_CUDA_TRY(cudaMemsetAsync(h->f_scratch.p, 0, scratch, ctx.stream));
+      uint32_t* ghist = h->f_scratch.as<uint32_t>();
+      uint32_t* tile_counters = ghist + rsort::MAX_PASSES * rsort::RADIX;
+      uint32_t* lookback = tile_counters + 64;
+      AXB_LAUNCH(ctx, (find_query_keys_kernel<T, D, Query, BuildState<T, D>>), capped_grid(nq, 256), 256, q, nq,
+                 h->state.as<BuildState<T, D>>(), h->f_keys_a.as<unsigned long long>(), ghist);
+      unsigned long long* sorted = nullptr;
+      AXB_TRY(sort_keys_generic(ctx, h->f_keys_a.as<unsigned long long>(), h->f_keys_b.as<unsigned long long>(), nq, ghist, tile_counters,
+                                lookback, &sorted));
+      AXB_LAUNCH(ctx, keys_to_perm_kernel, blocks_for(nq, 256), 256, sorted, nq, h->f_perm.as<int32_t>());
+      perm = h->f_perm.as<int32_t>();
+    }
+    // ---- pair buffer: sized from the last call of this kind, at least 4 hits per query ----
+    const long long want_pairs = std::max<long long>(4LL * nq + 65536, h->pair_hint[kind] + h->pair_hint[kind] / 4 + 65536);
+    // every resident warp can strand one partly filled chunk
+    if(h->walk_blocks_per_sm == 0)
+    {
+      int bps = 0;
+      AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, find_walk_kernel<T, D, Query>, 128, 0));
+      h->walk_blocks_per_sm = std::max(1, std::min(bps, 8));
+    }
+    int sms = kNumSMsB200;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
+    const int grid = (int)std::min<long long>(blocks_for(nq, 128), (long long)sms * h->walk_blocks_per_sm);
+    unsigned max_chunks = (unsigned)std::min<long long>((want_pairs + kPairChunk - 1) / kPairChunk + 4LL * grid, 0x7fffffffLL / kPairChunk);
+    if(h->find_strategy == 2) max_chunks = 2;  // test hook: force the overflow fallback
+    AXB_TRY(h->f_pairs.reserve(sizeof(int4) * (size_t)max_chunks * kPairChunk, ctx.stream));
+    AXB_TRY(h->f_unused.reserve(sizeof(unsigned int) * (size_t)max_chunks, ctx.stream));
+    AXB_TRY(h->f_cursor.reserve(sizeof(unsigned int) * 4, ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(h->f_unused.p, 0, sizeof(unsigned int) * (size_t)max_chunks, ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(h->f_cursor.p, 0, sizeof(unsigned int) * 4, ctx.stream));
+    PairBuf pb;
+    pb.pairs = h->f_pairs.as<int4>();
+    pb.cursor = h->f_cursor.as<unsigned int>();
+    pb.unused = h->f_unused.as<unsigned int>();
+    pb.max_chunks = max_chunks;
+    {
+      ScopedPhase ph(ctx, "find.count");  // the one traversal: counts + recorded hits
+      AXB_LAUNCH(ctx, (find_walk_kernel<T, D, Query>), grid, 128, nodes, h->leaf_nodes.as<int32_t>(), q, nq, tol, flags, perm, d_counts, pb);
+    }
+    {
+      ScopedPhase ph(ctx, "find.scan");
+      AXB_TRY(exclusive_scan(h, d_counts, nq, d_offsets, d_total));
+    }
+    unsigned int hcur[4] = {0, 0, 0, 0};
+    AXB_CUDA_TRY(cudaMemcpyAsync(&htotal, d_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(hcur, h->f_cursor.p, sizeof(hcur), cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_TRY(ctx.sync());
+    if(htotal > 2147483647LL)
+      return fail(AXB_ERR_OVERFLOW, "candidate total " + std::to_string(htotal) + " overflows int32 offsets: split the query batch");
+    h->pair_hint[kind] = htotal;
+    AXB_CUDA_TRY(cudaMallocAsync((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
     ScopedPhase ph(ctx, "find.fill");
-    AXB_LAUNCH(ctx, (fill_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, h->leaf_nodes.as<int32_t>(), q, nq, tol, flags,
-               (const int32_t*)nullptr, d_offsets, d_cand);
+    if(hcur[2] == 0u)
+    {
+      const unsigned nchunks = std::min(hcur[1], max_chunks);
+      if(nchunks)
+        AXB_LAUNCH(ctx, scatter_pairs_kernel, blocks_for((long long)nchunks * kPairChunk, 256), 256, pb.pairs, pb.unused, nchunks, d_offsets,
+                   d_cand);
+    }
+    else
+    {
+      // the pair buffer was too small for this call: second traversal, as the reference does
+      AXB_LAUNCH(ctx, (fill_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, h->leaf_nodes.as<int32_t>(), q, nq, tol, flags,
+                 (const int32_t*)nullptr, d_offsets, d_cand);
+    }
   }
   ctx.phase_end(tot);
   if(out_memspace == AXB_MEM_HOST)
@@ -651,16 +750,16 @@ int axb_bvh_find_points(axb_bvh* h, const axb_array_desc* pts, int32_t nq, int32
                         int32_t** candidates, int64_t* total)
 {
   if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
-  return h->ndims == 2 ? find_impl<2, PointQuery<double, 2>>(h, pts, 0, nq, offsets, counts, out_memspace, candidates, total)
-                       : find_impl<3, PointQuery<double, 3>>(h, pts, 0, nq, offsets, counts, out_memspace, candidates, total);
+  return h->ndims == 2 ? find_impl<2, PointQuery<double, 2>>(h, 0, pts, 0, nq, offsets, counts, out_memspace, candidates, total)
+                       : find_impl<3, PointQuery<double, 3>>(h, 0, pts, 0, nq, offsets, counts, out_memspace, candidates, total);
 }
 
 int axb_bvh_find_boxes(axb_bvh* h, const axb_array_desc* boxes, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
                        int32_t** candidates, int64_t* total)
 {
   if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
-  return h->ndims == 2 ? find_impl<2, BoxQuery<double, 2>>(h, boxes, 0, nq, offsets, counts, out_memspace, candidates, total)
-                       : find_impl<3, BoxQuery<double, 3>>(h, boxes, 0, nq, offsets, counts, out_memspace, candidates, total);
+  return h->ndims == 2 ? find_impl<2, BoxQuery<double, 2>>(h, 1, boxes, 0, nq, offsets, counts, out_memspace, candidates, total)
+                       : find_impl<3, BoxQuery<double, 3>>(h, 1, boxes, 0, nq, offsets, counts, out_memspace, candidates, total);
 }
 
 int axb_bvh_find_rays(axb_bvh* h, const axb_array_desc* rays, int rays_normalized, int32_t nq, int32_t* offsets, int32_t* counts,
@@ -668,8 +767,8 @@ int axb_bvh_find_rays(axb_bvh* h, const axb_array_desc* rays, int rays_normalize
 {
   if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
   const int f = rays_normalized ? 1 : 0;
-  return h->ndims == 2 ? find_impl<2, RayQuery<double, 2>>(h, rays, f, nq, offsets, counts, out_memspace, candidates, total)
-                       : find_impl<3, RayQuery<double, 3>>(h, rays, f, nq, offsets, counts, out_memspace, candidates, total);
+  return h->ndims == 2 ? find_impl<2, RayQuery<double, 2>>(h, 2, rays, f, nq, offsets, counts, out_memspace, candidates, total)
+                       : find_impl<3, RayQuery<double, 3>>(h, 2, rays, f, nq, offsets, counts, out_memspace, candidates, total);
 }
 
 int axb_bvh_free_candidates(axb_bvh* h, int32_t* candidates, int memspace)
@@ -724,6 +823,14 @@ int axb_bvh_copy_arrays(axb_bvh* h, uint32_t* mcodes, int32_t* leaf_nodes, doubl
                                    ctx.stream));
   }
   return ctx.sync();
+}
+
+int axb_bvh_set_find_strategy(axb_bvh* h, int strategy)
+{
+  if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(strategy < 0 || strategy > 2) return fail(AXB_ERR_BAD_ARG, "find strategy must be 0, 1 or 2");
+  h->find_strategy = strategy;
+  return AXB_OK;
 }
 
 int axb_bvh_set_profiling(axb_bvh* h, int e)

@@ -308,9 +308,9 @@ __device__ __forceinline__ Box<T, D> load_box_cg(const Box<T, D>* src)
 
 // K5+K7+K8: reorder (:199-219) + propagate_aabbs (:505-576) + the box half of emit.
 // One thread per leaf in sorted order.  A thread arriving at inner node p stores its box in
-// p's child slot (the final traversal layout), fences, and bumps p's counter; the first
-// arrival retires, the second reads the sibling slot, unions and climbs.  The atomicAdd +
-// __threadfence pair replaces the reference's atomicExch-store / volatile-poll workaround
+// p's child slot (the final traversal layout) and bumps p's counter with an acq_rel atomic; the
+// first arrival retires, the second reads the sibling slot, unions and climbs.  The single
+// acquire-release RMW replaces the reference's atomicExch-store / volatile-poll workaround
 // (:391-484); unions are exact min/max, so the result does not depend on arrival order.
 template <typename T, int D>
 __global__ void __launch_bounds__(256) refit_kernel(Desc<2 * D> boxes, int n, int n_real, T half_scale,
@@ -333,10 +333,11 @@ __global__ void __launch_bounds__(256) refit_kernel(Desc<2 * D> boxes, int n, in
     const int p = link >> 1;
     const int side = link & 1;
     store_box_cg(&nodes[p].box[side], aabb);
-    __threadfence();
-    const uint32_t old = atomicAdd(&nodes[p].counter, 1u);
+    // one release RMW per arrival publishes the box just stored; the second arrival reads the sibling
+    // slot with L2 loads (ld.cg) that are control-dependent on the RMW result, so no acquire fence is needed
+    uint32_t old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(&nodes[p].counter) : "memory");
     if(old == 0u) return;  // first arrival retires (:547-551)
-    __threadfence();
     const Box<T, D> other = load_box_cg(&nodes[p].box[side ^ 1]);
     box_add(aabb, other);  // aabb.addBox(other_aabb) (:567)
     link = nodes[p].parent;

@@ -95,6 +95,11 @@ struct PointQuery
 #pragma unroll
     for(int k = 0; k < D; ++k) p[k] = ld_comp<T>(d, k, i);
   }
+  __device__ __forceinline__ void center(T* c) const
+  {
+#pragma unroll
+    for(int k = 0; k < D; ++k) c[k] = p[k];
+  }
   __device__ __forceinline__ bool operator()(const Box<T, D>& bb) const
   {
     bool in = true;
@@ -111,6 +116,11 @@ struct BoxQuery
   static constexpr int NCOMP = 2 * D;
   Box<T, D> b;
   __device__ __forceinline__ void load(const Desc<NCOMP>& d, long long i, T /*tol*/, int /*flags*/) { b = load_box<T, D>(d, i); }
+  __device__ __forceinline__ void center(T* c) const
+  {
+#pragma unroll
+    for(int k = 0; k < D; ++k) c[k] = static_cast<T>(0.5 * (b.lo[k] + b.hi[k]));
+  }
   __device__ __forceinline__ bool operator()(const Box<T, D>& bb) const
   {
     bool hit = true;
@@ -128,6 +138,7 @@ struct RayQuery
   static constexpr int NCOMP = 2 * D;
   T o[D];
   T dir[D];
+  T inv[D];  // 1/dir[k]: a pure function of the ray, so hoisting it out of the box test changes nothing
   T tol;
   __device__ __forceinline__ void load(const Desc<NCOMP>& d, long long i, T tol_, int normalized)
   {
@@ -157,6 +168,13 @@ struct RayQuery
         for(int k = 1; k < D; ++k) dir[k] = (T)0;
       }
     }
+#pragma unroll
+    for(int k = 0; k < D; ++k) inv[k] = (T)1.0 / dir[k];
+  }
+  __device__ __forceinline__ void center(T* c) const
+  {
+#pragma unroll
+    for(int k = 0; k < D; ++k) c[k] = o[k];
   }
   __device__ __forceinline__ bool operator()(const Box<T, D>& bb) const
   {
@@ -172,7 +190,7 @@ struct RayQuery
       }
       else
       {
-        const T invn = (T)1.0 / dir[k];
+        const T invn = inv[k];
         T t1 = (bb.lo[k] - o[k]) * invn;
         T t2 = (bb.hi[k] - o[k]) * invn;
         if(t1 > t2)
@@ -223,6 +241,262 @@ __global__ void __launch_bounds__(256) fill_kernel(const Node<T, D>* __restrict_
   int off = offsets[qi];
   traverse_reference_order<T, D>(
     nodes, q, [&](int pos) { candidates[off++] = __ldg(leaf_nodes + pos); }, NoOrder {});
+}
+
+//------------------------------------------------------------------------------------------
+// SINGLE-TRAVERSAL candidate search.
+//
+// The reference walks the tree twice (count, then fill; LinearBVH.hpp:302-364).  Here one walk counts
+// AND records every hit as a (query, rank, candidate) triple in a chunked pair buffer; after the scan a
+// flat scatter kernel drops candidate k of query q at candidates[offsets[q] + k].  rank is the hit's
+// position in the query's own DFS order, so the per-query ORDER of the reference is preserved.
+//   * persistent warps pull queries (optionally in Morton order, `perm`) from a device cursor and a lane
+//     that finishes is refilled at once;
+//   * hits of the lanes that sit on a leaf in the same step are compacted by ballot + prefix into the
+//     warp's current chunk; chunks (kPairChunk triples) are reserved with ONE atomic each, and only a
+//     warp's last chunk can be partly filled (its slack is recorded in `unused`);
+//   * if the buffer runs out the walk keeps counting and sets `overflow`; the host then falls back to
+//     the classic fill traversal (fill_kernel) for this call and sizes the buffer better next time.
+//------------------------------------------------------------------------------------------
+constexpr int kPairChunk = 1024;
+constexpr int kFindQueryChunk = 32;
+
+struct PairBuf
+{
+  int4* pairs;              // .x query  .y rank  .z candidate (original box id)
+  unsigned int* cursor;     // [0] next query chunk  [1] next pair chunk  [2] overflow flag
+  unsigned int* unused;     // per pair chunk: slots left empty at the end (0 for full chunks)
+  unsigned int max_chunks;  // capacity of `pairs` in chunks (0 = recording disabled)
+};
+
+template <typename T, int D>
+__device__ __forceinline__ void load_node_boxes(const Node<T, D>* __restrict__ nodes, int32_t i, Box<T, D>& L, Box<T, D>& R, int32_t& lc,
+                                                int32_t& rc)
+{
+  const Node<T, D>& nd = nodes[i];
+  L = nd.box[0];
+  R = nd.box[1];
+  lc = nd.child[0];
+  rc = nd.child[1];
+}
+// 3-D double: the 128-byte record as four 256-bit loads
+template <>
+__device__ __forceinline__ void load_node_boxes<double, 3>(const Node<double, 3>* __restrict__ nodes, int32_t i, Box<double, 3>& L,
+                                                            Box<double, 3>& R, int32_t& lc, int32_t& rc)
+{
+  const D4* p = reinterpret_cast<const D4*>(nodes + i);
+  const D4 a = ldg256(p), b = ldg256(p + 1), c = ldg256(p + 2), d = ldg256(p + 3);
+  L.lo[0] = a.x;
+  L.lo[1] = a.y;
+  L.lo[2] = a.z;
+  L.hi[0] = a.w;
+  L.hi[1] = b.x;
+  L.hi[2] = b.y;
+  R.lo[0] = b.z;
+  R.lo[1] = b.w;
+  R.lo[2] = c.x;
+  R.hi[0] = c.y;
+  R.hi[1] = c.z;
+  R.hi[2] = c.w;
+  const long long ids = __double_as_longlong(d.x);
+  lc = (int32_t)(ids & 0xffffffffll);
+  rc = (int32_t)(ids >> 32);
+}
+
+template <typename T, int D, class Query>
+__global__ void __launch_bounds__(128) find_walk_kernel(const Node<T, D>* __restrict__ nodes, const int32_t* __restrict__ leaf_nodes,
+                                                         Desc<Query::NCOMP> prims, int nq, T tol, int flags,
+                                                         const int32_t* __restrict__ perm, int32_t* __restrict__ counts, PairBuf pb)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  const unsigned lane = lane_id();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int qi = -1;
+  Query q;
+  int32_t todo[kStackSize];
+  int sp = 0;
+  int32_t cur = kBarrier;
+  int cnt = 0;
+  unsigned wbase = 0, wcount = 0;
+  bool exhausted = false;
+  // the warp's pair chunk: [ppos, pend) are free slots of chunk pchunk
+  unsigned pchunk = 0xffffffffu, ppos = 0, pend = 0;
+  bool recording = pb.max_chunks != 0u;
+
+  while(true)
+  {
+    // ---- refill free lanes ----
+    const unsigned freem = __ballot_sync(FULL, qi < 0);
+    if(freem != 0u && !exhausted)
+    {
+      if(wcount == 0u)
+      {
+        unsigned b = 0;
+        if(lane == 0) b = atomicAdd(pb.cursor, (unsigned)kFindQueryChunk);
+        wbase = __shfl_sync(FULL, b, 0);
+        wcount = wbase < (unsigned)nq ? min((unsigned)kFindQueryChunk, (unsigned)nq - wbase) : 0u;
+        exhausted = (wcount == 0u);
+      }
+      if(wcount != 0u)
+      {
+        const unsigned rank = __popc(freem & lt_mask);
+        if(qi < 0 && rank < wcount)
+        {
+          const unsigned t = wbase + rank;
+          qi = perm ? perm[t] : (int)t;
+          q.load(prims, qi, tol, flags);
+          sp = 0;
+          cur = 0;  // root
+          cnt = 0;
+        }
+        const unsigned taken = min((unsigned)__popc(freem), wcount);
+        wbase += taken;
+        wcount -= taken;
+      }
+    }
+    const bool busy = qi >= 0;
+    if(__ballot_sync(FULL, busy) == 0u)
+    {
+      if(exhausted) break;
+      continue;
+    }
+    // ---- lanes that hold a leaf: record the hit (ballot + prefix into the warp's chunk), then pop ----
+    const bool at_leaf = busy && cur < 0 && cur != kBarrier;
+    const unsigned leafm = __ballot_sync(FULL, at_leaf);
+    if(leafm != 0u)
+    {
+      int32_t cand = 0;
+      if(at_leaf) cand = __ldg(leaf_nodes + (-cur - 1));
+      if(recording)
+      {
+        unsigned n = __popc(leafm);
+        unsigned my = __popc(leafm & lt_mask);  // rank of this lane among the recording lanes
+        unsigned done = 0;
+        while(done < n)
+        {
+          if(ppos == pend)
+          {
+            unsigned c = 0;
+            if(lane == 0) c = atomicAdd(pb.cursor + 1, 1u);
+            c = __shfl_sync(FULL, c, 0);
+            if(c >= pb.max_chunks)
+            {
+              if(lane == 0) atomicExch(pb.cursor + 2, 1u);
+              recording = false;
+              pchunk = 0xffffffffu;
+              break;
+            }
+            pchunk = c;
+            ppos = c * (unsigned)kPairChunk;
+            pend = ppos + (unsigned)kPairChunk;
+          }
+          const unsigned room = pend - ppos;
+          const unsigned take = min(room, n - done);
+          if(at_leaf && my >= done && my < done + take) pb.pairs[ppos + (my - done)] = make_int4(qi, cnt, cand, 0);
+          ppos += take;
+          done += take;
+        }
+      }
+    }
+    if(at_leaf)
+    {
+      ++cnt;
+      cur = sp > 0 ? todo[--sp] : kBarrier;
+    }
+    // ---- lanes that hold an inner node: the reference's step (bvh_traverse.hpp:86-123), left child first ----
+    else if(busy && cur >= 0)
+    {
+      Box<T, D> L, R;
+      int32_t lc, rc;
+      load_node_boxes<T, D>(nodes, cur, L, R, lc, rc);
+      const bool inL = box_valid(L) ? q(L) : false;
+      const bool inR = box_valid(R) ? q(R) : false;
+      if(inL && inR)
+      {
+        todo[sp++] = rc;
+        cur = lc;
+      }
+      else if(inL)
+      {
+        cur = lc;
+      }
+      else if(inR)
+      {
+        cur = rc;
+      }
+      else
+      {
+        cur = sp > 0 ? todo[--sp] : kBarrier;
+      }
+    }
+    // ---- finished lanes publish their count and become free ----
+    if(busy && cur == kBarrier)
+    {
+      counts[qi] = cnt;
+      qi = -1;
+    }
+  }
+  if(pchunk != 0xffffffffu && lane == 0) pb.unused[pchunk] = pend - ppos;
+}
+
+// candidates[offsets[q] + rank] = candidate, one thread per recorded slot
+__global__ void __launch_bounds__(256) scatter_pairs_kernel(const int4* __restrict__ pairs, const unsigned int* __restrict__ unused,
+                                                             unsigned int nchunks, const int32_t* __restrict__ offsets,
+                                                             int32_t* __restrict__ candidates)
+{
+  const unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned chunk = (unsigned)(slot / kPairChunk);
+  if(chunk >= nchunks) return;
+  const unsigned in_chunk = (unsigned)(slot % kPairChunk);
+  if(in_chunk >= (unsigned)kPairChunk - unused[chunk]) return;
+  const int4 p = pairs[slot];
+  candidates[(long long)offsets[p.x] + p.y] = p.z;
+}
+
+// Morton keys of the queries' reference points over the BVH bounds (centroid of a box, origin of a ray):
+// (code << 32) | index, for radix_sort.cuh.  Only the processing ORDER depends on it.
+template <typename T, int D, class Query, class State>
+__global__ void __launch_bounds__(256) find_query_keys_kernel(Desc<Query::NCOMP> prims, int nq, const State* __restrict__ st,
+                                                               unsigned long long* __restrict__ keys, uint32_t* __restrict__ ghist)
+{
+  __shared__ uint32_t sh[rsort::MAX_PASSES * rsort::RADIX];
+  for(int i = threadIdx.x; i < rsort::MAX_PASSES * rsort::RADIX; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  T mn[D], inv[D];
+#pragma unroll
+  for(int d = 0; d < D; ++d)
+  {
+    mn[d] = st->bmin[d];
+    inv[d] = st->inv_extent[d];
+  }
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x)
+  {
+    Query q;
+    q.load(prims, i, (T)0, 1);
+    T c[D];
+    q.center(c);
+    uint32_t qd[D];
+    constexpr int bits = 32 / D;
+#pragma unroll
+    for(int d = 0; d < D; ++d)
+    {
+      T v = (c[d] - mn[d]) * inv[d] * (T)(1 << bits);
+      v = v > (T)0 ? v : (T)0;  // also maps NaN to 0
+      v = v < (T)((1 << bits) - 1) ? v : (T)((1 << bits) - 1);
+      qd[d] = (uint32_t)(int32_t)v;
+    }
+    uint32_t code;
+    if(D == 2)
+      code = spread_bits_2d(qd[0]) | (spread_bits_2d(qd[1]) << 1);
+    else
+      code = spread_bits_3d(qd[0]) | (spread_bits_3d(qd[1]) << 1) | (spread_bits_3d(qd[D - 1]) << 2);
+    keys[i] = ((unsigned long long)code << 32) | (unsigned long long)(uint32_t)i;
+#pragma unroll
+    for(int p = 0; p < rsort::MAX_PASSES; ++p) atomicAdd(&sh[p * rsort::RADIX + ((code >> (p * 8)) & 255u)], 1u);
+  }
+  __syncthreads();
+  for(int i = threadIdx.x; i < rsort::MAX_PASSES * rsort::RADIX; i += blockDim.x)
+    if(sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
 //------------------------------------------------------------------------------------------

@@ -4,8 +4,10 @@
 Workload (BASELINE.json configs[1], "C2"): quest::SignedDistance on a synthetic 2M-triangle
 icosphere (geodesic frequency 316 -> 1 997 120 triangles, radius 0.5, watertight, signs on)
 evaluated on the 256^3 uniform grid spanning [-1,1]^3.  With N GPUs the grid is sharded by
-contiguous z-slabs (one process per GPU, surface BVH replicated and built per GPU, no data-path
-collective); total work is fixed, so scaling is "strong".
+z-planes dealt round-robin (plane k goes to rank k mod N: planes near the sphere's centre cost more
+than the outer ones, so contiguous slabs would leave the outer ranks idle); one process per GPU,
+surface BVH replicated and built per GPU, no data-path collective; total work is fixed, so scaling
+is "strong".
 
 A "step" is one computeDistances() pass over the rank's shard.
   value : whole-job points/s with queries and results resident in HBM (CUDA events, max over ranks)
@@ -46,6 +48,15 @@ def sublattice(step):
     ax = grid_axis()[::step]
     zz, yy, xx = np.meshgrid(ax, ax, ax, indexing="ij")
     return np.ascontiguousarray(np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1))
+
+
+def ncu_profile_summary():
+    """dram traffic of the distance kernel from the committed ncu capture (profiles/), if any"""
+    p = os.path.join(ROOT, "profiles", "sd_fast_kernel_ncu.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -192,8 +203,8 @@ def run_ours(args):
 
     # ---- this rank's z-slab of the 256^3 grid, generated on the device ----
     ax = torch.from_numpy(grid_axis()).to(dev)
-    k0, k1 = (GRID * rank) // world, (GRID * (rank + 1)) // world
-    zz, yy, xx = torch.meshgrid(ax[k0:k1], ax, ax, indexing="ij")
+    planes = torch.arange(rank, GRID, world, device=dev)  # z-planes dealt round-robin
+    zz, yy, xx = torch.meshgrid(ax[planes], ax, ax, indexing="ij")
     q_d = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=1).contiguous()
     del zz, yy, xx
     nq_local = q_d.shape[0]
@@ -263,16 +274,28 @@ def run_ours(args):
                 "traffic": None, "kernel": "signed-distance query kernel", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "latency/FP64-pipe bound traversal: see fp64 for the arithmetic side"}
+    prof = ncu_profile_summary()
+    if prof:
+        roofline["traffic"] = prof.get("dram_bytes_per_launch")
+        roofline["traffic_source"] = prof.get("source")
     flops = 80.0 * leaf_tests + 50.0 * inner_visits  # SURVEY.md 8(d) convention
     fp64 = {"leaf_tests_per_query": leaf_tests / nq_local, "inner_visits_per_query": inner_visits / nq_local,
-            "gflops_survey_convention": flops / (kernel_ms * 1e-3) / 1e9}
+            "gflops_survey_convention": flops / (kernel_ms * 1e-3) / 1e9,
+            "frac_of_nominal_fp64_peak": flops / (kernel_ms * 1e-3) / 37.2e12,
+            "nominal_fp64_peak": "37.2 TFLOP/s = 148 SMs x 64 DFMA/clk x 1.965 GHz (not in MEASURED_PEAKS.json)"}
+    # what actually bounds the kernel (ncu): L1 sector throughput of divergent node-record reads --
+    # every lane reads its own 256-byte record, 8 sectors per visit, 1 sector/clk/SM
+    sectors = nq_local * (8.0 * inner_visits / nq_local + 3.0 * leaf_tests / nq_local)
+    l1 = {"sector_requests_per_launch": sectors, "achieved_gsectors_per_s": sectors / (kernel_ms * 1e-3) / 1e9,
+          "peak_gsectors_per_s": 148 * 1.965, "frac": sectors / (kernel_ms * 1e-3) / 1e9 / (148 * 1.965),
+          "note": "1 x 32-B sector per clock per SM for uncoalesced loads (measured: l1tex throughput 83 % in profiles/r1c)"}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample, checked against the GPU result ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         step = 2 if args.cpu_sample == "large" else 4
         rate, info = cpu_reference_rate(x, y, z, conn, step)
-        sub = phi_d.reshape(GRID, GRID, GRID)[::step, ::step, ::step].reshape(-1).cpu().numpy()
+        sub = phi_d.reshape(GRID, GRID, GRID)[::step, ::step, ::step].reshape(-1).cpu().numpy()  # world == 1: all planes
         cpu = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                "sample": "%d^3 sub-lattice (i,j,k = 0 mod %d) of the %d^3 grid, %d points, OpenMP over queries, %.1f s" % (
                    GRID // step, step, GRID, info["npts"], info["seconds"][0]),
@@ -282,7 +305,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "queries_total": nq_total, "queries_per_gpu": nq_local, "sharding": "z-slabs, BVH replicated",
+        "config": {"workload": WORKLOAD, "queries_total": nq_total, "queries_per_gpu": nq_local, "sharding": "z-planes round-robin over ranks, BVH replicated per GPU",
                    "l2_policy": "inputs larger than L2 (403 MB of queries per pass)", "mode": "fast mode 1: oriented-bound overlay, Morton-ordered queries, persistent warp-scheduled traversal"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq_local * 24, "d2h_bytes_per_step": nq_local * 8,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
@@ -290,6 +313,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "fp64": fp64,
+        "l1": l1,
         "cpu_baseline": cpu,
         "build_ms": build_ms, "build_phases_ms": build_phases, "setmesh_wall_ms": setmesh_wall_ms,
         "build_roofline": {"bound": "hbm", "achieved": 156.0 * ntri / (build_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",

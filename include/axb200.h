@@ -133,6 +133,14 @@ int axb_bvh_find_boxes(axb_bvh* bvh, const axb_array_desc* boxes, int32_t num_qu
 int axb_bvh_find_rays(axb_bvh* bvh, const axb_array_desc* rays, int rays_normalized, int32_t num_queries, int32_t* offsets,
                       int32_t* counts, int out_memspace, int32_t** candidates, int64_t* total);
 int axb_bvh_free_candidates(axb_bvh* bvh, int32_t* candidates, int memspace);
+/* How find* produces the candidate lists (results are identical, including per-query order):
+ *   0 (default) one traversal that counts and records (query, rank, candidate) hits in a chunked
+ *               buffer, exclusive scan, flat scatter; queries are processed in Morton order;
+ *   1           the reference's shape, count -> scan -> fill with two traversals, one thread per query
+ *               (policy/LinearBVH.hpp:302-364);
+ *   2           as 0 with a deliberately tiny hit buffer, which forces the overflow path (second
+ *               traversal) -- a test hook. */
+int axb_bvh_set_find_strategy(axb_bvh* bvh, int strategy);
 
 /* Parity / debugging: copy the build artefacts to HOST buffers (any may be NULL).
  *   mcodes[n]          sorted 32-bit Morton codes        (RadixTree::m_mcodes)
@@ -144,7 +152,7 @@ int axb_bvh_copy_arrays(axb_bvh* bvh, uint32_t* mcodes, int32_t* leaf_nodes, dou
 /* Device time (ms, CUDA events on the handle's stream) of the phases of the calls made since
  * profiling was (re-)enabled: the MEAN over those calls.  Enabling profiling resets the record.
  * names: "build.total" "build.bounds" "build.morton" "build.sort" "build.tree" "build.refit"
- *        "find.total" "find.count" "find.scan" "find.fill" "find.sortq"                   */
+ *        "find.total" "find.sortq" "find.count" (the traversal) "find.scan" "find.fill" (scatter)                   */
 int axb_bvh_set_profiling(axb_bvh* bvh, int enabled);
 int axb_bvh_get_phase_ms(const axb_bvh* bvh, const char* name, double* ms);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */

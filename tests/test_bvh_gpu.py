@@ -87,6 +87,26 @@ def test_find_queries_bit_exact(oracle, ndims, n):
     assert _same(ref.find_rays(o, d, False), gpu.findRays(o, d, normalized=True))
 
 
+@pytest.mark.parametrize("strategy", [0, 1, 2])
+def test_find_strategies_large_batches(oracle, strategy):
+    """enough queries for the Morton-sorted path (>= 8192); strategy 0 = single traversal + scatter,
+    1 = the reference's count/fill double traversal, 2 = forced overflow of the hit buffer (fallback).
+    All three must reproduce the reference's offsets / counts / candidates exactly, order included."""
+    boxes = synth.triangle_aabbs(60000, seed=77)
+    ref, gpu = _check_build(oracle, boxes, 3)
+    gpu.setFindStrategy(strategy)
+    pts = synth.random_points(50000, seed=3)
+    pts[:100] += 5.0  # outside the tree bounds
+    assert _same(ref.find_points(pts), gpu.findPoints(pts))
+    qb = synth.triangle_aabbs(20000, seed=78)
+    qb[:, 3:] += 0.05  # fat query boxes: tens of candidates each
+    assert _same(ref.find_boxes(qb), gpu.findBoundingBoxes(qb))
+    o, d = synth.random_rays(12000, seed=79, lo=-0.2, hi=1.2)
+    assert _same(ref.find_rays(o, d, True), gpu.findRays(o, d))
+    # second call re-uses the sized buffers
+    assert _same(ref.find_boxes(qb), gpu.findBoundingBoxes(qb))
+
+
 def test_find_device_resident(oracle):
     import torch
     boxes = synth.triangle_aabbs(30000, seed=21)

@@ -1,0 +1,216 @@
+#!/usr/bin/env python3
+"""Measure the BASELINE.json configs that are NOT bench.py's headline line (C1, C3, C4, C5).
+
+    python tools/bench_configs.py c1|c3|c4|c5 [--scale S] [--steps K]
+    python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py c5      (N-way partitioned surface)
+
+Prints one JSON line per config with the same vocabulary as bench.py (value / roofline / cpu_baseline).
+`--scale` shrinks the sizes (scale 0.1 -> 10x fewer boxes and queries) for quick runs.
+The CPU baseline legs use oracle/ (test infrastructure) on a bounded sample, like bench.py.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def device_time_ms(fn, steps, warmup=2):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def find_config(name, args):
+    import torch
+    from axom_b200 import BVH, synth
+    from oracle import oracle as O
+    dev = torch.device("cuda", 0)
+    hbm, src = peaks()
+    if name == "c1":
+        n = q = int(1_000_000 * args.scale)
+        boxes = synth.triangle_aabbs(n, seed=12345)
+        prim = synth.random_points(q, seed=12346)
+        kind, P, label = "points", 24, "C1: spin::BVH<3> build over %d triangle AABBs + findPoints for %d random points" % (n, q)
+    elif name == "c3":
+        n = q = int(10_000_000 * args.scale)
+        h = float(n) ** (-1.0 / 3.0)
+        boxes = synth.triangle_aabbs(n, seed=12345)
+        prim = synth.triangle_aabbs(q, seed=54321, shift=(h / 2, h / 2, h / 2))
+        kind, P, label = "boxes", 48, "C3: findBoundingBoxes, two %d-triangle meshes (B shifted by h/2)" % n
+    else:  # c4
+        freq = max(2, int(round(1000 * args.scale ** 0.5)))
+        x, y, z, conn = synth.icosphere(freq)
+        boxes = synth.mesh_cell_boxes(x, y, z, conn)
+        n = len(boxes)
+        q = int(100_000_000 * args.scale)
+        o, d = synth.random_rays(q, seed=777)
+        prim = np.ascontiguousarray(np.concatenate([o, d], axis=1))
+        kind, P, label = "rays", 48, "C4: findRays, %d rays vs %d-triangle icosphere (freq %d), chunks of <= 16M rays" % (q, n, freq)
+    boxes_d = torch.from_numpy(boxes).to(dev)
+    b = BVH(3)
+    b.initialize(boxes_d)
+    b.setProfiling(True)
+    for _ in range(3):
+        b.initialize(boxes_d)
+    build_ms = b.phase_ms("build.total")
+    build_ph = {k: round(b.phase_ms("build." + k), 4) for k in ("bounds", "morton", "sort", "tree", "refit")}
+    fn = {"points": b.findPoints, "boxes": b.findBoundingBoxes, "rays": lambda r: b.findRays(r, normalized=False)}[kind]
+    chunk = 16_000_000
+    chunks = [torch.from_numpy(prim[i:i + chunk]).to(dev) for i in range(0, q, chunk)]
+
+    def step():
+        tot = 0
+        for c in chunks:
+            off, cnt, cand = fn(c)
+            tot += cand.numel()
+        return tot
+
+    step()
+    b.setProfiling(True)
+    ms, total = device_time_ms(step, args.steps)
+    ph = {k: round(b.phase_ms("find." + k), 4) for k in ("total", "sortq", "count", "scan", "fill")}
+    alg_bytes = q * (P + 8) + 4 * total + 108 * n * len(chunks)
+    # CPU baseline: reference SEQ_EXEC build (full size when small) + OpenMP count over a sample of the queries
+    cpu = None
+    if not args.no_cpu:
+        kind_ref = "reference" if O.have_reference() else "port"
+        t0 = time.perf_counter()
+        rb = O.Bvh(boxes, ndims=3, kind=kind_ref)
+        cpu_build_s = time.perf_counter() - t0
+        ns = min(q, 1_000_000)
+        t0 = time.perf_counter()
+        if kind == "points":
+            ctot, _ = rb.count_points_omp(prim[:ns], nthreads=0)
+            cores = O.max_threads(kind_ref)
+        elif kind == "boxes":
+            r = rb.find_boxes(prim[:ns])
+            ctot, cores = len(r[2]), 1
+        else:
+            r = rb.find_rays(prim[:ns, :3], prim[:ns, 3:], True)
+            ctot, cores = len(r[2]), 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": kind_ref,
+               "sample": "%d of the %d queries; SEQ_EXEC build of all %d boxes took %.2f s" % (ns, q, n, cpu_build_s),
+               "build_ms": cpu_build_s * 1e3}
+    line = {
+        "metric": "find%s queries/s; BVH build ms beside it" % kind.capitalize(), "value": q / (ms * 1e-3), "unit": "queries/s",
+        "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label, "boxes": n, "queries": q, "candidates": int(total), "candidates_per_query": total / q},
+        "find_phases_ms_per_call": ph, "build_ms": build_ms, "build_phases_ms": build_ph,
+        "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": alg_bytes, "peak_source": src, "traffic": None},
+        "build_roofline": {"bound": "hbm", "achieved": 156.0 * n / (build_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": 156.0 * n / (build_ms * 1e-3) / 1e9 / hbm},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def c5(args):
+    """distributed closest point: surface split into G Morton ranges (one per rank; 8 sequential partitions
+    when run on one GPU), unsigned distance per partition, elementwise MIN (NCCL all-reduce when G > 1)."""
+    import torch
+    import torch.distributed as dist
+    from axom_b200 import SignedDistance, synth
+    from axom_b200 import dist as D
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    freq = max(2, int(round(1000 * args.scale ** 0.5)))
+    x, y, z, conn = synth.icosphere(freq)
+    q = int(50_000_000 * args.scale)
+    pts = synth.random_points(q, seed=999, lo=-1.0, hi=1.0)
+    parts_total = world if world > 1 else 8
+    P = np.stack([x, y, z], 1)
+    cen = P[conn].mean(axis=1)
+    parts = D.morton_partition(cen, parts_total)
+    mine = [rank] if world > 1 else list(range(parts_total))
+    qd = torch.from_numpy(pts).to(dev)
+    sds = [SignedDistance(x, y, z, conn[parts[p]], 3, False, False, device=local) for p in mine]
+    out = torch.empty(q, dtype=torch.float64, device=dev)
+    tmp = torch.empty(q, dtype=torch.float64, device=dev)
+
+    def step():
+        for k, sd in enumerate(sds):
+            sd.computeDistances(qd, out=(out if k == 0 else tmp))
+            if k:
+                torch.minimum(out, tmp, out=out)
+        if world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.MIN)
+        return out
+
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ok = None
+    if rank == 0 and not args.no_check:
+        full = SignedDistance(x, y, z, conn, 3, False, False, device=local)
+        ref, _, _ = full.computeDistances(qd)
+        ok = bool(torch.equal(ref, out))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "distributed closest point queries/s (partitioned surface, MIN-reduce)", "value": q / (ms * 1e-3),
+            "unit": "queries/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64",
+            "data": "synthetic", "scaling": "strong",
+            "config": {"workload": "C5: %d-triangle icosphere split into %d Morton ranges, %d queries on every rank" % (len(conn), parts_total, q),
+                       "collective": "ncclAllReduce(MIN, f64) over %d x 8 B" % q if world > 1 else "none (partitions evaluated sequentially on one GPU)"},
+            "matches_single_bvh_bit_exact": ok}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    if args.config == "c5":
+        c5(args)
+    else:
+        find_config(args.config, args)
+
+
+if __name__ == "__main__":
+    main()
