@@ -30,59 +30,64 @@ class _Keep:
         self.desc, self.refs, self.count, self.device = desc, refs, count, device
 
 
-def make_desc(data, ncomp):
-    """Build an axb_array_desc for AoS (n, ncomp) or SoA (ncomp x (n,)) input on host or device."""
+def make_desc(data, ncomp, dtype=np.float64):
+    """Build an axb_array_desc for AoS (n, ncomp) or SoA (ncomp x (n,)) input on host or device.
+    dtype is the handle's FloatType (float64, or float32 for a BVH created with dtype=np.float32)."""
     d = ArrayDesc()
     d.ncomp = ncomp
+    dtype = np.dtype(dtype)
+    isz = dtype.itemsize
+    tname = "torch." + dtype.name
     if isinstance(data, (tuple, list)):
         if len(data) != ncomp:
             raise ValueError("expected %d component arrays, got %d" % (ncomp, len(data)))
         if all(_is_torch(a) for a in data):
             comps = [a.contiguous() for a in data]
             for a in comps:
-                if not a.is_cuda or str(a.dtype) != "torch.float64" or a.dim() != 1:
-                    raise ValueError("SoA components must be 1-D CUDA float64 tensors")
+                if not a.is_cuda or str(a.dtype) != tname or a.dim() != 1:
+                    raise ValueError("SoA components must be 1-D CUDA %s tensors" % dtype.name)
             n = comps[0].numel()
             for c, a in enumerate(comps):
                 d.comp[c] = a.data_ptr()
-            d.stride_bytes, d.memspace = 8, MEM_DEVICE
+            d.stride_bytes, d.memspace = isz, MEM_DEVICE
             return _Keep(d, comps, n, True)
-        comps = [np.ascontiguousarray(a, np.float64).reshape(-1) for a in data]
+        comps = [np.ascontiguousarray(a, dtype).reshape(-1) for a in data]
         n = comps[0].size
         for c, a in enumerate(comps):
             if a.size != n:
                 raise ValueError("SoA components differ in length")
             d.comp[c] = a.ctypes.data
-        d.stride_bytes, d.memspace = 8, MEM_HOST
+        d.stride_bytes, d.memspace = isz, MEM_HOST
         return _Keep(d, comps, n, False)
     if _is_torch(data):
-        if not data.is_cuda or str(data.dtype) != "torch.float64":
-            raise ValueError("device input must be a CUDA float64 tensor")
+        if not data.is_cuda or str(data.dtype) != tname:
+            raise ValueError("device input must be a CUDA %s tensor" % dtype.name)
         a = data.contiguous().reshape(-1, ncomp)
         base = a.data_ptr()
         for c in range(ncomp):
-            d.comp[c] = base + 8 * c
-        d.stride_bytes, d.memspace = 8 * ncomp, MEM_DEVICE
+            d.comp[c] = base + isz * c
+        d.stride_bytes, d.memspace = isz * ncomp, MEM_DEVICE
         return _Keep(d, [a], a.shape[0], True)
-    a = np.ascontiguousarray(data, np.float64).reshape(-1, ncomp)
+    a = np.ascontiguousarray(data, dtype).reshape(-1, ncomp)
     base = a.ctypes.data
     for c in range(ncomp):
-        d.comp[c] = base + 8 * c
-    d.stride_bytes, d.memspace = 8 * ncomp, MEM_HOST
+        d.comp[c] = base + isz * c
+    d.stride_bytes, d.memspace = isz * ncomp, MEM_HOST
     return _Keep(d, [a], a.shape[0], False)
 
 
 class BVH:
-    """spin::BVH<NDIMS, B200, double>."""
+    """spin::BVH<NDIMS, B200_EXEC, FloatType>; dtype = np.float64 (default) or np.float32."""
 
-    def __init__(self, ndims=3, device=0, _borrowed=None):
+    def __init__(self, ndims=3, device=0, _borrowed=None, dtype=np.float64):
         self._L = _lib.lib()
         self.ndims = ndims
         self.device = device
+        self.dtype = np.dtype(dtype)
         self._owned = _borrowed is None
         if _borrowed is None:
             h = C.c_void_p()
-            check(self._L.axb_bvh_create(C.byref(h), ndims, 8, device))
+            check(self._L.axb_bvh_create(C.byref(h), ndims, self.dtype.itemsize, device))
             self._h = h
         else:
             self._h = _borrowed
@@ -140,7 +145,7 @@ class BVH:
 
     # ---- build (spin/BVH.hpp:424-477) ----
     def initialize(self, boxes, numItems=None):
-        k = make_desc(boxes, 2 * self.ndims)
+        k = make_desc(boxes, 2 * self.ndims, self.dtype)
         n = k.count if numItems is None else int(numItems)
         if n > k.count:
             raise ValueError("numItems exceeds the supplied boxes")
@@ -193,11 +198,11 @@ class BVH:
         return offsets, counts, candidates
 
     def findPoints(self, points, numPts=None):
-        k = make_desc(points, self.ndims)
+        k = make_desc(points, self.ndims, self.dtype)
         return self._find("points", k, k.count if numPts is None else int(numPts))
 
     def findBoundingBoxes(self, boxes, numBoxes=None):
-        k = make_desc(boxes, 2 * self.ndims)
+        k = make_desc(boxes, 2 * self.ndims, self.dtype)
         return self._find("boxes", k, k.count if numBoxes is None else int(numBoxes))
 
     def findRays(self, origins, directions=None, numRays=None, normalized=False):
@@ -205,13 +210,13 @@ class BVH:
         normalized=False applies the primal::Ray constructor's normalisation."""
         D = self.ndims
         if directions is None:
-            k = make_desc(origins, 2 * D)
+            k = make_desc(origins, 2 * D, self.dtype)
         elif _is_torch(origins):
             import torch
-            k = make_desc(torch.cat([origins.reshape(-1, D), directions.reshape(-1, D)], dim=1), 2 * D)
+            k = make_desc(torch.cat([origins.reshape(-1, D), directions.reshape(-1, D)], dim=1), 2 * D, self.dtype)
         else:
-            k = make_desc(np.concatenate([np.asarray(origins, np.float64).reshape(-1, D),
-                                          np.asarray(directions, np.float64).reshape(-1, D)], axis=1), 2 * D)
+            k = make_desc(np.concatenate([np.asarray(origins, self.dtype).reshape(-1, D),
+                                          np.asarray(directions, self.dtype).reshape(-1, D)], axis=1), 2 * D, self.dtype)
         return self._find("rays", k, k.count if numRays is None else int(numRays), extra=(int(bool(normalized)),))
 
     # ---- traverser / parity views ----
@@ -225,11 +230,11 @@ class BVH:
         n = self.numLeaves()
         inner, D = n - 1, self.ndims
         out = dict(mcodes=np.empty(n, np.uint32), leafs=np.empty(n, np.int32),
-                   inner_nodes=np.empty((2 * inner, 2 * D), np.float64), inner_children=np.empty(2 * inner, np.int32))
+                   inner_nodes=np.empty((2 * inner, 2 * D), self.dtype), inner_children=np.empty(2 * inner, np.int32))
         check(self._L.axb_bvh_copy_arrays(self._h, out["mcodes"].ctypes.data, out["leafs"].ctypes.data,
                                           out["inner_nodes"].ctypes.data, out["inner_children"].ctypes.data))
         lo, hi = self.getBounds()
-        out["bounds"] = np.concatenate([lo, hi])
+        out["bounds"] = np.concatenate([lo, hi]).astype(self.dtype)
         return out
 
 

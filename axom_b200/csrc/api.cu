@@ -329,10 +329,9 @@ int sort_keys(axb_bvh* h, int n, uint32_t* ghist, uint32_t* tile_counters, uint3
                            lookback, &h->sorted_keys);
 }
 
-template <int D>
+template <typename T, int D>
 int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
 {
-  using T = double;
   Ctx& ctx = h->ctx;
   AXB_TRY(ctx.bind());
   ctx.begin_call();
@@ -405,10 +404,9 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
   return AXB_BVH_BUILD_OK;
 }
 
-template <int D>
+template <typename T, int D>
 int ensure_ref_view(axb_bvh* h)
 {
-  using T = double;
   if(h->ref_view_valid) return AXB_OK;
   Ctx& ctx = h->ctx;
   const int inner = h->n - 1;
@@ -434,11 +432,10 @@ int exclusive_scan(axb_bvh* h, const int32_t* counts, int nq, int32_t* offsets, 
 }
 
 // LinearBVH::findCandidatesImpl (policy/LinearBVH.hpp:271-402): count -> scan -> allocate -> fill
-template <int D, class Query>
+template <typename T, int D, class Query>
 int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
               int32_t** candidates, int64_t* total)
 {
-  using T = double;
   if(!h->built) return fail(AXB_ERR_NOT_BUILT, "BVH query before initialize()");
   if(nq < 0) return fail(AXB_ERR_BAD_ARG, "negative query count");
   if(!candidates || !total) return fail(AXB_ERR_BAD_ARG, "null output pointer");
@@ -594,6 +591,11 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
 
 bool valid_bvh(const axb_bvh* b) { return b != nullptr; }
 
+// (FloatType, NDIMS) -> template instantiation.  CALL is a macro taking (T, D).
+#define AXB_DISPATCH(h, CALL)                                             \
+  ((h)->fp_bytes == 8 ? ((h)->ndims == 2 ? CALL(double, 2) : CALL(double, 3)) \
+                      : ((h)->ndims == 2 ? CALL(float, 2) : CALL(float, 3)))
+
 }  // namespace
 
 extern "C" {
@@ -632,11 +634,11 @@ int axb_bvh_create(axb_bvh** out, int ndims, int fp_bytes, int device)
   if(!out) return fail(AXB_ERR_BAD_ARG, "null output handle");
   *out = nullptr;
   if(ndims != 2 && ndims != 3) return fail(AXB_ERR_BAD_ARG, "The BVH class may be used only in 2D or 3D.");
-  if(fp_bytes == 4) return fail(AXB_ERR_UNSUPPORTED, "float BVH is not built in this version (double only)");
-  if(fp_bytes != 8) return fail(AXB_ERR_BAD_ARG, "fp_bytes must be 8");
+  if(fp_bytes != 8 && fp_bytes != 4) return fail(AXB_ERR_BAD_ARG, "fp_bytes must be 8 (double) or 4 (float)");
   axb_bvh* h = new axb_bvh();
   h->ndims = ndims;
   h->fp_bytes = fp_bytes;
+  if(fp_bytes == 4) h->tol = FLT_EPSILON;  // DEFAULT_TOLERANCE = floating_point_limits<FloatType>::epsilon()
   int s = h->ctx.init(device);
   if(s != AXB_OK)
   {
@@ -712,10 +714,12 @@ int axb_bvh_initialize(axb_bvh* h, const axb_array_desc* boxes, int32_t n)
   axb_array_desc empty;
   memset(&empty, 0, sizeof(empty));
   empty.ncomp = 2 * h->ndims;
-  empty.stride_bytes = 8;
+  empty.stride_bytes = h->fp_bytes;
   empty.memspace = AXB_MEM_DEVICE;
   const axb_array_desc* d = (n == 0 && !boxes) ? &empty : boxes;
-  return h->ndims == 2 ? build_impl<2>(h, d, n) : build_impl<3>(h, d, n);
+#define AXB_CALL(T, D) build_impl<T, D>(h, d, n)
+  return AXB_DISPATCH(h, AXB_CALL);
+#undef AXB_CALL
 }
 
 int axb_bvh_is_initialized(const axb_bvh* h) { return (h && h->built) ? 1 : 0; }
@@ -736,7 +740,9 @@ int axb_bvh_get_traverser(axb_bvh* h, axb_traverser* out)
   if(!valid_bvh(h) || !out) return fail(AXB_ERR_BAD_ARG, "null argument");
   if(!h->built) return fail(AXB_ERR_NOT_BUILT, "getTraverser() before initialize()");
   AXB_TRY(h->ctx.bind());
-  AXB_TRY(h->ndims == 2 ? ensure_ref_view<2>(h) : ensure_ref_view<3>(h));
+#define AXB_CALL(T, D) ensure_ref_view<T, D>(h)
+  AXB_TRY(AXB_DISPATCH(h, AXB_CALL));
+#undef AXB_CALL
   out->inner_nodes = h->ref_inner_nodes.p;
   out->inner_node_children = h->ref_children.as<int32_t>();
   out->leaf_nodes = h->leaf_nodes.as<int32_t>();
@@ -750,16 +756,18 @@ int axb_bvh_find_points(axb_bvh* h, const axb_array_desc* pts, int32_t nq, int32
                         int32_t** candidates, int64_t* total)
 {
   if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
-  return h->ndims == 2 ? find_impl<2, PointQuery<double, 2>>(h, 0, pts, 0, nq, offsets, counts, out_memspace, candidates, total)
-                       : find_impl<3, PointQuery<double, 3>>(h, 0, pts, 0, nq, offsets, counts, out_memspace, candidates, total);
+#define AXB_CALL(T, D) find_impl<T, D, PointQuery<T, D>>(h, 0, pts, 0, nq, offsets, counts, out_memspace, candidates, total)
+  return AXB_DISPATCH(h, AXB_CALL);
+#undef AXB_CALL
 }
 
 int axb_bvh_find_boxes(axb_bvh* h, const axb_array_desc* boxes, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
                        int32_t** candidates, int64_t* total)
 {
   if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
-  return h->ndims == 2 ? find_impl<2, BoxQuery<double, 2>>(h, 1, boxes, 0, nq, offsets, counts, out_memspace, candidates, total)
-                       : find_impl<3, BoxQuery<double, 3>>(h, 1, boxes, 0, nq, offsets, counts, out_memspace, candidates, total);
+#define AXB_CALL(T, D) find_impl<T, D, BoxQuery<T, D>>(h, 1, boxes, 0, nq, offsets, counts, out_memspace, candidates, total)
+  return AXB_DISPATCH(h, AXB_CALL);
+#undef AXB_CALL
 }
 
 int axb_bvh_find_rays(axb_bvh* h, const axb_array_desc* rays, int rays_normalized, int32_t nq, int32_t* offsets, int32_t* counts,
@@ -767,8 +775,9 @@ int axb_bvh_find_rays(axb_bvh* h, const axb_array_desc* rays, int rays_normalize
 {
   if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
   const int f = rays_normalized ? 1 : 0;
-  return h->ndims == 2 ? find_impl<2, RayQuery<double, 2>>(h, 2, rays, f, nq, offsets, counts, out_memspace, candidates, total)
-                       : find_impl<3, RayQuery<double, 3>>(h, 2, rays, f, nq, offsets, counts, out_memspace, candidates, total);
+#define AXB_CALL(T, D) find_impl<T, D, RayQuery<T, D>>(h, 2, rays, f, nq, offsets, counts, out_memspace, candidates, total)
+  return AXB_DISPATCH(h, AXB_CALL);
+#undef AXB_CALL
 }
 
 int axb_bvh_free_candidates(axb_bvh* h, int32_t* candidates, int memspace)
@@ -794,7 +803,7 @@ int axb_bvh_num_leaves(const axb_bvh* h, int32_t* n)
   return AXB_OK;
 }
 
-int axb_bvh_copy_arrays(axb_bvh* h, uint32_t* mcodes, int32_t* leaf_nodes, double* inner_nodes, int32_t* inner_children)
+int axb_bvh_copy_arrays(axb_bvh* h, uint32_t* mcodes, int32_t* leaf_nodes, void* inner_nodes, int32_t* inner_children)
 {
   if(!valid_bvh(h)) return fail(AXB_ERR_BAD_ARG, "null handle");
   if(!h->built) return fail(AXB_ERR_NOT_BUILT, "BVH not initialized");
@@ -814,9 +823,11 @@ int axb_bvh_copy_arrays(axb_bvh* h, uint32_t* mcodes, int32_t* leaf_nodes, doubl
     AXB_CUDA_TRY(cudaMemcpyAsync(leaf_nodes, h->leaf_nodes.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx.stream));
   if(inner_nodes || inner_children)
   {
-    AXB_TRY(D == 2 ? ensure_ref_view<2>(h) : ensure_ref_view<3>(h));
+#define AXB_CALL(T, D) ensure_ref_view<T, D>(h)
+    AXB_TRY(AXB_DISPATCH(h, AXB_CALL));
+#undef AXB_CALL
     if(inner_nodes)
-      AXB_CUDA_TRY(cudaMemcpyAsync(inner_nodes, h->ref_inner_nodes.p, sizeof(double) * 2 * D * 2 * (size_t)inner, cudaMemcpyDeviceToHost,
+      AXB_CUDA_TRY(cudaMemcpyAsync(inner_nodes, h->ref_inner_nodes.p, (size_t)h->fp_bytes * 2 * D * 2 * (size_t)inner, cudaMemcpyDeviceToHost,
                                    ctx.stream));
     if(inner_children)
       AXB_CUDA_TRY(cudaMemcpyAsync(inner_children, h->ref_children.p, sizeof(int32_t) * 2 * (size_t)inner, cudaMemcpyDeviceToHost,
@@ -871,7 +882,7 @@ struct axb_sd
   int mode = 1;  // 1 = OBB-accelerated, Morton-ordered queries (default); 0 = reference visiting order
   bool count_work = false;
   SdParams prm;
-  DevBuf x, y, z, conn, soup, cell_boxes, obounds, q_stage, out_phi, out_cp, out_n, work;
+  DevBuf x, y, z, conn, offsets, soup, cell_boxes, obounds, q_stage, out_phi, out_cp, out_n, work;
   DevBuf sdnodes, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor;
   int fast_blocks_per_sm = 0;  // occupancy of the persistent query kernel (queried once)
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
@@ -886,8 +897,8 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
 {
   if(!out) return fail(AXB_ERR_BAD_ARG, "null output handle");
   *out = nullptr;
-  if(cell_node_offsets) return fail(AXB_ERR_UNSUPPORTED, "mixed-shape surface meshes are not built in this version");
-  if(nodes_per_cell != 3 && nodes_per_cell != 4) return fail(AXB_ERR_BAD_ARG, "surface cells must be triangles (3) or quads (4)");
+  const bool mixed = cell_node_offsets != nullptr;
+  if(!mixed && nodes_per_cell != 3 && nodes_per_cell != 4) return fail(AXB_ERR_BAD_ARG, "surface cells must be triangles (3) or quads (4)");
   if(nnodes < 0 || ncells < 0) return fail(AXB_ERR_BAD_ARG, "negative mesh size");
   if((nnodes > 0 && (!x || !y || !z)) || (ncells > 0 && !conn)) return fail(AXB_ERR_BAD_ARG, "null mesh array");
   mesh_memspace = resolve_memspace(mesh_memspace, x);
@@ -900,7 +911,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
     return st;
   }
   Ctx& ctx = s->ctx();
-  s->nv = nodes_per_cell;
+  s->nv = mixed ? 4 : nodes_per_cell;  // a mixed mesh uses the 4-vertex leaf records, NaN marks a missing 4th vertex
   s->ncells = ncells;
   s->nnodes = nnodes;
   s->prm.watertight = is_watertight != 0;
@@ -908,7 +919,21 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
   auto body = [&]() -> int {
     ctx.begin_call();
     const cudaMemcpyKind kind = mesh_memspace == AXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    const size_t nb = sizeof(double) * (size_t)nnodes, cb = sizeof(int32_t) * (size_t)ncells * nodes_per_cell;
+    size_t conn_len = (size_t)ncells * (mixed ? 0 : nodes_per_cell);
+    if(mixed)
+    {
+      // the connectivity length is the last offset
+      int32_t last = 0;
+      if(mesh_memspace == AXB_MEM_HOST)
+        last = cell_node_offsets[ncells];
+      else
+        AXB_CUDA_TRY(cudaMemcpy(&last, cell_node_offsets + ncells, sizeof(int32_t), cudaMemcpyDeviceToHost));
+      if(last < 0) return fail(AXB_ERR_BAD_ARG, "negative cell_node_offsets");
+      conn_len = (size_t)last;
+      AXB_TRY(s->offsets.reserve(sizeof(int32_t) * ((size_t)ncells + 1), ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(s->offsets.p, cell_node_offsets, sizeof(int32_t) * ((size_t)ncells + 1), kind, ctx.stream));
+    }
+    const size_t nb = sizeof(double) * (size_t)nnodes, cb = sizeof(int32_t) * conn_len;
     AXB_TRY(s->x.reserve(nb, ctx.stream));
     AXB_TRY(s->y.reserve(nb, ctx.stream));
     AXB_TRY(s->z.reserve(nb, ctx.stream));
@@ -919,7 +944,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       AXB_CUDA_TRY(cudaMemcpyAsync(s->y.p, y, nb, kind, ctx.stream));
       AXB_CUDA_TRY(cudaMemcpyAsync(s->z.p, z, nb, kind, ctx.stream));
     }
-    if(ncells) AXB_CUDA_TRY(cudaMemcpyAsync(s->conn.p, conn, cb, kind, ctx.stream));
+    if(cb) AXB_CUDA_TRY(cudaMemcpyAsync(s->conn.p, conn, cb, kind, ctx.stream));
     // mesh node bounds (m_boxDomain)
     AXB_TRY(s->obounds.reserve(sizeof(unsigned long long) * 6, ctx.stream));
     unsigned long long init[6];
@@ -936,7 +961,20 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
     AXB_CUDA_TRY(cudaMemcpyAsync(hb, s->obounds.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx.stream));
     // per-cell AABBs
     AXB_TRY(s->cell_boxes.reserve(sizeof(Box<double, 3>) * (size_t)std::max(ncells, 1), ctx.stream));
-    if(ncells)
+    DevBuf badflag;
+    if(ncells && mixed)
+    {
+      AXB_TRY(badflag.reserve(sizeof(int), ctx.stream));
+      AXB_CUDA_TRY(cudaMemsetAsync(badflag.p, 0, sizeof(int), ctx.stream));
+      AXB_LAUNCH(ctx, cell_boxes_mixed_kernel, blocks_for(ncells, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
+                 s->conn.as<int32_t>(), s->offsets.as<int32_t>(), ncells, s->cell_boxes.as<Box<double, 3>>(), badflag.as<int>());
+      int hbad = 0;
+      AXB_CUDA_TRY(cudaMemcpyAsync(&hbad, badflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+      AXB_TRY(ctx.sync());
+      badflag.release(ctx.stream);
+      if(hbad) return fail(AXB_ERR_BAD_ARG, "mixed surface mesh has a cell that is neither a triangle nor a quad");
+    }
+    else if(ncells)
     {
       if(s->nv == 3)
         AXB_LAUNCH(ctx, cell_boxes_kernel<3>, blocks_for(ncells, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
@@ -962,7 +1000,10 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
     // leaf geometry in sorted-leaf order
     const int nl = s->bvh->n;
     AXB_TRY(s->soup.reserve(sizeof(double) * kLeafDoubles * (size_t)nl, ctx.stream));
-    if(s->nv == 3)
+    if(mixed)
+      AXB_LAUNCH(ctx, gather_soup_mixed_kernel, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
+                 s->conn.as<int32_t>(), s->offsets.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
+    else if(s->nv == 3)
       AXB_LAUNCH(ctx, gather_soup_kernel<3>, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
                  s->conn.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
     else
@@ -1009,7 +1050,7 @@ int axb_sd_destroy(axb_sd* s)
   {
     cudaSetDevice(s->ctx().device);
     cudaStream_t st = s->ctx().stream;
-    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->soup, &s->cell_boxes, &s->obounds, &s->q_stage, &s->out_phi, &s->out_cp,
+    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->offsets, &s->soup, &s->cell_boxes, &s->obounds, &s->q_stage, &s->out_phi, &s->out_cp,
                      &s->out_n, &s->work, &s->sdnodes, &s->qkeys_a, &s->qkeys_b, &s->qscratch, &s->qperm, &s->qbounds, &s->cursor})
       b->release(st);
     axb_bvh_destroy(s->bvh);

@@ -154,6 +154,10 @@ __device__ __forceinline__ void load_leaf(const double* __restrict__ soup, int p
   }
 }
 
+// In a mixed triangle / quad mesh (UcdMeshData with cell_node_offsets, :44-96) the leaf records are
+// the 4-vertex ones and a triangle cell marks its missing 4th vertex with NaN.
+__device__ __forceinline__ bool has_fourth(const V3& v) { return v.x == v.x; }
+
 // checkCandidate (:636-737) for one (sub-)triangle T
 __device__ __forceinline__ void check_triangle(const V3& q, MinCand& m, const V3* T, int pos, int sub, bool computeNormal)
 {
@@ -210,7 +214,7 @@ __device__ __forceinline__ void check_leaf(const double* __restrict__ soup, cons
     const V3 T[3] = {v[0], v[1], v[2]};
     check_triangle(q, m, T, pos, 0, computeNormal);
   }
-  if(NV == 4)
+  if(NV == 4 && has_fourth(v[NV - 1]))
   {
     const V3 T[3] = {v[0], v[2], v[NV - 1]};  // quads split (0,1,2),(0,2,3) :652-658
     check_triangle(q, m, T, pos, 1, computeNormal);
@@ -405,6 +409,60 @@ __global__ void __launch_bounds__(256) cell_boxes_kernel(const double* __restric
     }
   }
   boxes[c] = bb;
+}
+
+// getCellBoundingBox for a mixed-shape mesh: the cell's nodes are conn[offsets[c] .. offsets[c+1])
+__global__ void __launch_bounds__(256) cell_boxes_mixed_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                                const double* __restrict__ z, const int32_t* __restrict__ conn,
+                                                                const int32_t* __restrict__ offsets, int ncells,
+                                                                Box<double, 3>* __restrict__ boxes, int* __restrict__ bad)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if(c >= ncells) return;
+  const int b = offsets[c], nn = offsets[c + 1] - b;
+  if(nn != 3 && nn != 4) atomicExch(bad, 1);  // SLIC_ASSERT(nnodes <= 4) (:648); only triangles and quads are surfaces
+  Box<double, 3> bb;
+  box_clear(bb);
+  for(int k = 0; k < nn; ++k)
+  {
+    const int nd = conn[b + k];
+    const double p[3] = {x[nd], y[nd], z[nd]};
+#pragma unroll
+    for(int d = 0; d < 3; ++d)
+    {
+      if(p[d] < bb.lo[d]) bb.lo[d] = p[d];
+      if(p[d] > bb.hi[d]) bb.hi[d] = p[d];
+    }
+  }
+  boxes[c] = bb;
+}
+
+__global__ void __launch_bounds__(256) gather_soup_mixed_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                                 const double* __restrict__ z, const int32_t* __restrict__ conn,
+                                                                 const int32_t* __restrict__ offsets, const int32_t* __restrict__ leaf_nodes,
+                                                                 int nleaves, int ncells, double* __restrict__ soup)
+{
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if(pos >= nleaves) return;
+  const int cell = leaf_nodes[pos];
+  double* o = soup + (size_t)pos * kLeafDoubles;
+  for(int k = 0; k < kLeafDoubles; ++k) o[k] = 0.0;
+  if(cell >= ncells) return;
+  const int b = offsets[cell], nn = offsets[cell + 1] - b;
+  for(int k = 0; k < 4; ++k)
+  {
+    if(k < nn)
+    {
+      const int nd = conn[b + k];
+      o[3 * k + 0] = x[nd];
+      o[3 * k + 1] = y[nd];
+      o[3 * k + 2] = z[nd];
+    }
+    else
+    {
+      o[3 * k + 0] = o[3 * k + 1] = o[3 * k + 2] = __longlong_as_double(0x7ff8000000000000ll);  // NaN: no 4th vertex
+    }
+  }
 }
 
 // gather leaf geometry into sorted-leaf order (one-time, at setMesh)

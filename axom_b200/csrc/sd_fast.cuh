@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     V3 v[NV];
     load_leaf<NV>(soup, p, v);
     V3 c = v3cross(v3sub(v[1], v[0]), v3sub(v[2], v[0]));
-    if(NV == 4) c = v3add(c, v3cross(v3sub(v[2], v[0]), v3sub(v[NV - 1], v[0])));
+    if(NV == 4 && has_fourth(v[NV - 1])) c = v3add(c, v3cross(v3sub(v[2], v[0]), v3sub(v[NV - 1], v[0])));
     nx += c.x;
     ny += c.y;
     nz += c.z;
@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
 #pragma unroll
     for(int j = 0; j < NV; ++j)
     {
+      if(j == 3 && !has_fourth(v[j])) continue;  // triangle cell of a mixed mesh
 #pragma unroll
       for(int k = 0; k < 3; ++k)
       {
@@ -320,7 +321,7 @@ __device__ __forceinline__ void check_leaf_lazy(const double* __restrict__ soup,
     const V3 T[3] = {v[0], v[1], v[2]};
     check_triangle_lazy<NV>(soup, q, m, cl, T, pos, 0, computeNormal);
   }
-  if(NV == 4)
+  if(NV == 4 && has_fourth(v[NV - 1]))
   {
     const V3 T[3] = {v[0], v[2], v[NV - 1]};  // quads split (0,1,2),(0,2,3) :652-658
     check_triangle_lazy<NV>(soup, q, m, cl, T, pos, 1, computeNormal);

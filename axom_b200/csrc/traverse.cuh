@@ -152,9 +152,10 @@ struct RayQuery
     if(!normalized)
     {
       // Ray ctor -> Vector::unitVector (primal/geometry/Ray.hpp:122-127, Vector.hpp:477-493)
-      double len2 = 0.0;
+      T acc = (T)0;  // Vector::dot_product accumulates in T (Vector.hpp:543-552), unitVector continues in double
 #pragma unroll
-      for(int k = 0; k < D; ++k) len2 += (double)(dir[k] * dir[k]);
+      for(int k = 0; k < D; ++k) acc += dir[k] * dir[k];
+      const double len2 = (double)acc;
       if(len2 >= 1e-50)
       {
         const double s = 1. / sqrt(len2);  // NumericArray::operator/= (core/NumericArray.hpp:510-514)

@@ -13,22 +13,32 @@ from .bvh import BVH, _is_torch, make_desc
 
 
 class SignedDistance:
-    def __init__(self, x, y, z, cells_to_nodes, nodes_per_cell=3, isWatertight=True, computeSign=True, device=0):
+    def __init__(self, x, y, z, cells_to_nodes, nodes_per_cell=3, isWatertight=True, computeSign=True, device=0,
+                 cell_node_offsets=None):
+        """cell_node_offsets (num_cells+1 int32 offsets into cells_to_nodes) selects a mixed triangle/quad
+        mesh (mint::UnstructuredMesh<MIXED_SHAPE>); nodes_per_cell is then ignored."""
         self._L = _lib.lib()
         self.device = device
         self._h = None
+        po = None
         if _is_torch(x):
             xs = [a.contiguous() for a in (x, y, z)]
             conn = cells_to_nodes.contiguous().reshape(-1)
             px, py, pz, pc = (a.data_ptr() for a in (*xs, conn))
             nn, nc, space = xs[0].numel(), conn.numel() // nodes_per_cell, MEM_DEVICE
+            if cell_node_offsets is not None:
+                offs = cell_node_offsets.contiguous().reshape(-1)
+                po, nc = offs.data_ptr(), offs.numel() - 1
         else:
             xs = [np.ascontiguousarray(a, np.float64).reshape(-1) for a in (x, y, z)]
             conn = np.ascontiguousarray(cells_to_nodes, np.int32).reshape(-1)
             px, py, pz, pc = (a.ctypes.data for a in (*xs, conn))
             nn, nc, space = xs[0].size, conn.size // nodes_per_cell, MEM_HOST
+            if cell_node_offsets is not None:
+                offs = np.ascontiguousarray(cell_node_offsets, np.int32).reshape(-1)
+                po, nc = offs.ctypes.data, offs.size - 1
         h = C.c_void_p()
-        check(self._L.axb_sd_create(C.byref(h), device, px, py, pz, nn, pc, None, nc, nodes_per_cell, space,
+        check(self._L.axb_sd_create(C.byref(h), device, px, py, pz, nn, pc, po, nc, nodes_per_cell, space,
                                     int(bool(isWatertight)), int(bool(computeSign))))
         self._h = h
 

@@ -99,9 +99,10 @@ int axb_device_count(void);
 const char* axb_status_string(int status);
 
 /* ---- spin::BVH ---------------------------------------------------------------------- */
-/* BVH() (spin/BVH.hpp:185).  ndims 2|3, fp_bytes 8 (double; 4 = float is AXB_ERR_UNSUPPORTED
- * in this build), device = CUDA ordinal.  Defaults: scale 1.000123, tolerance DBL_EPSILON
- * (spin/BVH.hpp:410-412). */
+/* BVH() (spin/BVH.hpp:185).  ndims 2|3, fp_bytes 8 (FloatType = double) or 4 (float: every box,
+ * point and ray component passed to this handle is then a 4-byte float, and all arithmetic is
+ * done in float exactly as spin::BVH<D,ExecSpace,float> does), device = CUDA ordinal.
+ * Defaults: scale 1.000123, tolerance = machine epsilon of FloatType (spin/BVH.hpp:410-412). */
 int axb_bvh_create(axb_bvh** out, int ndims, int fp_bytes, int device);
 int axb_bvh_destroy(axb_bvh* bvh);
 int axb_bvh_set_stream(axb_bvh* bvh, void* cuda_stream); /* optional: run on the caller's stream */
@@ -145,9 +146,9 @@ int axb_bvh_set_find_strategy(axb_bvh* bvh, int strategy);
 /* Parity / debugging: copy the build artefacts to HOST buffers (any may be NULL).
  *   mcodes[n]          sorted 32-bit Morton codes        (RadixTree::m_mcodes)
  *   leaf_nodes[n]      sort permutation                  (RadixTree::m_leafs)
- *   inner_nodes[2(n-1)*2D], inner_children[2(n-1)]       (LinearBVH arrays, reference layout) */
+ *   inner_nodes[2(n-1)*2D] (FloatType), inner_children[2(n-1)]   (LinearBVH arrays, reference layout) */
 int axb_bvh_num_leaves(const axb_bvh* bvh, int32_t* n);
-int axb_bvh_copy_arrays(axb_bvh* bvh, uint32_t* mcodes, int32_t* leaf_nodes, double* inner_nodes, int32_t* inner_children);
+int axb_bvh_copy_arrays(axb_bvh* bvh, uint32_t* mcodes, int32_t* leaf_nodes, void* inner_nodes /* FloatType */, int32_t* inner_children);
 
 /* Device time (ms, CUDA events on the handle's stream) of the phases of the calls made since
  * profiling was (re-)enabled: the MEAN over those calls.  Enabling profiling resets the record.
@@ -162,8 +163,9 @@ int axb_bvh_launch_count(const axb_bvh* bvh, int64_t* n);
 /* SignedDistance(mesh, isWatertight, computeSign) + setMesh (quest/SignedDistance.hpp:410-504).
  * The mint::Mesh is reduced to what SD_GetUcdMeshData extracts (quest/SignedDistance.cpp:15-45):
  * SoA node coordinates and int32 connectivity.  nodes_per_cell 3 (triangles) or 4 (quads,
- * split (0,1,2),(0,2,3)); cell_node_offsets != NULL selects a mixed-shape mesh
- * (AXB_ERR_UNSUPPORTED in this build).  The mesh is copied and re-laid-out on the device. */
+ * split (0,1,2),(0,2,3)); cell_node_offsets != NULL (num_cells+1 entries into cells_to_nodes)
+ * selects a mixed triangle/quad mesh (mint::UnstructuredMesh<MIXED_SHAPE>, UcdMeshData :44-96) and
+ * nodes_per_cell is ignored.  The mesh is copied and re-laid-out on the device. */
 int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, const double* z, int32_t num_nodes,
                   const int32_t* cells_to_nodes, const int32_t* cell_node_offsets, int32_t num_cells, int32_t nodes_per_cell,
                   int mesh_memspace, int is_watertight, int compute_sign);

@@ -26,20 +26,36 @@
 #include <cstring>
 #include <vector>
 
+#include <limits>
+
 #ifdef _OPENMP
   #include <omp.h>
 #endif
 
+// The BVH half of this file is written in terms of `real` so that the same restatement serves
+// spin::BVH<D,SEQ_EXEC,double> (liboracle.so) and spin::BVH<D,SEQ_EXEC,float>
+// (liboracle_f32.so, built with -DAXO_REAL=float -DAXO_FLOAT_BUILD; its entry points are axof_*).
+// SignedDistance is double only (quest/SignedDistance.hpp:151-156) and is left out of the float build.
+#ifndef AXO_REAL
+  #define AXO_REAL double
+#endif
+typedef AXO_REAL real;
+#ifdef AXO_FLOAT_BUILD
+  #define AXO_FN(name) axof_##name
+#else
+  #define AXO_FN(name) axo_##name
+#endif
+
 namespace
 {
-constexpr double kInvalidMin = DBL_MAX;   // primal/geometry/BoundingBox.hpp:72
-constexpr double kInvalidMax = -DBL_MAX;  // primal/geometry/BoundingBox.hpp:73
+constexpr real kInvalidMin = std::numeric_limits<real>::max();   // primal/geometry/BoundingBox.hpp:72
+constexpr real kInvalidMax = std::numeric_limits<real>::lowest();  // primal/geometry/BoundingBox.hpp:73
 
 template <int D>
 struct Box
 {
-  double lo[D];
-  double hi[D];
+  real lo[D];
+  real hi[D];
 };
 
 // primal/geometry/BoundingBox.hpp:451-461
@@ -75,11 +91,11 @@ template <int D>
 inline void box_scale(Box<D>& b, double s)
 {
   if(!box_valid(b)) return;
-  const double hs = s * 0.5;
+  const real hs = static_cast<real>(s * 0.5);  // static_cast<T>(scaleFactor * 0.5), scaleFactor is a double (:548)
   for(int d = 0; d < D; ++d)
   {
-    const double mid = 0.5 * (b.lo[d] + b.hi[d]);
-    const double r = hs * (b.hi[d] - b.lo[d]);
+    const real mid = static_cast<real>(0.5 * (b.lo[d] + b.hi[d]));  // Point::midpoint :279-290
+    const real r = hs * (b.hi[d] - b.lo[d]);
     b.lo[d] = mid - r;
     b.hi[d] = mid + r;
   }
@@ -131,13 +147,13 @@ inline uint32_t spread3(uint32_t x)
 
 // spin/internal/linear_bvh/build_radix_tree.hpp:48-65 (morton32_encode)
 template <int D>
-inline uint32_t morton32(const double* c01)
+inline uint32_t morton32(const real* c01)
 {
   constexpr int bits = 32 / D;
-  constexpr double to_int = double(1 << bits);
-  constexpr double ceil_v = to_int - 1.0;
+  constexpr real to_int = real(1 << bits);
+  constexpr real ceil_v = to_int - real(1);
   int32_t q[D];
-  for(int d = 0; d < D; ++d) q[d] = (int32_t)std::fmin(std::fmax(c01[d] * to_int, 0.0), ceil_v);
+  for(int d = 0; d < D; ++d) q[d] = (int32_t)std::fmin(std::fmax(c01[d] * to_int, real(0)), ceil_v);
   if(D == 2) return spread2((uint32_t)q[0]) | (spread2((uint32_t)q[1]) << 1);
   return spread3((uint32_t)q[0]) | (spread3((uint32_t)q[1]) << 1) | (spread3((uint32_t)q[D - 1]) << 2);
 }
@@ -148,8 +164,8 @@ template <int D>
 struct Bvh
 {
   int n = 0;  // number of leaves after the N<=1 padding
-  double scale = 1.000123;
-  double tol = DBL_EPSILON;
+  double scale = 1.000123;  // BoundingBox::scale takes a double
+  real tol = std::numeric_limits<real>::epsilon();
   Box<D> bounds;
   std::vector<uint32_t> mcodes;    // sorted
   std::vector<int32_t> leafs;      // sort permutation == final leaf_nodes
@@ -189,20 +205,21 @@ void build(Bvh<D>& t, const Box<D>* in, int n)
   box_clear(t.bounds);
   for(int i = 0; i < n; ++i) box_add(t.bounds, t.leaf_aabbs[i]);
   // get_mcodes :146-176
-  double inv_ext[D], mn[D];
+  real inv_ext[D], mn[D];
   for(int d = 0; d < D; ++d)
   {
-    const double ext = t.bounds.hi[d] - t.bounds.lo[d];
+    const real ext = t.bounds.hi[d] - t.bounds.lo[d];
     mn[d] = t.bounds.lo[d];
-    inv_ext[d] = (std::fabs(ext - 0.0) <= 1.0e-8) ? 0.0 : 1.0 / ext;  // core/utilities/Utilities.hpp:317-321
+    // isNearlyEqual<FloatType>(extent, .0f) ? 0.f : 1.f / extent   (core/utilities/Utilities.hpp:317-321)
+    inv_ext[d] = (std::fabs(ext - real(0)) <= real(1.0e-8)) ? real(0) : real(1) / ext;
   }
   std::vector<uint32_t> codes(n);
   for(int i = 0; i < n; ++i)
   {
-    double c[D];
+    real c[D];
     for(int d = 0; d < D; ++d)
     {
-      const double cen = 0.5 * (t.leaf_aabbs[i].lo[d] + t.leaf_aabbs[i].hi[d]);
+      const real cen = static_cast<real>(0.5 * (t.leaf_aabbs[i].lo[d] + t.leaf_aabbs[i].hi[d]));
       c[d] = (cen - mn[d]) * inv_ext[d];
     }
     codes[i] = morton32<D>(c);
@@ -235,8 +252,8 @@ void build(Bvh<D>& t, const Box<D>* in, int n)
     const int j = i + l * d;
     const int dnode = delta(t, i, j);
     int s = 0;
-    double div = 2.0;  // FloatType div_factor = 2.f  (:336)
-    for(int step = (int)std::ceil((double)(float)l / div);; div *= 2, step = (int)std::ceil((double)(float)l / div))
+    real div = 2.0;  // FloatType div_factor = 2.f  (:336); float32(l) / div_factor is evaluated in FloatType
+    for(int step = (int)std::ceil((real)(float)l / div);; div *= 2, step = (int)std::ceil((real)(float)l / div))
     {
       if(delta(t, i, i + (s + step) * d) > dnode) s += step;
       if(step == 1) break;
@@ -310,11 +327,11 @@ void build(Bvh<D>& t, const Box<D>* in, int n)
 
 // spin/BVH.hpp:424-477 (initialize, incl. the N<=1 padding :439-464)
 template <int D>
-Bvh<D>* create(const double* boxes_aos, int n, double scale, double tol)
+Bvh<D>* create(const real* boxes_aos, int n, double scale, double tol)
 {
   Bvh<D>* t = new Bvh<D>();
   if(scale > 0) t->scale = scale;
-  if(tol >= 0) t->tol = tol;
+  if(tol >= 0) t->tol = static_cast<real>(tol);
   const Box<D>* in = reinterpret_cast<const Box<D>*>(boxes_aos);
   if(n <= 1)
   {
@@ -410,20 +427,20 @@ int64_t find_generic(const Bvh<D>& t, int q, int32_t* offsets, int32_t* counts, 
 
 // primal/operators/detail/intersect_ray_impl.hpp:150-187 and :321-351
 template <int D>
-inline bool ray_hits(const double* o, const double* dir, const Box<D>& bb, double eps)
+inline bool ray_hits(const real* o, const real* dir, const Box<D>& bb, real eps)
 {
-  double tmin = DBL_MIN, tmax = DBL_MAX;
+  real tmin = std::numeric_limits<real>::min(), tmax = std::numeric_limits<real>::max();
   for(int d = 0; d < D; ++d)
   {
-    if(std::fabs(dir[d] - 0.0) <= eps)
+    if(std::fabs(dir[d] - real(0)) <= eps)
     {
       if(o[d] < bb.lo[d] || o[d] > bb.hi[d]) return false;
     }
     else
     {
-      const double inv = 1.0 / dir[d];
-      double t1 = (bb.lo[d] - o[d]) * inv;
-      double t2 = (bb.hi[d] - o[d]) * inv;
+      const real inv = static_cast<real>(1.0) / dir[d];
+      real t1 = (bb.lo[d] - o[d]) * inv;
+      real t2 = (bb.hi[d] - o[d]) * inv;
       if(t1 > t2) std::swap(t1, t2);
       tmin = (t1 < tmin) ? tmin : t1;  // utilities::max(x,y) = (y < x) ? x : y  (core/utilities/Utilities.hpp:80-83)
       tmax = (t2 < tmax) ? t2 : tmax;  // utilities::min(x,y) = (y < x) ? y : x  (:93-96)
@@ -435,14 +452,15 @@ inline bool ray_hits(const double* o, const double* dir, const Box<D>& bb, doubl
 
 // primal/geometry/Vector.hpp:477-493 (unitVector) via NumericArray::operator/= (core/NumericArray.hpp:510-514)
 template <int D>
-inline void unit_vector(const double* v, double* out)
+inline void unit_vector(const real* v, real* out)
 {
-  double len2 = 0.0;
-  for(int d = 0; d < D; ++d) len2 += v[d] * v[d];
+  real acc = 0;  // Vector::dot_product accumulates in T (Vector.hpp:543-552) ...
+  for(int d = 0; d < D; ++d) acc += v[d] * v[d];
+  const double len2 = acc;  // ... and unitVector continues in double (:482-486)
   if(len2 >= 1e-50)
   {
     const double s = 1. / std::sqrt(len2);
-    for(int d = 0; d < D; ++d) out[d] = v[d] * s;
+    for(int d = 0; d < D; ++d) out[d] = static_cast<real>(v[d] * s);  // NumericArray::operator*=(double)
   }
   else
   {
@@ -453,23 +471,24 @@ inline void unit_vector(const double* v, double* out)
 
 // primal/operators/squared_distance.hpp:77-100 (point, box)
 template <int D>
-inline double sqdist_point_box(const double* p, const Box<D>& b)
+inline real sqdist_point_box(const real* p, const Box<D>& b)
 {
-  if(!box_valid(b)) return DBL_MAX;
+  if(!box_valid(b)) return std::numeric_limits<real>::max();
   bool inside = true;
   for(int d = 0; d < D; ++d)
     if(p[d] < b.lo[d] || p[d] > b.hi[d]) inside = false;
   if(inside) return 0;
-  double s = 0.0;
+  real s = 0.0;
   for(int d = 0; d < D; ++d)
   {
-    const double c = (p[d] < b.lo[d]) ? b.lo[d] : (p[d] > b.hi[d]) ? b.hi[d] : p[d];
-    const double v = c - p[d];
+    const real c = (p[d] < b.lo[d]) ? b.lo[d] : (p[d] > b.hi[d]) ? b.hi[d] : p[d];
+    const real v = c - p[d];
     s += v * v;
   }
   return s;
 }
 
+#ifndef AXO_FLOAT_BUILD
 //------------------------------------------------------------------------------
 // SignedDistance (3-D only, quest/SignedDistance.hpp)
 //------------------------------------------------------------------------------
@@ -559,7 +578,19 @@ struct Surface
 {
   std::vector<double> x, y, z;
   std::vector<int32_t> conn;
+  std::vector<int32_t> offsets;  // mixed-shape meshes only (UcdMeshData::cell_node_offsets, :51,84-89)
   int ncells = 0, npc = 3;
+  // UcdMeshData::getCellNodeIDs (:76-93)
+  const int32_t* cell_nodes(int cell, int& nnodes) const
+  {
+    if(offsets.empty())
+    {
+      nnodes = npc;
+      return &conn[(size_t)cell * npc];
+    }
+    nnodes = offsets[cell + 1] - offsets[cell];
+    return &conn[offsets[cell]];
+  }
   bool watertight = true, compute_sign = true;
   Box<3> domain;  // node bounds, unscaled (quest/SignedDistance.hpp:483-486)
   Bvh<3>* bvh = nullptr;
@@ -592,11 +623,12 @@ inline double tri_angle(const V3* t, int idx)
 // quest/SignedDistance.hpp:636-737
 inline void check_candidate(const Surface& s, const V3& q, MinCand& m, int cell)
 {
-  const int32_t* nd = &s.conn[(size_t)cell * s.npc];
+  int nnodes;
+  const int32_t* nd = s.cell_nodes(cell, nnodes);
   auto P = [&](int k) { return V3 {s.x[nd[k]], s.y[nd[k]], s.z[nd[k]]}; };
   V3 elems[2][3] = {{P(0), P(1), P(2)}, {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}};
   int ncand = 1;
-  if(s.npc == 4)
+  if(nnodes == 4)
   {
     ncand = 2;
     elems[1][0] = P(0);
@@ -721,6 +753,8 @@ inline void sd_one(const Surface& s, const double* qp, double* phi, double* cp_o
   }
 }
 
+#endif  // !AXO_FLOAT_BUILD
+
 }  // namespace
 
 //------------------------------------------------------------------------------
@@ -736,14 +770,14 @@ struct AxoBvh
 
 extern "C" {
 
-AxoBvh* axo_bvh_create(int ndims, const double* boxes_aos, int n, double scale, double tol)
+AxoBvh* AXO_FN(bvh_create)(int ndims, const real* boxes_aos, int n, double scale, double tol)
 {
   AxoBvh* h = new AxoBvh {ndims, nullptr};
   h->impl = ndims == 2 ? (void*)create<2>(boxes_aos, n, scale, tol) : (void*)create<3>(boxes_aos, n, scale, tol);
   return h;
 }
 
-void axo_bvh_destroy(AxoBvh* h)
+void AXO_FN(bvh_destroy)(AxoBvh* h)
 {
   if(!h) return;
   if(h->ndims == 2)
@@ -753,12 +787,12 @@ void axo_bvh_destroy(AxoBvh* h)
   delete h;
 }
 
-int axo_bvh_num_leaves(const AxoBvh* h) { return DISPATCH(h, ((Bvh<2>*)h->impl)->n, ((Bvh<3>*)h->impl)->n); }
+int AXO_FN(bvh_num_leaves)(const AxoBvh* h) { return DISPATCH(h, ((Bvh<2>*)h->impl)->n, ((Bvh<3>*)h->impl)->n); }
 
 extern "C++" {
 template <int D>
 static void get_arrays(const Bvh<D>& t, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
-                       double* inner_nodes, int32_t* inner_children, double* bounds)
+                       real* inner_nodes, int32_t* inner_children, real* bounds)
 {
   const int n = t.n, inner = n - 1;
   if(mcodes) memcpy(mcodes, t.mcodes.data(), sizeof(uint32_t) * n);
@@ -772,8 +806,8 @@ static void get_arrays(const Bvh<D>& t, uint32_t* mcodes, int32_t* leafs, int32_
 }
 }  // extern "C++"
 
-void axo_bvh_get(const AxoBvh* h, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
-                 double* inner_nodes, int32_t* inner_children, double* bounds)
+void AXO_FN(bvh_get)(const AxoBvh* h, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
+                 real* inner_nodes, int32_t* inner_children, real* bounds)
 {
   if(h->ndims == 2)
     get_arrays(*(Bvh<2>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
@@ -781,7 +815,7 @@ void axo_bvh_get(const AxoBvh* h, uint32_t* mcodes, int32_t* leafs, int32_t* lch
     get_arrays(*(Bvh<3>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
 }
 
-void axo_free(void* p) { free(p); }
+void AXO_FN(free)(void* p) { free(p); }
 
 static int32_t* to_malloc(const std::vector<int32_t>& v)
 {
@@ -793,11 +827,11 @@ static int32_t* to_malloc(const std::vector<int32_t>& v)
 // spin/BVH.hpp:480-505
 extern "C++" {
 template <int D>
-static int64_t find_points(const Bvh<D>& t, const double* pts, int q, int32_t* off, int32_t* cnt, int32_t** cand)
+static int64_t find_points(const Bvh<D>& t, const real* pts, int q, int32_t* off, int32_t* cnt, int32_t** cand)
 {
   std::vector<int32_t> c;
   int64_t tot = find_generic(t, q, off, cnt, c, [&](int i) {
-    const double* p = pts + (size_t)i * D;
+    const real* p = pts + (size_t)i * D;
     return [p](const Box<D>& bb) {
       for(int d = 0; d < D; ++d)
         if(p[d] < bb.lo[d] || p[d] > bb.hi[d]) return false;  // BoundingBox.hpp:390-401
@@ -809,7 +843,7 @@ static int64_t find_points(const Bvh<D>& t, const double* pts, int q, int32_t* o
 }
 }  // extern "C++"
 
-int64_t axo_bvh_find_points(const AxoBvh* h, const double* pts_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
+int64_t AXO_FN(bvh_find_points)(const AxoBvh* h, const real* pts_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
 {
   return DISPATCH(h, find_points(*(Bvh<2>*)h->impl, pts_aos, q, offsets, counts, cand),
                   find_points(*(Bvh<3>*)h->impl, pts_aos, q, offsets, counts, cand));
@@ -818,7 +852,7 @@ int64_t axo_bvh_find_points(const AxoBvh* h, const double* pts_aos, int q, int32
 // spin/BVH.hpp:539-568
 extern "C++" {
 template <int D>
-static int64_t find_boxes(const Bvh<D>& t, const double* qb, int q, int32_t* off, int32_t* cnt, int32_t** cand)
+static int64_t find_boxes(const Bvh<D>& t, const real* qb, int q, int32_t* off, int32_t* cnt, int32_t** cand)
 {
   std::vector<int32_t> c;
   const Box<D>* qs = reinterpret_cast<const Box<D>*>(qb);
@@ -836,7 +870,7 @@ static int64_t find_boxes(const Bvh<D>& t, const double* qb, int q, int32_t* off
 }
 }  // extern "C++"
 
-int64_t axo_bvh_find_boxes(const AxoBvh* h, const double* boxes_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
+int64_t AXO_FN(bvh_find_boxes)(const AxoBvh* h, const real* boxes_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
 {
   return DISPATCH(h, find_boxes(*(Bvh<2>*)h->impl, boxes_aos, q, offsets, counts, cand),
                   find_boxes(*(Bvh<3>*)h->impl, boxes_aos, q, offsets, counts, cand));
@@ -845,15 +879,15 @@ int64_t axo_bvh_find_boxes(const AxoBvh* h, const double* boxes_aos, int q, int3
 // spin/BVH.hpp:508-536; normalize != 0 reproduces the primal::Ray constructor (Ray.hpp:122-127)
 extern "C++" {
 template <int D>
-static int64_t find_rays(const Bvh<D>& t, const double* orig, const double* dirs, int q, int normalize, int32_t* off, int32_t* cnt,
+static int64_t find_rays(const Bvh<D>& t, const real* orig, const real* dirs, int q, int normalize, int32_t* off, int32_t* cnt,
                          int32_t** cand)
 {
   std::vector<int32_t> c;
-  const double tol = t.tol;
+  const real tol = t.tol;
   int64_t tot = find_generic(t, q, off, cnt, c, [&](int i) {
     struct R
     {
-      double o[D], d[D];
+      real o[D], d[D];
     } r;
     for(int k = 0; k < D; ++k) r.o[k] = orig[(size_t)i * D + k];
     if(normalize)
@@ -867,13 +901,14 @@ static int64_t find_rays(const Bvh<D>& t, const double* orig, const double* dirs
 }
 }  // extern "C++"
 
-int64_t axo_bvh_find_rays(const AxoBvh* h, const double* origins_aos, const double* dirs_aos, int q, int normalize, int32_t* offsets,
+int64_t AXO_FN(bvh_find_rays)(const AxoBvh* h, const real* origins_aos, const real* dirs_aos, int q, int normalize, int32_t* offsets,
                           int32_t* counts, int32_t** cand)
 {
   return DISPATCH(h, find_rays(*(Bvh<2>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand),
                   find_rays(*(Bvh<3>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand));
 }
 
+#ifndef AXO_FLOAT_BUILD
 // count-only traversal driven by an external OpenMP loop (what RAJA's omp policy does
 // with policy/LinearBVH.hpp:302-321); used for the host-core baseline timing.
 int64_t axo_bvh_count_points_omp(const AxoBvh* h, const double* pts_aos, int q, int32_t* counts, int nthreads)
@@ -905,14 +940,22 @@ int64_t axo_bvh_count_points_omp(const AxoBvh* h, const double* pts_aos, int q, 
 }
 
 // quest/SignedDistance.hpp:427-504 (setMesh)
-void* axo_sd_create(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, int ncells, int nodes_per_cell,
-                    int watertight, int compute_sign)
+static void* sd_create_impl(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, const int32_t* offsets,
+                            int ncells, int nodes_per_cell, int watertight, int compute_sign)
 {
   Surface* s = new Surface();
   s->x.assign(x, x + nnodes);
   s->y.assign(y, y + nnodes);
   s->z.assign(z, z + nnodes);
-  s->conn.assign(conn, conn + (size_t)ncells * nodes_per_cell);
+  if(offsets)
+  {
+    s->offsets.assign(offsets, offsets + ncells + 1);
+    s->conn.assign(conn, conn + offsets[ncells]);
+  }
+  else
+  {
+    s->conn.assign(conn, conn + (size_t)ncells * nodes_per_cell);
+  }
   s->ncells = ncells;
   s->npc = nodes_per_cell;
   s->watertight = watertight != 0;
@@ -932,9 +975,11 @@ void* axo_sd_create(const double* x, const double* y, const double* z, int nnode
   {
     Box<3> bb;
     box_clear(bb);
-    for(int k = 0; k < nodes_per_cell; ++k)
+    int cn;
+    const int32_t* ids = s->cell_nodes(c, cn);
+    for(int k = 0; k < cn; ++k)
     {
-      const int nd = conn[(size_t)c * nodes_per_cell + k];
+      const int nd = ids[k];
       const double p[3] = {x[nd], y[nd], z[nd]};
       for(int d = 0; d < 3; ++d)
       {
@@ -946,6 +991,19 @@ void* axo_sd_create(const double* x, const double* y, const double* z, int nnode
   }
   s->bvh = create<3>(reinterpret_cast<const double*>(boxes.data()), ncells, -1.0, -1.0);
   return s;
+}
+
+void* axo_sd_create(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, int ncells, int nodes_per_cell,
+                    int watertight, int compute_sign)
+{
+  return sd_create_impl(x, y, z, nnodes, conn, nullptr, ncells, nodes_per_cell, watertight, compute_sign);
+}
+
+// mixed triangle / quad surface (mint::UnstructuredMesh<MIXED_SHAPE>): offsets[ncells+1] into conn
+void* axo_sd_create_mixed(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, const int32_t* offsets,
+                          int ncells, int watertight, int compute_sign)
+{
+  return sd_create_impl(x, y, z, nnodes, conn, offsets, ncells, -1, watertight, compute_sign);
 }
 
 void axo_sd_destroy(void* h) { delete(Surface*)h; }
@@ -971,7 +1029,9 @@ void axo_sd_compute(void* h, const double* qpts_aos, int npts, double* phi, doub
   }
 }
 
-int axo_max_threads()
+#endif  // !AXO_FLOAT_BUILD
+
+int AXO_FN(max_threads)()
 {
 #ifdef _OPENMP
   return omp_get_max_threads();

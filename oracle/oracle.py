@@ -15,6 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _PORT = os.path.join(HERE, "liboracle.so")
+_PORT_F32 = os.path.join(HERE, "liboracle_f32.so")
 _REF = os.path.join(HERE, "_ref", "libaxom_ref.so")
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -23,7 +24,7 @@ _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 
 
 def build_port():
-    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"])
+    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so", "liboracle_f32.so"])
 
 
 def have_reference():
@@ -31,18 +32,22 @@ def have_reference():
 
 
 class _Lib:
+    """kind: "port" | "reference" (FloatType = double), "port_f32" | "reference_f32" (FloatType = float, BVH only)"""
+
     def __init__(self, kind):
         self.kind = kind
-        if kind == "port":
-            if not os.path.exists(_PORT):
+        self.f32 = kind.endswith("_f32")
+        if kind in ("port", "port_f32"):
+            path = _PORT_F32 if self.f32 else _PORT
+            if not os.path.exists(path):
                 build_port()
-            self.lib = C.CDLL(_PORT)
-            self.pfx = "axo_"
-        elif kind == "reference":
+            self.lib = C.CDLL(path)
+            self.pfx = "axof_" if self.f32 else "axo_"
+        elif kind in ("reference", "reference_f32"):
             if not os.path.exists(_REF):
                 raise FileNotFoundError(_REF + " (run python oracle/build_ref.py where /root/reference exists)")
             self.lib = C.CDLL(_REF)
-            self.pfx = "axref_"
+            self.pfx = "axreff_" if self.f32 else "axref_"
         else:
             raise ValueError(kind)
         f = self.fn
@@ -58,12 +63,15 @@ class _Lib:
         f("bvh_find_rays").restype = C.c_int64
         f("bvh_find_rays").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_void_p)]
-        f("bvh_count_points_omp").restype = C.c_int64
-        f("bvh_count_points_omp").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
-        f("sd_create").restype = C.c_void_p
-        f("sd_create").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
-        f("sd_destroy").argtypes = [C.c_void_p]
-        f("sd_compute").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        if not self.f32:
+            f("bvh_count_points_omp").restype = C.c_int64
+            f("bvh_count_points_omp").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            f("sd_create").restype = C.c_void_p
+            f("sd_create").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+            f("sd_create_mixed").restype = C.c_void_p
+            f("sd_create_mixed").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+            f("sd_destroy").argtypes = [C.c_void_p]
+            f("sd_compute").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         f("max_threads").restype = C.c_int
 
     def fn(self, name):
@@ -89,7 +97,8 @@ class Bvh:
     def __init__(self, boxes, ndims=3, scale=-1.0, tol=-1.0, kind="port"):
         self.L = lib(kind)
         self.ndims = ndims
-        boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 2 * ndims)
+        self.ft = np.float32 if self.L.f32 else np.float64
+        boxes = np.ascontiguousarray(boxes, dtype=self.ft).reshape(-1, 2 * ndims)
         self.n_in = boxes.shape[0]
         self.h = self.L.fn("bvh_create")(ndims, _ptr(boxes), self.n_in, float(scale), float(tol))
         self.n = self.L.fn("bvh_num_leaves")(self.h)
@@ -107,8 +116,8 @@ class Bvh:
         out = dict(
             mcodes=np.empty(n, np.uint32), leafs=np.empty(n, np.int32), lchild=np.empty(inner, np.int32),
             rchild=np.empty(inner, np.int32), parents=np.empty(inner + n, np.int32),
-            inner_nodes=np.empty((2 * inner, 2 * D), np.float64), inner_children=np.empty(2 * inner, np.int32),
-            bounds=np.empty(2 * D, np.float64))
+            inner_nodes=np.empty((2 * inner, 2 * D), self.ft), inner_children=np.empty(2 * inner, np.int32),
+            bounds=np.empty(2 * D, self.ft))
         self.L.fn("bvh_get")(self.h, *[_ptr(out[k]) for k in
                                        ("mcodes", "leafs", "lchild", "rchild", "parents", "inner_nodes", "inner_children", "bounds")])
         return out
@@ -119,7 +128,7 @@ class Bvh:
         return cand
 
     def find_points(self, pts):
-        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, self.ndims)
+        pts = np.ascontiguousarray(pts, self.ft).reshape(-1, self.ndims)
         q = pts.shape[0]
         off, cnt = np.empty(q, np.int32), np.empty(q, np.int32)
         cp = C.c_void_p()
@@ -127,7 +136,7 @@ class Bvh:
         return off, cnt, self._collect(tot, cp)
 
     def find_boxes(self, qboxes):
-        qb = np.ascontiguousarray(qboxes, np.float64).reshape(-1, 2 * self.ndims)
+        qb = np.ascontiguousarray(qboxes, self.ft).reshape(-1, 2 * self.ndims)
         q = qb.shape[0]
         off, cnt = np.empty(q, np.int32), np.empty(q, np.int32)
         cp = C.c_void_p()
@@ -135,8 +144,8 @@ class Bvh:
         return off, cnt, self._collect(tot, cp)
 
     def find_rays(self, origins, dirs, normalize=True):
-        o = np.ascontiguousarray(origins, np.float64).reshape(-1, self.ndims)
-        d = np.ascontiguousarray(dirs, np.float64).reshape(-1, self.ndims)
+        o = np.ascontiguousarray(origins, self.ft).reshape(-1, self.ndims)
+        d = np.ascontiguousarray(dirs, self.ft).reshape(-1, self.ndims)
         q = o.shape[0]
         off, cnt = np.empty(q, np.int32), np.empty(q, np.int32)
         cp = C.c_void_p()
@@ -153,12 +162,18 @@ class Bvh:
 class SignedDistance:
     """quest::SignedDistance<3, SEQ_EXEC> on the CPU (port or real reference)."""
 
-    def __init__(self, x, y, z, conn, nodes_per_cell=3, watertight=True, compute_sign=True, kind="port"):
+    def __init__(self, x, y, z, conn, nodes_per_cell=3, watertight=True, compute_sign=True, kind="port", offsets=None):
+        """offsets (ncells+1 int32 into conn) selects a mixed triangle/quad mesh (UnstructuredMesh<MIXED_SHAPE>)"""
         self.L = lib(kind)
         self.x = np.ascontiguousarray(x, np.float64)
         self.y = np.ascontiguousarray(y, np.float64)
         self.z = np.ascontiguousarray(z, np.float64)
         self.conn = np.ascontiguousarray(conn, np.int32).reshape(-1)
+        if offsets is not None:
+            self.offsets = np.ascontiguousarray(offsets, np.int32)
+            self.h = self.L.fn("sd_create_mixed")(_ptr(self.x), _ptr(self.y), _ptr(self.z), self.x.size, _ptr(self.conn),
+                                                  _ptr(self.offsets), self.offsets.size - 1, int(watertight), int(compute_sign))
+            return
         ncells = self.conn.size // nodes_per_cell
         self.h = self.L.fn("sd_create")(_ptr(self.x), _ptr(self.y), _ptr(self.z), self.x.size, _ptr(self.conn), ncells,
                                         nodes_per_cell, int(watertight), int(compute_sign))

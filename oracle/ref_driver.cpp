@@ -48,32 +48,32 @@ void ensure_slic()
 
 // LinearBVHTraverser (spin/policy/LinearBVH.hpp:57-109) keeps its three ArrayViews private;
 // this mirror has the same members in the same order so the arrays can be read out.
-template <int D>
+template <typename F, int D>
 struct TraverserMirror
 {
-  axom::ArrayView<const axom::primal::BoundingBox<double, D>> inner_nodes;
+  axom::ArrayView<const axom::primal::BoundingBox<F, D>> inner_nodes;
   axom::ArrayView<const std::int32_t> inner_children;
   axom::ArrayView<const std::int32_t> leaf_nodes;
 };
 
-template <int D>
+template <typename F, int D>
 struct RefBvh
 {
-  using BVHType = axom::spin::BVH<D, SEQ_EXEC, double>;
-  using BoxType = axom::primal::BoundingBox<double, D>;
+  using BVHType = axom::spin::BVH<D, SEQ_EXEC, F>;
+  using BoxType = axom::primal::BoundingBox<F, D>;
   BVHType bvh;
   int n_in = 0;
   // radix-tree internals, from a second (identical) call of build_radix_tree
-  lbvh::RadixTree<double, D> radix;
+  lbvh::RadixTree<F, D> radix;
 };
 
-template <int D>
-RefBvh<D>* create(const double* boxes_aos, int n, double scale, double tol)
+template <typename F, int D>
+RefBvh<F, D>* create(const F* boxes_aos, int n, double scale, double tol)
 {
-  using BoxType = typename RefBvh<D>::BoxType;
-  static_assert(sizeof(BoxType) == sizeof(double) * 2 * D, "BoundingBox is min[D],max[D]");
+  using BoxType = typename RefBvh<F, D>::BoxType;
+  static_assert(sizeof(BoxType) == sizeof(F) * 2 * D, "BoundingBox is min[D],max[D]");
   ensure_slic();
-  RefBvh<D>* r = new RefBvh<D>();
+  RefBvh<F, D>* r = new RefBvh<F, D>();
   r->n_in = n;
   if(scale > 0) r->bvh.setScaleFactor(scale);
   if(tol >= 0) r->bvh.setTolerance(tol);
@@ -96,11 +96,11 @@ RefBvh<D>* create(const double* boxes_aos, int n, double scale, double tol)
   return r;
 }
 
-template <int D>
-void get_arrays(const RefBvh<D>& r, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
-                double* inner_nodes, int32_t* inner_children, double* bounds)
+template <typename F, int D>
+void get_arrays(const RefBvh<F, D>& r, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
+                F* inner_nodes, int32_t* inner_children, F* bounds)
 {
-  using BoxType = typename RefBvh<D>::BoxType;
+  using BoxType = typename RefBvh<F, D>::BoxType;
   const int n = r.radix.m_size, inner = n - 1;
   if(mcodes) memcpy(mcodes, r.radix.m_mcodes.data(), sizeof(uint32_t) * n);
   if(leafs) memcpy(leafs, r.radix.m_leafs.data(), sizeof(int32_t) * n);
@@ -108,8 +108,8 @@ void get_arrays(const RefBvh<D>& r, uint32_t* mcodes, int32_t* leafs, int32_t* l
   if(rchild) memcpy(rchild, r.radix.m_right_children.data(), sizeof(int32_t) * inner);
   if(parents) memcpy(parents, r.radix.m_parents.data(), sizeof(int32_t) * (inner + n));
   auto trav = r.bvh.getTraverser();
-  static_assert(sizeof(trav) == sizeof(TraverserMirror<D>), "traverser layout changed");
-  TraverserMirror<D> tm;
+  static_assert(sizeof(trav) == sizeof(TraverserMirror<F, D>), "traverser layout changed");
+  TraverserMirror<F, D> tm;
   memcpy((void*)&tm, (const void*)&trav, sizeof(tm));
   if(inner_nodes) memcpy(inner_nodes, tm.inner_nodes.data(), sizeof(BoxType) * 2 * inner);
   if(inner_children) memcpy(inner_children, tm.inner_children.data(), sizeof(int32_t) * 2 * inner);
@@ -133,10 +133,10 @@ int32_t* to_malloc(const axom::Array<axom::IndexType>& a)
   return p;
 }
 
-template <int D>
-int64_t find_points(const RefBvh<D>& r, const double* pts, int q, int32_t* off, int32_t* cnt, int32_t** cand)
+template <typename F, int D>
+int64_t find_points(const RefBvh<F, D>& r, const F* pts, int q, int32_t* off, int32_t* cnt, int32_t** cand)
 {
-  using PointType = axom::primal::Point<double, D>;
+  using PointType = axom::primal::Point<F, D>;
   axom::Array<axom::IndexType> c;
   r.bvh.findPoints(axom::ArrayView<axom::IndexType>(off, q), axom::ArrayView<axom::IndexType>(cnt, q), c, q,
                    reinterpret_cast<const PointType*>(pts));
@@ -144,10 +144,10 @@ int64_t find_points(const RefBvh<D>& r, const double* pts, int q, int32_t* off, 
   return c.size();
 }
 
-template <int D>
-int64_t find_boxes(const RefBvh<D>& r, const double* bx, int q, int32_t* off, int32_t* cnt, int32_t** cand)
+template <typename F, int D>
+int64_t find_boxes(const RefBvh<F, D>& r, const F* bx, int q, int32_t* off, int32_t* cnt, int32_t** cand)
 {
-  using BoxType = typename RefBvh<D>::BoxType;
+  using BoxType = typename RefBvh<F, D>::BoxType;
   axom::Array<axom::IndexType> c;
   r.bvh.findBoundingBoxes(axom::ArrayView<axom::IndexType>(off, q), axom::ArrayView<axom::IndexType>(cnt, q), c, q,
                           reinterpret_cast<const BoxType*>(bx));
@@ -155,13 +155,13 @@ int64_t find_boxes(const RefBvh<D>& r, const double* bx, int q, int32_t* off, in
   return c.size();
 }
 
-template <int D>
-int64_t find_rays(const RefBvh<D>& r, const double* orig, const double* dirs, int q, int normalize, int32_t* off, int32_t* cnt,
+template <typename F, int D>
+int64_t find_rays(const RefBvh<F, D>& r, const F* orig, const F* dirs, int q, int normalize, int32_t* off, int32_t* cnt,
                   int32_t** cand)
 {
-  using RayType = axom::primal::Ray<double, D>;
-  using PointType = axom::primal::Point<double, D>;
-  using VectorType = axom::primal::Vector<double, D>;
+  using RayType = axom::primal::Ray<F, D>;
+  using PointType = axom::primal::Point<F, D>;
+  using VectorType = axom::primal::Vector<F, D>;
   std::vector<RayType> rays;
   rays.reserve(q);
   for(int i = 0; i < q; ++i)
@@ -191,8 +191,9 @@ int64_t find_rays(const RefBvh<D>& r, const double* orig, const double* dirs, in
 struct RefSurface
 {
   using Mesh = axom::mint::UnstructuredMesh<axom::mint::SINGLE_SHAPE>;
+  using MixedMesh = axom::mint::UnstructuredMesh<axom::mint::MIXED_SHAPE>;
   using SD = axom::quest::SignedDistance<3, SEQ_EXEC>;
-  Mesh* mesh = nullptr;
+  axom::mint::Mesh* mesh = nullptr;
   SD* sd = nullptr;
   ~RefSurface()
   {
@@ -214,7 +215,7 @@ extern "C" {
 AxrefBvh* axref_bvh_create(int ndims, const double* boxes_aos, int n, double scale, double tol)
 {
   AxrefBvh* h = new AxrefBvh {ndims, nullptr};
-  h->impl = ndims == 2 ? (void*)create<2>(boxes_aos, n, scale, tol) : (void*)create<3>(boxes_aos, n, scale, tol);
+  h->impl = ndims == 2 ? (void*)create<double, 2>(boxes_aos, n, scale, tol) : (void*)create<double, 3>(boxes_aos, n, scale, tol);
   return h;
 }
 
@@ -222,45 +223,100 @@ void axref_bvh_destroy(AxrefBvh* h)
 {
   if(!h) return;
   if(h->ndims == 2)
-    delete(RefBvh<2>*)h->impl;
+    delete(RefBvh<double, 2>*)h->impl;
   else
-    delete(RefBvh<3>*)h->impl;
+    delete(RefBvh<double, 3>*)h->impl;
   delete h;
 }
 
 int axref_bvh_num_leaves(const AxrefBvh* h)
 {
-  return h->ndims == 2 ? ((RefBvh<2>*)h->impl)->radix.m_size : ((RefBvh<3>*)h->impl)->radix.m_size;
+  return h->ndims == 2 ? ((RefBvh<double, 2>*)h->impl)->radix.m_size : ((RefBvh<double, 3>*)h->impl)->radix.m_size;
 }
 
 void axref_bvh_get(const AxrefBvh* h, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
                    double* inner_nodes, int32_t* inner_children, double* bounds)
 {
   if(h->ndims == 2)
-    get_arrays(*(RefBvh<2>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
+    get_arrays(*(RefBvh<double, 2>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
   else
-    get_arrays(*(RefBvh<3>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
+    get_arrays(*(RefBvh<double, 3>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
 }
 
 void axref_free(void* p) { free(p); }
 
 int64_t axref_bvh_find_points(const AxrefBvh* h, const double* pts_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
 {
-  return h->ndims == 2 ? find_points(*(RefBvh<2>*)h->impl, pts_aos, q, offsets, counts, cand)
-                       : find_points(*(RefBvh<3>*)h->impl, pts_aos, q, offsets, counts, cand);
+  return h->ndims == 2 ? find_points(*(RefBvh<double, 2>*)h->impl, pts_aos, q, offsets, counts, cand)
+                       : find_points(*(RefBvh<double, 3>*)h->impl, pts_aos, q, offsets, counts, cand);
 }
 
 int64_t axref_bvh_find_boxes(const AxrefBvh* h, const double* boxes_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
 {
-  return h->ndims == 2 ? find_boxes(*(RefBvh<2>*)h->impl, boxes_aos, q, offsets, counts, cand)
-                       : find_boxes(*(RefBvh<3>*)h->impl, boxes_aos, q, offsets, counts, cand);
+  return h->ndims == 2 ? find_boxes(*(RefBvh<double, 2>*)h->impl, boxes_aos, q, offsets, counts, cand)
+                       : find_boxes(*(RefBvh<double, 3>*)h->impl, boxes_aos, q, offsets, counts, cand);
 }
 
 int64_t axref_bvh_find_rays(const AxrefBvh* h, const double* origins_aos, const double* dirs_aos, int q, int normalize,
                             int32_t* offsets, int32_t* counts, int32_t** cand)
 {
-  return h->ndims == 2 ? find_rays(*(RefBvh<2>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand)
-                       : find_rays(*(RefBvh<3>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand);
+  return h->ndims == 2 ? find_rays(*(RefBvh<double, 2>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand)
+                       : find_rays(*(RefBvh<double, 3>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand);
+}
+
+// ---- FloatType = float: spin::BVH<D,SEQ_EXEC,float> (spin/tests/spin_bvh.cpp:1563-1669 instantiates it) ----
+AxrefBvh* axreff_bvh_create(int ndims, const float* boxes_aos, int n, double scale, double tol)
+{
+  AxrefBvh* h = new AxrefBvh {ndims, nullptr};
+  h->impl = ndims == 2 ? (void*)create<float, 2>(boxes_aos, n, scale, tol) : (void*)create<float, 3>(boxes_aos, n, scale, tol);
+  return h;
+}
+
+void axreff_bvh_destroy(AxrefBvh* h)
+{
+  if(!h) return;
+  if(h->ndims == 2)
+    delete(RefBvh<float, 2>*)h->impl;
+  else
+    delete(RefBvh<float, 3>*)h->impl;
+  delete h;
+}
+
+int axreff_bvh_num_leaves(const AxrefBvh* h)
+{
+  return h->ndims == 2 ? ((RefBvh<float, 2>*)h->impl)->radix.m_size : ((RefBvh<float, 3>*)h->impl)->radix.m_size;
+}
+
+void axreff_bvh_get(const AxrefBvh* h, uint32_t* mcodes, int32_t* leafs, int32_t* lchild, int32_t* rchild, int32_t* parents,
+                   float* inner_nodes, int32_t* inner_children, float* bounds)
+{
+  if(h->ndims == 2)
+    get_arrays(*(RefBvh<float, 2>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
+  else
+    get_arrays(*(RefBvh<float, 3>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
+}
+
+void axreff_free(void* p) { free(p); }
+
+int axreff_max_threads() { return 1; }
+
+int64_t axreff_bvh_find_points(const AxrefBvh* h, const float* pts_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
+{
+  return h->ndims == 2 ? find_points(*(RefBvh<float, 2>*)h->impl, pts_aos, q, offsets, counts, cand)
+                       : find_points(*(RefBvh<float, 3>*)h->impl, pts_aos, q, offsets, counts, cand);
+}
+
+int64_t axreff_bvh_find_boxes(const AxrefBvh* h, const float* boxes_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)
+{
+  return h->ndims == 2 ? find_boxes(*(RefBvh<float, 2>*)h->impl, boxes_aos, q, offsets, counts, cand)
+                       : find_boxes(*(RefBvh<float, 3>*)h->impl, boxes_aos, q, offsets, counts, cand);
+}
+
+int64_t axreff_bvh_find_rays(const AxrefBvh* h, const float* origins_aos, const float* dirs_aos, int q, int normalize,
+                            int32_t* offsets, int32_t* counts, int32_t** cand)
+{
+  return h->ndims == 2 ? find_rays(*(RefBvh<float, 2>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand)
+                       : find_rays(*(RefBvh<float, 3>*)h->impl, origins_aos, dirs_aos, q, normalize, offsets, counts, cand);
 }
 
 // Reference traversal (getTraverser().traverse_tree, policy/LinearBVH.hpp:92-103) driven by an
@@ -270,7 +326,7 @@ int64_t axref_bvh_count_points_omp(const AxrefBvh* h, const double* pts_aos, int
   if(h->ndims != 3) return -1;
   using PointType = axom::primal::Point<double, 3>;
   using BoxType = axom::primal::BoundingBox<double, 3>;
-  const auto trav = ((RefBvh<3>*)h->impl)->bvh.getTraverser();
+  const auto trav = ((RefBvh<double, 3>*)h->impl)->bvh.getTraverser();
   const PointType* pts = reinterpret_cast<const PointType*>(pts_aos);
   int64_t total = 0;
 #ifdef _OPENMP
@@ -303,13 +359,34 @@ void* axref_sd_create(const double* x, const double* y, const double* z, int nno
   ensure_slic();
   RefSurface* s = new RefSurface();
   const axom::mint::CellType ct = nodes_per_cell == 3 ? axom::mint::TRIANGLE : axom::mint::QUAD;
-  s->mesh = new RefSurface::Mesh(3, ct, nnodes, ncells);
-  for(int i = 0; i < nnodes; ++i) s->mesh->appendNode(x[i], y[i], z[i]);
+  RefSurface::Mesh* m = new RefSurface::Mesh(3, ct, nnodes, ncells);
+  s->mesh = m;
+  for(int i = 0; i < nnodes; ++i) m->appendNode(x[i], y[i], z[i]);
   for(int c = 0; c < ncells; ++c)
   {
     axom::IndexType ids[4];
     for(int k = 0; k < nodes_per_cell; ++k) ids[k] = conn[(size_t)c * nodes_per_cell + k];
-    s->mesh->appendCell(ids);
+    m->appendCell(ids);
+  }
+  s->sd = new RefSurface::SD(s->mesh, watertight != 0, compute_sign != 0);
+  return s;
+}
+
+// mixed triangle / quad surface: mint::UnstructuredMesh<MIXED_SHAPE> (SD_GetUcdMeshData, quest/SignedDistance.cpp:29-37)
+void* axref_sd_create_mixed(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, const int32_t* offsets,
+                            int ncells, int watertight, int compute_sign)
+{
+  ensure_slic();
+  RefSurface* s = new RefSurface();
+  RefSurface::MixedMesh* m = new RefSurface::MixedMesh(3, nnodes, ncells);
+  s->mesh = m;
+  for(int i = 0; i < nnodes; ++i) m->appendNode(x[i], y[i], z[i]);
+  for(int c = 0; c < ncells; ++c)
+  {
+    const int nn = offsets[c + 1] - offsets[c];
+    axom::IndexType ids[4];
+    for(int k = 0; k < nn; ++k) ids[k] = conn[offsets[c] + k];
+    m->appendCell(ids, nn == 3 ? axom::mint::TRIANGLE : axom::mint::QUAD);
   }
   s->sd = new RefSurface::SD(s->mesh, watertight != 0, compute_sign != 0);
   return s;

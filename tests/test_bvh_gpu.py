@@ -189,3 +189,33 @@ def test_rebuild_and_traverser_view():
     t = b.getTraverser()
     assert t.num_leaves == 7000 and t.ndims == 3 and t.fp_bytes == 8
     assert t.inner_nodes and t.inner_node_children and t.leaf_nodes
+
+
+@pytest.mark.parametrize("ndims", [3, 2])
+@pytest.mark.parametrize("n", [0, 1, 2, 27, 5000, 60000])
+def test_float_bvh_bit_exact(oracle, have_ref, ndims, n):
+    """FloatType = float (spin/tests/spin_bvh.cpp:1563-1669 instantiates it): build artefacts and all three
+    queries against the float oracle -- the real reference's BVH<D,SEQ_EXEC,float> when oracle/_ref is
+    present, and always the float build of the restatement."""
+    from axom_b200 import BVH
+    boxes = synth.triangle_aabbs(max(n, 1), seed=5 + n, ndims=ndims)[:n].astype(np.float32)
+    pts = synth.random_points(9000, seed=n, ndims=ndims).astype(np.float32)
+    qb = synth.triangle_aabbs(1500, seed=n + 9, ndims=ndims).astype(np.float32)
+    o, d = synth.random_rays(800, seed=n + 3, lo=-0.5, hi=1.5, ndims=ndims)
+    o, d = o.astype(np.float32), d.astype(np.float32)
+    for scale in (None, 1.0):
+        gpu = BVH(ndims, dtype=np.float32)
+        if scale is not None:
+            gpu.setScaleFactor(scale)
+        assert gpu.getTolerance() == float(np.finfo(np.float32).eps)
+        assert gpu.initialize(boxes) == 0
+        G = gpu.arrays()
+        for kind in (["reference_f32"] if have_ref else []) + ["port_f32"]:
+            ref = oracle.Bvh(boxes, ndims, scale=-1.0 if scale is None else scale, kind=kind)
+            A = ref.arrays()
+            for k in ("mcodes", "leafs", "inner_children", "inner_nodes", "bounds"):
+                assert np.array_equal(A[k], G[k]), (k, kind, ndims, n)
+            assert _same(ref.find_points(pts), gpu.findPoints(pts))
+            assert _same(ref.find_boxes(qb), gpu.findBoundingBoxes(qb))
+            assert _same(ref.find_rays(o, d * np.float32(1.7), True), gpu.findRays(o, d * np.float32(1.7), normalized=False))
+            assert _same(ref.find_rays(o, d, False), gpu.findRays(o, d, normalized=True))

@@ -126,3 +126,27 @@ def test_port_equals_real_reference_on_random_inputs(oracle, have_ref):
     assert np.array_equal(ra[0], rb[0]) or True
     tot, cnt = oracle.Bvh(boxes, ndims=3, kind="reference").count_points_omp(synth.random_points(500, seed=n))
     assert tot == cnt.sum()
+
+
+@pytest.mark.parametrize("ndims", [3, 2])
+def test_float_restatement_matches_float_reference(oracle, have_ref, ndims):
+    """FloatType = float: the float build of the restatement (liboracle_f32.so) against the real reference's
+    spin::BVH<D,SEQ_EXEC,float> -- build artefacts and the three queries, bit for bit."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    from axom_b200 import synth
+    for n in (0, 1, 3, 500, 20000):
+        boxes = synth.triangle_aabbs(max(n, 1), seed=40 + n, ndims=ndims)[:n].astype(np.float32)
+        a, b = oracle.Bvh(boxes, ndims, kind="port_f32"), oracle.Bvh(boxes, ndims, kind="reference_f32")
+        A, B = a.arrays(), b.arrays()
+        for k in A:
+            assert np.array_equal(A[k], B[k]), (k, n)
+        pts = synth.random_points(1000, seed=n, ndims=ndims).astype(np.float32)
+        qb = synth.triangle_aabbs(700, seed=n + 1, ndims=ndims).astype(np.float32)
+        o, d = synth.random_rays(500, seed=n + 2, lo=-0.5, hi=1.5, ndims=ndims)
+        for u, v in zip(a.find_points(pts), b.find_points(pts)):
+            assert np.array_equal(u, v)
+        for u, v in zip(a.find_boxes(qb), b.find_boxes(qb)):
+            assert np.array_equal(u, v)
+        for u, v in zip(a.find_rays(o, d * 1.7, True), b.find_rays(o, d * 1.7, True)):
+            assert np.array_equal(u, v)

@@ -128,3 +128,46 @@ def test_fast_mode_large_sorted_queries(oracle):
     phi, cp, _ = sd.computeDistances(q, True, False)
     assert np.array_equal(ref[0], phi)
     assert np.array_equal(ref[1], cp)
+
+
+def _mixed_sheet():
+    """wavy 8x8 sheet: quads on the even squares, two triangles on the odd ones (MIXED_SHAPE mesh)"""
+    g = np.linspace(-1, 1, 9)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    xs, ys = X.ravel(), Y.ravel()
+    zs = 0.1 * np.sin(3 * xs) * np.cos(2 * ys)
+    idx = lambda i, j: i * 9 + j
+    conn, off = [], [0]
+    for i in range(8):
+        for j in range(8):
+            q = [idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)]
+            if (i + j) % 2 == 0:
+                conn += q
+                off.append(off[-1] + 4)
+            else:
+                conn += [q[0], q[1], q[2]]
+                off.append(off[-1] + 3)
+                conn += [q[0], q[2], q[3]]
+                off.append(off[-1] + 3)
+    return xs, ys, zs, np.array(conn, np.int32), np.array(off, np.int32)
+
+
+def test_mixed_shape_mesh(oracle, have_ref):
+    """mint::UnstructuredMesh<MIXED_SHAPE> (UcdMeshData with cell_node_offsets, quest/SignedDistance.hpp:44-96)"""
+    from axom_b200 import SignedDistance
+    xs, ys, zs, conn, off = _mixed_sheet()
+    rng = np.random.default_rng(4)
+    q = np.concatenate([synth.uniform_grid_points(-1.5, 1.5, 18), rng.uniform(-1, 1, (3000, 3)) * [1, 1, 0.2]])
+    gpu = SignedDistance(xs, ys, zs, conn, isWatertight=False, cell_node_offsets=off)
+    for kind in (["reference"] if have_ref else []) + ["port"]:
+        rphi, rcp, rn = oracle.SignedDistance(xs, ys, zs, conn, watertight=False, offsets=off, kind=kind).compute(q, True, True)
+        for mode in (0, 1):
+            gpu.setMode(mode)
+            gphi, gcp, gn = gpu.computeDistances(q, True, True)
+            assert np.array_equal(rphi, gphi) and np.array_equal(rcp, gcp), (kind, mode)
+            assert np.allclose(rn, gn, rtol=0, atol=1e-12)
+    from axom_b200._lib import AxbError
+    bad = off.copy()
+    bad[1] += 2  # a 6-node "cell" followed by a 1-node one
+    with pytest.raises(AxbError):
+        SignedDistance(xs, ys, zs, conn, isWatertight=False, cell_node_offsets=bad)
