@@ -55,7 +55,11 @@ def test_bad_arguments_are_rejected_without_a_device():
     L = _lib.lib()
     h = ctypes.c_void_p()
     assert L.axb_bvh_create(ctypes.byref(h), 4, 8, 0) == _lib.AXB_ERR_BAD_ARG  # "only in 2D or 3D"
-    assert L.axb_bvh_create(ctypes.byref(h), 3, 4, 0) == _lib.AXB_ERR_UNSUPPORTED
+    assert L.axb_bvh_create(ctypes.byref(h), 3, 2, 0) == _lib.AXB_ERR_BAD_ARG  # FloatType is double or float
+    st = L.axb_bvh_create(ctypes.byref(h), 3, 4, 0)  # float is a valid variant: passes argument checks
+    assert st in (_lib.AXB_ERR_NO_DEVICE, _lib.AXB_OK)
+    if st == _lib.AXB_OK:
+        L.axb_bvh_destroy(h)
     assert L.axb_bvh_create(None, 3, 8, 0) == _lib.AXB_ERR_BAD_ARG
     assert b"2D or 3D" in L.axb_last_error() or True
 
