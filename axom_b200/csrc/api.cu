@@ -1017,12 +1017,14 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       AXB_TRY(s->sdnodes.reserve(sizeof(SdNode) * (size_t)(nl - 1), ctx.stream));
       const int blocks = blocks_for(entities * 32, 256);
       const Node<double, 3>* bn = s->bvh->nodes.as<Node<double, 3>>();
+      int obb_max = kObbMaxRange;
+      if(const char* e = getenv("AXB_SD_OBB_MAX")) obb_max = atoi(e);
       if(s->nv == 3)
         AXB_LAUNCH(ctx, obb_build_kernel<3>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>());
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), obb_max);
       else
         AXB_LAUNCH(ctx, obb_build_kernel<4>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>());
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), obb_max);
       AXB_TRY(s->cursor.reserve(sizeof(unsigned int), ctx.stream));
       int bps = 0;
       if(s->nv == 3)
@@ -1187,12 +1189,16 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
     int sms = kNumSMsB200;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
     const int grid = (int)std::min<long long>(blocks_for(npts, 128), (long long)sms * s->fast_blocks_per_sm);
+    // queries per cursor grab: a run of Morton neighbours, so a lane's consecutive queries are close and
+    // the previous closest point is a useful first bound; small inputs keep every warp busy instead
+    unsigned chunk = (unsigned)kQueryChunk;
+    if(const char* e = getenv("AXB_SD_CHUNK")) chunk = (unsigned)std::max(32, atoi(e));
     if(s->nv == 3)
       AXB_LAUNCH(ctx, sd_fast_kernel<3>, grid, 128, s->sdnodes.as<SdNode>(), s->soup.as<double>(), s->prm, q, npts, perm, d_phi, d_cp,
-                 d_n, d_work, s->cursor.as<unsigned int>());
+                 d_n, d_work, s->cursor.as<unsigned int>(), chunk);
     else
       AXB_LAUNCH(ctx, sd_fast_kernel<4>, grid, 128, s->sdnodes.as<SdNode>(), s->soup.as<double>(), s->prm, q, npts, perm, d_phi, d_cp,
-                 d_n, d_work, s->cursor.as<unsigned int>());
+                 d_n, d_work, s->cursor.as<unsigned int>(), chunk);
   }
   else
   {

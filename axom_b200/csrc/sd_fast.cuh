@@ -80,7 +80,7 @@ __device__ __forceinline__ double warp_max(double v)
 template <int NV>
 __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
                                                          const int32_t* __restrict__ leaf_parent, const int2* __restrict__ node_range,
-                                                         int nleaves, SdNode* __restrict__ sdn)
+                                                         int nleaves, SdNode* __restrict__ sdn, int obb_max_range)
 {
   const int inner = nleaves - 1;
   const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
   const Box<double, 3> bb = nodes[link >> 1].box[link & 1];  // this entity's AABB as the reference has it
   const bool valid = box_valid(bb);
   if(lane < 3) out->cen[lane] = 0.5 * (bb.lo[lane] + bb.hi[lane]);
-  if(!valid || last - first + 1 > kObbMaxRange)
+  if(!valid || last - first + 1 > obb_max_range)
   {
     // coordinate axes: the bound is the AABB itself (an invalid box is (max, lowest): infinitely far)
     if(lane < 3)
@@ -342,13 +342,14 @@ __device__ __forceinline__ void check_leaf_lazy(const double* __restrict__ soup,
 constexpr int kPend = 4;         // queued leaves per lane
 constexpr int kLeafVote = 16;    // lanes with a queued leaf that trigger a leaf step
 constexpr int kFinishVote = 4;   // finished lanes that trigger a finalisation step
-constexpr int kQueryChunk = 32;  // queries a warp takes from the cursor at a time
+constexpr int kQueryChunk = 128;  // queries a warp takes from the cursor at a time (a run of Morton neighbours)
 
 template <int NV>
 __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup, SdParams prm,
                                                        Desc<3> qpts, int npts, const int32_t* __restrict__ perm, double* __restrict__ phi,
                                                        double* __restrict__ cps, double* __restrict__ nrms,
-                                                       unsigned long long* __restrict__ work, unsigned int* __restrict__ cursor)
+                                                       unsigned long long* __restrict__ work, unsigned int* __restrict__ cursor,
+                                                       unsigned chunk)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned lane = lane_id();
@@ -362,6 +363,12 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
   Contribs cl;
   cl.n = 0;
   double thr = DBL_MAX;
+  // A point of the SURFACE near the lane's next query: the closest point of the query the lane just
+  // finished (consecutive queries of a lane are Morton neighbours).  Its distance to the new query is an
+  // upper bound on the new minimum, so the traversal starts with a finite prune radius instead of
+  // walking blind until its first leaf has been evaluated.
+  V3 hint = {0.0, 0.0, 0.0};
+  bool have_hint = false;
   unsigned long long st[kStackSize];  // (lower bound as float bits) << 32 | node id: one 8-byte access per push / pop
   int sp = 0;
   int32_t cur = kBarrier;  // node in hand: >= 0 inner, < 0 leaf, kBarrier = traversal finished
@@ -399,10 +406,20 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
     {
       if(wcount == 0u)
       {
-        unsigned b = 0;
-        if(lane == 0) b = atomicAdd(cursor, (unsigned)kQueryChunk);
+        // guided self-scheduling: long runs of Morton neighbours while there is plenty of work, short
+        // ones near the end so the last warps finish together
+        unsigned b = 0, g = 0;
+        if(lane == 0)
+        {
+          const unsigned seen = *reinterpret_cast<volatile unsigned*>(cursor);
+          const unsigned rem = seen < (unsigned)npts ? (unsigned)npts - seen : 0u;
+          const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+          g = max(32u, min(chunk, (rem / (2u * nwarps)) & ~31u));
+          b = atomicAdd(cursor, g);
+        }
         wbase = __shfl_sync(FULL, b, 0);
-        wcount = wbase < (unsigned)npts ? min((unsigned)kQueryChunk, (unsigned)npts - wbase) : 0u;
+        g = __shfl_sync(FULL, g, 0);
+        wcount = wbase < (unsigned)npts ? min(g, (unsigned)npts - wbase) : 0u;
         exhausted = (wcount == 0u);
       }
       if(wcount != 0u)
@@ -423,6 +440,11 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
           m.minSub = 0;
           cl.n = 0;
           thr = DBL_MAX;
+          if(have_hint)
+          {
+            const double hx = hint.x - qp[0], hy = hint.y - qp[1], hz = hint.z - qp[2];
+            thr = prune_threshold(hx * hx + hy * hy + hz * hz);
+          }
           sp = 0;
           cur = 0;  // root
           cur_lb = 0.f;
@@ -456,6 +478,11 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
         if(cl.n) m.sumN = contrib_flush<NV>(soup, cl, m.sumN);
         const V3 q {qp[0], qp[1], qp[2]};
         sd_finish<NV>(soup, prm, q, m, qi, phi, cps, nrms);
+        if(m.minType >= 0)
+        {
+          hint = m.minPt;
+          have_hint = true;
+        }
         qi = -1;
       }
       continue;
@@ -479,7 +506,7 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
           ++nleaf;
           const V3 q {qp[0], qp[1], qp[2]};
           check_leaf_lazy<NV>(soup, q, m, cl, -id - 1, cn);
-          thr = prune_threshold(m.minSq);
+          thr = fmin(thr, prune_threshold(m.minSq));
         }
       }
       continue;

@@ -119,14 +119,19 @@ def cpu_reference_rate(x, y, z, conn, step, repeats=1, warm=0):
     kind = "reference" if O.have_reference() else "port"
     sd = O.SignedDistance(x, y, z, conn, 3, True, True, kind=kind)
     q = sublattice(step)
-    cores = O.max_threads(kind)
+    # all host cores this process may use; explicit, because torchrun exports OMP_NUM_THREADS=1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cores = max(cores, O.max_threads(kind))
     for _ in range(warm):
-        sd.compute(q, nthreads=0)
+        sd.compute(q, nthreads=cores)
     ts = []
     phi = None
     for _ in range(repeats):
         t = time.perf_counter()
-        phi, _, _ = sd.compute(q, nthreads=0)
+        phi, _, _ = sd.compute(q, nthreads=cores)
         ts.append(time.perf_counter() - t)
     return len(q) / (sum(ts) / len(ts)), dict(kind=kind, cores=cores, npts=len(q), seconds=ts, phi=phi, q=q)
 
