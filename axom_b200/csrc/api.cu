@@ -196,6 +196,14 @@ struct ScopedPhase
     AXB_CUDA_TRY(cudaGetLastError());                                \
   } while(0)
 
+#define AXB_LAUNCH_SMEM(ctx, kernel, grid, block, smem, ...)             \
+  do                                                                    \
+  {                                                                     \
+    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);     \
+    ++(ctx).launches;                                                   \
+    AXB_CUDA_TRY(cudaGetLastError());                                   \
+  } while(0)
+
 static inline int blocks_for(long long n, int block) { return (int)std::max<long long>(1, (n + block - 1) / block); }
 static inline int capped_grid(long long n, int block, int per_sm = 8)
 {
@@ -883,7 +891,7 @@ struct axb_sd
   bool count_work = false;
   SdParams prm;
   DevBuf x, y, z, conn, offsets, soup, cell_boxes, obounds, q_stage, out_phi, out_cp, out_n, work;
-  DevBuf sdnodes, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor;
+  DevBuf sdnodes, sdcens, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor;
   int fast_blocks_per_sm = 0;  // occupancy of the persistent query kernel (queried once)
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
   Ctx& ctx() { return bvh->ctx; }
@@ -1015,22 +1023,47 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
     {
       const long long entities = 2LL * nl - 1;
       AXB_TRY(s->sdnodes.reserve(sizeof(SdNode) * (size_t)(nl - 1), ctx.stream));
+      AXB_TRY(s->sdcens.reserve(sizeof(SdCen) * (size_t)(nl - 1), ctx.stream));
       const int blocks = blocks_for(entities * 32, 256);
       const Node<double, 3>* bn = s->bvh->nodes.as<Node<double, 3>>();
       int obb_max = kObbMaxRange;
       if(const char* e = getenv("AXB_SD_OBB_MAX")) obb_max = atoi(e);
+      // subtrees of more than kObbWarpRange leaves are queued and bounded by whole blocks
+      DevBuf big;
+      const size_t big_cap = (size_t)std::max(nl - 1, 1);
+      AXB_TRY(big.reserve(sizeof(int32_t) * (big_cap + 1), ctx.stream));
+      unsigned int* big_count = big.as<unsigned int>();
+      int32_t* big_list = big.as<int32_t>() + 1;
+      AXB_CUDA_TRY(cudaMemsetAsync(big_count, 0, sizeof(unsigned int), ctx.stream));
+      int sms = kNumSMsB200;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
       if(s->nv == 3)
+      {
         AXB_LAUNCH(ctx, obb_build_kernel<3>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), obb_max);
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, big_list, big_count);
+        AXB_LAUNCH(ctx, obb_build_big_kernel<3>, 2 * sms, 512, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
+                   s->sdnodes.as<SdNode>(), big_list, big_count);
+      }
       else
+      {
         AXB_LAUNCH(ctx, obb_build_kernel<4>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), obb_max);
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, big_list, big_count);
+        AXB_LAUNCH(ctx, obb_build_big_kernel<4>, 2 * sms, 512, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
+                   s->sdnodes.as<SdNode>(), big_list, big_count);
+      }
+      big.release(ctx.stream);
       AXB_TRY(s->cursor.reserve(sizeof(unsigned int), ctx.stream));
       int bps = 0;
       if(s->nv == 3)
-        AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_fast_kernel<3>, 128, 0));
+      {
+        AXB_CUDA_TRY(cudaFuncSetAttribute(sd_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdFastSmem));
+        AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_fast_kernel<3>, 128, kSdFastSmem));
+      }
       else
-        AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_fast_kernel<4>, 128, 0));
+      {
+        AXB_CUDA_TRY(cudaFuncSetAttribute(sd_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdFastSmem));
+        AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_fast_kernel<4>, 128, kSdFastSmem));
+      }
       s->fast_blocks_per_sm = std::max(1, bps);
     }
     return ctx.sync();
@@ -1053,7 +1086,7 @@ int axb_sd_destroy(axb_sd* s)
     cudaSetDevice(s->ctx().device);
     cudaStream_t st = s->ctx().stream;
     for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->offsets, &s->soup, &s->cell_boxes, &s->obounds, &s->q_stage, &s->out_phi, &s->out_cp,
-                     &s->out_n, &s->work, &s->sdnodes, &s->qkeys_a, &s->qkeys_b, &s->qscratch, &s->qperm, &s->qbounds, &s->cursor})
+                     &s->out_n, &s->work, &s->sdnodes, &s->sdcens, &s->qkeys_a, &s->qkeys_b, &s->qscratch, &s->qperm, &s->qbounds, &s->cursor})
       b->release(st);
     axb_bvh_destroy(s->bvh);
   }
@@ -1194,11 +1227,11 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
     unsigned chunk = (unsigned)kQueryChunk;
     if(const char* e = getenv("AXB_SD_CHUNK")) chunk = (unsigned)std::max(32, atoi(e));
     if(s->nv == 3)
-      AXB_LAUNCH(ctx, sd_fast_kernel<3>, grid, 128, s->sdnodes.as<SdNode>(), s->soup.as<double>(), s->prm, q, npts, perm, d_phi, d_cp,
-                 d_n, d_work, s->cursor.as<unsigned int>(), chunk);
+      AXB_LAUNCH_SMEM(ctx, sd_fast_kernel<3>, grid, 128, kSdFastSmem, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->soup.as<double>(), s->prm, q,
+                      npts, perm, d_phi, d_cp, d_n, d_work, s->cursor.as<unsigned int>(), chunk);
     else
-      AXB_LAUNCH(ctx, sd_fast_kernel<4>, grid, 128, s->sdnodes.as<SdNode>(), s->soup.as<double>(), s->prm, q, npts, perm, d_phi, d_cp,
-                 d_n, d_work, s->cursor.as<unsigned int>(), chunk);
+      AXB_LAUNCH_SMEM(ctx, sd_fast_kernel<4>, grid, 128, kSdFastSmem, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->soup.as<double>(), s->prm, q,
+                      npts, perm, d_phi, d_cp, d_n, d_work, s->cursor.as<unsigned int>(), chunk);
   }
   else
   {

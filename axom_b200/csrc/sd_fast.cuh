@@ -28,32 +28,47 @@
 
 namespace axb
 {
-// What the fast traversal keeps per CHILD of an inner node: the centroid of the child's AABB (the
-// reference orders children by it, LinearBVH.hpp:72-85; precomputed with the reference's own
-// 0.5*(min+max)) and an oriented bound: unit axes n, t1 (t2 = n x t1 is recomputed), and the extent
-// lo[k] <= axis_k . x <= hi[k] of every vertex below the child.  Large subtrees (no useful
-// orientation) and invalid boxes use the coordinate axes, i.e. the oriented bound IS the AABB.
-struct ChildBound
-{
-  double cen[3];
-  double n[3];
-  double t1[3];
-  double lo[3];
-  double hi[3];
-};
-
-// Traversal record of the fast path: everything one inner-node visit needs in ONE aligned 256-byte
-// read (8 x LDG.256 per lane).  The reference-layout view for getTraverser() and the reference-order
-// kernel keep using Node<>.
+// What the fast traversal keeps per CHILD of an inner node: an oriented bound -- unit axes n, t1
+// (t2 = n x t1 is recomputed) and the extent lo[k] <= axis_k . (x - org) <= hi[k] of every vertex x below
+// the child, org being a point of the PARENT (the centroid of its AABB) so the numbers are node-sized and
+// survive storage in binary32: axes rounded to float, extents rounded OUTWARD to float.  All arithmetic
+// on them is done in double on the exactly-converted floats (build and query share obb_axes()), so the
+// bound stays conservative; the frame is orthonormal only to ~1e-7, which bound_scale accounts for.
+// Large subtrees (no useful orientation) and invalid boxes use the coordinate axes: the bound is the AABB.
+//
+// Traversal record of the fast path: everything one inner-node visit needs in ONE aligned 128-byte line
+// (4 x LDG.256 per lane).  A lane reads its own record, nothing coalesces, every 32-byte sector is one
+// L1 wavefront -- the limiter of this kernel (profiles/r1c: l1tex 83 %) -- so bytes per visit are what
+// counts.  The centroids of the child AABBs (the reference orders children by them, LinearBVH.hpp:72-85;
+// precomputed with the reference's own 0.5*(min+max), kept in double because the ORDER must be exact)
+// live in a second 64-byte record that is read only when both children are entered.
+// The reference-layout view for getTraverser() and the reference-order kernel keep using Node<>.
 struct alignas(32) SdNode
 {
   int32_t child[2];  // >= 0 inner node, < 0 leaf -(sorted_pos+1)
-  double pad_;
-  ChildBound cb[2];  // 2 x 120 B
+  double org[3];
+  float cb[2][12];  // per child: n[3], t1[3], lo[3], hi[3]
 };
-static_assert(sizeof(SdNode) == 256, "SdNode is 8 x 32 B");
+static_assert(sizeof(SdNode) == 128, "SdNode is 4 x 32 B");
+struct alignas(32) SdCen
+{
+  double cen[2][3];
+  double pad_[2];
+};
+static_assert(sizeof(SdCen) == 64, "SdCen is 2 x 32 B");
 
-constexpr int kObbMaxRange = 4096;  // subtrees with more leaves keep only their AABB (top ~9 levels)
+// |M v|^2 <= (1 + 5e-7) |v|^2 for the rows M of a float-rounded frame: scale the bound down accordingly
+constexpr double kBoundScale = 1.0 - 1.0e-6;
+
+// the frame in double from the stored floats; the build and the query MUST agree bit for bit on t2
+__device__ __forceinline__ void obb_axes(const float* f, V3* A)
+{
+  A[0] = {(double)f[0], (double)f[1], (double)f[2]};
+  A[1] = {(double)f[3], (double)f[4], (double)f[5]};
+  A[2] = v3cross(A[0], A[1]);
+}
+
+constexpr int kObbMaxRange = 262144;  // subtrees with more leaves keep only their AABB (an orientation no longer helps)
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -76,50 +91,54 @@ __device__ __forceinline__ double warp_max(double v)
 
 // One warp per tree entity e: e < inner -> inner node e (leaves node_range[e]), else leaf e - inner.
 // The oriented bound of entity e is stored in its PARENT's record (slot = which child it is); the warp
-// of an inner entity also copies that node's child AABBs and ids into its own record.
-template <int NV>
-__global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
-                                                         const int32_t* __restrict__ leaf_parent, const int2* __restrict__ node_range,
-                                                         int nleaves, SdNode* __restrict__ sdn, int obb_max_range)
+// of an inner entity also writes that node's child ids and origin into its own record.
+__device__ __forceinline__ void node_origin(const Node<double, 3>& nd, double* org)
 {
-  const int inner = nleaves - 1;
-  const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  if(e >= inner + nleaves) return;
-  const int lane = (int)lane_id();
-  int first, last, link;
-  if(e < inner)
+  Box<double, 3> u = nd.box[0];
+  box_add(u, nd.box[1]);
+#pragma unroll
+  for(int d = 0; d < 3; ++d) org[d] = box_valid(u) ? 0.5 * (u.lo[d] + u.hi[d]) : 0.0;
+}
+
+// Reductions over the threads that share one entity: a warp (small subtrees) or a whole block (big ones)
+struct WarpGroup
+{
+  __device__ __forceinline__ int rank() const { return (int)lane_id(); }
+  __device__ __forceinline__ int size() const { return 32; }
+  __device__ __forceinline__ double sum(double v) const { return warp_sum(v); }
+  __device__ __forceinline__ double min(double v) const { return warp_min(v); }
+  __device__ __forceinline__ double max(double v) const { return warp_max(v); }
+};
+struct BlockGroup
+{
+  double* sh;  // 32 doubles of shared memory
+  __device__ __forceinline__ int rank() const { return (int)threadIdx.x; }
+  __device__ __forceinline__ int size() const { return (int)blockDim.x; }
+  template <typename F>
+  __device__ __forceinline__ double reduce(double v, double identity, F f) const
   {
-    const int2 r = node_range[e];
-    first = r.x;
-    last = r.y;
-    link = nodes[e].parent;
-    if(lane < 2) sdn[e].child[lane] = nodes[e].child[lane];
+    v = f(v);
+    __syncthreads();
+    if(lane_id() == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double w = (lane_id() < (blockDim.x >> 5)) ? sh[lane_id()] : identity;
+    return f(w);
   }
-  else
-  {
-    first = last = e - inner;
-    link = leaf_parent[first];
-  }
-  if(link < 0) return;  // the root is nobody's child
-  ChildBound* out = &sdn[link >> 1].cb[link & 1];
-  const Box<double, 3> bb = nodes[link >> 1].box[link & 1];  // this entity's AABB as the reference has it
-  const bool valid = box_valid(bb);
-  if(lane < 3) out->cen[lane] = 0.5 * (bb.lo[lane] + bb.hi[lane]);
-  if(!valid || last - first + 1 > obb_max_range)
-  {
-    // coordinate axes: the bound is the AABB itself (an invalid box is (max, lowest): infinitely far)
-    if(lane < 3)
-    {
-      out->n[lane] = lane == 0 ? 1.0 : 0.0;
-      out->t1[lane] = lane == 1 ? 1.0 : 0.0;
-      out->lo[lane] = bb.lo[lane];
-      out->hi[lane] = bb.hi[lane];
-    }
-    return;
-  }
+  __device__ __forceinline__ double sum(double v) const { return reduce(v, 0.0, [](double x) { return warp_sum(x); }); }
+  __device__ __forceinline__ double min(double v) const { return reduce(v, DBL_MAX, [](double x) { return warp_min(x); }); }
+  __device__ __forceinline__ double max(double v) const { return reduce(v, -DBL_MAX, [](double x) { return warp_max(x); }); }
+};
+
+// oriented bound of the leaves [first, last] written into slot `link` of the parent's record
+template <int NV, typename Group>
+__device__ __forceinline__ void obb_of_range(const Group& g, const double* __restrict__ soup, int first, int last, const double* org,
+                                             float* __restrict__ out)
+{
+  const int t = g.rank(), nt = g.size();
+  const double omag = fabs(org[0]) + fabs(org[1]) + fabs(org[2]);
   // pass 1: area-weighted normal sum
   double nx = 0.0, ny = 0.0, nz = 0.0;
-  for(int p = first + lane; p <= last; p += 32)
+  for(int p = first + t; p <= last; p += nt)
   {
     V3 v[NV];
     load_leaf<NV>(soup, p, v);
@@ -129,9 +148,9 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     ny += c.y;
     nz += c.z;
   }
-  nx = warp_sum(nx);
-  ny = warp_sum(ny);
-  nz = warp_sum(nz);
+  nx = g.sum(nx);
+  ny = g.sum(ny);
+  nz = g.sum(nz);
   double len2 = nx * nx + ny * ny + nz * nz;
   V3 n;
   if(len2 > 1e-280 && len2 < 1e280)
@@ -151,11 +170,13 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     const double s = 1.0 / sqrt(v3dot(t1, t1));
     t1 = v3mul(t1, s);
   }
-  const V3 t2 = v3cross(n, t1);
-  const V3 A[3] = {n, t1, t2};
-  // pass 2: extents of all vertices along the frame
+  // the stored frame: axes rounded to float, then everything below uses exactly what the query will see
+  float fr[6] = {(float)n.x, (float)n.y, (float)n.z, (float)t1.x, (float)t1.y, (float)t1.z};
+  V3 A[3];
+  obb_axes(fr, A);
+  // pass 2: extents of all vertices along the frame, relative to the parent's origin
   double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-  for(int p = first + lane; p <= last; p += 32)
+  for(int p = first + t; p <= last; p += nt)
   {
     V3 v[NV];
     load_leaf<NV>(soup, p, v);
@@ -163,10 +184,11 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     for(int j = 0; j < NV; ++j)
     {
       if(j == 3 && !has_fourth(v[j])) continue;  // triangle cell of a mixed mesh
+      const double rx = v[j].x - org[0], ry = v[j].y - org[1], rz = v[j].z - org[2];
 #pragma unroll
       for(int k = 0; k < 3; ++k)
       {
-        const double d = A[k].x * v[j].x + A[k].y * v[j].y + A[k].z * v[j].z;
+        const double d = A[k].x * rx + A[k].y * ry + A[k].z * rz;
         lo[k] = fmin(lo[k], d);
         hi[k] = fmax(hi[k], d);
       }
@@ -175,44 +197,126 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
 #pragma unroll
   for(int k = 0; k < 3; ++k)
   {
-    lo[k] = warp_min(lo[k]);
-    hi[k] = warp_max(hi[k]);
+    lo[k] = g.min(lo[k]);
+    hi[k] = g.max(hi[k]);
   }
-  if(lane == 0)
+  if(t == 0)
   {
-    out->n[0] = n.x;
-    out->n[1] = n.y;
-    out->n[2] = n.z;
-    out->t1[0] = t1.x;
-    out->t1[1] = t1.y;
-    out->t1[2] = t1.z;
+#pragma unroll
+    for(int k = 0; k < 6; ++k) out[k] = fr[k];
 #pragma unroll
     for(int k = 0; k < 3; ++k)
     {
-      // pad by the rounding of the projections (a few ulp of the coordinate magnitude)
-      const double pad = 1e-14 * (fabs(lo[k]) + fabs(hi[k])) + 1e-300;
-      out->lo[k] = lo[k] - pad;
-      out->hi[k] = hi[k] + pad;
+      // pad by the rounding of the projections (a few ulp of the coordinate magnitude), then round outward
+      const double pad = 1e-14 * (fabs(lo[k]) + fabs(hi[k]) + omag) + 1e-300;
+      out[6 + k] = __double2float_rd(lo[k] - pad);
+      out[9 + k] = __double2float_ru(hi[k] + pad);
     }
   }
 }
 
-// squared distance lower bound from q to the oriented box of a child, c = the 15 doubles of its
-// ChildBound (FMA is fine here: it only has to be a bound; t2 must be the build's n x t1, bit for bit)
-__device__ __forceinline__ double obb_sqdist(const double* c, const double* q)
+constexpr int kObbWarpRange = 4096;  // subtrees up to this many leaves are bounded by one warp, larger ones by a block
+
+template <int NV>
+__global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
+                                                         const int32_t* __restrict__ leaf_parent, const int2* __restrict__ node_range,
+                                                         int nleaves, SdNode* __restrict__ sdn, SdCen* __restrict__ sdc, int obb_max_range,
+                                                         int32_t* __restrict__ big_list, unsigned int* __restrict__ big_count)
 {
-  const V3 n {c[3], c[4], c[5]}, t1 {c[6], c[7], c[8]};
-  const V3 t2 = v3cross(n, t1);
-  const V3 A[3] = {n, t1, t2};
+  const int inner = nleaves - 1;
+  const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if(e >= inner + nleaves) return;
+  const int lane = (int)lane_id();
+  int first, last, link;
+  if(e < inner)
+  {
+    const int2 r = node_range[e];
+    first = r.x;
+    last = r.y;
+    link = nodes[e].parent;
+    if(lane < 2) sdn[e].child[lane] = nodes[e].child[lane];
+    double o[3];
+    node_origin(nodes[e], o);
+    if(lane < 3) sdn[e].org[lane] = o[lane];
+  }
+  else
+  {
+    first = last = e - inner;
+    link = leaf_parent[first];
+  }
+  if(link < 0) return;  // the root is nobody's child
+  float* out = sdn[link >> 1].cb[link & 1];
+  double org[3];
+  node_origin(nodes[link >> 1], org);
+  const Box<double, 3> bb = nodes[link >> 1].box[link & 1];  // this entity's AABB as the reference has it
+  const bool valid = box_valid(bb);
+  if(lane < 3) sdc[link >> 1].cen[link & 1][lane] = 0.5 * (bb.lo[lane] + bb.hi[lane]);
+  const int count = last - first + 1;
+  if(!valid || count > obb_max_range)
+  {
+    // coordinate axes: the bound is the AABB itself (an invalid box is infinitely far)
+    if(lane < 3)
+    {
+      const double omag = fabs(org[0]) + fabs(org[1]) + fabs(org[2]);
+      out[lane] = lane == 0 ? 1.f : 0.f;
+      out[3 + lane] = lane == 1 ? 1.f : 0.f;
+      if(valid)
+      {
+        const double lo = bb.lo[lane] - org[lane], hi = bb.hi[lane] - org[lane];
+        const double pad = 1e-14 * (fabs(lo) + fabs(hi) + omag) + 1e-300;
+        out[6 + lane] = __double2float_rd(lo - pad);
+        out[9 + lane] = __double2float_ru(hi + pad);
+      }
+      else
+      {
+        out[6 + lane] = __int_as_float(0x7f800000);  // +inf
+        out[9 + lane] = __int_as_float(0xff800000);  // -inf
+      }
+    }
+    return;
+  }
+  if(count > kObbWarpRange)
+  {
+    if(lane == 0) big_list[atomicAdd(big_count, 1u)] = e;  // left to obb_build_big_kernel
+    return;
+  }
+  obb_of_range<NV>(WarpGroup {}, soup, first, last, org, out);
+}
+
+// the big subtrees queued by obb_build_kernel: one block per entity
+template <int NV>
+__global__ void __launch_bounds__(512) obb_build_big_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
+                                                             const int2* __restrict__ node_range, SdNode* __restrict__ sdn,
+                                                             const int32_t* __restrict__ big_list, const unsigned int* __restrict__ big_count)
+{
+  __shared__ double sh[32];
+  const unsigned n = *big_count;
+  for(unsigned i = blockIdx.x; i < n; i += gridDim.x)
+  {
+    const int e = big_list[i];
+    const int2 r = node_range[e];
+    const int link = nodes[e].parent;
+    double org[3];
+    node_origin(nodes[link >> 1], org);
+    obb_of_range<NV>(BlockGroup {sh}, soup, r.x, r.y, org, sdn[link >> 1].cb[link & 1]);
+  }
+}
+
+// squared distance lower bound from the query to the oriented box of a child: f = the 12 floats of the
+// child's bound, r = q - org (FMA is fine here: it only has to be a bound)
+__device__ __forceinline__ double obb_sqdist(const float* f, const double* r)
+{
+  V3 A[3];
+  obb_axes(f, A);
   double s = 0.0;
 #pragma unroll
   for(int k = 0; k < 3; ++k)
   {
-    const double d = fma(A[k].x, q[0], fma(A[k].y, q[1], A[k].z * q[2]));
-    const double g = fmax(fmax(c[9 + k] - d, d - c[12 + k]), 0.0);
+    const double d = fma(A[k].x, r[0], fma(A[k].y, r[1], A[k].z * r[2]));
+    const double g = fmax(fmax((double)f[6 + k] - d, d - (double)f[9 + k]), 0.0);
     s = fma(g, g, s);
   }
-  return s;
+  return s * kBoundScale;
 }
 
 // prune threshold on squared distance: everything that could still improve the minimum or tie with it
@@ -339,13 +443,15 @@ __device__ __forceinline__ void check_leaf_lazy(const double* __restrict__ soup,
 // Each lane still walks the tree in the reference's child order with a (node, lower bound) stack, so
 // everything said in the header about bit-identical results holds.
 //------------------------------------------------------------------------------------------
+constexpr int kSmemStack = 32;   // stack levels kept in shared memory (the rest, rarely reached, in local memory)
+constexpr size_t kSdFastSmem = (size_t)kSmemStack * 128 * sizeof(unsigned long long);  // 128 threads per block
 constexpr int kPend = 4;         // queued leaves per lane
 constexpr int kLeafVote = 16;    // lanes with a queued leaf that trigger a leaf step
 constexpr int kFinishVote = 4;   // finished lanes that trigger a finalisation step
 constexpr int kQueryChunk = 128;  // queries a warp takes from the cursor at a time (a run of Morton neighbours)
 
 template <int NV>
-__global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup, SdParams prm,
+__global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__ nodes, const SdCen* __restrict__ cens, const double* __restrict__ soup, SdParams prm,
                                                        Desc<3> qpts, int npts, const int32_t* __restrict__ perm, double* __restrict__ phi,
                                                        double* __restrict__ cps, double* __restrict__ nrms,
                                                        unsigned long long* __restrict__ work, unsigned int* __restrict__ cursor,
@@ -369,8 +475,22 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
   // walking blind until its first leaf has been evaluated.
   V3 hint = {0.0, 0.0, 0.0};
   bool have_hint = false;
-  unsigned long long st[kStackSize];  // (lower bound as float bits) << 32 | node id: one 8-byte access per push / pop
+  // Traversal stack, entries (lower bound as float bits) << 32 | node id.  The first kSmemStack levels live
+  // in shared memory as [level][thread]: whatever level each lane is at, lane t touches bank pair t, so a
+  // push or pop is 2 wavefronts for the warp -- in local memory lanes at different depths hit different
+  // lines (up to 64 wavefronts, and the spills went to DRAM: 2.9 GB of writes in profiles/r1c).
+  extern __shared__ unsigned long long sstack[];
+  unsigned long long st_over[kStackSize - kSmemStack];
+  unsigned long long* const my_stack = sstack + threadIdx.x;
+  const unsigned stride = blockDim.x;
   int sp = 0;
+  auto st_get = [&](int k) -> unsigned long long { return k < kSmemStack ? my_stack[(unsigned)k * stride] : st_over[k - kSmemStack]; };
+  auto st_put = [&](int k, unsigned long long e) {
+    if(k < kSmemStack)
+      my_stack[(unsigned)k * stride] = e;
+    else
+      st_over[k - kSmemStack] = e;
+  };
   int32_t cur = kBarrier;  // node in hand: >= 0 inner, < 0 leaf, kBarrier = traversal finished
   float cur_lb = 0.f;
   int32_t pend_id[kPend];
@@ -387,7 +507,7 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
     while(sp > 0)
     {
       --sp;
-      const unsigned long long e = st[sp];
+      const unsigned long long e = st_get(sp);
       const float lb = __uint_as_float((unsigned)(e >> 32));
       if((double)lb <= thr)
       {
@@ -531,20 +651,22 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
       {
         ++ninner;
         const D4* rec = reinterpret_cast<const D4*>(nodes + cur);
-        double a[32];
-#pragma unroll
-        for(int k = 0; k < 8; ++k)
-        {
-          const D4 r = ldg256(rec + k);
-          a[4 * k + 0] = r.x;
-          a[4 * k + 1] = r.y;
-          a[4 * k + 2] = r.z;
-          a[4 * k + 3] = r.w;
-        }
-        const long long ids = __double_as_longlong(a[0]);
+        const D4 r0 = ldg256(rec), r1 = ldg256(rec + 1), r2 = ldg256(rec + 2), r3 = ldg256(rec + 3);
+        const long long ids = __double_as_longlong(r0.x);
         const int32_t child0 = (int32_t)(ids & 0xffffffffll), child1 = (int32_t)(ids >> 32);
+        const double rq[3] = {qp[0] - r0.y, qp[1] - r0.z, qp[2] - r0.w};
+        float f[24];
+        {
+          const double w[12] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+#pragma unroll
+          for(int k = 0; k < 12; ++k)
+          {
+            f[2 * k] = __int_as_float(__double2loint(w[k]));
+            f[2 * k + 1] = __int_as_float(__double2hiint(w[k]));
+          }
+        }
         // an invalid box is infinitely far (bvh_traverse.hpp:95-96)
-        const double d20 = obb_sqdist(a + 2, qp), d21 = obb_sqdist(a + 17, qp);
+        const double d20 = obb_sqdist(f, rq), d21 = obb_sqdist(f + 12, rq);
         const bool in0 = d20 <= thr, in1 = d21 <= thr;
         // Child order = the reference's (LinearBVH.hpp:72-85): when both children are entered, the one whose
         // AABB centroid is nearer goes first and the other waits on the stack -- leaf or not -- until
@@ -553,19 +675,22 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
         // summation order of the pseudo-normal are the reference's.
         if(in0 && in1)
         {
+          const D4* cr = reinterpret_cast<const D4*>(cens + cur);
+          const D4 c0 = ldg256(cr), c1 = ldg256(cr + 1);
+          const double cl3[3] = {c0.x, c0.y, c0.z}, cr3[3] = {c0.w, c1.x, c1.y};
           double dl = 0.0, dr = 0.0;
 #pragma unroll
           for(int d = 0; d < 3; ++d)
           {
-            const double cl_ = a[2 + d] - qp[d];
+            const double cl_ = cl3[d] - qp[d];
             dl += cl_ * cl_;
-            const double cr_ = a[17 + d] - qp[d];
+            const double cr_ = cr3[d] - qp[d];
             dr += cr_ * cr_;
           }
           const bool right_first = dl > dr;
           const int32_t c_second = right_first ? child0 : child1;
           const double d_second = right_first ? d20 : d21;
-          st[sp] = ((unsigned long long)__float_as_uint(__double2float_rd(d_second)) << 32) | (unsigned)c_second;
+          st_put(sp, ((unsigned long long)__float_as_uint(__double2float_rd(d_second)) << 32) | (unsigned)c_second);
           ++sp;
           cur = right_first ? child1 : child0;
           cur_lb = __double2float_rd(right_first ? d21 : d20);
