@@ -294,7 +294,8 @@ struct axb_bvh
   double bounds_lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
   double bounds_hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
 
-  DevBuf nodes, leaf_nodes, leaf_parent, node_range, keys_a, keys_b, state, sort_scratch, stage_in;
+  DevBuf nodes, leaf_nodes, leaf_parent, node_range, keys_a, keys_b, state, sort_scratch, stage_in, agglo_slots, agglo_flags;
+  bool legacy_build = false;  // AXB_BUILD_LEGACY=1: tree_kernel + refit_kernel instead of agglo_kernel
   unsigned long long* sorted_keys = nullptr;  // points into keys_a or keys_b
   DevBuf ref_inner_nodes, ref_children;       // reference-layout view, built lazily
   bool ref_view_valid = false;
@@ -307,7 +308,7 @@ struct axb_bvh
   void release_all()
   {
     cudaStream_t s = ctx.stream;
-    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &node_range, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &ref_inner_nodes,
+    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &node_range, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &agglo_slots, &agglo_flags, &ref_inner_nodes,
                      &ref_children, &q_stage, &q_counts, &q_offsets, &q_tiles, &q_total, &f_keys_a, &f_keys_b, &f_scratch, &f_perm, &f_pairs,
                      &f_unused, &f_cursor})
       b->release(s);
@@ -387,21 +388,48 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
     ScopedPhase ph(ctx, "build.sort");
     AXB_TRY(sort_keys(h, n, ghist, tile_counters, lookback));
   }
+  const bool legacy = h->legacy_build;
+  auto legacy_tree_refit = [&]() -> int {
+    {
+      ScopedPhase ph(ctx, "build.tree");
+      AXB_LAUNCH(ctx, (tree_kernel<T, D>), blocks_for(inner, 256), 256, h->sorted_keys, n, h->nodes.as<Node<T, D>>(),
+                 h->leaf_parent.as<int32_t>(), h->node_range.as<int2>());
+    }
+    {
+      ScopedPhase ph(ctx, "build.refit");
+      AXB_LAUNCH(ctx, (refit_kernel<T, D>), blocks_for(n, 256), 256, in, n, num_boxes, half_scale, h->sorted_keys,
+                 h->leaf_parent.as<int32_t>(), h->nodes.as<Node<T, D>>(), h->leaf_nodes.as<int32_t>());
+    }
+    return AXB_OK;
+  };
+  if(legacy)
   {
-    ScopedPhase ph(ctx, "build.tree");
-    AXB_LAUNCH(ctx, (tree_kernel<T, D>), blocks_for(inner, 256), 256, h->sorted_keys, n, h->nodes.as<Node<T, D>>(),
-               h->leaf_parent.as<int32_t>(), h->node_range.as<int2>());
+    AXB_TRY(legacy_tree_refit());
   }
+  else
   {
-    ScopedPhase ph(ctx, "build.refit");
-    AXB_LAUNCH(ctx, (refit_kernel<T, D>), blocks_for(n, 256), 256, in, n, num_boxes, half_scale, h->sorted_keys,
-               h->leaf_parent.as<int32_t>(), h->nodes.as<Node<T, D>>(), h->leaf_nodes.as<int32_t>());
+    // fused bottom-up hierarchy + refit (build.cuh: agglo_kernel)
+    ScopedPhase ph(ctx, "build.agglo");
+    constexpr int AB = 512;
+    AXB_TRY(h->agglo_slots.reserve(sizeof(AggloSlot<T, D>) * (size_t)n, ctx.stream));
+    AXB_TRY(h->agglo_flags.reserve(sizeof(uint32_t) * (size_t)inner, ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(h->agglo_flags.p, 0, sizeof(uint32_t) * (size_t)inner, ctx.stream));
+    AXB_LAUNCH(ctx, (agglo_kernel<T, D, AB>), blocks_for(n, AB), AB, in, n, num_boxes, half_scale, h->sorted_keys,
+               h->nodes.as<Node<T, D>>(), h->leaf_nodes.as<int32_t>(), h->leaf_parent.as<int32_t>(), h->node_range.as<int2>(),
+               h->agglo_slots.as<AggloSlot<T, D>>(), h->agglo_flags.as<uint32_t>(), &st->agglo_mismatch);
   }
   ctx.phase_end(tot);
   // bounds come back to the host (getBounds() is a host query); this is also the build's sync point
   BuildState<T, D> hst;
   AXB_CUDA_TRY(cudaMemcpyAsync(&hst, st, sizeof(hst), cudaMemcpyDeviceToHost, ctx.stream));
   AXB_TRY(ctx.sync());
+  if(!legacy && hst.agglo_mismatch)
+  {
+    // a >2^24-leaf node where the reference's float32 split search leaves the exact Karras split:
+    // rebuild the hierarchy with the reference-order search
+    AXB_TRY(legacy_tree_refit());
+    AXB_TRY(ctx.sync());
+  }
   for(int d = 0; d < 3; ++d)
   {
     h->bounds_lo[d] = d < D ? (double)hst.bmin[d] : 0.0;
@@ -647,6 +675,7 @@ int axb_bvh_create(axb_bvh** out, int ndims, int fp_bytes, int device)
   h->ndims = ndims;
   h->fp_bytes = fp_bytes;
   if(fp_bytes == 4) h->tol = FLT_EPSILON;  // DEFAULT_TOLERANCE = floating_point_limits<FloatType>::epsilon()
+  if(const char* e = getenv("AXB_BUILD_LEGACY")) h->legacy_build = atoi(e) != 0;
   int s = h->ctx.init(device);
   if(s != AXB_OK)
   {

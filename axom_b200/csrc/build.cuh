@@ -26,6 +26,7 @@ struct BuildState
   T bmin[D];                   // decoded bounds (getBounds())
   T bmax[D];
   T inv_extent[D];             // build_radix_tree.hpp:160-163
+  uint32_t agglo_mismatch;     // agglo_kernel: a >2^24-leaf node whose float32 split search differs (see there)
 };
 
 template <typename T, int D>
@@ -38,6 +39,7 @@ __global__ void init_state_kernel(BuildState<T, D>* st)
       st->omin[d] = f64_to_ordered((double)Lim<T>::max());
       st->omax[d] = f64_to_ordered((double)Lim<T>::lowest());
     }
+    st->agglo_mismatch = 0u;
   }
 }
 
@@ -341,6 +343,215 @@ __global__ void __launch_bounds__(256) refit_kernel(Desc<2 * D> boxes, int n, in
     const Box<T, D> other = load_box_cg(&nodes[p].box[side ^ 1]);
     box_add(aabb, other);  // aabb.addBox(other_aabb) (:567)
     link = nodes[p].parent;
+  }
+}
+
+//------------------------------------------------------------------------------------------
+// Fused hierarchy + refit ("agglomerative" bottom-up build, Apetrei 2014), the default path.
+//
+// The reference emits the Karras tree top-down (build_tree, :290-384: one binary search per inner
+// node over the sorted codes) and then refits bottom-up (propagate_aabbs, :505-576).  Both are
+// functions of the adjacent-key deltas only: a node covering sorted leaves [l, r] is the left child
+// of the node that splits at r when delta(r, r+1) > delta(l-1, l), else the right child of the node
+// that splits at l-1 (ties are impossible: keys are distinct once the sorted position breaks code
+// ties, :276-279).  Karras numbers a left child by its split (= its range's right end) and a right
+// child by split+1 (= its range's left end), so a node's reference index, its children's ids and its
+// range are all known the moment its two children have met -- no top-down search is needed, and
+// the tree comes out bit-identical (checked against the reference-order search for ranges above 2^24
+// leaves, where build_tree's float32(l) rounding could in principle pick another split; a mismatch
+// raises BuildState::agglo_mismatch and the host re-runs tree_kernel + refit_kernel).
+//
+// One thread per sorted leaf, B leaves per block.  Children whose parent's range lies inside the
+// block meet through shared memory (a slot per child index, an arrival flag per split); the few
+// block-straddling nodes meet through a global slot array with a release/acquire RMW.  Each finished
+// node is written once, complete: 96 B of child boxes + child ids + range; parents of the children.
+// HBM traffic per leaf: 8 B key + 48 B gathered box in, 128 B node record + 4 B leaf id + 12 B links out.
+//------------------------------------------------------------------------------------------
+template <typename T, int D>
+struct alignas(16) AggloSlot
+{
+  Box<T, D> box;
+  int32_t end;  // far end of the arriving child's leaf range
+};
+
+__device__ __forceinline__ int adj_delta(unsigned long long kj, unsigned long long kj1, int j)
+{
+  // delta(j, j+1) of :265-287 on (code << 32 | sorted position)
+  const unsigned long long a = (kj & 0xffffffff00000000ull) | (unsigned long long)(uint32_t)j;
+  const unsigned long long b = (kj1 & 0xffffffff00000000ull) | (unsigned long long)(uint32_t)(j + 1);
+  return __clzll((long long)(a ^ b));
+}
+
+// build_tree's split search (:333-348) for a node with index i, direction d, length l whose true
+// split is `gam`: delta(i, i+(s+t)d) > delta_node holds exactly while i+(s+t)d stays on i's side.
+template <typename T>
+__device__ __noinline__ bool reference_split_agrees(int lo, int hi, int gam, bool index_is_lo)
+{
+  const int d = index_is_lo ? 1 : -1;
+  const int i = index_is_lo ? lo : hi;
+  const int l = hi - lo;
+  int s = 0;
+  T div_factor = (T)2;
+  const T lf = (T)(float)l;
+  for(int t = (int)ceil(lf / div_factor);; div_factor *= 2, t = (int)ceil(lf / div_factor))
+  {
+    const long long x = (long long)i + (long long)(s + t) * d;
+    const bool same_side = d > 0 ? (x <= gam) : (x >= gam + 1);
+    if(same_side) s += t;
+    if(t == 1) break;
+  }
+  return i + s * d + (d < 0 ? d : 0) == gam;
+}
+
+template <typename T, int D, int B>
+__global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, int n, int n_real, T half_scale,
+                                                   const unsigned long long* __restrict__ keys, Node<T, D>* nodes,
+                                                   int32_t* __restrict__ leaf_nodes, int32_t* leaf_parent, int2* __restrict__ node_range,
+                                                   AggloSlot<T, D>* gslot, uint32_t* gflag, uint32_t* mismatch)
+{
+  __shared__ unsigned long long s_key[B + 2];  // keys of positions L-1 .. L+B
+  __shared__ int s_delta[B + 1];               // s_delta[k] = delta(L-1+k, L+k)
+  __shared__ int s_pre[B + 1];                 // min(s_delta[0..k])
+  __shared__ int s_suf[B + 2];                 // min(s_delta[k..B]);  s_suf[B+1] = +inf
+  __shared__ int s_wmin[2][B / 32];
+  __shared__ Box<T, D> s_box[B];               // hand-over slot of the child with index L+k
+  __shared__ int s_end[B];
+  __shared__ uint32_t s_flag[B];               // arrivals at split L+k; bit 31 = "parent range inside this block"
+
+  const int tid = threadIdx.x;
+  const int L = blockIdx.x * B;
+  const int g = L + tid;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  s_key[tid + 1] = g < n ? __ldg(keys + g) : 0ull;
+  if(tid == 0)
+  {
+    s_key[0] = L > 0 ? __ldg(keys + L - 1) : 0ull;
+    s_key[B + 1] = L + B < n ? __ldg(keys + L + B) : 0ull;
+  }
+  __syncthreads();
+  const int dme = g < n - 1 ? adj_delta(s_key[tid + 1], s_key[tid + 2], g) : -1;
+  const int d0 = L > 0 ? adj_delta(s_key[0], s_key[1], L - 1) : -1;
+  s_delta[tid + 1] = dme;
+  if(tid == 0) s_delta[0] = d0;
+  // prefix minima over s_delta[0..B] (thread t owns element t+1), suffix minima (thread t owns element t+1 as well)
+  int pv = dme, sv = dme;
+#pragma unroll
+  for(int o = 1; o < 32; o <<= 1)
+  {
+    const int a = __shfl_up_sync(0xffffffffu, pv, o);
+    const int b = __shfl_down_sync(0xffffffffu, sv, o);
+    if(lane >= o) pv = min(pv, a);
+    if(lane + o < 32) sv = min(sv, b);
+  }
+  if(lane == 31) s_wmin[0][warp] = pv;
+  if(lane == 0) s_wmin[1][warp] = sv;
+  __syncthreads();
+  {
+    int a = d0;
+    for(int w = 0; w < warp; ++w) a = min(a, s_wmin[0][w]);
+    int b = 0x7fffffff;
+    for(int w = warp + 1; w < B / 32; ++w) b = min(b, s_wmin[1][w]);
+    s_pre[tid + 1] = min(pv, a);
+    s_suf[tid + 1] = min(sv, b);
+    if(tid == 0)
+    {
+      s_pre[0] = d0;
+      s_suf[B + 1] = 0x7fffffff;
+    }
+  }
+  __syncthreads();
+  {
+    // split k = tid (between leaves L+k and L+k+1): its node's range stays inside the block iff a
+    // smaller delta exists on both sides within the block's window
+    const bool local = (tid < B - 1) && (g < n - 1) && s_pre[tid] < dme && s_suf[tid + 2] < dme;
+    s_flag[tid] = local ? 0x80000000u : 0u;
+  }
+  __syncthreads();
+  if(g >= n) return;
+
+  auto dlt = [&](int j) -> int {
+    if(j < 0 || j >= n - 1) return -1;
+    const int k = j - (L - 1);
+    if(k >= 0 && k <= B) return s_delta[k];
+    return adj_delta(__ldg(keys + j), __ldg(keys + j + 1), j);
+  };
+
+  const int leaf = (int)(uint32_t)(s_key[tid + 1] & 0xffffffffull);
+  leaf_nodes[g] = leaf;
+  Box<T, D> box;
+  if(leaf < n_real)
+    box = load_box<T, D>(boxes, leaf);
+  else
+    box_clear(box);
+  box_scale(box, half_scale);
+
+  int l = g, r = g;
+  int dl = dlt(l - 1), dr = dlt(r);
+  for(;;)
+  {
+    const bool is_left = dr > dl;
+    const int gam = is_left ? r : l - 1;
+    const int self = is_left ? gam : gam + 1;  // this child's reference index
+    const int sib = is_left ? gam + 1 : gam;
+    const int k = gam - L;
+    Box<T, D> other;
+    int oend;
+    if(k >= 0 && k < B - 1 && (s_flag[k] & 0x80000000u))
+    {
+      s_box[self - L] = box;
+      s_end[self - L] = is_left ? l : r;
+      uint32_t old;  // block-scope acq_rel RMW: publishes this child's slot, acquires the sibling's
+      asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;"
+                   : "=r"(old)
+                   : "r"((uint32_t)__cvta_generic_to_shared(&s_flag[k]))
+                   : "memory");
+      if((old & 1u) == 0u) return;  // first arrival retires (:547-551)
+      other = s_box[sib - L];
+      oend = s_end[sib - L];
+    }
+    else
+    {
+      store_box_cg(&gslot[self].box, box);
+      __stcg(&gslot[self].end, is_left ? l : r);
+      uint32_t old;
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(gflag + gam) : "memory");
+      if(old == 0u) return;
+      other = load_box_cg(&gslot[sib].box);
+      oend = __ldcg(&gslot[sib].end);
+    }
+    const int lo = is_left ? l : oend;
+    const int hi = is_left ? oend : r;
+    const bool root = (lo == 0 && hi == n - 1);
+    dl = dlt(lo - 1);
+    dr = dlt(hi);
+    const bool p_is_left = dr > dl;
+    const int P = root ? 0 : (p_is_left ? hi : lo);
+    if(hi - lo > (1 << 24))
+      if(!reference_split_agrees<T>(lo, hi, gam, root || !p_is_left)) atomicOr(mismatch, 1u);
+    const int lc = lo == gam ? -(gam + 1) : gam;
+    const int rc = hi == gam + 1 ? -(gam + 2) : gam + 1;
+    Node<T, D>* nd = nodes + P;
+    nd->box[0] = is_left ? box : other;
+    nd->box[1] = is_left ? other : box;
+    *reinterpret_cast<int2*>(nd->child) = make_int2(lc, rc);
+    node_range[P] = make_int2(lo, hi);
+    if(lc < 0)
+      leaf_parent[gam] = P << 1;
+    else
+      nodes[gam].parent = P << 1;
+    if(rc < 0)
+      leaf_parent[gam + 1] = (P << 1) | 1;
+    else
+      nodes[gam + 1].parent = (P << 1) | 1;
+    if(root)
+    {
+      nd->parent = -1;
+      return;
+    }
+    box_add(box, other);
+    l = lo;
+    r = hi;
   }
 }
 

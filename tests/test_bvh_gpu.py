@@ -50,6 +50,25 @@ def test_build_many_ties(oracle):
     _check_build(oracle, boxes, 3)
 
 
+def test_build_legacy_path(oracle, monkeypatch):
+    """AXB_BUILD_LEGACY=1: the reference-order top-down tree_kernel + refit_kernel pair (the fallback of the
+    fused bottom-up build) must give the same tree."""
+    monkeypatch.setenv("AXB_BUILD_LEGACY", "1")
+    for n, nd in ((4097, 3), (50000, 2), (200000, 3)):
+        boxes = synth.triangle_aabbs(n, seed=31 + n, ndims=nd)
+        boxes[100:140] = boxes[100]
+        _check_build(oracle, boxes, nd)
+
+
+def test_build_sorted_and_reversed_input(oracle):
+    """inputs already in Morton order / reverse order: long runs of in-block merges and deep cross-block chains"""
+    boxes = synth.triangle_aabbs(300000, seed=5)
+    ref = oracle.Bvh(boxes, ndims=3)
+    order = ref.arrays()["leafs"]
+    _check_build(oracle, np.ascontiguousarray(boxes[order]), 3)
+    _check_build(oracle, np.ascontiguousarray(boxes[order[::-1]]), 3)
+
+
 def test_build_1m(oracle):
     boxes = synth.triangle_aabbs(1_000_000, seed=12345)
     _check_build(oracle, boxes, 3)
