@@ -138,6 +138,15 @@ class BVH:
         check(self._L.axb_bvh_get_phase_ms(self._h, name.encode(), C.byref(v)))
         return v.value
 
+    def phases_ms(self, prefix, names):
+        """{name: ms} for the phases of the last profiled call that were recorded (a path not taken has none)"""
+        out = {}
+        for k in names:
+            v = C.c_double()
+            if self._L.axb_bvh_get_phase_ms(self._h, (prefix + k).encode(), C.byref(v)) == 0:
+                out[k] = round(v.value, 4)
+        return out
+
     def launch_count(self):
         v = C.c_int64()
         check(self._L.axb_bvh_launch_count(self._h, C.byref(v)))

@@ -295,6 +295,7 @@ struct axb_bvh
   double bounds_hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
 
   DevBuf nodes, leaf_nodes, leaf_parent, node_range, keys_a, keys_b, state, sort_scratch, stage_in, agglo_slots, agglo_flags;
+  int agglo_block = 128;      // leaves per block of agglo_kernel (AXB_AGGLO_BLOCK = 128 | 256 | 512)
   bool legacy_build = false;  // AXB_BUILD_LEGACY=1: tree_kernel + refit_kernel instead of agglo_kernel
   unsigned long long* sorted_keys = nullptr;  // points into keys_a or keys_b
   DevBuf ref_inner_nodes, ref_children;       // reference-layout view, built lazily
@@ -410,13 +411,20 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
   {
     // fused bottom-up hierarchy + refit (build.cuh: agglo_kernel)
     ScopedPhase ph(ctx, "build.agglo");
-    constexpr int AB = 512;
     AXB_TRY(h->agglo_slots.reserve(sizeof(AggloSlot<T, D>) * (size_t)n, ctx.stream));
     AXB_TRY(h->agglo_flags.reserve(sizeof(uint32_t) * (size_t)inner, ctx.stream));
     AXB_CUDA_TRY(cudaMemsetAsync(h->agglo_flags.p, 0, sizeof(uint32_t) * (size_t)inner, ctx.stream));
-    AXB_LAUNCH(ctx, (agglo_kernel<T, D, AB>), blocks_for(n, AB), AB, in, n, num_boxes, half_scale, h->sorted_keys,
-               h->nodes.as<Node<T, D>>(), h->leaf_nodes.as<int32_t>(), h->leaf_parent.as<int32_t>(), h->node_range.as<int2>(),
-               h->agglo_slots.as<AggloSlot<T, D>>(), h->agglo_flags.as<uint32_t>(), &st->agglo_mismatch);
+#define AXB_AGGLO(AB)                                                                                                          \
+  AXB_LAUNCH(ctx, (agglo_kernel<T, D, AB>), blocks_for(n, AB), AB, in, n, num_boxes, half_scale, h->sorted_keys,             \
+             h->nodes.as<Node<T, D>>(), h->leaf_nodes.as<int32_t>(), h->leaf_parent.as<int32_t>(), h->node_range.as<int2>(), \
+             h->agglo_slots.as<AggloSlot<T, D>>(), h->agglo_flags.as<uint32_t>(), &st->agglo_mismatch)
+    if(h->agglo_block == 256)
+      AXB_AGGLO(256);
+    else if(h->agglo_block == 512)
+      AXB_AGGLO(512);
+    else
+      AXB_AGGLO(128);
+#undef AXB_AGGLO
   }
   ctx.phase_end(tot);
   // bounds come back to the host (getBounds() is a host query); this is also the build's sync point
@@ -425,8 +433,8 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
   AXB_TRY(ctx.sync());
   if(!legacy && hst.agglo_mismatch)
   {
-    // a >2^24-leaf node where the reference's float32 split search leaves the exact Karras split:
-    // rebuild the hierarchy with the reference-order search
+    // a >2^24-leaf node where the reference's float32 split search leaves the exact Karras split, or a
+    // non-canonical invalid input box: rebuild the hierarchy with the reference-order kernels
     AXB_TRY(legacy_tree_refit());
     AXB_TRY(ctx.sync());
   }
@@ -676,6 +684,7 @@ int axb_bvh_create(axb_bvh** out, int ndims, int fp_bytes, int device)
   h->fp_bytes = fp_bytes;
   if(fp_bytes == 4) h->tol = FLT_EPSILON;  // DEFAULT_TOLERANCE = floating_point_limits<FloatType>::epsilon()
   if(const char* e = getenv("AXB_BUILD_LEGACY")) h->legacy_build = atoi(e) != 0;
+  if(const char* e = getenv("AXB_AGGLO_BLOCK")) h->agglo_block = atoi(e);
   int s = h->ctx.init(device);
   if(s != AXB_OK)
   {

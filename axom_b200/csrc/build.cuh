@@ -447,18 +447,36 @@ __global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, i
   if(lane == 31) s_wmin[0][warp] = pv;
   if(lane == 0) s_wmin[1][warp] = sv;
   __syncthreads();
+  if(warp == 0)
   {
-    int a = d0;
-    for(int w = 0; w < warp; ++w) a = min(a, s_wmin[0][w]);
-    int b = 0x7fffffff;
-    for(int w = warp + 1; w < B / 32; ++w) b = min(b, s_wmin[1][w]);
-    s_pre[tid + 1] = min(pv, a);
-    s_suf[tid + 1] = min(sv, b);
-    if(tid == 0)
+    // exclusive prefix / suffix minima over the per-warp minima (at most 32 warps)
+    int a = lane < B / 32 ? s_wmin[0][lane] : 0x7fffffff;
+    int b = lane < B / 32 ? s_wmin[1][lane] : 0x7fffffff;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
     {
-      s_pre[0] = d0;
-      s_suf[B + 1] = 0x7fffffff;
+      const int ua = __shfl_up_sync(0xffffffffu, a, o);
+      const int ub = __shfl_down_sync(0xffffffffu, b, o);
+      if(lane >= o) a = min(a, ua);
+      if(lane + o < 32) b = min(b, ub);
     }
+    int ea = __shfl_up_sync(0xffffffffu, a, 1);
+    int eb = __shfl_down_sync(0xffffffffu, b, 1);
+    ea = lane == 0 ? d0 : min(ea, d0);
+    if(lane == 31) eb = 0x7fffffff;
+    if(lane < B / 32)
+    {
+      s_wmin[0][lane] = ea;
+      s_wmin[1][lane] = eb;
+    }
+  }
+  __syncthreads();
+  s_pre[tid + 1] = min(pv, s_wmin[0][warp]);
+  s_suf[tid + 1] = min(sv, s_wmin[1][warp]);
+  if(tid == 0)
+  {
+    s_pre[0] = d0;
+    s_suf[B + 1] = 0x7fffffff;
   }
   __syncthreads();
   {
@@ -471,9 +489,9 @@ __global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, i
   if(g >= n) return;
 
   auto dlt = [&](int j) -> int {
-    if(j < 0 || j >= n - 1) return -1;
     const int k = j - (L - 1);
-    if(k >= 0 && k <= B) return s_delta[k];
+    if(k >= 0 && k <= B) return s_delta[k];  // s_delta is -1 at and beyond the array ends
+    if(j < 0 || j >= n - 1) return -1;
     return adj_delta(__ldg(keys + j), __ldg(keys + j + 1), j);
   };
 
@@ -481,13 +499,24 @@ __global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, i
   leaf_nodes[g] = leaf;
   Box<T, D> box;
   if(leaf < n_real)
+  {
     box = load_box<T, D>(boxes, leaf);
+    if(!box_valid(box))
+    {
+      // the unions below are plain min/max, which equals BoundingBox::addBox (:487-508) for valid boxes and
+      // for the canonical invalid box (max(), lowest()); any other invalid input box goes to the legacy path
+      bool canonical = true;
+#pragma unroll
+      for(int d = 0; d < D; ++d) canonical = canonical && box.lo[d] == Lim<T>::max() && box.hi[d] == Lim<T>::lowest();
+      if(!canonical) atomicOr(mismatch, 2u);
+    }
+  }
   else
     box_clear(box);
   box_scale(box, half_scale);
 
   int l = g, r = g;
-  int dl = dlt(l - 1), dr = dlt(r);
+  int dl = s_delta[tid], dr = dme;
   for(;;)
   {
     const bool is_left = dr > dl;
@@ -520,38 +549,43 @@ __global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, i
       other = load_box_cg(&gslot[sib].box);
       oend = __ldcg(&gslot[sib].end);
     }
-    const int lo = is_left ? l : oend;
-    const int hi = is_left ? oend : r;
-    const bool root = (lo == 0 && hi == n - 1);
-    dl = dlt(lo - 1);
-    dr = dlt(hi);
+    // the parent covers [l, oend] or [oend, r]: only one of the two outer deltas changes
+    if(is_left)
+    {
+      r = oend;
+      dr = dlt(r);
+    }
+    else
+    {
+      l = oend;
+      dl = dlt(l - 1);
+    }
+    const bool root = (l == 0 && r == n - 1);
     const bool p_is_left = dr > dl;
-    const int P = root ? 0 : (p_is_left ? hi : lo);
-    if(hi - lo > (1 << 24))
-      if(!reference_split_agrees<T>(lo, hi, gam, root || !p_is_left)) atomicOr(mismatch, 1u);
-    const int lc = lo == gam ? -(gam + 1) : gam;
-    const int rc = hi == gam + 1 ? -(gam + 2) : gam + 1;
+    const int P = root ? 0 : (p_is_left ? r : l);
+    if(r - l > (1 << 24))
+      if(!reference_split_agrees<T>(l, r, gam, root || !p_is_left)) atomicOr(mismatch, 1u);
+    const int lc = l == gam ? -(gam + 1) : gam;
+    const int rc = r == gam + 1 ? -(gam + 2) : gam + 1;
     Node<T, D>* nd = nodes + P;
-    nd->box[0] = is_left ? box : other;
-    nd->box[1] = is_left ? other : box;
+    nd->box[is_left ? 0 : 1] = box;
+    nd->box[is_left ? 1 : 0] = other;
     *reinterpret_cast<int2*>(nd->child) = make_int2(lc, rc);
-    node_range[P] = make_int2(lo, hi);
-    if(lc < 0)
-      leaf_parent[gam] = P << 1;
-    else
-      nodes[gam].parent = P << 1;
-    if(rc < 0)
-      leaf_parent[gam + 1] = (P << 1) | 1;
-    else
-      nodes[gam + 1].parent = (P << 1) | 1;
+    node_range[P] = make_int2(l, r);
+    // parent links of the two children (leaf_parent for leaves, Node::parent for inner nodes)
+    *(lc < 0 ? leaf_parent + gam : &nodes[gam].parent) = P << 1;
+    *(rc < 0 ? leaf_parent + gam + 1 : &nodes[gam + 1].parent) = (P << 1) | 1;
     if(root)
     {
       nd->parent = -1;
       return;
     }
-    box_add(box, other);
-    l = lo;
-    r = hi;
+#pragma unroll
+    for(int d = 0; d < D; ++d)
+    {
+      box.lo[d] = other.lo[d] < box.lo[d] ? other.lo[d] : box.lo[d];
+      box.hi[d] = other.hi[d] > box.hi[d] ? other.hi[d] : box.hi[d];
+    }
   }
 }
 

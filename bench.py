@@ -203,7 +203,7 @@ def run_ours(args):
     for _ in range(5):
         tb.initialize(boxes_d)
     build_ms = tb.phase_ms("build.total")
-    build_phases = {k: tb.phase_ms("build." + k) for k in ("bounds", "morton", "sort", "tree", "refit", "agglo")}
+    build_phases = tb.phases_ms("build.", ("bounds", "morton", "sort", "tree", "refit", "agglo"))
     del tb, boxes_d
 
     # ---- this rank's z-slab of the 256^3 grid, generated on the device ----

@@ -60,6 +60,25 @@ def test_build_legacy_path(oracle, monkeypatch):
         _check_build(oracle, boxes, nd)
 
 
+@pytest.mark.parametrize("block", [256, 512])
+def test_build_fused_block_sizes(oracle, monkeypatch, block):
+    """the fused build with other leaves-per-block settings (default 128): in-block vs cross-block merges move"""
+    monkeypatch.setenv("AXB_AGGLO_BLOCK", str(block))
+    boxes = synth.triangle_aabbs(70001, seed=block)
+    boxes[1000:1300] = boxes[1000]
+    _check_build(oracle, boxes, 3)
+    _check_build(oracle, synth.triangle_aabbs(33333, seed=block + 1, ndims=2), 2)
+
+
+def test_build_noncanonical_invalid_boxes(oracle):
+    """input boxes with min > max in one dimension only (not the canonical invalid box): the fused build hands
+    over to the reference-order kernels, whose addBox handling is the reference's (BoundingBox.hpp:487-508)"""
+    boxes = synth.triangle_aabbs(5000, seed=11)
+    boxes[17, 0], boxes[17, 3] = 0.9, 0.1
+    boxes[4000, 1], boxes[4000, 4] = 0.8, 0.2
+    _check_build(oracle, boxes, 3)
+
+
 def test_build_sorted_and_reversed_input(oracle):
     """inputs already in Morton order / reverse order: long runs of in-block merges and deep cross-block chains"""
     boxes = synth.triangle_aabbs(300000, seed=5)

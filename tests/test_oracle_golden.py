@@ -98,6 +98,19 @@ def test_signed_distance_plane_exact(oracle):
     assert np.array_equal(phi, q[:, 2])
 
 
+def test_port_equals_real_reference_on_invalid_input_boxes(oracle, have_ref):
+    """raw box memory with min > max in one dimension (isValid() false, not the canonical invalid box):
+    scale() and addBox() treat it as invalid (BoundingBox.hpp:451-461,487-508,548-561)"""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libaxom_ref.so not present (needs /root/reference to build)")
+    boxes = synth.triangle_aabbs(5000, seed=11)
+    boxes[17, 0], boxes[17, 3] = 0.9, 0.1
+    boxes[4000, 1], boxes[4000, 4] = 0.8, 0.2
+    A, B = oracle.Bvh(boxes, ndims=3, kind="port").arrays(), oracle.Bvh(boxes, ndims=3, kind="reference").arrays()
+    for k in A:
+        assert np.array_equal(A[k], B[k]), k
+
+
 def test_port_equals_real_reference_on_random_inputs(oracle, have_ref):
     if not have_ref:
         pytest.skip("oracle/_ref/libaxom_ref.so not present (needs /root/reference to build)")

@@ -75,7 +75,7 @@ def find_config(name, args):
     for _ in range(3):
         b.initialize(boxes_d)
     build_ms = b.phase_ms("build.total")
-    build_ph = {k: round(b.phase_ms("build." + k), 4) for k in ("bounds", "morton", "sort", "tree", "refit", "agglo")}
+    build_ph = b.phases_ms("build.", ("bounds", "morton", "sort", "tree", "refit", "agglo"))
     fn = {"points": b.findPoints, "boxes": b.findBoundingBoxes, "rays": lambda r: b.findRays(r, normalized=False)}[kind]
     chunk = 16_000_000
     chunks = [torch.from_numpy(prim[i:i + chunk]).to(dev) for i in range(0, q, chunk)]

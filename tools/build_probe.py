@@ -35,7 +35,7 @@ def main():
             best = None
             for _ in range(args.reps):
                 b.initialize(boxes)
-                ph = {k: round(b.phase_ms("build." + k), 4) for k in ("total", "bounds", "morton", "sort", "tree", "refit", "agglo")}
+                ph = b.phases_ms("build.", ("total", "bounds", "morton", "sort", "tree", "refit", "agglo"))
                 if best is None or ph["total"] < best["total"]:
                     best = ph
             line = {"boxes": n, "legacy": bool(legacy), "build_ms": best, "achieved_gbs": round(156.0 * n / best["total"] / 1e6, 1),
