@@ -77,6 +77,13 @@ SYMBOLS = [
     ("axb_sd_get_phase_ms", C.c_int, [_P, C.c_char_p, _PD]),
     ("axb_sd_launch_count", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("axb_sd_get_work_counters", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("axb_meshtester_create", C.c_int, [_PP, C.c_int, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int]),
+    ("axb_meshtester_destroy", C.c_int, [_P]),
+    ("axb_meshtester_find_intersections", C.c_int, [_P, C.c_double, C.c_int, _PP, _PP, C.POINTER(C.c_int64)]),
+    ("axb_meshtester_get_degenerate", C.c_int, [_P, C.c_int, _PP, C.POINTER(C.c_int64)]),
+    ("axb_meshtester_free", C.c_int, [_P, _P, C.c_int]),
+    ("axb_meshtester_get_bvh", C.c_int, [_P, _PP]),
+    ("axb_tri_tri_intersect", C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_double, _P]),
 ]
 
 

@@ -15,6 +15,7 @@
 #include "radix_sort.cuh"
 #include "sd.cuh"
 #include "sd_fast.cuh"
+#include "meshtester.cuh"
 #include "traverse.cuh"
 
 namespace axb
@@ -302,8 +303,8 @@ struct axb_bvh
   bool ref_view_valid = false;
   DevBuf q_stage, q_counts, q_offsets, q_tiles, q_total;
   DevBuf f_keys_a, f_keys_b, f_scratch, f_perm, f_pairs, f_unused, f_cursor;
-  long long pair_hint[3] = {0, 0, 0};  // candidates found by the last find* call of each kind (sizes the pair buffer)
-  int walk_blocks_per_sm = 0;
+  long long pair_hint[4] = {0, 0, 0, 0};  // candidates found by the last find* call of each kind (sizes the pair buffer)
+  int walk_blocks_per_sm[4] = {0, 0, 0, 0};  // resident blocks/SM of the walk kernel of each kind
   int find_strategy = 0;  // 0 = single traversal + scatter (default), 1 = the reference's count / fill double traversal
 
   void release_all()
@@ -476,9 +477,11 @@ int exclusive_scan(axb_bvh* h, const int32_t* counts, int nq, int32_t* offsets, 
 }
 
 // LinearBVH::findCandidatesImpl (policy/LinearBVH.hpp:271-402): count -> scan -> allocate -> fill
-template <typename T, int D, class Query>
+// Filter (traverse.cuh / tritri.cuh) is the optional narrow phase applied to every candidate before it is
+// counted or recorded; `firsts` (optional) receives the query id of every kept candidate (pair form).
+template <typename T, int D, class Query, class Filter = NoFilter>
 int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int32_t nq, int32_t* offsets, int32_t* counts, int out_memspace,
-              int32_t** candidates, int64_t* total)
+              int32_t** candidates, int64_t* total, Filter filt = Filter(), int32_t** firsts = nullptr)
 {
   if(!h->built) return fail(AXB_ERR_NOT_BUILT, "BVH query before initialize()");
   if(nq < 0) return fail(AXB_ERR_BAD_ARG, "negative query count");
@@ -490,6 +493,7 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
   AXB_TRY(ctx.bind());
   ctx.begin_call();
   *candidates = nullptr;
+  if(firsts) *firsts = nullptr;
   *total = 0;
   if(nq == 0) return AXB_OK;
   const int tot = ctx.phase_begin("find.total");
@@ -511,12 +515,15 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
   const T tol = (T)h->tol;
   long long htotal = 0;
   int32_t* d_cand = nullptr;
+  int32_t* d_first = nullptr;
+  const int32_t* leaf_nodes = h->leaf_nodes.as<int32_t>();
   if(h->find_strategy == 1)
   {
     // the reference's shape: count -> scan -> fill, one thread per query (LinearBVH.hpp:302-364)
     {
       ScopedPhase ph(ctx, "find.count");
-      AXB_LAUNCH(ctx, (count_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, q, nq, tol, flags, (const int32_t*)nullptr, d_counts);
+      AXB_LAUNCH(ctx, (count_kernel<T, D, Query, Filter>), blocks_for(nq, 256), 256, nodes, q, nq, tol, flags, (const int32_t*)nullptr,
+                 d_counts, leaf_nodes, filt);
     }
     {
       ScopedPhase ph(ctx, "find.scan");
@@ -527,10 +534,11 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
     if(htotal > 2147483647LL)
       return fail(AXB_ERR_OVERFLOW, "candidate total " + std::to_string(htotal) + " overflows int32 offsets: split the query batch");
     AXB_CUDA_TRY(cudaMallocAsync((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+    if(firsts) AXB_CUDA_TRY(cudaMallocAsync((void**)&d_first, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
     {
       ScopedPhase ph(ctx, "find.fill");
-      AXB_LAUNCH(ctx, (fill_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, h->leaf_nodes.as<int32_t>(), q, nq, tol, flags,
-                 (const int32_t*)nullptr, d_offsets, d_cand);
+      AXB_LAUNCH(ctx, (fill_kernel<T, D, Query, Filter>), blocks_for(nq, 256), 256, nodes, leaf_nodes, q, nq, tol, flags,
+                 (const int32_t*)nullptr, d_offsets, d_cand, d_first, filt);
     }
   }
   else
@@ -561,15 +569,15 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
     // ---- pair buffer: sized from the last call of this kind, at least 4 hits per query ----
     const long long want_pairs = std::max<long long>(4LL * nq + 65536, h->pair_hint[kind] + h->pair_hint[kind] / 4 + 65536);
     // every resident warp can strand one partly filled chunk
-    if(h->walk_blocks_per_sm == 0)
+    if(h->walk_blocks_per_sm[kind] == 0)
     {
       int bps = 0;
-      AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, find_walk_kernel<T, D, Query>, 128, 0));
-      h->walk_blocks_per_sm = std::max(1, std::min(bps, 8));
+      AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, find_walk_kernel<T, D, Query, Filter>, 128, 0));
+      h->walk_blocks_per_sm[kind] = std::max(1, std::min(bps, 8));
     }
     int sms = kNumSMsB200;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
-    const int grid = (int)std::min<long long>(blocks_for(nq, 128), (long long)sms * h->walk_blocks_per_sm);
+    const int grid = (int)std::min<long long>(blocks_for(nq, 128), (long long)sms * h->walk_blocks_per_sm[kind]);
     unsigned max_chunks = (unsigned)std::min<long long>((want_pairs + kPairChunk - 1) / kPairChunk + 4LL * grid, 0x7fffffffLL / kPairChunk);
     if(h->find_strategy == 2) max_chunks = 2;  // test hook: force the overflow fallback
     AXB_TRY(h->f_pairs.reserve(sizeof(int4) * (size_t)max_chunks * kPairChunk, ctx.stream));
@@ -584,7 +592,7 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
     pb.max_chunks = max_chunks;
     {
       ScopedPhase ph(ctx, "find.count");  // the one traversal: counts + recorded hits
-      AXB_LAUNCH(ctx, (find_walk_kernel<T, D, Query>), grid, 128, nodes, h->leaf_nodes.as<int32_t>(), q, nq, tol, flags, perm, d_counts, pb);
+      AXB_LAUNCH(ctx, (find_walk_kernel<T, D, Query, Filter>), grid, 128, nodes, leaf_nodes, q, nq, tol, flags, perm, d_counts, pb, filt);
     }
     {
       ScopedPhase ph(ctx, "find.scan");
@@ -598,19 +606,20 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
       return fail(AXB_ERR_OVERFLOW, "candidate total " + std::to_string(htotal) + " overflows int32 offsets: split the query batch");
     h->pair_hint[kind] = htotal;
     AXB_CUDA_TRY(cudaMallocAsync((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+    if(firsts) AXB_CUDA_TRY(cudaMallocAsync((void**)&d_first, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
     ScopedPhase ph(ctx, "find.fill");
     if(hcur[2] == 0u)
     {
       const unsigned nchunks = std::min(hcur[1], max_chunks);
       if(nchunks)
         AXB_LAUNCH(ctx, scatter_pairs_kernel, blocks_for((long long)nchunks * kPairChunk, 256), 256, pb.pairs, pb.unused, nchunks, d_offsets,
-                   d_cand);
+                   d_cand, d_first);
     }
     else
     {
       // the pair buffer was too small for this call: second traversal, as the reference does
-      AXB_LAUNCH(ctx, (fill_kernel<T, D, Query>), blocks_for(nq, 256), 256, nodes, h->leaf_nodes.as<int32_t>(), q, nq, tol, flags,
-                 (const int32_t*)nullptr, d_offsets, d_cand);
+      AXB_LAUNCH(ctx, (fill_kernel<T, D, Query, Filter>), blocks_for(nq, 256), 256, nodes, leaf_nodes, q, nq, tol, flags,
+                 (const int32_t*)nullptr, d_offsets, d_cand, d_first, filt);
     }
   }
   ctx.phase_end(tot);
@@ -619,6 +628,14 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
     int32_t* hc = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1));
     if(!hc) return fail(AXB_ERR_BAD_ARG, "host allocation of the candidate array failed");
     AXB_CUDA_TRY(cudaMemcpyAsync(hc, d_cand, sizeof(int32_t) * (size_t)htotal, cudaMemcpyDeviceToHost, ctx.stream));
+    if(firsts)
+    {
+      int32_t* hf = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1));
+      if(!hf) return fail(AXB_ERR_BAD_ARG, "host allocation of the pair array failed");
+      AXB_CUDA_TRY(cudaMemcpyAsync(hf, d_first, sizeof(int32_t) * (size_t)htotal, cudaMemcpyDeviceToHost, ctx.stream));
+      AXB_CUDA_TRY(cudaFreeAsync(d_first, ctx.stream));
+      *firsts = hf;
+    }
     AXB_CUDA_TRY(cudaMemcpyAsync(counts, d_counts, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, ctx.stream));
     AXB_CUDA_TRY(cudaMemcpyAsync(offsets, d_offsets, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, ctx.stream));
     AXB_CUDA_TRY(cudaFreeAsync(d_cand, ctx.stream));
@@ -628,6 +645,7 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
   else
   {
     *candidates = d_cand;
+    if(firsts) *firsts = d_first;
   }
   *total = htotal;
   return ctx.finish_call();
@@ -1298,6 +1316,249 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
     s->last_inner_visits = (int64_t)hw[1];
   }
   return ctx.finish_call();
+}
+
+}  // extern "C"
+
+//==========================================================================================
+// quest::findTriMeshIntersectionsBVH (quest/MeshTester.hpp:67-104): broad phase + exact narrow phase
+//==========================================================================================
+struct axb_meshtester
+{
+  axb_bvh* bvh = nullptr;  // owns
+  int ncells = 0;
+  int nnodes = 0;
+  DevBuf tris, boxes, degflag, off, cnt;
+  Ctx& ctx() { return bvh->ctx; }
+};
+
+extern "C" {
+
+int axb_meshtester_create(axb_meshtester** out, int device, const double* x, const double* y, const double* z, int32_t nnodes,
+                          const int32_t* conn, int32_t ncells, int mesh_memspace)
+{
+  if(!out) return fail(AXB_ERR_BAD_ARG, "null output handle");
+  *out = nullptr;
+  if(nnodes < 0 || ncells < 0) return fail(AXB_ERR_BAD_ARG, "negative mesh size");
+  if((nnodes > 0 && (!x || !y || !z)) || (ncells > 0 && !conn)) return fail(AXB_ERR_BAD_ARG, "null mesh array");
+  mesh_memspace = resolve_memspace(mesh_memspace, x);
+  if(mesh_memspace != AXB_MEM_HOST && mesh_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  axb_meshtester* m = new axb_meshtester();
+  int st = axb_bvh_create(&m->bvh, 3, 8, device);
+  if(st != AXB_OK)
+  {
+    delete m;
+    return st;
+  }
+  m->ncells = ncells;
+  m->nnodes = nnodes;
+  Ctx& ctx = m->ctx();
+  auto body = [&]() -> int {
+    AXB_TRY(ctx.bind());
+    const cudaMemcpyKind kind = mesh_memspace == AXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const size_t nb = sizeof(double) * (size_t)nnodes, cb = sizeof(int32_t) * 3 * (size_t)ncells;
+    DevBuf dx, dy, dz, dc;
+    const double *px = x, *py = y, *pz = z;
+    const int32_t* pc = conn;
+    if(mesh_memspace == AXB_MEM_HOST)
+    {
+      AXB_TRY(dx.reserve(nb, ctx.stream));
+      AXB_TRY(dy.reserve(nb, ctx.stream));
+      AXB_TRY(dz.reserve(nb, ctx.stream));
+      AXB_TRY(dc.reserve(cb, ctx.stream));
+      if(nnodes)
+      {
+        AXB_CUDA_TRY(cudaMemcpyAsync(dx.p, x, nb, kind, ctx.stream));
+        AXB_CUDA_TRY(cudaMemcpyAsync(dy.p, y, nb, kind, ctx.stream));
+        AXB_CUDA_TRY(cudaMemcpyAsync(dz.p, z, nb, kind, ctx.stream));
+      }
+      if(cb) AXB_CUDA_TRY(cudaMemcpyAsync(dc.p, conn, cb, kind, ctx.stream));
+      px = dx.as<double>();
+      py = dy.as<double>();
+      pz = dz.as<double>();
+      pc = dc.as<int32_t>();
+    }
+    const size_t nc = (size_t)std::max(ncells, 1);
+    AXB_TRY(m->tris.reserve(sizeof(double) * 9 * nc, ctx.stream));
+    AXB_TRY(m->boxes.reserve(sizeof(Box<double, 3>) * nc, ctx.stream));
+    AXB_TRY(m->degflag.reserve(sizeof(int32_t) * nc, ctx.stream));
+    if(ncells)
+      AXB_LAUNCH(ctx, tri_prepare_kernel, blocks_for(ncells, 256), 256, px, py, pz, pc, ncells, m->tris.as<double>(),
+                 m->boxes.as<Box<double, 3>>(), m->degflag.as<int32_t>());
+    for(DevBuf* b : {&dx, &dy, &dz, &dc}) b->release(ctx.stream);
+    // spin::BVH over the triangle AABBs, default scale factor (MeshTester_detail.hpp:325-327)
+    axb_array_desc bd;
+    memset(&bd, 0, sizeof(bd));
+    for(int c = 0; c < 6; ++c) bd.comp[c] = m->boxes.as<char>() + 8 * c;
+    bd.stride_bytes = 48;
+    bd.ncomp = 6;
+    bd.memspace = AXB_MEM_DEVICE;
+    return axb_bvh_initialize(m->bvh, &bd, ncells);
+  };
+  st = body();
+  if(st != AXB_OK)
+  {
+    axb_meshtester_destroy(m);
+    return st;
+  }
+  *out = m;
+  return AXB_OK;
+}
+
+int axb_meshtester_destroy(axb_meshtester* m)
+{
+  if(!m) return AXB_OK;
+  if(m->bvh)
+  {
+    cudaSetDevice(m->ctx().device);
+    cudaStream_t st = m->ctx().stream;
+    for(DevBuf* b : {&m->tris, &m->boxes, &m->degflag, &m->off, &m->cnt}) b->release(st);
+    axb_bvh_destroy(m->bvh);
+  }
+  delete m;
+  return AXB_OK;
+}
+
+int axb_meshtester_get_bvh(axb_meshtester* m, axb_bvh** bvh)
+{
+  if(!m || !bvh) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *bvh = m->bvh;
+  return AXB_OK;
+}
+
+// CandidateFinderBase::findTriMeshIntersections (MeshTester_detail.hpp:201-307) with the BVH candidate finder
+// (:313-340): findBoundingBoxes(own AABBs), keep i < candidate, primal::intersect(tri_i, tri_c, false, threshold).
+// One BVH walk does all three; pairs come back in the SEQ_EXEC order (i ascending, then candidate DFS order).
+int axb_meshtester_find_intersections(axb_meshtester* m, double intersection_threshold, int out_memspace, int32_t** first, int32_t** second,
+                                      int64_t* npairs)
+{
+  if(!m || !first || !second || !npairs) return fail(AXB_ERR_BAD_ARG, "null argument");
+  if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "out_memspace must be HOST or DEVICE");
+  *first = *second = nullptr;
+  *npairs = 0;
+  if(m->ncells == 0) return AXB_OK;
+  Ctx& ctx = m->ctx();
+  AXB_TRY(ctx.bind());
+  AXB_TRY(m->off.reserve(sizeof(int32_t) * (size_t)m->ncells, ctx.stream));
+  AXB_TRY(m->cnt.reserve(sizeof(int32_t) * (size_t)m->ncells, ctx.stream));
+  axb_array_desc bd;
+  memset(&bd, 0, sizeof(bd));
+  for(int c = 0; c < 6; ++c) bd.comp[c] = m->boxes.as<char>() + 8 * c;
+  bd.stride_bytes = 48;
+  bd.ncomp = 6;
+  bd.memspace = AXB_MEM_DEVICE;
+  TriTriFilter filt;
+  filt.query_tris = m->tris.as<double>();
+  filt.tree_tris = m->tris.as<double>();
+  filt.eps = intersection_threshold;
+  filt.upper_only = 1;
+  filt.include_boundary = 0;
+  int32_t *d_second = nullptr, *d_first = nullptr;
+  int64_t total = 0;
+  AXB_TRY((find_impl<double, 3, BoxQuery<double, 3>, TriTriFilter>(m->bvh, 3, &bd, 0, m->ncells, m->off.as<int32_t>(), m->cnt.as<int32_t>(),
+                                                                   AXB_MEM_DEVICE, &d_second, &total, filt, &d_first)));
+  if(out_memspace == AXB_MEM_HOST)
+  {
+    int32_t* hf = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1));
+    int32_t* hs = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1));
+    if(!hf || !hs) return fail(AXB_ERR_BAD_ARG, "host allocation of the pair arrays failed");
+    AXB_CUDA_TRY(cudaMemcpyAsync(hf, d_first, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(hs, d_second, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaFreeAsync(d_first, ctx.stream));
+    AXB_CUDA_TRY(cudaFreeAsync(d_second, ctx.stream));
+    AXB_TRY(ctx.sync());
+    *first = hf;
+    *second = hs;
+  }
+  else
+  {
+    *first = d_first;
+    *second = d_second;
+  }
+  *npairs = total;
+  return AXB_OK;
+}
+
+// indices of the degenerate triangles, ascending (MeshTester_detail.hpp:297-305)
+int axb_meshtester_get_degenerate(axb_meshtester* m, int out_memspace, int32_t** indices, int64_t* n)
+{
+  if(!m || !indices || !n) return fail(AXB_ERR_BAD_ARG, "null argument");
+  if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "out_memspace must be HOST or DEVICE");
+  *indices = nullptr;
+  *n = 0;
+  if(m->ncells == 0) return AXB_OK;
+  Ctx& ctx = m->ctx();
+  AXB_TRY(ctx.bind());
+  AXB_TRY(m->off.reserve(sizeof(int32_t) * (size_t)m->ncells, ctx.stream));
+  AXB_TRY(m->bvh->q_total.reserve(sizeof(long long), ctx.stream));
+  long long* d_total = m->bvh->q_total.as<long long>();
+  AXB_TRY(exclusive_scan(m->bvh, m->degflag.as<int32_t>(), m->ncells, m->off.as<int32_t>(), d_total));
+  long long htotal = 0;
+  AXB_CUDA_TRY(cudaMemcpyAsync(&htotal, d_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx.stream));
+  AXB_TRY(ctx.sync());
+  int32_t* d_idx = nullptr;
+  AXB_CUDA_TRY(cudaMallocAsync((void**)&d_idx, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+  AXB_LAUNCH(ctx, compact_flagged_kernel, blocks_for(m->ncells, 256), 256, m->degflag.as<int32_t>(), m->off.as<int32_t>(), m->ncells, d_idx);
+  if(out_memspace == AXB_MEM_HOST)
+  {
+    int32_t* h = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1));
+    if(!h) return fail(AXB_ERR_BAD_ARG, "host allocation failed");
+    AXB_CUDA_TRY(cudaMemcpyAsync(h, d_idx, sizeof(int32_t) * (size_t)htotal, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaFreeAsync(d_idx, ctx.stream));
+    AXB_TRY(ctx.sync());
+    *indices = h;
+  }
+  else
+  {
+    AXB_TRY(ctx.sync());
+    *indices = d_idx;
+  }
+  *n = htotal;
+  return AXB_OK;
+}
+
+int axb_meshtester_free(axb_meshtester* m, int32_t* p, int memspace)
+{
+  if(!p) return AXB_OK;
+  if(!m) return fail(AXB_ERR_BAD_ARG, "null handle");
+  return axb_bvh_free_candidates(m->bvh, p, memspace);
+}
+
+// primal::intersect(Triangle3, Triangle3, includeBoundary, EPS) on n explicit pairs (9 doubles per triangle);
+// tris1 / tris2 / out live in `memspace` (host buffers are staged).  Synchronous.
+int axb_tri_tri_intersect(int device, const double* tris1, const double* tris2, int64_t n, int memspace, int include_boundary, double eps,
+                          uint8_t* out)
+{
+  if(n < 0 || (n > 0 && (!tris1 || !tris2 || !out))) return fail(AXB_ERR_BAD_ARG, "null or negative argument");
+  memspace = resolve_memspace(memspace, tris1);
+  if(memspace != AXB_MEM_HOST && memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  Ctx ctx;
+  AXB_TRY(ctx.init(device));
+  auto body = [&]() -> int {
+    if(n == 0) return AXB_OK;
+    DevBuf a, b, o;
+    const double *pa = tris1, *pb = tris2;
+    uint8_t* po = out;
+    const size_t tb = sizeof(double) * 9 * (size_t)n;
+    if(memspace == AXB_MEM_HOST)
+    {
+      AXB_TRY(a.reserve(tb, ctx.stream));
+      AXB_TRY(b.reserve(tb, ctx.stream));
+      AXB_TRY(o.reserve((size_t)n, ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(a.p, tris1, tb, cudaMemcpyHostToDevice, ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(b.p, tris2, tb, cudaMemcpyHostToDevice, ctx.stream));
+      pa = a.as<double>();
+      pb = b.as<double>();
+      po = o.as<uint8_t>();
+    }
+    AXB_LAUNCH(ctx, tri_tri_pairs_kernel, blocks_for(n, 256), 256, pa, pb, (long long)n, include_boundary, eps, po);
+    if(memspace == AXB_MEM_HOST) AXB_CUDA_TRY(cudaMemcpyAsync(out, po, (size_t)n, cudaMemcpyDeviceToHost, ctx.stream));
+    for(DevBuf* d : {&a, &b, &o}) d->release(ctx.stream);
+    return ctx.sync();
+  };
+  const int st = body();
+  ctx.destroy();
+  return st;
 }
 
 }  // extern "C"

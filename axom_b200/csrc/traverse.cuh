@@ -6,6 +6,7 @@
 //   predicates of findPoints/Boxes/Rays spin/BVH.hpp:499-501, :558-560, :529-532
 #pragma once
 #include "common.cuh"
+#include "tritri.cuh"
 
 namespace axb
 {
@@ -212,9 +213,10 @@ struct RayQuery
 //------------------------------------------------------------------------------------------
 // PASS 1: count (LinearBVH.hpp:302-321).  perm == nullptr: thread t handles query t.
 //------------------------------------------------------------------------------------------
-template <typename T, int D, class Query>
+template <typename T, int D, class Query, class Filter = NoFilter>
 __global__ void __launch_bounds__(256) count_kernel(const Node<T, D>* __restrict__ nodes, Desc<Query::NCOMP> prims, int nq, T tol, int flags,
-                                                     const int32_t* __restrict__ perm, int32_t* __restrict__ counts)
+                                                     const int32_t* __restrict__ perm, int32_t* __restrict__ counts,
+                                                     const int32_t* __restrict__ leaf_nodes = nullptr, Filter filt = Filter())
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if(t >= nq) return;
@@ -222,17 +224,22 @@ __global__ void __launch_bounds__(256) count_kernel(const Node<T, D>* __restrict
   Query q;
   q.load(prims, qi, tol, flags);
   int c = 0;
-  traverse_reference_order<T, D>(nodes, q, [&](int) { ++c; }, NoOrder {});
+  if(std::is_same<Filter, NoFilter>::value)
+    traverse_reference_order<T, D>(nodes, q, [&](int) { ++c; }, NoOrder {});
+  else
+    traverse_reference_order<T, D>(
+      nodes, q, [&](int pos) { c += filt(qi, __ldg(leaf_nodes + pos)) ? 1 : 0; }, NoOrder {});
   counts[qi] = c;
 }
 
 //------------------------------------------------------------------------------------------
 // PASS 2: fill (LinearBVH.hpp:346-364): candidates[offset++] = leaf_nodes[pos]
 //------------------------------------------------------------------------------------------
-template <typename T, int D, class Query>
+template <typename T, int D, class Query, class Filter = NoFilter>
 __global__ void __launch_bounds__(256) fill_kernel(const Node<T, D>* __restrict__ nodes, const int32_t* __restrict__ leaf_nodes,
                                                     Desc<Query::NCOMP> prims, int nq, T tol, int flags, const int32_t* __restrict__ perm,
-                                                    const int32_t* __restrict__ offsets, int32_t* __restrict__ candidates)
+                                                    const int32_t* __restrict__ offsets, int32_t* __restrict__ candidates,
+                                                    int32_t* __restrict__ firsts = nullptr, Filter filt = Filter())
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if(t >= nq) return;
@@ -241,7 +248,16 @@ __global__ void __launch_bounds__(256) fill_kernel(const Node<T, D>* __restrict_
   q.load(prims, qi, tol, flags);
   int off = offsets[qi];
   traverse_reference_order<T, D>(
-    nodes, q, [&](int pos) { candidates[off++] = __ldg(leaf_nodes + pos); }, NoOrder {});
+    nodes, q,
+    [&](int pos) {
+      const int32_t cand = __ldg(leaf_nodes + pos);
+      if(filt(qi, cand))
+      {
+        if(firsts) firsts[off] = qi;
+        candidates[off++] = cand;
+      }
+    },
+    NoOrder {});
 }
 
 //------------------------------------------------------------------------------------------
@@ -304,10 +320,11 @@ __device__ __forceinline__ void load_node_boxes<double, 3>(const Node<double, 3>
   rc = (int32_t)(ids >> 32);
 }
 
-template <typename T, int D, class Query>
+template <typename T, int D, class Query, class Filter = NoFilter>
 __global__ void __launch_bounds__(128) find_walk_kernel(const Node<T, D>* __restrict__ nodes, const int32_t* __restrict__ leaf_nodes,
                                                          Desc<Query::NCOMP> prims, int nq, T tol, int flags,
-                                                         const int32_t* __restrict__ perm, int32_t* __restrict__ counts, PairBuf pb)
+                                                         const int32_t* __restrict__ perm, int32_t* __restrict__ counts, PairBuf pb,
+                                                         Filter filt = Filter())
 {
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned lane = lane_id();
@@ -363,11 +380,19 @@ __global__ void __launch_bounds__(128) find_walk_kernel(const Node<T, D>* __rest
     }
     // ---- lanes that hold a leaf: record the hit (ballot + prefix into the warp's chunk), then pop ----
     const bool at_leaf = busy && cur < 0 && cur != kBarrier;
-    const unsigned leafm = __ballot_sync(FULL, at_leaf);
+    bool keep = at_leaf;  // the hit is recorded unless the narrow-phase filter rejects it
+    int32_t cand = 0;
+    if(__any_sync(FULL, at_leaf))
+    {
+      if(at_leaf)
+      {
+        cand = __ldg(leaf_nodes + (-cur - 1));
+        keep = filt(qi, cand);
+      }
+    }
+    const unsigned leafm = __ballot_sync(FULL, keep);
     if(leafm != 0u)
     {
-      int32_t cand = 0;
-      if(at_leaf) cand = __ldg(leaf_nodes + (-cur - 1));
       if(recording)
       {
         unsigned n = __popc(leafm);
@@ -393,7 +418,7 @@ __global__ void __launch_bounds__(128) find_walk_kernel(const Node<T, D>* __rest
           }
           const unsigned room = pend - ppos;
           const unsigned take = min(room, n - done);
-          if(at_leaf && my >= done && my < done + take) pb.pairs[ppos + (my - done)] = make_int4(qi, cnt, cand, 0);
+          if(keep && my >= done && my < done + take) pb.pairs[ppos + (my - done)] = make_int4(qi, cnt, cand, 0);
           ppos += take;
           done += take;
         }
@@ -401,7 +426,7 @@ __global__ void __launch_bounds__(128) find_walk_kernel(const Node<T, D>* __rest
     }
     if(at_leaf)
     {
-      ++cnt;
+      if(keep) ++cnt;
       cur = sp > 0 ? todo[--sp] : kBarrier;
     }
     // ---- lanes that hold an inner node: the reference's step (bvh_traverse.hpp:86-123), left child first ----
@@ -443,7 +468,7 @@ __global__ void __launch_bounds__(128) find_walk_kernel(const Node<T, D>* __rest
 // candidates[offsets[q] + rank] = candidate, one thread per recorded slot
 __global__ void __launch_bounds__(256) scatter_pairs_kernel(const int4* __restrict__ pairs, const unsigned int* __restrict__ unused,
                                                              unsigned int nchunks, const int32_t* __restrict__ offsets,
-                                                             int32_t* __restrict__ candidates)
+                                                             int32_t* __restrict__ candidates, int32_t* __restrict__ firsts = nullptr)
 {
   const unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned chunk = (unsigned)(slot / kPairChunk);
@@ -451,7 +476,9 @@ __global__ void __launch_bounds__(256) scatter_pairs_kernel(const int4* __restri
   const unsigned in_chunk = (unsigned)(slot % kPairChunk);
   if(in_chunk >= (unsigned)kPairChunk - unused[chunk]) return;
   const int4 p = pairs[slot];
-  candidates[(long long)offsets[p.x] + p.y] = p.z;
+  const long long o = (long long)offsets[p.x] + p.y;
+  candidates[o] = p.z;
+  if(firsts) firsts[o] = p.x;
 }
 
 // Morton keys of the queries' reference points over the BVH bounds (centroid of a box, origin of a ray):

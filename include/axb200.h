@@ -11,6 +11,8 @@
  *   spin/policy/LinearBVH.hpp:57-109        LinearBVHTraverser (device arrays)
  *   quest/SignedDistance.hpp:147-397        class SignedDistance<NDIMS,ExecSpace>
  *   quest/interface/signed_distance.hpp:117-319  (process-global C-style API)
+ *   quest/MeshTester.hpp:67-104             findTriMeshIntersectionsBVH (broad + narrow phase)
+ *   primal/operators/intersect.hpp:64-71    intersect(Triangle3, Triangle3, includeBoundary, EPS)
  *
  * Conventions
  *   - every function returns AXB_OK (0) or a negative axb_status; nothing throws or exits.
@@ -91,6 +93,7 @@ typedef struct axb_traverser
 
 typedef struct axb_bvh axb_bvh;
 typedef struct axb_sd axb_sd;
+typedef struct axb_meshtester axb_meshtester;
 
 /* ---- library ------------------------------------------------------------------------ */
 const char* axb_version(void);
@@ -191,6 +194,32 @@ int axb_sd_launch_count(const axb_sd* sd, int64_t* n);
 /* work counters of the last query when profiling is enabled (device-side atomics in a
  * profiling build of the kernel): leaf tests and inner nodes visited */
 int axb_sd_get_work_counters(const axb_sd* sd, int64_t* leaf_tests, int64_t* inner_visits);
+
+/* ---- quest::findTriMeshIntersectionsBVH (the narrow phase downstream of findBoundingBoxes) ------ */
+/* CandidateFinder<BVH>(surface_mesh, threshold) + initialize() (quest/detail/MeshTester_detail.hpp:158-199,
+ * :313-340): the triangle mesh (SoA node coordinates, int32 connectivity, 3 nodes per cell) is reduced to
+ * per-cell Triangle3 / AABB / degenerate flag on the device and a spin::BVH<3> is built over the AABBs with
+ * the default scale factor. */
+int axb_meshtester_create(axb_meshtester** out, int device, const double* x, const double* y, const double* z, int32_t num_nodes,
+                          const int32_t* cells_to_nodes, int32_t num_cells, int mesh_memspace);
+int axb_meshtester_destroy(axb_meshtester* mt);
+/* findTriMeshIntersections (:201-307): pairs (first[k], second[k]), first < second, of triangles whose AABBs
+ * overlap (findBoundingBoxes with the mesh's own AABBs) AND for which
+ * primal::intersect(tri_first, tri_second, includeBoundary = false, intersection_threshold) holds.  The BVH walk,
+ * the i < j filter and the exact test run in ONE kernel; the candidate list is never materialised.  Pairs are
+ * returned in the reference's SEQ_EXEC order (first ascending, then the candidate's DFS order).  *first and
+ * *second are allocated in `out_memspace` (HOST or DEVICE); release with axb_meshtester_free. */
+int axb_meshtester_find_intersections(axb_meshtester* mt, double intersection_threshold, int out_memspace, int32_t** first,
+                                      int32_t** second, int64_t* num_pairs);
+/* indices of the degenerate triangles (Triangle::degenerate(), primal/geometry/Triangle.hpp:326-330), ascending */
+int axb_meshtester_get_degenerate(axb_meshtester* mt, int out_memspace, int32_t** indices, int64_t* n);
+int axb_meshtester_free(axb_meshtester* mt, int32_t* p, int memspace);
+/* the BVH over the triangle AABBs -- borrowed handle (profiling: "find.count" is the fused walk) */
+int axb_meshtester_get_bvh(axb_meshtester* mt, axb_bvh** bvh);
+/* primal::intersect(Triangle<double,3>, Triangle<double,3>, includeBoundary, EPS) (primal/operators/intersect.hpp:64-71)
+ * on n explicit pairs: tris1 / tris2 are AoS double[9] per triangle, out[i] = 0 / 1; all three live in `memspace`. */
+int axb_tri_tri_intersect(int device, const double* tris1, const double* tris2, int64_t n, int memspace, int include_boundary, double eps,
+                          uint8_t* out);
 
 #ifdef __cplusplus
 }

@@ -1031,6 +1031,272 @@ void axo_sd_compute(void* h, const double* qpts_aos, int npts, double* phi, doub
 
 #endif  // !AXO_FLOAT_BUILD
 
+#ifndef AXO_FLOAT_BUILD
+//------------------------------------------------------------------------------
+// Narrow phase downstream of findBoundingBoxes:
+// primal::intersect(Triangle3, Triangle3, includeBoundary, EPS) and
+// quest::findTriMeshIntersectionsBVH (quest/MeshTester.hpp:67-83,
+// quest/detail/MeshTester_detail.hpp:158-307).
+//------------------------------------------------------------------------------
+extern "C++" {
+namespace tt
+{
+struct P2
+{
+  double x, y;
+};
+// primal/operators/detail/fuzzy_comparators.hpp:20-64
+inline bool is_gt(double x, double y, double e) { return (x > y) && !nearly_eq(x, y, e); }
+inline bool is_lt(double x, double y, double e) { return (x < y) && !nearly_eq(x, y, e); }
+inline bool is_lpeq(double x, double y, bool inc, double e) { return (inc && nearly_eq(x, y, e)) ? true : is_lt(x, y, e); }
+inline bool is_gpeq(double x, double y, bool inc, double e) { return (inc && nearly_eq(x, y, e)) ? true : is_gt(x, y, e); }
+// intersect_impl.hpp:539-542
+inline double cross2(const P2& A, const P2& B, const P2& C) { return (A.x - C.x) * (B.y - C.y) - (A.y - C.y) * (B.x - C.x); }
+// :548-590
+inline int sgn(double x) { return (0 < x) - (x < 0); }
+inline int count_zeros(double x, double y, double z, double e) { return (int)nearly_eq(x, 0., e) + (int)nearly_eq(y, 0., e) + (int)nearly_eq(z, 0., e); }
+inline bool nonzero_sign_match(double x, double y, double z, double e)
+{
+  return !nearly_eq(x, 0., e) && !nearly_eq(y, 0., e) && !nearly_eq(z, 0., e) && sgn(x) == sgn(y) && sgn(x) == sgn(z);
+}
+inline bool one_zero_others_match(double x, double y, double z, double e)
+{
+  return count_zeros(x, y, z, e) == 1 &&
+    ((nearly_eq(x, 0., e) && is_gt(y * z, 0., e)) || (nearly_eq(y, 0., e) && is_gt(z * x, 0., e)) || (nearly_eq(z, 0., e) && is_gt(x * y, 0., e)));
+}
+// Triangle::normal (primal/geometry/Triangle.hpp:98-102)
+inline V3 tri_normal(const V3& a, const V3& b, const V3& c) { return cross(sub(b, a), sub(c, a)); }
+
+// :1286-1385 checkEdge
+inline bool check_edge(const P2& p1, const P2& q1, const P2& r1, const P2& p2, const P2& r2, bool b, double e)
+{
+  if(is_gpeq(cross2(r2, p2, q1), 0., b, e))
+  {
+    if(is_gpeq(cross2(r2, p1, q1), 0., b, e))
+    {
+      if(is_gpeq(cross2(p1, p2, q1), 0., b, e)) return true;
+      return is_gpeq(cross2(p1, p2, r1), 0., b, e) && is_gpeq(cross2(q1, r1, p2), 0., b, e);
+    }
+    return false;
+  }
+  return is_gpeq(cross2(r2, p2, r1), 0., b, e) && is_gpeq(cross2(q1, r1, r2), 0., b, e) && is_gpeq(cross2(p1, p2, r1), 0., b, e);
+}
+// :1393-1484 checkVertex
+inline bool check_vertex(const P2& p1, const P2& q1, const P2& r1, const P2& p2, const P2& q2, const P2& r2, bool b, double e)
+{
+  if(is_gpeq(cross2(r2, p2, q1), 0., b, e))
+  {
+    if(is_gpeq(cross2(q2, r2, q1), 0., b, e))
+    {
+      if(is_gpeq(cross2(p1, p2, q1), 0., b, e)) return is_lpeq(cross2(p1, q2, q1), 0., b, e);
+      return is_gpeq(cross2(p1, p2, r1), 0., b, e) && is_lpeq(cross2(q1, p2, r1), 0., b, e);
+    }
+    return is_lpeq(cross2(p1, q2, q1), 0., b, e) && is_gpeq(cross2(q2, r2, r1), 0., b, e) && is_gpeq(cross2(q1, r1, q2), 0., b, e);
+  }
+  if(is_gpeq(cross2(r2, p2, r1), 0., b, e))
+  {
+    if(is_gpeq(cross2(q1, r1, r2), 0., b, e)) return is_gpeq(cross2(r1, p1, p2), 0., b, e);
+    return is_gpeq(cross2(q1, r1, q2), 0., b, e) && is_gpeq(cross2(q2, r2, r1), 0., b, e);
+  }
+  return false;
+}
+// :1281-1350 intersectPermuted2DTriangles
+inline bool permuted_2d(const P2& p1, const P2& q1, const P2& r1, const P2& p2, const P2& q2, const P2& r2, bool b, double e)
+{
+  if(is_gpeq(cross2(p2, q2, p1), 0., b, e))
+  {
+    if(is_gpeq(cross2(q2, r2, p1), 0., b, e))
+    {
+      if(is_gpeq(cross2(r2, p2, p1), 0., b, e)) return true;
+      return check_edge(p1, q1, r1, p2, r2, b, e);
+    }
+    if(is_gpeq(cross2(r2, p2, p1), 0., b, e)) return check_edge(p1, q1, r1, r2, q2, b, e);
+    return check_vertex(p1, q1, r1, p2, q2, r2, b, e);
+  }
+  if(is_gpeq(cross2(q2, r2, p1), 0., b, e))
+  {
+    if(is_gpeq(cross2(r2, p2, p1), 0., b, e)) return check_edge(p1, q1, r1, q2, p2, b, e);
+    return check_vertex(p1, q1, r1, q2, r2, p2, b, e);
+  }
+  return check_vertex(p1, q1, r1, r2, p2, q2, b, e);
+}
+// :1245-1278 TriangleIntersection2D
+inline bool tri2d(const P2* t1, const P2* t2, bool b, double e)
+{
+  const bool f1 = is_lt(cross2(t1[0], t1[1], t1[2]), 0., e);
+  const bool f2 = is_lt(cross2(t2[0], t2[1], t2[2]), 0., e);
+  return permuted_2d(t1[0], f1 ? t1[2] : t1[1], f1 ? t1[1] : t1[2], t2[0], f2 ? t2[2] : t2[1], f2 ? t2[1] : t2[2], b, e);
+}
+// :1185-1242 intersectCoplanar3DTriangles
+inline bool coplanar(const V3& p1, const V3& q1, const V3& r1, const V3& p2, const V3& q2, const V3& r2, V3 n, bool b, double e)
+{
+  n.x = std::fabs(n.x);
+  n.y = std::fabs(n.y);
+  n.z = std::fabs(n.z);
+  if(is_gt(n.x, n.z, e) && is_geq(n.x, n.y, e))
+  {
+    const P2 a[3] = {{q1.z, q1.y}, {p1.z, p1.y}, {r1.z, r1.y}};
+    const P2 c[3] = {{q2.z, q2.y}, {p2.z, p2.y}, {r2.z, r2.y}};
+    return tri2d(a, c, b, e);
+  }
+  if(is_gt(n.y, n.z, e) && is_geq(n.y, n.x, e))
+  {
+    const P2 a[3] = {{q1.x, q1.z}, {p1.x, p1.z}, {r1.x, r1.z}};
+    const P2 c[3] = {{q2.x, q2.z}, {p2.x, p2.z}, {r2.x, r2.z}};
+    return tri2d(a, c, b, e);
+  }
+  const P2 a[3] = {{p1.x, p1.y}, {q1.x, q1.y}, {r1.x, r1.y}};
+  const P2 c[3] = {{p2.x, p2.y}, {q2.x, q2.y}, {r2.x, r2.y}};
+  return tri2d(a, c, b, e);
+}
+// :457-474 intersectTwoPermutedTriangles
+inline bool two_permuted(const V3& p1, const V3& q1, const V3& r1, const V3& p2, const V3& q2, const V3& r2, bool b, double e)
+{
+  return is_lpeq(dot(sub(q2, q1), tri_normal(q1, p2, p1)), 0., b, e) && is_lpeq(dot(sub(r2, p1), tri_normal(p1, p2, r1)), 0., b, e);
+}
+// :1103-1182 intersectOnePermutedTriangle
+inline bool one_permuted(const V3& p1, const V3& q1, const V3& r1, const V3& p2, const V3& q2, const V3& r2, double dp2, double dq2,
+                         double dr2, const V3& n, bool b, double e)
+{
+  if(is_gt(dp2, 0., e))
+  {
+    if(is_gt(dq2, 0., e)) return two_permuted(p1, r1, q1, r2, p2, q2, b, e);
+    if(is_gt(dr2, 0., e)) return two_permuted(p1, r1, q1, q2, r2, p2, b, e);
+    return two_permuted(p1, q1, r1, p2, q2, r2, b, e);
+  }
+  if(is_lt(dp2, 0., e))
+  {
+    if(is_lt(dq2, 0., e)) return two_permuted(p1, q1, r1, r2, p2, q2, b, e);
+    if(is_lt(dr2, 0., e)) return two_permuted(p1, q1, r1, q2, r2, p2, b, e);
+    return two_permuted(p1, r1, q1, p2, q2, r2, b, e);
+  }
+  if(is_lt(dq2, 0., e))
+  {
+    if(is_geq(dr2, 0., e)) return two_permuted(p1, r1, q1, q2, r2, p2, b, e);
+    return two_permuted(p1, q1, r1, p2, q2, r2, b, e);
+  }
+  if(is_gt(dq2, 0., e))
+  {
+    if(is_gt(dr2, 0., e)) return two_permuted(p1, r1, q1, p2, q2, r2, b, e);
+    return two_permuted(p1, q1, r1, q2, r2, p2, b, e);
+  }
+  if(is_gt(dr2, 0., e)) return two_permuted(p1, q1, r1, r2, p2, q2, b, e);
+  if(is_lt(dr2, 0., e)) return two_permuted(p1, r1, q1, r2, p2, q2, b, e);
+  return coplanar(p1, q1, r1, p2, q2, r2, n, b, e);
+}
+// :156-436 intersect_tri3D_tri3D
+inline bool tri_tri(const V3* t1, const V3* t2, bool b, double e)
+{
+  const V3 n2 = unit(tri_normal(t2[0], t2[1], t2[2]));
+  const double dp1 = dot(sub(t1[0], t2[2]), n2), dq1 = dot(sub(t1[1], t2[2]), n2), dr1 = dot(sub(t1[2], t2[2]), n2);
+  if(nonzero_sign_match(dp1, dq1, dr1, e)) return false;
+  if(!b && (count_zeros(dp1, dq1, dr1, e) == 2 || one_zero_others_match(dp1, dq1, dr1, e))) return false;
+  const V3 n1 = unit(tri_normal(t1[0], t1[1], t1[2]));
+  const double dp2 = dot(sub(t2[0], t1[2]), n1), dq2 = dot(sub(t2[1], t1[2]), n1), dr2 = dot(sub(t2[2], t1[2]), n1);
+  if(nonzero_sign_match(dp2, dq2, dr2, e)) return false;
+  if(!b && (count_zeros(dp2, dq2, dr2, e) == 2 || one_zero_others_match(dp2, dq2, dr2, e))) return false;
+  // the permutation tables of :222-435: A = (t2 as is, dp2,dq2,dr2), S = (t2[0],t2[2],t2[1], dp2,dr2,dq2)
+  auto A = [&](int i0, int i1, int i2) { return one_permuted(t1[i0], t1[i1], t1[i2], t2[0], t2[1], t2[2], dp2, dq2, dr2, n1, b, e); };
+  auto S = [&](int i0, int i1, int i2) { return one_permuted(t1[i0], t1[i1], t1[i2], t2[0], t2[2], t2[1], dp2, dr2, dq2, n1, b, e); };
+  if(is_gt(dp1, 0., e))
+  {
+    if(is_gt(dq1, 0., e)) return S(2, 0, 1);
+    if(is_gt(dr1, 0., e)) return S(1, 2, 0);
+    return A(0, 1, 2);
+  }
+  if(is_lt(dp1, 0., e))
+  {
+    if(is_lt(dq1, 0., e)) return A(2, 0, 1);
+    if(is_lt(dr1, 0., e)) return A(1, 2, 0);
+    return S(0, 1, 2);
+  }
+  if(is_lt(dq1, 0., e))
+  {
+    if(is_geq(dr1, 0., e)) return S(1, 2, 0);
+    return A(0, 1, 2);
+  }
+  if(is_gt(dq1, 0., e))
+  {
+    if(is_gt(dr1, 0., e)) return S(0, 1, 2);
+    return A(1, 2, 0);
+  }
+  if(is_gt(dr1, 0., e)) return A(2, 0, 1);
+  if(is_lt(dr1, 0., e)) return S(2, 0, 1);
+  return coplanar(t1[0], t1[1], t1[2], t2[0], t2[1], t2[2], n1, b, e);
+}
+}  // namespace tt
+}  // extern "C++"
+
+// primal::intersect(Triangle<double,3>, Triangle<double,3>, includeBoundary, EPS) on n pairs of 9-double triangles
+void axo_tri_tri_intersect(const double* tris1, const double* tris2, int n, int include_boundary, double eps, uint8_t* out)
+{
+  for(int i = 0; i < n; ++i)
+  {
+    V3 a[3], b[3];
+    for(int k = 0; k < 3; ++k)
+    {
+      a[k] = {tris1[i * 9 + 3 * k], tris1[i * 9 + 3 * k + 1], tris1[i * 9 + 3 * k + 2]};
+      b[k] = {tris2[i * 9 + 3 * k], tris2[i * 9 + 3 * k + 1], tris2[i * 9 + 3 * k + 2]};
+    }
+    out[i] = tt::tri_tri(a, b, include_boundary != 0, eps) ? 1 : 0;
+  }
+}
+
+// quest::findTriMeshIntersectionsBVH<SEQ_EXEC,double> (MeshTester.hpp:67-104, MeshTester_detail.hpp:158-307):
+// triangle AABBs -> BVH (default scale) -> findBoundingBoxes(own AABBs) -> pairs i < j in candidate order ->
+// primal::intersect(tri_i, tri_j, false, threshold).  Returns the pair count; first/second/degenerate are malloc'ed.
+int64_t axo_find_tri_mesh_intersections(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, int ncells,
+                                        double threshold, int32_t** first, int32_t** second, int32_t** degenerate, int64_t* ndegenerate)
+{
+  (void)nnodes;
+  std::vector<V3> tri((size_t)ncells * 3);
+  std::vector<Box<3>> boxes(ncells > 0 ? ncells : 1);
+  std::vector<int32_t> deg;
+  for(int c = 0; c < ncells; ++c)
+  {
+    Box<3> bb;
+    box_clear(bb);
+    for(int k = 0; k < 3; ++k)
+    {
+      const int nd = conn[c * 3 + k];
+      tri[c * 3 + k] = {x[nd], y[nd], z[nd]};
+      const double p[3] = {x[nd], y[nd], z[nd]};
+      for(int d = 0; d < 3; ++d)
+      {
+        if(p[d] < bb.lo[d]) bb.lo[d] = p[d];
+        if(p[d] > bb.hi[d]) bb.hi[d] = p[d];
+      }
+    }
+    boxes[c] = bb;
+    // Triangle::degenerate (Triangle.hpp:326-330): |0.5 * |normal|| <= 1e-12
+    const V3 n = tt::tri_normal(tri[c * 3], tri[c * 3 + 1], tri[c * 3 + 2]);
+    if(nearly_eq(0.5 * std::sqrt(dot(n, n)), 0.0, 1.0e-12)) deg.push_back(c);
+  }
+  Bvh<3>* bvh = create<3>(reinterpret_cast<const double*>(boxes.data()), ncells, -1.0, -1.0);
+  std::vector<int32_t> off(ncells > 0 ? ncells : 1), cnt(ncells > 0 ? ncells : 1);
+  int32_t* cand = nullptr;
+  find_boxes<3>(*bvh, reinterpret_cast<const double*>(boxes.data()), ncells, off.data(), cnt.data(), &cand);
+  std::vector<int32_t> f, s;
+  for(int i = 0; i < ncells; ++i)
+    for(int j = 0; j < cnt[i]; ++j)
+    {
+      const int c = cand[off[i] + j];
+      if(i < c && tt::tri_tri(&tri[(size_t)i * 3], &tri[(size_t)c * 3], false, threshold))
+      {
+        f.push_back(i);
+        s.push_back(c);
+      }
+    }
+  free(cand);
+  delete bvh;
+  *first = to_malloc(f);
+  *second = to_malloc(s);
+  *degenerate = to_malloc(deg);
+  *ndegenerate = (int64_t)deg.size();
+  return (int64_t)f.size();
+}
+#endif  // !AXO_FLOAT_BUILD
+
 int AXO_FN(max_threads)()
 {
 #ifdef _OPENMP

@@ -72,6 +72,11 @@ class _Lib:
             f("sd_create_mixed").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
             f("sd_destroy").argtypes = [C.c_void_p]
             f("sd_compute").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            f("tri_tri_intersect").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+            f("find_tri_mesh_intersections").restype = C.c_int64
+            f("find_tri_mesh_intersections").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                         C.POINTER(C.c_int64)]
         f("max_threads").restype = C.c_int
 
     def fn(self, name):
@@ -194,6 +199,32 @@ class SignedDistance:
         nr = np.empty((n, 3), np.float64) if want_normals else None
         self.L.fn("sd_compute")(self.h, _ptr(q), n, _ptr(phi), _ptr(cp), _ptr(nr), int(nthreads))
         return phi, cp, nr
+
+
+def tri_tri_intersect(tris1, tris2, include_boundary=False, eps=1e-8, kind="port"):
+    """primal::intersect(Triangle3, Triangle3, includeBoundary, EPS) on n pairs; tris are (n, 3, 3) doubles"""
+    a = np.ascontiguousarray(tris1, np.float64).reshape(-1, 9)
+    b = np.ascontiguousarray(tris2, np.float64).reshape(-1, 9)
+    out = np.zeros(a.shape[0], np.uint8)
+    lib(kind).fn("tri_tri_intersect")(_ptr(a), _ptr(b), a.shape[0], int(include_boundary), float(eps), _ptr(out))
+    return out.astype(bool)
+
+
+def find_tri_mesh_intersections(x, y, z, conn, threshold=1e-8, kind="port"):
+    """quest::findTriMeshIntersectionsBVH<SEQ_EXEC,double>: ((npairs, 2) int32 pairs in the SEQ order, degenerate ids)"""
+    L = lib(kind)
+    x, y, z = (np.ascontiguousarray(a, np.float64) for a in (x, y, z))
+    conn = np.ascontiguousarray(conn, np.int32).reshape(-1, 3)
+    f, s, d = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nd = C.c_int64()
+    n = L.fn("find_tri_mesh_intersections")(_ptr(x), _ptr(y), _ptr(z), x.size, _ptr(conn), conn.shape[0], float(threshold),
+                                            C.byref(f), C.byref(s), C.byref(d), C.byref(nd))
+
+    def take(p, k):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(max(k, 1),))[:k].copy()
+        L.fn("free")(p)
+        return a
+    return np.stack([take(f, n), take(s, n)], axis=1), take(d, nd.value)
 
 
 def max_threads(kind="port"):

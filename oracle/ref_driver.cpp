@@ -21,6 +21,9 @@
 #include "axom/spin/BVH.hpp"
 #include "axom/mint/mesh/UnstructuredMesh.hpp"
 #include "axom/quest/SignedDistance.hpp"
+#include "axom/primal/geometry/Triangle.hpp"
+#include "axom/primal/operators/intersect.hpp"
+#include "axom/quest/MeshTester.hpp"
 
 #include <cstdint>
 #include <cstdlib>
@@ -420,6 +423,55 @@ void axref_sd_compute(void* h, const double* qpts_aos, int npts, double* phi, do
     const int m = (b + chunk <= npts) ? chunk : npts - b;
     s.sd->computeDistances(m, q + b, phi + b, cps ? cps + b : nullptr, nrm ? nrm + b : nullptr);
   }
+}
+
+// primal::intersect(Triangle3, Triangle3, includeBoundary, EPS) (primal/operators/intersect.hpp:64-71) on n pairs
+void axref_tri_tri_intersect(const double* tris1, const double* tris2, int n, int include_boundary, double eps, uint8_t* out)
+{
+  using PointType = axom::primal::Point<double, 3>;
+  using Tri = axom::primal::Triangle<double, 3>;
+  for(int i = 0; i < n; ++i)
+  {
+    const double* a = tris1 + (size_t)i * 9;
+    const double* b = tris2 + (size_t)i * 9;
+    const Tri t1(PointType {a[0], a[1], a[2]}, PointType {a[3], a[4], a[5]}, PointType {a[6], a[7], a[8]});
+    const Tri t2(PointType {b[0], b[1], b[2]}, PointType {b[3], b[4], b[5]}, PointType {b[6], b[7], b[8]});
+    out[i] = axom::primal::intersect(t1, t2, include_boundary != 0, eps) ? 1 : 0;
+  }
+}
+
+// quest::findTriMeshIntersectionsBVH<SEQ_EXEC, double> (quest/MeshTester.hpp:67-104)
+int64_t axref_find_tri_mesh_intersections(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, int ncells,
+                                          double threshold, int32_t** first, int32_t** second, int32_t** degenerate,
+                                          int64_t* ndegenerate)
+{
+  ensure_slic();
+  axom::slic::setLoggingMsgLevel(axom::slic::message::Warning);
+  using UMesh = axom::mint::UnstructuredMesh<axom::mint::SINGLE_SHAPE>;
+  UMesh mesh(3, axom::mint::TRIANGLE, nnodes, ncells);
+  for(int i = 0; i < nnodes; ++i) mesh.appendNode(x[i], y[i], z[i]);
+  for(int c = 0; c < ncells; ++c)
+  {
+    const axom::IndexType ids[3] = {conn[3 * c], conn[3 * c + 1], conn[3 * c + 2]};
+    mesh.appendCell(ids);
+  }
+  std::vector<std::pair<int, int>> isect;
+  std::vector<int> deg;
+  axom::quest::findTriMeshIntersectionsBVH<SEQ_EXEC, double>(&mesh, isect, deg, threshold);
+  int32_t* f = (int32_t*)malloc(sizeof(int32_t) * (isect.size() + 1));
+  int32_t* s = (int32_t*)malloc(sizeof(int32_t) * (isect.size() + 1));
+  int32_t* d = (int32_t*)malloc(sizeof(int32_t) * (deg.size() + 1));
+  for(size_t i = 0; i < isect.size(); ++i)
+  {
+    f[i] = isect[i].first;
+    s[i] = isect[i].second;
+  }
+  for(size_t i = 0; i < deg.size(); ++i) d[i] = deg[i];
+  *first = f;
+  *second = s;
+  *degenerate = d;
+  *ndegenerate = (int64_t)deg.size();
+  return (int64_t)isect.size();
 }
 
 int axref_max_threads()

@@ -45,9 +45,31 @@ def sd_case(name, freq, grid):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, y=y, z=z, conn=conn, q=q, phi=phi, cp=cp, nrm=nrm)
 
 
+def meshtester_case(name):
+    """quest::findTriMeshIntersectionsBVH<SEQ_EXEC,double> on two interpenetrating spheres + 2 degenerate cells,
+    and primal::intersect on seeded random / lattice triangle pairs"""
+    x, y, z, c = synth.icosphere(8)
+    x2, y2, z2, c2 = synth.icosphere(6)
+    X, Y, Z = np.concatenate([x, x2 * 0.9 + 0.3]), np.concatenate([y, y2 * 0.9]), np.concatenate([z, z2 * 0.9])
+    C = np.concatenate([c, c2 + len(x), [[0, 0, 1], [2, 3, 2]]]).astype(np.int32)
+    pairs, deg = O.find_tri_mesh_intersections(X, Y, Z, C, 1e-8, "reference")
+    rng = np.random.default_rng(77)
+    a = rng.random((3000, 3, 3))
+    b = rng.random((3000, 3, 3)) * 0.4 + 0.3
+    g = rng.integers(0, 3, (3000, 3, 3)).astype(np.float64)
+    h = rng.integers(0, 3, (3000, 3, 3)).astype(np.float64)
+    g[:1000, :, 2] = 0
+    h[:1000, :, 2] = 0
+    t1, t2 = np.concatenate([a, g]), np.concatenate([b, h])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pairs=pairs, degenerate=deg, t1=t1.astype(np.float32), t2=t2.astype(np.float32),
+                        hit_open=O.tri_tri_intersect(t1.astype(np.float32), t2.astype(np.float32), False, 1e-8, "reference"),
+                        hit_closed=O.tri_tri_intersect(t1.astype(np.float32), t2.astype(np.float32), True, 1e-8, "reference"))
+
+
 if __name__ == "__main__":
     assert O.have_reference(), "build the reference first: python oracle/build_ref.py"
     bvh_case("bvh3d_n600", 600, 3, 41)
     bvh_case("bvh2d_n400", 400, 2, 43)
     sd_case("sd_icosphere5", 5, 9)
+    meshtester_case("meshtester_spheres")
     print("golden fixtures written to", HERE)

@@ -75,3 +75,56 @@ def check_points(bvh, boxes, ndims):
     assert np.array_equal(np.asarray(cand)[off], np.arange(len(boxes)))
     off, cnt, cand = bvh.find_points(cen + 10.0)
     assert (cnt == 0).all() and len(cand) == 0
+
+
+# ---- primal::intersect(Triangle3, Triangle3): primal/tests/primal_intersect.cpp:826-1106 --------------------
+# (t1, t2, expected with includeBoundary=True, expected with includeBoundary=False); every case is run over the
+# 36 corner permutations of permuteCornersTest (:53-125), EPS = 1e-8.
+_TRI_A = [(0, 0, 0), (1, 0, 0), (0, 1.7, 2.3)]
+_I152 = [(1, 0, 0.5), (1, 0, -0.5), (0, 0, 0)]
+TRI_TRI_KATS = [
+    ([(-1, -1, -1), (-2, -5, -5), (-4, -8, -8)], [(-1, -1, -1), (-2, -5, -5), (-4, -8, -8)], True, True),   # identical
+    ([(-1, -1, -1), (-2, -5, -5), (-4, -8, -8)], [(1, 1, 1), (5, 5, 5), (8, 7, 92)], False, False),         # disjunct
+    (_TRI_A, [(0, 0, 0), (1, 0, 0), (0, -2, 1.2)], True, False),          # sharing a segment
+    (_TRI_A, [(-0.2, 0, 0), (0.7, 0, 0), (0, -2, 1.2)], True, False),     # sharing part of a segment
+    (_TRI_A, [(-1, 0, 0), (0, 4.3, 6), (0, 1.7, 2.3)], True, False),      # sharing a vertex
+    (_TRI_A, [(0, -1, 0), (1, 1, 0), (0, 1.7, -2.3)], True, False),       # edges cross
+    (_TRI_A, [(0, -1, -1), (0.5, 0, 0), (1, 1, -1)], True, False),        # B vertex lands on A's edge
+    (_TRI_A, [(0.5, -1, 0.1), (0.5, 1, 0.1), (1, 1, -1)], True, True),    # two links in a chain
+    (_TRI_A, [(-1, -1, 1), (0, 2, 1), (5, 0, 1)], True, True),            # A pokes through B
+    (_TRI_A, [(1, -1, 1), (1, 2, 1), (1, 0, -1)], True, False),           # A vertex tangent on B
+    (_TRI_A, [(1.00001, -1, 1), (1, 2, 1), (1, 0, -1)], False, False),    # not quite tangent
+    # regression cases :923-1106
+    ([(-1.83697e-14, 62.5, 300), (16.17619, 60.37037, 300), (-5.790149e-16, 11.26926, 9.456031)],
+     [(-5.790149e-16, 11.26926, 9.456031), (16.17619, 60.37037, 300), (2.916699, 10.88527, 9.456031)], True, False),
+    ([(-138.02488708496094, -14398.0908203125, 111881.2421875), (0.067092768847942352, -14407.21875, 111891.078125),
+      (-136.77900695800781, -14416.4912109375, 111891.078125)],
+     [(1.1611454486846924, -14423.3466796875, 111904.359375), (0.067092768847942352, -14407.21875, 111891.078125),
+      (136.91319274902344, -14397.947265625, 111891.078125)], True, False),
+    ([(-1, -1, -1), (0, 0, -0.005), (-1, 0, 0)], [(0, 1, -1), (0, 0, -0.005), (1, 0, 0)], True, False),
+    ([(76.648, 54.6752, 15.0012), (76.648, 54.6752, 14.5542), (76.582, 54.6752, 14.7879)],
+     [(76.6252, 54.6752, 14.892), (76.582, 54.6752, 14.7879), (76.5617, 54.6752, 14.7929)], True, True),
+    ([(0.066, 0, 0.2133), (0.066, 0, -0.2337), (0, 0, 0)], [(0.0432, 0, 0.1041), (0, 0, 0), (-0.0203, 0, 0.005)], True, True),
+    (_I152, [(0.5, 0, 0.1), (0, 0, 0), (-0.1, 0, -0.2)], True, True),
+    (_I152, [(0.5, 0, 0.1), (0, 0, 0), (-0.1, 0, 0.05)], True, True),
+    (_I152, [(0.5, 0, 0.1), (0, 0, 0), (-0.1, 0, 0.06)], True, True),
+    (_I152, [(0.5, 0, 0.1), (0, 0, 0), (-0.1, 0, 0.04)], True, True),
+]
+
+
+def tri_tri_cases():
+    """-> (t1 (n,3,3), t2 (n,3,3), include_boundary (n,) bool, expected (n,) bool) over all corner permutations"""
+    def roll(t, i):
+        return [t[i % 3], t[(i + 1) % 3], t[(i + 2) % 3]]
+    T1, T2, INC, WANT = [], [], [], []
+    for a, b, with_bdry, without_bdry in TRI_TRI_KATS:
+        ap, bp = [a[0], a[2], a[1]], [b[0], b[2], b[1]]
+        for inc, want in ((True, with_bdry), (False, without_bdry)):
+            for u, v in ((a, b), (ap, bp), (b, a), (bp, ap)):
+                for i in range(3):
+                    for j in range(3):
+                        T1.append(roll(u, i))
+                        T2.append(roll(v, j))
+                        INC.append(inc)
+                        WANT.append(want)
+    return np.array(T1, np.float64), np.array(T2, np.float64), np.array(INC, bool), np.array(WANT, bool)

@@ -163,3 +163,51 @@ def test_float_restatement_matches_float_reference(oracle, have_ref, ndims):
             assert np.array_equal(u, v)
         for u, v in zip(a.find_rays(o, d * 1.7, True), b.find_rays(o, d * 1.7, True)):
             assert np.array_equal(u, v)
+
+
+# ---- narrow phase: primal::intersect(Triangle3, Triangle3) and findTriMeshIntersectionsBVH ----
+def test_tri_tri_reference_kats(oracle, have_ref):
+    """the explicit cases of primal/tests/primal_intersect.cpp:826-1106 over permuteCornersTest's 36 permutations"""
+    t1, t2, inc, want = kats.tri_tri_cases()
+    for kind in ("port", "reference") if have_ref else ("port",):
+        for b in (False, True):
+            m = inc == b
+            got = oracle.tri_tri_intersect(t1[m], t2[m], b, 1e-8, kind)
+            assert np.array_equal(got, want[m]), (kind, b, np.nonzero(got != want[m]))
+
+
+def test_tri_tri_port_equals_real_reference(oracle, have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref/libaxom_ref.so not present (needs /root/reference to build)")
+    rng = np.random.default_rng(1)
+    for spread in (1.0, 0.5, 0.2):
+        a = rng.random((20000, 3, 3))
+        b = rng.random((20000, 3, 3)) * spread + (1 - spread) / 2
+        for inc in (False, True):
+            assert np.array_equal(oracle.tri_tri_intersect(a, b, inc, 1e-8, "port"), oracle.tri_tri_intersect(a, b, inc, 1e-8, "reference"))
+    g = rng.integers(0, 3, (40000, 3, 3)).astype(np.float64)
+    h = rng.integers(0, 3, (40000, 3, 3)).astype(np.float64)
+    g[:10000, :, 2] = 0
+    h[:10000, :, 2] = 0
+    for inc in (False, True):
+        for eps in (1e-8, 1e-12):
+            assert np.array_equal(oracle.tri_tri_intersect(g, h, inc, eps, "port"), oracle.tri_tri_intersect(g, h, inc, eps, "reference"))
+
+
+def test_find_tri_mesh_intersections_port_equals_real_reference(oracle, have_ref):
+    """quest::findTriMeshIntersectionsBVH<SEQ_EXEC,double>: two interpenetrating spheres + two degenerate cells;
+    the golden fixture tests/golden/meshtester_spheres.npz holds the reference's answer for the GPU box"""
+    x, y, z, c = synth.icosphere(8)
+    x2, y2, z2, c2 = synth.icosphere(6)
+    X, Y, Z = np.concatenate([x, x2 * 0.9 + 0.3]), np.concatenate([y, y2 * 0.9]), np.concatenate([z, z2 * 0.9])
+    C = np.concatenate([c, c2 + len(x), [[0, 0, 1], [2, 3, 2]]]).astype(np.int32)
+    pp, dp = oracle.find_tri_mesh_intersections(X, Y, Z, C, 1e-8, "port")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "meshtester_spheres.npz"))
+    assert np.array_equal(pp, g["pairs"]) and np.array_equal(dp, g["degenerate"]) and len(pp) == 146
+    if have_ref:
+        pr, dr = oracle.find_tri_mesh_intersections(X, Y, Z, C, 1e-8, "reference")
+        assert np.array_equal(pp, pr) and np.array_equal(dp, dr)
+    # seeded triangle pairs (stored as float32 so the fixture stays small; exactly representable in double)
+    t1, t2 = g["t1"].astype(np.float64), g["t2"].astype(np.float64)
+    assert np.array_equal(oracle.tri_tri_intersect(t1, t2, False, 1e-8), g["hit_open"])
+    assert np.array_equal(oracle.tri_tri_intersect(t1, t2, True, 1e-8), g["hit_closed"])
