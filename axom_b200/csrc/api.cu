@@ -1379,7 +1379,7 @@ int axb_meshtester_create(axb_meshtester** out, int device, const double* x, con
       pc = dc.as<int32_t>();
     }
     const size_t nc = (size_t)std::max(ncells, 1);
-    AXB_TRY(m->tris.reserve(sizeof(double) * 9 * nc, ctx.stream));
+    AXB_TRY(m->tris.reserve(sizeof(double) * tt::kTriRecDoubles * nc, ctx.stream));
     AXB_TRY(m->boxes.reserve(sizeof(Box<double, 3>) * nc, ctx.stream));
     AXB_TRY(m->degflag.reserve(sizeof(int32_t) * nc, ctx.stream));
     if(ncells)

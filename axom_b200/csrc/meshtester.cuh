@@ -10,7 +10,7 @@
 
 namespace axb
 {
-// one thread per cell: tris[c] = 9 doubles (three vertices), boxes[c] = AABB of the vertices, degenerate[c] = 0/1
+// one thread per cell: tris[c] = 96-byte record (tt::load_tri_rec), boxes[c] = AABB of the vertices, degenerate[c] = 0/1
 __global__ void __launch_bounds__(256) tri_prepare_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                                                            const int32_t* __restrict__ conn, int ncells, double* __restrict__ tris,
                                                            Box<double, 3>* __restrict__ boxes, int32_t* __restrict__ degenerate)
@@ -31,9 +31,11 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double* __restri
     {
       if(p[d] < bb.lo[d]) bb.lo[d] = p[d];
       if(p[d] > bb.hi[d]) bb.hi[d] = p[d];
-      tris[(size_t)c * 9 + 3 * k + d] = p[d];
+      tris[(size_t)c * tt::kTriRecDoubles + 3 * k + d] = p[d];
     }
   }
+#pragma unroll
+  for(int k = 9; k < tt::kTriRecDoubles; ++k) tris[(size_t)c * tt::kTriRecDoubles + k] = 0.0;
   boxes[c] = bb;
   degenerate[c] = tt::degenerate(t) ? 1 : 0;
 }

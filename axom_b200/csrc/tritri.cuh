@@ -66,7 +66,7 @@ __device__ __forceinline__ bool one_zero_others_match(double x, double y, double
 }
 
 // checkEdge (:1352-1390)
-__device__ __noinline__ bool check_edge(const P2& p1, const P2& q1, const P2& r1, const P2& p2, const P2& r2, bool b, double e)
+__device__ __forceinline__ bool check_edge(const P2& p1, const P2& q1, const P2& r1, const P2& p2, const P2& r2, bool b, double e)
 {
   if(is_gpeq(cross2(r2, p2, q1), 0., b, e))
   {
@@ -80,7 +80,7 @@ __device__ __noinline__ bool check_edge(const P2& p1, const P2& q1, const P2& r1
   return is_gpeq(cross2(r2, p2, r1), 0., b, e) && is_gpeq(cross2(q1, r1, r2), 0., b, e) && is_gpeq(cross2(p1, p2, r1), 0., b, e);
 }
 // checkVertex (:1393-1484)
-__device__ __noinline__ bool check_vertex(const P2& p1, const P2& q1, const P2& r1, const P2& p2, const P2& q2, const P2& r2, bool b, double e)
+__device__ __forceinline__ bool check_vertex(const P2& p1, const P2& q1, const P2& r1, const P2& p2, const P2& q2, const P2& r2, bool b, double e)
 {
   if(is_gpeq(cross2(r2, p2, q1), 0., b, e))
   {
@@ -125,8 +125,9 @@ __device__ __forceinline__ bool tri2d(const P2* t1, const P2* t2, bool b, double
   const bool f2 = is_lt(cross2(t2[0], t2[1], t2[2]), 0., e);
   return permuted_2d(t1[0], f1 ? t1[2] : t1[1], f1 ? t1[1] : t1[2], t2[0], f2 ? t2[2] : t2[1], f2 ? t2[1] : t2[2], b, e);
 }
-// intersectCoplanar3DTriangles (:1185-1242): project on the plane of largest normal component
-__device__ __noinline__ bool coplanar(const V3& p1, const V3& q1, const V3& r1, const V3& p2, const V3& q2, const V3& r2, V3 n, bool b, double e)
+// intersectCoplanar3DTriangles (:1185-1242): project on the plane of largest normal component.
+// Rare path, kept out of line; arguments by value so that the callers' vertices stay in registers.
+__device__ __noinline__ bool coplanar(V3 p1, V3 q1, V3 r1, V3 p2, V3 q2, V3 r2, V3 n, bool b, double e)
 {
   n.x = fabs(n.x);
   n.y = fabs(n.y);
@@ -235,14 +236,25 @@ __device__ __forceinline__ void load_tri(const double* __restrict__ tris, long l
 #pragma unroll
   for(int k = 0; k < 3; ++k) t[k] = {__ldg(p + 3 * k), __ldg(p + 3 * k + 1), __ldg(p + 3 * k + 2)};
 }
+// internal triangle record of the mesh tester: 96 bytes = 3 x 32 B (v0.xyz v1.x | v1.yz v2.xy | v2.z pad pad pad),
+// fetched with three LDG.E.256 -- a lane reads a record of its own, so every load instruction is one L1 wavefront
+constexpr int kTriRecDoubles = 12;
+__device__ __forceinline__ void load_tri_rec(const double* __restrict__ recs, long long i, V3* t)
+{
+  const double* p = recs + i * kTriRecDoubles;
+  const D4 a = ldg256(p), b = ldg256(p + 4), c = ldg256(p + 8);
+  t[0] = {a.x, a.y, a.z};
+  t[1] = {a.w, b.x, b.y};
+  t[2] = {b.z, b.w, c.x};
+}
 }  // namespace tt
 
 // Candidate filter of the fused broad + narrow phase (quest/detail/MeshTester_detail.hpp:236-283):
 // keep candidate c of query i iff (i < c or !upper_only) and primal::intersect(tri_i, tri_c, include_boundary, eps)
 struct TriTriFilter
 {
-  const double* __restrict__ query_tris;
-  const double* __restrict__ tree_tris;
+  const double* __restrict__ query_tris;  // 96-byte records (tt::kTriRecDoubles), indexed by query id
+  const double* __restrict__ tree_tris;   // 96-byte records, indexed by candidate (original box) id
   double eps;
   int upper_only;
   int include_boundary;
@@ -250,8 +262,8 @@ struct TriTriFilter
   {
     if(upper_only && !(qi < cand)) return false;
     tt::V3 a[3], b[3];
-    tt::load_tri(query_tris, qi, a);
-    tt::load_tri(tree_tris, cand, b);
+    tt::load_tri_rec(query_tris, qi, a);
+    tt::load_tri_rec(tree_tris, cand, b);
     return tt::tri_tri(a, b, include_boundary != 0, eps);
   }
 };

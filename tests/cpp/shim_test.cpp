@@ -14,6 +14,7 @@
 
 #include "axom_b200/BVH.hpp"
 #include "axom_b200/SignedDistance.hpp"
+#include "axom_b200/MeshTester.hpp"
 
 namespace primal = axom::primal;
 using axom::IndexType;
@@ -214,6 +215,35 @@ static void test_signed_distance()
   EXPECT(mb.getMin()[0] == -5.0 && mb.getMax()[1] == 5.0 && mb.getMax()[2] == 0.0);
 }
 
+static void test_mesh_tester()
+{
+  // primal/tests/primal_intersect.cpp:826-880: "3D tri A pokes through B" intersects with and without the boundary,
+  // "3D tris sharing a segment" only when the boundary is included
+  using Tri3 = primal::Triangle<double, 3>;
+  const Tri3 A(Pt3 {0, 0, 0}, Pt3 {1, 0, 0}, Pt3 {0, 1.7, 2.3});
+  const Tri3 poke(Pt3 {-1, -1, 1}, Pt3 {0, 2, 1}, Pt3 {5, 0, 1});
+  const Tri3 seg(Pt3 {0, 0, 0}, Pt3 {1, 0, 0}, Pt3 {0, -2, 1.2});
+  EXPECT(primal::intersect(A, poke, true) && primal::intersect(A, poke, false));
+  EXPECT(primal::intersect(A, seg, true) && !primal::intersect(A, seg, false));
+  // quest::findTriMeshIntersectionsBVH: the two poking triangles, a far-away one and a degenerate cell
+  const double px[10] = {0, 1, 0, -1, 0, 5, 10, 11, 10, 0}, py[10] = {0, 0, 1.7, -1, 2, 0, 10, 10, 11, 0},
+               pz[10] = {0, 0, 2.3, 1, 1, 1, 10, 10, 10, 0};
+  const IndexType tris[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 0, 0, 1};
+  axom::quest::SurfaceMesh mesh;
+  mesh.x = px;
+  mesh.y = py;
+  mesh.z = pz;
+  mesh.num_nodes = 10;
+  mesh.cells_to_nodes = tris;
+  mesh.num_cells = 4;
+  mesh.nodes_per_cell = 3;
+  std::vector<std::pair<int, int>> isect;
+  std::vector<int> deg;
+  axom::quest::findTriMeshIntersectionsBVH(&mesh, isect, deg);
+  EXPECT(isect.size() == 1 && isect[0].first == 0 && isect[0].second == 1);
+  EXPECT(deg.size() == 1 && deg[0] == 3);
+}
+
 int main(int argc, char** argv)
 {
   axom::error_handler() = throwing_handler;
@@ -243,6 +273,7 @@ int main(int argc, char** argv)
   {
     test_bvh();
     test_signed_distance();
+    test_mesh_tester();
   }
   catch(const std::exception& e)
   {

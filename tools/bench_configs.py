@@ -128,6 +128,80 @@ def find_config(name, args):
     print(json.dumps(line), flush=True)
 
 
+def c3n(args):
+    """SURVEY 8(f) rank 1, the step downstream of C3: quest::findTriMeshIntersectionsBVH on two interpenetrating
+    icospheres (10 M triangles at scale 1): BVH build + ONE fused walk (findBoundingBoxes with the mesh's own AABBs,
+    i < j, exact primal::intersect) + pair scatter.  CPU baseline: the reference's SEQ_EXEC implementation on a smaller
+    mesh of the same shape (triangles/s)."""
+    import torch
+    from axom_b200 import MeshTester, synth
+    from oracle import oracle as O
+    hbm, src = peaks()
+    dev = torch.device("cuda", 0)
+
+    def two_spheres(freq):
+        # coordinates scaled by the geodesic frequency so that triangle edges are O(1): the reference's fuzzy
+        # comparators are absolute (1e-8 on unnormalised cross products), a unit sphere at this resolution
+        # would report no intersections at all
+        x, y, z, c = synth.icosphere(freq)
+        x, y, z = x * freq, y * freq, z * freq
+        X = np.concatenate([x, x * 0.9 + 0.3 * freq])
+        Y = np.concatenate([y, y * 0.9])
+        Z = np.concatenate([z, z * 0.9])
+        return X, Y, Z, np.concatenate([c, c + len(x)]).astype(np.int32)
+
+    freq = max(2, int(round(500 * args.scale ** 0.5)))
+    X, Y, Z, C = two_spheres(freq)
+    n = len(C)
+    Xd, Yd, Zd, Cd = (torch.from_numpy(a).to(dev) for a in (X, Y, Z, C))
+    t0 = time.perf_counter()
+    mt = MeshTester(Xd, Yd, Zd, Cd)
+    torch.cuda.synchronize()
+    setup_wall_ms = (time.perf_counter() - t0) * 1e3
+    b = mt.getBVH()
+
+    def step():
+        return mt.findTriMeshIntersections(1e-8)
+
+    step()
+    b.setProfiling(True)
+    ms, pairs = device_time_ms(step, args.steps)
+    ph = b.phases_ms("find.", ("total", "sortq", "count", "scan", "fill"))
+    # end to end from host arrays: mesh upload + setup + BVH build + fused walk + pairs back on the host
+    t0 = time.perf_counter()
+    mt2 = MeshTester(X, Y, Z, C)
+    hp = mt2.findTriMeshIntersections(1e-8)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    assert np.array_equal(hp, pairs.cpu().numpy())
+    # algorithmic bytes: per triangle its 72 B vertices + 48 B AABB, the node array once, 8 B per reported pair
+    alg_bytes = n * (72 + 48) + 108 * n + 8 * int(pairs.shape[0])
+    cpu = None
+    if not args.no_cpu:
+        kind_ref = "reference" if O.have_reference() else "port"
+        cf = max(2, int(round(freq * 0.2)))
+        x, y, z, c = two_spheres(cf)
+        t0 = time.perf_counter()
+        rp, _ = O.find_tri_mesh_intersections(x, y, z, c, 1e-8, kind_ref)
+        dt = time.perf_counter() - t0
+        gp = MeshTester(x, y, z, c).findTriMeshIntersections(1e-8)
+        cpu = {"value": len(c) / dt, "unit": "triangles/s", "cores": 1, "kind": kind_ref,
+               "sample": "same two-sphere mesh at icosphere frequency %d (%d triangles, %d intersecting pairs), SEQ_EXEC, %.2f s"
+                         % (cf, len(c), len(rp), dt), "matches_gpu_bit_exact": bool(np.array_equal(rp, gp))}
+    print(json.dumps({
+        "metric": "findTriMeshIntersectionsBVH triangles/s (fused broad + narrow phase); setup + BVH build beside it",
+        "value": n / (ms * 1e-3), "unit": "triangles/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "two interpenetrating icospheres (freq %d), %d triangles" % (freq, n), "triangles": n,
+                   "intersecting_pairs": int(pairs.shape[0])},
+        "find_phases_ms_per_call": ph, "setup_wall_ms": setup_wall_ms,
+        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "triangles/s", "ms": e2e_ms,
+                "h2d_bytes_per_step": int(X.nbytes * 3 + C.nbytes), "d2h_bytes_per_step": int(hp.nbytes),
+                "note": "host mesh -> upload, triangle/AABB setup, BVH build, fused walk, pairs back on the host (wall clock)"},
+        "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": alg_bytes, "peak_source": src, "traffic": None},
+        "cpu_baseline": cpu}), flush=True)
+
+
 def c5(args):
     """distributed closest point: surface split into G Morton ranges (one per rank; 8 sequential partitions
     when run on one GPU), unsigned distance per partition, elementwise MIN (NCCL all-reduce when G > 1)."""
@@ -200,7 +274,7 @@ def c5(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("config", choices=["c1", "c3", "c3n", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
@@ -208,6 +282,8 @@ def main():
     args = ap.parse_args()
     if args.config == "c5":
         c5(args)
+    elif args.config == "c3n":
+        c3n(args)
     else:
         find_config(args.config, args)
 
