@@ -84,6 +84,27 @@ SYMBOLS = [
     ("axb_meshtester_free", C.c_int, [_P, _P, C.c_int]),
     ("axb_meshtester_get_bvh", C.c_int, [_P, _PP]),
     ("axb_tri_tri_intersect", C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_double, _P]),
+    # include/axb200_quest.h: the reference's legacy process-global C surface (wrapQUEST.h:83-127) + STL / welding
+    ("QUEST_signed_distance_init_serial", C.c_int, [C.c_char_p]),
+    ("QUEST_signed_distance_init_serial_bufferify", C.c_int, [C.c_char_p, C.c_int]),
+    ("QUEST_signed_distance_initialized", C.c_bool, []),
+    ("QUEST_signed_distance_get_mesh_bounds", None, [_P, _P]),
+    ("QUEST_signed_distance_set_dimension", None, [C.c_int]),
+    ("QUEST_signed_distance_set_closed_surface", None, [C.c_bool]),
+    ("QUEST_signed_distance_set_compute_signs", None, [C.c_bool]),
+    ("QUEST_signed_distance_set_allocator", None, [C.c_int]),
+    ("QUEST_signed_distance_set_verbose", None, [C.c_bool]),
+    ("QUEST_signed_distance_use_shared_memory", None, [C.c_bool]),
+    ("QUEST_signed_distance_set_execution_space", None, [C.c_int]),
+    ("QUEST_signed_distance_evaluate_0", C.c_double, [C.c_double, C.c_double, C.c_double]),
+    ("QUEST_signed_distance_evaluate_1", C.c_double, [C.c_double, C.c_double, C.c_double, _PD, _PD, _PD, _PD, _PD, _PD]),
+    ("QUEST_signed_distance_finalize", None, []),
+    ("axb_quest_signed_distance_init_mesh", C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int]),
+    ("axb_quest_signed_distance_evaluate_n", None, [_P, _P, _P, C.c_int, _P]),
+    ("axb_stl_read", C.c_int, [C.c_char_p, _PP, _PP, _PP, C.POINTER(C.c_int32), _PP, C.POINTER(C.c_int32)]),
+    ("axb_weld_tri_mesh_vertices", C.c_int, [_P, _P, _P, C.POINTER(C.c_int32), _P, C.POINTER(C.c_int32), C.c_double]),
+    ("axb_host_free", None, [_P]),
+    ("axb_quest_set_error_handler", None, [_P]),
 ]
 
 

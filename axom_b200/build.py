@@ -29,7 +29,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(HERE, "..", "include", "axb200.h")]
+    deps = sources() + [os.path.join(HERE, "..", "include", h) for h in ("axb200.h", "axb200_quest.h")]
     return any(os.path.getmtime(s) > t for s in deps)
 
 
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found at %s and no prebuilt %s" % (nvcc, LIB))
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-ccbin", os.environ.get("AXB_HOST_CXX", "/usr/bin/g++"), "-o", LIB, os.path.join(SRC, "api.cu")]
+          ["-ccbin", os.environ.get("AXB_HOST_CXX", "/usr/bin/g++"), "-o", LIB] + [s for s in sources() if s.endswith(".cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

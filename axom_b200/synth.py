@@ -168,3 +168,29 @@ def mesh_cell_boxes(x, y, z, conn):
     """per-cell AABB over the cell's nodes (quest/SignedDistance.hpp:608-633), (ncells, 6)."""
     P = np.stack([x, y, z], axis=1)[conn]
     return np.ascontiguousarray(np.concatenate([P.min(axis=1), P.max(axis=1)], axis=1))
+
+
+def write_stl(path, x, y, z, conn, binary=False, jitter=None):
+    """write a triangle mesh as an STL file (ASCII with 17 significant digits, or binary float32).  `jitter`
+    (n, 3, 3) is added to the per-triangle vertex copies (to exercise vertex welding)."""
+    P = np.stack([x, y, z], 1)[np.asarray(conn)]
+    if jitter is not None:
+        P = P + jitter
+    n = np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])
+    if binary:
+        rec = np.zeros(len(P), dtype=[("n", "<f4", 3), ("v", "<f4", 9), ("a", "<u2")])
+        rec["n"] = n
+        rec["v"] = P.reshape(-1, 9)
+        with open(path, "wb") as f:
+            f.write(b"axom_b200 synthetic surface".ljust(80, b" "))
+            f.write(np.int32(len(P)).tobytes())
+            f.write(rec.tobytes())
+        return
+    with open(path, "w") as f:
+        f.write("solid synth\n")
+        for t, nn in zip(P, n):
+            f.write(" facet normal %.9g %.9g %.9g\n  outer loop\n" % tuple(nn))
+            for v in t:
+                f.write("   vertex %.17g %.17g %.17g\n" % tuple(v))
+            f.write("  endloop\n endfacet\n")
+        f.write("endsolid synth\n")

@@ -68,7 +68,8 @@ COMPONENT_SOURCES = {
              "mesh/RectilinearMesh.cpp", "mesh/StructuredMesh.cpp",
              "mesh/UniformMesh.cpp", "fem/FiniteElement.cpp"],
     "slam": ["BitSet.cpp", "OrderedSet.cpp"],
-    "quest": ["SignedDistance.cpp"],
+    "quest": ["SignedDistance.cpp", "interface/signed_distance.cpp", "interface/internal/QuestHelpers.cpp",
+              "readers/STLReader.cpp", "readers/ProEReader.cpp", "MeshTester.cpp"],
 }
 
 # NOTE: the image exports CXX=/opt/gcc/bin/g++, a wrapper without libgomp; use the system g++.

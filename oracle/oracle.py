@@ -227,5 +227,39 @@ def find_tri_mesh_intersections(x, y, z, conn, threshold=1e-8, kind="port"):
     return np.stack([take(f, n), take(s, n)], axis=1), take(d, nd.value)
 
 
+def ref_legacy_signed_distance(stl_file, x, y, z, closed_surface=True, compute_sign=True):
+    """the REAL reference's process-global interface end to end (quest::signed_distance_init(file), batched evaluate,
+    get_mesh_bounds, finalize).  Reference only.  -> (phi, lo, hi)"""
+    L = lib("reference").lib
+    x, y, z = (np.ascontiguousarray(a, np.float64) for a in (x, y, z))
+    phi, lo, hi = np.empty_like(x), np.empty(3), np.empty(3)
+    L.axref_legacy_signed_distance.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
+    rc = L.axref_legacy_signed_distance(stl_file.encode(), int(closed_surface), int(compute_sign), _ptr(x), _ptr(y), _ptr(z), x.size,
+                                        _ptr(phi), _ptr(lo), _ptr(hi))
+    if rc != 0:
+        raise RuntimeError("reference signed_distance_init failed")
+    return phi, lo, hi
+
+
+def ref_stl_read_weld(stl_file, eps=0.0):
+    """the REAL reference's quest::STLReader (+ quest::weldTriMeshVertices when eps > 0).  -> (x, y, z, conn (n,3))"""
+    L = lib("reference").lib
+    px, py, pz, pc = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nn, nc = C.c_int32(), C.c_int32()
+    L.axref_stl_read_weld.argtypes = [C.c_char_p, C.c_double] + [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
+                                                                                             C.POINTER(C.c_int32)]
+    if L.axref_stl_read_weld(stl_file.encode(), float(eps), C.byref(px), C.byref(py), C.byref(pz), C.byref(nn), C.byref(pc),
+                             C.byref(nc)) != 0:
+        raise RuntimeError("reference STL read failed")
+
+    def take(p, n, ct):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(max(n, 1),))[:n].copy()
+        L.axref_free(p)
+        return a
+    x, y, z = (take(p, nn.value, C.c_double) for p in (px, py, pz))
+    return x, y, z, take(pc, 3 * nc.value, C.c_int32).reshape(-1, 3)
+
+
 def max_threads(kind="port"):
     return lib(kind).fn("max_threads")()

@@ -24,6 +24,8 @@
 #include "axom/primal/geometry/Triangle.hpp"
 #include "axom/primal/operators/intersect.hpp"
 #include "axom/quest/MeshTester.hpp"
+#include "axom/quest/readers/STLReader.hpp"
+#include "axom/quest/interface/signed_distance.hpp"
 
 #include <cstdint>
 #include <cstdlib>
@@ -472,6 +474,54 @@ int64_t axref_find_tri_mesh_intersections(const double* x, const double* y, cons
   *degenerate = d;
   *ndegenerate = (int64_t)deg.size();
   return (int64_t)isect.size();
+}
+
+// the legacy process-global interface, end to end: quest::signed_distance_init(file) -> evaluate(x[],y[],z[],n,phi[])
+// -> get_mesh_bounds -> finalize (quest/interface/signed_distance.hpp:117-319)
+int axref_legacy_signed_distance(const char* stl_file, int closed_surface, int compute_sign, const double* x, const double* y,
+                                 const double* z, int n, double* phi, double* lo, double* hi)
+{
+  namespace q = axom::quest;
+  q::signed_distance_set_closed_surface(closed_surface != 0);
+  q::signed_distance_set_compute_signs(compute_sign != 0);
+  q::signed_distance_set_execution_space(q::SignedDistExec::CPU);
+  const int rc = q::signed_distance_init(std::string(stl_file));
+  if(rc != 0) return rc;
+  q::signed_distance_evaluate(x, y, z, n, phi);
+  q::signed_distance_get_mesh_bounds(lo, hi);
+  q::signed_distance_finalize();
+  return 0;
+}
+
+// quest::STLReader::read + getMesh, then optionally quest::weldTriMeshVertices(&mesh, eps) (eps > 0)
+int axref_stl_read_weld(const char* stl_file, double eps, double** x, double** y, double** z, int32_t* num_nodes, int32_t** conn,
+                        int32_t* num_cells)
+{
+  ensure_slic();
+  using UMesh = axom::mint::UnstructuredMesh<axom::mint::SINGLE_SHAPE>;
+  axom::quest::STLReader reader;
+  reader.setFileName(stl_file);
+  if(reader.read() != 0) return -1;
+  UMesh* mesh = new UMesh(3, axom::mint::TRIANGLE);
+  reader.getMesh(mesh);
+  if(eps > 0.) axom::quest::weldTriMeshVertices(&mesh, eps);
+  const int nn = mesh->getNumberOfNodes(), nc = mesh->getNumberOfCells();
+  *x = (double*)malloc(sizeof(double) * (nn + 1));
+  *y = (double*)malloc(sizeof(double) * (nn + 1));
+  *z = (double*)malloc(sizeof(double) * (nn + 1));
+  *conn = (int32_t*)malloc(sizeof(int32_t) * (3 * nc + 1));
+  memcpy(*x, mesh->getCoordinateArray(0), sizeof(double) * nn);
+  memcpy(*y, mesh->getCoordinateArray(1), sizeof(double) * nn);
+  memcpy(*z, mesh->getCoordinateArray(2), sizeof(double) * nn);
+  for(int c = 0; c < nc; ++c)
+  {
+    const axom::IndexType* ids = mesh->getCellNodeIDs(c);
+    for(int k = 0; k < 3; ++k) (*conn)[3 * c + k] = ids[k];
+  }
+  *num_nodes = nn;
+  *num_cells = nc;
+  delete mesh;
+  return 0;
 }
 
 int axref_max_threads()

@@ -15,6 +15,7 @@
 #include "axom_b200/BVH.hpp"
 #include "axom_b200/SignedDistance.hpp"
 #include "axom_b200/MeshTester.hpp"
+#include "axom_b200/signed_distance.hpp"
 
 namespace primal = axom::primal;
 using axom::IndexType;
@@ -244,6 +245,52 @@ static void test_mesh_tester()
   EXPECT(deg.size() == 1 && deg[0] == 3);
 }
 
+static bool g_quest_error = false;
+static void quest_error_recorder(const char*) { g_quest_error = true; }
+
+static void test_legacy_interface()
+{
+  // quest/tests/quest_signed_distance_interface.cpp:186-237 through the process-global API: z = 0 plane, phi == z
+  namespace quest = axom::quest;
+  axb_quest_set_error_handler(quest_error_recorder);
+  EXPECT(!quest::signed_distance_initialized());
+  g_quest_error = false;
+  quest::signed_distance_evaluate(0., 0., 1.);  // evaluate before init is a SLIC_ERROR (:245-262)
+  EXPECT(g_quest_error);
+  const double px[5] = {-5, 5, 5, -5, 0}, py[5] = {-5, -5, 5, 5, 0}, pz[5] = {0, 0, 0, 0, 0};
+  const IndexType tris[12] = {0, 1, 4, 1, 2, 4, 2, 3, 4, 3, 0, 4};
+  axom::quest::SurfaceMesh mesh;
+  mesh.x = px;
+  mesh.y = py;
+  mesh.z = pz;
+  mesh.num_nodes = 5;
+  mesh.cells_to_nodes = tris;
+  mesh.num_cells = 4;
+  mesh.nodes_per_cell = 3;
+  quest::signed_distance_set_closed_surface(false);
+  quest::signed_distance_set_execution_space(quest::SignedDistExec::GPU);
+  EXPECT(quest::signed_distance_init(&mesh) == 0);
+  EXPECT(quest::signed_distance_initialized());
+  g_quest_error = false;
+  quest::signed_distance_set_closed_surface(true);  // setter after init is a SLIC_ERROR (:264-330)
+  EXPECT(g_quest_error);
+  EXPECT(quest::signed_distance_evaluate(1.0, 2.0, -3.0) == -3.0);
+  double cx, cy, cz, nx, ny, nz;
+  EXPECT(quest::signed_distance_evaluate(0.25, 0.5, 2.0, cx, cy, cz, nx, ny, nz) == 2.0);
+  EXPECT(cx == 0.25 && cy == 0.5 && cz == 0.0 && nz == 1.0);
+  const double qx[3] = {0, 1, -2}, qy[3] = {0, -1, 2}, qz[3] = {0.5, -0.25, 4};
+  double phi[3];
+  quest::signed_distance_evaluate(qx, qy, qz, 3, phi);
+  EXPECT(phi[0] == 0.5 && phi[1] == -0.25 && phi[2] == 4.0);
+  double lo[3], hi[3];
+  quest::signed_distance_get_mesh_bounds(lo, hi);
+  EXPECT(lo[0] == -5.0 && hi[1] == 5.0 && lo[2] == 0.0 && hi[2] == 0.0);
+  quest::signed_distance_finalize();
+  EXPECT(!quest::signed_distance_initialized());
+  quest::signed_distance_set_closed_surface(true);
+  axb_quest_set_error_handler(nullptr);
+}
+
 int main(int argc, char** argv)
 {
   axom::error_handler() = throwing_handler;
@@ -274,6 +321,7 @@ int main(int argc, char** argv)
     test_bvh();
     test_signed_distance();
     test_mesh_tester();
+    test_legacy_interface();
   }
   catch(const std::exception& e)
   {

@@ -66,10 +66,35 @@ def meshtester_case(name):
                         hit_closed=O.tri_tri_intersect(t1.astype(np.float32), t2.astype(np.float32), True, 1e-8, "reference"))
 
 
+def stl_weld_case(name):
+    """quest::STLReader + quest::weldTriMeshVertices on a jittered icosphere soup, and the legacy process-global
+    signed-distance API (signed_distance_init(file) ... evaluate) on an ASCII STL: the inputs are re-created by
+    tests/test_quest_interface.py with the same seeds"""
+    import tempfile
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        x, y, z, conn = synth.icosphere(6)
+        jit = np.random.default_rng(3).uniform(-2e-8, 2e-8, (len(conn), 3, 3))
+        p = os.path.join(d, "s.stl")
+        synth.write_stl(p, x, y, z, conn, binary=False, jitter=jit)
+        for eps in (1e-7, 1e-3, 0.1):
+            wx, wy, wz, wc = O.ref_stl_read_weld(p, eps)
+            out["eps_%g_xyz" % eps] = np.stack([wx, wy, wz], 1)
+            out["eps_%g_conn" % eps] = wc
+        x, y, z, conn = synth.icosphere(8)
+        p = os.path.join(d, "t.stl")
+        synth.write_stl(p, x, y, z, conn, binary=False)
+        q = synth.uniform_grid_points(-1, 1, 12)
+        phi, lo, hi = O.ref_legacy_signed_distance(p, q[:, 0].copy(), q[:, 1].copy(), q[:, 2].copy())
+        out["legacy_phi_ascii_f8"] = phi
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 if __name__ == "__main__":
     assert O.have_reference(), "build the reference first: python oracle/build_ref.py"
     bvh_case("bvh3d_n600", 600, 3, 41)
     bvh_case("bvh2d_n400", 400, 2, 43)
     sd_case("sd_icosphere5", 5, 9)
     meshtester_case("meshtester_spheres")
+    stl_weld_case("stl_weld")
     print("golden fixtures written to", HERE)

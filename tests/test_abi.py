@@ -10,9 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_functions():
-    txt = open(os.path.join(ROOT, "include", "axb200.h")).read()
-    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(axb_[a-z0-9_]+)\s*\(", txt)))
+    names = set()
+    for h in ("axb200.h", "axb200_quest.h"):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        txt = re.sub(r"typedef[^;]*;", "", txt)
+        names |= set(re.findall(r"\b((?:axb|QUEST)_[A-Za-z0-9_]+)\s*\(", txt))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
