@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libaxb200.so")
+LIB_PATH = os.environ.get("AXB200_LIB") or os.path.join(HERE, "lib", "libaxb200.so")  # AXB200_LIB: tuning builds
 
 AXB_OK = 0
 AXB_ERR_BAD_ARG, AXB_ERR_CUDA, AXB_ERR_OVERFLOW, AXB_ERR_NOT_BUILT, AXB_ERR_NO_DEVICE, AXB_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6

@@ -946,8 +946,20 @@ struct axb_sd
   int mode = 1;  // 1 = OBB-accelerated, Morton-ordered queries (default); 0 = reference visiting order
   bool count_work = false;
   SdParams prm;
-  DevBuf x, y, z, conn, offsets, soup, cell_boxes, obounds, q_stage, out_phi, out_cp, out_n, work;
-  DevBuf sdnodes, sdcens, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor;
+  DevBuf x, y, z, conn, offsets, soup, cell_boxes, obounds, work;
+  DevBuf sdnodes, sdcens;
+  // per-query scratch, two sets: a host-to-host query is cut into chunks that alternate between two streams so
+  // that the upload of chunk i+1 and the download of chunk i-1 overlap the kernel of chunk i
+  struct QBufs
+  {
+    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor;
+    void release(cudaStream_t st)
+    {
+      for(DevBuf* b : {&q_stage, &out_phi, &out_cp, &out_n, &qkeys_a, &qkeys_b, &qscratch, &qperm, &qbounds, &cursor}) b->release(st);
+    }
+  } qb[2];
+  cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+  cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
   int fast_blocks_per_sm = 0;  // occupancy of the persistent query kernel (queried once)
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
   Ctx& ctx() { return bvh->ctx; }
@@ -1108,7 +1120,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
                    s->sdnodes.as<SdNode>(), big_list, big_count);
       }
       big.release(ctx.stream);
-      AXB_TRY(s->cursor.reserve(sizeof(unsigned int), ctx.stream));
+      for(int k = 0; k < 2; ++k) AXB_TRY(s->qb[k].cursor.reserve(sizeof(unsigned int), ctx.stream));
       int bps = 0;
       if(s->nv == 3)
       {
@@ -1141,9 +1153,19 @@ int axb_sd_destroy(axb_sd* s)
   {
     cudaSetDevice(s->ctx().device);
     cudaStream_t st = s->ctx().stream;
-    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->offsets, &s->soup, &s->cell_boxes, &s->obounds, &s->q_stage, &s->out_phi, &s->out_cp,
-                     &s->out_n, &s->work, &s->sdnodes, &s->sdcens, &s->qkeys_a, &s->qkeys_b, &s->qscratch, &s->qperm, &s->qbounds, &s->cursor})
+    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->offsets, &s->soup, &s->cell_boxes, &s->obounds, &s->work, &s->sdnodes, &s->sdcens})
       b->release(st);
+    for(int k = 0; k < 2; ++k)
+    {
+      s->qb[k].release(st);
+      if(s->pipe_stream[k])
+      {
+        cudaStreamSynchronize(s->pipe_stream[k]);
+        cudaStreamDestroy(s->pipe_stream[k]);
+      }
+    }
+    for(cudaEvent_t& e : s->pipe_event)
+      if(e) cudaEventDestroy(e);
     axb_bvh_destroy(s->bvh);
   }
   delete s;
@@ -1199,43 +1221,29 @@ int axb_sd_get_work_counters(const axb_sd* s, int64_t* leaf_tests, int64_t* inne
   return AXB_OK;
 }
 
-int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts, double* phi, double* cps, double* nrms, int out_memspace)
+// One contiguous range of queries, enqueued on ctx.stream with the scratch set B: stage (host inputs), Morton
+// order, the query kernel, and -- for host outputs -- the copies back.  Does not synchronise.
+static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpts, int32_t npts, double* phi, double* cps, double* nrms,
+                          int out_memspace, unsigned long long* d_work)
 {
-  if(!s) return fail(AXB_ERR_BAD_ARG, "null handle");
-  if(npts < 0) return fail(AXB_ERR_BAD_ARG, "negative point count");
-  if(npts > 0 && !phi) return fail(AXB_ERR_BAD_ARG, "outSgnDist != nullptr");
-  out_memspace = resolve_memspace(out_memspace, phi);
-  if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown output memspace");
-  if(!s->bvh->built) return fail(AXB_ERR_NOT_BUILT, "SignedDistance query before setMesh()");
   Ctx& ctx = s->ctx();
-  AXB_TRY(ctx.bind());
-  ctx.begin_call();
-  if(npts == 0) return AXB_OK;
-  const int tot = ctx.phase_begin("query.total");
   Desc<3> q;
-  AXB_TRY(stage_desc<3>(ctx, qpts, npts, sizeof(double), s->q_stage, q));
+  AXB_TRY(stage_desc<3>(ctx, qpts, npts, sizeof(double), B.q_stage, q));
   double *d_phi = phi, *d_cp = cps, *d_n = nrms;
   if(out_memspace == AXB_MEM_HOST)
   {
-    AXB_TRY(s->out_phi.reserve(sizeof(double) * (size_t)npts, ctx.stream));
-    d_phi = s->out_phi.as<double>();
+    AXB_TRY(B.out_phi.reserve(sizeof(double) * (size_t)npts, ctx.stream));
+    d_phi = B.out_phi.as<double>();
     if(cps)
     {
-      AXB_TRY(s->out_cp.reserve(sizeof(double) * 3 * (size_t)npts, ctx.stream));
-      d_cp = s->out_cp.as<double>();
+      AXB_TRY(B.out_cp.reserve(sizeof(double) * 3 * (size_t)npts, ctx.stream));
+      d_cp = B.out_cp.as<double>();
     }
     if(nrms)
     {
-      AXB_TRY(s->out_n.reserve(sizeof(double) * 3 * (size_t)npts, ctx.stream));
-      d_n = s->out_n.as<double>();
+      AXB_TRY(B.out_n.reserve(sizeof(double) * 3 * (size_t)npts, ctx.stream));
+      d_n = B.out_n.as<double>();
     }
-  }
-  unsigned long long* d_work = nullptr;
-  if(s->count_work)
-  {
-    AXB_TRY(s->work.reserve(sizeof(unsigned long long) * 2, ctx.stream));
-    AXB_CUDA_TRY(cudaMemsetAsync(s->work.p, 0, sizeof(unsigned long long) * 2, ctx.stream));
-    d_work = s->work.as<unsigned long long>();
   }
   const Node<double, 3>* nodes = s->bvh->nodes.as<Node<double, 3>>();
   if(s->mode == 1)
@@ -1246,35 +1254,31 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
       // Morton order of the query points: neighbouring threads walk the same nodes
       ScopedPhase ph(ctx, "query.sortq");
       const size_t kb = sizeof(unsigned long long) * (size_t)npts;
-      AXB_TRY(s->qkeys_a.reserve(kb, ctx.stream));
-      AXB_TRY(s->qkeys_b.reserve(kb, ctx.stream));
-      AXB_TRY(s->qperm.reserve(sizeof(int32_t) * (size_t)npts, ctx.stream));
-      AXB_TRY(s->qbounds.reserve(sizeof(unsigned long long) * 6, ctx.stream));
+      AXB_TRY(B.qkeys_a.reserve(kb, ctx.stream));
+      AXB_TRY(B.qkeys_b.reserve(kb, ctx.stream));
+      AXB_TRY(B.qperm.reserve(sizeof(int32_t) * (size_t)npts, ctx.stream));
+      AXB_TRY(B.qbounds.reserve(sizeof(unsigned long long) * 6, ctx.stream));
       const size_t scratch = rsort::scratch_bytes(npts);
-      AXB_TRY(s->qscratch.reserve(scratch, ctx.stream));
-      AXB_CUDA_TRY(cudaMemsetAsync(s->qscratch.p, 0, scratch, ctx.stream));
-      uint32_t* ghist = s->qscratch.as<uint32_t>();
+      AXB_TRY(B.qscratch.reserve(scratch, ctx.stream));
+      AXB_CUDA_TRY(cudaMemsetAsync(B.qscratch.p, 0, scratch, ctx.stream));
+      uint32_t* ghist = B.qscratch.as<uint32_t>();
       uint32_t* tile_counters = ghist + rsort::MAX_PASSES * rsort::RADIX;
       uint32_t* lookback = tile_counters + 64;
-      unsigned long long init[6];
-      for(int d = 0; d < 3; ++d)
-      {
-        init[d] = f64_to_ordered(DBL_MAX);
-        init[3 + d] = f64_to_ordered(-DBL_MAX);
-      }
-      AXB_CUDA_TRY(cudaMemcpyAsync(s->qbounds.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
-      AXB_LAUNCH(ctx, query_bounds_kernel, capped_grid(npts, 256), 256, q, npts, s->qbounds.as<unsigned long long>());
-      AXB_LAUNCH(ctx, query_keys_kernel, capped_grid(npts, 256), 256, q, npts, s->qbounds.as<unsigned long long>(),
-                 s->qkeys_a.as<unsigned long long>(), ghist);
+      // (a kernel, not a copy from pageable host memory: that would block the host until the stream gets there and
+      // serialise the chunk pipeline)
+      AXB_LAUNCH(ctx, init_query_bounds_kernel, 1, 32, B.qbounds.as<unsigned long long>());
+      AXB_LAUNCH(ctx, query_bounds_kernel, capped_grid(npts, 256), 256, q, npts, B.qbounds.as<unsigned long long>());
+      AXB_LAUNCH(ctx, query_keys_kernel, capped_grid(npts, 256), 256, q, npts, B.qbounds.as<unsigned long long>(),
+                 B.qkeys_a.as<unsigned long long>(), ghist);
       unsigned long long* sorted = nullptr;
-      AXB_TRY(sort_keys_generic(ctx, s->qkeys_a.as<unsigned long long>(), s->qkeys_b.as<unsigned long long>(), npts, ghist,
+      AXB_TRY(sort_keys_generic(ctx, B.qkeys_a.as<unsigned long long>(), B.qkeys_b.as<unsigned long long>(), npts, ghist,
                                 tile_counters, lookback, &sorted));
-      AXB_LAUNCH(ctx, keys_to_perm_kernel, blocks_for(npts, 256), 256, sorted, npts, s->qperm.as<int32_t>());
-      perm = s->qperm.as<int32_t>();
+      AXB_LAUNCH(ctx, keys_to_perm_kernel, blocks_for(npts, 256), 256, sorted, npts, B.qperm.as<int32_t>());
+      perm = B.qperm.as<int32_t>();
     }
     ScopedPhase ph(ctx, "query.kernel");
     // persistent warps: one resident wave, queries pulled from a device-side cursor
-    AXB_CUDA_TRY(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned int), ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(B.cursor.p, 0, sizeof(unsigned int), ctx.stream));
     int sms = kNumSMsB200;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
     const int grid = (int)std::min<long long>(blocks_for(npts, 128), (long long)sms * s->fast_blocks_per_sm);
@@ -1284,10 +1288,10 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
     if(const char* e = getenv("AXB_SD_CHUNK")) chunk = (unsigned)std::max(32, atoi(e));
     if(s->nv == 3)
       AXB_LAUNCH_SMEM(ctx, sd_fast_kernel<3>, grid, 128, kSdFastSmem, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->soup.as<double>(), s->prm, q,
-                      npts, perm, d_phi, d_cp, d_n, d_work, s->cursor.as<unsigned int>(), chunk);
+                      npts, perm, d_phi, d_cp, d_n, d_work, B.cursor.as<unsigned int>(), chunk);
     else
       AXB_LAUNCH_SMEM(ctx, sd_fast_kernel<4>, grid, 128, kSdFastSmem, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->soup.as<double>(), s->prm, q,
-                      npts, perm, d_phi, d_cp, d_n, d_work, s->cursor.as<unsigned int>(), chunk);
+                      npts, perm, d_phi, d_cp, d_n, d_work, B.cursor.as<unsigned int>(), chunk);
   }
   else
   {
@@ -1299,14 +1303,78 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
       AXB_LAUNCH(ctx, sd_reference_order_kernel<4>, blocks_for(npts, 128), 128, nodes, s->soup.as<double>(), s->prm, q, npts,
                  (const int32_t*)nullptr, d_phi, d_cp, d_n, d_work);
   }
-  ctx.phase_end(tot);
   if(out_memspace == AXB_MEM_HOST)
   {
     AXB_CUDA_TRY(cudaMemcpyAsync(phi, d_phi, sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
     if(cps) AXB_CUDA_TRY(cudaMemcpyAsync(cps, d_cp, sizeof(double) * 3 * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
     if(nrms) AXB_CUDA_TRY(cudaMemcpyAsync(nrms, d_n, sizeof(double) * 3 * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
-    AXB_TRY(ctx.sync());
   }
+  return AXB_OK;
+}
+
+int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts, double* phi, double* cps, double* nrms, int out_memspace)
+{
+  if(!s) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(npts < 0) return fail(AXB_ERR_BAD_ARG, "negative point count");
+  if(npts > 0 && !phi) return fail(AXB_ERR_BAD_ARG, "outSgnDist != nullptr");
+  if(npts > 0 && !qpts) return fail(AXB_ERR_BAD_ARG, "null query descriptor");
+  out_memspace = resolve_memspace(out_memspace, phi);
+  if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown output memspace");
+  if(!s->bvh->built) return fail(AXB_ERR_NOT_BUILT, "SignedDistance query before setMesh()");
+  Ctx& ctx = s->ctx();
+  AXB_TRY(ctx.bind());
+  ctx.begin_call();
+  if(npts == 0) return AXB_OK;
+  const int tot = ctx.phase_begin("query.total");
+  unsigned long long* d_work = nullptr;
+  if(s->count_work)
+  {
+    AXB_TRY(s->work.reserve(sizeof(unsigned long long) * 2, ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(s->work.p, 0, sizeof(unsigned long long) * 2, ctx.stream));
+    d_work = s->work.as<unsigned long long>();
+  }
+  // Opt-in (AXB_SD_PIPE_CHUNK = points per chunk): with host inputs AND host outputs, cut the call into chunks that
+  // alternate between two streams, so the PCIe traffic of neighbouring chunks hides behind the kernel (pinned host
+  // buffers).  The result does not depend on the chunking: queries are independent.  Off by default: measured on the
+  // C2 workload (tools/pipe_probe.py) the copies do overlap, but a persistent kernel per chunk loses as much in
+  // start-up and tail (8 x 2 M points: 110.9 ms, 2 x 8 M: 105.8 ms, unchunked: 107.0 ms of which 96.3 ms kernel).
+  long long pipe_chunk = 0;
+  if(const char* e = getenv("AXB_SD_PIPE_CHUNK")) pipe_chunk = atoll(e);
+  const bool host_in = resolve_memspace(qpts->memspace, qpts->comp[0]) == AXB_MEM_HOST;
+  if(host_in && out_memspace == AXB_MEM_HOST && !ctx.async && pipe_chunk > 0 && (long long)npts >= 2 * pipe_chunk)
+  {
+    for(int k = 0; k < 2; ++k)
+      if(!s->pipe_stream[k]) AXB_CUDA_TRY(cudaStreamCreateWithFlags(&s->pipe_stream[k], cudaStreamNonBlocking));
+    for(cudaEvent_t& e : s->pipe_event)
+      if(!e) AXB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaStream_t main_stream = ctx.stream;
+    AXB_CUDA_TRY(cudaEventRecord(s->pipe_event[2], main_stream));
+    for(int k = 0; k < 2; ++k) AXB_CUDA_TRY(cudaStreamWaitEvent(s->pipe_stream[k], s->pipe_event[2], 0));
+    int st = AXB_OK;
+    int k = 0;
+    for(long long first = 0; first < npts && st == AXB_OK; first += pipe_chunk, k ^= 1)
+    {
+      const int32_t n = (int32_t)std::min<long long>(pipe_chunk, npts - first);
+      axb_array_desc sub = *qpts;
+      for(int c = 0; c < sub.ncomp && c < 6; ++c) sub.comp[c] = (const char*)qpts->comp[c] + first * qpts->stride_bytes;
+      ctx.stream = s->pipe_stream[k];  // everything sd_query_range enqueues goes to this chunk's stream
+      st = sd_query_range(s, s->qb[k], &sub, n, phi + first, cps ? cps + 3 * first : nullptr, nrms ? nrms + 3 * first : nullptr,
+                          AXB_MEM_HOST, d_work);
+    }
+    ctx.stream = main_stream;
+    for(int j = 0; j < 2; ++j)
+    {
+      AXB_CUDA_TRY(cudaEventRecord(s->pipe_event[j], s->pipe_stream[j]));
+      AXB_CUDA_TRY(cudaStreamWaitEvent(main_stream, s->pipe_event[j], 0));
+    }
+    AXB_TRY(st);
+  }
+  else
+  {
+    AXB_TRY(sd_query_range(s, s->qb[0], qpts, npts, phi, cps, nrms, out_memspace, d_work));
+  }
+  ctx.phase_end(tot);
+  if(out_memspace == AXB_MEM_HOST) AXB_TRY(ctx.sync());
   if(d_work)
   {
     unsigned long long hw[2];

@@ -53,54 +53,53 @@ __device__ __forceinline__ bool is_geq(double x, double y, double e) { return !(
 
 // primal::closest_point(Point, Triangle, int* loc, EPS) -- closest_point.hpp:162-290.
 // Region tests in the reference's order: A, B, AB (with the !isNearlyEqual(d1,d3) guard), C, AC, BC, face.
+//
+// The reference returns from the first region that matches.  In a warp every lane tests a different triangle
+// and lands in a different region, so the early returns execute 7 ways divergent (profiles/r1h: 3-5 of 32 lanes
+// active on these lines, 30 % of the kernel's instructions).  Here all six dot products, the three sub-determinants
+// and the seven region predicates are evaluated unconditionally, the FIRST matching region in the reference's order
+// is selected, and the single division any region needs is issued once.  Every value that reaches the result is
+// computed by the same expression (same operands, same order, no FMA) as in the reference, so the closest point and
+// `loc` are bit-identical; values of regions not taken are discarded (a zero denominator there is harmless).
 __device__ __forceinline__ V3 closest_point_tri(const V3& P, const V3& A, const V3& B, const V3& C, int& loc, double EPS)
 {
-  const V3 ab = v3sub(B, A), ac = v3sub(C, A), ap = v3sub(P, A);
+  const V3 ab = v3sub(B, A), ac = v3sub(C, A), ap = v3sub(P, A), bp = v3sub(P, B), cp = v3sub(P, C);
   const double d1 = v3dot(ab, ap), d2 = v3dot(ac, ap);
-  if(is_leq(d1, 0, EPS) && is_leq(d2, 0, EPS))
-  {
-    loc = 0;
-    return A;
-  }
-  const V3 bp = v3sub(P, B);
   const double d3 = v3dot(ab, bp), d4 = v3dot(ac, bp);
-  if(is_geq(d3, 0, EPS) && is_leq(d4, d3, EPS))
-  {
-    loc = 1;
-    return B;
-  }
-  const double vc = d1 * d4 - d3 * d2;
-  if(is_leq(vc, 0, EPS) && is_geq(d1, 0, EPS) && is_leq(d3, 0, EPS) && !nearly_eq(d1, d3, EPS))
-  {
-    const double v = d1 / (d1 - d3);
-    loc = -1;
-    return v3add(A, v3mul(ab, v));
-  }
-  const V3 cp = v3sub(P, C);
   const double d5 = v3dot(ab, cp), d6 = v3dot(ac, cp);
-  if(is_geq(d6, 0, EPS) && is_leq(d5, d6, EPS))
-  {
-    loc = 2;
-    return C;
-  }
+  const double vc = d1 * d4 - d3 * d2;
   const double vb = d5 * d2 - d1 * d6;
-  if(is_leq(vb, 0, EPS) && is_geq(d2, 0, EPS) && is_leq(d6, 0, EPS))
-  {
-    const double w = d2 / (d2 - d6);
-    loc = -3;
-    return v3add(A, v3mul(ac, w));
-  }
   const double va = d3 * d6 - d5 * d4;
-  if(is_leq(va, 0, EPS) && is_geq(d4 - d3, 0, EPS) && is_geq(d5 - d6, 0, EPS))
-  {
-    const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
-    loc = -2;
-    return v3add(B, v3mul(v3sub(C, B), w));
-  }
-  const double denom = 1.0 / (va + vb + vc);
-  const double v = vb * denom, w = vc * denom;
-  loc = 3;
-  return v3add(A, v3add(v3mul(ab, v), v3mul(ac, w)));
+  const double d43 = d4 - d3, d56 = d5 - d6;
+  const bool rA = is_leq(d1, 0, EPS) && is_leq(d2, 0, EPS);
+  const bool rB = is_geq(d3, 0, EPS) && is_leq(d4, d3, EPS);
+  const bool rAB = is_leq(vc, 0, EPS) && is_geq(d1, 0, EPS) && is_leq(d3, 0, EPS) && !nearly_eq(d1, d3, EPS);
+  const bool rC = is_geq(d6, 0, EPS) && is_leq(d5, d6, EPS);
+  const bool rAC = is_leq(vb, 0, EPS) && is_geq(d2, 0, EPS) && is_leq(d6, 0, EPS);
+  const bool rBC = is_leq(va, 0, EPS) && is_geq(d43, 0, EPS) && is_geq(d56, 0, EPS);
+  // first match wins: 0 A, 1 B, 2 AB, 3 C, 4 AC, 5 BC, 6 face
+  const int region = rA ? 0 : (rB ? 1 : (rAB ? 2 : (rC ? 3 : (rAC ? 4 : (rBC ? 5 : 6)))));
+  // the one quotient of the region: AB d1/(d1-d3), AC d2/(d2-d6), BC (d4-d3)/((d4-d3)+(d5-d6)), face 1/(va+vb+vc)
+  const double num = region == 2 ? d1 : (region == 4 ? d2 : (region == 5 ? d43 : 1.0));
+  const double den = region == 2 ? (d1 - d3) : (region == 4 ? (d2 - d6) : (region == 5 ? (d43 + d56) : (region == 6 ? (va + vb + vc) : 1.0)));
+  const double q = num / den;
+  // edge form  base + dir * q
+  const V3 bc = v3sub(C, B);
+  const V3 base = region == 5 ? B : A;
+  const V3 dir = region == 2 ? ab : (region == 4 ? ac : bc);
+  const V3 edge_pt = v3add(base, v3mul(dir, q));
+  // face form  A + (ab * (vb * q) + ac * (vc * q))
+  const double v = vb * q, w = vc * q;
+  const V3 face_pt = v3add(A, v3add(v3mul(ab, v), v3mul(ac, w)));
+  const V3 vert_pt = region == 0 ? A : (region == 1 ? B : C);
+  loc = region == 0 ? 0 : (region == 1 ? 1 : (region == 2 ? -1 : (region == 3 ? 2 : (region == 4 ? -3 : (region == 5 ? -2 : 3)))));
+  const bool is_vertex = region == 0 || region == 1 || region == 3;
+  const bool is_face = region == 6;
+  V3 r;
+  r.x = is_vertex ? vert_pt.x : (is_face ? face_pt.x : edge_pt.x);
+  r.y = is_vertex ? vert_pt.y : (is_face ? face_pt.y : edge_pt.y);
+  r.z = is_vertex ? vert_pt.z : (is_face ? face_pt.z : edge_pt.z);
+  return r;
 }
 
 // Triangle::angle (Triangle.hpp:384-400); idx in {0,1,2}, selected without indexing so the

@@ -47,7 +47,7 @@ struct alignas(32) SdNode
 {
   int32_t child[2];  // >= 0 inner node, < 0 leaf -(sorted_pos+1)
   double org[3];
-  float cb[2][12];  // per child: n[3], t1[3], lo[3], hi[3]
+  float cb[2][12];  // per child: n[3], t1[3], c[3] (extent centre), h[3] (half extent, rounded up; -inf = invalid)
 };
 static_assert(sizeof(SdNode) == 128, "SdNode is 4 x 32 B");
 struct alignas(32) SdCen
@@ -66,6 +66,17 @@ __device__ __forceinline__ void obb_axes(const float* f, V3* A)
   A[0] = {(double)f[0], (double)f[1], (double)f[2]};
   A[1] = {(double)f[3], (double)f[4], (double)f[5]};
   A[2] = v3cross(A[0], A[1]);
+}
+
+// extent [lo, hi] of a child along axis k, stored as centre c (float, nearest) and half extent h (float, rounded UP
+// from the larger one-sided distance to the ROUNDED centre), so that  max(lo - d, d - hi, 0) >= max(|d - c| - h, 0):
+// one |.|, one subtraction and one clamp per axis in the query instead of three double-precision fmax
+__device__ __forceinline__ void store_extent(float* out, int k, double lo, double hi)
+{
+  const float c = __double2float_rn(0.5 * (lo + hi));
+  const double cd = (double)c;
+  out[6 + k] = c;
+  out[9 + k] = __double2float_ru(fmax(hi - cd, cd - lo));
 }
 
 constexpr int kObbMaxRange = 262144;  // subtrees with more leaves keep only their AABB (an orientation no longer helps)
@@ -209,8 +220,7 @@ __device__ __forceinline__ void obb_of_range(const Group& g, const double* __res
     {
       // pad by the rounding of the projections (a few ulp of the coordinate magnitude), then round outward
       const double pad = 1e-14 * (fabs(lo[k]) + fabs(hi[k]) + omag) + 1e-300;
-      out[6 + k] = __double2float_rd(lo[k] - pad);
-      out[9 + k] = __double2float_ru(hi[k] + pad);
+      store_extent(out, k, lo[k] - pad, hi[k] + pad);
     }
   }
 }
@@ -264,13 +274,12 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
       {
         const double lo = bb.lo[lane] - org[lane], hi = bb.hi[lane] - org[lane];
         const double pad = 1e-14 * (fabs(lo) + fabs(hi) + omag) + 1e-300;
-        out[6 + lane] = __double2float_rd(lo - pad);
-        out[9 + lane] = __double2float_ru(hi + pad);
+        store_extent(out, lane, lo - pad, hi + pad);
       }
       else
       {
-        out[6 + lane] = __int_as_float(0x7f800000);  // +inf
-        out[9 + lane] = __int_as_float(0xff800000);  // -inf
+        out[6 + lane] = 0.f;
+        out[9 + lane] = __int_as_float(0xff800000);  // half extent -inf: |d - c| - h = +inf, infinitely far
       }
     }
     return;
@@ -313,7 +322,8 @@ __device__ __forceinline__ double obb_sqdist(const float* f, const double* r)
   for(int k = 0; k < 3; ++k)
   {
     const double d = fma(A[k].x, r[0], fma(A[k].y, r[1], A[k].z * r[2]));
-    const double g = fmax(fmax((double)f[6 + k] - d, d - (double)f[9 + k]), 0.0);
+    const double t = fabs(d - (double)f[6 + k]) - (double)f[9 + k];
+    const double g = t > 0.0 ? t : 0.0;
     s = fma(g, g, s);
   }
   return s * kBoundScale;
@@ -443,6 +453,9 @@ __device__ __forceinline__ void check_leaf_lazy(const double* __restrict__ soup,
 // Each lane still walks the tree in the reference's child order with a (node, lower bound) stack, so
 // everything said in the header about bit-identical results holds.
 //------------------------------------------------------------------------------------------
+#ifndef AXB_SD_MIN_BLOCKS
+  #define AXB_SD_MIN_BLOCKS 4  // resident blocks per SM the register allocation is sized for
+#endif
 constexpr int kSmemStack = 32;   // stack levels kept in shared memory (the rest, rarely reached, in local memory)
 constexpr size_t kSdFastSmem = (size_t)kSmemStack * 128 * sizeof(unsigned long long);  // 128 threads per block
 constexpr int kPend = 4;         // queued leaves per lane
@@ -451,7 +464,7 @@ constexpr int kFinishVote = 4;   // finished lanes that trigger a finalisation s
 constexpr int kQueryChunk = 128;  // queries a warp takes from the cursor at a time (a run of Morton neighbours)
 
 template <int NV>
-__global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__ nodes, const SdCen* __restrict__ cens, const double* __restrict__ soup, SdParams prm,
+__global__ void __launch_bounds__(128, AXB_SD_MIN_BLOCKS) sd_fast_kernel(const SdNode* __restrict__ nodes, const SdCen* __restrict__ cens, const double* __restrict__ soup, SdParams prm,
                                                        Desc<3> qpts, int npts, const int32_t* __restrict__ perm, double* __restrict__ phi,
                                                        double* __restrict__ cps, double* __restrict__ nrms,
                                                        unsigned long long* __restrict__ work, unsigned int* __restrict__ cursor,
@@ -634,19 +647,7 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
     // ---- inner step ----
     if(want_inner)
     {
-      // a leaf in hand joins the queue; what follows it on the stack comes into hand
-      while(cur < 0 && cur != kBarrier && npend < kPend)
-      {
-#pragma unroll
-        for(int k = 0; k < kPend; ++k)
-          if(k == npend)
-          {
-            pend_id[k] = cur;
-            pend_lb[k] = cur_lb;
-          }
-        ++npend;
-        pop();
-      }
+      bool need_pop = false;
       if(cur >= 0)
       {
         ++ninner;
@@ -707,8 +708,34 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
         }
         else
         {
-          pop();
+          need_pop = true;
         }
+      }
+      // One pop site for the whole step (lanes whose children were both pruned and lanes holding a leaf converge
+      // here; with a pop() in each branch they ran it 3 lanes at a time, 11 % of the kernel's instructions).
+      // A leaf in hand joins the queue and what follows it on the stack comes into hand, until the lane holds an
+      // inner node, the queue is full or the traversal is finished.
+      while(true)
+      {
+        if(need_pop)
+        {
+          pop();
+          need_pop = false;
+        }
+        if(cur < 0 && cur != kBarrier && npend < kPend)
+        {
+#pragma unroll
+          for(int k = 0; k < kPend; ++k)
+            if(k == npend)
+            {
+              pend_id[k] = cur;
+              pend_lb[k] = cur_lb;
+            }
+          ++npend;
+          need_pop = true;
+        }
+        else
+          break;
       }
     }
   }
@@ -726,6 +753,16 @@ __global__ void __launch_bounds__(128) sd_fast_kernel(const SdNode* __restrict__
       atomicAdd(&work[0], a);
       atomicAdd(&work[1], b);
     }
+  }
+}
+
+// empty bounds (ordered-uint64 encoding) for query_bounds_kernel
+__global__ void init_query_bounds_kernel(unsigned long long* __restrict__ ob)
+{
+  if(threadIdx.x < 3)
+  {
+    ob[threadIdx.x] = f64_to_ordered(DBL_MAX);
+    ob[3 + threadIdx.x] = f64_to_ordered(-DBL_MAX);
   }
 }
 

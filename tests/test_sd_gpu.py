@@ -171,3 +171,24 @@ def test_mixed_shape_mesh(oracle, have_ref):
     bad[1] += 2  # a 6-node "cell" followed by a 1-node one
     with pytest.raises(AxbError):
         SignedDistance(xs, ys, zs, conn, isWatertight=False, cell_node_offsets=bad)
+
+
+def test_host_to_host_query_is_pipelined_in_chunks(oracle, monkeypatch):
+    """host inputs + host outputs above 2 x AXB_SD_PIPE_CHUNK points go through the two-stream chunk pipeline
+    (upload / kernel / download of neighbouring chunks overlap); results must not depend on the chunking, with
+    closest points and normals, AoS and SoA query layouts, and a ragged last chunk"""
+    from axom_b200 import SignedDistance
+    monkeypatch.setenv("AXB_SD_PIPE_CHUNK", "4096")
+    x, y, z, conn = synth.icosphere(12)
+    q = synth.random_points(4096 * 5 + 123, seed=4, lo=-1.0, hi=1.0)
+    want_phi, want_cp, _ = oracle.SignedDistance(x, y, z, conn).compute(q, True, True)
+    sd = SignedDistance(x, y, z, conn)
+    phi, cp, nrm = sd.computeDistances(q, True, True)
+    assert np.array_equal(phi, want_phi) and np.array_equal(cp, want_cp)
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-12)
+    soa = tuple(np.ascontiguousarray(q[:, c]) for c in range(3))
+    phi2, _, _ = sd.computeDistances(soa)
+    assert np.array_equal(phi2, want_phi)
+    monkeypatch.setenv("AXB_SD_PIPE_CHUNK", "0")  # pipeline off: same answer
+    phi3, cp3, nrm3 = sd.computeDistances(q, True, True)
+    assert np.array_equal(phi3, want_phi) and np.array_equal(cp3, cp) and np.array_equal(nrm3, nrm)
