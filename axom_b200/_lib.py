@@ -84,6 +84,13 @@ SYMBOLS = [
     ("axb_meshtester_free", C.c_int, [_P, _P, C.c_int]),
     ("axb_meshtester_get_bvh", C.c_int, [_P, _PP]),
     ("axb_tri_tri_intersect", C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_double, _P]),
+    ("axb_dcp_create", C.c_int, [_PP, C.c_int, C.c_int]),
+    ("axb_dcp_destroy", C.c_int, [_P]),
+    ("axb_dcp_set_object_points", C.c_int, [_P, _P, _P, C.c_int32, C.c_int]),
+    ("axb_dcp_generate_bvh_tree", C.c_int, [_P]),
+    ("axb_dcp_set_squared_distance_threshold", C.c_int, [_P, C.c_double]),
+    ("axb_dcp_get_bvh", C.c_int, [_P, _PP]),
+    ("axb_dcp_compute_local_closest_points", C.c_int, [_P, C.c_int, _P, C.c_int32, C.c_int, _P, _P, _P, _P, _P, C.c_int]),
     # include/axb200_quest.h: the reference's legacy process-global C surface (wrapQUEST.h:83-127) + STL / welding
     ("QUEST_signed_distance_init_serial", C.c_int, [C.c_char_p]),
     ("QUEST_signed_distance_init_serial_bufferify", C.c_int, [C.c_char_p, C.c_int]),

@@ -16,6 +16,7 @@
 #include "sd.cuh"
 #include "sd_fast.cuh"
 #include "meshtester.cuh"
+#include "dcp.cuh"
 #include "traverse.cuh"
 
 namespace axb
@@ -1627,6 +1628,189 @@ int axb_tri_tri_intersect(int device, const double* tris1, const double* tris2, 
   const int st = body();
   ctx.destroy();
   return st;
+}
+
+}  // extern "C"
+
+//==========================================================================================
+// quest::DistributedClosestPoint, per-rank step (quest/detail/DistributedClosestPointImpl.hpp:883-1079)
+//==========================================================================================
+struct axb_dcp
+{
+  axb_bvh* bvh = nullptr;  // owns; built over the object points' zero-size boxes
+  int ndims = 3;
+  int npts = 0;
+  bool tree_built = false;
+  double sq_thresh = DBL_MAX;  // m_sqDistanceThreshold default (:252)
+  DevBuf pts, dom, boxes;
+  DevBuf q_stage, st_idx, st_dom, st_rank, st_coords, st_dist;
+  Ctx& ctx() { return bvh->ctx; }
+};
+
+extern "C" {
+
+int axb_dcp_create(axb_dcp** out, int ndims, int device)
+{
+  if(!out) return fail(AXB_ERR_BAD_ARG, "null output handle");
+  *out = nullptr;
+  if(ndims != 2 && ndims != 3) return fail(AXB_ERR_BAD_ARG, "DistributedClosestPoint is 2-D or 3-D");
+  axb_dcp* h = new axb_dcp();
+  h->ndims = ndims;
+  const int st = axb_bvh_create(&h->bvh, ndims, 8, device);
+  if(st != AXB_OK)
+  {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return AXB_OK;
+}
+
+int axb_dcp_destroy(axb_dcp* h)
+{
+  if(!h) return AXB_OK;
+  if(h->bvh)
+  {
+    cudaSetDevice(h->ctx().device);
+    cudaStream_t st = h->ctx().stream;
+    for(DevBuf* b : {&h->pts, &h->dom, &h->boxes, &h->q_stage, &h->st_idx, &h->st_dom, &h->st_rank, &h->st_coords, &h->st_dist}) b->release(st);
+    axb_bvh_destroy(h->bvh);
+  }
+  delete h;
+  return AXB_OK;
+}
+
+// importObjectPoints (:590-649): interleaved coordinates of all local domains, one domain id per point
+int axb_dcp_set_object_points(axb_dcp* h, const double* coords, const int32_t* domain_ids, int32_t npts, int memspace)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(npts < 0 || (npts > 0 && (!coords || !domain_ids))) return fail(AXB_ERR_BAD_ARG, "null or negative object point arrays");
+  memspace = resolve_memspace(memspace, coords);
+  if(memspace != AXB_MEM_HOST && memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  Ctx& ctx = h->ctx();
+  AXB_TRY(ctx.bind());
+  const cudaMemcpyKind kind = memspace == AXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  h->npts = npts;
+  h->tree_built = false;
+  AXB_TRY(h->pts.reserve(sizeof(double) * h->ndims * (size_t)std::max(npts, 1), ctx.stream));
+  AXB_TRY(h->dom.reserve(sizeof(int32_t) * (size_t)std::max(npts, 1), ctx.stream));
+  if(npts)
+  {
+    AXB_CUDA_TRY(cudaMemcpyAsync(h->pts.p, coords, sizeof(double) * h->ndims * (size_t)npts, kind, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(h->dom.p, domain_ids, sizeof(int32_t) * (size_t)npts, kind, ctx.stream));
+  }
+  return ctx.sync();
+}
+
+// generateBVHTreeImpl (:883-903)
+int axb_dcp_generate_bvh_tree(axb_dcp* h)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  Ctx& ctx = h->ctx();
+  AXB_TRY(ctx.bind());
+  h->tree_built = true;
+  if(h->npts == 0) return AXB_OK;  // no object points on this rank: queries only get initialised
+  const int n = h->npts, D = h->ndims;
+  AXB_TRY(h->boxes.reserve(sizeof(double) * 2 * D * (size_t)n, ctx.stream));
+  if(D == 3)
+    AXB_LAUNCH(ctx, dcp_point_boxes_kernel<3>, blocks_for(n, 256), 256, h->pts.as<double>(), n, h->boxes.as<Box<double, 3>>());
+  else
+    AXB_LAUNCH(ctx, dcp_point_boxes_kernel<2>, blocks_for(n, 256), 256, h->pts.as<double>(), n, h->boxes.as<Box<double, 2>>());
+  axb_array_desc bd;
+  memset(&bd, 0, sizeof(bd));
+  for(int c = 0; c < 2 * D; ++c) bd.comp[c] = h->boxes.as<char>() + 8 * c;
+  bd.stride_bytes = 16 * D;
+  bd.ncomp = 2 * D;
+  bd.memspace = AXB_MEM_DEVICE;
+  AXB_TRY(axb_bvh_initialize(h->bvh, &bd, n));
+  h->boxes.release(ctx.stream);
+  return AXB_OK;
+}
+
+int axb_dcp_set_squared_distance_threshold(axb_dcp* h, double sq_threshold)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(sq_threshold < 0.0) return fail(AXB_ERR_BAD_ARG, "Squared distance-threshold must be non-negative.");
+  h->sq_thresh = sq_threshold;
+  return AXB_OK;
+}
+
+int axb_dcp_get_bvh(axb_dcp* h, axb_bvh** bvh)
+{
+  if(!h || !bvh) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *bvh = h->bvh;
+  return AXB_OK;
+}
+
+// computeLocalClosestPoints (:905-1079) for one block of query points.  The five state arrays are the xferDom fields
+// cp_index / cp_domain_index / cp_rank / cp_coords (interleaved) / debug/cp_distance (may be NULL); is_first != 0
+// initialises them (-1, signalling NaN) before the search, otherwise they carry what earlier ranks of the ring found.
+int axb_dcp_compute_local_closest_points(axb_dcp* h, int rank, const double* query_coords, int32_t nq, int is_first, int32_t* cp_index,
+                                         int32_t* cp_domain_index, int32_t* cp_rank, double* cp_coords, double* cp_distance, int memspace)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(nq < 0) return fail(AXB_ERR_BAD_ARG, "negative query count");
+  if(nq > 0 && (!query_coords || !cp_index || !cp_domain_index || !cp_rank || !cp_coords)) return fail(AXB_ERR_BAD_ARG, "null query / state array");
+  if(!h->tree_built) return fail(AXB_ERR_NOT_BUILT, "BVH tree must be initialized before calling 'computeClosestPoints");
+  memspace = resolve_memspace(memspace, query_coords);
+  if(memspace != AXB_MEM_HOST && memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  if(nq == 0) return AXB_OK;
+  Ctx& ctx = h->ctx();
+  AXB_TRY(ctx.bind());
+  ctx.begin_call();
+  const int D = h->ndims;
+  const size_t cb = sizeof(double) * D * (size_t)nq, ib = sizeof(int32_t) * (size_t)nq, db = sizeof(double) * (size_t)nq;
+  const double* d_q = query_coords;
+  int32_t *d_idx = cp_index, *d_dom = cp_domain_index, *d_rank = cp_rank;
+  double *d_coords = cp_coords, *d_dist = cp_distance;
+  if(memspace == AXB_MEM_HOST)
+  {
+    AXB_TRY(h->q_stage.reserve(cb, ctx.stream));
+    AXB_TRY(h->st_idx.reserve(ib, ctx.stream));
+    AXB_TRY(h->st_dom.reserve(ib, ctx.stream));
+    AXB_TRY(h->st_rank.reserve(ib, ctx.stream));
+    AXB_TRY(h->st_coords.reserve(cb, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(h->q_stage.p, query_coords, cb, cudaMemcpyHostToDevice, ctx.stream));
+    d_q = h->q_stage.as<double>();
+    d_idx = h->st_idx.as<int32_t>();
+    d_dom = h->st_dom.as<int32_t>();
+    d_rank = h->st_rank.as<int32_t>();
+    d_coords = h->st_coords.as<double>();
+    if(cp_distance)
+    {
+      AXB_TRY(h->st_dist.reserve(db, ctx.stream));
+      d_dist = h->st_dist.as<double>();
+    }
+    if(!is_first)
+    {
+      AXB_CUDA_TRY(cudaMemcpyAsync(d_idx, cp_index, ib, cudaMemcpyHostToDevice, ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(d_dom, cp_domain_index, ib, cudaMemcpyHostToDevice, ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(d_rank, cp_rank, ib, cudaMemcpyHostToDevice, ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(d_coords, cp_coords, cb, cudaMemcpyHostToDevice, ctx.stream));
+      if(cp_distance) AXB_CUDA_TRY(cudaMemcpyAsync(d_dist, cp_distance, db, cudaMemcpyHostToDevice, ctx.stream));
+    }
+  }
+  {
+    ScopedPhase ph(ctx, "dcp.kernel");
+    const bool has = h->npts > 0;
+    if(D == 3)
+      AXB_LAUNCH(ctx, dcp_local_kernel<3>, blocks_for(nq, 128), 128, has ? h->bvh->nodes.as<Node<double, 3>>() : nullptr,
+                 h->bvh->leaf_nodes.as<int32_t>(), h->pts.as<double>(), h->dom.as<int32_t>(), rank, h->sq_thresh, d_q, nq,
+                 (const int32_t*)nullptr, is_first, d_idx, d_dom, d_rank, d_coords, d_dist);
+    else
+      AXB_LAUNCH(ctx, dcp_local_kernel<2>, blocks_for(nq, 128), 128, has ? h->bvh->nodes.as<Node<double, 2>>() : nullptr,
+                 h->bvh->leaf_nodes.as<int32_t>(), h->pts.as<double>(), h->dom.as<int32_t>(), rank, h->sq_thresh, d_q, nq,
+                 (const int32_t*)nullptr, is_first, d_idx, d_dom, d_rank, d_coords, d_dist);
+  }
+  if(memspace == AXB_MEM_HOST)
+  {
+    AXB_CUDA_TRY(cudaMemcpyAsync(cp_index, d_idx, ib, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(cp_domain_index, d_dom, ib, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(cp_rank, d_rank, ib, cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(cp_coords, d_coords, cb, cudaMemcpyDeviceToHost, ctx.stream));
+    if(cp_distance) AXB_CUDA_TRY(cudaMemcpyAsync(cp_distance, d_dist, db, cudaMemcpyDeviceToHost, ctx.stream));
+  }
+  return ctx.finish_call();
 }
 
 }  // extern "C"

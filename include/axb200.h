@@ -94,6 +94,7 @@ typedef struct axb_traverser
 typedef struct axb_bvh axb_bvh;
 typedef struct axb_sd axb_sd;
 typedef struct axb_meshtester axb_meshtester;
+typedef struct axb_dcp axb_dcp;
 
 /* ---- library ------------------------------------------------------------------------ */
 const char* axb_version(void);
@@ -220,6 +221,26 @@ int axb_meshtester_get_bvh(axb_meshtester* mt, axb_bvh** bvh);
  * on n explicit pairs: tris1 / tris2 are AoS double[9] per triangle, out[i] = 0 / 1; all three live in `memspace`. */
 int axb_tri_tri_intersect(int device, const double* tris1, const double* tris2, int64_t n, int memspace, int include_boundary, double eps,
                           uint8_t* out);
+
+/* ---- quest::DistributedClosestPoint, the per-rank step ---------------------------------------------- */
+/* DistributedClosestPointExec<DIM, ExecSpace> (quest/detail/DistributedClosestPointImpl.hpp:551-1095) without its
+ * Conduit / MPI plumbing: the object "mesh" is a point cloud (all local domains flattened, one domain id per point),
+ * the BVH is built over one zero-size box per point (:883-903), and computeLocalClosestPoints (:905-1079) updates
+ * the query block's state arrays -- the xferDom fields cp_index (flattened local point index), cp_domain_index,
+ * cp_rank, cp_coords (interleaved) and cp_distance -- only where this rank improves on what earlier ranks of the
+ * ring left there (strict <: the first point visited wins a tie).  The ring itself (or its NVSwitch replacement:
+ * all ranks search all queries, then MIN-reduce with a ring-order tie-break) is host logic,
+ * axom_b200/distributed_closest_point.py. */
+int axb_dcp_create(axb_dcp** out, int ndims, int device);
+int axb_dcp_destroy(axb_dcp* dcp);
+int axb_dcp_set_object_points(axb_dcp* dcp, const double* coords_interleaved, const int32_t* domain_ids, int32_t num_points,
+                              int memspace);                                              /* importObjectPoints :590-649 */
+int axb_dcp_generate_bvh_tree(axb_dcp* dcp);                                               /* generateBVHTree :651-668    */
+int axb_dcp_set_squared_distance_threshold(axb_dcp* dcp, double sq_threshold);             /* :297-301, default DBL_MAX   */
+int axb_dcp_get_bvh(axb_dcp* dcp, axb_bvh** bvh); /* borrowed; its getBounds() is what gatherBVHRoots exchanges (:671-677) */
+int axb_dcp_compute_local_closest_points(axb_dcp* dcp, int rank, const double* query_coords_interleaved, int32_t num_queries,
+                                         int is_first, int32_t* cp_index, int32_t* cp_domain_index, int32_t* cp_rank,
+                                         double* cp_coords, double* cp_distance /* may be NULL */, int memspace);
 
 #ifdef __cplusplus
 }

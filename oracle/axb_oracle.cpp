@@ -1297,6 +1297,135 @@ int64_t axo_find_tri_mesh_intersections(const double* x, const double* y, const 
 }
 #endif  // !AXO_FLOAT_BUILD
 
+#ifndef AXO_FLOAT_BUILD
+//------------------------------------------------------------------------------
+// quest::DistributedClosestPoint, the per-rank step:
+// DistributedClosestPointImpl<D, ExecSpace>::generateBVHTreeImpl + computeLocalClosestPoints
+// (quest/detail/DistributedClosestPointImpl.hpp:883-1079).  The object "mesh" is a point cloud: every object
+// point is a zero-size box, the query keeps the nearest OBJECT POINT (strict <, so the first one visited wins a
+// tie), and a rank only overwrites an entry when it improves on what earlier ranks of the ring left there.
+//------------------------------------------------------------------------------
+extern "C++" {
+template <int D>
+struct Dcp
+{
+  Bvh<D>* bvh = nullptr;
+  std::vector<double> pts;   // flattened object points of all local domains (:560-640)
+  std::vector<int32_t> dom;  // domain id of every object point
+  ~Dcp() { delete bvh; }
+};
+
+template <int D>
+static void dcp_local(const Dcp<D>& o, int rank, double sq_thresh, const double* q, int nq, int is_first, int32_t* cp_index,
+                      int32_t* cp_dom, int32_t* cp_rank, double* cp_coords, double* cp_dist)
+{
+  const double snan = std::numeric_limits<double>::signaling_NaN();
+  for(int i = 0; i < nq; ++i)
+  {
+    if(is_first)  // :971-979
+    {
+      cp_rank[i] = cp_index[i] = cp_dom[i] = -1;
+      for(int d = 0; d < D; ++d) cp_coords[(size_t)i * D + d] = snan;
+      if(cp_dist) cp_dist[i] = snan;
+    }
+    if(!o.bvh) continue;  // hasObjectPoints == false (:911-916, :990)
+    const double* p = q + (size_t)i * D;
+    double cur_sq = std::numeric_limits<double>::max();  // MinCandidate{} (:231-243)
+    int cur_idx = -1, cur_dom = -1, cur_rank = -1;
+    if(cp_rank[i] >= 0)  // preset with the closest point found so far (:1013-1019)
+    {
+      double s = 0.0;
+      for(int d = 0; d < D; ++d)
+      {
+        const double v = cp_coords[(size_t)i * D + d] - p[d];  // Vector(A, B) = B - A, squared_norm
+        s += v * v;
+      }
+      cur_sq = s;
+      cur_idx = cp_index[i];
+      cur_dom = cp_dom[i];
+      cur_rank = cp_rank[i];
+    }
+    traverse(
+      *o.bvh,
+      [&](const Box<D>& bb) {  // traversePredicate (:1037-1040)
+        const double sq = sqdist_point_box<D>(p, bb);
+        return sq <= cur_sq && sq <= sq_thresh;
+      },
+      [&](int pos) {  // checkMinDist (:1021-1035)
+        const int c = o.bvh->leafs[pos];
+        double s = 0.0;
+        for(int d = 0; d < D; ++d)
+        {
+          const double v = o.pts[(size_t)c * D + d] - p[d];
+          s += v * v;
+        }
+        if(s < cur_sq)
+        {
+          cur_sq = s;
+          cur_idx = c;
+          cur_dom = o.dom[c];
+          cur_rank = rank;
+        }
+      },
+      [](const Box<D>&, const Box<D>&) { return false; });
+    if(cur_rank == rank)  // :1045-1058
+    {
+      cp_index[i] = cur_idx;
+      cp_dom[i] = cur_dom;
+      cp_rank[i] = cur_rank;
+      for(int d = 0; d < D; ++d) cp_coords[(size_t)i * D + d] = o.pts[(size_t)cur_idx * D + d];
+      if(cp_dist) cp_dist[i] = std::sqrt(cur_sq);
+    }
+  }
+}
+}  // extern "C++"
+
+// setObjectMesh (flattened points + domain ids) + generateBVHTree: boxes = BoxType{pt}, default scale factor
+void* axo_dcp_create(int ndims, const double* pts, const int32_t* domain_ids, int npts)
+{
+  if(ndims == 2)
+  {
+    Dcp<2>* o = new Dcp<2>();
+    o->pts.assign(pts, pts + (size_t)npts * 2);
+    o->dom.assign(domain_ids, domain_ids + npts);
+    if(npts > 0)
+    {
+      std::vector<double> boxes((size_t)npts * 4);
+      for(int i = 0; i < npts; ++i)
+        for(int d = 0; d < 2; ++d) boxes[(size_t)i * 4 + d] = boxes[(size_t)i * 4 + 2 + d] = pts[(size_t)i * 2 + d];
+      o->bvh = create<2>(boxes.data(), npts, -1.0, -1.0);
+    }
+    return o;
+  }
+  Dcp<3>* o = new Dcp<3>();
+  o->pts.assign(pts, pts + (size_t)npts * 3);
+  o->dom.assign(domain_ids, domain_ids + npts);
+  if(npts > 0)
+  {
+    std::vector<double> boxes((size_t)npts * 6);
+    for(int i = 0; i < npts; ++i)
+      for(int d = 0; d < 3; ++d) boxes[(size_t)i * 6 + d] = boxes[(size_t)i * 6 + 3 + d] = pts[(size_t)i * 3 + d];
+    o->bvh = create<3>(boxes.data(), npts, -1.0, -1.0);
+  }
+  return o;
+}
+void axo_dcp_destroy(void* h, int ndims)
+{
+  if(ndims == 2)
+    delete(Dcp<2>*)h;
+  else
+    delete(Dcp<3>*)h;
+}
+void axo_dcp_compute_local(void* h, int ndims, int rank, double sq_thresh, const double* q, int nq, int is_first, int32_t* cp_index,
+                           int32_t* cp_dom, int32_t* cp_rank, double* cp_coords, double* cp_dist)
+{
+  if(ndims == 2)
+    dcp_local<2>(*(Dcp<2>*)h, rank, sq_thresh, q, nq, is_first, cp_index, cp_dom, cp_rank, cp_coords, cp_dist);
+  else
+    dcp_local<3>(*(Dcp<3>*)h, rank, sq_thresh, q, nq, is_first, cp_index, cp_dom, cp_rank, cp_coords, cp_dist);
+}
+#endif  // !AXO_FLOAT_BUILD
+
 int AXO_FN(max_threads)()
 {
 #ifdef _OPENMP

@@ -72,6 +72,11 @@ class _Lib:
             f("sd_create_mixed").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
             f("sd_destroy").argtypes = [C.c_void_p]
             f("sd_compute").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            f("dcp_create").restype = C.c_void_p
+            f("dcp_create").argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+            f("dcp_destroy").argtypes = [C.c_void_p, C.c_int]
+            f("dcp_compute_local").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
             f("tri_tri_intersect").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
             f("find_tri_mesh_intersections").restype = C.c_int64
             f("find_tri_mesh_intersections").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
@@ -199,6 +204,40 @@ class SignedDistance:
         nr = np.empty((n, 3), np.float64) if want_normals else None
         self.L.fn("sd_compute")(self.h, _ptr(q), n, _ptr(phi), _ptr(cp), _ptr(nr), int(nthreads))
         return phi, cp, nr
+
+
+class DistributedClosestPointRank:
+    """one rank of quest::DistributedClosestPoint: flattened object points + domain ids, BVH over BoxType{pt}
+    (generateBVHTreeImpl), and computeLocalClosestPoints on caller-held state arrays."""
+
+    def __init__(self, points, domain_ids=None, ndims=3, kind="port"):
+        self.L = lib(kind)
+        self.ndims = ndims
+        self.pts = np.ascontiguousarray(points, np.float64).reshape(-1, ndims)
+        n = self.pts.shape[0]
+        self.dom = np.zeros(n, np.int32) if domain_ids is None else np.ascontiguousarray(domain_ids, np.int32)
+        self.h = self.L.fn("dcp_create")(ndims, _ptr(self.pts), _ptr(self.dom), n)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.fn("dcp_destroy")(self.h, self.ndims)
+                self.h = None
+        except Exception:
+            pass
+
+    def compute_local(self, rank, query, state=None, sq_threshold=np.finfo(np.float64).max):
+        """state = dict(cp_index, cp_domain_index, cp_rank, cp_coords, cp_distance) updated in place; None = is_first"""
+        q = np.ascontiguousarray(query, np.float64).reshape(-1, self.ndims)
+        n = q.shape[0]
+        first = state is None
+        if first:
+            state = {"cp_index": np.empty(n, np.int32), "cp_domain_index": np.empty(n, np.int32), "cp_rank": np.empty(n, np.int32),
+                     "cp_coords": np.empty((n, self.ndims), np.float64), "cp_distance": np.empty(n, np.float64)}
+        self.L.fn("dcp_compute_local")(self.h, self.ndims, int(rank), float(sq_threshold), _ptr(q), n, int(first), _ptr(state["cp_index"]),
+                                       _ptr(state["cp_domain_index"]), _ptr(state["cp_rank"]), _ptr(state["cp_coords"]),
+                                       _ptr(state["cp_distance"]))
+        return state
 
 
 def tri_tri_intersect(tris1, tris2, include_boundary=False, eps=1e-8, kind="port"):

@@ -26,6 +26,9 @@
 #include "axom/quest/MeshTester.hpp"
 #include "axom/quest/readers/STLReader.hpp"
 #include "axom/quest/interface/signed_distance.hpp"
+#include "axom/primal/operators/squared_distance.hpp"
+#include <limits>
+#include <memory>
 
 #include <cstdint>
 #include <cstdlib>
@@ -522,6 +525,125 @@ int axref_stl_read_weld(const char* stl_file, double eps, double** x, double** y
   *num_cells = nc;
   delete mesh;
   return 0;
+}
+
+// quest::DistributedClosestPoint needs Conduit + MPI, which are not in this image, so the class itself cannot be
+// built.  Its per-rank step is a traversal of the real spin::BVH with two small lambdas; this entry point drives the
+// REAL BVH / traverse_tree / primal::squared_distance with those lambdas restated from
+// quest/detail/DistributedClosestPointImpl.hpp:883-903 (boxes = BoxType{pt}) and :1008-1060 (preset, checkMinDist,
+// traversePredicate, write-back).  It pins the oracle's traversal order, pruning and tie-breaking.
+extern "C++" {
+template <int D>
+struct RefDcp
+{
+  using PointType = axom::primal::Point<double, D>;
+  using BoxType = axom::primal::BoundingBox<double, D>;
+  axom::Array<PointType> pts;
+  axom::Array<axom::IndexType> dom;
+  std::unique_ptr<axom::spin::BVH<D, SEQ_EXEC, double>> bvh;
+};
+
+template <int D>
+static void* ref_dcp_create(const double* p, const int32_t* dom, int n)
+{
+  using R = RefDcp<D>;
+  R* r = new R();
+  r->pts.resize(n);
+  r->dom.resize(n);
+  axom::Array<typename R::BoxType> boxes(n, n);
+  for(int i = 0; i < n; ++i)
+  {
+    r->pts[i] = typename R::PointType(p + (size_t)i * D);
+    r->dom[i] = dom[i];
+    boxes[i] = typename R::BoxType {r->pts[i]};
+  }
+  if(n > 0)
+  {
+    r->bvh.reset(new axom::spin::BVH<D, SEQ_EXEC, double>());
+    r->bvh->initialize(boxes.view(), n);
+  }
+  return r;
+}
+
+template <int D>
+static void ref_dcp_local(const RefDcp<D>& o, int rank, double sqThresh, const double* q, int nq, int is_first, int32_t* cp_index,
+                          int32_t* cp_dom, int32_t* cp_rank, double* cp_coords, double* cp_dist)
+{
+  using PointType = typename RefDcp<D>::PointType;
+  using BoxType = typename RefDcp<D>::BoxType;
+  using axom::primal::squared_distance;
+  const double snan = std::numeric_limits<double>::signaling_NaN();
+  for(int i = 0; i < nq; ++i)
+  {
+    if(is_first)
+    {
+      cp_rank[i] = cp_index[i] = cp_dom[i] = -1;
+      for(int d = 0; d < D; ++d) cp_coords[(size_t)i * D + d] = snan;
+      if(cp_dist) cp_dist[i] = snan;
+    }
+  }
+  if(!o.bvh) return;
+  auto it = o.bvh->getTraverser();
+  for(int idx = 0; idx < nq; ++idx)
+  {
+    const PointType qpt(q + (size_t)idx * D);
+    double sqDist = axom::numerics::floating_point_limits<double>::max();
+    int pointIdx = -1, domainIdx = -1, minRank = -1;
+    if(cp_rank[idx] >= 0)
+    {
+      sqDist = squared_distance(qpt, PointType(cp_coords + (size_t)idx * D));
+      pointIdx = cp_index[idx];
+      domainIdx = cp_dom[idx];
+      minRank = cp_rank[idx];
+    }
+    auto checkMinDist = [&](std::int32_t current_node, const std::int32_t* leaf_nodes) {
+      const int c = leaf_nodes[current_node];
+      const double sq = squared_distance(qpt, o.pts[c]);
+      if(sq < sqDist)
+      {
+        sqDist = sq;
+        pointIdx = c;
+        domainIdx = o.dom[c];
+        minRank = rank;
+      }
+    };
+    auto traversePredicate = [&](const PointType& p, const BoxType& bb) -> bool {
+      auto sq = squared_distance(p, bb);
+      return sq <= sqDist && sq <= sqThresh;
+    };
+    it.traverse_tree(qpt, checkMinDist, traversePredicate);
+    if(minRank == rank)
+    {
+      cp_index[idx] = pointIdx;
+      cp_dom[idx] = domainIdx;
+      cp_rank[idx] = minRank;
+      for(int d = 0; d < D; ++d) cp_coords[(size_t)idx * D + d] = o.pts[pointIdx][d];
+      if(cp_dist) cp_dist[idx] = sqrt(sqDist);
+    }
+  }
+}
+
+}  // extern "C++"
+
+void* axref_dcp_create(int ndims, const double* pts, const int32_t* domain_ids, int npts)
+{
+  ensure_slic();
+  return ndims == 2 ? ref_dcp_create<2>(pts, domain_ids, npts) : ref_dcp_create<3>(pts, domain_ids, npts);
+}
+void axref_dcp_destroy(void* h, int ndims)
+{
+  if(ndims == 2)
+    delete(RefDcp<2>*)h;
+  else
+    delete(RefDcp<3>*)h;
+}
+void axref_dcp_compute_local(void* h, int ndims, int rank, double sq_thresh, const double* q, int nq, int is_first, int32_t* cp_index,
+                             int32_t* cp_dom, int32_t* cp_rank, double* cp_coords, double* cp_dist)
+{
+  if(ndims == 2)
+    ref_dcp_local<2>(*(RefDcp<2>*)h, rank, sq_thresh, q, nq, is_first, cp_index, cp_dom, cp_rank, cp_coords, cp_dist);
+  else
+    ref_dcp_local<3>(*(RefDcp<3>*)h, rank, sq_thresh, q, nq, is_first, cp_index, cp_dom, cp_rank, cp_coords, cp_dist);
 }
 
 int axref_max_threads()
