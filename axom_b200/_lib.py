@@ -89,6 +89,7 @@ SYMBOLS = [
     ("axb_dcp_set_object_points", C.c_int, [_P, _P, _P, C.c_int32, C.c_int]),
     ("axb_dcp_generate_bvh_tree", C.c_int, [_P]),
     ("axb_dcp_set_squared_distance_threshold", C.c_int, [_P, C.c_double]),
+    ("axb_dcp_set_mode", C.c_int, [_P, C.c_int]),
     ("axb_dcp_get_bvh", C.c_int, [_P, _PP]),
     ("axb_dcp_compute_local_closest_points", C.c_int, [_P, C.c_int, _P, C.c_int32, C.c_int, _P, _P, _P, _P, _P, C.c_int]),
     # include/axb200_quest.h: the reference's legacy process-global C surface (wrapQUEST.h:83-127) + STL / welding

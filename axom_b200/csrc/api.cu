@@ -1643,11 +1643,20 @@ struct axb_dcp
   bool tree_built = false;
   double sq_thresh = DBL_MAX;  // m_sqDistanceThreshold default (:252)
   DevBuf pts, dom, boxes;
-  DevBuf q_stage, st_idx, st_dom, st_rank, st_coords, st_dist;
+  DevBuf q_stage, st_idx, st_dom, st_rank, st_coords, st_dist, keys_a, keys_b, scratch, perm;
+  int mode = 1;  // 1 = nearest-first search with explicit tie-break (default), 0 = the reference's traversal order
   Ctx& ctx() { return bvh->ctx; }
 };
 
 extern "C" {
+
+int axb_dcp_set_mode(axb_dcp* h, int mode)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(mode != 0 && mode != 1) return fail(AXB_ERR_BAD_ARG, "mode must be 0 or 1");
+  h->mode = mode;
+  return AXB_OK;
+}
 
 int axb_dcp_create(axb_dcp** out, int ndims, int device)
 {
@@ -1673,7 +1682,9 @@ int axb_dcp_destroy(axb_dcp* h)
   {
     cudaSetDevice(h->ctx().device);
     cudaStream_t st = h->ctx().stream;
-    for(DevBuf* b : {&h->pts, &h->dom, &h->boxes, &h->q_stage, &h->st_idx, &h->st_dom, &h->st_rank, &h->st_coords, &h->st_dist}) b->release(st);
+    for(DevBuf* b : {&h->pts, &h->dom, &h->boxes, &h->q_stage, &h->st_idx, &h->st_dom, &h->st_rank, &h->st_coords, &h->st_dist, &h->keys_a,
+                     &h->keys_b, &h->scratch, &h->perm})
+      b->release(st);
     axb_bvh_destroy(h->bvh);
   }
   delete h;
@@ -1790,17 +1801,55 @@ int axb_dcp_compute_local_closest_points(axb_dcp* h, int rank, const double* que
       if(cp_distance) AXB_CUDA_TRY(cudaMemcpyAsync(d_dist, cp_distance, db, cudaMemcpyHostToDevice, ctx.stream));
     }
   }
+  const bool has = h->npts > 0;
+  const int32_t* perm = nullptr;
+  if(h->mode == 1 && has && nq >= 4096)
+  {
+    // Morton order of the queries (processing order only): neighbouring threads walk the same nodes
+    ScopedPhase ph(ctx, "dcp.sortq");
+    const size_t kb = sizeof(unsigned long long) * (size_t)nq;
+    AXB_TRY(h->keys_a.reserve(kb, ctx.stream));
+    AXB_TRY(h->keys_b.reserve(kb, ctx.stream));
+    AXB_TRY(h->perm.reserve(sizeof(int32_t) * (size_t)nq, ctx.stream));
+    const size_t scratch = rsort::scratch_bytes(nq);
+    AXB_TRY(h->scratch.reserve(scratch, ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(h->scratch.p, 0, scratch, ctx.stream));
+    uint32_t* ghist = h->scratch.as<uint32_t>();
+    uint32_t* tile_counters = ghist + rsort::MAX_PASSES * rsort::RADIX;
+    uint32_t* lookback = tile_counters + 64;
+    if(D == 3)
+      AXB_LAUNCH(ctx, (dcp_query_keys_kernel<3, BuildState<double, 3>>), capped_grid(nq, 256), 256, d_q, nq,
+                 h->bvh->state.as<BuildState<double, 3>>(), h->keys_a.as<unsigned long long>(), ghist);
+    else
+      AXB_LAUNCH(ctx, (dcp_query_keys_kernel<2, BuildState<double, 2>>), capped_grid(nq, 256), 256, d_q, nq,
+                 h->bvh->state.as<BuildState<double, 2>>(), h->keys_a.as<unsigned long long>(), ghist);
+    unsigned long long* sorted = nullptr;
+    AXB_TRY(sort_keys_generic(ctx, h->keys_a.as<unsigned long long>(), h->keys_b.as<unsigned long long>(), nq, ghist, tile_counters, lookback,
+                              &sorted));
+    AXB_LAUNCH(ctx, keys_to_perm_kernel, blocks_for(nq, 256), 256, sorted, nq, h->perm.as<int32_t>());
+    perm = h->perm.as<int32_t>();
+  }
   {
     ScopedPhase ph(ctx, "dcp.kernel");
-    const bool has = h->npts > 0;
-    if(D == 3)
-      AXB_LAUNCH(ctx, dcp_local_kernel<3>, blocks_for(nq, 128), 128, has ? h->bvh->nodes.as<Node<double, 3>>() : nullptr,
-                 h->bvh->leaf_nodes.as<int32_t>(), h->pts.as<double>(), h->dom.as<int32_t>(), rank, h->sq_thresh, d_q, nq,
-                 (const int32_t*)nullptr, is_first, d_idx, d_dom, d_rank, d_coords, d_dist);
+#define AXB_DCP_LAUNCH(KERNEL, DD)                                                                                                 \
+  AXB_LAUNCH(ctx, KERNEL<DD>, blocks_for(nq, 128), 128, has ? h->bvh->nodes.as<Node<double, DD>>() : nullptr,                      \
+             h->bvh->leaf_nodes.as<int32_t>(), h->pts.as<double>(), h->dom.as<int32_t>(), rank, h->sq_thresh, d_q, nq, perm, is_first, \
+             d_idx, d_dom, d_rank, d_coords, d_dist)
+    if(h->mode == 1)
+    {
+      if(D == 3)
+        AXB_DCP_LAUNCH(dcp_nearest_kernel, 3);
+      else
+        AXB_DCP_LAUNCH(dcp_nearest_kernel, 2);
+    }
     else
-      AXB_LAUNCH(ctx, dcp_local_kernel<2>, blocks_for(nq, 128), 128, has ? h->bvh->nodes.as<Node<double, 2>>() : nullptr,
-                 h->bvh->leaf_nodes.as<int32_t>(), h->pts.as<double>(), h->dom.as<int32_t>(), rank, h->sq_thresh, d_q, nq,
-                 (const int32_t*)nullptr, is_first, d_idx, d_dom, d_rank, d_coords, d_dist);
+    {
+      if(D == 3)
+        AXB_DCP_LAUNCH(dcp_local_kernel, 3);
+      else
+        AXB_DCP_LAUNCH(dcp_local_kernel, 2);
+    }
+#undef AXB_DCP_LAUNCH
   }
   if(memspace == AXB_MEM_HOST)
   {

@@ -11,6 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "traverse.cuh"
+#include "build.cuh"
 
 namespace axb
 {
@@ -121,5 +122,164 @@ __global__ void __launch_bounds__(128) dcp_local_kernel(const Node<double, D>* _
     for(int d = 0; d < D; ++d) cp_coords[(size_t)i * D + d] = __ldg(obj_pts + (size_t)cur_idx * D + d);
     if(cp_dist) cp_dist[i] = sqrt(cur_sq);
   }
+}
+
+// MODE 1 (default): the same answer from a nearest-first search.
+//
+// The reference walks its tree left child first with no initial bound (traverse_tree's default comparator), so a
+// query first descends to leaves that may be arbitrarily far away and only then starts pruning: thousands of node
+// visits per query on a 2 M-point cloud.  Its RESULT, however, has an order-free description: left-first DFS over a
+// tree built on the sorted leaves visits leaves in increasing sorted position, and a leaf replaces the running minimum
+// only on a strict <, so the reference reports the nearest object point and, among exactly equidistant ones, the one
+// with the smallest sorted position (a preset from an earlier rank wins every tie).  This kernel searches in
+// best-first order -- nearer child first, the other on a (lower bound, node) stack, subtrees pruned when their bound
+// exceeds the running minimum -- and breaks ties by sorted position explicitly.  Bounds equal to the running minimum
+// are still entered (<=), as in the reference's predicate, so that an equidistant point with a smaller position is found.
+// The arithmetic of every distance is the reference's; the answer is bit-identical (tests run both modes).
+template <int D>
+__global__ void __launch_bounds__(128) dcp_nearest_kernel(const Node<double, D>* __restrict__ nodes, const int32_t* __restrict__ leaf_nodes,
+                                                           const double* __restrict__ obj_pts, const int32_t* __restrict__ obj_dom, int rank,
+                                                           double sq_thresh, const double* __restrict__ query, int nq,
+                                                           const int32_t* __restrict__ perm, int is_first, int32_t* __restrict__ cp_index,
+                                                           int32_t* __restrict__ cp_dom, int32_t* __restrict__ cp_rank,
+                                                           double* __restrict__ cp_coords, double* __restrict__ cp_dist)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= nq) return;
+  const int i = perm ? perm[t] : t;
+  double p[D];
+#pragma unroll
+  for(int d = 0; d < D; ++d) p[d] = query[(size_t)i * D + d];
+  double cur_sq = DBL_MAX;
+  int cur_pos = 0x7fffffff;  // sorted position of the running minimum; -1 = a preset, which wins every tie
+  int cur_idx = -1;
+  bool improved = false;
+  if(is_first)
+  {
+    const double snan = __longlong_as_double(0x7ff4000000000000ll);
+    cp_rank[i] = -1;
+    cp_index[i] = -1;
+    cp_dom[i] = -1;
+#pragma unroll
+    for(int d = 0; d < D; ++d) cp_coords[(size_t)i * D + d] = snan;
+    if(cp_dist) cp_dist[i] = snan;
+  }
+  else if(cp_rank[i] >= 0)
+  {
+    double s = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d)
+    {
+      const double v = cp_coords[(size_t)i * D + d] - p[d];
+      s += v * v;
+    }
+    cur_sq = s;
+    cur_pos = -1;
+  }
+  if(nodes == nullptr) return;
+
+  auto leaf = [&](int pos) {
+    const int c = __ldg(leaf_nodes + pos);
+    double s = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d)
+    {
+      const double v = __ldg(obj_pts + (size_t)c * D + d) - p[d];
+      s += v * v;
+    }
+    // reached in the reference only if the leaf's own (zero-size) box passes the predicate: s <= threshold
+    if(s <= sq_thresh && (s < cur_sq || (s == cur_sq && pos < cur_pos)))
+    {
+      cur_sq = s;
+      cur_pos = pos;
+      cur_idx = c;
+      improved = true;
+    }
+  };
+
+  double st_lb[kStackSize];
+  int32_t st_id[kStackSize];
+  int sp = 0;
+  int32_t cur = 0;  // root
+  while(true)
+  {
+    const Node<double, D>& nd = nodes[cur];
+    const Box<double, D> L = nd.box[0], R = nd.box[1];
+    const int32_t lc = nd.child[0], rc = nd.child[1];
+    double dl = box_valid(L) ? dcp_sqdist_box<D>(p, L) : DBL_MAX;
+    double dr = box_valid(R) ? dcp_sqdist_box<D>(p, R) : DBL_MAX;
+    bool inl = box_valid(L) && dl <= cur_sq && dl <= sq_thresh;
+    bool inr = box_valid(R) && dr <= cur_sq && dr <= sq_thresh;
+    // leaves are evaluated on the spot (a leaf's bound IS its distance), nearer one first
+    if(inl && lc < 0 && (!(inr && rc < 0) || dl <= dr))
+    {
+      leaf(-lc - 1);
+      inl = false;
+      inr = inr && dr <= cur_sq;
+    }
+    if(inr && rc < 0)
+    {
+      leaf(-rc - 1);
+      inr = false;
+      inl = inl && dl <= cur_sq;
+    }
+    if(inl && lc < 0)
+    {
+      leaf(-lc - 1);
+      inl = false;
+    }
+    int32_t next = kBarrier;
+    if(inl && inr)
+    {
+      const bool left_first = dl <= dr;
+      st_lb[sp] = left_first ? dr : dl;
+      st_id[sp] = left_first ? rc : lc;
+      ++sp;
+      next = left_first ? lc : rc;
+    }
+    else if(inl)
+      next = lc;
+    else if(inr)
+      next = rc;
+    while(next == kBarrier && sp > 0)
+    {
+      --sp;
+      if(st_lb[sp] <= cur_sq) next = st_id[sp];
+    }
+    if(next == kBarrier) break;
+    cur = next;
+  }
+  if(improved)
+  {
+    cp_index[i] = cur_idx;
+    cp_dom[i] = __ldg(obj_dom + cur_idx);
+    cp_rank[i] = rank;
+#pragma unroll
+    for(int d = 0; d < D; ++d) cp_coords[(size_t)i * D + d] = __ldg(obj_pts + (size_t)cur_idx * D + d);
+    if(cp_dist) cp_dist[i] = sqrt(cur_sq);
+  }
+}
+
+// Morton key of a query point over the object BVH's bounds (processing order only): (code << 32) | index
+template <int D, class State>
+__global__ void __launch_bounds__(256) dcp_query_keys_kernel(const double* __restrict__ query, int nq, const State* __restrict__ st,
+                                                              unsigned long long* __restrict__ keys, uint32_t* __restrict__ ghist)
+{
+  __shared__ uint32_t sh[rsort::MAX_PASSES * rsort::RADIX];
+  for(int i = threadIdx.x; i < rsort::MAX_PASSES * rsort::RADIX; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x)
+  {
+    double c[D];
+#pragma unroll
+    for(int d = 0; d < D; ++d) c[d] = (query[(size_t)i * D + d] - st->bmin[d]) * st->inv_extent[d];
+    const uint32_t code = morton32<double, D>(c);
+    keys[i] = ((unsigned long long)code << 32) | (unsigned long long)(uint32_t)i;
+#pragma unroll
+    for(int p = 0; p < rsort::MAX_PASSES; ++p) atomicAdd(&sh[p * rsort::RADIX + ((code >> (p * 8)) & 255u)], 1u);
+  }
+  __syncthreads();
+  for(int i = threadIdx.x; i < rsort::MAX_PASSES * rsort::RADIX; i += blockDim.x)
+    if(sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 }  // namespace axb

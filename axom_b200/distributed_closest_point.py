@@ -62,6 +62,9 @@ class _GpuBackend:
     def set_sq_threshold(self, t):
         check(self._L.axb_dcp_set_squared_distance_threshold(self._h, float(t)))
 
+    def set_mode(self, mode):
+        check(self._L.axb_dcp_set_mode(self._h, int(mode)))
+
     def tensor_device(self):
         import torch
         return torch.device("cuda", self.device)
@@ -78,6 +81,9 @@ class _GpuBackend:
     def compute_local(self, rank, q, state=None):
         """q: (n, D) float64 CUDA tensor.  state None = is_first.  Returns the state dict (updated in place)."""
         import torch
+        # the library works on its own stream: whatever torch still has in flight for q (a gather, a slice copy)
+        # must be complete before the kernel reads it
+        torch.cuda.current_stream(q.device).synchronize()
         n = q.shape[0]
         first = state is None
         if first:

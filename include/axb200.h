@@ -237,6 +237,9 @@ int axb_dcp_set_object_points(axb_dcp* dcp, const double* coords_interleaved, co
                               int memspace);                                              /* importObjectPoints :590-649 */
 int axb_dcp_generate_bvh_tree(axb_dcp* dcp);                                               /* generateBVHTree :651-668    */
 int axb_dcp_set_squared_distance_threshold(axb_dcp* dcp, double sq_threshold);             /* :297-301, default DBL_MAX   */
+/* search strategy: 1 (default) nearest-first with an explicit sorted-position tie-break, 0 the reference's left-first
+ * traversal (thousands of node visits per query on large clouds); results are bit-identical */
+int axb_dcp_set_mode(axb_dcp* dcp, int mode);
 int axb_dcp_get_bvh(axb_dcp* dcp, axb_bvh** bvh); /* borrowed; its getBounds() is what gatherBVHRoots exchanges (:671-677) */
 int axb_dcp_compute_local_closest_points(axb_dcp* dcp, int rank, const double* query_coords_interleaved, int32_t num_queries,
                                          int is_first, int32_t* cp_index, int32_t* cp_domain_index, int32_t* cp_rank,

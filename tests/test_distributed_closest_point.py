@@ -157,8 +157,9 @@ def test_api_argument_checks():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 0])
 @pytest.mark.parametrize("nd", [3, 2])
-def test_gpu_ring_of_handles_matches_oracle(oracle, nd):
+def test_gpu_ring_of_handles_matches_oracle(oracle, nd, mode):
     """four axb_dcp handles on one GPU play the four ranks; the state arrays go round the ring through the C ABI
     (is_first on the owner, then in-place updates), host memspace and device memspace"""
     import ctypes as C
@@ -167,6 +168,7 @@ def test_gpu_ring_of_handles_matches_oracle(oracle, nd):
     from axom_b200._lib import MEM_DEVICE, MEM_HOST, check
     L = _lib.lib()
     parts, q = _cloud_parts(nd)
+    q = np.ascontiguousarray(np.concatenate([q, q[:3000] * 0.5 + 0.25]))  # > 4096 queries: the Morton-sorted path
     doms = [np.where(np.arange(len(p)) < len(p) // 2, 10 * i, 10 * i + 1).astype(np.int32) for i, p in enumerate(parts)]
     oranks = [oracle.DistributedClosestPointRank(p, d, nd) for p, d in zip(parts, doms)]
     handles = []
@@ -176,6 +178,7 @@ def test_gpu_ring_of_handles_matches_oracle(oracle, nd):
         pc = np.ascontiguousarray(p)
         check(L.axb_dcp_set_object_points(h, pc.ctypes.data, d.ctypes.data, len(p), MEM_HOST))
         check(L.axb_dcp_generate_bvh_tree(h))
+        check(L.axb_dcp_set_mode(h, mode))
         handles.append(h)
     try:
         for th in (_DBL_MAX, 0.05 ** 2):
