@@ -118,7 +118,16 @@ class BVH:
         return v.value
 
     def setStream(self, cuda_stream_ptr):
+        """run on the caller's stream (e.g. torch's current stream): the caller then owns the ordering"""
         check(self._L.axb_bvh_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+        self._own_stream = False
+
+    def _wait_for_torch(self, k):
+        """device inputs produced by torch may still be in flight on torch's stream; the handle works on its own
+        stream unless setStream() was called, so wait for them first"""
+        if k.device and getattr(self, "_own_stream", True):
+            import torch
+            torch.cuda.current_stream(self.device).synchronize()
 
     def setAsync(self, enabled):
         check(self._L.axb_bvh_set_async(self._h, int(bool(enabled))))
@@ -158,6 +167,7 @@ class BVH:
         n = k.count if numItems is None else int(numItems)
         if n > k.count:
             raise ValueError("numItems exceeds the supplied boxes")
+        self._wait_for_torch(k)
         st = self._L.axb_bvh_initialize(self._h, C.byref(k.desc), n)
         if st < 0:
             check(st)
@@ -179,6 +189,7 @@ class BVH:
 
     # ---- queries (spin/BVH.hpp:341-398) ----
     def _find(self, which, k, nq, extra=()):
+        self._wait_for_torch(k)
         import_torch = k.device
         total = C.c_int64()
         cand = C.c_void_p()

@@ -22,8 +22,10 @@ class MeshTester:
         self.device = device
         self._h = None
         if _is_torch(x):
+            import torch
             xs = [a.contiguous() for a in (x, y, z)]
             conn = cells_to_nodes.contiguous().reshape(-1)
+            torch.cuda.current_stream(xs[0].device).synchronize()  # the library works on its own stream
             px, py, pz, pc = (a.data_ptr() for a in (*xs, conn))
             nn, nc, space = xs[0].numel(), conn.numel() // 3, MEM_DEVICE
         else:

@@ -22,8 +22,10 @@ class SignedDistance:
         self._h = None
         po = None
         if _is_torch(x):
+            import torch
             xs = [a.contiguous() for a in (x, y, z)]
             conn = cells_to_nodes.contiguous().reshape(-1)
+            torch.cuda.current_stream(xs[0].device).synchronize()  # the library works on its own stream
             px, py, pz, pc = (a.data_ptr() for a in (*xs, conn))
             nn, nc, space = xs[0].numel(), conn.numel() // nodes_per_cell, MEM_DEVICE
             if cell_node_offsets is not None:
@@ -65,6 +67,7 @@ class SignedDistance:
 
     def setStream(self, ptr):
         check(self._L.axb_sd_set_stream(self._h, C.c_void_p(ptr)))
+        self._own_stream = False
 
     def setAsync(self, e):
         check(self._L.axb_sd_set_async(self._h, int(bool(e))))
@@ -98,6 +101,8 @@ class SignedDistance:
         n = k.count
         if k.device:
             import torch
+            if getattr(self, "_own_stream", True):
+                torch.cuda.current_stream(self.device).synchronize()  # inputs torch may still be producing
             dev = torch.device("cuda", self.device)
             phi = out if out is not None else torch.empty(n, dtype=torch.float64, device=dev)
             cp = torch.empty((n, 3), dtype=torch.float64, device=dev) if outClosestPts else None
