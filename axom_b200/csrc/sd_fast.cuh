@@ -458,9 +458,18 @@ __device__ __forceinline__ void check_leaf_lazy(const double* __restrict__ soup,
 #endif
 constexpr int kSmemStack = 32;   // stack levels kept in shared memory (the rest, rarely reached, in local memory)
 constexpr size_t kSdFastSmem = (size_t)kSmemStack * 128 * sizeof(unsigned long long);  // 128 threads per block
-constexpr int kPend = 4;         // queued leaves per lane
-constexpr int kLeafVote = 16;    // lanes with a queued leaf that trigger a leaf step
-constexpr int kFinishVote = 4;   // finished lanes that trigger a finalisation step
+#ifndef AXB_SD_PEND
+  #define AXB_SD_PEND 4
+#endif
+#ifndef AXB_SD_LEAF_VOTE
+  #define AXB_SD_LEAF_VOTE 16
+#endif
+#ifndef AXB_SD_FINISH_VOTE
+  #define AXB_SD_FINISH_VOTE 4
+#endif
+constexpr int kPend = AXB_SD_PEND;                // queued leaves per lane
+constexpr int kLeafVote = AXB_SD_LEAF_VOTE;       // lanes with a queued leaf that trigger a leaf step
+constexpr int kFinishVote = AXB_SD_FINISH_VOTE;   // finished lanes that trigger a finalisation step
 constexpr int kQueryChunk = 128;  // queries a warp takes from the cursor at a time (a run of Morton neighbours)
 
 template <int NV>
