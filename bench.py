@@ -3,10 +3,11 @@
 
 Workload (BASELINE.json configs[1], "C2"): quest::SignedDistance on a synthetic 2M-triangle
 icosphere (geodesic frequency 316 -> 1 997 120 triangles, radius 0.5, watertight, signs on)
-evaluated on the 256^3 uniform grid spanning [-1,1]^3.  With N GPUs the grid is sharded by
-z-planes dealt round-robin (plane k goes to rank k mod N: planes near the sphere's centre cost more
-than the outer ones, so contiguous slabs would leave the outer ranks idle); one process per GPU,
-surface BVH replicated and built per GPU, no data-path collective; total work is fixed, so scaling
+evaluated on the 256^3 uniform grid spanning [-1,1]^3.  With N GPUs the grid is sharded into
+contiguous z-slabs (rank r takes planes [256 r / N, 256 (r+1) / N)); --sharding planes
+deals the planes round-robin instead.  Measured on one GPU (tools/sd_shard_probe.py) a 1/8 shard costs
+15.9-17.1 ms as a slab and 16.9-19.4 ms as every 8th plane, so slabs are the default.  One process per
+GPU, surface BVH replicated and built per GPU, no data-path collective; total work is fixed, so scaling
 is "strong".
 
 A "step" is one computeDistances() pass over the rank's shard.
@@ -212,7 +213,10 @@ def run_ours(args):
 
     # ---- this rank's z-slab of the 256^3 grid, generated on the device ----
     ax = torch.from_numpy(grid_axis()).to(dev)
-    planes = torch.arange(rank, GRID, world, device=dev)  # z-planes dealt round-robin
+    if args.sharding == "planes":
+        planes = torch.arange(rank, GRID, world, device=dev)  # z-planes dealt round-robin
+    else:
+        planes = torch.arange((GRID * rank) // world, (GRID * (rank + 1)) // world, device=dev)  # contiguous z-slab
     zz, yy, xx = torch.meshgrid(ax[planes], ax, ax, indexing="ij")
     q_d = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=1).contiguous()
     del zz, yy, xx
@@ -282,7 +286,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": None, "kernel": "signed-distance query kernel", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "latency/FP64-pipe bound traversal: see fp64 for the arithmetic side"}
+                "note": "not HBM-bound: a latency-bound tree traversal (see l1 / fp64); HBM frac is reported because the contract asks for it"}
     prof = ncu_profile_summary()
     if prof:
         roofline["traffic"] = prof.get("dram_bytes_per_launch")
@@ -292,12 +296,14 @@ def run_ours(args):
             "gflops_survey_convention": flops / (kernel_ms * 1e-3) / 1e9,
             "frac_of_nominal_fp64_peak": flops / (kernel_ms * 1e-3) / 37.2e12,
             "nominal_fp64_peak": "37.2 TFLOP/s = 148 SMs x 64 DFMA/clk x 1.965 GHz (not in MEASURED_PEAKS.json)"}
-    # what actually bounds the kernel (ncu): L1 sector throughput of divergent node-record reads --
-    # every lane reads its own 256-byte record, 8 sectors per visit, 1 sector/clk/SM
-    sectors = nq_local * (8.0 * inner_visits / nq_local + 3.0 * leaf_tests / nq_local)
+    # the L1 side (ncu, profiles/r1i): every lane reads its own 128-byte node record (4 sectors per visit) and 96-byte
+    # leaf record (3 sectors per test); nothing coalesces, so sectors ~ L1 wavefronts, 1 per clock per SM at best
+    sectors = 4.0 * inner_visits + 3.0 * leaf_tests
     l1 = {"sector_requests_per_launch": sectors, "achieved_gsectors_per_s": sectors / (kernel_ms * 1e-3) / 1e9,
           "peak_gsectors_per_s": 148 * 1.965, "frac": sectors / (kernel_ms * 1e-3) / 1e9 / (148 * 1.965),
-          "note": "1 x 32-B sector per clock per SM for uncoalesced loads (measured: l1tex throughput 83 % in profiles/r1c)"}
+          "note": "modelled from the work counters; ncu (profiles/r1i_sd_fast_kernel_ncu_full.txt): l1tex LSU wavefronts 57 % of peak, "
+                  "issue slots 49 %, FP64 pipe 27 %, 13.5 of 32 lanes active -- the kernel is bound by the dependent latency of "
+                  "its traversal steps (2.3 us per step for a lone warp), not by one saturated unit"}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample, checked against the GPU result ----
     cpu = None
@@ -314,7 +320,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "queries_total": nq_total, "queries_per_gpu": nq_local, "sharding": "z-planes round-robin over ranks, BVH replicated per GPU",
+        "config": {"workload": WORKLOAD, "queries_total": nq_total, "queries_per_gpu": nq_local, "sharding": ("z-planes round-robin over ranks" if args.sharding == "planes" else "contiguous z-slabs, one per rank") + ", BVH replicated per GPU",
                    "l2_policy": "inputs larger than L2 (403 MB of queries per pass)", "mode": "fast mode 1: oriented-bound overlay, Morton-ordered queries, persistent warp-scheduled traversal"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq_local * 24, "d2h_bytes_per_step": nq_local * 8,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_path": same},
@@ -339,6 +345,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sharding", default="slabs", choices=["slabs", "planes"], help="how the 256 z-planes are split over ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default="small", choices=["small", "large"])
     args = ap.parse_args()
