@@ -456,7 +456,10 @@ __device__ __forceinline__ void check_leaf_lazy(const double* __restrict__ soup,
 #ifndef AXB_SD_MIN_BLOCKS
   #define AXB_SD_MIN_BLOCKS 4  // resident blocks per SM the register allocation is sized for
 #endif
-constexpr int kSmemStack = 32;   // stack levels kept in shared memory (the rest, rarely reached, in local memory)
+#ifndef AXB_SD_SMEM_STACK
+  #define AXB_SD_SMEM_STACK 32
+#endif
+constexpr int kSmemStack = AXB_SD_SMEM_STACK;   // stack levels kept in shared memory (the rest, rarely reached, in local memory)
 constexpr size_t kSdFastSmem = (size_t)kSmemStack * 128 * sizeof(unsigned long long);  // 128 threads per block
 #ifndef AXB_SD_PEND
   #define AXB_SD_PEND 4
