@@ -302,6 +302,9 @@ struct axb_bvh
   unsigned long long* sorted_keys = nullptr;  // points into keys_a or keys_b
   DevBuf ref_inner_nodes, ref_children;       // reference-layout view, built lazily
   bool ref_view_valid = false;
+  DevBuf fnodes;                              // compact 64-byte records for point / box walks (3-D double), built lazily
+  bool fnodes_valid = false;
+  bool find_compact = true;                   // AXB_FIND_COMPACT=0: walk the 128-byte records
   DevBuf q_stage, q_counts, q_offsets, q_tiles, q_total;
   DevBuf f_keys_a, f_keys_b, f_scratch, f_perm, f_pairs, f_unused, f_cursor;
   long long pair_hint[4] = {0, 0, 0, 0};  // candidates found by the last find* call of each kind (sizes the pair buffer)
@@ -311,7 +314,7 @@ struct axb_bvh
   void release_all()
   {
     cudaStream_t s = ctx.stream;
-    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &node_range, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &agglo_slots, &agglo_flags, &ref_inner_nodes,
+    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &node_range, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &agglo_slots, &agglo_flags, &fnodes, &ref_inner_nodes,
                      &ref_children, &q_stage, &q_counts, &q_offsets, &q_tiles, &q_total, &f_keys_a, &f_keys_b, &f_scratch, &f_perm, &f_pairs,
                      &f_unused, &f_cursor})
       b->release(s);
@@ -350,6 +353,7 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
   const int tot = ctx.phase_begin("build.total");
   h->built = false;
   h->ref_view_valid = false;
+  h->fnodes_valid = false;
   h->n_in = num_boxes;
   const int n = num_boxes <= 1 ? 2 : num_boxes;  // spin/BVH.hpp:439-464
   h->n = n;
@@ -593,7 +597,19 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
     pb.max_chunks = max_chunks;
     {
       ScopedPhase ph(ctx, "find.count");  // the one traversal: counts + recorded hits
-      AXB_LAUNCH(ctx, (find_walk_kernel<T, D, Query, Filter>), grid, 128, nodes, leaf_nodes, q, nq, tol, flags, perm, d_counts, pb, filt);
+      // comparison-only predicates on the 3-D double tree walk the compact records (traverse.cuh: FNode)
+      const FNode* fn = nullptr;
+      if(std::is_same<T, double>::value && D == 3 && kind != 2 && h->find_compact)
+      {
+        if(!h->fnodes_valid)
+        {
+          AXB_TRY(h->fnodes.reserve(sizeof(FNode) * (size_t)(h->n - 1), ctx.stream));
+          AXB_LAUNCH(ctx, fnode_kernel, blocks_for(h->n - 1, 256), 256, h->nodes.as<Node<double, 3>>(), h->n - 1, h->fnodes.as<FNode>());
+          h->fnodes_valid = true;
+        }
+        fn = h->fnodes.as<FNode>();
+      }
+      AXB_LAUNCH(ctx, (find_walk_kernel<T, D, Query, Filter>), grid, 128, nodes, leaf_nodes, q, nq, tol, flags, perm, d_counts, pb, filt, fn);
     }
     {
       ScopedPhase ph(ctx, "find.scan");
@@ -704,6 +720,7 @@ int axb_bvh_create(axb_bvh** out, int ndims, int fp_bytes, int device)
   if(fp_bytes == 4) h->tol = FLT_EPSILON;  // DEFAULT_TOLERANCE = floating_point_limits<FloatType>::epsilon()
   if(const char* e = getenv("AXB_BUILD_LEGACY")) h->legacy_build = atoi(e) != 0;
   if(const char* e = getenv("AXB_AGGLO_BLOCK")) h->agglo_block = atoi(e);
+  if(const char* e = getenv("AXB_FIND_COMPACT")) h->find_compact = atoi(e) != 0;
   int s = h->ctx.init(device);
   if(s != AXB_OK)
   {

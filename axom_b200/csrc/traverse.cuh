@@ -320,11 +320,97 @@ __device__ __forceinline__ void load_node_boxes<double, 3>(const Node<double, 3>
   rc = (int32_t)(ids >> 32);
 }
 
+// Compact traversal record for comparison-only predicates (point-in-box, box-box) on the 3-D double tree: both child
+// boxes as binary32 rounded OUTWARD (lo down, hi up) + the child ids = 64 bytes = two 32-byte sectors instead of four.
+// The walk is bound by L1 sector throughput of divergent node reads (a lane reads a record of its own), so bytes per
+// visit are what counts.  An outward-rounded box passes every query the exact box passes (the predicates only compare
+// coordinates), so inner nodes are entered conservatively; a LEAF child that passes is re-tested against its exact
+// double box in the 128-byte record, so the candidates, and their order, are exactly the reference's.  A box that is
+// invalid in double stays invalid unless lo and hi straddle a binary32 rounding gap; then only invalid leaves lie below
+// it and the exact leaf test rejects them.  Rays keep the 128-byte records: the slab test does arithmetic on the box.
+struct alignas(32) FNode
+{
+  float lo0[3], hi0[3], lo1[3], hi1[3];
+  int32_t child[2];
+  int32_t pad_[2];
+};
+static_assert(sizeof(FNode) == 64, "FNode is 2 x 32 B");
+
+__global__ void __launch_bounds__(256) fnode_kernel(const Node<double, 3>* __restrict__ nodes, int inner, FNode* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= inner) return;
+  const Node<double, 3> nd = nodes[i];
+  FNode f;
+#pragma unroll
+  for(int d = 0; d < 3; ++d)
+  {
+    f.lo0[d] = __double2float_rd(nd.box[0].lo[d]);
+    f.hi0[d] = __double2float_ru(nd.box[0].hi[d]);
+    f.lo1[d] = __double2float_rd(nd.box[1].lo[d]);
+    f.hi1[d] = __double2float_ru(nd.box[1].hi[d]);
+  }
+  f.child[0] = nd.child[0];
+  f.child[1] = nd.child[1];
+  f.pad_[0] = f.pad_[1] = 0;
+  out[i] = f;
+}
+
+__device__ __forceinline__ void load_fnode_boxes(const FNode* __restrict__ fnodes, int32_t i, Box<double, 3>& L, Box<double, 3>& R, int32_t& lc,
+                                                 int32_t& rc)
+{
+  const D4* p = reinterpret_cast<const D4*>(fnodes + i);
+  const D4 a = ldg256(p), b = ldg256(p + 1);
+  const double w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float f[16];
+#pragma unroll
+  for(int k = 0; k < 8; ++k)
+  {
+    f[2 * k] = __int_as_float(__double2loint(w[k]));
+    f[2 * k + 1] = __int_as_float(__double2hiint(w[k]));
+  }
+#pragma unroll
+  for(int d = 0; d < 3; ++d)
+  {
+    L.lo[d] = (double)f[d];
+    L.hi[d] = (double)f[3 + d];
+    R.lo[d] = (double)f[6 + d];
+    R.hi[d] = (double)f[9 + d];
+  }
+  lc = __float_as_int(f[12]);
+  rc = __float_as_int(f[13]);
+}
+
+// visit of inner node `cur` through the compact record; leaf children that pass are confirmed on the exact box
+template <class Query>
+__device__ __forceinline__ void compact_visit(const Node<double, 3>* __restrict__ nodes, const FNode* __restrict__ fnodes, int32_t cur,
+                                              const Query& q, int32_t& lc, int32_t& rc, bool& inL, bool& inR)
+{
+  Box<double, 3> L, R;
+  load_fnode_boxes(fnodes, cur, L, R, lc, rc);
+  inL = box_valid(L) ? q(L) : false;
+  inR = box_valid(R) ? q(R) : false;
+  if(inL && lc < 0)
+  {
+    const Box<double, 3> e = nodes[cur].box[0];
+    inL = box_valid(e) ? q(e) : false;
+  }
+  if(inR && rc < 0)
+  {
+    const Box<double, 3> e = nodes[cur].box[1];
+    inR = box_valid(e) ? q(e) : false;
+  }
+}
+template <typename T, int D, class Query>
+__device__ __forceinline__ void compact_visit(const Node<T, D>*, const FNode*, int32_t, const Query&, int32_t&, int32_t&, bool&, bool&)
+{
+}
+
 template <typename T, int D, class Query, class Filter = NoFilter>
 __global__ void __launch_bounds__(128) find_walk_kernel(const Node<T, D>* __restrict__ nodes, const int32_t* __restrict__ leaf_nodes,
                                                          Desc<Query::NCOMP> prims, int nq, T tol, int flags,
                                                          const int32_t* __restrict__ perm, int32_t* __restrict__ counts, PairBuf pb,
-                                                         Filter filt = Filter())
+                                                         Filter filt = Filter(), const FNode* __restrict__ fnodes = nullptr)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned lane = lane_id();
@@ -434,9 +520,17 @@ __global__ void __launch_bounds__(128) find_walk_kernel(const Node<T, D>* __rest
     {
       Box<T, D> L, R;
       int32_t lc, rc;
-      load_node_boxes<T, D>(nodes, cur, L, R, lc, rc);
-      const bool inL = box_valid(L) ? q(L) : false;
-      const bool inR = box_valid(R) ? q(R) : false;
+      bool inL, inR;
+      if(std::is_same<T, double>::value && D == 3 && fnodes != nullptr)
+      {
+        compact_visit(nodes, fnodes, cur, q, lc, rc, inL, inR);
+      }
+      else
+      {
+        load_node_boxes<T, D>(nodes, cur, L, R, lc, rc);
+        inL = box_valid(L) ? q(L) : false;
+        inR = box_valid(R) ? q(R) : false;
+      }
       if(inL && inR)
       {
         todo[sp++] = rc;

@@ -145,6 +145,33 @@ def test_find_strategies_large_batches(oracle, strategy):
     assert _same(ref.find_boxes(qb), gpu.findBoundingBoxes(qb))
 
 
+@pytest.mark.parametrize("compact", ["1", "0"])
+def test_find_compact_records_boundary_cases(oracle, monkeypatch, compact):
+    """point / box walks use 64-byte records with outward-rounded float boxes (AXB_FIND_COMPACT=0: the 128-byte ones);
+    leaves are confirmed on the exact double boxes, so queries that touch a box exactly, miss it by one ulp, or fall in
+    the float rounding gap give the reference's candidates in both settings"""
+    monkeypatch.setenv("AXB_FIND_COMPACT", compact)
+    rng = np.random.default_rng(12)
+    n = 40000
+    c = rng.random((n, 3)) * 1000.0 + 1.0 / 3.0  # coordinates that are not representable in binary32
+    boxes = np.concatenate([c, c + rng.random((n, 3)) * 3.0], axis=1)
+    ref, gpu = _check_build(oracle, boxes, 3, scale=1.0)
+    # points on box corners, one ulp inside / outside, and in the float rounding gap around them
+    corner = np.concatenate([boxes[:6000, :3], boxes[6000:12000, 3:]])
+    pts = np.concatenate([corner, np.nextafter(corner, np.inf), np.nextafter(corner, -np.inf),
+                          corner.astype(np.float32).astype(np.float64), corner * (1 + 1e-9)])
+    assert _same(ref.find_points(pts), gpu.findPoints(pts))
+    # query boxes that touch stored boxes exactly or miss them by one ulp
+    lo, hi = boxes[:9000, 3:], boxes[:9000, 3:] + 2.0
+    qb = np.concatenate([np.concatenate([lo, hi], 1), np.concatenate([np.nextafter(lo, np.inf), hi], 1),
+                         np.concatenate([boxes[9000:12000, :3] - 2.0, np.nextafter(boxes[9000:12000, :3], -np.inf)], 1)])
+    assert _same(ref.find_boxes(qb), gpu.findBoundingBoxes(qb))
+    # default scale factor (inflated leaf boxes) as well
+    ref2, gpu2 = _check_build(oracle, boxes, 3)
+    assert _same(ref2.find_points(pts), gpu2.findPoints(pts))
+    assert _same(ref2.find_boxes(qb), gpu2.findBoundingBoxes(qb))
+
+
 def test_find_device_resident(oracle):
     import torch
     boxes = synth.triangle_aabbs(30000, seed=21)
