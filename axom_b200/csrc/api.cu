@@ -296,7 +296,7 @@ struct axb_bvh
   double bounds_lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
   double bounds_hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
 
-  DevBuf nodes, leaf_nodes, leaf_parent, node_range, keys_a, keys_b, state, sort_scratch, stage_in, agglo_slots, agglo_flags;
+  DevBuf nodes, leaf_nodes, leaf_parent, node_range, keys_a, keys_b, state, sort_scratch, stage_in, agglo_slots, agglo_flags, agglo_open;
   int agglo_block = 128;      // leaves per block of agglo_kernel (AXB_AGGLO_BLOCK = 128 | 256 | 512)
   bool legacy_build = false;  // AXB_BUILD_LEGACY=1: tree_kernel + refit_kernel instead of agglo_kernel
   unsigned long long* sorted_keys = nullptr;  // points into keys_a or keys_b
@@ -314,7 +314,7 @@ struct axb_bvh
   void release_all()
   {
     cudaStream_t s = ctx.stream;
-    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &node_range, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &agglo_slots, &agglo_flags, &fnodes, &ref_inner_nodes,
+    for(DevBuf* b : {&nodes, &leaf_nodes, &leaf_parent, &node_range, &keys_a, &keys_b, &state, &sort_scratch, &stage_in, &agglo_slots, &agglo_flags, &agglo_open, &fnodes, &ref_inner_nodes,
                      &ref_children, &q_stage, &q_counts, &q_offsets, &q_tiles, &q_total, &f_keys_a, &f_keys_b, &f_scratch, &f_perm, &f_pairs,
                      &f_unused, &f_cursor})
       b->release(s);
@@ -420,10 +420,12 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
     AXB_TRY(h->agglo_slots.reserve(sizeof(AggloSlot<T, D>) * (size_t)n, ctx.stream));
     AXB_TRY(h->agglo_flags.reserve(sizeof(uint32_t) * (size_t)inner, ctx.stream));
     AXB_CUDA_TRY(cudaMemsetAsync(h->agglo_flags.p, 0, sizeof(uint32_t) * (size_t)inner, ctx.stream));
+    AXB_TRY(h->agglo_open.reserve(sizeof(AggloOpen<T, D>) * (size_t)n, ctx.stream));  // worst case: every leaf is open
 #define AXB_AGGLO(AB)                                                                                                          \
   AXB_LAUNCH(ctx, (agglo_kernel<T, D, AB>), blocks_for(n, AB), AB, in, n, num_boxes, half_scale, h->sorted_keys,             \
              h->nodes.as<Node<T, D>>(), h->leaf_nodes.as<int32_t>(), h->leaf_parent.as<int32_t>(), h->node_range.as<int2>(), \
-             h->agglo_slots.as<AggloSlot<T, D>>(), h->agglo_flags.as<uint32_t>(), &st->agglo_mismatch)
+             h->agglo_slots.as<AggloSlot<T, D>>(), h->agglo_flags.as<uint32_t>(), &st->agglo_mismatch,              \
+             h->agglo_open.as<AggloOpen<T, D>>(), &st->agglo_open_count)
     if(h->agglo_block == 256)
       AXB_AGGLO(256);
     else if(h->agglo_block == 512)
@@ -431,6 +433,10 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
     else
       AXB_AGGLO(128);
 #undef AXB_AGGLO
+    // the upper tree, from the subtrees the blocks left open (none when the whole tree fitted one block)
+    AXB_LAUNCH(ctx, (agglo_upper_kernel<T, D>), capped_grid(std::max(n / 8, 128), 128, 16), 128, n, h->sorted_keys, h->nodes.as<Node<T, D>>(),
+               h->leaf_parent.as<int32_t>(), h->node_range.as<int2>(), h->agglo_slots.as<AggloSlot<T, D>>(), h->agglo_flags.as<uint32_t>(),
+               &st->agglo_mismatch, h->agglo_open.as<AggloOpen<T, D>>(), &st->agglo_open_count);
   }
   ctx.phase_end(tot);
   // bounds come back to the host (getBounds() is a host query); this is also the build's sync point

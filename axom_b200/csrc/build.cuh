@@ -27,6 +27,7 @@ struct BuildState
   T bmax[D];
   T inv_extent[D];             // build_radix_tree.hpp:160-163
   uint32_t agglo_mismatch;     // agglo_kernel: a >2^24-leaf node whose float32 split search differs (see there)
+  uint32_t agglo_open_count;   // subtrees the block-local pass left for agglo_upper_kernel
 };
 
 template <typename T, int D>
@@ -40,6 +41,7 @@ __global__ void init_state_kernel(BuildState<T, D>* st)
       st->omax[d] = f64_to_ordered((double)Lim<T>::lowest());
     }
     st->agglo_mismatch = 0u;
+    st->agglo_open_count = 0u;
   }
 }
 
@@ -374,6 +376,14 @@ struct alignas(16) AggloSlot
   int32_t end;  // far end of the arriving child's leaf range
 };
 
+// a finished block-local subtree whose parent covers leaves of another block: input of agglo_upper_kernel
+template <typename T, int D>
+struct alignas(8) AggloOpen
+{
+  Box<T, D> box;
+  int32_t lo, hi;
+};
+
 __device__ __forceinline__ int adj_delta(unsigned long long kj, unsigned long long kj1, int j)
 {
   // delta(j, j+1) of :265-287 on (code << 32 | sorted position)
@@ -403,11 +413,39 @@ __device__ __noinline__ bool reference_split_agrees(int lo, int hi, int gam, boo
   return i + s * d + (d < 0 ? d : 0) == gam;
 }
 
+// The two children of the node that splits at `gam` have met: [l, r] is the node's range, dl / dr the deltas just
+// outside it, `box` the arriving child's box (the left one iff is_left), `other` its sibling's.  Writes the node's
+// record under its reference index, its range, and the parent links of the two children.  Returns true for the root.
+template <typename T, int D>
+__device__ __forceinline__ bool agglo_finish_node(Node<T, D>* nodes, int32_t* leaf_parent, int2* __restrict__ node_range, uint32_t* mismatch, int n,
+                                                  int l, int r, int gam, bool is_left, int dl, int dr, const Box<T, D>& box,
+                                                  const Box<T, D>& other)
+{
+  const bool root = (l == 0 && r == n - 1);
+  const bool p_is_left = dr > dl;
+  const int P = root ? 0 : (p_is_left ? r : l);
+  if(r - l > (1 << 24))
+    if(!reference_split_agrees<T>(l, r, gam, root || !p_is_left)) atomicOr(mismatch, 1u);
+  const int lc = l == gam ? -(gam + 1) : gam;
+  const int rc = r == gam + 1 ? -(gam + 2) : gam + 1;
+  Node<T, D>* nd = nodes + P;
+  nd->box[is_left ? 0 : 1] = box;
+  nd->box[is_left ? 1 : 0] = other;
+  *reinterpret_cast<int2*>(nd->child) = make_int2(lc, rc);
+  node_range[P] = make_int2(l, r);
+  // parent links of the two children (leaf_parent for leaves, Node::parent for inner nodes)
+  *(lc < 0 ? leaf_parent + gam : &nodes[gam].parent) = P << 1;
+  *(rc < 0 ? leaf_parent + gam + 1 : &nodes[gam + 1].parent) = (P << 1) | 1;
+  if(root) nd->parent = -1;
+  return root;
+}
+
 template <typename T, int D, int B>
 __global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, int n, int n_real, T half_scale,
                                                    const unsigned long long* __restrict__ keys, Node<T, D>* nodes,
                                                    int32_t* __restrict__ leaf_nodes, int32_t* leaf_parent, int2* __restrict__ node_range,
-                                                   AggloSlot<T, D>* gslot, uint32_t* gflag, uint32_t* mismatch)
+                                                   AggloSlot<T, D>* gslot, uint32_t* gflag, uint32_t* mismatch, AggloOpen<T, D>* open_list,
+                                                   unsigned int* open_count)
 {
   __shared__ unsigned long long s_key[B + 2];  // keys of positions L-1 .. L+B
   __shared__ int s_delta[B + 1];               // s_delta[k] = delta(L-1+k, L+k)
@@ -528,19 +566,55 @@ __global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, i
     int oend;
     if(k >= 0 && k < B - 1 && (s_flag[k] & 0x80000000u))
     {
+      uint32_t old;
+#ifndef AXB_AGGLO_RELAXED_SMEM
       s_box[self - L] = box;
       s_end[self - L] = is_left ? l : r;
-      uint32_t old;  // block-scope acq_rel RMW: publishes this child's slot, acquires the sibling's
+      // block-scope acq_rel RMW: publishes this child's slot, acquires the sibling's
       asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;"
                    : "=r"(old)
                    : "r"((uint32_t)__cvta_generic_to_shared(&s_flag[k]))
                    : "memory");
+#else
+      // -DAXB_AGGLO_RELAXED_SMEM: publish through shared memory WITHOUT a fence (relaxed RMW, volatile accesses; relies
+      // on shared memory being one in-order pipeline per SM).  Measured on B200: bit-identical trees at 1-20 M boxes
+      // and no gain over the fenced form (the membar stall of profiles/r1o came from the gpu-scope RMW of the
+      // cross-block path, now moved to agglo_upper_kernel), so the fenced, formally correct form is the default.
+      {
+        volatile T* sb = reinterpret_cast<volatile T*>(&s_box[self - L]);
+#pragma unroll
+        for(int d = 0; d < D; ++d)
+        {
+          sb[d] = box.lo[d];
+          sb[D + d] = box.hi[d];
+        }
+        *reinterpret_cast<volatile int*>(&s_end[self - L]) = is_left ? l : r;
+      }
+      asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], 1;"
+                   : "=r"(old)
+                   : "r"((uint32_t)__cvta_generic_to_shared(&s_flag[k]))
+                   : "memory");
+#endif
       if((old & 1u) == 0u) return;  // first arrival retires (:547-551)
+#ifndef AXB_AGGLO_RELAXED_SMEM
       other = s_box[sib - L];
       oend = s_end[sib - L];
+#else
+      {
+        const volatile T* ob = reinterpret_cast<const volatile T*>(&s_box[sib - L]);
+#pragma unroll
+        for(int d = 0; d < D; ++d)
+        {
+          other.lo[d] = ob[d];
+          other.hi[d] = ob[D + d];
+        }
+        oend = *reinterpret_cast<const volatile int*>(&s_end[sib - L]);
+      }
+#endif
     }
     else
     {
+#ifdef AXB_AGGLO_SINGLE_PASS
       store_box_cg(&gslot[self].box, box);
       __stcg(&gslot[self].end, is_left ? l : r);
       uint32_t old;
@@ -548,6 +622,19 @@ __global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, i
       if(old == 0u) return;
       other = load_box_cg(&gslot[sib].box);
       oend = __ldcg(&gslot[sib].end);
+#else
+      // The parent's range leaves the block: park this subtree in the open list and retire.  agglo_upper_kernel
+      // finishes the upper tree from the open entries.  (Meeting across blocks needs a gpu-scope release/acquire RMW,
+      // i.e. a MEMBAR.ALL.GPU that also waits for the node records this thread has just written; done here it stalled
+      // whole warps for one or two lanes -- a third of the kernel's stall cycles in profiles/r1o.)
+      const unsigned e = atomicAdd(open_count, 1u);
+      AggloOpen<T, D> o;
+      o.box = box;
+      o.lo = l;
+      o.hi = r;
+      open_list[e] = o;
+      return;
+#endif
     }
     // the parent covers [l, oend] or [oend, r]: only one of the two outer deltas changes
     if(is_left)
@@ -560,31 +647,65 @@ __global__ void __launch_bounds__(B, 1024 / B) agglo_kernel(Desc<2 * D> boxes, i
       l = oend;
       dl = dlt(l - 1);
     }
-    const bool root = (l == 0 && r == n - 1);
-    const bool p_is_left = dr > dl;
-    const int P = root ? 0 : (p_is_left ? r : l);
-    if(r - l > (1 << 24))
-      if(!reference_split_agrees<T>(l, r, gam, root || !p_is_left)) atomicOr(mismatch, 1u);
-    const int lc = l == gam ? -(gam + 1) : gam;
-    const int rc = r == gam + 1 ? -(gam + 2) : gam + 1;
-    Node<T, D>* nd = nodes + P;
-    nd->box[is_left ? 0 : 1] = box;
-    nd->box[is_left ? 1 : 0] = other;
-    *reinterpret_cast<int2*>(nd->child) = make_int2(lc, rc);
-    node_range[P] = make_int2(l, r);
-    // parent links of the two children (leaf_parent for leaves, Node::parent for inner nodes)
-    *(lc < 0 ? leaf_parent + gam : &nodes[gam].parent) = P << 1;
-    *(rc < 0 ? leaf_parent + gam + 1 : &nodes[gam + 1].parent) = (P << 1) | 1;
-    if(root)
-    {
-      nd->parent = -1;
-      return;
-    }
+    if(agglo_finish_node<T, D>(nodes, leaf_parent, node_range, mismatch, n, l, r, gam, is_left, dl, dr, box, other)) return;  // root
 #pragma unroll
     for(int d = 0; d < D; ++d)
     {
       box.lo[d] = other.lo[d] < box.lo[d] ? other.lo[d] : box.lo[d];
       box.hi[d] = other.hi[d] > box.hi[d] ? other.hi[d] : box.hi[d];
+    }
+  }
+}
+
+// Second pass of the fused build: the upper tree.  One thread per open entry (grid-stride: the count is only known
+// on the device); every meeting goes through the global slots with a gpu-scope acq_rel RMW.  All lanes of a warp are
+// in this path, so the fences are amortised over 32 merges instead of stalling a warp for one.
+template <typename T, int D>
+__global__ void __launch_bounds__(128) agglo_upper_kernel(int n, const unsigned long long* __restrict__ keys, Node<T, D>* nodes,
+                                                           int32_t* leaf_parent, int2* __restrict__ node_range, AggloSlot<T, D>* gslot,
+                                                           uint32_t* gflag, uint32_t* mismatch, const AggloOpen<T, D>* __restrict__ open_list,
+                                                           const unsigned int* __restrict__ open_count)
+{
+  auto dlt = [&](int j) -> int {
+    if(j < 0 || j >= n - 1) return -1;
+    return adj_delta(__ldg(keys + j), __ldg(keys + j + 1), j);
+  };
+  const unsigned count = *open_count;
+  for(unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x)
+  {
+    Box<T, D> box = open_list[e].box;
+    int l = open_list[e].lo, r = open_list[e].hi;
+    int dl = dlt(l - 1), dr = dlt(r);
+    for(;;)
+    {
+      const bool is_left = dr > dl;
+      const int gam = is_left ? r : l - 1;
+      const int self = is_left ? gam : gam + 1;
+      const int sib = is_left ? gam + 1 : gam;
+      store_box_cg(&gslot[self].box, box);
+      __stcg(&gslot[self].end, is_left ? l : r);
+      uint32_t old;
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(gflag + gam) : "memory");
+      if(old == 0u) break;  // first arrival: on to this thread's next open entry
+      const Box<T, D> other = load_box_cg(&gslot[sib].box);
+      const int oend = __ldcg(&gslot[sib].end);
+      if(is_left)
+      {
+        r = oend;
+        dr = dlt(r);
+      }
+      else
+      {
+        l = oend;
+        dl = dlt(l - 1);
+      }
+      if(agglo_finish_node<T, D>(nodes, leaf_parent, node_range, mismatch, n, l, r, gam, is_left, dl, dr, box, other)) break;  // root
+#pragma unroll
+      for(int d = 0; d < D; ++d)
+      {
+        box.lo[d] = other.lo[d] < box.lo[d] ? other.lo[d] : box.lo[d];
+        box.hi[d] = other.hi[d] > box.hi[d] ? other.hi[d] : box.hi[d];
+      }
     }
   }
 }
