@@ -9,15 +9,17 @@ entry of cp_rank / cp_index / cp_domain_index / cp_coords / cp_distance only if 
 the whole machine; among equidistant points the first rank in ring order from the owner wins, and within a rank the
 first point in the BVH's traversal order.
 
-On one NVSwitch box the ring of Conduit messages is replaced by: all-gather the query blocks; every rank searches
-every block it is not pruned from with its own BVH (one kernel per block, axb_dcp_compute_local_closest_points with
-is_first); then three all-reduces per block select the winner exactly as the ring would --
+On one NVSwitch box the ring of Conduit messages is replaced by: every rank searches its OWN block first (is_first);
+the blocks are all-gathered together with the owners' answers; every other rank searches every block it is not pruned
+from with the owner's answer as the preset (so, like a later rank of the ring, it reports only a strictly nearer point,
+and usually prunes its whole tree at the root); then three all-reduces per block select the winner exactly as the
+ring would --
   MIN  over the squared distances (recomputed from cp_coords with the reference's own expression, so equal values
        are bit-equal),
   MIN  over the ring position (rank - owner) mod N of the ranks that attain that minimum,
   SUM  of the winner's payload as integer bit patterns (everyone else contributes zeros; exact, keeps -0.0).
-A rank's local answer does not depend on what earlier ranks found (the preset only prunes), so the result is
-identical to the reference's ring, ties included.  With world size 1 no collective is issued.
+A rank's strictly-nearer answer does not depend on what other ranks found (a preset only prunes), and a tie with the
+owner goes to the owner in the ring as well, so the result is identical to the reference's ring, ties included.  With world size 1 no collective is issued.
 
 The mint / Conduit blueprint nodes of the reference are reduced to arrays: the object mesh is a list of domains
 (coords (n_i, D) interleaved, optional state/domain_id), the query mesh is coords (n, D).
@@ -158,19 +160,26 @@ class DistributedClosestPoint:
         if world == 1:
             return self._select(self._b.compute_local(rank, q))
 
-        # ---- query blocks and bounding boxes of every rank ----
+        # ---- phase A: every rank searches its OWN block first; the result is an upper bound for everyone else ----
+        own = self._b.compute_local(rank, q)
+
+        # ---- query blocks (with the owner's closest point so far) and bounding boxes of every rank ----
+        D = self.ndims
         counts = torch.zeros(world, dtype=torch.int64, device=dev)
         counts[rank] = q.shape[0]
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         counts = [int(c) for c in counts.tolist()]
-        nmax = max(counts)
-        padded = torch.zeros((max(nmax, 1), self.ndims), dtype=torch.float64, device=dev)
-        padded[:q.shape[0]] = q
+        nmax = max(max(counts), 1)
+        # columns: query coords | owner's cp_coords | owner's cp_rank (as float64, exact for small ints)
+        padded = torch.zeros((nmax, 2 * D + 1), dtype=torch.float64, device=dev)
+        padded[:q.shape[0], :D] = q
+        padded[:q.shape[0], D:2 * D] = own["cp_coords"]
+        padded[:q.shape[0], 2 * D] = own["cp_rank"].to(torch.float64)
         blocks = [torch.empty_like(padded) for _ in range(world)]
         dist.all_gather(blocks, padded)
         # [query lo, query hi, object lo, object hi] per rank, for the reference's pruning test (:762-775, :859-878)
         olo, ohi = self._b.object_bounds()
-        bb = torch.full((4, self.ndims), _DBL_MAX, dtype=torch.float64, device=dev)
+        bb = torch.full((4, D), _DBL_MAX, dtype=torch.float64, device=dev)
         bb[1] = -_DBL_MAX
         if q.shape[0]:
             bb[0], bb[1] = q.min(dim=0).values, q.max(dim=0).values
@@ -190,21 +199,33 @@ class DistributedClosestPoint:
             n = counts[owner]
             if n == 0:
                 continue
-            qo = blocks[owner][:n].contiguous()
-            # which ranks take part for this block: the owner always, the others if their object box is close enough
-            # (every rank evaluates the same test on the same gathered boxes, so the collectives below match up)
-            mine = owner == rank or box_sqdist(bbs[owner][0], bbs[owner][1], bbs[rank][2], bbs[rank][3]) <= self._sq_threshold
-            if mine:
-                st = self._b.compute_local(rank, qo)
+            qo = blocks[owner][:n, :D].contiguous()
+            # ---- phase B: the other ranks search the block with the owner's answer as the preset: like the ring's
+            # later ranks they only report a STRICTLY nearer point (a tie goes to the owner, ring position 0), and a
+            # good preset prunes their whole tree at the root.  A rank whose object box is farther than the threshold
+            # from the block's box sits the block out (every rank evaluates this test on the same gathered boxes, so
+            # the collectives below match up).
+            if owner == rank:
+                st = own
                 valid = st["cp_rank"] >= 0
-                v = st["cp_coords"] - qo
-                sq = torch.zeros(n, dtype=torch.float64, device=dev)
-                for d in range(self.ndims):  # squared_distance(qpt, query_pos): += in order, separately rounded
-                    sq = sq + v[:, d] * v[:, d]
-                sq = torch.where(valid, sq, torch.full_like(sq, float("inf")))
+            elif box_sqdist(bbs[owner][0], bbs[owner][1], bbs[rank][2], bbs[rank][3]) <= self._sq_threshold:
+                st = {"cp_index": torch.full((n,), -1, dtype=torch.int32, device=dev),
+                      "cp_domain_index": torch.full((n,), -1, dtype=torch.int32, device=dev),
+                      "cp_rank": blocks[owner][:n, 2 * D].to(torch.int32).contiguous(),
+                      "cp_coords": blocks[owner][:n, D:2 * D].contiguous(),
+                      "cp_distance": torch.zeros(n, dtype=torch.float64, device=dev)}
+                st = self._b.compute_local(rank, qo, st)
+                valid = st["cp_rank"] == rank
             else:
                 st = None
                 valid = torch.zeros(n, dtype=torch.bool, device=dev)
+            if st is not None:
+                v = st["cp_coords"] - qo
+                sq = torch.zeros(n, dtype=torch.float64, device=dev)
+                for d in range(D):  # squared_distance(qpt, query_pos): += in order, separately rounded
+                    sq = sq + v[:, d] * v[:, d]
+                sq = torch.where(valid, sq, torch.full_like(sq, float("inf")))
+            else:
                 sq = torch.full((n,), float("inf"), dtype=torch.float64, device=dev)
             smin = sq.clone()
             dist.all_reduce(smin, op=dist.ReduceOp.MIN)
@@ -213,15 +234,15 @@ class DistributedClosestPoint:
             win = pos.clone()
             dist.all_reduce(win, op=dist.ReduceOp.MIN)
             i_win = valid & (pos == win)
-            payload = torch.zeros((n, 4 + self.ndims), dtype=torch.int64, device=dev)
+            payload = torch.zeros((n, 4 + D), dtype=torch.int64, device=dev)
             if st is not None:
                 sel = i_win
                 payload[:, 0] = torch.where(sel, st["cp_index"].to(torch.int64), payload[:, 0])
                 payload[:, 1] = torch.where(sel, st["cp_domain_index"].to(torch.int64), payload[:, 1])
                 payload[:, 2] = torch.where(sel, st["cp_rank"].to(torch.int64), payload[:, 2])
-                payload[:, 3] = torch.where(sel, st["cp_distance"].view(torch.int64), payload[:, 3])
+                payload[:, 3] = torch.where(sel, st["cp_distance"].contiguous().view(torch.int64), payload[:, 3])
                 bits = st["cp_coords"].contiguous().view(torch.int64)
-                for d in range(self.ndims):
+                for d in range(D):
                     payload[:, 4 + d] = torch.where(sel, bits[:, d], payload[:, 4 + d])
             dist.all_reduce(payload, op=dist.ReduceOp.SUM)
             if owner == rank:
@@ -232,10 +253,10 @@ class DistributedClosestPoint:
                     "cp_domain_index": torch.where(found, payload[:, 1], torch.full_like(win, -1)).to(torch.int32),
                     "cp_rank": torch.where(found, payload[:, 2], torch.full_like(win, -1)).to(torch.int32),
                     "cp_distance": torch.where(found, payload[:, 3].view(torch.float64), snan.expand(n)),
-                    "cp_coords": torch.where(found[:, None], payload[:, 4:].contiguous().view(torch.float64), snan.expand(n, self.ndims)),
+                    "cp_coords": torch.where(found[:, None], payload[:, 4:].contiguous().view(torch.float64), snan.expand(n, D)),
                 }
         if result is None:
-            result = self._b.compute_local(rank, q)  # this rank has no queries: empty arrays of the right types
+            result = own  # this rank has no queries: empty arrays of the right types
         return self._select(result)
 
     def _select(self, st):

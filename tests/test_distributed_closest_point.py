@@ -84,7 +84,9 @@ class _OracleBackend:
 
     def compute_local(self, rank, q, state=None):
         import torch
-        st = self.rank_obj.compute_local(rank, q.numpy(), None, self.sq)
+        if state is not None:  # preset from the owner: updated in place, like the xferDom arrays
+            state = {k: np.ascontiguousarray(v.numpy()) for k, v in state.items()}
+        st = self.rank_obj.compute_local(rank, q.numpy(), state, self.sq)
         return {k: torch.from_numpy(v) for k, v in st.items()}
 
 
