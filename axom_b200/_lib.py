@@ -92,6 +92,7 @@ SYMBOLS = [
     ("axb_dcp_set_mode", C.c_int, [_P, C.c_int]),
     ("axb_dcp_get_bvh", C.c_int, [_P, _PP]),
     ("axb_dcp_compute_local_closest_points", C.c_int, [_P, C.c_int, _P, C.c_int32, C.c_int, _P, _P, _P, _P, _P, C.c_int]),
+    ("axb_dcp_compute_bounded_closest_points", C.c_int, [_P, C.c_int, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     # include/axb200_quest.h: the reference's legacy process-global C surface (wrapQUEST.h:83-127) + STL / welding
     ("QUEST_signed_distance_init_serial", C.c_int, [C.c_char_p]),
     ("QUEST_signed_distance_init_serial_bufferify", C.c_int, [C.c_char_p, C.c_int]),

@@ -1781,8 +1781,30 @@ int axb_dcp_get_bvh(axb_dcp* h, axb_bvh** bvh)
 // computeLocalClosestPoints (:905-1079) for one block of query points.  The five state arrays are the xferDom fields
 // cp_index / cp_domain_index / cp_rank / cp_coords (interleaved) / debug/cp_distance (may be NULL); is_first != 0
 // initialises them (-1, signalling NaN) before the search, otherwise they carry what earlier ranks of the ring found.
+static int dcp_compute(axb_dcp* h, int rank, const double* query_coords, int32_t nq, int is_first, const double* bound_sq, int32_t* cp_index,
+                       int32_t* cp_domain_index, int32_t* cp_rank, double* cp_coords, double* cp_distance, int memspace);
+
 int axb_dcp_compute_local_closest_points(axb_dcp* h, int rank, const double* query_coords, int32_t nq, int is_first, int32_t* cp_index,
                                          int32_t* cp_domain_index, int32_t* cp_rank, double* cp_coords, double* cp_distance, int memspace)
+{
+  return dcp_compute(h, rank, query_coords, nq, is_first, nullptr, cp_index, cp_domain_index, cp_rank, cp_coords, cp_distance, memspace);
+}
+
+// The first-visit search (is_first) restricted to points within a per-query squared-distance bound that some other rank
+// has already achieved: the state arrays are initialised, and an entry is filled only if this rank holds a point with
+// squared distance <= bound_sq[i] (ties included: who wins a tie is decided by ring order afterwards).  Device memory
+// only; used by the collective replacement of the ring (axom_b200/distributed_closest_point.py).
+int axb_dcp_compute_bounded_closest_points(axb_dcp* h, int rank, const double* query_coords, int32_t nq, const double* bound_sq,
+                                           int32_t* cp_index, int32_t* cp_domain_index, int32_t* cp_rank, double* cp_coords,
+                                           double* cp_distance)
+{
+  if(nq > 0 && !bound_sq) return fail(AXB_ERR_BAD_ARG, "null bound array");
+  if(h && h->mode != 1) return fail(AXB_ERR_UNSUPPORTED, "bounded search needs the nearest-first mode (axb_dcp_set_mode 1)");
+  return dcp_compute(h, rank, query_coords, nq, 1, bound_sq, cp_index, cp_domain_index, cp_rank, cp_coords, cp_distance, AXB_MEM_DEVICE);
+}
+
+static int dcp_compute(axb_dcp* h, int rank, const double* query_coords, int32_t nq, int is_first, const double* bound_sq, int32_t* cp_index,
+                       int32_t* cp_domain_index, int32_t* cp_rank, double* cp_coords, double* cp_distance, int memspace)
 {
   if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
   if(nq < 0) return fail(AXB_ERR_BAD_ARG, "negative query count");
@@ -1860,7 +1882,19 @@ int axb_dcp_compute_local_closest_points(axb_dcp* h, int rank, const double* que
   AXB_LAUNCH(ctx, KERNEL<DD>, blocks_for(nq, 128), 128, has ? h->bvh->nodes.as<Node<double, DD>>() : nullptr,                      \
              h->bvh->leaf_nodes.as<int32_t>(), h->pts.as<double>(), h->dom.as<int32_t>(), rank, h->sq_thresh, d_q, nq, perm, is_first, \
              d_idx, d_dom, d_rank, d_coords, d_dist)
-    if(h->mode == 1)
+    if(h->mode == 1 && bound_sq)
+    {
+#define AXB_DCP_LAUNCH_B(DD)                                                                                                       \
+  AXB_LAUNCH(ctx, dcp_nearest_kernel<DD>, blocks_for(nq, 128), 128, has ? h->bvh->nodes.as<Node<double, DD>>() : nullptr,          \
+             h->bvh->leaf_nodes.as<int32_t>(), h->pts.as<double>(), h->dom.as<int32_t>(), rank, h->sq_thresh, d_q, nq, perm, is_first, \
+             d_idx, d_dom, d_rank, d_coords, d_dist, bound_sq)
+      if(D == 3)
+        AXB_DCP_LAUNCH_B(3);
+      else
+        AXB_DCP_LAUNCH_B(2);
+#undef AXB_DCP_LAUNCH_B
+    }
+    else if(h->mode == 1)
     {
       if(D == 3)
         AXB_DCP_LAUNCH(dcp_nearest_kernel, 3);

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(128) dcp_nearest_kernel(const Node<double, D>*
                                                            double sq_thresh, const double* __restrict__ query, int nq,
                                                            const int32_t* __restrict__ perm, int is_first, int32_t* __restrict__ cp_index,
                                                            int32_t* __restrict__ cp_dom, int32_t* __restrict__ cp_rank,
-                                                           double* __restrict__ cp_coords, double* __restrict__ cp_dist)
+                                                           double* __restrict__ cp_coords, double* __restrict__ cp_dist,
+                                                           const double* __restrict__ bound_sq = nullptr)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if(t >= nq) return;
@@ -150,7 +151,9 @@ __global__ void __launch_bounds__(128) dcp_nearest_kernel(const Node<double, D>*
   double p[D];
 #pragma unroll
   for(int d = 0; d < D; ++d) p[d] = query[(size_t)i * D + d];
-  double cur_sq = DBL_MAX;
+  // bound_sq (optional, with is_first): only a point with squared distance <= bound_sq[i] is of interest -- an upper
+  // bound some other rank already achieved.  Unlike a preset it does NOT win ties: a point AT the bound is reported.
+  double cur_sq = bound_sq ? bound_sq[i] : DBL_MAX;
   int cur_pos = 0x7fffffff;  // sorted position of the running minimum; -1 = a preset, which wins every tie
   int cur_idx = -1;
   bool improved = false;

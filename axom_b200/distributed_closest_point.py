@@ -9,17 +9,20 @@ entry of cp_rank / cp_index / cp_domain_index / cp_coords / cp_distance only if 
 the whole machine; among equidistant points the first rank in ring order from the owner wins, and within a rank the
 first point in the BVH's traversal order.
 
-On one NVSwitch box the ring of Conduit messages is replaced by: every rank searches its OWN block first (is_first);
-the blocks are all-gathered together with the owners' answers; every other rank searches every block it is not pruned
-from with the owner's answer as the preset (so, like a later rank of the ring, it reports only a strictly nearer point,
-and usually prunes its whole tree at the root); then three all-reduces per block select the winner exactly as the
+On one NVSwitch box the ring of Conduit messages is replaced by collectives.  All query blocks and all object
+bounding boxes are all-gathered.  Phase 1: every query is searched, unbounded, by the rank whose object box is nearest
+to it; one MIN all-reduce turns the distances found into an upper bound for everybody.  Phase 2: every other rank
+searches a query only if its own object box is within that bound (and within the distance threshold), and only for a
+point at least as near as the bound (axb_dcp_compute_bounded_closest_points) -- the ring prunes with the same two
+tests, per block instead of per query.  Phase 3: three all-reduces over all queries select the winner exactly as the
 ring would --
   MIN  over the squared distances (recomputed from cp_coords with the reference's own expression, so equal values
        are bit-equal),
-  MIN  over the ring position (rank - owner) mod N of the ranks that attain that minimum,
+  MIN  over the ring position (rank - home) mod N of the ranks that attain that minimum,
   SUM  of the winner's payload as integer bit patterns (everyone else contributes zeros; exact, keeps -0.0).
-A rank's strictly-nearer answer does not depend on what other ranks found (a preset only prunes), and a tie with the
-owner goes to the owner in the ring as well, so the result is identical to the reference's ring, ties included.  With world size 1 no collective is issued.
+Which point a rank reports (its nearest, ties by traversal order) does not depend on the bound, a bound only prunes, and
+every rank that holds a point at the global minimum still reports it, so the result is identical to the reference's
+ring, ties included.  With world size 1 no collective is issued.
 
 The mint / Conduit blueprint nodes of the reference are reduced to arrays: the object mesh is a list of domains
 (coords (n_i, D) interleaved, optional state/domain_id), the query mesh is coords (n, D).
@@ -31,7 +34,35 @@ import numpy as np
 from . import _lib
 from ._lib import MEM_DEVICE, MEM_HOST, check
 
+import os
+import time
+
 OUTPUT_FIELDS = ("cp_rank", "cp_index", "cp_distance", "cp_coords", "cp_domain_index")
+
+
+class _Phases:
+    """AXB_DCP_TIMING=1: wall time per phase of computeClosestPoints (synchronising), printed by rank 0"""
+
+    def __init__(self, dev):
+        self.on = os.environ.get("AXB_DCP_TIMING") == "1"
+        self.dev, self.t, self.acc = dev, None, {}
+
+    def mark(self, name):
+        if not self.on:
+            return
+        import torch
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        now = time.perf_counter()
+        if self.t is not None:
+            self.acc[self._name] = self.acc.get(self._name, 0.0) + (now - self.t) * 1e3
+        self.t, self._name = now, name
+
+    def report(self, rank):
+        self.mark("end")
+        if self.on and rank == 0:
+            print("[dcp phases ms]", {k: round(v, 1) for k, v in self.acc.items()}, flush=True)
+
 _DBL_MAX = float(np.finfo(np.float64).max)
 
 
@@ -79,6 +110,20 @@ class _GpuBackend:
         if not bvh.isInitialized():
             return np.full(self.ndims, _DBL_MAX), np.full(self.ndims, -_DBL_MAX)
         return bvh.getBounds()
+
+    def compute_bounded(self, rank, q, bound_sq):
+        """first-visit search for points with squared distance <= bound_sq (ties included); q, bound_sq CUDA tensors"""
+        import torch
+        torch.cuda.current_stream(q.device).synchronize()
+        n, dev = q.shape[0], q.device
+        st = {"cp_index": torch.empty(n, dtype=torch.int32, device=dev), "cp_domain_index": torch.empty(n, dtype=torch.int32, device=dev),
+              "cp_rank": torch.empty(n, dtype=torch.int32, device=dev), "cp_coords": torch.empty((n, self.ndims), dtype=torch.float64, device=dev),
+              "cp_distance": torch.empty(n, dtype=torch.float64, device=dev)}
+        if n:
+            check(self._L.axb_dcp_compute_bounded_closest_points(self._h, int(rank), q.data_ptr(), n, bound_sq.data_ptr(), st["cp_index"].data_ptr(),
+                                                                 st["cp_domain_index"].data_ptr(), st["cp_rank"].data_ptr(),
+                                                                 st["cp_coords"].data_ptr(), st["cp_distance"].data_ptr()))
+        return st
 
     def compute_local(self, rank, q, state=None):
         """q: (n, D) float64 CUDA tensor.  state None = is_first.  Returns the state dict (updated in place)."""
@@ -160,103 +205,111 @@ class DistributedClosestPoint:
         if world == 1:
             return self._select(self._b.compute_local(rank, q))
 
-        # ---- phase A: every rank searches its OWN block first; the result is an upper bound for everyone else ----
-        own = self._b.compute_local(rank, q)
-
-        # ---- query blocks (with the owner's closest point so far) and bounding boxes of every rank ----
+        ph = _Phases(dev)
+        ph.mark("gather")
         D = self.ndims
+        # ---- every rank gets all query blocks and all object bounding boxes ----
         counts = torch.zeros(world, dtype=torch.int64, device=dev)
         counts[rank] = q.shape[0]
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         counts = [int(c) for c in counts.tolist()]
         nmax = max(max(counts), 1)
-        # columns: query coords | owner's cp_coords | owner's cp_rank (as float64, exact for small ints)
-        padded = torch.zeros((nmax, 2 * D + 1), dtype=torch.float64, device=dev)
-        padded[:q.shape[0], :D] = q
-        padded[:q.shape[0], D:2 * D] = own["cp_coords"]
-        padded[:q.shape[0], 2 * D] = own["cp_rank"].to(torch.float64)
+        padded = torch.zeros((nmax, D), dtype=torch.float64, device=dev)
+        padded[:q.shape[0]] = q
         blocks = [torch.empty_like(padded) for _ in range(world)]
         dist.all_gather(blocks, padded)
-        # [query lo, query hi, object lo, object hi] per rank, for the reference's pruning test (:762-775, :859-878)
+        Q = torch.cat([blocks[o][:counts[o]] for o in range(world)]).contiguous()  # all queries, grouped by home rank
+        home = torch.cat([torch.full((counts[o],), o, dtype=torch.int64, device=dev) for o in range(world)])
+        ntot = Q.shape[0]
+        first = sum(counts[:rank])  # this rank's own queries are Q[first : first + counts[rank]]
         olo, ohi = self._b.object_bounds()
-        bb = torch.full((4, D), _DBL_MAX, dtype=torch.float64, device=dev)
-        bb[1] = -_DBL_MAX
-        if q.shape[0]:
-            bb[0], bb[1] = q.min(dim=0).values, q.max(dim=0).values
-        bb[2], bb[3] = torch.as_tensor(olo, device=dev), torch.as_tensor(ohi, device=dev)
+        bb = torch.stack([torch.as_tensor(olo, dtype=torch.float64, device=dev), torch.as_tensor(ohi, dtype=torch.float64, device=dev)])
         bbs = [torch.empty_like(bb) for _ in range(world)]
         dist.all_gather(bbs, bb)
-        bbs = [b.cpu().numpy() for b in bbs]
 
-        def box_sqdist(alo, ahi, blo, bhi):  # primal::squared_distance(BoundingBox, BoundingBox): gap per dimension
-            if np.any(alo > ahi) or np.any(blo > bhi):
-                return _DBL_MAX
-            gap = np.maximum(np.maximum(blo - ahi, alo - bhi), 0.0)
-            return float(np.sum(gap * gap))
+        # squared distance from every query to every rank's object box (primal::squared_distance(Point, BoundingBox);
+        # an empty rank is infinitely far).  Only used to order and to prune the searches, never in a result.
+        INF = float("inf")
+        boxd = torch.empty((world, ntot), dtype=torch.float64, device=dev)
+        for r in range(world):
+            lo_r, hi_r = bbs[r][0], bbs[r][1]
+            if bool((lo_r > hi_r).any()):
+                boxd[r] = INF
+            else:
+                gap = torch.clamp(torch.maximum(lo_r - Q, Q - hi_r), min=0.0)
+                boxd[r] = (gap * gap).sum(dim=1)
+        mine = boxd[rank]
+        nearest_rank = torch.argmin(boxd, dim=0)  # the rank whose object box is nearest: it searches the query first
 
-        result = None
-        for owner in range(world):
-            n = counts[owner]
-            if n == 0:
-                continue
-            qo = blocks[owner][:n, :D].contiguous()
-            # ---- phase B: the other ranks search the block with the owner's answer as the preset: like the ring's
-            # later ranks they only report a STRICTLY nearer point (a tie goes to the owner, ring position 0), and a
-            # good preset prunes their whole tree at the root.  A rank whose object box is farther than the threshold
-            # from the block's box sits the block out (every rank evaluates this test on the same gathered boxes, so
-            # the collectives below match up).
-            if owner == rank:
-                st = own
-                valid = st["cp_rank"] >= 0
-            elif box_sqdist(bbs[owner][0], bbs[owner][1], bbs[rank][2], bbs[rank][3]) <= self._sq_threshold:
-                st = {"cp_index": torch.full((n,), -1, dtype=torch.int32, device=dev),
-                      "cp_domain_index": torch.full((n,), -1, dtype=torch.int32, device=dev),
-                      "cp_rank": blocks[owner][:n, 2 * D].to(torch.int32).contiguous(),
-                      "cp_coords": blocks[owner][:n, D:2 * D].contiguous(),
-                      "cp_distance": torch.zeros(n, dtype=torch.float64, device=dev)}
-                st = self._b.compute_local(rank, qo, st)
-                valid = st["cp_rank"] == rank
-            else:
-                st = None
-                valid = torch.zeros(n, dtype=torch.bool, device=dev)
-            if st is not None:
-                v = st["cp_coords"] - qo
-                sq = torch.zeros(n, dtype=torch.float64, device=dev)
-                for d in range(D):  # squared_distance(qpt, query_pos): += in order, separately rounded
-                    sq = sq + v[:, d] * v[:, d]
-                sq = torch.where(valid, sq, torch.full_like(sq, float("inf")))
-            else:
-                sq = torch.full((n,), float("inf"), dtype=torch.float64, device=dev)
-            smin = sq.clone()
-            dist.all_reduce(smin, op=dist.ReduceOp.MIN)
-            pos = torch.full((n,), world, dtype=torch.int64, device=dev)
-            pos = torch.where(valid & (sq == smin), torch.full_like(pos, (rank - owner) % world), pos)
-            win = pos.clone()
-            dist.all_reduce(win, op=dist.ReduceOp.MIN)
-            i_win = valid & (pos == win)
-            payload = torch.zeros((n, 4 + D), dtype=torch.int64, device=dev)
-            if st is not None:
-                sel = i_win
-                payload[:, 0] = torch.where(sel, st["cp_index"].to(torch.int64), payload[:, 0])
-                payload[:, 1] = torch.where(sel, st["cp_domain_index"].to(torch.int64), payload[:, 1])
-                payload[:, 2] = torch.where(sel, st["cp_rank"].to(torch.int64), payload[:, 2])
-                payload[:, 3] = torch.where(sel, st["cp_distance"].contiguous().view(torch.int64), payload[:, 3])
-                bits = st["cp_coords"].contiguous().view(torch.int64)
-                for d in range(D):
-                    payload[:, 4 + d] = torch.where(sel, bits[:, d], payload[:, 4 + d])
-            dist.all_reduce(payload, op=dist.ReduceOp.SUM)
-            if owner == rank:
-                found = win < world
-                snan = torch.tensor([0x7ff4000000000000], dtype=torch.int64, device=dev).view(torch.float64)[0]
-                result = {
-                    "cp_index": torch.where(found, payload[:, 0], torch.full_like(win, -1)).to(torch.int32),
-                    "cp_domain_index": torch.where(found, payload[:, 1], torch.full_like(win, -1)).to(torch.int32),
-                    "cp_rank": torch.where(found, payload[:, 2], torch.full_like(win, -1)).to(torch.int32),
-                    "cp_distance": torch.where(found, payload[:, 3].view(torch.float64), snan.expand(n)),
-                    "cp_coords": torch.where(found[:, None], payload[:, 4:].contiguous().view(torch.float64), snan.expand(n, D)),
-                }
-        if result is None:
-            result = own  # this rank has no queries: empty arrays of the right types
+        def scatter_state(full, idx, st):
+            for k in ("cp_index", "cp_domain_index", "cp_rank", "cp_coords", "cp_distance"):
+                full[k][idx] = st[k]
+
+        snan = torch.tensor([0x7ff4000000000000], dtype=torch.int64, device=dev).view(torch.float64)[0]
+        cand = {"cp_index": torch.full((ntot,), -1, dtype=torch.int32, device=dev),
+                "cp_domain_index": torch.full((ntot,), -1, dtype=torch.int32, device=dev),
+                "cp_rank": torch.full((ntot,), -1, dtype=torch.int32, device=dev),
+                "cp_coords": snan.expand(ntot, D).clone(), "cp_distance": snan.expand(ntot).clone()}
+
+        def sq_of(st, qq):
+            v = st["cp_coords"] - qq
+            sq = torch.zeros(qq.shape[0], dtype=torch.float64, device=dev)
+            for d in range(D):  # squared_distance(qpt, query_pos): += in order, separately rounded
+                sq = sq + v[:, d] * v[:, d]
+            return torch.where(st["cp_rank"] >= 0, sq, torch.full_like(sq, INF))
+
+        # ---- phase 1: each query is searched, unbounded, by the rank whose object box is nearest to it; the distance
+        # found there is an upper bound for everybody else (one MIN all-reduce) ----
+        ph.mark("first search")
+        idx1 = torch.nonzero((nearest_rank == rank) & (mine <= self._sq_threshold)).reshape(-1)
+        bound = torch.full((ntot,), INF, dtype=torch.float64, device=dev)
+        if idx1.numel():
+            q1 = Q[idx1].contiguous()
+            st1 = self._b.compute_local(rank, q1)
+            scatter_state(cand, idx1, st1)
+            bound[idx1] = sq_of(st1, q1)
+        ph.mark("bound all-reduce")
+        dist.all_reduce(bound, op=dist.ReduceOp.MIN)
+
+        # ---- phase 2: the other ranks look only for a point at least as near as the bound, and only where their
+        # object box is that near at all (the reference's ring prunes with the same two tests, per block instead of
+        # per query: DistributedClosestPointImpl.hpp:762-775, :859-878, :1037-1040) ----
+        ph.mark("bounded search")
+        limit = torch.minimum(bound, torch.full_like(bound, self._sq_threshold))
+        idx2 = torch.nonzero((nearest_rank != rank) & (mine <= limit)).reshape(-1)
+        if idx2.numel():
+            q2 = Q[idx2].contiguous()
+            st2 = self._b.compute_bounded(rank, q2, bound[idx2].contiguous())
+            scatter_state(cand, idx2, st2)
+
+        # ---- phase 3: the winner of every query, exactly as the ring would pick it ----
+        ph.mark("combine")
+        valid = cand["cp_rank"] >= 0
+        sq = sq_of(cand, Q)
+        smin = sq.clone()
+        dist.all_reduce(smin, op=dist.ReduceOp.MIN)
+        pos = torch.where(valid & (sq == smin), (rank - home) % world, torch.full_like(home, world))
+        win = pos.clone()
+        dist.all_reduce(win, op=dist.ReduceOp.MIN)
+        sel = valid & (pos == win)
+        zero = torch.zeros(ntot, dtype=torch.int64, device=dev)
+        cols = [torch.where(sel, cand["cp_index"].to(torch.int64), zero), torch.where(sel, cand["cp_domain_index"].to(torch.int64), zero),
+                torch.where(sel, cand["cp_rank"].to(torch.int64), zero), torch.where(sel, cand["cp_distance"].view(torch.int64), zero)]
+        bits = cand["cp_coords"].contiguous().view(torch.int64)
+        cols += [torch.where(sel, bits[:, d], zero) for d in range(D)]
+        payload = torch.stack(cols, dim=1).contiguous()
+        dist.all_reduce(payload, op=dist.ReduceOp.SUM)
+        n = counts[rank]
+        pl, found = payload[first:first + n], (win[first:first + n] < world)
+        neg = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        result = {
+            "cp_index": torch.where(found, pl[:, 0], neg).to(torch.int32),
+            "cp_domain_index": torch.where(found, pl[:, 1], neg).to(torch.int32),
+            "cp_rank": torch.where(found, pl[:, 2], neg).to(torch.int32),
+            "cp_distance": torch.where(found, pl[:, 3].contiguous().view(torch.float64), snan.expand(n)),
+            "cp_coords": torch.where(found[:, None], pl[:, 4:].contiguous().view(torch.float64), snan.expand(n, D)),
+        }
+        ph.report(rank)
         return self._select(result)
 
     def _select(self, st):

@@ -245,6 +245,13 @@ int axb_dcp_compute_local_closest_points(axb_dcp* dcp, int rank, const double* q
                                          int is_first, int32_t* cp_index, int32_t* cp_domain_index, int32_t* cp_rank,
                                          double* cp_coords, double* cp_distance /* may be NULL */, int memspace);
 
+/* The first-visit search restricted to points within a per-query squared-distance bound another rank already achieved
+ * (device arrays only): state arrays are initialised and an entry is filled only if this rank holds a point with squared
+ * distance <= bound_sq[i], ties included.  A building block of the collective form of the ring. */
+int axb_dcp_compute_bounded_closest_points(axb_dcp* dcp, int rank, const double* query_coords_interleaved, int32_t num_queries,
+                                           const double* bound_sq, int32_t* cp_index, int32_t* cp_domain_index, int32_t* cp_rank,
+                                           double* cp_coords, double* cp_distance);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,21 @@ class _OracleBackend:
         b = self.O.Bvh(np.concatenate([self.coords, self.coords], axis=1), ndims=self.nd).arrays()["bounds"]
         return b[:self.nd], b[self.nd:]
 
+    def compute_bounded(self, rank, q, bound_sq):
+        import torch
+        st = self.rank_obj.compute_local(rank, q.numpy(), None, self.sq)
+        v = st["cp_coords"] - q.numpy()
+        sq = np.zeros(len(v))
+        for d in range(self.nd):
+            sq = sq + v[:, d] * v[:, d]
+        drop = ~((st["cp_rank"] >= 0) & (sq <= bound_sq.numpy()))
+        snan = np.frombuffer(np.array([0x7ff4000000000000], np.int64).tobytes(), np.float64)[0]
+        for k in ("cp_index", "cp_domain_index", "cp_rank"):
+            st[k][drop] = -1
+        st["cp_coords"][drop] = snan
+        st["cp_distance"][drop] = snan
+        return {k: torch.from_numpy(v) for k, v in st.items()}
+
     def compute_local(self, rank, q, state=None):
         import torch
         if state is not None:  # preset from the owner: updated in place, like the xferDom arrays
@@ -231,3 +246,32 @@ def test_gpu_single_rank_class_and_outputs(oracle):
     want = oracle.DistributedClosestPointRank(parts[0], dom, 3).compute_local(0, q, None, 0.03 ** 2)
     assert _same_state({k: v.cpu().numpy() for k, v in got.items()}, want)
     assert (want["cp_rank"] < 0).any() and (want["cp_rank"] >= 0).any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nd", [3, 2])
+def test_gpu_bounded_search_keeps_exactly_the_points_within_the_bound(oracle, nd):
+    """axb_dcp_compute_bounded_closest_points == the unbounded first-visit search, kept only where the squared distance
+    is <= the bound (ties with the bound included)"""
+    import torch
+    from axom_b200.distributed_closest_point import _GpuBackend
+    parts, q = _cloud_parts(nd)
+    q = np.ascontiguousarray(np.concatenate([q, q[:3000] * 0.5 + 0.25]))
+    b = _GpuBackend(nd, 0)
+    b.set_object_points(parts[0], np.zeros(len(parts[0]), np.int32))
+    b.generate_bvh_tree()
+    qd = torch.from_numpy(q).cuda()
+    full = b.compute_local(5, qd)
+    v = full["cp_coords"] - qd
+    sq = torch.zeros(len(q), dtype=torch.float64, device="cuda")
+    for d in range(nd):
+        sq = sq + v[:, d] * v[:, d]
+    rng = np.random.default_rng(8)
+    factor = torch.from_numpy(rng.choice([0.5, 1.0, 1.0, 2.0], len(q))).cuda()  # below, AT, and above the true distance
+    bound = (sq * factor).contiguous()
+    got = b.compute_bounded(5, qd, bound)
+    keep = sq <= bound
+    assert bool(keep.any()) and bool((~keep).any())
+    assert torch.equal(got["cp_rank"], torch.where(keep, full["cp_rank"], torch.full_like(full["cp_rank"], -1)))
+    assert torch.equal(got["cp_index"][keep], full["cp_index"][keep]) and torch.equal(got["cp_coords"][keep], full["cp_coords"][keep])
+    assert torch.equal(got["cp_distance"][keep], full["cp_distance"][keep]) and bool((got["cp_index"][~keep] == -1).all())
