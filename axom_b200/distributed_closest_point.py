@@ -10,8 +10,8 @@ the whole machine; among equidistant points the first rank in ring order from th
 first point in the BVH's traversal order.
 
 On one NVSwitch box the ring of Conduit messages is replaced by collectives.  All query blocks and all object
-bounding boxes are all-gathered.  Phase 1: every query is searched, unbounded, by the rank whose object box is nearest
-to it; one MIN all-reduce turns the distances found into an upper bound for everybody.  Phase 2: every other rank
+bounding boxes are all-gathered.  Phase 1: every query is searched, unbounded, by the rank whose object box centre is
+nearest to it; one MIN all-reduce turns the distances found into an upper bound for everybody.  Phase 2: every other rank
 searches a query only if its own object box is within that bound (and within the distance threshold), and only for a
 point at least as near as the bound (axb_dcp_compute_bounded_closest_points) -- the ring prunes with the same two
 tests, per block instead of per query.  Phase 3: three all-reduces over all queries select the winner exactly as the
@@ -230,16 +230,24 @@ class DistributedClosestPoint:
         # squared distance from every query to every rank's object box (primal::squared_distance(Point, BoundingBox);
         # an empty rank is infinitely far).  Only used to order and to prune the searches, never in a result.
         INF = float("inf")
-        boxd = torch.empty((world, ntot), dtype=torch.float64, device=dev)
+        lo_m, hi_m = bbs[rank][0], bbs[rank][1]
+        if bool((lo_m > hi_m).any()):
+            mine = torch.full((ntot,), INF, dtype=torch.float64, device=dev)
+        else:
+            gap = torch.clamp(torch.maximum(lo_m - Q, Q - hi_m), min=0.0)
+            mine = (gap * gap).sum(dim=1)
+        # who searches a query first: the rank whose object box CENTRE is nearest (box distances tie at 0 wherever boxes
+        # overlap, which would pile those queries on the lowest rank).  Any choice is correct; this one is balanced.
+        cend = torch.empty((world, ntot), dtype=torch.float64, device=dev)
         for r in range(world):
             lo_r, hi_r = bbs[r][0], bbs[r][1]
             if bool((lo_r > hi_r).any()):
-                boxd[r] = INF
+                cend[r] = INF
             else:
-                gap = torch.clamp(torch.maximum(lo_r - Q, Q - hi_r), min=0.0)
-                boxd[r] = (gap * gap).sum(dim=1)
-        mine = boxd[rank]
-        nearest_rank = torch.argmin(boxd, dim=0)  # the rank whose object box is nearest: it searches the query first
+                dc = Q - 0.5 * (lo_r + hi_r)
+                cend[r] = (dc * dc).sum(dim=1)
+        nearest_rank = torch.argmin(cend, dim=0)
+        del cend
 
         def scatter_state(full, idx, st):
             for k in ("cp_index", "cp_domain_index", "cp_rank", "cp_coords", "cp_distance"):
@@ -258,7 +266,7 @@ class DistributedClosestPoint:
                 sq = sq + v[:, d] * v[:, d]
             return torch.where(st["cp_rank"] >= 0, sq, torch.full_like(sq, INF))
 
-        # ---- phase 1: each query is searched, unbounded, by the rank whose object box is nearest to it; the distance
+        # ---- phase 1: each query is searched, unbounded, by the rank whose object box centre is nearest; the distance
         # found there is an upper bound for everybody else (one MIN all-reduce) ----
         ph.mark("first search")
         idx1 = torch.nonzero((nearest_rank == rank) & (mine <= self._sq_threshold)).reshape(-1)
