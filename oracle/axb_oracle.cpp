@@ -8,12 +8,16 @@
 // the algorithm of
 //   spin::BVH<D,SEQ_EXEC,double>::initialize / findPoints / findBoundingBoxes / findRays
 //   quest::SignedDistance<3,SEQ_EXEC>::setMesh / computeDistances
+//   primal::intersect(Triangle3, Triangle3) and quest::findTriMeshIntersectionsBVH<SEQ_EXEC,double>   (8(f) rank 1)
+//   the per-rank step of quest::DistributedClosestPoint (generateBVHTreeImpl + computeLocalClosestPoints) (8(f) rank 3)
 // Every function cites the reference file:line (relative to /root/reference/src/axom)
 // it follows.  Parity is PINNED: tests/test_oracle_golden.py checks this file against
 // golden vectors produced by the real reference compiled from /root/reference
 // (oracle/build_ref.py -> oracle/_ref/libaxom_ref.so, generator tests/golden/make_golden.py)
 // and against the known-answer tests of the reference's own unit tests
-// (spin/tests/spin_bvh.cpp, quest/tests/quest_signed_distance*.cpp).
+// (spin/tests/spin_bvh.cpp, quest/tests/quest_signed_distance*.cpp, primal/tests/primal_intersect.cpp).
+// DistributedClosestPoint itself needs Conduit + MPI and cannot be built here: its per-rank step is pinned against the
+// real spin::BVH traversal driven with the reference's two lambdas (oracle/ref_driver.cpp: axref_dcp_*).
 //
 // Compile with -ffp-contract=off (no FMA), as the reference's own Release build does
 // on x86-64 baseline: the Morton quantisation and the closest-point region tests are

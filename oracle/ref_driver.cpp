@@ -6,6 +6,11 @@
 //   spin::BVH<D,SEQ_EXEC,double>           (spin/BVH.hpp:129)
 //   lbvh::build_radix_tree<SEQ_EXEC>       (spin/internal/linear_bvh/build_radix_tree.hpp:579)
 //   quest::SignedDistance<3,SEQ_EXEC>      (quest/SignedDistance.hpp:147)
+//   primal::intersect(Triangle3,Triangle3) (primal/operators/intersect.hpp:64), quest::findTriMeshIntersectionsBVH
+//   (quest/MeshTester.hpp:67), quest::STLReader, quest::weldTriMeshVertices (quest/MeshTester.cpp:218),
+//   quest::signed_distance_init / evaluate / finalize (quest/interface/signed_distance.hpp:117-319)
+// One exception, marked below: the two lambdas of DistributedClosestPointImpl::computeLocalClosestPoints are restated
+// here around the real BVH traverser, because the class itself needs Conduit + MPI.
 // The entry points mirror oracle/axb_oracle.cpp one to one (axref_* vs axo_*), so the same
 // Python wrapper drives both.
 #include "axom/config.hpp"
