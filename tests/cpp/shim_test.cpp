@@ -16,6 +16,7 @@
 #include "axom_b200/SignedDistance.hpp"
 #include "axom_b200/MeshTester.hpp"
 #include "axom_b200/signed_distance.hpp"
+#include "axom_b200/DistributedClosestPoint.hpp"
 
 namespace primal = axom::primal;
 using axom::IndexType;
@@ -245,6 +246,37 @@ static void test_mesh_tester()
   EXPECT(deg.size() == 1 && deg[0] == 3);
 }
 
+static void test_distributed_closest_point()
+{
+  // two "ranks" on one GPU: rank 0 owns the lattice points with even x, rank 1 those with odd x; a query block goes
+  // round the ring 0 -> 1 and ends with the nearest lattice point overall; an equidistant point on the later rank
+  // does not replace the earlier one (strict <, DistributedClosestPointImpl.hpp:1027)
+  using DCP = axom::quest::DistributedClosestPoint<3>;
+  std::vector<std::vector<Pt3>> dom0(2), dom1(1);
+  for(int i = 0; i < 6; ++i)
+    for(int j = 0; j < 6; ++j)
+      for(int k = 0; k < 6; ++k) (i % 2 == 0 ? dom0[k % 2] : dom1[0]).push_back(Pt3 {double(i), double(j), double(k)});
+  DCP r0(0, 0), r1(0, 1);
+  r0.setObjectMesh(dom0, {7, 9});
+  r1.setObjectMesh(dom1);
+  EXPECT(r0.generateBVHTree() && r1.generateBVHTree());
+  std::vector<Pt3> q = {Pt3 {2.1, 3.0, 4.0}, Pt3 {2.9, 3.0, 4.2}, Pt3 {2.5, 1.0, 1.0}, Pt3 {-3.0, 0.2, 0.1}};
+  const int n = (int)q.size();
+  std::vector<IndexType> idx(n), dom(n), rank(n);
+  std::vector<Pt3> cp(n);
+  std::vector<double> dist(n);
+  r0.computeLocalClosestPoints(q.data(), n, true, idx.data(), dom.data(), rank.data(), cp.data(), dist.data());
+  r1.computeLocalClosestPoints(q.data(), n, false, idx.data(), dom.data(), rank.data(), cp.data(), dist.data());
+  EXPECT(rank[0] == 0 && cp[0][0] == 2.0 && cp[0][1] == 3.0 && cp[0][2] == 4.0 && dom[0] == 7);  // k = 4 even -> domain id 7
+  EXPECT(rank[1] == 1 && cp[1][0] == 3.0 && cp[1][2] == 4.0 && dom[1] == 0);
+  EXPECT(rank[2] == 0 && cp[2][0] == 2.0 && dom[2] == 9);  // x = 2.5 ties x = 2 (rank 0) with x = 3 (rank 1): the earlier rank keeps it
+  EXPECT(rank[3] == 0 && cp[3][0] == 0.0 && cp[3][1] == 0.0 && cp[3][2] == 0.0);
+  // a threshold of 0.5 leaves the far query without an answer
+  r0.setDistanceThreshold(0.5);
+  r0.computeLocalClosestPoints(q.data(), n, true, idx.data(), dom.data(), rank.data(), cp.data(), dist.data());
+  EXPECT(rank[0] == 0 && rank[3] == -1 && idx[3] == -1 && cp[3][0] != cp[3][0]);
+}
+
 static bool g_quest_error = false;
 static void quest_error_recorder(const char*) { g_quest_error = true; }
 
@@ -322,6 +354,7 @@ int main(int argc, char** argv)
     test_signed_distance();
     test_mesh_tester();
     test_legacy_interface();
+    test_distributed_closest_point();
   }
   catch(const std::exception& e)
   {
