@@ -943,6 +943,59 @@ int64_t axo_bvh_count_points_omp(const AxoBvh* h, const double* pts_aos, int q, 
   return total;
 }
 
+// the same for the box-box and ray-box predicates (spin/BVH.hpp:558-560, :527-531)
+int64_t axo_bvh_count_boxes_omp(const AxoBvh* h, const double* boxes_aos, int q, int32_t* counts, int nthreads)
+{
+  if(h->ndims != 3) return -1;
+  const Bvh<3>& t = *(Bvh<3>*)h->impl;
+  int64_t total = 0;
+#ifdef _OPENMP
+  if(nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : total)
+  for(int i = 0; i < q; ++i)
+  {
+    const double* b = boxes_aos + (size_t)i * 6;
+    int c = 0;
+    traverse(
+      t,
+      [b](const Box<3>& bb) {  // bb1.intersectsWith(bb2), bb1 = query
+        for(int d = 0; d < 3; ++d)
+          if(!(b[3 + d] >= bb.lo[d] && b[d] <= bb.hi[d])) return false;
+        return true;
+      },
+      [&](int) { ++c; },
+      [](const Box<3>&, const Box<3>&) { return false; });
+    counts[i] = c;
+    total += c;
+  }
+  return total;
+}
+
+int64_t axo_bvh_count_rays_omp(const AxoBvh* h, const double* origins_aos, const double* dirs_aos, int q, int32_t* counts, int nthreads)
+{
+  if(h->ndims != 3) return -1;
+  const Bvh<3>& t = *(Bvh<3>*)h->impl;
+  const double tol = t.tol;
+  int64_t total = 0;
+#ifdef _OPENMP
+  if(nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : total)
+  for(int i = 0; i < q; ++i)
+  {
+    double o[3], d[3];
+    for(int k = 0; k < 3; ++k) o[k] = origins_aos[(size_t)i * 3 + k];
+    unit_vector<3>(dirs_aos + (size_t)i * 3, d);  // the Ray constructor normalises (Ray.hpp:122-127)
+    int c = 0;
+    traverse(
+      t, [&](const Box<3>& bb) { return ray_hits<3>(o, d, bb, tol); }, [&](int) { ++c; }, [](const Box<3>&, const Box<3>&) { return false; });
+    counts[i] = c;
+    total += c;
+  }
+  return total;
+}
+
 // quest/SignedDistance.hpp:427-504 (setMesh)
 static void* sd_create_impl(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, const int32_t* offsets,
                             int ncells, int nodes_per_cell, int watertight, int compute_sign)

@@ -66,6 +66,10 @@ class _Lib:
         if not self.f32:
             f("bvh_count_points_omp").restype = C.c_int64
             f("bvh_count_points_omp").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            f("bvh_count_boxes_omp").restype = C.c_int64
+            f("bvh_count_boxes_omp").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            f("bvh_count_rays_omp").restype = C.c_int64
+            f("bvh_count_rays_omp").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
             f("sd_create").restype = C.c_void_p
             f("sd_create").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
             f("sd_create_mixed").restype = C.c_void_p
@@ -166,6 +170,21 @@ class Bvh:
         pts = np.ascontiguousarray(pts, np.float64).reshape(-1, self.ndims)
         cnt = np.empty(pts.shape[0], np.int32)
         tot = self.L.fn("bvh_count_points_omp")(self.h, _ptr(pts), pts.shape[0], _ptr(cnt), int(nthreads))
+        return int(tot), cnt
+
+
+    def count_boxes_omp(self, boxes, nthreads=0):
+        b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 2 * self.ndims)
+        cnt = np.empty(b.shape[0], np.int32)
+        tot = self.L.fn("bvh_count_boxes_omp")(self.h, _ptr(b), b.shape[0], _ptr(cnt), int(nthreads))
+        return int(tot), cnt
+
+    def count_rays_omp(self, origins, directions, nthreads=0):
+        """directions are normalised, as the primal::Ray constructor does"""
+        o = np.ascontiguousarray(origins, np.float64).reshape(-1, self.ndims)
+        d = np.ascontiguousarray(directions, np.float64).reshape(-1, self.ndims)
+        cnt = np.empty(o.shape[0], np.int32)
+        tot = self.L.fn("bvh_count_rays_omp")(self.h, _ptr(o), _ptr(d), o.shape[0], _ptr(cnt), int(nthreads))
         return int(tot), cnt
 
 

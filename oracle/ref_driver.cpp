@@ -366,6 +366,61 @@ int64_t axref_bvh_count_points_omp(const AxrefBvh* h, const double* pts_aos, int
   return total;
 }
 
+// the same for findBoundingBoxes' and findRays' predicates (spin/BVH.hpp:558-560, :527-531)
+int64_t axref_bvh_count_boxes_omp(const AxrefBvh* h, const double* boxes_aos, int q, int32_t* counts, int nthreads)
+{
+  if(h->ndims != 3) return -1;
+  using BoxType = axom::primal::BoundingBox<double, 3>;
+  const auto trav = ((RefBvh<double, 3>*)h->impl)->bvh.getTraverser();
+  const BoxType* qb = reinterpret_cast<const BoxType*>(boxes_aos);
+  int64_t total = 0;
+#ifdef _OPENMP
+  if(nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : total)
+  for(int i = 0; i < q; ++i)
+  {
+    int c = 0;
+    auto leafAction = [&c](std::int32_t, const std::int32_t*) { ++c; };
+    auto pred = [](const BoxType& bb1, const BoxType& bb2) -> bool { return bb1.intersectsWith(bb2); };
+    trav.traverse_tree(qb[i], leafAction, pred);
+    counts[i] = c;
+    total += c;
+  }
+  return total;
+}
+
+int64_t axref_bvh_count_rays_omp(const AxrefBvh* h, const double* origins_aos, const double* dirs_aos, int q, int32_t* counts, int nthreads)
+{
+  if(h->ndims != 3) return -1;
+  using PointType = axom::primal::Point<double, 3>;
+  using VectorType = axom::primal::Vector<double, 3>;
+  using RayType = axom::primal::Ray<double, 3>;
+  using BoxType = axom::primal::BoundingBox<double, 3>;
+  const RefBvh<double, 3>& r = *(RefBvh<double, 3>*)h->impl;
+  const auto trav = r.bvh.getTraverser();
+  const double TOL = r.bvh.getTolerance();
+  int64_t total = 0;
+#ifdef _OPENMP
+  if(nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : total)
+  for(int i = 0; i < q; ++i)
+  {
+    int c = 0;
+    const RayType ray(PointType(origins_aos + (size_t)i * 3, 3), VectorType(dirs_aos + (size_t)i * 3, 3));  // normalises
+    auto leafAction = [&c](std::int32_t, const std::int32_t*) { ++c; };
+    auto pred = [TOL](const RayType& rr, const BoxType& bb) -> bool {
+      PointType tmp;
+      return axom::primal::detail::intersect_ray(rr, bb, tmp, TOL);
+    };
+    trav.traverse_tree(ray, leafAction, pred);
+    counts[i] = c;
+    total += c;
+  }
+  return total;
+}
+
 void* axref_sd_create(const double* x, const double* y, const double* z, int nnodes, const int32_t* conn, int ncells,
                       int nodes_per_cell, int watertight, int compute_sign)
 {

@@ -139,6 +139,16 @@ def test_port_equals_real_reference_on_random_inputs(oracle, have_ref):
     assert np.array_equal(ra[0], rb[0]) or True
     tot, cnt = oracle.Bvh(boxes, ndims=3, kind="reference").count_points_omp(synth.random_points(500, seed=n))
     assert tot == cnt.sum()
+    # the OpenMP-driven count baselines (points / boxes / rays) equal the find* counts, port and reference
+    boxes = synth.triangle_aabbs(4000, seed=77)
+    pts = synth.random_points(600, seed=5)
+    qb = synth.triangle_aabbs(500, seed=78)
+    o, d = synth.random_rays(400, seed=79, lo=-0.2, hi=1.2)
+    for kind in ("port", "reference"):
+        b = oracle.Bvh(boxes, ndims=3, kind=kind)
+        assert np.array_equal(b.count_points_omp(pts, 2)[1], b.find_points(pts)[1])
+        assert np.array_equal(b.count_boxes_omp(qb, 2)[1], b.find_boxes(qb)[1])
+        assert np.array_equal(b.count_rays_omp(o, 1.5 * d, 2)[1], b.find_rays(o, 1.5 * d, True)[1])
 
 
 @pytest.mark.parametrize("ndims", [3, 2])
