@@ -297,7 +297,7 @@ struct axb_bvh
   double bounds_hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
 
   DevBuf nodes, leaf_nodes, leaf_parent, node_range, keys_a, keys_b, state, sort_scratch, stage_in, agglo_slots, agglo_flags, agglo_open;
-  int agglo_block = 128;      // leaves per block of agglo_kernel (AXB_AGGLO_BLOCK = 128 | 256 | 512)
+  int agglo_block = 256;      // leaves per block of agglo_kernel (AXB_AGGLO_BLOCK = 128 | 256 | 512)
   bool legacy_build = false;  // AXB_BUILD_LEGACY=1: tree_kernel + refit_kernel instead of agglo_kernel
   unsigned long long* sorted_keys = nullptr;  // points into keys_a or keys_b
   DevBuf ref_inner_nodes, ref_children;       // reference-layout view, built lazily
@@ -426,12 +426,12 @@ int build_impl(axb_bvh* h, const axb_array_desc* boxes, int32_t num_boxes)
              h->nodes.as<Node<T, D>>(), h->leaf_nodes.as<int32_t>(), h->leaf_parent.as<int32_t>(), h->node_range.as<int2>(), \
              h->agglo_slots.as<AggloSlot<T, D>>(), h->agglo_flags.as<uint32_t>(), &st->agglo_mismatch,              \
              h->agglo_open.as<AggloOpen<T, D>>(), &st->agglo_open_count)
-    if(h->agglo_block == 256)
-      AXB_AGGLO(256);
+    if(h->agglo_block == 128)
+      AXB_AGGLO(128);
     else if(h->agglo_block == 512)
       AXB_AGGLO(512);
     else
-      AXB_AGGLO(128);
+      AXB_AGGLO(256);
 #undef AXB_AGGLO
     // the upper tree, from the subtrees the blocks left open (none when the whole tree fitted one block)
     AXB_LAUNCH(ctx, (agglo_upper_kernel<T, D>), capped_grid(std::max(n / 8, 128), 128, 16), 128, n, h->sorted_keys, h->nodes.as<Node<T, D>>(),

@@ -60,9 +60,9 @@ def test_build_legacy_path(oracle, monkeypatch):
         _check_build(oracle, boxes, nd)
 
 
-@pytest.mark.parametrize("block", [256, 512])
+@pytest.mark.parametrize("block", [128, 512])
 def test_build_fused_block_sizes(oracle, monkeypatch, block):
-    """the fused build with other leaves-per-block settings (default 128): in-block vs cross-block merges move"""
+    """the fused build with other leaves-per-block settings (default 256): in-block vs cross-block merges move"""
     monkeypatch.setenv("AXB_AGGLO_BLOCK", str(block))
     boxes = synth.triangle_aabbs(70001, seed=block)
     boxes[1000:1300] = boxes[1000]
