@@ -8,5 +8,6 @@ from .bvh import BVH, BVH_BUILD_OK, DEFAULT_SCALE_FACTOR  # noqa: F401
 from .signed_distance import SignedDistance  # noqa: F401
 from .distributed_closest_point import DistributedClosestPoint  # noqa: F401
 from .mesh_tester import MeshTester, findTriMeshIntersectionsBVH, intersect_triangles  # noqa: F401
+from .marching_cubes import MarchingCubes, MarchingCubesDataParallelism  # noqa: F401
 
 __version__ = "0.1.0"

@@ -93,6 +93,21 @@ SYMBOLS = [
     ("axb_dcp_get_bvh", C.c_int, [_P, _PP]),
     ("axb_dcp_compute_local_closest_points", C.c_int, [_P, C.c_int, _P, C.c_int32, C.c_int, _P, _P, _P, _P, _P, C.c_int]),
     ("axb_dcp_compute_bounded_closest_points", C.c_int, [_P, C.c_int, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    # quest::MarchingCubes
+    ("axb_mc_create", C.c_int, [_PP, C.c_int, C.c_int]),
+    ("axb_mc_destroy", C.c_int, [_P]),
+    ("axb_mc_set_stream", C.c_int, [_P, _P]),
+    ("axb_mc_set_mesh", C.c_int, [_P, _P, C.c_int32, C.c_int]),
+    ("axb_mc_set_mask_value", C.c_int, [_P, C.c_int]),
+    ("axb_mc_compute_isocontour", C.c_int, [_P, C.c_double]),
+    ("axb_mc_get_contour_cell_count", C.c_int, [_P, C.POINTER(C.c_int64)]),
+    ("axb_mc_get_contour_node_count", C.c_int, [_P, C.POINTER(C.c_int64)]),
+    ("axb_mc_get_contour_views", C.c_int, [_P, _PP, _PP, _PP, _PP]),
+    ("axb_mc_copy_contour", C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
+    ("axb_mc_clear_output", C.c_int, [_P]),
+    ("axb_mc_set_profiling", C.c_int, [_P, C.c_int]),
+    ("axb_mc_get_phase_ms", C.c_int, [_P, C.c_char_p, _PD]),
+    ("axb_mc_launch_count", C.c_int, [_P, C.POINTER(C.c_int64)]),
     # include/axb200_quest.h: the reference's legacy process-global C surface (wrapQUEST.h:83-127) + STL / welding
     ("QUEST_signed_distance_init_serial", C.c_int, [C.c_char_p]),
     ("QUEST_signed_distance_init_serial_bufferify", C.c_int, [C.c_char_p, C.c_int]),

@@ -17,6 +17,7 @@
 #include "sd_fast.cuh"
 #include "meshtester.cuh"
 #include "dcp.cuh"
+#include "mc.cuh"
 #include "traverse.cuh"
 
 namespace axb
@@ -1919,6 +1920,365 @@ static int dcp_compute(axb_dcp* h, int rank, const double* query_coords, int32_t
     if(cp_distance) AXB_CUDA_TRY(cudaMemcpyAsync(cp_distance, d_dist, db, cudaMemcpyDeviceToHost, ctx.stream));
   }
   return ctx.finish_call();
+}
+
+}  // extern "C"
+
+//==========================================================================================
+// quest::MarchingCubes
+//==========================================================================================
+
+struct axb_mc
+{
+  Ctx ctx;
+  int ndims = 3;
+  int mask_val = 1;
+  struct Domain
+  {
+    axb_mc_domain d;        // pointers resolved to device memory
+    int slowest[3] = {0, 1, 2};
+    long long case_stride[3] = {0, 0, 0};
+    long long num_cells = 0;
+    int num_tiles = 0;
+    DevBuf staged[5];       // host inputs: coords x/y/z, fcn, mask
+    DevBuf case_ids, tile_offsets;
+  };
+  std::vector<Domain> doms;
+  DevBuf totals;            // one int64 per domain
+  long long* h_totals = nullptr;
+  size_t h_totals_cap = 0;
+  long long facet_count = 0;
+  DevBuf node_ids, node_coords, parent_ids, domain_ids;
+  void release_domains()
+  {
+    for(auto& dm : doms)
+    {
+      for(auto& b : dm.staged) b.release(ctx.stream);
+      dm.case_ids.release(ctx.stream);
+      dm.tile_offsets.release(ctx.stream);
+    }
+    doms.clear();
+  }
+};
+
+namespace
+{
+// the span of elements a ghost-free strided view touches: 1 + sum (shape[d] - 1) * stride[d]
+// (extra = 1: nodal arrays, cell_shape + 1 entries per direction; extra = 0: cell-centred arrays)
+long long view_span(const int64_t* cell_shape, int extra, const int64_t* strides, int nd)
+{
+  long long span = 1;
+  for(int d = 0; d < nd; ++d) span += (long long)(cell_shape[d] + extra - 1) * strides[d];
+  return span;
+}
+
+template <int DIM>
+mc::DomainView<DIM> make_view(const axb_mc::Domain& dm)
+{
+  mc::DomainView<DIM> v;
+  for(int d = 0; d < DIM; ++d)
+  {
+    v.case_div[d] = mc::make_fastdiv((uint32_t)dm.case_stride[d]);
+    v.slowest[d] = dm.slowest[d];
+    v.fcn_stride[d] = dm.d.fcn_strides[d];
+    v.coords[d] = dm.d.coords[d];
+    v.coords_stride[d] = dm.d.coords_strides[d];
+    v.mask_stride[d] = dm.d.mask_strides[d];
+  }
+  v.fcn = dm.d.fcn;
+  v.mask = dm.d.mask;
+  v.num_cells = (uint32_t)dm.num_cells;
+  return v;
+}
+
+// grow a device array to new_bytes keeping its first keep_bytes (Array::resize keeps the earlier contour)
+int grow_preserve(Ctx& ctx, DevBuf& b, size_t keep_bytes, size_t new_bytes)
+{
+  if(new_bytes <= b.cap && b.p) return AXB_OK;
+  DevBuf nb;
+  AXB_TRY(nb.reserve(std::max(new_bytes, b.cap + b.cap / 2), ctx.stream));
+  if(keep_bytes && b.p) AXB_CUDA_TRY(cudaMemcpyAsync(nb.p, b.p, keep_bytes, cudaMemcpyDeviceToDevice, ctx.stream));
+  b.release(ctx.stream);
+  b = nb;
+  return AXB_OK;
+}
+
+template <int DIM>
+int mc_compute(axb_mc* h, double contour_val)
+{
+  Ctx& ctx = h->ctx;
+  const int nd = (int)h->doms.size();
+  if(nd == 0) return ctx.finish_call();
+  AXB_TRY(h->totals.reserve(sizeof(long long) * nd, ctx.stream));
+  if(h->h_totals_cap < (size_t)nd)
+  {
+    if(h->h_totals) cudaFreeHost(h->h_totals);
+    h->h_totals = nullptr;
+    AXB_CUDA_TRY(cudaMallocHost(&h->h_totals, sizeof(long long) * nd));
+    h->h_totals_cap = nd;
+  }
+  // markCrossings + scanCrossings for every domain (MarchingCubes.cpp:112-121)
+  for(int k = 0; k < nd; ++k)
+  {
+    axb_mc::Domain& dm = h->doms[k];
+    long long* tot = h->totals.as<long long>() + k;
+    if(dm.num_cells == 0)
+    {
+      AXB_CUDA_TRY(cudaMemsetAsync(tot, 0, sizeof(long long), ctx.stream));
+      continue;
+    }
+    const mc::DomainView<DIM> v = make_view<DIM>(dm);
+    {
+      ScopedPhase ph(ctx, "mc.mark");
+      AXB_LAUNCH(ctx, mc::mark_count_kernel<DIM>, dm.num_tiles, mc::kTileThreads, v, contour_val, h->mask_val, dm.case_ids.as<uint8_t>(),
+                 dm.tile_offsets.as<int32_t>());
+    }
+    {
+      ScopedPhase ph(ctx, "mc.scan");
+      AXB_LAUNCH(ctx, mc::scan_tiles_kernel, 1, mc::kScanThreads, dm.tile_offsets.as<int32_t>(), dm.num_tiles, tot);
+    }
+  }
+  AXB_CUDA_TRY(cudaMemcpyAsync(h->h_totals, h->totals.p, sizeof(long long) * nd, cudaMemcpyDeviceToHost, ctx.stream));
+  AXB_TRY(ctx.sync());  // the facet count sizes the output, as m_facetCount does in the reference
+  std::vector<long long> first(nd);
+  long long count = h->facet_count;
+  for(int k = 0; k < nd; ++k)
+  {
+    first[k] = count;  // m_facetIndexOffsets[d]
+    count += h->h_totals[k];
+  }
+  if(count * DIM > (long long)INT32_MAX)
+    return fail(AXB_ERR_OVERFLOW, "contour node count does not fit the reference's 32-bit IndexType");
+  // allocateOutputBuffers (:235-248)
+  const size_t old = (size_t)h->facet_count, now = (size_t)count;
+  AXB_TRY(grow_preserve(ctx, h->node_ids, old * DIM * sizeof(int32_t), now * DIM * sizeof(int32_t)));
+  AXB_TRY(grow_preserve(ctx, h->node_coords, old * DIM * DIM * sizeof(double), now * DIM * DIM * sizeof(double)));
+  AXB_TRY(grow_preserve(ctx, h->parent_ids, old * sizeof(int32_t), now * sizeof(int32_t)));
+  AXB_TRY(grow_preserve(ctx, h->domain_ids, old * sizeof(int32_t), now * sizeof(int32_t)));
+  // computeFacets per domain (:133-136)
+  for(int k = 0; k < nd; ++k)
+  {
+    axb_mc::Domain& dm = h->doms[k];
+    if(dm.num_cells == 0 || h->h_totals[k] == 0) continue;
+    const mc::DomainView<DIM> v = make_view<DIM>(dm);
+    ScopedPhase ph(ctx, "mc.emit");
+    AXB_LAUNCH(ctx, mc::emit_kernel<DIM>, dm.num_tiles, mc::kTileThreads, v, contour_val, dm.case_ids.as<uint8_t>(),
+               dm.tile_offsets.as<int32_t>(), (int32_t)first[k], (int32_t)dm.d.domain_id, h->node_ids.as<int32_t>(),
+               h->node_coords.as<double>(), h->parent_ids.as<int32_t>(), h->domain_ids.as<int32_t>());
+  }
+  h->facet_count = count;
+  return ctx.finish_call();
+}
+}  // namespace
+
+extern "C" {
+
+int axb_mc_create(axb_mc** out, int ndims, int device)
+{
+  if(!out) return fail(AXB_ERR_BAD_ARG, "null output handle");
+  *out = nullptr;
+  if(ndims != 2 && ndims != 3) return fail(AXB_ERR_BAD_ARG, "ndims must be 2 or 3");
+  axb_mc* h = new axb_mc();
+  h->ndims = ndims;
+  int st = h->ctx.init(device);
+  if(st != AXB_OK)
+  {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return AXB_OK;
+}
+
+int axb_mc_destroy(axb_mc* h)
+{
+  if(!h) return AXB_OK;
+  cudaSetDevice(h->ctx.device);
+  h->release_domains();
+  for(DevBuf* b : {&h->totals, &h->node_ids, &h->node_coords, &h->parent_ids, &h->domain_ids}) b->release(h->ctx.stream);
+  if(h->h_totals) cudaFreeHost(h->h_totals);
+  cudaStreamSynchronize(h->ctx.stream);
+  h->ctx.destroy();
+  delete h;
+  return AXB_OK;
+}
+
+int axb_mc_set_stream(axb_mc* h, void* s)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  AXB_TRY(h->ctx.sync());
+  if(h->ctx.own_stream && h->ctx.stream) cudaStreamDestroy(h->ctx.stream);
+  h->ctx.stream = (cudaStream_t)s;
+  h->ctx.own_stream = false;
+  return AXB_OK;
+}
+
+int axb_mc_set_mask_value(axb_mc* h, int mask_val)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  h->mask_val = mask_val;
+  return AXB_OK;
+}
+
+int axb_mc_set_mesh(axb_mc* h, const axb_mc_domain* domains, int32_t num_domains, int memspace)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(num_domains < 0 || (num_domains > 0 && !domains)) return fail(AXB_ERR_BAD_ARG, "bad domain list");
+  Ctx& ctx = h->ctx;
+  AXB_TRY(ctx.bind());
+  const int D = h->ndims;
+  // validate everything before touching the handle's state
+  for(int k = 0; k < num_domains; ++k)
+  {
+    const axb_mc_domain& in = domains[k];
+    long long cells = 1;
+    for(int d = 0; d < D; ++d)
+    {
+      if(in.cell_shape[d] < 0) return fail(AXB_ERR_BAD_ARG, "negative cell shape");
+      cells *= in.cell_shape[d];
+      if(cells > (long long)INT32_MAX) return fail(AXB_ERR_OVERFLOW, "cell count does not fit the reference's 32-bit IndexType");
+    }
+    if(cells == 0) continue;
+    if(!in.fcn) return fail(AXB_ERR_BAD_ARG, "null function field");
+    for(int d = 0; d < D; ++d)
+    {
+      if(!in.coords[d]) return fail(AXB_ERR_BAD_ARG, "null coordinate array");
+      if(in.fcn_strides[d] <= 0 || in.coords_strides[d] <= 0 || (in.mask && in.mask_strides[d] <= 0))
+        return fail(AXB_ERR_BAD_ARG, "strides must be positive");
+      for(int e = 0; e < d; ++e)
+        if(in.fcn_strides[d] == in.fcn_strides[e])
+          return fail(AXB_ERR_BAD_ARG, "non-unique function strides: impossible to compute index ordering (MDMapping)");
+    }
+  }
+  h->release_domains();
+  h->doms.resize(num_domains);
+  for(int k = 0; k < num_domains; ++k)
+  {
+    axb_mc::Domain& dm = h->doms[k];
+    dm.d = domains[k];
+    long long cells = 1;
+    for(int d = 0; d < D; ++d) cells *= dm.d.cell_shape[d];
+    dm.num_cells = cells;
+    if(cells == 0) continue;
+    // MDMapping::initializeStrides(strides, ROW) (core/MDMapping.hpp:255-275): directions by decreasing stride
+    for(int d = 0; d < D; ++d) dm.slowest[d] = d;
+    for(int s = 0; s < D; ++s)
+      for(int d = s; d < D; ++d)
+        if(dm.d.fcn_strides[dm.slowest[s]] < dm.d.fcn_strides[dm.slowest[d]]) std::swap(dm.slowest[s], dm.slowest[d]);
+    // MDMapping::initializeShape(bShape, slowestDirs) (:182-198): compact strides of the case-id array in that order
+    dm.case_stride[dm.slowest[D - 1]] = 1;
+    for(int s = D - 2; s >= 0; --s)
+      dm.case_stride[dm.slowest[s]] = dm.case_stride[dm.slowest[s + 1]] * dm.d.cell_shape[dm.slowest[s + 1]];
+    dm.num_tiles = (int)((cells + mc::kTileCells - 1) / mc::kTileCells);
+    const int ms = resolve_memspace(memspace, dm.d.fcn);
+    if(ms != AXB_MEM_HOST && ms != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+    if(ms == AXB_MEM_HOST)
+    {
+      const long long nspan = view_span(dm.d.cell_shape, 1, dm.d.coords_strides, D);
+      for(int d = 0; d < D; ++d)
+      {
+        AXB_TRY(dm.staged[d].reserve(sizeof(double) * nspan, ctx.stream));
+        AXB_CUDA_TRY(cudaMemcpyAsync(dm.staged[d].p, dm.d.coords[d], sizeof(double) * nspan, cudaMemcpyHostToDevice, ctx.stream));
+        dm.d.coords[d] = dm.staged[d].as<double>();
+      }
+      const long long fspan = view_span(dm.d.cell_shape, 1, dm.d.fcn_strides, D);
+      AXB_TRY(dm.staged[3].reserve(sizeof(double) * fspan, ctx.stream));
+      AXB_CUDA_TRY(cudaMemcpyAsync(dm.staged[3].p, dm.d.fcn, sizeof(double) * fspan, cudaMemcpyHostToDevice, ctx.stream));
+      dm.d.fcn = dm.staged[3].as<double>();
+      if(dm.d.mask)
+      {
+        const long long mspan = view_span(dm.d.cell_shape, 0, dm.d.mask_strides, D);
+        AXB_TRY(dm.staged[4].reserve(sizeof(int32_t) * mspan, ctx.stream));
+        AXB_CUDA_TRY(cudaMemcpyAsync(dm.staged[4].p, dm.d.mask, sizeof(int32_t) * mspan, cudaMemcpyHostToDevice, ctx.stream));
+        dm.d.mask = dm.staged[4].as<int32_t>();
+      }
+    }
+    AXB_TRY(dm.case_ids.reserve((size_t)dm.num_tiles * mc::kTileCells, ctx.stream));
+    AXB_TRY(dm.tile_offsets.reserve(sizeof(int32_t) * ((size_t)dm.num_tiles + 1), ctx.stream));
+  }
+  return ctx.sync();  // host inputs may be released by the caller on return
+}
+
+int axb_mc_compute_isocontour(axb_mc* h, double contour_val)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  AXB_TRY(h->ctx.bind());
+  return h->ndims == 2 ? mc_compute<2>(h, contour_val) : mc_compute<3>(h, contour_val);
+}
+
+int axb_mc_get_contour_cell_count(const axb_mc* h, int64_t* n)
+{
+  if(!h || !n) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *n = h->facet_count;
+  return AXB_OK;
+}
+
+int axb_mc_get_contour_node_count(const axb_mc* h, int64_t* n)
+{
+  if(!h || !n) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *n = h->doms.empty() ? 0 : h->facet_count * h->ndims;  // MarchingCubes.cpp:149-154
+  return AXB_OK;
+}
+
+int axb_mc_get_contour_views(axb_mc* h, const int32_t** ids, const double** coords, const int32_t** parents, const int32_t** domains)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  const bool any = h->facet_count > 0;
+  if(ids) *ids = any ? h->node_ids.as<int32_t>() : nullptr;
+  if(coords) *coords = any ? h->node_coords.as<double>() : nullptr;
+  if(parents) *parents = any ? h->parent_ids.as<int32_t>() : nullptr;
+  if(domains) *domains = any ? h->domain_ids.as<int32_t>() : nullptr;
+  return AXB_OK;
+}
+
+int axb_mc_copy_contour(axb_mc* h, int memspace, int32_t* ids, double* coords, int32_t* parents, int32_t* domains)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(memspace != AXB_MEM_HOST && memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "memspace must be HOST or DEVICE");
+  Ctx& ctx = h->ctx;
+  AXB_TRY(ctx.bind());
+  const size_t n = (size_t)h->facet_count, D = (size_t)h->ndims;
+  const cudaMemcpyKind kind = memspace == AXB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if(n)
+  {
+    if(ids) AXB_CUDA_TRY(cudaMemcpyAsync(ids, h->node_ids.p, n * D * sizeof(int32_t), kind, ctx.stream));
+    if(coords) AXB_CUDA_TRY(cudaMemcpyAsync(coords, h->node_coords.p, n * D * D * sizeof(double), kind, ctx.stream));
+    if(parents) AXB_CUDA_TRY(cudaMemcpyAsync(parents, h->parent_ids.p, n * sizeof(int32_t), kind, ctx.stream));
+    if(domains) AXB_CUDA_TRY(cudaMemcpyAsync(domains, h->domain_ids.p, n * sizeof(int32_t), kind, ctx.stream));
+  }
+  return ctx.sync();
+}
+
+int axb_mc_clear_output(axb_mc* h)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  h->facet_count = 0;  // buffers are kept for the next contour, like Array::clear()
+  return AXB_OK;
+}
+
+int axb_mc_set_profiling(axb_mc* h, int enabled)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  h->ctx.set_profiling(enabled != 0);
+  return AXB_OK;
+}
+
+int axb_mc_get_phase_ms(const axb_mc* hc, const char* name, double* ms)
+{
+  axb_mc* h = const_cast<axb_mc*>(hc);
+  if(!h || !name || !ms) return fail(AXB_ERR_BAD_ARG, "null argument");
+  h->ctx.resolve();
+  auto it = h->ctx.acc.find(name);
+  if(it == h->ctx.acc.end() || it->second.calls == 0) return fail(AXB_ERR_BAD_ARG, std::string("no timing recorded for phase ") + name);
+  *ms = it->second.sum / (double)it->second.calls;
+  return AXB_OK;
+}
+
+int axb_mc_launch_count(const axb_mc* h, int64_t* n)
+{
+  if(!h || !n) return fail(AXB_ERR_BAD_ARG, "null argument");
+  *n = h->ctx.launches;
+  return AXB_OK;
 }
 
 }  // extern "C"

@@ -194,3 +194,91 @@ def write_stl(path, x, y, z, conn, binary=False, jitter=None):
                 f.write("   vertex %.17g %.17g %.17g\n" % tuple(v))
             f.write("  endloop\n endfacet\n")
         f.write("endsolid synth\n")
+
+
+def blueprint_structured_mesh(cells, lo=-1.0, hi=1.0, domains=(1, 1, 1), fcn="dist", center=None, ghosts=0, order="column",
+                              mask_every=0, warp=0.0, domain_id_base=None):
+    """A multi-domain Blueprint-shaped structured mesh (dict tree, numpy leaves) like the one
+    quest/examples/quest_marching_cubes_example.cpp builds: `cells` = total cells per direction (2 or 3 entries) split into
+    `domains` blocks per direction; a nodal field `fcn` = distance to `center` (the example's "round" contour), so its
+    iso-contours are circles / spheres.  ghosts > 0 pads coordinates and fields with that many ghost layers on every side
+    (elements/dims/offsets+strides and fields/*/offsets+strides are then present); order = "column" (direction 0 fastest,
+    Conduit's default) or "row" (last direction fastest) applies to the fields; mask_every = m > 0 adds an int32 cell field
+    "mask" that is 1 except on every m-th cell (0 there); warp > 0 bends the grid (curvilinear coordinates)."""
+    nd = len(cells)
+    cells = [int(c) for c in cells]
+    nper = [int(d) for d in domains[:nd]]
+    center = [0.0] * nd if center is None else list(center)
+    lo = [lo] * nd if np.isscalar(lo) else list(lo)
+    hi = [hi] * nd if np.isscalar(hi) else list(hi)
+    # global node lattice (exactly as one global linspace, so domain boundaries share bit-identical coordinates)
+    axes = [np.linspace(lo[d], hi[d], cells[d] + 1) for d in range(nd)]
+    splits = [np.linspace(0, cells[d], nper[d] + 1).astype(int) for d in range(nd)]
+    mesh = {}
+    blocks = [(a, b, c) for c in range(nper[2] if nd == 3 else 1) for b in range(nper[1]) for a in range(nper[0])]
+    for pos, blk in enumerate(blocks):
+        c0 = [int(splits[d][blk[d]]) for d in range(nd)]
+        c1 = [int(splits[d][blk[d] + 1]) for d in range(nd)]
+        shape = [c1[d] - c0[d] for d in range(nd)]
+        g = int(ghosts)
+        # padded node index ranges (ghost nodes extrapolate the lattice)
+        idx = [np.arange(c0[d] - g, c1[d] + 1 + g) for d in range(nd)]
+        ax = []
+        for d in range(nd):
+            h = (hi[d] - lo[d]) / cells[d]
+            a = np.where((idx[d] >= 0) & (idx[d] <= cells[d]), axes[d][np.clip(idx[d], 0, cells[d])], lo[d] + idx[d] * h)
+            ax.append(a)
+        grids = np.meshgrid(*ax, indexing="ij")  # arrays indexed [i, j(, k)]
+        if warp:
+            w = [grids[d] + warp * np.sin(np.pi * grids[(d + 1) % nd]) for d in range(nd)]
+            grids = w
+        dist = np.sqrt(sum((grids[d] - center[d]) ** 2 for d in range(nd)))
+        pshape = [len(i) for i in idx]
+
+        def flat(a, how):
+            # "column": direction 0 fastest = Fortran order of the [i,j,k] array
+            return np.ascontiguousarray(a.ravel(order="F" if how == "column" else "C"))
+
+        def strides_of(shp, how):
+            s, t = [0] * nd, 1
+            for d in (range(nd) if how == "column" else range(nd - 1, -1, -1)):
+                s[d] = t
+                t *= shp[d]
+            return s
+        dims = {k: shape[d] for d, k in enumerate("ijk"[:nd])}
+        if g:
+            dims["offsets"] = np.array([g] * nd, np.int32)
+            dims["strides"] = np.array(strides_of(pshape, "column"), np.int32)
+        dom = {
+            "coordsets": {"coords": {"type": "explicit", "values": {k: flat(grids[d], "column") for d, k in enumerate("xyz"[:nd])}}},
+            "topologies": {"mesh": {"type": "structured", "coordset": "coords", "elements": {"dims": dims}}},
+            "fields": {fcn: {"association": "vertex", "topology": "mesh", "values": flat(dist, order)}},
+        }
+        if g or order != "column":
+            dom["fields"][fcn]["strides"] = np.array(strides_of(pshape, order), np.int32)
+            dom["fields"][fcn]["offsets"] = np.array([g] * nd, np.int32)
+        if mask_every:
+            cshape = [s + 2 * g for s in shape]
+            m = np.ones(cshape, np.int32)
+            m.ravel()[::mask_every] = 0
+            dom["fields"]["mask"] = {"association": "element", "topology": "mesh", "values": flat(m, order)}
+            if g or order != "column":
+                dom["fields"]["mask"]["strides"] = np.array(strides_of(cshape, order), np.int32)
+                dom["fields"]["mask"]["offsets"] = np.array([g] * nd, np.int32)
+        if domain_id_base is not None:
+            dom["state"] = {"domain_id": domain_id_base + pos}
+        mesh["domain_%06d" % pos] = dom
+    return mesh
+
+
+def blueprint_to_device(mesh, device=0):
+    """the same tree with every float64 / int32 data array moved to cuda:<device> (index vectors stay on the host)"""
+    import torch
+
+    def walk(n, key=None):
+        if isinstance(n, dict):
+            return {k: walk(v, k) for k, v in n.items()}
+        if isinstance(n, np.ndarray) and key not in ("offsets", "strides"):
+            return torch.from_numpy(n).to("cuda:%d" % device)
+        return n
+    return walk(mesh)

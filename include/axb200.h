@@ -13,6 +13,7 @@
  *   quest/interface/signed_distance.hpp:117-319  (process-global C-style API)
  *   quest/MeshTester.hpp:67-104             findTriMeshIntersectionsBVH (broad + narrow phase)
  *   primal/operators/intersect.hpp:64-71    intersect(Triangle3, Triangle3, includeBoundary, EPS)
+ *   quest/MarchingCubes.hpp:107-306         class MarchingCubes (iso-contour of a nodal field)
  *
  * Conventions
  *   - every function returns AXB_OK (0) or a negative axb_status; nothing throws or exits.
@@ -251,6 +252,54 @@ int axb_dcp_compute_local_closest_points(axb_dcp* dcp, int rank, const double* q
 int axb_dcp_compute_bounded_closest_points(axb_dcp* dcp, int rank, const double* query_coords_interleaved, int32_t num_queries,
                                            const double* bound_sq, int32_t* cp_index, int32_t* cp_domain_index, int32_t* cp_rank,
                                            double* cp_coords, double* cp_distance);
+
+/* ---- quest::MarchingCubes (the consumer of the distance field: iso-contour of a nodal function) ------------- */
+/* One structured domain, as MarchingCubesImpl::setDomain / setFunctionField see it through MeshViewUtil
+ * (quest/detail/MarchingCubesImpl.hpp:100-145, quest/MeshViewUtil.hpp:454-482,560-607): ghost-free views, i.e. every
+ * pointer addresses node (0,0[,0]) / cell (0,0[,0]) of the REAL mesh and strides are in elements (any ghost layers
+ * are skipped by the caller through the pointer, exactly what ArrayView::subspan(offsets, realShape) does).
+ * Entries [2] of the 3-vectors are ignored for ndims == 2. */
+typedef struct axb_mc_domain
+{
+  int64_t cell_shape[3];     /* topologies/<t>/elements/dims/{i,j,k}: real cells per direction            */
+  const double* coords[3];   /* coordsets/<c>/values/{x,y,z}: one array per direction (not interleaved)   */
+  int64_t coords_strides[3]; /* elements/dims/strides, default (1, ni+1, (ni+1)(nj+1))                    */
+  const double* fcn;         /* fields/<fcn>/values: the nodal function (double)                          */
+  int64_t fcn_strides[3];    /* fields/<fcn>/strides; their order fixes the parent-cell numbering         */
+  const int32_t* mask;       /* fields/<mask>/values (cell-centred int32) or NULL                         */
+  int64_t mask_strides[3];
+  int64_t domain_id;         /* state/domain_id, else the domain's position (MarchingCubesSingleDomain.cpp:168-176) */
+} axb_mc_domain;
+
+typedef struct axb_mc axb_mc;
+/* MarchingCubes(runtimePolicy, allocatorID, dataParallelism) (quest/MarchingCubes.hpp:112-114): ndims 2 | 3.  The two
+ * data-parallel variants of the reference give the same output; there is one device path. */
+int axb_mc_create(axb_mc** out, int ndims, int device);
+int axb_mc_destroy(axb_mc* mc);
+int axb_mc_set_stream(axb_mc* mc, void* cuda_stream);
+/* setMesh(bpMesh, topologyName, maskField) + setFunctionField(fcnField) (MarchingCubes.cpp:47-105).  Arrays in
+ * `memspace` HOST are staged to the device here (once); DEVICE arrays are used in place and must outlive the
+ * compute calls, like the Blueprint node the reference caches views of.  The function's strides must be unique
+ * (core/MDMapping.hpp:221-243 aborts otherwise) and the cell count must fit IndexType (int32). */
+int axb_mc_set_mesh(axb_mc* mc, const axb_mc_domain* domains, int32_t num_domains, int memspace);
+int axb_mc_set_mask_value(axb_mc* mc, int mask_val); /* setMaskValue, default 1 (quest/MarchingCubes.hpp:148) */
+/* computeIsocontour(contourVal) (MarchingCubes.cpp:107-147): ADDS the contour to what earlier calls produced. */
+int axb_mc_compute_isocontour(axb_mc* mc, double contour_val);
+int axb_mc_get_contour_cell_count(const axb_mc* mc, int64_t* n); /* getContourCellCount / getContourFacetCount */
+int axb_mc_get_contour_node_count(const axb_mc* mc, int64_t* n); /* getContourNodeCount = cells * ndims          */
+/* getContourFacetCorners [cells][ndims], getContourNodeCoords [nodes][ndims], getContourFacetParents [cells],
+ * getContourFacetDomainIds [cells] (quest/MarchingCubes.hpp:203-250): borrowed DEVICE views, valid until the next
+ * compute / clear / destroy.  Any output pointer may be NULL. */
+int axb_mc_get_contour_views(axb_mc* mc, const int32_t** facet_node_ids, const double** node_coords, const int32_t** facet_parent_ids,
+                             const int32_t** facet_domain_ids);
+/* the same four arrays copied into caller buffers in `memspace` (what populateContourMesh :169-233 appends to the
+ * mint::UnstructuredMesh: nodes, cells, cellIdField, domainIdField).  Any pointer may be NULL. */
+int axb_mc_copy_contour(axb_mc* mc, int memspace, int32_t* facet_node_ids, double* node_coords, int32_t* facet_parent_ids,
+                        int32_t* facet_domain_ids);
+int axb_mc_clear_output(axb_mc* mc); /* clearOutput (MarchingCubes.cpp:156-163) */
+int axb_mc_set_profiling(axb_mc* mc, int enabled); /* phases: "mc.mark", "mc.scan", "mc.emit" */
+int axb_mc_get_phase_ms(const axb_mc* mc, const char* phase, double* ms);
+int axb_mc_launch_count(const axb_mc* mc, int64_t* n);
 
 #ifdef __cplusplus
 }

@@ -169,8 +169,17 @@ def main():
     jobs.append((os.path.join(OUT, "gen", "About.cpp"), os.path.join(OBJ, "core_About.o")))
     driver = os.path.join(HERE, "ref_driver.cpp")
     jobs.append((driver, os.path.join(OBJ, "ref_driver.o")))
+    # quest::MarchingCubes needs Conduit, which is not in this image: the reference's two sources + our driver are compiled
+    # against the Node MOCK in oracle/conduit_stub/ (a named tree of external arrays; no algorithm), reference files unmodified
+    mc_flags = ("-DAXOM_USE_CONDUIT", "-I" + os.path.join(HERE, "conduit_stub"))
+    mc_jobs = [(os.path.join(SRC, "axom", "quest", "MarchingCubes.cpp"), os.path.join(OBJ, "quest_MarchingCubes.o"), mc_flags),
+               (os.path.join(SRC, "axom", "quest", "detail", "MarchingCubesSingleDomain.cpp"),
+                os.path.join(OBJ, "quest_detail_MarchingCubesSingleDomain.o"), mc_flags),
+               (os.path.join(HERE, "ref_mc_driver.cpp"), os.path.join(OBJ, "ref_mc_driver.o"), mc_flags)]
+    jobs = [j + ((),) for j in jobs] + mc_jobs
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         list(ex.map(lambda j: compile_one(*j), jobs))
+    jobs = [j[:2] for j in jobs]
     objs = [o for _, o in jobs]
     if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [CXX, "-shared", "-fopenmp", "-o", LIB] + objs

@@ -321,3 +321,122 @@ def ref_stl_read_weld(stl_file, eps=0.0):
 
 def max_threads(kind="port"):
     return lib(kind).fn("max_threads")()
+
+
+# ---- quest::MarchingCubes (mc_oracle.cpp) --------------------------------------------------------------------------
+_MC = os.path.join(HERE, "liboracle_mc.so")
+_mc_lib = None
+
+
+class _McDomain(C.Structure):  # mc_oracle.cpp: McDomain
+    _fields_ = [("cell_shape", C.c_int64 * 3), ("coords", C.c_void_p * 3), ("coords_strides", C.c_int64 * 3), ("fcn", C.c_void_p),
+                ("fcn_strides", C.c_int64 * 3), ("mask", C.c_void_p), ("mask_strides", C.c_int64 * 3), ("domain_id", C.c_int64)]
+
+
+def mc_lib():
+    global _mc_lib
+    if _mc_lib is None:
+        if not os.path.exists(_MC):
+            subprocess.check_call(["make", "-s", "-C", HERE, "liboracle_mc.so"])
+        L = C.CDLL(_MC)
+        L.axo_mc_compute_isocontour.restype = C.c_int64
+        L.axo_mc_compute_isocontour.argtypes = [C.c_int, C.c_void_p, C.c_int32, C.c_double, C.c_int, C.c_int64] + [C.POINTER(C.c_void_p)] * 4
+        L.axo_mc_free.argtypes = [C.c_void_p]
+        L.axo_mc_table.argtypes = [C.c_int] * 3
+        L.axo_mc_num_contour_cells.argtypes = [C.c_int] * 2
+        L.axo_mc_mapping.argtypes = [C.c_int] + [C.c_void_p] * 4
+        L.axo_mc_to_multi_index.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        _mc_lib = L
+    return _mc_lib
+
+
+def mc_isocontour(views, contour_val=0.0, mask_val=1, first_facet=0):
+    """the restated MarchingCubes::computeIsocontour over host views (objects with the attributes of
+    axom_b200.marching_cubes.DomainView holding numpy arrays).  -> (facetNodeIds (n, D), nodeCoords (n*D, D), parents, domainIds)
+    for the facets this call adds to a contour that already holds `first_facet` facets."""
+    L = mc_lib()
+    nd = len(views[0].cell_shape) if views else 3
+    arr = (_McDomain * max(len(views), 1))()
+    keep = []
+
+    def ptr(a, dt, off):
+        a = np.ascontiguousarray(a, dt).reshape(-1)
+        keep.append(a)
+        return a.ctypes.data + off * a.itemsize
+
+    for k, v in enumerate(views):
+        d = arr[k]
+        for i in range(3):
+            d.cell_shape[i] = v.cell_shape[i] if i < nd else 1
+            d.coords_strides[i] = v.coords_strides[i] if i < nd else 0
+            d.fcn_strides[i] = v.fcn_strides[i] if i < nd else 0
+            d.mask_strides[i] = v.mask_strides[i] if i < nd else 0
+            d.coords[i] = ptr(v.coords[i], np.float64, v.coords_offset) if i < nd else None
+        d.fcn = ptr(v.fcn, np.float64, v.fcn_offset)
+        d.mask = ptr(v.mask, np.int32, v.mask_offset) if v.mask is not None else None
+        d.domain_id = v.domain_id
+    p = [C.c_void_p() for _ in range(4)]
+    n = L.axo_mc_compute_isocontour(nd, arr, len(views), float(contour_val), int(mask_val), int(first_facet), *[C.byref(x) for x in p])
+
+    def take(q, count, ct, shape):
+        a = np.ctypeslib.as_array(C.cast(q, C.POINTER(ct)), shape=(max(count, 1),))[:count].copy().reshape(shape)
+        L.axo_mc_free(q)
+        return a
+    return (take(p[0], n * nd, C.c_int32, (n, nd)), take(p[1], n * nd * nd, C.c_double, (n * nd, nd)), take(p[2], n, C.c_int32, (n,)),
+            take(p[3], n, C.c_int32, (n,)))
+
+
+def ref_mc_isocontour(bpMesh, topology, fcn_field, mask_field="", mask_val=1, contour_vals=(0.0,), data_parallelism=0):
+    """the REAL reference's quest::MarchingCubes (seq policy) on a Blueprint-shaped dict tree (numpy leaves), through the
+    Conduit mock of oracle/conduit_stub.  Every contour value is computed in turn into the same (accumulating) contour mesh.
+    -> (facetNodeIds (n, D), nodeCoords (n*D, D), parents, domainIds)"""
+    L = lib("reference").lib
+    L.axref_node_new.restype = C.c_void_p
+    L.axref_node_free.argtypes = [C.c_void_p]
+    L.axref_node_set_string.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    L.axref_node_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+    L.axref_node_set_external.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]
+    L.axref_mc_run.restype = C.c_int64
+    L.axref_mc_run.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)] + \
+        [C.POINTER(C.c_void_p)] * 4
+    root = L.axref_node_new()
+    keep = []
+
+    def walk(n, path):
+        if isinstance(n, dict):
+            for k, v in n.items():
+                walk(v, path + "/" + k if path else k)
+        elif isinstance(n, str):
+            L.axref_node_set_string(root, path.encode(), n.encode())
+        elif isinstance(n, (int, np.integer)):
+            L.axref_node_set_int(root, path.encode(), int(n))
+        else:
+            a = np.ascontiguousarray(n)
+            kind = {np.dtype(np.int32): 0, np.dtype(np.int64): 1, np.dtype(np.float64): 2}[a.dtype]
+            keep.append(a)
+            L.axref_node_set_external(root, path.encode(), kind, a.ctypes.data, a.size)
+    walk(bpMesh, "")
+    cv = np.ascontiguousarray(contour_vals, np.float64)
+    p = [C.c_void_p() for _ in range(4)]
+    nd = C.c_int()
+    try:
+        n = L.axref_mc_run(root, topology.encode(), fcn_field.encode(), mask_field.encode(), int(mask_val), cv.ctypes.data, cv.size,
+                           int(data_parallelism), C.byref(nd), *[C.byref(x) for x in p])
+    finally:
+        L.axref_node_free(root)
+    D = nd.value
+
+    def take(q, count, ct, shape):
+        a = np.ctypeslib.as_array(C.cast(q, C.POINTER(ct)), shape=(max(count, 1),))[:count].copy().reshape(shape)
+        L.axref_free(q)
+        return a
+    return (take(p[0], n * D, C.c_int32, (n, D)), take(p[1], n * D * D, C.c_double, (n * D, D)), take(p[2], n, C.c_int32, (n,)),
+            take(p[3], n, C.c_int32, (n,)))
+
+
+def ref_mc_table(dim, case, edge):
+    return lib("reference").lib.axref_mc_table(dim, case, edge)
+
+
+def ref_mc_num_contour_cells(dim, case):
+    return lib("reference").lib.axref_mc_num_contour_cells(dim, case)
