@@ -1941,7 +1941,8 @@ struct axb_mc
     long long num_cells = 0;
     int num_tiles = 0;
     DevBuf staged[5];       // host inputs: coords x/y/z, fcn, mask
-    DevBuf case_ids, tile_offsets;
+    DevBuf case_ids, tile_offsets, lut;
+    uint8_t h_lut[256];     // compact corner bits -> case id for this domain's direction order (mark_rows_kernel)
   };
   std::vector<Domain> doms;
   DevBuf totals;            // one int64 per domain
@@ -1956,6 +1957,7 @@ struct axb_mc
       for(auto& b : dm.staged) b.release(ctx.stream);
       dm.case_ids.release(ctx.stream);
       dm.tile_offsets.release(ctx.stream);
+      dm.lut.release(ctx.stream);
     }
     doms.clear();
   }
@@ -1988,7 +1990,58 @@ mc::DomainView<DIM> make_view(const axb_mc::Domain& dm)
   v.fcn = dm.d.fcn;
   v.mask = dm.d.mask;
   v.num_cells = (uint32_t)dm.num_cells;
+  v.fast_extent = (uint32_t)dm.d.cell_shape[dm.slowest[DIM - 1]];
   return v;
+}
+
+template <int DIM>
+mc::RowView<DIM> make_row_view(const axb_mc::Domain& dm)
+{
+  mc::RowView<DIM> v;
+  const int F = dm.slowest[DIM - 1], M = dm.slowest[DIM - 2], S = dm.slowest[0];
+  const int dir[3] = {F, M, S};
+  for(int a = 0; a < 3; ++a)
+  {
+    const bool on = a < DIM;
+    v.fs[a] = on ? dm.d.fcn_strides[dir[a]] : 0;
+    v.ms[a] = on ? dm.d.mask_strides[dir[a]] : 0;
+  }
+  v.fcn = dm.d.fcn;
+  v.mask = dm.d.mask;
+  v.nf = (uint32_t)dm.d.cell_shape[F];
+  v.nm = (uint32_t)dm.d.cell_shape[M];
+  v.ns = DIM == 3 ? (uint32_t)dm.d.cell_shape[S] : 1u;
+  v.cs_m = (uint32_t)dm.case_stride[M];
+  v.cs_s = DIM == 3 ? (uint32_t)dm.case_stride[S] : 0u;
+  const uint32_t chunks = (v.nf + mc::kUnitCells - 1) / mc::kUnitCells, mgroups = (v.nm + mc::kRows - 1) / mc::kRows;
+  v.chunks = mc::make_fastdiv(chunks);
+  v.mgroups = mc::make_fastdiv(mgroups);
+  v.num_units = chunks * mgroups * v.ns;
+  v.lut = dm.lut.as<uint8_t>();
+  return v;
+}
+
+// compact corner bits of the row kernel -> the reference's case id: bit p of the code is the node at offsets
+// (df, dm[, ds]) along (F, M[, S]) with p = df * CB + dm * NS + ds
+template <int DIM>
+void build_row_lut(axb_mc::Domain& dm)
+{
+  constexpr int NS = DIM == 3 ? 2 : 1, CB = DIM == 3 ? 4 : 2;
+  const int F = dm.slowest[DIM - 1], M = dm.slowest[DIM - 2], S = dm.slowest[0];
+  for(int code = 0; code < 256; ++code)
+  {
+    int case_id = 0;
+    for(int p = 0; p < 2 * CB; ++p)
+    {
+      if(!((code >> p) & 1)) continue;
+      int o[DIM];
+      o[F] = p / CB;
+      o[M] = (p % CB) / NS;
+      if(DIM == 3) o[S] = p % NS;
+      case_id |= 1 << mc::corner_id<DIM>(o);
+    }
+    dm.h_lut[code] = (uint8_t)case_id;
+  }
 }
 
 // grow a device array to new_bytes keeping its first keep_bytes (Array::resize keeps the earlier contour)
@@ -2017,6 +2070,9 @@ int mc_compute(axb_mc* h, double contour_val)
     AXB_CUDA_TRY(cudaMallocHost(&h->h_totals, sizeof(long long) * nd));
     h->h_totals_cap = nd;
   }
+  // tuning / A-B switch: AXB_MC_MARK_PLAIN=1 selects the mark kernel without the lane-sharing of corner bits
+  const char* env = getenv("AXB_MC_MARK_PLAIN");
+  const bool plain_mark = env && env[0] == '1';
   // markCrossings + scanCrossings for every domain (MarchingCubes.cpp:112-121)
   for(int k = 0; k < nd; ++k)
   {
@@ -2030,7 +2086,19 @@ int mc_compute(axb_mc* h, double contour_val)
     const mc::DomainView<DIM> v = make_view<DIM>(dm);
     {
       ScopedPhase ph(ctx, "mc.mark");
-      AXB_LAUNCH(ctx, mc::mark_count_kernel<DIM>, dm.num_tiles, mc::kTileThreads, v, contour_val, h->mask_val, dm.case_ids.as<uint8_t>(),
+      if(plain_mark)
+        AXB_LAUNCH(ctx, mc::mark_plain_kernel<DIM>, dm.num_tiles, mc::kTileThreads, v, contour_val, h->mask_val, dm.case_ids.as<uint8_t>());
+      else
+      {
+        const mc::RowView<DIM> rv = make_row_view<DIM>(dm);
+        const int warps_per_block = mc::kTileThreads / 32;
+        const int grid = (int)std::min<long long>(((long long)rv.num_units + warps_per_block - 1) / warps_per_block, (long long)kNumSMsB200 * 8);
+        AXB_LAUNCH(ctx, mc::mark_rows_kernel<DIM>, grid, mc::kTileThreads, rv, contour_val, h->mask_val, dm.case_ids.as<uint8_t>());
+      }
+    }
+    {
+      ScopedPhase ph(ctx, "mc.count");
+      AXB_LAUNCH(ctx, mc::count_tiles_kernel<DIM>, dm.num_tiles, mc::kTileThreads, dm.case_ids.as<uint8_t>(), (uint32_t)dm.num_cells,
                  dm.tile_offsets.as<int32_t>());
     }
     {
@@ -2193,6 +2261,12 @@ int axb_mc_set_mesh(axb_mc* h, const axb_mc_domain* domains, int32_t num_domains
         dm.d.mask = dm.staged[4].as<int32_t>();
       }
     }
+    if(D == 2)
+      build_row_lut<2>(dm);
+    else
+      build_row_lut<3>(dm);
+    AXB_TRY(dm.lut.reserve(256, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(dm.lut.p, dm.h_lut, 256, cudaMemcpyHostToDevice, ctx.stream));
     AXB_TRY(dm.case_ids.reserve((size_t)dm.num_tiles * mc::kTileCells, ctx.stream));
     AXB_TRY(dm.tile_offsets.reserve(sizeof(int32_t) * ((size_t)dm.num_tiles + 1), ctx.stream));
   }

@@ -5,8 +5,8 @@
 // scan, a compaction pass, a second scan and the facet pass, keeping 2 + 4 + 4 + 4 bytes per CELL of scratch and
 // 2 + 4 + 4 + 4 bytes per crossing.  Here:
 //
-//   mark_count_kernel   one read of the nodal function (8 B / node, the compulsory traffic): case id per cell
-//                       (1 byte, kept) and the facet count of each 1024-cell tile
+//   mark_rows_kernel    one read of the nodal function (8 B / node, the compulsory traffic): case id per cell (1 byte, kept)
+//   count_tiles_kernel  facet count of each 1024-cell tile from the case bytes
 //   scan_tiles_kernel   exclusive scan of the tile counts (one block; 16 K tiles for 255^3 cells) + the domain total
 //   emit_kernel         tiles without facets exit on two loads; the others rescan their 1024 case bytes in shared
 //                       memory and write the facets of their crossing cells straight into the output arrays
@@ -76,6 +76,7 @@ struct DomainView
   const int32_t* mask;       // nullptr: no mask
   long long mask_stride[DIM];
   uint32_t num_cells;
+  uint32_t fast_extent;      // cells along the fastest direction slowest[DIM-1]: consecutive flat ids are neighbours along it
 };
 
 // MDMapping::toMultiIndex (core/MDMapping.hpp:361-371)
@@ -86,15 +87,17 @@ __device__ __forceinline__ void to_multi_index(const DomainView<DIM>& v, uint32_
   for(int s = 0; s < DIM; ++s)
   {
     const int dir = v.slowest[s];
-    const uint32_t q = fastdiv(flat, v.case_div[dir]);
-    idx[dir] = q;
-    flat -= q * v.case_div[dir].d;
+    const FastDiv f = v.case_div[dir];  // kernel-parameter (constant bank) indexing
+    const uint32_t q = fastdiv(flat, f);
+#pragma unroll
+    for(int d = 0; d < DIM; ++d) idx[d] = (d == dir) ? q : idx[d];
+    flat -= q * f.d;
   }
 }
 
 // corner c of a cell as a node offset from the cell's (i,j[,k]) node: MarchingCubesImpl.hpp:329-333 (2-D), :349-357 (3-D)
 template <int DIM>
-__device__ __forceinline__ void corner_offset(int c, int o[DIM])
+__host__ __device__ __forceinline__ void corner_offset(int c, int o[DIM])
 {
   if(DIM == 2)
   {
@@ -107,6 +110,24 @@ __device__ __forceinline__ void corner_offset(int c, int o[DIM])
     o[1] = ((c & 3) == 1 || (c & 3) == 2);
     o[DIM - 1] = (c >> 2);
   }
+}
+
+// a[i] for a runtime i without indexing the array dynamically (keeps small arrays in registers)
+template <int DIM, typename T>
+__device__ __forceinline__ T pick(const T a[DIM], int i)
+{
+  T r = a[0];
+#pragma unroll
+  for(int d = 1; d < DIM; ++d) r = (i == d) ? a[d] : r;
+  return r;
+}
+
+// inverse of corner_offset
+template <int DIM>
+__host__ __device__ __forceinline__ int corner_id(const int o[DIM])
+{
+  if(DIM == 2) return o[1] ? (o[0] ? 2 : 3) : (o[0] ? 1 : 0);
+  return (o[0] ? (o[1] ? 1 : 0) : (o[1] ? 2 : 3)) + 4 * o[DIM - 1];
 }
 
 template <int DIM>
@@ -127,27 +148,22 @@ __device__ __forceinline__ int used_entries(int case_id)
 //------------------------------------------------------------------------------------------
 // pass 1: computeCaseId (:306-361) for every cell + per-tile facet count (num_contour_cells, :815-843)
 //------------------------------------------------------------------------------------------
+// The plain form: one cell per thread-iteration, every lane loads all its corners.  Kept as the A/B reference of the row
+// kernel below (AXB_MC_MARK_PLAIN=1); ~100 instructions per cell, issue-bound.
 template <int DIM>
-__global__ void __launch_bounds__(kTileThreads) mark_count_kernel(DomainView<DIM> v, double contour_val, int mask_val,
-                                                                  uint8_t* __restrict__ case_ids, int32_t* __restrict__ tile_facets)
+__global__ void __launch_bounds__(kTileThreads) mark_plain_kernel(DomainView<DIM> v, double contour_val, int mask_val,
+                                                                  uint8_t* __restrict__ case_ids)
 {
-  constexpr int NCASE = DIM == 2 ? 16 : 256;
   constexpr int NCORNER = DIM == 2 ? 4 : 8;
-  __shared__ uint8_t s_nfacets[NCASE];
-  __shared__ int s_warp[kTileThreads / 32];
-  if(threadIdx.x < NCASE) s_nfacets[threadIdx.x] = (uint8_t)(used_entries<DIM>(threadIdx.x) / DIM);
-  __syncthreads();
-
   const uint32_t base = blockIdx.x * (uint32_t)kTileCells;
-  int nf = 0;
 #pragma unroll
   for(int r = 0; r < kCellsPerThread; ++r)
   {
-    const uint32_t n = base + r * kTileThreads + threadIdx.x;  // consecutive lanes -> consecutive cells of the fastest direction
-    int case_id = 0;                                           // m_caseIdsFlat.fill(0) (:162)
+    const uint32_t n = base + r * kTileThreads + threadIdx.x;
+    int case_id = 0;  // m_caseIdsFlat.fill(0) (:162)
     if(n < v.num_cells)
     {
-      uint32_t idx[DIM];
+      uint32_t idx[DIM] = {};
       to_multi_index<DIM>(v, n, idx);
       bool use_zone = true;
       if(v.mask)
@@ -155,7 +171,7 @@ __global__ void __launch_bounds__(kTileThreads) mark_count_kernel(DomainView<DIM
         long long mo = 0;
 #pragma unroll
         for(int d = 0; d < DIM; ++d) mo += (long long)idx[d] * v.mask_stride[d];
-        use_zone = (__ldg(v.mask + mo) == mask_val);
+        use_zone = (__ldg(v.mask + mo) == mask_val);  // :325 / :345
       }
       if(use_zone)
       {
@@ -174,10 +190,111 @@ __global__ void __launch_bounds__(kTileThreads) mark_count_kernel(DomainView<DIM
         }
       }
     }
-    // the tail of the last tile is written too (case 0), so pass 3 can read whole tiles
-    case_ids[n] = (uint8_t)case_id;
-    nf += s_nfacets[case_id];
+    case_ids[n] = (uint8_t)case_id;  // the tail of the last tile is written too (case 0): later passes read whole tiles
   }
+}
+
+// The row kernel (default).  Directions are named by speed in the case-id / function layout: F fastest, M middle, S slowest
+// (2-D: F, M).  A warp takes a unit of 31 cells along F x kRows cells along M at one S: lane l evaluates
+// (value >= contour_val) ONCE for the 2 * (kRows + 1) nodes of its node column f = 31 * chunk + l (10 loads for 4 cells
+// instead of 32), packs the bits into one word and hands them to lane l - 1 with a single shuffle; lane 31 only supplies
+// bits.  The 8 bits of a cell (4 own, 4 from the right-hand neighbour) index a 256-byte table, built on the host from the
+// direction permutation, that yields the reference's case id (corner numbering of :349-357).  Warps walk the units
+// grid-stride, so the table is staged in shared memory once per block.
+constexpr int kRows = 4;
+constexpr int kUnitCells = 31;
+
+template <int DIM>
+struct RowView
+{
+  const double* fcn;
+  const int32_t* mask;     // nullptr: no mask
+  long long fs[3];         // function strides along F, M, S
+  long long ms[3];         // mask strides along F, M, S
+  uint32_t cs_m, cs_s;     // case-id strides along M, S (F has stride 1)
+  uint32_t nf, nm, ns;     // cells along F, M, S (ns = 1 in 2-D)
+  FastDiv chunks, mgroups; // units per row / row groups per S
+  uint32_t num_units;
+  const uint8_t* lut;      // compact corner bits -> case id
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(kTileThreads) mark_rows_kernel(RowView<DIM> v, double contour_val, int mask_val,
+                                                                 uint8_t* __restrict__ case_ids)
+{
+  constexpr int NS = DIM == 3 ? 2 : 1;            // node planes a cell touches along S
+  constexpr int CB = DIM == 3 ? 4 : 2;            // corner bits a cell takes from one node column
+  __shared__ uint8_t s_lut[256];
+  if(threadIdx.x < 64) reinterpret_cast<uint32_t*>(s_lut)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(v.lut) + threadIdx.x);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for(uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < v.num_units; u += warps)
+  {
+    const uint32_t t = fastdiv(u, v.chunks);
+    const uint32_t chunk = u - t * v.chunks.d;
+    const uint32_t s = fastdiv(t, v.mgroups);
+    const uint32_t m0 = (t - s * v.mgroups.d) * kRows;
+    const uint32_t f = chunk * kUnitCells + lane;  // node column
+    // (value >= contour_val) for nodes (f, m0 + mm, s + ss): bit mm * NS + ss
+    uint32_t bits = 0;
+    if(f <= v.nf)
+    {
+      const double* p = v.fcn + (long long)f * v.fs[0] + (long long)m0 * v.fs[1] + (DIM == 3 ? (long long)s * v.fs[2] : 0);
+#pragma unroll
+      for(int mm = 0; mm <= kRows; ++mm)
+      {
+        if(m0 + mm <= v.nm)
+        {
+#pragma unroll
+          for(int ss = 0; ss < NS; ++ss)
+            if(__ldg(p + ss * v.fs[2]) >= contour_val) bits |= 1u << (mm * NS + ss);  // computeCrossingCase (:307-319)
+        }
+        p += v.fs[1];
+      }
+    }
+    const uint32_t right = __shfl_down_sync(0xffffffffu, bits, 1);
+    if(lane < kUnitCells && f < v.nf)
+    {
+      uint32_t flat = f + m0 * v.cs_m + (DIM == 3 ? s * v.cs_s : 0);
+      const int32_t* mp = v.mask ? v.mask + (long long)f * v.ms[0] + (long long)m0 * v.ms[1] + (DIM == 3 ? (long long)s * v.ms[2] : 0) : nullptr;
+#pragma unroll
+      for(int r = 0; r < kRows; ++r)
+      {
+        if(m0 + r < v.nm)
+        {
+          const uint32_t code = ((bits >> (r * NS)) & ((1u << CB) - 1)) | (((right >> (r * NS)) & ((1u << CB) - 1)) << CB);
+          int case_id = s_lut[code];
+          if(mp && __ldg(mp + r * v.ms[1]) != mask_val) case_id = 0;  // :325 / :345 (m_caseIdsFlat.fill(0), :162)
+          case_ids[flat] = (uint8_t)case_id;
+        }
+        flat += v.cs_m;
+      }
+    }
+  }
+}
+
+// per-tile facet count from the case ids (num_contour_cells, :815-843); also zeroes the tail of the last tile
+template <int DIM>
+__global__ void __launch_bounds__(kTileThreads) count_tiles_kernel(uint8_t* __restrict__ case_ids, uint32_t num_cells,
+                                                                   int32_t* __restrict__ tile_facets)
+{
+  constexpr int NCASE = DIM == 2 ? 16 : 256;
+  __shared__ uint8_t s_nfacets[NCASE];
+  __shared__ int s_warp[kTileThreads / 32];
+  if(threadIdx.x < NCASE) s_nfacets[threadIdx.x] = (uint8_t)(used_entries<DIM>(threadIdx.x) / DIM);
+  __syncthreads();
+  const uint32_t cell0 = blockIdx.x * (uint32_t)kTileCells + threadIdx.x * kCellsPerThread;
+  uchar4 c = *reinterpret_cast<const uchar4*>(case_ids + cell0);
+  if(cell0 + 3 >= num_cells)  // ragged tail: cells past the end count (and later read) as case 0
+  {
+    if(cell0 + 0 >= num_cells) c.x = 0;
+    if(cell0 + 1 >= num_cells) c.y = 0;
+    if(cell0 + 2 >= num_cells) c.z = 0;
+    c.w = 0;
+    *reinterpret_cast<uchar4*>(case_ids + cell0) = c;
+  }
+  int nf = s_nfacets[c.x] + s_nfacets[c.y] + s_nfacets[c.z] + s_nfacets[c.w];
 #pragma unroll
   for(int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
   if((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = nf;

@@ -17,6 +17,8 @@
 #include "axom_b200/MeshTester.hpp"
 #include "axom_b200/signed_distance.hpp"
 #include "axom_b200/DistributedClosestPoint.hpp"
+#include "axom_b200/MarchingCubes.hpp"
+#include <cmath>
 
 namespace primal = axom::primal;
 using axom::IndexType;
@@ -246,6 +248,57 @@ static void test_mesh_tester()
   EXPECT(deg.size() == 1 && deg[0] == 3);
 }
 
+static void test_marching_cubes()
+{
+  // quest/examples/quest_marching_cubes_example.cpp ("round" contour): nodal distance to the origin on [-1,1]^3, 8 cells
+  // per direction (h = 0.25), contour 0.5 -- the value is hit exactly on six axis nodes (the isNearlyEqual branches)
+  const int n = 8, nn = n + 1;
+  std::vector<double> x(nn * nn * nn), y(x.size()), z(x.size()), f(x.size());
+  for(int k = 0; k < nn; ++k)
+    for(int j = 0; j < nn; ++j)
+      for(int i = 0; i < nn; ++i)
+      {
+        const std::size_t o = (std::size_t)i + nn * ((std::size_t)j + nn * k);
+        x[o] = -1.0 + 0.25 * i;
+        y[o] = -1.0 + 0.25 * j;
+        z[o] = -1.0 + 0.25 * k;
+        f[o] = std::sqrt(x[o] * x[o] + y[o] * y[o] + z[o] * z[o]);
+      }
+  axom::quest::StructuredDomain dom;
+  dom.ndims = 3;
+  for(int d = 0; d < 3; ++d) dom.cellShape[d] = n;
+  dom.coords[0] = x.data();
+  dom.coords[1] = y.data();
+  dom.coords[2] = z.data();
+  dom.fcn = f.data();
+  dom.domainId = 7;
+  axom::quest::MarchingCubes mc;
+  mc.setMesh(&dom, 1);
+  mc.computeIsocontour(0.5);
+  const IndexType nc = mc.getContourCellCount();
+  EXPECT(nc > 0 && mc.getContourNodeCount() == 3 * nc && mc.getContourFacetCorners() != nullptr);
+  std::vector<double> xyz;
+  std::vector<IndexType> cells, parents, domains;
+  mc.populateContourMesh(xyz, cells, &parents, &domains);
+  bool ok = true;
+  for(IndexType c = 0; c < nc; ++c)
+  {
+    ok = ok && domains[c] == 7 && parents[c] >= 0 && parents[c] < n * n * n && (c == 0 || parents[c] >= parents[c - 1]);
+    for(int v = 0; v < 3; ++v)
+    {
+      ok = ok && cells[3 * c + v] == 3 * c + v;
+      const double* p = &xyz[3 * (std::size_t)(3 * c + v)];
+      const double r = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+      ok = ok && r <= 0.5 + 1e-12 && r >= 0.5 - 0.07;  // linear interpolation of a convex function stays inside the sphere
+    }
+  }
+  EXPECT(ok);
+  mc.computeIsocontour(0.25);  // accumulates
+  EXPECT(mc.getContourCellCount() > nc);
+  mc.clearOutput();
+  EXPECT(mc.getContourCellCount() == 0);
+}
+
 static void test_distributed_closest_point()
 {
   // two "ranks" on one GPU: rank 0 owns the lattice points with even x, rank 1 those with odd x; a query block goes
@@ -355,6 +408,7 @@ int main(int argc, char** argv)
     test_mesh_tester();
     test_legacy_interface();
     test_distributed_closest_point();
+    test_marching_cubes();
   }
   catch(const std::exception& e)
   {

@@ -90,6 +90,25 @@ def stl_weld_case(name):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+def mc_cases(name):
+    """quest::MarchingCubes (the real reference through oracle/ref_mc_driver.cpp) on tests/mc_cases.py"""
+    import hashlib
+    sys.path.insert(0, os.path.dirname(HERE))
+    import mc_cases
+    out = {}
+    for cname in mc_cases.CASES:
+        mesh, mask_field, mask_val, contours = mc_cases.build(cname)
+        ids, xyz, par, dom = O.ref_mc_isocontour(mesh, "mesh", "dist", mask_field, mask_val, contours, data_parallelism=1)
+        full = O.ref_mc_isocontour(mesh, "mesh", "dist", mask_field, mask_val, contours, data_parallelism=2)
+        assert all(np.array_equal(a, b) for a, b in zip((ids, xyz, par, dom), full)), cname  # hybridParallel == fullParallel
+        sha = hashlib.sha256()
+        for d in mesh.values():
+            sha.update(np.ascontiguousarray(d["fields"]["dist"]["values"]).tobytes())
+        out[cname + "/ids"], out[cname + "/xyz"], out[cname + "/par"], out[cname + "/dom"] = ids, xyz, par, dom
+        out[cname + "/fcn_sha"] = np.frombuffer(sha.digest(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 if __name__ == "__main__":
     assert O.have_reference(), "build the reference first: python oracle/build_ref.py"
     bvh_case("bvh3d_n600", 600, 3, 41)
@@ -97,4 +116,5 @@ if __name__ == "__main__":
     sd_case("sd_icosphere5", 5, 9)
     meshtester_case("meshtester_spheres")
     stl_weld_case("stl_weld")
+    mc_cases("mc_contours")
     print("golden fixtures written to", HERE)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Measure the BASELINE.json configs that are NOT bench.py's headline line (C1, C3, C4, C5).
 
-    python tools/bench_configs.py c1|c3|c4|c5 [--scale S] [--steps K]
+    python tools/bench_configs.py c1|c3|c3n|c4|c5|c5p|c2mc [--scale S] [--steps K]
     python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py c5      (N-way partitioned surface)
 
 Prints one JSON line per config with the same vocabulary as bench.py (value / roofline / cpu_baseline).
@@ -202,6 +202,73 @@ def c3n(args):
         "cpu_baseline": cpu}), flush=True)
 
 
+def c2mc(args):
+    """SURVEY 8(f) rank 4, the consumer of C2: quest::MarchingCubes iso-contour of the 256^3 nodal distance field
+    (255^3 = 16.6 M cells, a sphere of radius 0.5) with the field resident in HBM.  One pass = computeIsocontour on a cleared
+    contour: mark (one read of the field) + count + scan + emit.  Metric: cells/s.  The dominant kernel is mc.mark, HBM-bound:
+    algorithmic bytes = 8 B per node read once + 1 B per cell of case ids written.  CPU baseline: the REAL reference
+    (quest::MarchingCubes, seq policy, through the Conduit mock) on the same field -- its OpenMP policy needs RAJA, so 1 core."""
+    import torch
+    from axom_b200 import MarchingCubes, synth
+    from oracle import oracle as O
+    hbm, src = peaks()
+    n = max(8, int(round(255 * args.scale ** (1.0 / 3.0))))
+    mesh = synth.blueprint_structured_mesh(cells=(n, n, n), center=(0.01, -0.02, 0.03))
+    dmesh = synth.blueprint_to_device(mesh)
+    cells, nodes = n ** 3, (n + 1) ** 3
+    mc = MarchingCubes(device=0)
+    mc.setMesh(dmesh, "mesh")
+    mc.setFunctionField("dist")
+
+    def step():
+        mc.clearOutput()
+        mc.computeIsocontour(0.5)
+        return mc.getContourCellCount()
+
+    step()
+    mc.set_profiling(True)
+    # the field (134 MB) is larger than L2, so every pass reads it from HBM
+    ms, facets = device_time_ms(step, args.steps, warmup=3)
+    ph = {k: mc.phase_ms("mc." + k) for k in ("mark", "count", "scan", "emit")}
+    # end to end through the public API with HOST arrays: upload of coordinates + field, contour, contour back on the host
+    t0 = time.perf_counter()
+    mh = MarchingCubes(device=0)
+    mh.setMesh(mesh, "mesh")
+    mh.setFunctionField("dist")
+    mh.computeIsocontour(0.5)
+    host = mh.relinquishContourData()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    dev_out = [a.cpu().numpy() for a in mc.relinquishContourData(device_out=True)]
+    same = all(np.array_equal(a, b) for a, b in zip(host, dev_out))
+    alg_mark = 8 * nodes + cells
+    cpu = None
+    if not args.no_cpu:
+        kind_ref = "reference" if O.have_reference() else "port"
+        t0 = time.perf_counter()
+        if kind_ref == "reference":
+            ref = O.ref_mc_isocontour(mesh, "mesh", "dist", "", 1, (0.5,), 1)
+        else:
+            from axom_b200.marching_cubes import domain_views
+            ref = O.mc_isocontour(domain_views(mesh, "mesh", "dist"), 0.5)
+        dt = time.perf_counter() - t0
+        cpu = {"value": cells / dt, "unit": "cells/s", "cores": 1, "kind": kind_ref,
+               "sample": "the full %d^3-cell field, seq policy (hybridParallel), %.2f s" % (n, dt),
+               "matches_gpu_bit_exact": bool(all(a.size == b.size and np.array_equal(a.reshape(-1), b.reshape(-1)) for a, b in zip(ref, dev_out)))}
+    print(json.dumps({
+        "metric": "MarchingCubes cells/s (iso-contour of the nodal distance field)", "value": cells / (ms * 1e-3), "unit": "cells/s",
+        "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 consumer: %d^3 nodes, distance to a point, contour 0.5" % (n + 1), "cells": cells, "facets": int(facets),
+                   "l2_policy": "field larger than L2 (%d MB)" % (8 * nodes // 2 ** 20)},
+        "phases_ms_per_call": ph, "gpu_launches_per_step": 4, "mark_kernel": "plain" if os.environ.get("AXB_MC_MARK_PLAIN") == "1" else "rows",
+        "e2e": {"value": cells / (e2e_ms * 1e-3), "unit": "cells/s", "ms": e2e_ms, "h2d_bytes_per_step": int(4 * 8 * nodes),
+                "d2h_bytes_per_step": int(sum(a.nbytes for a in host)), "matches_device_path": bool(same),
+                "note": "host mesh -> upload of x, y, z and the field, contour, contour arrays back on the host (wall clock, first call)"},
+        "roofline": {"bound": "hbm", "kernel": "mc.mark", "achieved": alg_mark / (ph["mark"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": alg_mark / (ph["mark"] * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_launch": alg_mark, "peak_source": src,
+                     "traffic": None},
+        "cpu_baseline": cpu}), flush=True)
+
+
 def c5(args):
     """distributed closest point: surface split into G Morton ranges (one per rank; 8 sequential partitions
     when run on one GPU), unsigned distance per partition, elementwise MIN (NCCL all-reduce when G > 1)."""
@@ -360,7 +427,7 @@ def c5p(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["c1", "c3", "c3n", "c4", "c5", "c5p"])
+    ap.add_argument("config", choices=["c1", "c3", "c3n", "c4", "c5", "c5p", "c2mc"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
@@ -372,6 +439,8 @@ def main():
         c3n(args)
     elif args.config == "c5p":
         c5p(args)
+    elif args.config == "c2mc":
+        c2mc(args)
     else:
         find_config(args.config, args)
 
