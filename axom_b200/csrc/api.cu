@@ -2098,8 +2098,9 @@ int mc_compute(axb_mc* h, double contour_val)
     }
     {
       ScopedPhase ph(ctx, "mc.count");
-      AXB_LAUNCH(ctx, mc::count_tiles_kernel<DIM>, dm.num_tiles, mc::kTileThreads, dm.case_ids.as<uint8_t>(), (uint32_t)dm.num_cells,
-                 dm.tile_offsets.as<int32_t>());
+      const int count_grid = (int)std::min<long long>(((long long)dm.num_tiles + 7) / 8, (long long)kNumSMsB200 * 8);
+      AXB_LAUNCH(ctx, mc::count_tiles_kernel<DIM>, count_grid, mc::kTileThreads, dm.case_ids.as<uint8_t>(), (uint32_t)dm.num_cells,
+                 (uint32_t)dm.num_tiles, dm.tile_offsets.as<int32_t>());
     }
     {
       ScopedPhase ph(ctx, "mc.scan");

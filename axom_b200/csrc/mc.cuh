@@ -8,8 +8,8 @@
 //   mark_rows_kernel    one read of the nodal function (8 B / node, the compulsory traffic): case id per cell (1 byte, kept)
 //   count_tiles_kernel  facet count of each 1024-cell tile from the case bytes
 //   scan_tiles_kernel   exclusive scan of the tile counts (one block; 16 K tiles for 255^3 cells) + the domain total
-//   emit_kernel         tiles without facets exit on two loads; the others rescan their 1024 case bytes in shared
-//                       memory and write the facets of their crossing cells straight into the output arrays
+//   emit_kernel         tiles without facets exit on two loads; the others list their facets in shared memory and
+//                       spread the facet corners over all threads (one output node per thread)
 //
 // Output order is the reference's: facets sorted by the parent cell's flat index in the case-id array (whose stride
 // order follows the function's, MarchingCubesImpl.hpp:164-169), then by the case table's facet order; facet f owns
@@ -30,8 +30,16 @@ constexpr int kTileThreads = 256;
 constexpr int kCellsPerThread = 4;
 constexpr int kTileCells = kTileThreads * kCellsPerThread;  // 1024 cells of the flat case-id order per block
 
-__constant__ uint64_t c_cases3d[256] = {AXB_MC_CASES3D_WORDS};
-__constant__ uint16_t c_cases2d[16] = {AXB_MC_CASES2D_WORDS};
+// in global memory, read through the read-only path: the index differs per thread (a divergent index serialises on the
+// constant bank, L1 serves it in one pass per cache line)
+__device__ const uint64_t g_cases3d[256] = {AXB_MC_CASES3D_WORDS};
+__device__ const uint16_t g_cases2d[16] = {AXB_MC_CASES2D_WORDS};
+
+template <int DIM>
+__device__ __forceinline__ uint64_t case_word(int case_id)
+{
+  return DIM == 2 ? (uint64_t)__ldg(&g_cases2d[case_id]) : __ldg(&g_cases3d[case_id]);
+}
 
 // exact n / d for 0 <= n < 2^31 by multiply-high (d >= 1): the flat cell index is a 32-bit IndexType in the reference
 struct FastDiv
@@ -136,11 +144,11 @@ __device__ __forceinline__ int used_entries(int case_id)
   // entries are packed from nibble 0 and terminated by 0xF nibbles
   if(DIM == 2)
   {
-    const uint32_t w = c_cases2d[case_id];
+    const uint32_t w = (uint32_t)case_word<2>(case_id);
     const uint32_t m = w & (w >> 1) & (w >> 2) & (w >> 3) & 0x1111u;
     return m ? (__ffs(m) - 1) >> 2 : 4;
   }
-  const uint64_t w = c_cases3d[case_id];
+  const uint64_t w = case_word<3>(case_id);
   const uint64_t m = w & (w >> 1) & (w >> 2) & (w >> 3) & 0x1111111111111111ull;
   return (__ffsll((long long)m) - 1) >> 2;  // nibble 15 is never used, so m != 0
 }
@@ -196,12 +204,12 @@ __global__ void __launch_bounds__(kTileThreads) mark_plain_kernel(DomainView<DIM
 
 // The row kernel (default).  Directions are named by speed in the case-id / function layout: F fastest, M middle, S slowest
 // (2-D: F, M).  A warp takes a unit of 31 cells along F x kRows cells along M at one S: lane l evaluates
-// (value >= contour_val) ONCE for the 2 * (kRows + 1) nodes of its node column f = 31 * chunk + l (10 loads for 4 cells
-// instead of 32), packs the bits into one word and hands them to lane l - 1 with a single shuffle; lane 31 only supplies
+// (value >= contour_val) ONCE for the 2 * (kRows + 1) nodes of its node column f = 31 * chunk + l (18 loads for 8 cells
+// instead of 64), packs the bits into one word and hands them to lane l - 1 with a single shuffle; lane 31 only supplies
 // bits.  The 8 bits of a cell (4 own, 4 from the right-hand neighbour) index a 256-byte table, built on the host from the
 // direction permutation, that yields the reference's case id (corner numbering of :349-357).  Warps walk the units
 // grid-stride, so the table is staged in shared memory once per block.
-constexpr int kRows = 4;
+constexpr int kRows = 8;
 constexpr int kUnitCells = 31;
 
 template <int DIM>
@@ -274,37 +282,40 @@ __global__ void __launch_bounds__(kTileThreads) mark_rows_kernel(RowView<DIM> v,
   }
 }
 
-// per-tile facet count from the case ids (num_contour_cells, :815-843); also zeroes the tail of the last tile
+// per-tile facet count from the case ids (num_contour_cells, :815-843); also zeroes the tail of the last tile.
+// One warp per tile (8 x uint32 = 32 case bytes per lane), warps walk the tiles grid-stride.
 template <int DIM>
-__global__ void __launch_bounds__(kTileThreads) count_tiles_kernel(uint8_t* __restrict__ case_ids, uint32_t num_cells,
+__global__ void __launch_bounds__(kTileThreads) count_tiles_kernel(uint8_t* __restrict__ case_ids, uint32_t num_cells, uint32_t num_tiles,
                                                                    int32_t* __restrict__ tile_facets)
 {
   constexpr int NCASE = DIM == 2 ? 16 : 256;
   __shared__ uint8_t s_nfacets[NCASE];
-  __shared__ int s_warp[kTileThreads / 32];
   if(threadIdx.x < NCASE) s_nfacets[threadIdx.x] = (uint8_t)(used_entries<DIM>(threadIdx.x) / DIM);
   __syncthreads();
-  const uint32_t cell0 = blockIdx.x * (uint32_t)kTileCells + threadIdx.x * kCellsPerThread;
-  uchar4 c = *reinterpret_cast<const uchar4*>(case_ids + cell0);
-  if(cell0 + 3 >= num_cells)  // ragged tail: cells past the end count (and later read) as case 0
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for(uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < num_tiles; tile += warps)
   {
-    if(cell0 + 0 >= num_cells) c.x = 0;
-    if(cell0 + 1 >= num_cells) c.y = 0;
-    if(cell0 + 2 >= num_cells) c.z = 0;
-    c.w = 0;
-    *reinterpret_cast<uchar4*>(case_ids + cell0) = c;
-  }
-  int nf = s_nfacets[c.x] + s_nfacets[c.y] + s_nfacets[c.z] + s_nfacets[c.w];
+    const uint32_t tile0 = tile * (uint32_t)kTileCells;
+    int nf = 0;
 #pragma unroll
-  for(int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
-  if((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = nf;
-  __syncthreads();
-  if(threadIdx.x == 0)
-  {
-    int t = 0;
+    for(int k = 0; k < kTileCells / 128; ++k)
+    {
+      const uint32_t cell0 = tile0 + (k * 32 + lane) * 4;  // coalesced 128 B per warp load
+      uchar4 c = *reinterpret_cast<const uchar4*>(case_ids + cell0);
+      if(cell0 + 3 >= num_cells)  // ragged tail: cells past the end count (and are later read) as case 0
+      {
+        if(cell0 + 0 >= num_cells) c.x = 0;
+        if(cell0 + 1 >= num_cells) c.y = 0;
+        if(cell0 + 2 >= num_cells) c.z = 0;
+        c.w = 0;
+        *reinterpret_cast<uchar4*>(case_ids + cell0) = c;
+      }
+      nf += s_nfacets[c.x] + s_nfacets[c.y] + s_nfacets[c.z] + s_nfacets[c.w];
+    }
 #pragma unroll
-    for(int w = 0; w < kTileThreads / 32; ++w) t += s_warp[w];
-    tile_facets[blockIdx.x] = t;
+    for(int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
+    if(lane == 0) tile_facets[tile] = nf;
   }
 }
 
@@ -315,22 +326,37 @@ __global__ void __launch_bounds__(kTileThreads) count_tiles_kernel(uint8_t* __re
 constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __restrict__ tile_facets, int num_tiles, long long* __restrict__ total)
 {
-  __shared__ long long s_part[kScanThreads];
+  __shared__ long long s_warp[kScanThreads / 32];
   const int per = (num_tiles + kScanThreads - 1) / kScanThreads;
   const int lo = min(num_tiles, (int)threadIdx.x * per), hi = min(num_tiles, lo + per);
   long long sum = 0;
+#pragma unroll 8
   for(int i = lo; i < hi; ++i) sum += tile_facets[i];
-  s_part[threadIdx.x] = sum;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over the 1024 partial sums
-  for(int o = 1; o < kScanThreads; o <<= 1)
+  // block-wide inclusive scan of the per-thread sums: warp shuffles, then the 32 warp totals
+  long long incl = sum;
+#pragma unroll
+  for(int o = 1; o < 32; o <<= 1)
   {
-    const long long add = (int)threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
-    __syncthreads();
-    s_part[threadIdx.x] += add;
-    __syncthreads();
+    const long long u = __shfl_up_sync(0xffffffffu, incl, o);
+    if((int)(threadIdx.x & 31) >= o) incl += u;
   }
-  long long run = s_part[threadIdx.x] - sum;
+  if((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if(threadIdx.x < 32)
+  {
+    long long w = s_warp[threadIdx.x];
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+      const long long u = __shfl_up_sync(0xffffffffu, w, o);
+      if((int)threadIdx.x >= o) w += u;
+    }
+    s_warp[threadIdx.x] = w;  // inclusive totals of warps 0 .. threadIdx.x
+  }
+  __syncthreads();
+  const long long before_warp = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+  long long run = before_warp + incl - sum;
+#pragma unroll 8
   for(int i = lo; i < hi; ++i)
   {
     const int c = tile_facets[i];
@@ -340,40 +366,41 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __res
   }
   if(threadIdx.x == kScanThreads - 1)
   {
-    tile_facets[num_tiles] = (int32_t)s_part[threadIdx.x];
-    *total = s_part[threadIdx.x];
+    tile_facets[num_tiles] = (int32_t)s_warp[kScanThreads / 32 - 1];
+    *total = s_warp[kScanThreads / 32 - 1];
   }
 }
 
 //------------------------------------------------------------------------------------------
 // pass 3: computeFacets (:575-620) -- get_corner_coords_and_values (:644-703) + linear_interp (:706-807)
 //------------------------------------------------------------------------------------------
+// the two corners of cell edge `edge`: 2-D (:718-719), 3-D hex_edge_table (:766-770): base 0-1 1-2 2-3 3-0, top 4-5 5-6 6-7
+// 7-4, vertical 0-4 1-5 2-6 3-7
 template <int DIM>
-__device__ __forceinline__ void linear_interp(int edge, const double (*cc)[DIM], const double* cv, double contour_val, double* out)
+__device__ __forceinline__ void edge_corners(int edge, int& n1, int& n2)
 {
-  int n1, n2;
   if(DIM == 2)
   {
     n1 = edge;
     n2 = (edge == 3) ? 0 : edge + 1;
   }
+  else if(edge < 8)
+  {
+    n1 = edge;
+    n2 = (edge & 4) | ((edge + 1) & 3);
+  }
   else
   {
-    // hex_edge_table (:766-770): base 0-1 1-2 2-3 3-0, top 4-5 5-6 6-7 7-4, vertical 0-4 1-5 2-6 3-7
-    if(edge < 8)
-    {
-      n1 = edge;
-      n2 = (edge & 4) | ((edge + 1) & 3);
-    }
-    else
-    {
-      n1 = edge - 8;
-      n2 = edge - 4;
-    }
+    n1 = edge - 8;
+    n2 = edge - 4;
   }
-  const double f1 = cv[n1], f2 = cv[n2];
-  const double* p1 = cc[n1];
-  const double* p2 = cc[n2];
+}
+
+// linear_interp (:706-807) on the edge's two end nodes
+template <int DIM>
+__device__ __forceinline__ void linear_interp(double f1, double f2, const double p1[DIM], const double p2[DIM], double contour_val,
+                                              double out[DIM])
+{
   // isNearlyEqual(a, b) = abs(a - b) <= 1e-8 (core/utilities/Utilities.hpp:317-321)
   if(fabs(contour_val - f1) <= 1.0e-8 || fabs(f1 - f2) <= 1.0e-8)
   {
@@ -393,6 +420,11 @@ __device__ __forceinline__ void linear_interp(int edge, const double (*cc)[DIM],
   for(int d = 0; d < DIM; ++d) out[d] = p1[d] + w * (p2[d] - p1[d]);
 }
 
+// One block per 1024-cell tile.  Tiles without facets exit on two loads.  The others (a) scan their case bytes and list
+// their facets as (cell in tile, facet in cell) in shared memory, in output order, then (b) spread the facet CORNERS over
+// all threads: a thread owns one output node, reads only the two end nodes of its edge (2 values + 2 * DIM coordinates
+// instead of the cell's 8 * (1 + DIM)), interpolates and writes DIM consecutive doubles -- consecutive threads write
+// consecutive nodes.  The reference walks crossing cells instead (:590-619); the arithmetic per node is the same.
 template <int DIM>
 __global__ void __launch_bounds__(kTileThreads) emit_kernel(DomainView<DIM> v, double contour_val, const uint8_t* __restrict__ case_ids,
                                                             const int32_t* __restrict__ tile_offsets, int32_t facet_index_offset,
@@ -400,19 +432,25 @@ __global__ void __launch_bounds__(kTileThreads) emit_kernel(DomainView<DIM> v, d
                                                             double* __restrict__ facet_node_coords, int32_t* __restrict__ facet_parent_ids,
                                                             int32_t* __restrict__ facet_domain_ids)
 {
-  constexpr int NCORNER = DIM == 2 ? 4 : 8;
+  constexpr int MAXF = DIM == 2 ? 2 : 5;  // facets per cell
   const int32_t tile_first = tile_offsets[blockIdx.x];
-  if(tile_offsets[blockIdx.x + 1] == tile_first) return;  // no crossing in this tile (the common case)
+  const int tile_total = tile_offsets[blockIdx.x + 1] - tile_first;
+  if(tile_total == 0) return;  // no crossing in this tile (the common case)
 
   __shared__ int s_warp[kTileThreads / 32];
-  const uint32_t cell0 = blockIdx.x * (uint32_t)kTileCells + threadIdx.x * kCellsPerThread;  // 4 consecutive cells per thread
-  const uchar4 cs4 = *reinterpret_cast<const uchar4*>(case_ids + cell0);
+  __shared__ uint8_t s_case[kTileCells];
+  __shared__ uint16_t s_cell[kTileCells * MAXF];  // facet (in tile order) -> cell within the tile
+  __shared__ uint8_t s_fid[kTileCells * MAXF];    //                      -> facet within the cell
+  const uint32_t tile0 = blockIdx.x * (uint32_t)kTileCells;
+  const uint32_t local0 = threadIdx.x * kCellsPerThread;  // 4 consecutive cells per thread
+  const uchar4 cs4 = *reinterpret_cast<const uchar4*>(case_ids + tile0 + local0);
+  *reinterpret_cast<uchar4*>(s_case + local0) = cs4;
   const int cs[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
   int cnt[4], mine = 0;
 #pragma unroll
   for(int r = 0; r < 4; ++r)
   {
-    cnt[r] = used_entries<DIM>(cs[r]) / DIM;
+    cnt[r] = (cs[r] == 0) ? 0 : used_entries<DIM>(cs[r]) / DIM;
     mine += cnt[r];
   }
   // block-wide exclusive scan of `mine` in thread order = flat cell order
@@ -421,62 +459,71 @@ __global__ void __launch_bounds__(kTileThreads) emit_kernel(DomainView<DIM> v, d
   for(int o = 1; o < 32; o <<= 1)
   {
     const int u = __shfl_up_sync(0xffffffffu, incl, o);
-    if((threadIdx.x & 31) >= o) incl += u;
+    if((int)(threadIdx.x & 31) >= o) incl += u;
   }
   if((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
   __syncthreads();
-  int before = 0;
-  for(int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s_warp[w];
-  int facet = facet_index_offset + tile_first + before + incl - mine;  // firstFacetId (:599)
-
-#pragma unroll 1
+  int pos = incl - mine;
+  for(int w = 0; w < (int)(threadIdx.x >> 5); ++w) pos += s_warp[w];
+#pragma unroll
   for(int r = 0; r < 4; ++r)
+    for(int f = 0; f < cnt[r]; ++f, ++pos)
+    {
+      s_cell[pos] = (uint16_t)(local0 + r);
+      s_fid[pos] = (uint8_t)f;
+    }
+  __syncthreads();
+
+  const int first = facet_index_offset + tile_first;  // firstFacetId of the tile's first crossing (:599)
+  for(int q = threadIdx.x; q < tile_total * DIM; q += kTileThreads)
   {
-    if(cnt[r] == 0) continue;
-    const uint32_t parent = cell0 + r;
-    uint32_t idx[DIM];
-    to_multi_index<DIM>(v, parent, idx);
-    long long fo = 0, co = 0;
-#pragma unroll
-    for(int d = 0; d < DIM; ++d)
-    {
-      fo += (long long)idx[d] * v.fcn_stride[d];
-      co += (long long)idx[d] * v.coords_stride[d];
-    }
-    double cc[NCORNER][DIM], cv[NCORNER];
-#pragma unroll
-    for(int c = 0; c < NCORNER; ++c)
-    {
-      int o[DIM];
-      corner_offset<DIM>(c, o);
-      long long f = fo, x = co;
-#pragma unroll
-      for(int d = 0; d < DIM; ++d)
-      {
-        f += o[d] ? v.fcn_stride[d] : 0;
-        x += o[d] ? v.coords_stride[d] : 0;
-      }
-      cv[c] = __ldg(v.fcn + f);
-#pragma unroll
-      for(int d = 0; d < DIM; ++d) cc[c][d] = __ldg(v.coords[d] + x);
-    }
-    const uint64_t word = DIM == 2 ? (uint64_t)c_cases2d[cs[r]] : c_cases3d[cs[r]];
-    for(int f = 0; f < cnt[r]; ++f, ++facet)
+    const int fl = q / DIM, d = q - fl * DIM;  // facet within the tile, corner within the facet
+    const uint32_t local = s_cell[fl];
+    const int f = s_fid[fl];
+    const uint32_t parent = tile0 + local;
+    const int facet = first + fl;
+    const int corner = facet * DIM + d;  // newCornerId (:610)
+    if(d == 0)
     {
       facet_parent_ids[facet] = (int32_t)parent;
       facet_domain_ids[facet] = domain_id;  // m_facetDomainIds.fill (MarchingCubes.cpp:140-146)
-#pragma unroll
-      for(int d = 0; d < DIM; ++d)
-      {
-        const int corner = facet * DIM + d;
-        facet_node_ids[corner] = corner;
-        const int edge = (int)((word >> (4 * (f * DIM + d))) & 0xF);  // cases_table(caseId, fId * DIM + d)
-        double p[DIM];
-        linear_interp<DIM>(edge, cc, cv, contour_val, p);
-#pragma unroll
-        for(int k = 0; k < DIM; ++k) facet_node_coords[(long long)corner * DIM + k] = p[k];
-      }
     }
+    facet_node_ids[corner] = corner;
+    const int edge = (int)((case_word<DIM>(s_case[local]) >> (4 * (f * DIM + d))) & 0xF);  // cases_table(caseId, fId * DIM + d)
+    int n1, n2;
+    edge_corners<DIM>(edge, n1, n2);
+    uint32_t idx[DIM] = {};
+    to_multi_index<DIM>(v, parent, idx);
+    long long fo = 0, co = 0;
+#pragma unroll
+    for(int k = 0; k < DIM; ++k)
+    {
+      fo += (long long)idx[k] * v.fcn_stride[k];
+      co += (long long)idx[k] * v.coords_stride[k];
+    }
+    int o1[DIM], o2[DIM];
+    corner_offset<DIM>(n1, o1);
+    corner_offset<DIM>(n2, o2);
+    long long f1o = fo, f2o = fo, c1o = co, c2o = co;
+#pragma unroll
+    for(int k = 0; k < DIM; ++k)
+    {
+      f1o += o1[k] ? v.fcn_stride[k] : 0;
+      f2o += o2[k] ? v.fcn_stride[k] : 0;
+      c1o += o1[k] ? v.coords_stride[k] : 0;
+      c2o += o2[k] ? v.coords_stride[k] : 0;
+    }
+    const double f1 = __ldg(v.fcn + f1o), f2 = __ldg(v.fcn + f2o);
+    double p1[DIM], p2[DIM], out[DIM];
+#pragma unroll
+    for(int k = 0; k < DIM; ++k)
+    {
+      p1[k] = __ldg(v.coords[k] + c1o);
+      p2[k] = __ldg(v.coords[k] + c2o);
+    }
+    linear_interp<DIM>(f1, f2, p1, p2, contour_val, out);
+#pragma unroll
+    for(int k = 0; k < DIM; ++k) facet_node_coords[(long long)corner * DIM + k] = out[k];
   }
 }
 
