@@ -1941,11 +1941,11 @@ struct axb_mc
     long long num_cells = 0;
     int num_tiles = 0;
     DevBuf staged[5];       // host inputs: coords x/y/z, fcn, mask
-    DevBuf case_ids, tile_offsets, lut;
+    DevBuf case_ids, tile_offsets, active_tiles, lut;
     uint8_t h_lut[256];     // compact corner bits -> case id for this domain's direction order (mark_rows_kernel)
   };
   std::vector<Domain> doms;
-  DevBuf totals;            // one int64 per domain
+  DevBuf totals;            // two int64 per domain: facets, active tiles
   long long* h_totals = nullptr;
   size_t h_totals_cap = 0;
   long long facet_count = 0;
@@ -1958,6 +1958,7 @@ struct axb_mc
       dm.case_ids.release(ctx.stream);
       dm.tile_offsets.release(ctx.stream);
       dm.lut.release(ctx.stream);
+      dm.active_tiles.release(ctx.stream);
     }
     doms.clear();
   }
@@ -2062,12 +2063,12 @@ int mc_compute(axb_mc* h, double contour_val)
   Ctx& ctx = h->ctx;
   const int nd = (int)h->doms.size();
   if(nd == 0) return ctx.finish_call();
-  AXB_TRY(h->totals.reserve(sizeof(long long) * nd, ctx.stream));
+  AXB_TRY(h->totals.reserve(sizeof(long long) * 2 * nd, ctx.stream));
   if(h->h_totals_cap < (size_t)nd)
   {
     if(h->h_totals) cudaFreeHost(h->h_totals);
     h->h_totals = nullptr;
-    AXB_CUDA_TRY(cudaMallocHost(&h->h_totals, sizeof(long long) * nd));
+    AXB_CUDA_TRY(cudaMallocHost(&h->h_totals, sizeof(long long) * 2 * nd));
     h->h_totals_cap = nd;
   }
   // tuning / A-B switch: AXB_MC_MARK_PLAIN=1 selects the mark kernel without the lane-sharing of corner bits
@@ -2077,10 +2078,10 @@ int mc_compute(axb_mc* h, double contour_val)
   for(int k = 0; k < nd; ++k)
   {
     axb_mc::Domain& dm = h->doms[k];
-    long long* tot = h->totals.as<long long>() + k;
+    long long* tot = h->totals.as<long long>() + 2 * k;
     if(dm.num_cells == 0)
     {
-      AXB_CUDA_TRY(cudaMemsetAsync(tot, 0, sizeof(long long), ctx.stream));
+      AXB_CUDA_TRY(cudaMemsetAsync(tot, 0, 2 * sizeof(long long), ctx.stream));
       continue;
     }
     const mc::DomainView<DIM> v = make_view<DIM>(dm);
@@ -2093,7 +2094,10 @@ int mc_compute(axb_mc* h, double contour_val)
         const mc::RowView<DIM> rv = make_row_view<DIM>(dm);
         const int warps_per_block = mc::kTileThreads / 32;
         const int grid = (int)std::min<long long>(((long long)rv.num_units + warps_per_block - 1) / warps_per_block, (long long)kNumSMsB200 * 8);
-        AXB_LAUNCH(ctx, mc::mark_rows_kernel<DIM>, grid, mc::kTileThreads, rv, contour_val, h->mask_val, dm.case_ids.as<uint8_t>());
+        if(rv.mask)
+          AXB_LAUNCH(ctx, (mc::mark_rows_kernel<DIM, true>), grid, mc::kTileThreads, rv, contour_val, h->mask_val, dm.case_ids.as<uint8_t>());
+        else
+          AXB_LAUNCH(ctx, (mc::mark_rows_kernel<DIM, false>), grid, mc::kTileThreads, rv, contour_val, h->mask_val, dm.case_ids.as<uint8_t>());
       }
     }
     {
@@ -2104,17 +2108,17 @@ int mc_compute(axb_mc* h, double contour_val)
     }
     {
       ScopedPhase ph(ctx, "mc.scan");
-      AXB_LAUNCH(ctx, mc::scan_tiles_kernel, 1, mc::kScanThreads, dm.tile_offsets.as<int32_t>(), dm.num_tiles, tot);
+      AXB_LAUNCH(ctx, mc::scan_tiles_kernel, 1, mc::kScanThreads, dm.tile_offsets.as<int32_t>(), dm.num_tiles, tot, dm.active_tiles.as<int32_t>());
     }
   }
-  AXB_CUDA_TRY(cudaMemcpyAsync(h->h_totals, h->totals.p, sizeof(long long) * nd, cudaMemcpyDeviceToHost, ctx.stream));
+  AXB_CUDA_TRY(cudaMemcpyAsync(h->h_totals, h->totals.p, sizeof(long long) * 2 * nd, cudaMemcpyDeviceToHost, ctx.stream));
   AXB_TRY(ctx.sync());  // the facet count sizes the output, as m_facetCount does in the reference
   std::vector<long long> first(nd);
   long long count = h->facet_count;
   for(int k = 0; k < nd; ++k)
   {
     first[k] = count;  // m_facetIndexOffsets[d]
-    count += h->h_totals[k];
+    count += h->h_totals[2 * k];
   }
   if(count * DIM > (long long)INT32_MAX)
     return fail(AXB_ERR_OVERFLOW, "contour node count does not fit the reference's 32-bit IndexType");
@@ -2128,11 +2132,11 @@ int mc_compute(axb_mc* h, double contour_val)
   for(int k = 0; k < nd; ++k)
   {
     axb_mc::Domain& dm = h->doms[k];
-    if(dm.num_cells == 0 || h->h_totals[k] == 0) continue;
+    if(dm.num_cells == 0 || h->h_totals[2 * k] == 0) continue;
     const mc::DomainView<DIM> v = make_view<DIM>(dm);
     ScopedPhase ph(ctx, "mc.emit");
-    AXB_LAUNCH(ctx, mc::emit_kernel<DIM>, dm.num_tiles, mc::kTileThreads, v, contour_val, dm.case_ids.as<uint8_t>(),
-               dm.tile_offsets.as<int32_t>(), (int32_t)first[k], (int32_t)dm.d.domain_id, h->node_ids.as<int32_t>(),
+    AXB_LAUNCH(ctx, mc::emit_kernel<DIM>, (int)h->h_totals[2 * k + 1], mc::kTileThreads, v, contour_val, dm.case_ids.as<uint8_t>(),
+               dm.tile_offsets.as<int32_t>(), dm.active_tiles.as<int32_t>(), (int32_t)first[k], (int32_t)dm.d.domain_id, h->node_ids.as<int32_t>(),
                h->node_coords.as<double>(), h->parent_ids.as<int32_t>(), h->domain_ids.as<int32_t>());
   }
   h->facet_count = count;
@@ -2270,6 +2274,7 @@ int axb_mc_set_mesh(axb_mc* h, const axb_mc_domain* domains, int32_t num_domains
     AXB_CUDA_TRY(cudaMemcpyAsync(dm.lut.p, dm.h_lut, 256, cudaMemcpyHostToDevice, ctx.stream));
     AXB_TRY(dm.case_ids.reserve((size_t)dm.num_tiles * mc::kTileCells, ctx.stream));
     AXB_TRY(dm.tile_offsets.reserve(sizeof(int32_t) * ((size_t)dm.num_tiles + 1), ctx.stream));
+    AXB_TRY(dm.active_tiles.reserve(sizeof(int32_t) * (size_t)dm.num_tiles, ctx.stream));
   }
   return ctx.sync();  // host inputs may be released by the caller on return
 }

@@ -7,9 +7,10 @@
 //
 //   mark_rows_kernel    one read of the nodal function (8 B / node, the compulsory traffic): case id per cell (1 byte, kept)
 //   count_tiles_kernel  facet count of each 1024-cell tile from the case bytes
-//   scan_tiles_kernel   exclusive scan of the tile counts (one block; 16 K tiles for 255^3 cells) + the domain total
-//   emit_kernel         tiles without facets exit on two loads; the others list their facets in shared memory and
-//                       spread the facet corners over all threads (one output node per thread)
+//   scan_tiles_kernel   exclusive scan of the tile counts (one block; 16 K tiles for 255^3 cells), the domain total and
+//                       the ordered list of tiles that hold facets
+//   emit_kernel         one block per listed tile: the facets are listed in shared memory and their corners spread over
+//                       all threads (one output node per thread)
 //
 // Output order is the reference's: facets sorted by the parent cell's flat index in the case-id array (whose stride
 // order follows the function's, MarchingCubesImpl.hpp:164-169), then by the case table's facet order; facet f owns
@@ -226,12 +227,56 @@ struct RowView
   const uint8_t* lut;      // compact corner bits -> case id
 };
 
-template <int DIM>
-__global__ void __launch_bounds__(kTileThreads) mark_rows_kernel(RowView<DIM> v, double contour_val, int mask_val,
-                                                                 uint8_t* __restrict__ case_ids)
+// one unit; FULL: all kRows rows of the group exist (no per-row bounds checks), MASK: a cell mask is present
+template <int DIM, bool MASK, bool FULL>
+__device__ __forceinline__ void mark_rows_unit(const RowView<DIM>& v, const uint8_t* s_lut, double contour_val, int mask_val, uint32_t lane,
+                                               uint32_t f, uint32_t m0, uint32_t s, uint8_t* __restrict__ case_ids)
 {
   constexpr int NS = DIM == 3 ? 2 : 1;            // node planes a cell touches along S
   constexpr int CB = DIM == 3 ? 4 : 2;            // corner bits a cell takes from one node column
+  // (value >= contour_val) for nodes (f, m0 + mm, s + ss): bit mm * NS + ss
+  uint32_t bits = 0;
+  if(f <= v.nf)
+  {
+    const double* p0 = v.fcn + (long long)f * v.fs[0] + (long long)m0 * v.fs[1] + (DIM == 3 ? (long long)s * v.fs[2] : 0);
+    const double* p1 = p0 + v.fs[2];
+#pragma unroll
+    for(int mm = 0; mm <= kRows; ++mm)
+    {
+      if(FULL || m0 + mm <= v.nm)
+      {
+        if(__ldg(p0) >= contour_val) bits |= 1u << (mm * NS);  // computeCrossingCase (:307-319)
+        if(DIM == 3 && __ldg(p1) >= contour_val) bits |= 1u << (mm * NS + 1);
+      }
+      p0 += v.fs[1];
+      p1 += v.fs[1];
+    }
+  }
+  const uint32_t right = __shfl_down_sync(0xffffffffu, bits, 1);
+  if(lane < kUnitCells && f < v.nf)
+  {
+    uint8_t* out = case_ids + (f + m0 * v.cs_m + (DIM == 3 ? s * v.cs_s : 0));
+    const int32_t* mp = MASK ? v.mask + (long long)f * v.ms[0] + (long long)m0 * v.ms[1] + (DIM == 3 ? (long long)s * v.ms[2] : 0) : nullptr;
+#pragma unroll
+    for(int r = 0; r < kRows; ++r)
+    {
+      if(FULL || m0 + r < v.nm)
+      {
+        const uint32_t code = ((bits >> (r * NS)) & ((1u << CB) - 1)) | (((right >> (r * NS)) & ((1u << CB) - 1)) << CB);
+        int case_id = s_lut[code];
+        if(MASK && __ldg(mp) != mask_val) case_id = 0;  // :325 / :345 (m_caseIdsFlat.fill(0), :162)
+        *out = (uint8_t)case_id;
+      }
+      out += v.cs_m;
+      if(MASK) mp += v.ms[1];
+    }
+  }
+}
+
+template <int DIM, bool MASK>
+__global__ void __launch_bounds__(kTileThreads) mark_rows_kernel(RowView<DIM> v, double contour_val, int mask_val,
+                                                                 uint8_t* __restrict__ case_ids)
+{
   __shared__ uint8_t s_lut[256];
   if(threadIdx.x < 64) reinterpret_cast<uint32_t*>(s_lut)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(v.lut) + threadIdx.x);
   __syncthreads();
@@ -244,41 +289,10 @@ __global__ void __launch_bounds__(kTileThreads) mark_rows_kernel(RowView<DIM> v,
     const uint32_t s = fastdiv(t, v.mgroups);
     const uint32_t m0 = (t - s * v.mgroups.d) * kRows;
     const uint32_t f = chunk * kUnitCells + lane;  // node column
-    // (value >= contour_val) for nodes (f, m0 + mm, s + ss): bit mm * NS + ss
-    uint32_t bits = 0;
-    if(f <= v.nf)
-    {
-      const double* p = v.fcn + (long long)f * v.fs[0] + (long long)m0 * v.fs[1] + (DIM == 3 ? (long long)s * v.fs[2] : 0);
-#pragma unroll
-      for(int mm = 0; mm <= kRows; ++mm)
-      {
-        if(m0 + mm <= v.nm)
-        {
-#pragma unroll
-          for(int ss = 0; ss < NS; ++ss)
-            if(__ldg(p + ss * v.fs[2]) >= contour_val) bits |= 1u << (mm * NS + ss);  // computeCrossingCase (:307-319)
-        }
-        p += v.fs[1];
-      }
-    }
-    const uint32_t right = __shfl_down_sync(0xffffffffu, bits, 1);
-    if(lane < kUnitCells && f < v.nf)
-    {
-      uint32_t flat = f + m0 * v.cs_m + (DIM == 3 ? s * v.cs_s : 0);
-      const int32_t* mp = v.mask ? v.mask + (long long)f * v.ms[0] + (long long)m0 * v.ms[1] + (DIM == 3 ? (long long)s * v.ms[2] : 0) : nullptr;
-#pragma unroll
-      for(int r = 0; r < kRows; ++r)
-      {
-        if(m0 + r < v.nm)
-        {
-          const uint32_t code = ((bits >> (r * NS)) & ((1u << CB) - 1)) | (((right >> (r * NS)) & ((1u << CB) - 1)) << CB);
-          int case_id = s_lut[code];
-          if(mp && __ldg(mp + r * v.ms[1]) != mask_val) case_id = 0;  // :325 / :345 (m_caseIdsFlat.fill(0), :162)
-          case_ids[flat] = (uint8_t)case_id;
-        }
-        flat += v.cs_m;
-      }
-    }
+    if(m0 + kRows <= v.nm)                         // warp-uniform
+      mark_rows_unit<DIM, MASK, true>(v, s_lut, contour_val, mask_val, lane, f, m0, s, case_ids);
+    else
+      mark_rows_unit<DIM, MASK, false>(v, s_lut, contour_val, mask_val, lane, f, m0, s, case_ids);
   }
 }
 
@@ -323,51 +337,84 @@ __global__ void __launch_bounds__(kTileThreads) count_tiles_kernel(uint8_t* __re
 // pass 2: exclusive scan of the tile counts, in place, + total (the two inclusive scans of :413-483 collapse
 // into this one because crossing ids are never an output)
 //------------------------------------------------------------------------------------------
+// One block walks the tile counts in chunks of 4096 (an int4 per thread, coalesced), carrying the running totals.  It also
+// lists the tiles that hold facets, in order, so that pass 3 launches one block per ACTIVE tile only.
+// totals[0] = facets of the domain, totals[1] = active tiles.
 constexpr int kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __restrict__ tile_facets, int num_tiles, long long* __restrict__ total)
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __restrict__ tile_facets, int num_tiles, long long* __restrict__ totals,
+                                                                  int32_t* __restrict__ active_tiles)
 {
-  __shared__ long long s_warp[kScanThreads / 32];
-  const int per = (num_tiles + kScanThreads - 1) / kScanThreads;
-  const int lo = min(num_tiles, (int)threadIdx.x * per), hi = min(num_tiles, lo + per);
-  long long sum = 0;
-#pragma unroll 8
-  for(int i = lo; i < hi; ++i) sum += tile_facets[i];
-  // block-wide inclusive scan of the per-thread sums: warp shuffles, then the 32 warp totals
-  long long incl = sum;
+  __shared__ unsigned long long s_warp[kScanThreads / 32];
+  __shared__ unsigned long long s_total;
+  long long carry = 0;  // facets before this chunk
+  int carry_active = 0;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for(int base = 0; base < num_tiles; base += kScanThreads * 4)
+  {
+    const int i0 = base + (int)threadIdx.x * 4;
+    int c[4] = {0, 0, 0, 0};
+    if(i0 + 3 < num_tiles)
+    {
+      const int4 q = *reinterpret_cast<const int4*>(tile_facets + i0);
+      c[0] = q.x;
+      c[1] = q.y;
+      c[2] = q.z;
+      c[3] = q.w;
+    }
+    else
+    {
 #pragma unroll
-  for(int o = 1; o < 32; o <<= 1)
-  {
-    const long long u = __shfl_up_sync(0xffffffffu, incl, o);
-    if((int)(threadIdx.x & 31) >= o) incl += u;
-  }
-  if((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  if(threadIdx.x < 32)
-  {
-    long long w = s_warp[threadIdx.x];
+      for(int k = 0; k < 4; ++k)
+        if(i0 + k < num_tiles) c[k] = tile_facets[i0 + k];
+    }
+    const int sum = c[0] + c[1] + c[2] + c[3];
+    const int act = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+    // one scan for both: a chunk holds < 2^25 facets (4096 tiles x 5120) and <= 4096 active tiles
+    const unsigned long long mine = ((unsigned long long)act << 40) | (unsigned long long)sum;
+    unsigned long long incl = mine;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1)
     {
-      const long long u = __shfl_up_sync(0xffffffffu, w, o);
-      if((int)threadIdx.x >= o) w += u;
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+      if((int)lane >= o) incl += u;
     }
-    s_warp[threadIdx.x] = w;  // inclusive totals of warps 0 .. threadIdx.x
+    if(lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if(warp == 0)
+    {
+      unsigned long long w = s_warp[lane];
+#pragma unroll
+      for(int o = 1; o < 32; o <<= 1)
+      {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, w, o);
+        if((int)lane >= o) w += u;
+      }
+      s_warp[lane] = w;  // inclusive totals of warps 0 .. lane
+      if(lane == 31) s_total = w;
+    }
+    __syncthreads();
+    const unsigned long long excl = (warp ? s_warp[warp - 1] : 0ull) + incl - mine;
+    long long run = carry + (long long)(excl & ((1ull << 40) - 1));
+    int slot = carry_active + (int)(excl >> 40);
+#pragma unroll
+    for(int k = 0; k < 4; ++k)
+      if(i0 + k < num_tiles)
+      {
+        // offsets are 32-bit like the reference's IndexType; the host rejects totals that do not fit before pass 3 runs
+        tile_facets[i0 + k] = (int32_t)run;
+        run += c[k];
+        if(c[k] > 0) active_tiles[slot++] = i0 + k;
+      }
+    const unsigned long long tot = s_total;
+    carry += (long long)(tot & ((1ull << 40) - 1));
+    carry_active += (int)(tot >> 40);
+    __syncthreads();  // s_warp / s_total are rewritten by the next chunk
   }
-  __syncthreads();
-  const long long before_warp = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
-  long long run = before_warp + incl - sum;
-#pragma unroll 8
-  for(int i = lo; i < hi; ++i)
+  if(threadIdx.x == 0)
   {
-    const int c = tile_facets[i];
-    // offsets are 32-bit like the reference's IndexType; the host rejects totals that do not fit before pass 3 runs
-    tile_facets[i] = (int32_t)run;
-    run += c;
-  }
-  if(threadIdx.x == kScanThreads - 1)
-  {
-    tile_facets[num_tiles] = (int32_t)s_warp[kScanThreads / 32 - 1];
-    *total = s_warp[kScanThreads / 32 - 1];
+    tile_facets[num_tiles] = (int32_t)carry;
+    totals[0] = carry;
+    totals[1] = carry_active;
   }
 }
 
@@ -420,28 +467,29 @@ __device__ __forceinline__ void linear_interp(double f1, double f2, const double
   for(int d = 0; d < DIM; ++d) out[d] = p1[d] + w * (p2[d] - p1[d]);
 }
 
-// One block per 1024-cell tile.  Tiles without facets exit on two loads.  The others (a) scan their case bytes and list
-// their facets as (cell in tile, facet in cell) in shared memory, in output order, then (b) spread the facet CORNERS over
+// One block per ACTIVE 1024-cell tile (the list pass 2 made; tiles without facets are never launched).  A block (a) scans its case bytes and lists
+// its facets as (cell in tile, facet in cell) in shared memory, in output order, then (b) spread the facet CORNERS over
 // all threads: a thread owns one output node, reads only the two end nodes of its edge (2 values + 2 * DIM coordinates
 // instead of the cell's 8 * (1 + DIM)), interpolates and writes DIM consecutive doubles -- consecutive threads write
 // consecutive nodes.  The reference walks crossing cells instead (:590-619); the arithmetic per node is the same.
 template <int DIM>
 __global__ void __launch_bounds__(kTileThreads) emit_kernel(DomainView<DIM> v, double contour_val, const uint8_t* __restrict__ case_ids,
-                                                            const int32_t* __restrict__ tile_offsets, int32_t facet_index_offset,
-                                                            int32_t domain_id, int32_t* __restrict__ facet_node_ids,
+                                                            const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ active_tiles,
+                                                            int32_t facet_index_offset, int32_t domain_id, int32_t* __restrict__ facet_node_ids,
                                                             double* __restrict__ facet_node_coords, int32_t* __restrict__ facet_parent_ids,
                                                             int32_t* __restrict__ facet_domain_ids)
 {
   constexpr int MAXF = DIM == 2 ? 2 : 5;  // facets per cell
-  const int32_t tile_first = tile_offsets[blockIdx.x];
-  const int tile_total = tile_offsets[blockIdx.x + 1] - tile_first;
-  if(tile_total == 0) return;  // no crossing in this tile (the common case)
+  const uint32_t tile = (uint32_t)active_tiles[blockIdx.x];
+  const int32_t tile_first = tile_offsets[tile];
+  const int tile_total = tile_offsets[tile + 1] - tile_first;
+  if(tile_total == 0) return;  // cannot happen for a listed tile
 
   __shared__ int s_warp[kTileThreads / 32];
   __shared__ uint8_t s_case[kTileCells];
   __shared__ uint16_t s_cell[kTileCells * MAXF];  // facet (in tile order) -> cell within the tile
   __shared__ uint8_t s_fid[kTileCells * MAXF];    //                      -> facet within the cell
-  const uint32_t tile0 = blockIdx.x * (uint32_t)kTileCells;
+  const uint32_t tile0 = tile * (uint32_t)kTileCells;
   const uint32_t local0 = threadIdx.x * kCellsPerThread;  // 4 consecutive cells per thread
   const uchar4 cs4 = *reinterpret_cast<const uchar4*>(case_ids + tile0 + local0);
   *reinterpret_cast<uchar4*>(s_case + local0) = cs4;
