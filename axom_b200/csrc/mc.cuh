@@ -234,22 +234,28 @@ __device__ __forceinline__ void mark_rows_unit(const RowView<DIM>& v, const uint
 {
   constexpr int NS = DIM == 3 ? 2 : 1;            // node planes a cell touches along S
   constexpr int CB = DIM == 3 ? 4 : 2;            // corner bits a cell takes from one node column
-  // (value >= contour_val) for nodes (f, m0 + mm, s + ss): bit mm * NS + ss
+  // (value >= contour_val) for nodes (f, m0 + mm, s + ss): bit mm * NS + ss.  All 2 * (kRows + 1) loads are issued before
+  // the first comparison, so a warp keeps 4.6 KB in flight per unit (the kernel is latency-bound otherwise).
   uint32_t bits = 0;
   if(f <= v.nf)
   {
     const double* p0 = v.fcn + (long long)f * v.fs[0] + (long long)m0 * v.fs[1] + (DIM == 3 ? (long long)s * v.fs[2] : 0);
     const double* p1 = p0 + v.fs[2];
+    double a0[kRows + 1], a1[kRows + 1];
 #pragma unroll
     for(int mm = 0; mm <= kRows; ++mm)
     {
-      if(FULL || m0 + mm <= v.nm)
-      {
-        if(__ldg(p0) >= contour_val) bits |= 1u << (mm * NS);  // computeCrossingCase (:307-319)
-        if(DIM == 3 && __ldg(p1) >= contour_val) bits |= 1u << (mm * NS + 1);
-      }
+      const bool row = FULL || m0 + mm <= v.nm;  // a missing node row is never used by an existing cell
+      a0[mm] = row ? __ldg(p0) : 0.0;
+      a1[mm] = (DIM == 3 && row) ? __ldg(p1) : 0.0;
       p0 += v.fs[1];
       p1 += v.fs[1];
+    }
+#pragma unroll
+    for(int mm = 0; mm <= kRows; ++mm)
+    {
+      if(a0[mm] >= contour_val) bits |= 1u << (mm * NS);  // computeCrossingCase (:307-319)
+      if(DIM == 3 && a1[mm] >= contour_val) bits |= 1u << (mm * NS + 1);
     }
   }
   const uint32_t right = __shfl_down_sync(0xffffffffu, bits, 1);
