@@ -241,6 +241,13 @@ def c2mc(args):
     dev_out = [a.cpu().numpy() for a in mc.relinquishContourData(device_out=True)]
     same = all(np.array_equal(a, b) for a, b in zip(host, dev_out))
     alg_mark = 8 * nodes + cells
+    traffic, traffic_source = None, None
+    try:  # dram bytes of the mark kernel from the committed ncu capture (full-size workload only)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "mc_mark_kernel_ncu.json")))
+        if n == 255:
+            traffic, traffic_source = prof["dram_bytes_per_launch"], prof["source"]
+    except Exception:
+        pass
     cpu = None
     if not args.no_cpu:
         kind_ref = "reference" if O.have_reference() else "port"
@@ -265,7 +272,7 @@ def c2mc(args):
                 "note": "host mesh -> upload of x, y, z and the field, contour, contour arrays back on the host (wall clock, first call)"},
         "roofline": {"bound": "hbm", "kernel": "mc.mark", "achieved": alg_mark / (ph["mark"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                      "frac": alg_mark / (ph["mark"] * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_launch": alg_mark, "peak_source": src,
-                     "traffic": None},
+                     "kernel_ms": ph["mark"], "traffic": traffic, "traffic_source": traffic_source},
         "cpu_baseline": cpu}), flush=True)
 
 
