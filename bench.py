@@ -160,6 +160,63 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def marching_cubes_leg(phi_d, ax, device, check=True, steps=10):
+    """quest::MarchingCubes::computeIsocontour(0.0) on the signed-distance field the timed region just produced (256^3 nodes,
+    x fastest = Blueprint's default layout), everything resident in HBM: ms per contour, per-kernel times, and -- through
+    Blueprint strides / offsets into the SAME arrays -- a 64^3-cell sub-domain checked bit for bit against the CPU oracle."""
+    import torch
+    from axom_b200 import MarchingCubes
+    n = GRID - 1
+    zz, yy, xx = torch.meshgrid(ax, ax, ax, indexing="ij")  # [k][j][i] contiguous = i fastest
+    coords = {"x": xx.reshape(-1).contiguous(), "y": yy.reshape(-1).contiguous(), "z": zz.reshape(-1).contiguous()}
+    del zz, yy, xx
+
+    def domain(cells, offset):
+        dims = {"i": cells, "j": cells, "k": cells}
+        fld = {"association": "vertex", "topology": "mesh", "values": phi_d}
+        if offset:
+            lay = {"offsets": np.array([offset] * 3, np.int32), "strides": np.array([1, GRID, GRID * GRID], np.int32)}
+            dims.update(lay)
+            fld.update(lay)
+        return {"domain_000000": {"coordsets": {"coords": {"type": "explicit", "values": coords}},
+                                  "topologies": {"mesh": {"type": "structured", "coordset": "coords", "elements": {"dims": dims}}},
+                                  "fields": {"phi": fld}}}
+
+    mc = MarchingCubes(device=device)
+    mc.setMesh(domain(n, 0), "mesh")
+    mc.setFunctionField("phi")
+    mc.computeIsocontour(0.0)
+    mc.set_profiling(True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mc.clearOutput()
+        mc.computeIsocontour(0.0)  # synchronous: the facet count comes back to the host inside the call
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    facets = mc.getContourCellCount()
+    phases = {k: mc.phase_ms("mc." + k) for k in ("mark", "count", "scan", "emit")}
+    info = {"ms_per_contour": ms, "cells": n ** 3, "facets": int(facets), "cells_per_s": n ** 3 / (ms * 1e-3), "contour_value": 0.0,
+            "phases_ms": phases, "launches_per_contour": 4,
+            "mark_kernel_hbm_frac": (8.0 * GRID ** 3 + n ** 3) / (phases["mark"] * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}
+    if check:
+        from axom_b200.marching_cubes import domain_views
+        from oracle import oracle as O
+        sub = domain(64, 32)  # nodes 32..96 per direction: a block that straddles the sphere
+        ms_ = MarchingCubes(device=device)
+        ms_.setMesh(sub, "mesh")
+        ms_.setFunctionField("phi")
+        ms_.computeIsocontour(0.0)
+        got = ms_.relinquishContourData()
+        host = {"domain_000000": dict(sub["domain_000000"])}
+        host["domain_000000"]["coordsets"] = {"coords": {"type": "explicit", "values": {k: v.cpu().numpy() for k, v in coords.items()}}}
+        host["domain_000000"]["fields"] = {"phi": dict(sub["domain_000000"]["fields"]["phi"], values=phi_d.cpu().numpy())}
+        want = O.mc_isocontour(domain_views(host, "mesh", "phi"), 0.0)
+        info["sub_domain_check"] = {"cells": 64 ** 3, "facets": int(want[2].size), "kind": "port",
+                                    "matches_gpu_bit_exact": bool(want[2].size > 0 and all(np.array_equal(a.reshape(-1), b.reshape(-1))
+                                                                                          for a, b in zip(want, got)))}
+    return info
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -316,6 +373,15 @@ def run_ours(args):
                    GRID // step, step, GRID, info["npts"], info["seconds"][0]),
                "matches_gpu_bit_exact": bool(np.array_equal(sub, info["phi"]))}
 
+
+    # ---- the consumer of the field: quest::MarchingCubes on phi, zero level set, device-resident ----
+    mc_info = None
+    if world == 1 and not args.no_marching_cubes:
+        try:
+            mc_info = marching_cubes_leg(phi_d, ax, local, check=not args.no_cpu_baseline)
+        except Exception as e:  # never lose the headline line to the secondary leg
+            mc_info = {"error": "%s: %s" % (type(e).__name__, e)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -330,6 +396,7 @@ def run_ours(args):
         "fp64": fp64,
         "l1": l1,
         "cpu_baseline": cpu,
+        "marching_cubes": mc_info,
         "build_ms": build_ms, "build_phases_ms": build_phases, "setmesh_wall_ms": setmesh_wall_ms, "first_setmesh_wall_ms": first_setmesh_wall_ms,
         "build_roofline": {"bound": "hbm", "achieved": 156.0 * ntri / (build_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": 156.0 * ntri / (build_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_box": 156},
@@ -343,6 +410,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--no-marching-cubes", action="store_true", help="skip the MarchingCubes leg on the computed field")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sharding", default="slabs", choices=["slabs", "planes"], help="how the 256 z-planes are split over ranks")
