@@ -121,16 +121,6 @@ __host__ __device__ __forceinline__ void corner_offset(int c, int o[DIM])
   }
 }
 
-// a[i] for a runtime i without indexing the array dynamically (keeps small arrays in registers)
-template <int DIM, typename T>
-__device__ __forceinline__ T pick(const T a[DIM], int i)
-{
-  T r = a[0];
-#pragma unroll
-  for(int d = 1; d < DIM; ++d) r = (i == d) ? a[d] : r;
-  return r;
-}
-
 // inverse of corner_offset
 template <int DIM>
 __host__ __device__ __forceinline__ int corner_id(const int o[DIM])
@@ -331,7 +321,10 @@ __global__ void __launch_bounds__(kTileThreads) count_tiles_kernel(uint8_t* __re
         c.w = 0;
         *reinterpret_cast<uchar4*>(case_ids + cell0) = c;
       }
-      nf += s_nfacets[c.x] + s_nfacets[c.y] + s_nfacets[c.z] + s_nfacets[c.w];
+      // away from the contour the four cells are all "outside" (0) or all "inside" (2^corners - 1): no facets, no look-up
+      const uint32_t w = (uint32_t)c.x | ((uint32_t)c.y << 8) | ((uint32_t)c.z << 16) | ((uint32_t)c.w << 24);
+      constexpr uint32_t kAllInside = DIM == 2 ? 0x0F0F0F0Fu : 0xFFFFFFFFu;
+      if(w != 0u && w != kAllInside) nf += s_nfacets[c.x] + s_nfacets[c.y] + s_nfacets[c.z] + s_nfacets[c.w];
     }
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
@@ -343,10 +336,11 @@ __global__ void __launch_bounds__(kTileThreads) count_tiles_kernel(uint8_t* __re
 // pass 2: exclusive scan of the tile counts, in place, + total (the two inclusive scans of :413-483 collapse
 // into this one because crossing ids are never an output)
 //------------------------------------------------------------------------------------------
-// One block walks the tile counts in chunks of 4096 (an int4 per thread, coalesced), carrying the running totals.  It also
-// lists the tiles that hold facets, in order, so that pass 3 launches one block per ACTIVE tile only.
-// totals[0] = facets of the domain, totals[1] = active tiles.
+// One block walks the tile counts in chunks of 16384 (four int4 per thread, issued together), carrying the running
+// totals: 255^3 cells = 16193 tiles = one chunk.  It also lists the tiles that hold facets, in order, so that pass 3
+// launches one block per ACTIVE tile only.  totals[0] = facets of the domain, totals[1] = active tiles.
 constexpr int kScanThreads = 1024;
+constexpr int kScanPerThread = 16;
 __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __restrict__ tile_facets, int num_tiles, long long* __restrict__ totals,
                                                                   int32_t* __restrict__ active_tiles)
 {
@@ -355,27 +349,35 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __res
   long long carry = 0;  // facets before this chunk
   int carry_active = 0;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for(int base = 0; base < num_tiles; base += kScanThreads * 4)
+  for(int base = 0; base < num_tiles; base += kScanThreads * kScanPerThread)
   {
-    const int i0 = base + (int)threadIdx.x * 4;
-    int c[4] = {0, 0, 0, 0};
-    if(i0 + 3 < num_tiles)
+    const int i0 = base + (int)threadIdx.x * kScanPerThread;
+    int c[kScanPerThread];
+    if(i0 + kScanPerThread <= num_tiles)
     {
-      const int4 q = *reinterpret_cast<const int4*>(tile_facets + i0);
-      c[0] = q.x;
-      c[1] = q.y;
-      c[2] = q.z;
-      c[3] = q.w;
+#pragma unroll
+      for(int k = 0; k < kScanPerThread / 4; ++k)
+      {
+        const int4 q = *reinterpret_cast<const int4*>(tile_facets + i0 + 4 * k);
+        c[4 * k + 0] = q.x;
+        c[4 * k + 1] = q.y;
+        c[4 * k + 2] = q.z;
+        c[4 * k + 3] = q.w;
+      }
     }
     else
     {
 #pragma unroll
-      for(int k = 0; k < 4; ++k)
-        if(i0 + k < num_tiles) c[k] = tile_facets[i0 + k];
+      for(int k = 0; k < kScanPerThread; ++k) c[k] = (i0 + k < num_tiles) ? tile_facets[i0 + k] : 0;
     }
-    const int sum = c[0] + c[1] + c[2] + c[3];
-    const int act = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
-    // one scan for both: a chunk holds < 2^25 facets (4096 tiles x 5120) and <= 4096 active tiles
+    int sum = 0, act = 0;
+#pragma unroll
+    for(int k = 0; k < kScanPerThread; ++k)
+    {
+      sum += c[k];
+      act += (c[k] > 0);
+    }
+    // one scan for both: a chunk holds < 2^27 facets (16384 tiles x 5120) and <= 16384 active tiles
     const unsigned long long mine = ((unsigned long long)act << 40) | (unsigned long long)sum;
     unsigned long long incl = mine;
 #pragma unroll
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __res
     long long run = carry + (long long)(excl & ((1ull << 40) - 1));
     int slot = carry_active + (int)(excl >> 40);
 #pragma unroll
-    for(int k = 0; k < 4; ++k)
+    for(int k = 0; k < kScanPerThread; ++k)
       if(i0 + k < num_tiles)
       {
         // offsets are 32-bit like the reference's IndexType; the host rejects totals that do not fit before pass 3 runs
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(kTileThreads) emit_kernel(DomainView<DIM> v, d
 #pragma unroll
   for(int r = 0; r < 4; ++r)
   {
-    cnt[r] = (cs[r] == 0) ? 0 : used_entries<DIM>(cs[r]) / DIM;
+    cnt[r] = (cs[r] == 0 || cs[r] == (DIM == 2 ? 15 : 255)) ? 0 : used_entries<DIM>(cs[r]) / DIM;
     mine += cnt[r];
   }
   // block-wide exclusive scan of `mine` in thread order = flat cell order
