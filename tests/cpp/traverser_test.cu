@@ -2,6 +2,13 @@
 // C++ shim, then walks it from ITS OWN kernel with axom_b200::spin::traverse_tree (include/axom_b200/traverser.cuh),
 // the drop-in for LinearBVHTraverser::traverse_tree (spin/policy/LinearBVH.hpp:57-109).  The hits of the
 // user kernel must equal findPoints' candidate lists, in the same order (bvh_traverse.hpp:66-154).
+//
+// A second kernel follows the other getTraverser() caller of the reference, mir::TopologyMapper
+// (mir/utilities/TopologyMapper.hpp:489-560): one thread per TARGET zone walks the BVH of the SOURCE zones' bounding
+// boxes with a box-intersects predicate and, in the leaf action, computes the overlap of the two zones and accumulates
+// overlap / targetAmount per source material -- here for axis-aligned hexahedral zones, whose shapeOverlap is the volume
+// of the box intersection.  The per-material sums must equal, bit for bit, the same sums taken on the host over
+// findBoundingBoxes' candidate lists in their order.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -41,6 +48,132 @@ __global__ void user_kernel(ab::spin::LinearBVHTraverser<double, 3> tr, const Pt
   auto leaf = [&](std::int32_t pos, const std::int32_t* leaf_nodes) { out[base + k++] = leaf_nodes[pos]; };
   ab::spin::traverse_tree(tr, p, leaf, pred);
   counts[i] = k;
+}
+
+// mir::TopologyMapper's loop body (TopologyMapper.hpp:493-560) for axis-aligned zones
+constexpr int kMaterials = 4;
+__host__ __device__ inline double box_overlap(const Box3& a, const Box3& b)
+{
+  double v = 1.0;
+  for(int d = 0; d < 3; ++d)
+  {
+    const double lo = a.m_min.m_components[d] > b.m_min.m_components[d] ? a.m_min.m_components[d] : b.m_min.m_components[d];
+    const double hi = a.m_max.m_components[d] < b.m_max.m_components[d] ? a.m_max.m_components[d] : b.m_max.m_components[d];
+    if(hi <= lo) return 0.0;
+    v = v * (hi - lo);
+  }
+  return v;
+}
+__host__ __device__ inline double box_volume(const Box3& a)
+{
+  double v = 1.0;
+  for(int d = 0; d < 3; ++d) v = v * (a.m_max.m_components[d] - a.m_min.m_components[d]);
+  return v;
+}
+
+__global__ void mapper_kernel(ab::spin::LinearBVHTraverser<double, 3> tr, const Box3* src, const int* src_material, const Box3* target, int n,
+                              double* vf /* [n][kMaterials] */)
+{
+  const int zi = blockIdx.x * blockDim.x + threadIdx.x;
+  if(zi >= n) return;
+  const Box3 targetBBox = target[zi];
+  const double targetAmount = box_volume(targetBBox);
+  double acc[kMaterials] = {0., 0., 0., 0.};
+  auto bbIsect = [](const Box3& q, const Box3& b) {  // BoundingBox::intersectsWith
+    for(int d = 0; d < 3; ++d)
+      if(q.m_max.m_components[d] < b.m_min.m_components[d] || q.m_min.m_components[d] > b.m_max.m_components[d]) return false;
+    return true;
+  };
+  auto handleIntersection = [&](std::int32_t currentNode, const std::int32_t* leafNodes) {
+    const int srcZone = leafNodes[currentNode];
+    const double srcOverlapsTarget = box_overlap(src[srcZone], targetBBox);
+    if(srcOverlapsTarget > 0.)
+    {
+      const double f = srcOverlapsTarget / targetAmount;
+      const int m = src_material[srcZone];
+      for(int k = 0; k < kMaterials; ++k) acc[k] = (k == m) ? acc[k] + f : acc[k];
+    }
+  };
+  ab::spin::traverse_tree(tr, targetBBox, handleIntersection, bbIsect);
+  for(int k = 0; k < kMaterials; ++k) vf[zi * kMaterials + k] = acc[k];
+}
+
+static int test_topology_mapper_pattern()
+{
+  // source: 24^3 unit-ish cells of a rectilinear grid with jittered planes; target: 17^3 cells over the same region
+  const int NS = 24, NT = 17;
+  unsigned s = 777u;
+  auto rnd = [&]() {
+    s = s * 1664525u + 1013904223u;
+    return (s >> 8) * (1.0 / 16777216.0);
+  };
+  auto planes = [&](int n) {
+    std::vector<double> p(n + 1);
+    for(int i = 0; i <= n; ++i) p[i] = (i + (i > 0 && i < n ? 0.6 * (rnd() - 0.5) : 0.0)) / n;
+    return p;
+  };
+  auto cells = [&](int n, std::vector<Box3>& out) {
+    const std::vector<double> px = planes(n), py = planes(n), pz = planes(n);
+    for(int k = 0; k < n; ++k)
+      for(int j = 0; j < n; ++j)
+        for(int i = 0; i < n; ++i) out.emplace_back(Pt3 {px[i], py[j], pz[k]}, Pt3 {px[i + 1], py[j + 1], pz[k + 1]});
+  };
+  std::vector<Box3> src, tgt;
+  cells(NS, src);
+  cells(NT, tgt);
+  std::vector<int> mat(src.size());
+  for(auto& m : mat) m = (int)(rnd() * kMaterials) % kMaterials;
+  const int nS = (int)src.size(), nT = (int)tgt.size();
+
+  ab::spin::BVH<3> bvh;
+  bvh.setScaleFactor(1.0);
+  bvh.initialize(src.data(), nS);
+  std::vector<ab::IndexType> off(nT), cnt(nT);
+  ab::Array<ab::IndexType> cand;
+  bvh.findBoundingBoxes(ab::ArrayView<ab::IndexType>(off), ab::ArrayView<ab::IndexType>(cnt), cand, nT, tgt.data());
+  std::vector<double> want((size_t)nT * kMaterials, 0.0);
+  for(int zi = 0; zi < nT; ++zi)
+  {
+    const double amount = box_volume(tgt[zi]);
+    for(int c = 0; c < cnt[zi]; ++c)
+    {
+      const int z = cand[off[zi] + c];
+      const double o = box_overlap(src[z], tgt[zi]);
+      if(o > 0.) want[(size_t)zi * kMaterials + mat[z]] += o / amount;
+    }
+  }
+
+  Box3 *d_src, *d_tgt;
+  int* d_mat;
+  double* d_vf;
+  CK(cudaMalloc(&d_src, sizeof(Box3) * nS));
+  CK(cudaMalloc(&d_tgt, sizeof(Box3) * nT));
+  CK(cudaMalloc(&d_mat, sizeof(int) * nS));
+  CK(cudaMalloc(&d_vf, sizeof(double) * nT * kMaterials));
+  CK(cudaMemcpy(d_src, src.data(), sizeof(Box3) * nS, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_tgt, tgt.data(), sizeof(Box3) * nT, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_mat, mat.data(), sizeof(int) * nS, cudaMemcpyHostToDevice));
+  mapper_kernel<<<(nT + 127) / 128, 128>>>(bvh.getTraverser(), d_src, d_mat, d_tgt, nT, d_vf);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<double> got((size_t)nT * kMaterials);
+  CK(cudaMemcpy(got.data(), d_vf, sizeof(double) * got.size(), cudaMemcpyDeviceToHost));
+  long bad = 0;
+  double worst_sum = 0.0;
+  for(int zi = 0; zi < nT; ++zi)
+  {
+    double sum = 0.0;
+    for(int k = 0; k < kMaterials; ++k)
+    {
+      if(got[(size_t)zi * kMaterials + k] != want[(size_t)zi * kMaterials + k]) ++bad;
+      sum += got[(size_t)zi * kMaterials + k];
+    }
+    const double e = sum > 1.0 ? sum - 1.0 : 1.0 - sum;  // the source cells tile the region: fractions add up to 1
+    if(e > worst_sum) worst_sum = e;
+  }
+  std::printf("traverser_test (TopologyMapper pattern): %s (%d target zones, %d source zones, %ld mismatches, |sum vf - 1| <= %.2e)\n",
+              bad == 0 && worst_sum < 1e-12 ? "OK" : "FAILED", nT, nS, bad, worst_sum);
+  return bad == 0 && worst_sum < 1e-12 ? 0 : 1;
 }
 
 int main()
@@ -89,6 +222,8 @@ int main()
   }
   for(ab::IndexType i = 0; i < cand.size(); ++i)
     if(out[i] != cand[i]) ++bad;
-  std::printf("traverser_test: %s (%d queries, %ld candidates, %ld mismatches)\n", bad == 0 && total > 0 ? "OK" : "FAILED", Q, total, bad);
-  return bad == 0 && total > 0 ? 0 : 1;
+  const int mapper_rc = test_topology_mapper_pattern();
+  std::printf("traverser_test: %s (%d queries, %ld candidates, %ld mismatches)\n", bad == 0 && total > 0 && mapper_rc == 0 ? "OK" : "FAILED", Q,
+              total, bad);
+  return bad == 0 && total > 0 && mapper_rc == 0 ? 0 : 1;
 }
