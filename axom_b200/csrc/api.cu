@@ -2225,6 +2225,7 @@ int axb_mc_set_mesh(axb_mc* h, const axb_mc_domain* domains, int32_t num_domains
   }
   h->release_domains();
   h->doms.resize(num_domains);
+  auto stage = [&]() -> int {
   for(int k = 0; k < num_domains; ++k)
   {
     axb_mc::Domain& dm = h->doms[k];
@@ -2277,6 +2278,10 @@ int axb_mc_set_mesh(axb_mc* h, const axb_mc_domain* domains, int32_t num_domains
     AXB_TRY(dm.active_tiles.reserve(sizeof(int32_t) * (size_t)dm.num_tiles, ctx.stream));
   }
   return ctx.sync();  // host inputs may be released by the caller on return
+  };
+  const int st = stage();
+  if(st != AXB_OK) h->release_domains();  // never leave a half-staged mesh behind
+  return st;
 }
 
 int axb_mc_compute_isocontour(axb_mc* h, double contour_val)

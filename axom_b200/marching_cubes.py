@@ -111,10 +111,12 @@ def pack_domains(views, keep):
 
     def ptr(a, dtype, torch_dtype_name, offset, itemsize):
         nonlocal device
+        if _is_torch(a) and not a.is_cuda:
+            a = a.numpy()  # a (pinned) host tensor is a host array
         if _is_torch(a):
             import torch
             want = getattr(torch, torch_dtype_name)
-            if a.dtype != want or not a.is_cuda:
+            if a.dtype != want:
                 raise TypeError("device arrays must be CUDA tensors of dtype %s" % torch_dtype_name)
             a = a.contiguous().reshape(-1)
             is_dev, p = True, a.data_ptr()
@@ -159,6 +161,7 @@ class MarchingCubes:
         self._mask_val = 1
         self._dirty = False
         self._keep = []
+        self._cache = None  # (device_out, arrays) of the last read-out; dropped by compute / clear
         self.dataParallelism = MarchingCubesDataParallelism(dataParallelism)
 
     def __del__(self):
@@ -210,10 +213,12 @@ class MarchingCubes:
         """adds the contour at contourVal to the contour mesh computed so far (MarchingCubes.cpp:107-147)"""
         if self._dirty or self._h is None:
             self._push_mesh()
+        self._cache = None
         check(self._L.axb_mc_set_mask_value(self._h, self._mask_val))
         check(self._L.axb_mc_compute_isocontour(self._h, float(contourVal)))
 
     def clearOutput(self):
+        self._cache = None
         if self._h is not None:
             check(self._L.axb_mc_clear_output(self._h))
 
@@ -235,6 +240,13 @@ class MarchingCubes:
         return n.value
 
     def _contour(self, device_out):
+        if self._cache is not None and self._cache[0] == bool(device_out):
+            return self._cache[1]
+        out = self._read_contour(device_out)
+        self._cache = (bool(device_out), out)
+        return out
+
+    def _read_contour(self, device_out):
         n, D = self.getContourCellCount(), self._ndims or 3
         if device_out:
             import torch
