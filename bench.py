@@ -217,6 +217,90 @@ def marching_cubes_leg(phi_d, ax, device, check=True, steps=10):
     return info
 
 
+def marching_cubes_sharded_leg(phi_d, ax, p0, p1, rank, world, device, dist, steps=10):
+    """N > 1: every rank contours ITS z-slab of phi (the slab the timed region just filled) as one Blueprint domain with
+    domain id = rank.  The cells between two slabs need the first node plane of the next rank: one NCCL all-gather of a
+    512 KB plane per rank over NVLink -- the only exchange; facets stay sharded.  Checked when the slabs are equal-sized:
+    the slabs' facets, taken in rank order, ARE the single-domain contour of the whole field bit for bit (every rank
+    recomputes that contour from the all-gathered field and compares its own range).
+    Every collective below is reached by every rank unconditionally; only the local work sits in try blocks."""
+    import torch
+    from axom_b200 import MarchingCubes
+    dev = phi_d.device
+    plane = GRID * GRID
+    halo = torch.empty(world * plane, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(halo, phi_d[:plane].contiguous())  # (1) halo exchange
+    ok, err, facets_local, ms, got = 1, None, 0, 0.0, None
+    nplanes = (p1 - p0) + (1 if rank < world - 1 else 0)
+    try:
+        phi_ext = torch.cat([phi_d, halo[(rank + 1) * plane:(rank + 2) * plane]]) if rank < world - 1 else phi_d
+        zz, yy, xx = torch.meshgrid(ax[p0:p0 + nplanes], ax, ax, indexing="ij")
+        coords = {"x": xx.reshape(-1).contiguous(), "y": yy.reshape(-1).contiguous(), "z": zz.reshape(-1).contiguous()}
+        del zz, yy, xx
+        dom = {"domain_%06d" % rank: {
+            "coordsets": {"coords": {"type": "explicit", "values": coords}},
+            "topologies": {"mesh": {"type": "structured", "coordset": "coords",
+                                    "elements": {"dims": {"i": GRID - 1, "j": GRID - 1, "k": nplanes - 1}}}},
+            "fields": {"phi": {"association": "vertex", "topology": "mesh", "values": phi_ext}},
+            "state": {"domain_id": rank}}}
+        mc = MarchingCubes(device=device)
+        mc.setMesh(dom, "mesh")
+        mc.setFunctionField("phi")
+        mc.computeIsocontour(0.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            mc.clearOutput()
+            mc.computeIsocontour(0.0)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        facets_local = mc.getContourCellCount()
+        got = mc.relinquishContourData(device_out=True)
+    except Exception as e:
+        ok, err = 0, "%s: %s" % (type(e).__name__, e)
+    t = torch.tensor([float(ok), float(facets_local), ms], dtype=torch.float64, device=dev)
+    tsum, tmax = t.clone(), t.clone()
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)  # (2) totals
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    all_ok = int(round(float(tsum[0].item()))) == world
+    match = None
+    if GRID % world == 0:  # equal slabs: the whole field can be all-gathered into one tensor
+        full = torch.empty(world * phi_d.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full, phi_d)  # (3) the whole field on every rank, for the check only
+        good = 0
+        try:
+            if all_ok:
+                zz, yy, xx = torch.meshgrid(ax, ax, ax, indexing="ij")
+                fc = {"x": xx.reshape(-1).contiguous(), "y": yy.reshape(-1).contiguous(), "z": zz.reshape(-1).contiguous()}
+                del zz, yy, xx
+                fd = {"domain_000000": {"coordsets": {"coords": {"type": "explicit", "values": fc}},
+                                        "topologies": {"mesh": {"type": "structured", "coordset": "coords",
+                                                                "elements": {"dims": {"i": GRID - 1, "j": GRID - 1, "k": GRID - 1}}}},
+                                        "fields": {"phi": {"association": "vertex", "topology": "mesh", "values": full}}}}
+                mf = MarchingCubes(device=device)
+                mf.setMesh(fd, "mesh")
+                mf.setFunctionField("phi")
+                mf.computeIsocontour(0.0)
+                _, fxyz, fpar, _ = mf.relinquishContourData(device_out=True)
+                cpp = (GRID - 1) ** 2  # cells per cell plane; parents are sorted, x fastest, z slowest
+                edges = torch.tensor([p0 * cpp, (p0 + nplanes - 1) * cpp], dtype=torch.int32, device=dev)
+                lo, hi = (int(v) for v in torch.searchsorted(fpar, edges).tolist())
+                good = int(hi - lo == facets_local and torch.equal(fxyz[3 * lo:3 * hi], got[1])
+                           and torch.equal(fpar[lo:hi] - p0 * cpp, got[2]) and bool((got[3] == rank).all()))
+        except Exception as e:
+            err = err or "%s: %s" % (type(e).__name__, e)
+        g = torch.tensor([good], dtype=torch.int32, device=dev)
+        dist.all_reduce(g, op=dist.ReduceOp.MIN)
+        match = bool(int(g.item()) == 1)
+    ms_max = float(tmax[2].item())
+    info = {"sharding": "one Blueprint domain per rank = its z-slab + the next rank's first node plane (NCCL all-gather, %d B per rank)" % (plane * 8),
+            "ms_per_contour_max_over_ranks": ms_max, "cells": (GRID - 1) ** 3, "facets_total": int(round(float(tsum[1].item()))),
+            "cells_per_s": ((GRID - 1) ** 3 / (ms_max * 1e-3)) if ms_max > 0 else None, "contour_value": 0.0,
+            "matches_single_domain_bit_exact": match, "all_ranks_ok": all_ok}
+    if err:
+        info["error"] = err
+    return info
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -330,6 +414,12 @@ def run_ours(args):
     leaf_tests, inner_visits = sd.work_counters()
     sd.setProfiling(0)
 
+    # ---- N > 1: the consumer of the field, sharded like the queries (every rank takes part: collectives inside) ----
+    mc_sharded = None
+    if world > 1 and not args.no_marching_cubes and args.sharding != "planes":
+        # the collectives inside are reached by every rank unconditionally; local failures are reported, not raised
+        mc_sharded = marching_cubes_sharded_leg(phi_d, ax, (GRID * rank) // world, (GRID * (rank + 1)) // world, rank, world, local, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -375,7 +465,7 @@ def run_ours(args):
 
 
     # ---- the consumer of the field: quest::MarchingCubes on phi, zero level set, device-resident ----
-    mc_info = None
+    mc_info = mc_sharded
     if world == 1 and not args.no_marching_cubes:
         try:
             mc_info = marching_cubes_leg(phi_d, ax, local, check=not args.no_cpu_baseline)
