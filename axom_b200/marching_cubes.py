@@ -98,6 +98,37 @@ def domain_views(bpMesh, topologyName, fcnField, maskField=""):
     return views
 
 
+def slab_domain(field_slab, next_first_plane, axes, k0, domain_id, fcn="phi", topology="mesh"):
+    """A Blueprint domain for one z-slab of a nodal field on a rectilinear lattice -- how a field that is SHARDED across
+    ranks by contiguous z-slabs is contoured without gathering it: `field_slab` holds the rank's node planes k0, k0+1, ...
+    (x fastest, then y, then z) and `next_first_plane` the first node plane of the next rank's slab (None for the last
+    rank) -- the halo the cells between the two slabs need, one plane per rank and the only data exchanged.
+    axes = (ax, ay, az): the lattice coordinates per direction.  numpy arrays or torch tensors (host or CUDA) alike.
+    The slabs' contours, taken in rank order with parent ids offset by k0 * (cells per plane), are the single-domain
+    contour of the whole field bit for bit (tests/test_marching_cubes.py, bench.py at N > 1).
+    -> ({name: domain}, number of cell planes in the slab)"""
+    ax, ay, az = axes
+    nx, ny = len(ax), len(ay)
+    plane = nx * ny
+    if _is_torch(field_slab):
+        import torch
+        vals = torch.cat([field_slab.reshape(-1), next_first_plane.reshape(-1)]) if next_first_plane is not None else field_slab.reshape(-1)
+        nplanes = vals.numel() // plane
+        zz, yy, xx = torch.meshgrid(az[k0:k0 + nplanes], ay, ax, indexing="ij")
+        coords = {"x": xx.reshape(-1).contiguous(), "y": yy.reshape(-1).contiguous(), "z": zz.reshape(-1).contiguous()}
+    else:
+        vals = np.concatenate([np.ravel(field_slab), np.ravel(next_first_plane)]) if next_first_plane is not None else np.ravel(field_slab)
+        nplanes = vals.size // plane
+        zz, yy, xx = np.meshgrid(np.asarray(az)[k0:k0 + nplanes], ay, ax, indexing="ij")
+        coords = {"x": np.ascontiguousarray(xx.ravel()), "y": np.ascontiguousarray(yy.ravel()), "z": np.ascontiguousarray(zz.ravel())}
+    dom = {"coordsets": {"coords": {"type": "explicit", "values": coords}},
+           "topologies": {topology: {"type": "structured", "coordset": "coords",
+                                     "elements": {"dims": {"i": nx - 1, "j": ny - 1, "k": nplanes - 1}}}},
+           "fields": {fcn: {"association": "vertex", "topology": topology, "values": vals}},
+           "state": {"domain_id": int(domain_id)}}
+    return {"domain_%06d" % int(domain_id): dom}, nplanes - 1
+
+
 class McDomain(C.Structure):
     """axb_mc_domain (include/axb200.h)"""
     _fields_ = [("cell_shape", C.c_int64 * 3), ("coords", C.c_void_p * 3), ("coords_strides", C.c_int64 * 3), ("fcn", C.c_void_p),

@@ -226,6 +226,7 @@ def marching_cubes_sharded_leg(phi_d, ax, p0, p1, rank, world, device, dist, ste
     Every collective below is reached by every rank unconditionally; only the local work sits in try blocks."""
     import torch
     from axom_b200 import MarchingCubes
+    from axom_b200.marching_cubes import slab_domain
     dev = phi_d.device
     plane = GRID * GRID
     halo = torch.empty(world * plane, dtype=torch.float64, device=dev)
@@ -233,16 +234,7 @@ def marching_cubes_sharded_leg(phi_d, ax, p0, p1, rank, world, device, dist, ste
     ok, err, facets_local, ms, got = 1, None, 0, 0.0, None
     nplanes = (p1 - p0) + (1 if rank < world - 1 else 0)
     try:
-        phi_ext = torch.cat([phi_d, halo[(rank + 1) * plane:(rank + 2) * plane]]) if rank < world - 1 else phi_d
-        zz, yy, xx = torch.meshgrid(ax[p0:p0 + nplanes], ax, ax, indexing="ij")
-        coords = {"x": xx.reshape(-1).contiguous(), "y": yy.reshape(-1).contiguous(), "z": zz.reshape(-1).contiguous()}
-        del zz, yy, xx
-        dom = {"domain_%06d" % rank: {
-            "coordsets": {"coords": {"type": "explicit", "values": coords}},
-            "topologies": {"mesh": {"type": "structured", "coordset": "coords",
-                                    "elements": {"dims": {"i": GRID - 1, "j": GRID - 1, "k": nplanes - 1}}}},
-            "fields": {"phi": {"association": "vertex", "topology": "mesh", "values": phi_ext}},
-            "state": {"domain_id": rank}}}
+        dom, _ = slab_domain(phi_d, halo[(rank + 1) * plane:(rank + 2) * plane] if rank < world - 1 else None, (ax, ax, ax), p0, rank)
         mc = MarchingCubes(device=device)
         mc.setMesh(dom, "mesh")
         mc.setFunctionField("phi")

@@ -368,3 +368,62 @@ def test_gpu_signed_distance_field_to_contour_chain(oracle):
     mesh["domain_000000"]["fields"]["dist"]["values"] = rphi
     got, _ = _gpu_contour(dmesh, "", 1, (0.05,), device_out=True)
     assert got[2].size > 1000 and _same(got, mc_cases.oracle_contour(oracle, mesh, "", 1, (0.05,)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# N > 1: a field sharded by z-slabs, one halo plane exchanged per rank (the flow of bench.py at N > 1), under gloo on CPU
+# with the oracle as the per-rank contouring step: the slabs' facets in rank order == the single-domain contour
+# ---------------------------------------------------------------------------------------------------------------------
+def _slab_field(n):
+    ax = np.linspace(-1.0, 1.0, n)
+    zz, yy, xx = np.meshgrid(ax, ax, ax, indexing="ij")
+    rng = np.random.default_rng(77)
+    return ax, (np.sqrt((xx - 0.05) ** 2 + (yy + 0.02) ** 2 + zz ** 2) + rng.normal(0, 0.03, xx.shape)).reshape(-1)
+
+
+def _slab_worker(rank, world, port, n, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from axom_b200.marching_cubes import slab_domain
+        from oracle import oracle as O
+        ax, field = _slab_field(n)
+        plane = n * n
+        p0, p1 = (n * rank) // world, (n * (rank + 1)) // world  # ragged slabs when world does not divide n
+        mine = torch.from_numpy(field[p0 * plane:p1 * plane].copy())
+        # the halo exchange: every rank contributes its first node plane
+        firsts = [torch.empty(plane, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(firsts, mine[:plane].contiguous())
+        dom, ncell_planes = slab_domain(mine.numpy(), firsts[rank + 1].numpy() if rank < world - 1 else None, (ax, ax, ax), p0, rank)
+        ids, xyz, par, did = O.mc_isocontour(domain_views(dom, "mesh", "phi"), 0.5)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (p0, ncell_planes, xyz, par, did))
+        if rank == 0:
+            full, _ = slab_domain(field, None, (ax, ax, ax), 0, 0)
+            _, fxyz, fpar, _ = O.mc_isocontour(domain_views(full, "mesh", "phi"), 0.5)
+            cpp = (n - 1) ** 2
+            cat_xyz = np.concatenate([g[2] for g in gathered])
+            cat_par = np.concatenate([g[3] + g[0] * cpp for g in gathered])
+            ok = (np.array_equal(cat_xyz, fxyz) and np.array_equal(cat_par, fpar) and sum(g[1] for g in gathered) == n - 1
+                  and all((g[4] == r).all() for r, g in enumerate(gathered)))
+            out.put((bool(ok), int(fpar.size)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 20), (3, 23)])
+def test_sharded_slabs_with_halo_equal_single_domain_under_gloo(oracle, world, n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + 11 * world
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, nfacets = out.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok and nfacets > 500
