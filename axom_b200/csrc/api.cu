@@ -1945,8 +1945,7 @@ struct axb_mc
     uint8_t h_lut[256];     // compact corner bits -> case id for this domain's direction order (mark_rows_kernel)
   };
   std::vector<Domain> doms;
-  DevBuf totals;            // two int64 per domain: facets, active tiles
-  long long* h_totals = nullptr;
+  long long* h_totals = nullptr;  // pinned + device-mapped: (facets, active tiles) per domain, written by the scan kernel
   size_t h_totals_cap = 0;
   long long facet_count = 0;
   DevBuf node_ids, node_coords, parent_ids, domain_ids;
@@ -2063,14 +2062,17 @@ int mc_compute(axb_mc* h, double contour_val)
   Ctx& ctx = h->ctx;
   const int nd = (int)h->doms.size();
   if(nd == 0) return ctx.finish_call();
-  AXB_TRY(h->totals.reserve(sizeof(long long) * 2 * nd, ctx.stream));
+  // (facets, active tiles) per domain land straight in pinned, device-mapped host memory: the scan kernel writes them
+  // over PCIe and the stream synchronisation below makes them visible -- no copy to enqueue
   if(h->h_totals_cap < (size_t)nd)
   {
     if(h->h_totals) cudaFreeHost(h->h_totals);
     h->h_totals = nullptr;
-    AXB_CUDA_TRY(cudaMallocHost(&h->h_totals, sizeof(long long) * 2 * nd));
+    AXB_CUDA_TRY(cudaHostAlloc(&h->h_totals, sizeof(long long) * 2 * nd, cudaHostAllocMapped));
     h->h_totals_cap = nd;
   }
+  long long* d_totals = nullptr;
+  AXB_CUDA_TRY(cudaHostGetDevicePointer(&d_totals, h->h_totals, 0));
   // tuning / A-B switch: AXB_MC_MARK_PLAIN=1 selects the mark kernel without the lane-sharing of corner bits
   const char* env = getenv("AXB_MC_MARK_PLAIN");
   const bool plain_mark = env && env[0] == '1';
@@ -2078,10 +2080,10 @@ int mc_compute(axb_mc* h, double contour_val)
   for(int k = 0; k < nd; ++k)
   {
     axb_mc::Domain& dm = h->doms[k];
-    long long* tot = h->totals.as<long long>() + 2 * k;
+    long long* tot = d_totals + 2 * k;
     if(dm.num_cells == 0)
     {
-      AXB_CUDA_TRY(cudaMemsetAsync(tot, 0, 2 * sizeof(long long), ctx.stream));
+      h->h_totals[2 * k] = h->h_totals[2 * k + 1] = 0;
       continue;
     }
     const mc::DomainView<DIM> v = make_view<DIM>(dm);
@@ -2111,7 +2113,6 @@ int mc_compute(axb_mc* h, double contour_val)
       AXB_LAUNCH(ctx, mc::scan_tiles_kernel, 1, mc::kScanThreads, dm.tile_offsets.as<int32_t>(), dm.num_tiles, tot, dm.active_tiles.as<int32_t>());
     }
   }
-  AXB_CUDA_TRY(cudaMemcpyAsync(h->h_totals, h->totals.p, sizeof(long long) * 2 * nd, cudaMemcpyDeviceToHost, ctx.stream));
   AXB_TRY(ctx.sync());  // the facet count sizes the output, as m_facetCount does in the reference
   std::vector<long long> first(nd);
   long long count = h->facet_count;
@@ -2168,7 +2169,7 @@ int axb_mc_destroy(axb_mc* h)
   if(!h) return AXB_OK;
   cudaSetDevice(h->ctx.device);
   h->release_domains();
-  for(DevBuf* b : {&h->totals, &h->node_ids, &h->node_coords, &h->parent_ids, &h->domain_ids}) b->release(h->ctx.stream);
+  for(DevBuf* b : {&h->node_ids, &h->node_coords, &h->parent_ids, &h->domain_ids}) b->release(h->ctx.stream);
   if(h->h_totals) cudaFreeHost(h->h_totals);
   cudaStreamSynchronize(h->ctx.stream);
   h->ctx.destroy();
