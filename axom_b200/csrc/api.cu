@@ -1949,6 +1949,7 @@ struct axb_mc
   size_t h_totals_cap = 0;
   long long facet_count = 0;
   DevBuf node_ids, node_coords, parent_ids, domain_ids;
+  DevBuf ticket;            // the count kernel's block ticket (zero between launches)
   void release_domains()
   {
     for(auto& dm : doms)
@@ -2103,14 +2104,11 @@ int mc_compute(axb_mc* h, double contour_val)
       }
     }
     {
+      // tile counts + (last block) their scan, totals and the active-tile list: one launch
       ScopedPhase ph(ctx, "mc.count");
-      const int count_grid = (int)std::min<long long>(((long long)dm.num_tiles + 7) / 8, (long long)kNumSMsB200 * 8);
-      AXB_LAUNCH(ctx, mc::count_tiles_kernel<DIM>, count_grid, mc::kTileThreads, dm.case_ids.as<uint8_t>(), (uint32_t)dm.num_cells,
-                 (uint32_t)dm.num_tiles, dm.tile_offsets.as<int32_t>());
-    }
-    {
-      ScopedPhase ph(ctx, "mc.scan");
-      AXB_LAUNCH(ctx, mc::scan_tiles_kernel, 1, mc::kScanThreads, dm.tile_offsets.as<int32_t>(), dm.num_tiles, tot, dm.active_tiles.as<int32_t>());
+      const int count_grid = (int)std::min<long long>(((long long)dm.num_tiles + 31) / 32, (long long)kNumSMsB200 * 2);
+      AXB_LAUNCH(ctx, mc::count_scan_kernel<DIM>, count_grid, mc::kScanThreads, dm.case_ids.as<uint8_t>(), (uint32_t)dm.num_cells,
+                 (uint32_t)dm.num_tiles, dm.tile_offsets.as<int32_t>(), tot, dm.active_tiles.as<int32_t>(), h->ticket.as<unsigned int>());
     }
   }
   AXB_TRY(ctx.sync());  // the facet count sizes the output, as m_facetCount does in the reference
@@ -2169,7 +2167,7 @@ int axb_mc_destroy(axb_mc* h)
   if(!h) return AXB_OK;
   cudaSetDevice(h->ctx.device);
   h->release_domains();
-  for(DevBuf* b : {&h->node_ids, &h->node_coords, &h->parent_ids, &h->domain_ids}) b->release(h->ctx.stream);
+  for(DevBuf* b : {&h->node_ids, &h->node_coords, &h->parent_ids, &h->domain_ids, &h->ticket}) b->release(h->ctx.stream);
   if(h->h_totals) cudaFreeHost(h->h_totals);
   cudaStreamSynchronize(h->ctx.stream);
   h->ctx.destroy();
@@ -2227,6 +2225,8 @@ int axb_mc_set_mesh(axb_mc* h, const axb_mc_domain* domains, int32_t num_domains
   h->release_domains();
   h->doms.resize(num_domains);
   auto stage = [&]() -> int {
+  AXB_TRY(h->ticket.reserve(sizeof(unsigned int), ctx.stream));
+  AXB_CUDA_TRY(cudaMemsetAsync(h->ticket.p, 0, sizeof(unsigned int), ctx.stream));
   for(int k = 0; k < num_domains; ++k)
   {
     axb_mc::Domain& dm = h->doms[k];

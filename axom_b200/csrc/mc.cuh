@@ -6,9 +6,9 @@
 // 2 + 4 + 4 + 4 bytes per crossing.  Here:
 //
 //   mark_rows_kernel    one read of the nodal function (8 B / node, the compulsory traffic): case id per cell (1 byte, kept)
-//   count_tiles_kernel  facet count of each 1024-cell tile from the case bytes
-//   scan_tiles_kernel   exclusive scan of the tile counts (one block; 16 K tiles for 255^3 cells), the domain total and
-//                       the ordered list of tiles that hold facets
+//   count_scan_kernel   facet count of each 1024-cell tile from the case bytes; the last block to finish then runs the
+//                       exclusive scan of the tile counts (16 K tiles for 255^3 cells), the domain total and the ordered
+//                       list of tiles that hold facets
 //   emit_kernel         one block per listed tile: the facets are listed in shared memory and their corners spread over
 //                       all threads (one output node per thread)
 //
@@ -292,57 +292,17 @@ __global__ void __launch_bounds__(kTileThreads) mark_rows_kernel(RowView<DIM> v,
   }
 }
 
-// per-tile facet count from the case ids (num_contour_cells, :815-843); also zeroes the tail of the last tile.
-// One warp per tile (8 x uint32 = 32 case bytes per lane), warps walk the tiles grid-stride.
-template <int DIM>
-__global__ void __launch_bounds__(kTileThreads) count_tiles_kernel(uint8_t* __restrict__ case_ids, uint32_t num_cells, uint32_t num_tiles,
-                                                                   int32_t* __restrict__ tile_facets)
-{
-  constexpr int NCASE = DIM == 2 ? 16 : 256;
-  __shared__ uint8_t s_nfacets[NCASE];
-  if(threadIdx.x < NCASE) s_nfacets[threadIdx.x] = (uint8_t)(used_entries<DIM>(threadIdx.x) / DIM);
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for(uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < num_tiles; tile += warps)
-  {
-    const uint32_t tile0 = tile * (uint32_t)kTileCells;
-    int nf = 0;
-#pragma unroll
-    for(int k = 0; k < kTileCells / 128; ++k)
-    {
-      const uint32_t cell0 = tile0 + (k * 32 + lane) * 4;  // coalesced 128 B per warp load
-      uchar4 c = *reinterpret_cast<const uchar4*>(case_ids + cell0);
-      if(cell0 + 3 >= num_cells)  // ragged tail: cells past the end count (and are later read) as case 0
-      {
-        if(cell0 + 0 >= num_cells) c.x = 0;
-        if(cell0 + 1 >= num_cells) c.y = 0;
-        if(cell0 + 2 >= num_cells) c.z = 0;
-        c.w = 0;
-        *reinterpret_cast<uchar4*>(case_ids + cell0) = c;
-      }
-      // away from the contour the four cells are all "outside" (0) or all "inside" (2^corners - 1): no facets, no look-up
-      const uint32_t w = (uint32_t)c.x | ((uint32_t)c.y << 8) | ((uint32_t)c.z << 16) | ((uint32_t)c.w << 24);
-      constexpr uint32_t kAllInside = DIM == 2 ? 0x0F0F0F0Fu : 0xFFFFFFFFu;
-      if(w != 0u && w != kAllInside) nf += s_nfacets[c.x] + s_nfacets[c.y] + s_nfacets[c.z] + s_nfacets[c.w];
-    }
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
-    if(lane == 0) tile_facets[tile] = nf;
-  }
-}
-
 //------------------------------------------------------------------------------------------
-// pass 2: exclusive scan of the tile counts, in place, + total (the two inclusive scans of :413-483 collapse
-// into this one because crossing ids are never an output)
+// pass 2: tile counts + their exclusive scan, in place, + total (the two inclusive scans of :413-483 collapse into this
+// one because crossing ids are never an output)
 //------------------------------------------------------------------------------------------
 // One block walks the tile counts in chunks of 16384 (four int4 per thread, issued together), carrying the running
 // totals: 255^3 cells = 16193 tiles = one chunk.  It also lists the tiles that hold facets, in order, so that pass 3
 // launches one block per ACTIVE tile only.  totals[0] = facets of the domain, totals[1] = active tiles.
 constexpr int kScanThreads = 1024;
 constexpr int kScanPerThread = 16;
-__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __restrict__ tile_facets, int num_tiles, long long* __restrict__ totals,
-                                                                  int32_t* __restrict__ active_tiles)
+__device__ __forceinline__ void scan_tiles_block(int32_t* tile_facets, int num_tiles, long long* __restrict__ totals,
+                                                 int32_t* __restrict__ active_tiles)
 {
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_total;
@@ -358,7 +318,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __res
 #pragma unroll
       for(int k = 0; k < kScanPerThread / 4; ++k)
       {
-        const int4 q = *reinterpret_cast<const int4*>(tile_facets + i0 + 4 * k);
+        const int4 q = __ldcg(reinterpret_cast<const int4*>(tile_facets + i0 + 4 * k));  // written by other blocks: L2, not L1
         c[4 * k + 0] = q.x;
         c[4 * k + 1] = q.y;
         c[4 * k + 2] = q.z;
@@ -368,7 +328,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __res
     else
     {
 #pragma unroll
-      for(int k = 0; k < kScanPerThread; ++k) c[k] = (i0 + k < num_tiles) ? tile_facets[i0 + k] : 0;
+      for(int k = 0; k < kScanPerThread; ++k) c[k] = (i0 + k < num_tiles) ? __ldcg(tile_facets + i0 + k) : 0;
     }
     int sum = 0, act = 0;
 #pragma unroll
@@ -424,6 +384,62 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __res
     totals[0] = carry;
     totals[1] = carry_active;
   }
+}
+
+// pass 2 (one launch): per-tile facet count from the case ids (num_contour_cells, :815-843; one warp per tile, warps walk
+// the tiles grid-stride; the tail of the last tile is zeroed), then the LAST block to finish -- a ticket taken after a
+// __threadfence(), the classic single-pass reduction hand-over -- runs the exclusive scan of the tile counts below.
+template <int DIM>
+__global__ void __launch_bounds__(kScanThreads) count_scan_kernel(uint8_t* __restrict__ case_ids, uint32_t num_cells, uint32_t num_tiles,
+                                                                  int32_t* tile_facets, long long* __restrict__ totals,
+                                                                  int32_t* __restrict__ active_tiles, unsigned int* __restrict__ ticket)
+{
+  constexpr int NCASE = DIM == 2 ? 16 : 256;
+  __shared__ uint8_t s_nfacets[NCASE];
+  __shared__ bool s_last;
+  if(threadIdx.x < NCASE) s_nfacets[threadIdx.x] = (uint8_t)(used_entries<DIM>(threadIdx.x) / DIM);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for(uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < num_tiles; tile += warps)
+  {
+    const uint32_t tile0 = tile * (uint32_t)kTileCells;
+    int nf = 0;
+#pragma unroll
+    for(int k = 0; k < kTileCells / 128; ++k)
+    {
+      const uint32_t cell0 = tile0 + (k * 32 + lane) * 4;  // coalesced 128 B per warp load
+      uchar4 c = *reinterpret_cast<const uchar4*>(case_ids + cell0);
+      if(cell0 + 3 >= num_cells)  // ragged tail: cells past the end count (and are later read) as case 0
+      {
+        if(cell0 + 0 >= num_cells) c.x = 0;
+        if(cell0 + 1 >= num_cells) c.y = 0;
+        if(cell0 + 2 >= num_cells) c.z = 0;
+        c.w = 0;
+        *reinterpret_cast<uchar4*>(case_ids + cell0) = c;
+      }
+      // away from the contour the four cells are all "outside" (0) or all "inside" (2^corners - 1): no facets, no look-up
+      const uint32_t w = (uint32_t)c.x | ((uint32_t)c.y << 8) | ((uint32_t)c.z << 16) | ((uint32_t)c.w << 24);
+      constexpr uint32_t kAllInside = DIM == 2 ? 0x0F0F0F0Fu : 0xFFFFFFFFu;
+      if(w != 0u && w != kAllInside) nf += s_nfacets[c.x] + s_nfacets[c.y] + s_nfacets[c.z] + s_nfacets[c.w];
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
+    if(lane == 0) tile_facets[tile] = nf;
+  }
+  // hand-over: make this block's counts visible, take a ticket; the block that draws the last one scans
+  __threadfence();
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+    if(s_last) *ticket = 0;  // ready for the next launch
+  }
+  __syncthreads();
+  if(!s_last) return;
+  __threadfence();
+  scan_tiles_block(tile_facets, (int)num_tiles, totals, active_tiles);
 }
 
 //------------------------------------------------------------------------------------------

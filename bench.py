@@ -197,10 +197,10 @@ def marching_cubes_leg(phi_d, ax, device, check=True, steps=10):
     for _ in range(steps):
         mc.clearOutput()
         mc.computeIsocontour(0.0)
-    phases = {k: mc.phase_ms("mc." + k) for k in ("mark", "count", "scan", "emit")}
+    phases = {k: mc.phase_ms("mc." + k) for k in ("mark", "count", "emit")}
     mc.set_profiling(False)
     info = {"ms_per_contour": ms, "cells": n ** 3, "facets": int(facets), "cells_per_s": n ** 3 / (ms * 1e-3), "contour_value": 0.0,
-            "phases_ms": phases, "launches_per_contour": 4,
+            "phases_ms": phases, "launches_per_contour": 3,
             "mark_kernel_hbm_frac": (8.0 * GRID ** 3 + n ** 3) / (phases["mark"] * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}
     if check:
         from axom_b200.marching_cubes import domain_views

@@ -297,7 +297,7 @@ int axb_mc_get_contour_views(axb_mc* mc, const int32_t** facet_node_ids, const d
 int axb_mc_copy_contour(axb_mc* mc, int memspace, int32_t* facet_node_ids, double* node_coords, int32_t* facet_parent_ids,
                         int32_t* facet_domain_ids);
 int axb_mc_clear_output(axb_mc* mc); /* clearOutput (MarchingCubes.cpp:156-163) */
-int axb_mc_set_profiling(axb_mc* mc, int enabled); /* phases: "mc.mark", "mc.count", "mc.scan", "mc.emit" */
+int axb_mc_set_profiling(axb_mc* mc, int enabled); /* phases: "mc.mark", "mc.count" (tile counts + scan), "mc.emit" */
 int axb_mc_get_phase_ms(const axb_mc* mc, const char* phase, double* ms);
 int axb_mc_launch_count(const axb_mc* mc, int64_t* n);
 

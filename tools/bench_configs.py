@@ -205,7 +205,7 @@ def c3n(args):
 def c2mc(args):
     """SURVEY 8(f) rank 4, the consumer of C2: quest::MarchingCubes iso-contour of the 256^3 nodal distance field
     (255^3 = 16.6 M cells, a sphere of radius 0.5) with the field resident in HBM.  One pass = computeIsocontour on a cleared
-    contour: mark (one read of the field) + count + scan + emit.  Metric: cells/s.  The dominant kernel is mc.mark, HBM-bound:
+    contour: mark (one read of the field) + count/scan + emit.  Metric: cells/s.  The dominant kernel is mc.mark, HBM-bound:
     algorithmic bytes = 8 B per node read once + 1 B per cell of case ids written.  CPU baseline: the REAL reference
     (quest::MarchingCubes, seq policy, through the Conduit mock) on the same field -- its OpenMP policy needs RAJA, so 1 core."""
     import torch
@@ -232,7 +232,7 @@ def c2mc(args):
     mc.set_profiling(True)
     for _ in range(args.steps):
         step()
-    ph = {k: mc.phase_ms("mc." + k) for k in ("mark", "count", "scan", "emit")}
+    ph = {k: mc.phase_ms("mc." + k) for k in ("mark", "count", "emit")}
     mc.set_profiling(False)
     # end to end through the public API with HOST arrays: upload of coordinates + field, contour, contour back on the host
     t0 = time.perf_counter()
@@ -270,7 +270,7 @@ def c2mc(args):
         "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2 consumer: %d^3 nodes, distance to a point, contour 0.5" % (n + 1), "cells": cells, "facets": int(facets),
                    "l2_policy": "field larger than L2 (%d MB)" % (8 * nodes // 2 ** 20)},
-        "phases_ms_per_call": ph, "gpu_launches_per_step": 4, "mark_kernel": "plain" if os.environ.get("AXB_MC_MARK_PLAIN") == "1" else "rows",
+        "phases_ms_per_call": ph, "gpu_launches_per_step": 3, "mark_kernel": "plain" if os.environ.get("AXB_MC_MARK_PLAIN") == "1" else "rows",
         "e2e": {"value": cells / (e2e_ms * 1e-3), "unit": "cells/s", "ms": e2e_ms, "h2d_bytes_per_step": int(4 * 8 * nodes),
                 "d2h_bytes_per_step": int(sum(a.nbytes for a in host)), "matches_device_path": bool(same),
                 "note": "host mesh -> upload of x, y, z and the field, contour, contour arrays back on the host (wall clock, first call)"},
