@@ -64,6 +64,8 @@ def _field_view(dom, name, cell_shape, ndim):
 
 def domain_views(bpMesh, topologyName, fcnField, maskField=""):
     """one DomainView per child of the multi-domain mesh, in child order (MarchingCubes.cpp:76-80)"""
+    if "coordsets" in bpMesh or "topologies" in bpMesh:  # conduit::blueprint::mesh::is_multi_domain (MarchingCubes.cpp:51-52)
+        raise ValueError("MarchingCubes class input mesh must be in multidomain format.")
     views = []
     for pos, (_, dom) in enumerate(bpMesh.items()):
         topo = dom["topologies"][topologyName]

@@ -212,6 +212,12 @@ def test_domain_views_follow_meshviewutil_defaults():
     assert v[0].mask_strides == [20, 4, 1] and v[0].mask_offset == 20 + 4 + 1          # padded cell shape (4, 5, 4)
 
 
+def test_single_domain_tree_is_rejected_like_the_reference():
+    mesh = synth.blueprint_structured_mesh(cells=(3, 3, 3))
+    with pytest.raises(ValueError, match="multidomain"):
+        domain_views(mesh["domain_000000"], "mesh", "dist")
+
+
 def test_mc_fails_loudly_without_a_device():
     """no CPU fallback: on a box without a GPU the C ABI reports AXB_ERR_NO_DEVICE"""
     import torch
