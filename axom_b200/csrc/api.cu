@@ -2017,7 +2017,8 @@ mc::RowView<DIM> make_row_view(const axb_mc::Domain& dm)
   const uint32_t chunks = (v.nf + mc::kUnitCells - 1) / mc::kUnitCells, mgroups = (v.nm + mc::kRows - 1) / mc::kRows;
   v.chunks = mc::make_fastdiv(chunks);
   v.mgroups = mc::make_fastdiv(mgroups);
-  v.num_units = chunks * mgroups * v.ns;
+  const uint32_t sgroups = DIM == 3 ? (v.ns + mc::kPlanes - 1) / mc::kPlanes : 1u;
+  v.num_units = chunks * mgroups * sgroups;
   v.lut = dm.lut.as<uint8_t>();
   return v;
 }

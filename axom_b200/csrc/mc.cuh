@@ -194,13 +194,17 @@ __global__ void __launch_bounds__(kTileThreads) mark_plain_kernel(DomainView<DIM
 }
 
 // The row kernel (default).  Directions are named by speed in the case-id / function layout: F fastest, M middle, S slowest
-// (2-D: F, M).  A warp takes a unit of 31 cells along F x kRows cells along M at one S: lane l evaluates
-// (value >= contour_val) ONCE for the 2 * (kRows + 1) nodes of its node column f = 31 * chunk + l (18 loads for 8 cells
-// instead of 64), packs the bits into one word and hands them to lane l - 1 with a single shuffle; lane 31 only supplies
+// (2-D: F, M).  A warp takes a unit of 31 cells along F x kRows cells along M x kPlanes cells along S: lane l evaluates
+// (value >= contour_val) ONCE for the (kPlanes + 1) * (kRows + 1) nodes of its node column f = 31 * chunk + l (27 loads for
+// 16 cells instead of 128), packs the bits into one word and hands them to lane l - 1 with a single shuffle; lane 31 only supplies
 // bits.  The 8 bits of a cell (4 own, 4 from the right-hand neighbour) index a 256-byte table, built on the host from the
 // direction permutation, that yields the reference's case id (corner numbering of :349-357).  Warps walk the units
 // grid-stride, so the table is staged in shared memory once per block.
 constexpr int kRows = 8;
+#ifndef AXB_MC_PLANES
+  #define AXB_MC_PLANES 2
+#endif
+constexpr int kPlanes = AXB_MC_PLANES;  // cell planes per unit along S (3-D): kPlanes + 1 node planes are read once for kPlanes cell planes
 constexpr int kUnitCells = 31;
 
 template <int DIM>
@@ -217,54 +221,63 @@ struct RowView
   const uint8_t* lut;      // compact corner bits -> case id
 };
 
-// one unit; FULL: all kRows rows of the group exist (no per-row bounds checks), MASK: a cell mask is present
+// one unit; FULL: all kRows rows and all kPlanes cell planes of the unit exist (no bounds checks), MASK: a cell mask is present
 template <int DIM, bool MASK, bool FULL>
 __device__ __forceinline__ void mark_rows_unit(const RowView<DIM>& v, const uint8_t* s_lut, double contour_val, int mask_val, uint32_t lane,
                                                uint32_t f, uint32_t m0, uint32_t s, uint8_t* __restrict__ case_ids)
 {
-  constexpr int NS = DIM == 3 ? 2 : 1;            // node planes a cell touches along S
-  constexpr int CB = DIM == 3 ? 4 : 2;            // corner bits a cell takes from one node column
-  // (value >= contour_val) for nodes (f, m0 + mm, s + ss): bit mm * NS + ss.  All 2 * (kRows + 1) loads are issued before
-  // the first comparison, so a warp keeps 4.6 KB in flight per unit (the kernel is latency-bound otherwise).
+  constexpr int SP = DIM == 3 ? kPlanes : 1;   // cell planes of the unit along S
+  constexpr int NSN = DIM == 3 ? SP + 1 : 1;   // node planes of the unit along S
+  constexpr int CB = DIM == 3 ? 4 : 2;         // corner bits a cell takes from one node column
+  // (value >= contour_val) for nodes (f, m0 + mm, s + ss): bit mm * NSN + ss.  All (kRows + 1) * NSN loads are issued before
+  // the first comparison, so a warp keeps several KB in flight per unit (the kernel is latency-bound otherwise).
   uint32_t bits = 0;
   if(f <= v.nf)
   {
-    const double* p0 = v.fcn + (long long)f * v.fs[0] + (long long)m0 * v.fs[1] + (DIM == 3 ? (long long)s * v.fs[2] : 0);
-    const double* p1 = p0 + v.fs[2];
-    double a0[kRows + 1], a1[kRows + 1];
+    const double* p = v.fcn + (long long)f * v.fs[0] + (long long)m0 * v.fs[1] + (DIM == 3 ? (long long)s * v.fs[2] : 0);
+    double a[kRows + 1][NSN];
 #pragma unroll
     for(int mm = 0; mm <= kRows; ++mm)
     {
-      const bool row = FULL || m0 + mm <= v.nm;  // a missing node row is never used by an existing cell
-      a0[mm] = row ? __ldg(p0) : 0.0;
-      a1[mm] = (DIM == 3 && row) ? __ldg(p1) : 0.0;
-      p0 += v.fs[1];
-      p1 += v.fs[1];
+      const bool row = FULL || m0 + mm <= v.nm;  // a missing node row / plane is never used by an existing cell
+#pragma unroll
+      for(int ss = 0; ss < NSN; ++ss) a[mm][ss] = (row && (FULL || ss == 0 || s + ss <= v.ns)) ? __ldg(p + ss * v.fs[2]) : 0.0;
+      p += v.fs[1];
     }
 #pragma unroll
     for(int mm = 0; mm <= kRows; ++mm)
-    {
-      if(a0[mm] >= contour_val) bits |= 1u << (mm * NS);  // computeCrossingCase (:307-319)
-      if(DIM == 3 && a1[mm] >= contour_val) bits |= 1u << (mm * NS + 1);
-    }
+#pragma unroll
+      for(int ss = 0; ss < NSN; ++ss)
+        if(a[mm][ss] >= contour_val) bits |= 1u << (mm * NSN + ss);  // computeCrossingCase (:307-319)
   }
   const uint32_t right = __shfl_down_sync(0xffffffffu, bits, 1);
   if(lane < kUnitCells && f < v.nf)
   {
-    uint8_t* out = case_ids + (f + m0 * v.cs_m + (DIM == 3 ? s * v.cs_s : 0));
-    const int32_t* mp = MASK ? v.mask + (long long)f * v.ms[0] + (long long)m0 * v.ms[1] + (DIM == 3 ? (long long)s * v.ms[2] : 0) : nullptr;
 #pragma unroll
-    for(int r = 0; r < kRows; ++r)
+    for(int cs = 0; cs < SP; ++cs)
     {
-      if(FULL || m0 + r < v.nm)
+      if(FULL || s + cs < v.ns)
       {
-        const uint32_t code = ((bits >> (r * NS)) & ((1u << CB) - 1)) | (((right >> (r * NS)) & ((1u << CB) - 1)) << CB);
-        int case_id = s_lut[code];
-        if(MASK && __ldg(mp) != mask_val) case_id = 0;  // :325 / :345 (m_caseIdsFlat.fill(0), :162)
-        *out = (uint8_t)case_id;
+        uint8_t* out = case_ids + (f + m0 * v.cs_m + (DIM == 3 ? (s + cs) * v.cs_s : 0));
+        const int32_t* mp =
+          MASK ? v.mask + (long long)f * v.ms[0] + (long long)m0 * v.ms[1] + (DIM == 3 ? (long long)(s + cs) * v.ms[2] : 0) : nullptr;
+#pragma unroll
+        for(int r = 0; r < kRows; ++r)
+        {
+          if(FULL || m0 + r < v.nm)
+          {
+            // the cell's nodes in this column: (r, cs), (r, cs + 1), (r + 1, cs), (r + 1, cs + 1) -> 4 compact bits (2 in 2-D)
+            const uint32_t o = bits >> (r * NSN + cs), q = right >> (r * NSN + cs);
+            const uint32_t own = DIM == 3 ? ((o & 3u) | ((o >> (NSN - 2)) & 0xCu)) : (o & 3u);
+            const uint32_t rgt = DIM == 3 ? ((q & 3u) | ((q >> (NSN - 2)) & 0xCu)) : (q & 3u);
+            int case_id = s_lut[own | (rgt << CB)];
+            if(MASK && __ldg(mp) != mask_val) case_id = 0;  // :325 / :345 (m_caseIdsFlat.fill(0), :162)
+            *out = (uint8_t)case_id;
+          }
+          out += v.cs_m;
+          if(MASK) mp += v.ms[1];
+        }
       }
-      out += v.cs_m;
-      if(MASK) mp += v.ms[1];
     }
   }
 }
@@ -273,6 +286,7 @@ template <int DIM, bool MASK>
 __global__ void __launch_bounds__(kTileThreads) mark_rows_kernel(RowView<DIM> v, double contour_val, int mask_val,
                                                                  uint8_t* __restrict__ case_ids)
 {
+  constexpr uint32_t SP = DIM == 3 ? kPlanes : 1;
   __shared__ uint8_t s_lut[256];
   if(threadIdx.x < 64) reinterpret_cast<uint32_t*>(s_lut)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(v.lut) + threadIdx.x);
   __syncthreads();
@@ -282,10 +296,11 @@ __global__ void __launch_bounds__(kTileThreads) mark_rows_kernel(RowView<DIM> v,
   {
     const uint32_t t = fastdiv(u, v.chunks);
     const uint32_t chunk = u - t * v.chunks.d;
-    const uint32_t s = fastdiv(t, v.mgroups);
-    const uint32_t m0 = (t - s * v.mgroups.d) * kRows;
+    const uint32_t sg = fastdiv(t, v.mgroups);
+    const uint32_t m0 = (t - sg * v.mgroups.d) * kRows;
+    const uint32_t s = sg * SP;                    // first cell plane of the unit
     const uint32_t f = chunk * kUnitCells + lane;  // node column
-    if(m0 + kRows <= v.nm)                         // warp-uniform
+    if(m0 + kRows <= v.nm && s + SP <= v.ns)       // warp-uniform
       mark_rows_unit<DIM, MASK, true>(v, s_lut, contour_val, mask_val, lane, f, m0, s, case_ids);
     else
       mark_rows_unit<DIM, MASK, false>(v, s_lut, contour_val, mask_val, lane, f, m0, s, case_ids);
