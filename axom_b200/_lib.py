@@ -84,6 +84,10 @@ SYMBOLS = [
     ("axb_meshtester_free", C.c_int, [_P, _P, C.c_int]),
     ("axb_meshtester_get_bvh", C.c_int, [_P, _PP]),
     ("axb_tri_tri_intersect", C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_double, _P]),
+    ("axb_closest_point_tri", C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_double, _P, _P]),
+    ("axb_squared_distance_point_box", C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, _P]),
+    ("axb_intersect_ray_box", C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_double, _P]),
+    ("axb_box_scale", C.c_int, [C.c_int, _P, C.c_int64, C.c_int, C.c_double, _P]),
     ("axb_dcp_create", C.c_int, [_PP, C.c_int, C.c_int]),
     ("axb_dcp_destroy", C.c_int, [_P]),
     ("axb_dcp_set_object_points", C.c_int, [_P, _P, _P, C.c_int32, C.c_int]),

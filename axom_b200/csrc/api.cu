@@ -16,6 +16,7 @@
 #include "sd.cuh"
 #include "sd_fast.cuh"
 #include "meshtester.cuh"
+#include "leafmath.cuh"
 #include "dcp.cuh"
 #include "mc.cuh"
 #include "traverse.cuh"
@@ -1654,6 +1655,122 @@ int axb_tri_tri_intersect(int device, const double* tris1, const double* tris2, 
   const int st = body();
   ctx.destroy();
   return st;
+}
+
+}  // extern "C"
+
+// ---- leaf arithmetic on n independent items (leafmath.cuh) ----
+namespace
+{
+struct LeafIO
+{
+  const void* in[2] = {nullptr, nullptr};
+  size_t in_bytes[2] = {0, 0};
+  void* out[2] = {nullptr, nullptr};
+  size_t out_bytes[2] = {0, 0};
+};
+// stage host inputs, run `launch(in0, in1, out0, out1)`, copy host outputs back
+template <class F>
+int leaf_op(int device, int memspace, int64_t n, LeafIO io, F&& launch)
+{
+  if(n < 0) return fail(AXB_ERR_BAD_ARG, "negative item count");
+  for(int k = 0; k < 2; ++k)
+    if(n > 0 && ((io.in_bytes[k] && !io.in[k]) || (io.out_bytes[k] && !io.out[k]))) return fail(AXB_ERR_BAD_ARG, "null argument");
+  memspace = resolve_memspace(memspace, io.in[0]);
+  if(memspace != AXB_MEM_HOST && memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  Ctx ctx;
+  AXB_TRY(ctx.init(device));
+  auto body = [&]() -> int {
+    if(n == 0) return AXB_OK;
+    DevBuf bi[2], bo[2];
+    const void* pi[2] = {io.in[0], io.in[1]};
+    void* po[2] = {io.out[0], io.out[1]};
+    if(memspace == AXB_MEM_HOST)
+    {
+      for(int k = 0; k < 2; ++k)
+      {
+        if(io.in_bytes[k])
+        {
+          AXB_TRY(bi[k].reserve(io.in_bytes[k], ctx.stream));
+          AXB_CUDA_TRY(cudaMemcpyAsync(bi[k].p, io.in[k], io.in_bytes[k], cudaMemcpyHostToDevice, ctx.stream));
+          pi[k] = bi[k].p;
+        }
+        if(io.out_bytes[k])
+        {
+          AXB_TRY(bo[k].reserve(io.out_bytes[k], ctx.stream));
+          po[k] = bo[k].p;
+        }
+      }
+    }
+    AXB_TRY(launch(ctx, pi[0], pi[1], po[0], po[1]));
+    if(memspace == AXB_MEM_HOST)
+      for(int k = 0; k < 2; ++k)
+        if(io.out_bytes[k]) AXB_CUDA_TRY(cudaMemcpyAsync(io.out[k], po[k], io.out_bytes[k], cudaMemcpyDeviceToHost, ctx.stream));
+    for(int k = 0; k < 2; ++k)
+    {
+      bi[k].release(ctx.stream);
+      bo[k].release(ctx.stream);
+    }
+    return ctx.sync();
+  };
+  const int st = body();
+  ctx.destroy();
+  return st;
+}
+}  // namespace
+
+extern "C" {
+
+int axb_closest_point_tri(int device, const double* pts, const double* tris, int64_t n, int memspace, double eps, double* cp, int32_t* loc)
+{
+  LeafIO io;
+  io.in[0] = pts, io.in_bytes[0] = sizeof(double) * 3 * (size_t)std::max<int64_t>(n, 0);
+  io.in[1] = tris, io.in_bytes[1] = sizeof(double) * 9 * (size_t)std::max<int64_t>(n, 0);
+  io.out[0] = cp, io.out_bytes[0] = sizeof(double) * 3 * (size_t)std::max<int64_t>(n, 0);
+  io.out[1] = loc, io.out_bytes[1] = sizeof(int32_t) * (size_t)std::max<int64_t>(n, 0);
+  return leaf_op(device, memspace, n, io, [&](Ctx& ctx, const void* a, const void* b, void* o0, void* o1) -> int {
+    AXB_LAUNCH(ctx, closest_point_tri_kernel, blocks_for(n, 256), 256, (const double*)a, (const double*)b, (long long)n, eps, (double*)o0,
+               (int32_t*)o1);
+    return AXB_OK;
+  });
+}
+
+int axb_squared_distance_point_box(int device, const double* pts, const double* boxes, int64_t n, int memspace, double* out)
+{
+  LeafIO io;
+  io.in[0] = pts, io.in_bytes[0] = sizeof(double) * 3 * (size_t)std::max<int64_t>(n, 0);
+  io.in[1] = boxes, io.in_bytes[1] = sizeof(double) * 6 * (size_t)std::max<int64_t>(n, 0);
+  io.out[0] = out, io.out_bytes[0] = sizeof(double) * (size_t)std::max<int64_t>(n, 0);
+  return leaf_op(device, memspace, n, io, [&](Ctx& ctx, const void* a, const void* b, void* o0, void*) -> int {
+    AXB_LAUNCH(ctx, sqdist_point_box_kernel, blocks_for(n, 256), 256, (const double*)a, (const double*)b, (long long)n, (double*)o0);
+    return AXB_OK;
+  });
+}
+
+int axb_intersect_ray_box(int device, const double* rays, const double* boxes, int64_t n, int memspace, int rays_normalized, double tol,
+                          uint8_t* out)
+{
+  LeafIO io;
+  io.in[0] = rays, io.in_bytes[0] = sizeof(double) * 6 * (size_t)std::max<int64_t>(n, 0);
+  io.in[1] = boxes, io.in_bytes[1] = sizeof(double) * 6 * (size_t)std::max<int64_t>(n, 0);
+  io.out[0] = out, io.out_bytes[0] = (size_t)std::max<int64_t>(n, 0);
+  return leaf_op(device, memspace, n, io, [&](Ctx& ctx, const void* a, const void* b, void* o0, void*) -> int {
+    AXB_LAUNCH(ctx, ray_box_kernel, blocks_for(n, 256), 256, (const double*)a, (const double*)b, (long long)n, rays_normalized, tol,
+               (uint8_t*)o0);
+    return AXB_OK;
+  });
+}
+
+int axb_box_scale(int device, const double* boxes_in, int64_t n, int memspace, double scale_factor, double* boxes_out)
+{
+  LeafIO io;
+  io.in[0] = boxes_in, io.in_bytes[0] = sizeof(double) * 6 * (size_t)std::max<int64_t>(n, 0);
+  io.out[0] = boxes_out, io.out_bytes[0] = sizeof(double) * 6 * (size_t)std::max<int64_t>(n, 0);
+  const double half_scale = static_cast<double>(scale_factor * 0.5);
+  return leaf_op(device, memspace, n, io, [&](Ctx& ctx, const void* a, const void*, void* o0, void*) -> int {
+    AXB_LAUNCH(ctx, box_scale_kernel, blocks_for(n, 256), 256, (const double*)a, (long long)n, half_scale, (double*)o0);
+    return AXB_OK;
+  });
 }
 
 }  // extern "C"

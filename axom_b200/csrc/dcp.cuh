@@ -4,7 +4,9 @@
 //   generateBVHTreeImpl       :883-903    one zero-size box per object point, spin::BVH::initialize
 //   computeLocalClosestPoints :905-1079   per query: preset from the state earlier ranks left, traverse_tree with
 //                                         checkMinDist / traversePredicate, write back only what this rank improved
-// The object "mesh" is a point cloud.  The traversal is the reference's (traverse_reference_order, left child first,
+// The object "mesh" is a point cloud.  The traversal is the reference's (traverse_reference_order; the query is a
+// PointType, so overload resolution picks LinearBVHTraverser::traverse_tree(const PointType&, ...), policy/LinearBVH.hpp:72-85,
+// which enters the child with the nearer box centroid first;
 // both child predicates evaluated at the parent), the arithmetic is primal::squared_distance (point-point: sum of
 // squared differences in order; point-box: clamp, then the same sum) with separately rounded operations, and the
 // leaf test is a strict <, so the nearest point, ties included, is the one the reference reports.
@@ -45,6 +47,37 @@ __device__ __forceinline__ double dcp_sqdist_box(const double* p, const Box<doub
   }
   return s;
 }
+
+// traversePref of the point overload (policy/LinearBVH.hpp:75-82): true = the right child's centroid is nearer
+template <int D>
+struct DcpCentroidOrder
+{
+  const double* p;
+  __device__ __forceinline__ bool operator()(const Box<double, D>& L, const Box<double, D>& R) const
+  {
+    double dl = 0.0, dr = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d)
+    {
+      const double c = 0.5 * (L.lo[d] + L.hi[d]) - p[d];
+      dl += c * c;
+    }
+    if(box_valid(R))
+    {
+#pragma unroll
+      for(int d = 0; d < D; ++d)
+      {
+        const double c = 0.5 * (R.lo[d] + R.hi[d]) - p[d];
+        dr += c * c;
+      }
+    }
+    else
+    {
+      dr = DBL_MAX;
+    }
+    return dl > dr;
+  }
+};
 
 // One thread per query.  State arrays (cp_*) are read and updated in place; is_first initialises them (:971-979).
 // nodes == nullptr: the rank has no object points (only the initialisation happens, :911-916).
@@ -112,7 +145,7 @@ __global__ void __launch_bounds__(128) dcp_local_kernel(const Node<double, D>* _
         cur_rank = rank;
       }
     },
-    NoOrder {});
+    DcpCentroidOrder<D> {p});
   if(cur_rank == rank)  // :1045-1058
   {
     cp_index[i] = cur_idx;
@@ -126,16 +159,18 @@ __global__ void __launch_bounds__(128) dcp_local_kernel(const Node<double, D>* _
 
 // MODE 1 (default): the same answer from a nearest-first search.
 //
-// The reference walks its tree left child first with no initial bound (traverse_tree's default comparator), so a
-// query first descends to leaves that may be arbitrarily far away and only then starts pruning: thousands of node
-// visits per query on a 2 M-point cloud.  Its RESULT, however, has an order-free description: left-first DFS over a
-// tree built on the sorted leaves visits leaves in increasing sorted position, and a leaf replaces the running minimum
-// only on a strict <, so the reference reports the nearest object point and, among exactly equidistant ones, the one
-// with the smallest sorted position (a preset from an earlier rank wins every tie).  This kernel searches in
-// best-first order -- nearer child first, the other on a (lower bound, node) stack, subtrees pruned when their bound
-// exceeds the running minimum -- and breaks ties by sorted position explicitly.  Bounds equal to the running minimum
-// are still entered (<=), as in the reference's predicate, so that an equidistant point with a smaller position is found.
-// The arithmetic of every distance is the reference's; the answer is bit-identical (tests run both modes).
+// The reference walks its tree nearer-centroid-first with no initial bound, so a query first descends to leaves that
+// may be far away and only then starts pruning: thousands of node visits per query on a 2 M-point cloud.  Its RESULT
+// has an order-free description except for exact ties: a leaf replaces the running minimum only on a strict <, and
+// every leaf at the minimum distance d* is reached (its zero-size box is never pruned), so the reference reports the
+// FIRST leaf of its own visiting order among those at d* (a preset from an earlier rank wins every tie).  This kernel
+// searches in best-first order -- nearer child first, the other on a (lower bound, node) stack, subtrees pruned when
+// their bound exceeds the running minimum, bounds EQUAL to it still entered (<=) -- which finds d* and notices
+// whether a second leaf attains it.  Only then (rare: lattice clouds) the query is replayed in the reference's order
+// with the prune radius fixed at d*, stopping at the first leaf at d*: the leaves that replay visits are a subsequence
+// of the reference's, in the same relative order (the centroid comparison does not depend on the radius), and it
+// contains every leaf at d*.  The arithmetic of every distance is the reference's; the answer is bit-identical
+// (tests run both modes, including clouds and queries on a lattice where up to 8 points tie).
 template <int D>
 __global__ void __launch_bounds__(128) dcp_nearest_kernel(const Node<double, D>* __restrict__ nodes, const int32_t* __restrict__ leaf_nodes,
                                                            const double* __restrict__ obj_pts, const int32_t* __restrict__ obj_dom, int rank,
@@ -156,7 +191,7 @@ __global__ void __launch_bounds__(128) dcp_nearest_kernel(const Node<double, D>*
   double cur_sq = bound_sq ? bound_sq[i] : DBL_MAX;
   int cur_pos = 0x7fffffff;  // sorted position of the running minimum; -1 = a preset, which wins every tie
   int cur_idx = -1;
-  bool improved = false;
+  bool improved = false, tie = false;
   if(is_first)
   {
     const double snan = __longlong_as_double(0x7ff4000000000000ll);
@@ -191,12 +226,20 @@ __global__ void __launch_bounds__(128) dcp_nearest_kernel(const Node<double, D>*
       s += v * v;
     }
     // reached in the reference only if the leaf's own (zero-size) box passes the predicate: s <= threshold
-    if(s <= sq_thresh && (s < cur_sq || (s == cur_sq && pos < cur_pos)))
+    if(s <= sq_thresh)
     {
-      cur_sq = s;
-      cur_pos = pos;
-      cur_idx = c;
-      improved = true;
+      if(s < cur_sq || (s == cur_sq && !improved && cur_pos != -1))
+      {
+        cur_sq = s;
+        cur_pos = pos;
+        cur_idx = c;
+        improved = true;
+        tie = false;
+      }
+      else if(s == cur_sq && improved)
+      {
+        tie = true;  // a second point at the running minimum: which one the reference reports depends on its visiting order
+      }
     }
   };
 
@@ -251,6 +294,36 @@ __global__ void __launch_bounds__(128) dcp_nearest_kernel(const Node<double, D>*
     }
     if(next == kBarrier) break;
     cur = next;
+  }
+  if(tie)
+  {
+    // several points at d* = cur_sq: the reference reports the first one of ITS visiting order
+    const double dstar = cur_sq;
+    bool found = false;
+    traverse_reference_order<double, D>(
+      nodes,
+      [&](const Box<double, D>& bb) {
+        if(found) return false;
+        const double sq = dcp_sqdist_box<D>(p, bb);
+        return sq <= dstar && sq <= sq_thresh;
+      },
+      [&](int pos) {
+        if(found) return;
+        const int c = __ldg(leaf_nodes + pos);
+        double sl = 0.0;
+#pragma unroll
+        for(int d = 0; d < D; ++d)
+        {
+          const double v = __ldg(obj_pts + (size_t)c * D + d) - p[d];
+          sl += v * v;
+        }
+        if(sl == dstar)
+        {
+          cur_idx = c;
+          found = true;
+        }
+      },
+      DcpCentroidOrder<D> {p});
   }
   if(improved)
   {

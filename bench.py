@@ -297,6 +297,346 @@ def marching_cubes_sharded_leg(phi_d, ax, p0, p1, rank, world, device, dist, ste
     return info
 
 
+
+# ======================================================================================================================
+# The other BASELINE.json configs, each with its parity bit against the UNMODIFIED reference (oracle/_ref):
+#   C1 findPoints        1 M triangle AABBs, 1 M random points            (spin/BVH.hpp:480-506)
+#   C3 findBoundingBoxes two 10 M-triangle meshes, B shifted by h/2       (spin/BVH.hpp:539-571)
+#   C4 findRays          20 M-triangle icosphere x 100 M random rays      (spin/BVH.hpp:508-537), calls of <= 16 M rays
+#   C5 distributed closest point: surface in G Morton ranges (one per rank), 50 M queries on every rank, elementwise MIN
+# Query sets are generated on the device (torch generator, fixed seeds), sharded over the ranks as contiguous slices with
+# the BVH replicated per GPU and no data-path collective; the first queries go to the host for the reference.
+# ======================================================================================================================
+def _aabbs_device(n, seed, shift, dev):
+    """C1/C3 generator on the device: centres U[0,1)^3, three vertices = centre + h U(-1/2,1/2)^3, h = n^(-1/3)"""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    h = float(n) ** (-1.0 / 3.0)
+    c = torch.rand((n, 1, 3), generator=g, dtype=torch.float64, device=dev)
+    v = c + h * (torch.rand((n, 3, 3), generator=g, dtype=torch.float64, device=dev) - 0.5)
+    v = v + torch.tensor(shift, dtype=torch.float64, device=dev)
+    return torch.cat([v.amin(dim=1), v.amax(dim=1)], dim=1).contiguous()
+
+
+def _points_device(n, seed, lo, hi, dev):
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    return (lo + (hi - lo) * torch.rand((n, 3), generator=g, dtype=torch.float64, device=dev)).contiguous()
+
+
+def _rays_device(n, seed, dev):
+    """C4: origins U[-1,1]^3, directions uniform on the sphere (a normalised Gaussian triple; the reference normalises again)"""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty((n, 6), dtype=torch.float64, device=dev)
+    step = 10_000_000
+    for i in range(0, n, step):
+        m = min(step, n - i)
+        out[i:i + m, :3] = -1.0 + 2.0 * torch.rand((m, 3), generator=g, dtype=torch.float64, device=dev)
+        d = torch.randn((m, 3), generator=g, dtype=torch.float64, device=dev)
+        out[i:i + m, 3:] = d / d.norm(dim=1, keepdim=True)
+    return out
+
+
+def _surface_boxes_device(x, y, z, conn, dev):
+    import torch
+    P = torch.from_numpy(np.stack([x, y, z], axis=1)).to(dev)
+    c = torch.from_numpy(conn.astype(np.int64)).to(dev)
+    out = torch.empty((len(conn), 6), dtype=torch.float64, device=dev)
+    step = 4_000_000
+    for i in range(0, len(conn), step):
+        t = P[c[i:i + step]]
+        out[i:i + step, :3] = t.amin(dim=1)
+        out[i:i + step, 3:] = t.amax(dim=1)
+    return out
+
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def find_leg(name, ctx, surface=None):
+    """One find* config: BVH build + the candidate query over this rank's slice of the query set.  Returns the leg's
+    dict on rank 0 (None elsewhere).  Collectives (max over ranks) are reached by every rank unconditionally."""
+    import torch
+    from axom_b200 import BVH
+    rank, world, dev, local, args = ctx["rank"], ctx["world"], ctx["dev"], ctx["local"], ctx["args"]
+    s = args.config_scale
+    err = None
+    res = {}
+    ms = 0.0
+    total_local = 0
+    q_local = 0
+    try:
+        if name == "C1":
+            n = q = max(1000, int(1_000_000 * s))
+            boxes_d = _aabbs_device(n, 12345, (0.0, 0.0, 0.0), dev)
+            prim_d = _points_device(q, 12346, 0.0, 1.0, dev)
+            kind, P = "points", 24
+            label = "C1: spin::BVH<3> build over %d triangle AABBs + findPoints for %d random points" % (n, q)
+        elif name == "C3":
+            n = q = max(1000, int(10_000_000 * s))
+            h = float(n) ** (-1.0 / 3.0)
+            boxes_d = _aabbs_device(n, 12345, (0.0, 0.0, 0.0), dev)
+            prim_d = _aabbs_device(q, 54321, (h / 2, h / 2, h / 2), dev)
+            kind, P = "boxes", 48
+            label = "C3: findBoundingBoxes, two %d-triangle meshes (B shifted by h/2)" % n
+        else:
+            x, y, z, conn = surface
+            boxes_d = _surface_boxes_device(x, y, z, conn, dev)
+            n = len(conn)
+            q = max(1000, int(100_000_000 * s))
+            prim_d = _rays_device(q, 777, dev)
+            kind, P = "rays", 48
+            label = "C4: findRays, %d random rays vs the %d-triangle icosphere, calls of <= 16 M rays" % (q, n)
+        lo, hi = (q * rank) // world, (q * (rank + 1)) // world
+        mine = prim_d[lo:hi]
+        q_local = hi - lo
+        b = BVH(3, device=local)
+        b.setStream(torch.cuda.current_stream().cuda_stream)  # the CUDA events below are recorded on the launching stream
+        b.initialize(boxes_d)
+        b.setProfiling(True)
+        for _ in range(3):
+            b.initialize(boxes_d)
+        build_ms = b.phase_ms("build.total")
+        build_ph = b.phases_ms("build.", ("bounds", "morton", "sort", "tree", "refit", "agglo"))
+        fn = {"points": b.findPoints, "boxes": b.findBoundingBoxes, "rays": lambda r: b.findRays(r, normalized=False)}[kind]
+        chunk = 16_000_000
+        chunks = [mine[i:i + chunk] for i in range(0, q_local, chunk)]
+
+        def step():
+            tot = 0
+            for c in chunks:
+                _, _, cand = fn(c)
+                tot += cand.numel()
+            return tot
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.config_steps):
+            total_local = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.config_steps
+        walk_ms = b.phase_ms("find.count")
+        find_ph = {k: round(b.phase_ms("find." + k), 4) for k in ("total", "sortq", "count", "scan", "fill")}
+        b.setProfiling(False)
+        res = {"label": label, "n": n, "q": q, "kind": kind, "P": P, "build_ms": build_ms, "build_ph": build_ph, "find_ph": find_ph,
+               "walk_ms": walk_ms, "calls": len(chunks)}
+        # ---- end to end through the C ABI with pinned HOST buffers: one call over min(4 M, slice) queries ----
+        ne = min(q_local, 4_000_000)
+        host_q = torch.empty((ne, mine.shape[1]), dtype=torch.float64, pin_memory=True)
+        host_q.copy_(mine[:ne])
+        hq = host_q.numpy()
+        fh = {"points": b.findPoints, "boxes": b.findBoundingBoxes, "rays": lambda r: b.findRays(r, normalized=False)}[kind]
+        fh(hq)
+        t0 = time.perf_counter()
+        oh, ch, candh = fh(hq)
+        e2e_s = time.perf_counter() - t0
+        res["e2e"] = {"value": ne / e2e_s, "unit": "queries/s", "queries": ne, "ms": e2e_s * 1e3, "h2d_bytes_per_step": int(hq.nbytes),
+                      "d2h_bytes_per_step": int(oh.nbytes + ch.nbytes + candh.nbytes)}
+        # ---- parity against the unmodified reference (rank 0): counts on the first <= 1 M queries, lists on 100 k ----
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            kind_ref = "reference" if O.have_reference() else "port"
+            boxes_h = boxes_d.cpu().numpy()
+            t0 = time.perf_counter()
+            rb = O.Bvh(boxes_h, ndims=3, kind=kind_ref)
+            cpu_build_s = time.perf_counter() - t0
+            ns = min(q_local, 1_000_000)
+            sample = mine[:ns].cpu().numpy()
+            cores = max(_host_cores(), O.max_threads(kind_ref))
+            t0 = time.perf_counter()
+            if kind == "points":
+                _, rc = rb.count_points_omp(sample, nthreads=cores)
+            elif kind == "boxes":
+                _, rc = rb.count_boxes_omp(sample, nthreads=cores)
+            else:
+                _, rc = rb.count_rays_omp(sample[:, :3], sample[:, 3:], nthreads=cores)
+            dt = time.perf_counter() - t0
+            _, gc, _ = fn(mine[:ns])
+            counts_ok = bool(np.array_equal(rc, gc.cpu().numpy()))
+            nl = min(ns, 100_000)
+            if kind == "points":
+                ro, rcnt, rcand = rb.find_points(sample[:nl])
+            elif kind == "boxes":
+                ro, rcnt, rcand = rb.find_boxes(sample[:nl])
+            else:
+                ro, rcnt, rcand = rb.find_rays(sample[:nl, :3], sample[:nl, 3:], normalize=True)
+            go, gcnt, gcand = fn(mine[:nl])
+            lists_ok = bool(np.array_equal(ro, go.cpu().numpy()) and np.array_equal(rcnt, gcnt.cpu().numpy())
+                            and np.array_equal(rcand, gcand.cpu().numpy()))
+            ga = b.arrays() if n <= 2_000_000 else None
+            res["cpu"] = {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": kind_ref,
+                          "sample": "the first %d of the %d queries: the reference's traverse_tree under an external OpenMP loop (RAJA absent), "
+                                    "%.2f s; SEQ_EXEC build of all %d boxes %.2f s" % (ns, q, dt, n, cpu_build_s),
+                          "build_ms": cpu_build_s * 1e3, "counts_checked": ns, "counts_match": counts_ok,
+                          "candidate_lists_checked": nl, "candidate_lists_match": lists_ok}
+            if ga is not None:
+                ra = rb.arrays()
+                res["cpu"]["build_arrays_match"] = bool(all(np.array_equal(ra[k], ga[k]) for k in ("mcodes", "leafs", "inner_children", "inner_nodes", "bounds")))
+            res["cpu"]["matches_reference_bit_exact"] = bool(counts_ok and lists_ok and res["cpu"].get("build_arrays_match", True))
+            del rb
+        del b, boxes_d, prim_d, mine, chunks
+        torch.cuda.empty_cache()
+    except Exception as e:  # never lose the headline to a secondary leg; the collectives below still run
+        err = "%s: %s" % (type(e).__name__, e)
+    ms_max = ctx["max_over_ranks"](ms)
+    tot_all = ctx["sum_over_ranks"](float(total_local))
+    bad = ctx["sum_over_ranks"](1.0 if err else 0.0)
+    if rank != 0:
+        return None
+    if err or bad:
+        return {"error": err or "a rank other than 0 failed"}
+    peaks, peak_src = measured_peaks()
+    n, q, P = res["n"], res["q"], res["P"]
+    # SURVEY 8(d): per query sizeof(prim) + 8 B (offset, count) + 4 B per candidate, plus the node array once per call
+    alg_local = q_local * (P + 8) + 4 * total_local + 108 * n * res["calls"]
+    ach = alg_local / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    leg = {
+        "workload": res["label"], "metric": "find%s queries/s" % res["kind"].capitalize(), "value": q / (ms_max * 1e-3), "unit": "queries/s",
+        "ms_per_step": ms_max, "steps": args.config_steps, "boxes": n, "queries": q, "queries_per_gpu": q_local,
+        "candidates": int(tot_all), "candidates_per_query": tot_all / q, "calls_per_step": res["calls"],
+        "find_phases_ms_per_call": res["find_ph"], "build_ms": res["build_ms"], "build_phases_ms": res["build_ph"],
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                     "algorithmic_bytes_per_step": alg_local, "peak_source": peak_src, "traffic": None,
+                     "note": "rank 0's slice; a latency-bound tree walk, not a stream (see DESIGN 3.2)"},
+        "build_roofline": {"bound": "hbm", "achieved": 156.0 * n / (res["build_ms"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": 156.0 * n / (res["build_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_box": 156},
+        "e2e": res.get("e2e"), "cpu_baseline": res.get("cpu"),
+        "matches_reference_bit_exact": (res.get("cpu") or {}).get("matches_reference_bit_exact"),
+    }
+    return leg
+
+
+def c5_leg(ctx, surface):
+    """BASELINE config 5: the surface split into G spatially coherent parts (Morton ranges of the triangle centroids), one
+    per rank with its own BVH; every rank evaluates ALL queries unsigned against its part; one elementwise MIN over the
+    ranks (NCCL all-reduce over NVLink) gives the distance to the whole surface -- bit-identical, a min of exact
+    per-triangle values.  On one GPU the 8 parts are evaluated in turn and folded with a device-side minimum (no
+    collective).  Checked against the unmodified reference's SignedDistance over the WHOLE surface on a query sample."""
+    import torch
+    from axom_b200 import SignedDistance
+    from axom_b200 import dist as D
+    rank, world, dev, local, args = ctx["rank"], ctx["world"], ctx["dev"], ctx["local"], ctx["args"]
+    x, y, z, conn = surface
+    q = max(1000, int(50_000_000 * args.config_scale))
+    parts_total = world if world > 1 else 8
+    err, ms, coll_ms, out = None, 0.0, 0.0, None
+    try:
+        P = np.stack([x, y, z], 1)
+        cen = (P[conn[:, 0]] + P[conn[:, 1]] + P[conn[:, 2]]) / 3.0
+        parts = D.morton_partition(cen, parts_total)
+        mine = [rank] if world > 1 else list(range(parts_total))
+        qd = _points_device(q, 999, -1.0, 1.0, dev)
+        sds = [SignedDistance(x, y, z, conn[parts[p]], 3, False, False, device=local) for p in mine]
+        out = torch.empty(q, dtype=torch.float64, device=dev)
+        tmp = torch.empty(q, dtype=torch.float64, device=dev) if len(sds) > 1 else None
+        stream = torch.cuda.current_stream()
+        for sd in sds:
+            sd.setStream(stream.cuda_stream)
+            sd.setAsync(True)
+    except Exception as e:
+        err = "%s: %s" % (type(e).__name__, e)
+    ok_all = ctx["sum_over_ranks"](0.0 if err else 1.0) == world
+    if not ok_all:
+        return {"error": err or "setup failed on another rank"} if rank == 0 else None
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step(timed=False):
+        for k, sd in enumerate(sds):
+            sd.computeDistances(qd, out=(out if k == 0 else tmp))
+            if k:
+                torch.minimum(out, tmp, out=out)
+        if world > 1:
+            if timed:
+                ev[2].record()
+            ctx["dist"].all_reduce(out, op=ctx["dist"].ReduceOp.MIN)
+            if timed:
+                ev[3].record()
+
+    step()
+    ctx["barrier"]()
+    ev[0].record()
+    for _ in range(args.config_steps):
+        step()
+    ev[1].record()
+    ctx["barrier"]()
+    ms = ctx["max_over_ranks"](ev[0].elapsed_time(ev[1]) / args.config_steps)
+    if world > 1:
+        step(timed=True)
+        torch.cuda.synchronize()
+        coll_ms = ctx["max_over_ranks"](ev[2].elapsed_time(ev[3]))
+    if rank != 0:
+        return None
+    leg = {"workload": "C5: %d-triangle icosphere in %d Morton ranges (one BVH per %s), %d queries in [-1,1]^3 on every rank, unsigned distance, elementwise MIN"
+                       % (len(conn), parts_total, "rank" if world > 1 else "part, evaluated in turn on one GPU", q),
+           "metric": "distributed closest point queries/s", "value": q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+           "steps": args.config_steps, "queries": q, "partitions": parts_total,
+           "collective": ("ncclAllReduce(MIN, f64), %d B per rank" % (8 * q)) if world > 1 else "none (one GPU)"}
+    if world > 1:
+        bus = 2.0 * (world - 1) / world * 8.0 * q
+        leg["nccl"] = {"allreduce_ms": coll_ms, "bus_bytes": bus, "bus_gbs": bus / (coll_ms * 1e-3) / 1e9 if coll_ms > 0 else None,
+                       "nvlink5_peak_gbs_per_direction": 900.0}
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as O
+            kind_ref = "reference" if O.have_reference() else "port"
+            cores = max(_host_cores(), O.max_threads(kind_ref))
+            t0 = time.perf_counter()
+            ref = O.SignedDistance(x, y, z, conn, 3, False, False, kind=kind_ref)
+            setup_s = time.perf_counter() - t0
+            # bounded sample: grow in blocks until ~20 s of CPU work or 1 M queries
+            got = out.cpu().numpy()
+            done, block, t_q, match = 0, 50_000, 0.0, True
+            while done < min(q, 1_000_000) and t_q < 20.0:
+                m = min(block, q - done)
+                qs = qd[done:done + m].cpu().numpy()
+                t0 = time.perf_counter()
+                phi, _, _ = ref.compute(qs, nthreads=cores)
+                t_q += time.perf_counter() - t0
+                match = match and bool(np.array_equal(phi, got[done:done + m]))
+                done += m
+                block = min(2 * block, 250_000)
+            leg["cpu_baseline"] = {"value": done / t_q, "unit": "queries/s", "cores": cores, "kind": kind_ref,
+                                   "sample": "the first %d of the %d queries against the WHOLE %d-triangle surface (quest::SignedDistance, computeSign off), "
+                                             "OpenMP over queries, %.1f s (+ %.1f s setMesh)" % (done, q, len(conn), t_q, setup_s),
+                                   "matches_gpu_bit_exact": match}
+            leg["matches_reference_bit_exact"] = match
+        except Exception as e:
+            leg["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return leg
+
+
+def config_legs(ctx):
+    """C1, C3, C4, C5 -> {"C1": {...}, ...} on rank 0"""
+    from axom_b200 import synth
+    args = ctx["args"]
+    want = [c.strip().upper() for c in args.configs.split(",") if c.strip()]
+    out = {}
+    for name in ("C1", "C3"):
+        if name in want:
+            out[name] = find_leg(name, ctx)
+    if "C4" in want or "C5" in want:
+        freq = max(2, int(round(1000 * args.config_scale ** 0.5)))
+        surface = synth.icosphere(freq)
+        if "C4" in want:
+            out["C4"] = find_leg("C4", ctx, surface)
+        if "C5" in want:
+            out["C5"] = c5_leg(ctx, surface)
+    return out if ctx["rank"] == 0 else None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -324,6 +664,16 @@ def run_ours(args):
         t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def min_over_ranks(v):
+        return -max_over_ranks(-v)
 
     # ---- surface + BVH (replicated per GPU) ----
     x, y, z, conn = synth.icosphere(FREQ)
@@ -416,6 +766,17 @@ def run_ours(args):
         # the collectives inside are reached by every rank unconditionally; local failures are reported, not raised
         mc_sharded = marching_cubes_sharded_leg(phi_d, ax, (GRID * rank) // world, (GRID * (rank + 1)) // world, rank, world, local, dist)
 
+    # ---- per-rank imbalance of the distance kernel (N > 1: the tail of the slowest rank sets the step) ----
+    kernel_ms_min, kernel_ms_max = min_over_ranks(kernel_ms), max_over_ranks(kernel_ms)
+
+    # ---- the other BASELINE configs (C1, C3, C4, C5), each checked against the reference; every rank takes part ----
+    cfg = None
+    if args.configs:
+        host_phi = phi_d.cpu().numpy() if (world == 1 and not args.no_cpu_baseline) else None
+        ctx = {"rank": rank, "world": world, "dev": dev, "local": local, "args": args, "dist": dist, "barrier": barrier,
+               "max_over_ranks": max_over_ranks, "sum_over_ranks": sum_over_ranks}
+        cfg = config_legs(ctx)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -483,6 +844,8 @@ def run_ours(args):
         "l1": l1,
         "cpu_baseline": cpu,
         "marching_cubes": mc_info,
+        "kernel_ms_per_rank": {"min": kernel_ms_min, "max": kernel_ms_max},
+        "configs": cfg,
         "build_ms": build_ms, "build_phases_ms": build_phases, "setmesh_wall_ms": setmesh_wall_ms, "first_setmesh_wall_ms": first_setmesh_wall_ms,
         "build_roofline": {"bound": "hbm", "achieved": 156.0 * ntri / (build_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": 156.0 * ntri / (build_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_box": 156},
@@ -502,6 +865,9 @@ def main():
     ap.add_argument("--sharding", default="slabs", choices=["slabs", "planes"], help="how the 256 z-planes are split over ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default="small", choices=["small", "large"])
+    ap.add_argument("--configs", default="C1,C3,C4,C5", help="the other BASELINE configs to run after the headline (C2); '' = none")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="shrink C1/C3/C4/C5 (0.1 -> 10x fewer boxes and queries); 1.0 = BASELINE sizes")
+    ap.add_argument("--config-steps", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

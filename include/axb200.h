@@ -223,6 +223,23 @@ int axb_meshtester_get_bvh(axb_meshtester* mt, axb_bvh** bvh);
 int axb_tri_tri_intersect(int device, const double* tris1, const double* tris2, int64_t n, int memspace, int include_boundary, double eps,
                           uint8_t* out);
 
+/* ---- leaf arithmetic of the path on n independent items (so the reference's own unit tests can be run against the
+ * device functions the query kernels use).  All arrays live in `memspace` (host buffers are staged); synchronous. ---- */
+/* primal::closest_point(Point, Triangle, int* loc, EPS) (primal/operators/closest_point.hpp:162-290):
+ * pts double[3] per item, tris double[9] (A, B, C); cp double[3], loc int32 (0/1/2 vertex, -1/-2/-3 edge AB/BC/CA, 3 face) */
+int axb_closest_point_tri(int device, const double* pts, const double* tris, int64_t n, int memspace, double eps, double* cp, int32_t* loc);
+/* primal::squared_distance(Point, BoundingBox) (primal/operators/squared_distance.hpp:77-100): boxes double[6] = min, max;
+ * an invalid box gives DBL_MAX */
+int axb_squared_distance_point_box(int device, const double* pts, const double* boxes, int64_t n, int memspace, double* out);
+/* the findRays predicate primal::detail::intersect_ray(Ray, BoundingBox, ip, tol) (spin/BVH.hpp:529-532,
+ * primal/operators/detail/intersect_ray_impl.hpp:321-351): rays double[6] = origin, direction; rays_normalized = 0
+ * applies the primal::Ray constructor's normalisation (primal/geometry/Ray.hpp:122-127) */
+int axb_intersect_ray_box(int device, const double* rays, const double* boxes, int64_t n, int memspace, int rays_normalized, double tol,
+                          uint8_t* out);
+/* BoundingBox::scale(scale_factor) (primal/geometry/BoundingBox.hpp:548-561) as transform_boxes applies it
+ * (spin/internal/linear_bvh/build_radix_tree.hpp:85-99): boxes_in / boxes_out double[6] per item */
+int axb_box_scale(int device, const double* boxes_in, int64_t n, int memspace, double scale_factor, double* boxes_out);
+
 /* ---- quest::DistributedClosestPoint, the per-rank step ---------------------------------------------- */
 /* DistributedClosestPointExec<DIM, ExecSpace> (quest/detail/DistributedClosestPointImpl.hpp:551-1095) without its
  * Conduit / MPI plumbing: the object "mesh" is a point cloud (all local domains flattened, one domain id per point),

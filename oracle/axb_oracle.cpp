@@ -1299,6 +1299,73 @@ void axo_tri_tri_intersect(const double* tris1, const double* tris2, int n, int 
   }
 }
 
+// ---- leaf math on n independent items (the reference's own unit tests run through these: tests/test_leaf_math.py) ----
+// primal::closest_point(Point, Triangle, int* loc, EPS) (closest_point.hpp:162-290); tris are 9 doubles A,B,C
+void axo_closest_point_tri(const double* pts, const double* tris, int n, double eps, double* cp, int32_t* loc)
+{
+  for(int i = 0; i < n; ++i)
+  {
+    const V3 P {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    const double* t = tris + (size_t)i * 9;
+    int l = 0;
+    const V3 c = closest_point_tri(P, V3 {t[0], t[1], t[2]}, V3 {t[3], t[4], t[5]}, V3 {t[6], t[7], t[8]}, &l, eps);
+    cp[3 * i] = c.x;
+    cp[3 * i + 1] = c.y;
+    cp[3 * i + 2] = c.z;
+    loc[i] = l;
+  }
+}
+// primal::squared_distance(Point, BoundingBox) (squared_distance.hpp:77-100); boxes are lo[3], hi[3]
+void axo_squared_distance_point_box(const double* pts, const double* boxes, int n, double* out)
+{
+  for(int i = 0; i < n; ++i)
+  {
+    Box<3> b;
+    for(int d = 0; d < 3; ++d)
+    {
+      b.lo[d] = boxes[6 * i + d];
+      b.hi[d] = boxes[6 * i + 3 + d];
+    }
+    out[i] = sqdist_point_box<3>(pts + 3 * i, b);
+  }
+}
+// primal::intersect(Ray, BoundingBox) as BVH::findRays evaluates it (BVH.hpp:529-532, intersect_ray_impl.hpp:321-351);
+// rays are origin[3], direction[3]; normalize != 0 applies the primal::Ray constructor's unitVector
+void axo_intersect_ray_box(const double* rays, const double* boxes, int n, int normalize, double tol, uint8_t* out)
+{
+  for(int i = 0; i < n; ++i)
+  {
+    Box<3> b;
+    for(int d = 0; d < 3; ++d)
+    {
+      b.lo[d] = boxes[6 * i + d];
+      b.hi[d] = boxes[6 * i + 3 + d];
+    }
+    double dir[3] = {rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]};
+    if(normalize) unit_vector<3>(rays + 6 * i + 3, dir);
+    out[i] = ray_hits<3>(rays + 6 * i, dir, b, tol) ? 1 : 0;
+  }
+}
+// BoundingBox::scale (BoundingBox.hpp:548-561), in place on n boxes
+void axo_box_scale(double* boxes, int n, double scale)
+{
+  for(int i = 0; i < n; ++i)
+  {
+    Box<3> b;
+    for(int d = 0; d < 3; ++d)
+    {
+      b.lo[d] = boxes[6 * i + d];
+      b.hi[d] = boxes[6 * i + 3 + d];
+    }
+    box_scale(b, scale);
+    for(int d = 0; d < 3; ++d)
+    {
+      boxes[6 * i + d] = b.lo[d];
+      boxes[6 * i + 3 + d] = b.hi[d];
+    }
+  }
+}
+
 // quest::findTriMeshIntersectionsBVH<SEQ_EXEC,double> (MeshTester.hpp:67-104, MeshTester_detail.hpp:158-307):
 // triangle AABBs -> BVH (default scale) -> findBoundingBoxes(own AABBs) -> pairs i < j in candidate order ->
 // primal::intersect(tri_i, tri_j, false, threshold).  Returns the pair count; first/second/degenerate are malloc'ed.
@@ -1424,7 +1491,29 @@ static void dcp_local(const Dcp<D>& o, int rank, double sq_thresh, const double*
           cur_rank = rank;
         }
       },
-      [](const Box<D>&, const Box<D>&) { return false; });
+      // qpt is a PointType, so overload resolution picks LinearBVHTraverser::traverse_tree(const PointType&, ...)
+      // (policy/LinearBVH.hpp:72-85): the child whose box centroid is nearer is entered first
+      [&](const Box<D>& L, const Box<D>& R) {
+        double dl = 0.0, dr = 0.0;
+        for(int d = 0; d < D; ++d)
+        {
+          const double c = 0.5 * (L.lo[d] + L.hi[d]) - p[d];
+          dl += c * c;
+        }
+        if(box_valid(R))
+        {
+          for(int d = 0; d < D; ++d)
+          {
+            const double c = 0.5 * (R.lo[d] + R.hi[d]) - p[d];
+            dr += c * c;
+          }
+        }
+        else
+        {
+          dr = std::numeric_limits<double>::max();
+        }
+        return dl > dr;
+      });
     if(cur_rank == rank)  // :1045-1058
     {
       cp_index[i] = cur_idx;

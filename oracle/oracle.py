@@ -82,6 +82,10 @@ class _Lib:
             f("dcp_compute_local").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
             f("tri_tri_intersect").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+            f("closest_point_tri").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+            f("squared_distance_point_box").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            f("intersect_ray_box").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+            f("box_scale").argtypes = [C.c_void_p, C.c_int, C.c_double]
             f("find_tri_mesh_intersections").restype = C.c_int64
             f("find_tri_mesh_intersections").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
@@ -266,6 +270,38 @@ def tri_tri_intersect(tris1, tris2, include_boundary=False, eps=1e-8, kind="port
     out = np.zeros(a.shape[0], np.uint8)
     lib(kind).fn("tri_tri_intersect")(_ptr(a), _ptr(b), a.shape[0], int(include_boundary), float(eps), _ptr(out))
     return out.astype(bool)
+
+
+def closest_point_tri(points, triangles, eps=1e-50, kind="port"):
+    """primal::closest_point(Point, Triangle, &loc, EPS) on n items -> (cp (n,3), loc (n,))"""
+    p = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+    t = np.ascontiguousarray(triangles, np.float64).reshape(-1, 9)
+    cp, loc = np.empty_like(p), np.empty(len(p), np.int32)
+    lib(kind).fn("closest_point_tri")(_ptr(p), _ptr(t), len(p), float(eps), _ptr(cp), _ptr(loc))
+    return cp, loc
+
+
+def squared_distance_point_box(points, boxes, kind="port"):
+    p = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+    b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 6)
+    out = np.empty(len(p), np.float64)
+    lib(kind).fn("squared_distance_point_box")(_ptr(p), _ptr(b), len(p), _ptr(out))
+    return out
+
+
+def intersect_ray_box(rays, boxes, tol, kind="port"):
+    """primal::detail::intersect_ray(Ray(origin, direction), box, ip, tol); the Ray constructor normalises"""
+    r = np.ascontiguousarray(rays, np.float64).reshape(-1, 6)
+    b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 6)
+    out = np.zeros(len(r), np.uint8)
+    lib(kind).fn("intersect_ray_box")(_ptr(r), _ptr(b), len(r), 1, float(tol), _ptr(out))
+    return out.astype(bool)
+
+
+def box_scale(boxes, scale, kind="port"):
+    b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 6).copy()
+    lib(kind).fn("box_scale")(_ptr(b), len(b), float(scale))
+    return b
 
 
 def find_tri_mesh_intersections(x, y, z, conn, threshold=1e-8, kind="port"):

@@ -32,6 +32,8 @@
 #include "axom/quest/readers/STLReader.hpp"
 #include "axom/quest/interface/signed_distance.hpp"
 #include "axom/primal/operators/squared_distance.hpp"
+#include "axom/primal/operators/closest_point.hpp"
+#include "axom/primal/operators/detail/intersect_ray_impl.hpp"
 #include <limits>
 #include <memory>
 
@@ -502,6 +504,68 @@ void axref_tri_tri_intersect(const double* tris1, const double* tris2, int n, in
     const Tri t1(PointType {a[0], a[1], a[2]}, PointType {a[3], a[4], a[5]}, PointType {a[6], a[7], a[8]});
     const Tri t2(PointType {b[0], b[1], b[2]}, PointType {b[3], b[4], b[5]}, PointType {b[6], b[7], b[8]});
     out[i] = axom::primal::intersect(t1, t2, include_boundary != 0, eps) ? 1 : 0;
+  }
+}
+
+// ---- leaf math on n independent items, forwarded to primal (tests/test_leaf_math.py) ----
+void axref_closest_point_tri(const double* pts, const double* tris, int n, double eps, double* cp, int32_t* loc)
+{
+  using PointType = axom::primal::Point<double, 3>;
+  using Tri = axom::primal::Triangle<double, 3>;
+  for(int i = 0; i < n; ++i)
+  {
+    const double* t = tris + (size_t)i * 9;
+    const Tri tri(PointType {t[0], t[1], t[2]}, PointType {t[3], t[4], t[5]}, PointType {t[6], t[7], t[8]});
+    int l = 0;
+    const PointType c = axom::primal::closest_point(PointType {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]}, tri, &l, eps);
+    for(int d = 0; d < 3; ++d) cp[3 * i + d] = c[d];
+    loc[i] = l;
+  }
+}
+void axref_squared_distance_point_box(const double* pts, const double* boxes, int n, double* out)
+{
+  using PointType = axom::primal::Point<double, 3>;
+  using BoxType = axom::primal::BoundingBox<double, 3>;
+  for(int i = 0; i < n; ++i)
+  {
+    const double* b = boxes + (size_t)i * 6;
+    BoxType bb;  // invalid unless lo <= hi: keep an invalid input invalid (the two-point constructor would swap it)
+    if(b[0] <= b[3] && b[1] <= b[4] && b[2] <= b[5]) bb = BoxType(PointType {b[0], b[1], b[2]}, PointType {b[3], b[4], b[5]});
+    out[i] = axom::primal::squared_distance(PointType {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]}, bb);
+  }
+}
+void axref_intersect_ray_box(const double* rays, const double* boxes, int n, int normalize, double tol, uint8_t* out)
+{
+  using PointType = axom::primal::Point<double, 3>;
+  using VectorType = axom::primal::Vector<double, 3>;
+  using BoxType = axom::primal::BoundingBox<double, 3>;
+  using RayType = axom::primal::Ray<double, 3>;
+  for(int i = 0; i < n; ++i)
+  {
+    const double* r = rays + (size_t)i * 6;
+    const double* b = boxes + (size_t)i * 6;
+    const BoxType bb(PointType {b[0], b[1], b[2]}, PointType {b[3], b[4], b[5]});
+    (void)normalize;  // the primal::Ray constructor always normalises (Ray.hpp:122-127)
+    const RayType ray(PointType {r[0], r[1], r[2]}, VectorType {r[3], r[4], r[5]});
+    PointType ip;
+    out[i] = axom::primal::detail::intersect_ray(ray, bb, ip, tol) ? 1 : 0;  // as BVH::findRays does (spin/BVH.hpp:529-532)
+  }
+}
+void axref_box_scale(double* boxes, int n, double scale)
+{
+  using PointType = axom::primal::Point<double, 3>;
+  using BoxType = axom::primal::BoundingBox<double, 3>;
+  for(int i = 0; i < n; ++i)
+  {
+    double* b = boxes + (size_t)i * 6;
+    BoxType bb;
+    if(b[0] <= b[3] && b[1] <= b[4] && b[2] <= b[5]) bb = BoxType(PointType {b[0], b[1], b[2]}, PointType {b[3], b[4], b[5]});
+    bb.scale(scale);
+    for(int d = 0; d < 3; ++d)
+    {
+      b[d] = bb.getMin()[d];
+      b[3 + d] = bb.getMax()[d];
+    }
   }
 }
 

@@ -128,3 +128,132 @@ def tri_tri_cases():
                         INC.append(inc)
                         WANT.append(want)
     return np.array(T1, np.float64), np.array(T2, np.float64), np.array(INC, bool), np.array(WANT, bool)
+
+
+# ---- leaf math: the reference's own unit tests for the arithmetic on the path ------------------------------------------
+def closest_point_tri_cases():
+    """primal/tests/primal_closest_point.cpp:239-576: (points, triangles, eps, expected cp, expected loc, cp tolerance).
+    The 1e-16-thin triangle and the four degenerate-side triangles, EPS = PRIMAL_TINY."""
+    P, T, C, L, TOL = [], [], [], [], []
+
+    def add(tri, q, cp, loc, tol=0.0):
+        P.append(q), T.append(np.asarray(tri, np.float64).reshape(9)), C.append(cp), L.append(loc), TOL.append(tol)
+
+    tiny = [[0.0, 0.0, 0.0], [0.0, 0.0, 1.0e-16], [0.0, 1.0, 0.0]]  # :246
+    A, B, Cv = tiny
+    add(tiny, [0, 0, 0], A, 0), add(tiny, [0, 0, -1e-16], A, 0), add(tiny, [0, 0, 1e-16], B, 1), add(tiny, [0, 0, 1e-15], B, 1)
+    add(tiny, [0, 1, 0], Cv, 2), add(tiny, [0, 1.0 + 1e-16, 0], Cv, 2)
+    add(tiny, [0, 0, 1e-17], [0, 0, 1e-17], -1, 1e-16), add(tiny, [0, -0.1, 1e-17], [0, 0, 1e-17], -1, 1e-16)
+    add(tiny, [0, 0.5, 5e-17], [0, 0.5, 5e-17], -2, 1e-16), add(tiny, [0.5, 0.5, 5e-17], [0, 0.5, 5e-17], -2, 1e-16)
+    add(tiny, [0, 0.25, 0], [0, 0.25, 0], -3, 1e-16), add(tiny, [-0.25, 0.75, -0.25], [0, 0.75, 0], -3, 1e-16)
+    add(tiny, [0, 1.0 / 3.0, 1e-16 / 3.0], [0, 1.0 / 3.0, 1e-16 / 3.0], 3, 1e-16)
+    add(tiny, [-0.5, 1.0 / 3.0, 1e-16 / 3.0], [0, 1.0 / 3.0, 1e-16 / 3.0], 3, 1e-16)
+    ab = [[0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0]]  # degenerate side AB :383
+    add(ab, [0, 0, 0], ab[0], 0), add(ab, [0, 0, -1e-16], ab[0], 0), add(ab, [0, 0, 1e-16], ab[0], 0), add(ab, [0, -1e-16, 0], ab[0], 0)
+    add(ab, [0, 1, 0], ab[2], 2), add(ab, [0, 1.0 + 1e-16, 0], ab[2], 2)
+    add(ab, [0, 0.25, 0], [0, 0.25, 0], -3, 1e-16), add(ab, [-0.25, 0.75, -0.25], [0, 0.75, 0], -3, 1e-16)
+    bc = [[2.0, 0.0, 0.0], [2.0, 1.0, 1.0], [2.0, 1.0, 1.0]]  # degenerate side BC :449
+    add(bc, [2, 0, 0], bc[0], 0), add(bc, [2, 1, 1], bc[1], 1), add(bc, [3, 2, 2], bc[1], 1)
+    add(bc, [2, 0.75, 0.75], [2, 0.75, 0.75], -1, 1e-16), add(bc, [2, 1, 0], [2, 0.5, 0.5], -1, 1e-16)
+    ca = [[1.0, 3.0, 1.0], [2.0, 4.0, 2.0], [1.0, 3.0, 1.0]]  # degenerate side CA :506
+    add(ca, [1, 3, 1], ca[0], 0), add(ca, [0, 0, 0], ca[0], 0), add(ca, [2, 4, 2], ca[1], 1), add(ca, [2.1, 4.1, 2.1], ca[1], 1)
+    add(ca, [4.0 / 3.0, 10.0 / 3.0, 4.0 / 3.0], [4.0 / 3.0, 10.0 / 3.0, 4.0 / 3.0], -1, 1e-16)
+    add(ca, [1, 4, 1], [4.0 / 3.0, 10.0 / 3.0, 4.0 / 3.0], -1, 1e-16)
+    pt = [[1.0, 3.0, 1.0]] * 3  # all sides degenerate :561
+    add(pt, [1, 3, 1], pt[0], 0), add(pt, [2, 4, 2], pt[0], 0)
+    return (np.asarray(P, np.float64), np.asarray(T, np.float64), 1e-50, np.asarray(C, np.float64), np.asarray(L, np.int32),
+            np.asarray(TOL, np.float64))
+
+
+def check_closest_point_tri(fn):
+    """fn(points, triangles, eps) -> (cp, loc)"""
+    P, T, eps, C, L, TOL = closest_point_tri_cases()
+    cp, loc = fn(P, T, eps)
+    assert np.array_equal(loc, L), (loc, L)
+    assert np.all(np.abs(cp - C) <= TOL[:, None]), np.abs(cp - C).max(axis=1)
+
+
+def check_squared_distance_point_box(fn):
+    """primal_squared_distance.cpp:167-201: 27 points around the cube [-1,1]^3, and the empty box; fn(points, boxes) -> d2"""
+    pts = np.array([[3.0 * i, 3.0 * j, 3.0 * k] for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)], np.float64)
+    cube = np.tile(np.array([-1, -1, -1, 1, 1, 1], np.float64), (27, 1))
+    want = np.array([(0 if i == 0 else 4) + (0 if j == 0 else 4) + (0 if k == 0 else 4) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)],
+                    np.float64)
+    assert np.allclose(fn(pts, cube), want, rtol=0, atol=1e-12)
+    big = np.finfo(np.float64).max
+    empty = np.tile(np.array([big, big, big, -big, -big, -big], np.float64), (27, 1))
+    assert np.array_equal(fn(pts, empty), np.full(27, big))
+
+
+def ray_box_cases():
+    """primal_ray_intersect.cpp:149-380 (ray_aabb_intersection_3D): rays from outside each face of [0,1]^3 (hit) and their
+    reverses (miss), then 60 rays from the box centre (hit).  -> (rays (n,6), boxes (n,6), expected)"""
+    x = np.linspace(0.0, 1.0, 3)
+    rays, want = [], []
+    faces = [((None, None, -1.0), (0, 0, 1)), ((None, None, 2.0), (0, 0, -1)), ((None, -1.0, None), (0, 1, 0)),
+             ((None, 2.0, None), (0, -1, 0)), ((-1.0, None, None), (1, 0, 0)), ((2.0, None, None), (-1, 0, 0))]
+    for origin, n in faces:
+        for a in x:
+            for b in x:
+                free = iter((a, b))
+                o = [next(free) if c is None else c for c in origin]
+                rays.append(o + list(map(float, n))), want.append(True)
+                rays.append(o + [-float(c) for c in n]), want.append(False)
+    for ang in np.linspace(0.0, 360.0, 20):
+        t = ang * np.pi / 180.0
+        c, s = np.cos(t), np.sin(t)
+        # Rx e1 = e1, Ry e2 = e2, Rz e3 = e3 (the reference multiplies each rotation with its own axis)
+        for n in ([1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.0, c, s], [s, 0.0, c], [c, s, 0.0]):
+            rays.append([0.5, 0.5, 0.5] + n), want.append(True)
+    rays = np.asarray(rays, np.float64)
+    boxes = np.tile(np.array([0, 0, 0, 1, 1, 1], np.float64), (len(rays), 1))
+    return rays, boxes, np.asarray(want, bool)
+
+
+def check_ray_box(fn):
+    """fn(rays, boxes, tol) -> bool per ray (the Ray constructor's normalisation applied)"""
+    rays, boxes, want = ray_box_cases()
+    assert np.array_equal(fn(rays, boxes, 1e-9), want)
+
+
+def check_box_scale(fn):
+    """primal_boundingbox.cpp:523-569 (bb_scale); fn(boxes, scale) -> scaled boxes"""
+    b = np.array([[1, 1, 1, 3, 3, 3]], np.float64)
+    assert np.array_equal(fn(b, 1.5), [[.5, .5, .5, 3.5, 3.5, 3.5]])
+    assert np.array_equal(fn(b, 0.5), [[1.5, 1.5, 1.5, 2.5, 2.5, 2.5]])
+    assert np.array_equal(fn(b, 0.0), [[2, 2, 2, 2, 2, 2]])
+    assert np.array_equal(fn(b, -1.0), b)
+    big = np.finfo(np.float64).max
+    inv = np.array([[big, big, big, -big, -big, -big]], np.float64)
+    assert np.array_equal(fn(inv, 1.5), inv)
+
+
+def sliver_triangle_cloud(n, seed=5):
+    """random point / triangle pairs that stress closest_point's region tests: slivers (area down to 1e-13), needles,
+    coincident vertices, query points on vertices / edges / within 1e-12 of them"""
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(-1, 1, (n, 3))
+    e1 = rng.uniform(-1, 1, (n, 3))
+    e2 = rng.uniform(-1, 1, (n, 3))
+    kind = rng.integers(0, 8, n)
+    s = 10.0 ** rng.uniform(-14, -1, (n, 1))
+    B = A + e1
+    C = A + e2
+    C = np.where((kind == 1)[:, None], A + e1 * rng.uniform(0, 1, (n, 1)) + s * e2, C)     # sliver: C almost on AB
+    B = np.where((kind == 2)[:, None], A + s * e1, B)                                       # needle: B almost at A
+    C = np.where((kind == 3)[:, None], B, C)                                                # B == C
+    B = np.where((kind == 4)[:, None], A, B)                                                # A == B
+    C = np.where((kind == 5)[:, None], A, C)                                                # A == C
+    tri = np.stack([A, B, C], axis=1)
+    w = rng.dirichlet([1, 1, 1], n)
+    onplane = (w[:, :, None] * tri).sum(axis=1)
+    nrm = np.cross(B - A, C - A)
+    pk = rng.integers(0, 6, n)
+    q = onplane + rng.uniform(-1, 1, (n, 1)) * nrm                                          # above the face
+    q = np.where((pk == 1)[:, None], tri[np.arange(n), rng.integers(0, 3, n)], q)          # exactly a vertex
+    t = rng.uniform(0, 1, (n, 1))
+    q = np.where((pk == 2)[:, None], A + t * (B - A), q)                                    # on edge AB
+    q = np.where((pk == 3)[:, None], B + t * (C - B) + 1e-12 * rng.uniform(-1, 1, (n, 3)), q)  # within 1e-12 of BC
+    q = np.where((pk == 4)[:, None], rng.uniform(-3, 3, (n, 3)), q)                         # anywhere
+    q = np.where((pk == 5)[:, None], A + 1e-13 * rng.uniform(-1, 1, (n, 3)), q)             # within 1e-13 of A
+    return np.ascontiguousarray(q), np.ascontiguousarray(tri.reshape(n, 9))
