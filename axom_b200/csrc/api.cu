@@ -15,6 +15,7 @@
 #include "radix_sort.cuh"
 #include "sd.cuh"
 #include "sd_fast.cuh"
+#include "sd_two.cuh"
 #include "meshtester.cuh"
 #include "leafmath.cuh"
 #include "dcp.cuh"
@@ -975,20 +976,22 @@ struct axb_sd
   bool count_work = false;
   SdParams prm;
   DevBuf x, y, z, conn, offsets, soup, cell_boxes, obounds, work;
-  DevBuf sdnodes, sdcens;
+  DevBuf sdnodes, sdcens, sdup;
   // per-query scratch, two sets: a host-to-host query is cut into chunks that alternate between two streams so
   // that the upload of chunk i+1 and the download of chunk i-1 overlap the kernel of chunk i
   struct QBufs
   {
-    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor;
+    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor, cand, cand_n, seed;
     void release(cudaStream_t st)
     {
-      for(DevBuf* b : {&q_stage, &out_phi, &out_cp, &out_n, &qkeys_a, &qkeys_b, &qscratch, &qperm, &qbounds, &cursor}) b->release(st);
+      for(DevBuf* b : {&q_stage, &out_phi, &out_cp, &out_n, &qkeys_a, &qkeys_b, &qscratch, &qperm, &qbounds, &cursor, &cand, &cand_n, &seed}) b->release(st);
     }
   } qb[2];
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
   int fast_blocks_per_sm = 0;  // occupancy of the persistent query kernel (queried once)
+  int two_blocks_per_sm = 0;   // same for sd_two_phase_kernel
+  int kernel = 2;              // mode 1 kernel: 2 = sd_two_phase_kernel (default), 1 = sd_fast_kernel (AXB_SD_KERNEL=fast)
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
   Ctx& ctx() { return bvh->ctx; }
 };
@@ -1161,6 +1164,24 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
         AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_fast_kernel<4>, 128, kSdFastSmem));
       }
       s->fast_blocks_per_sm = std::max(1, bps);
+      // the two-phase kernel: parent / range of every inner node for phase 2's climb
+      AXB_TRY(s->sdup.reserve(sizeof(SdUp) * (size_t)std::max(nl - 1, 1), ctx.stream));
+      AXB_LAUNCH(ctx, sd_up_kernel, blocks_for(nl - 1, 256), 256, bn, s->bvh->node_range.as<int2>(), nl - 1, s->sdup.as<SdUp>());
+      bps = 0;
+      if(s->nv == 3)
+      {
+        AXB_CUDA_TRY(cudaFuncSetAttribute(sd_min_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSd2SmemMin));
+        AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_min_kernel<3>, kSd2Threads, kSd2SmemMin));
+      }
+      else
+      {
+        AXB_CUDA_TRY(cudaFuncSetAttribute(sd_min_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSd2SmemMin));
+        AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sd_min_kernel<4>, kSd2Threads, kSd2SmemMin));
+      }
+      s->two_blocks_per_sm = std::max(1, bps);
+      s->kernel = 2;
+      if(const char* e = getenv("AXB_SD_KERNEL"))
+        if(!strcmp(e, "fast")) s->kernel = 1;
     }
     return ctx.sync();
   };
@@ -1181,7 +1202,7 @@ int axb_sd_destroy(axb_sd* s)
   {
     cudaSetDevice(s->ctx().device);
     cudaStream_t st = s->ctx().stream;
-    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->offsets, &s->soup, &s->cell_boxes, &s->obounds, &s->work, &s->sdnodes, &s->sdcens})
+    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->offsets, &s->soup, &s->cell_boxes, &s->obounds, &s->work, &s->sdnodes, &s->sdcens, &s->sdup})
       b->release(st);
     for(int k = 0; k < 2; ++k)
     {
@@ -1309,12 +1330,36 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
     AXB_CUDA_TRY(cudaMemsetAsync(B.cursor.p, 0, sizeof(unsigned int), ctx.stream));
     int sms = kNumSMsB200;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
-    const int grid = (int)std::min<long long>(blocks_for(npts, 128), (long long)sms * s->fast_blocks_per_sm);
+    const int grid = (int)std::min<long long>(blocks_for(npts, 128), (long long)sms * (s->kernel == 2 ? s->two_blocks_per_sm : s->fast_blocks_per_sm));
     // queries per cursor grab: a run of Morton neighbours, so a lane's consecutive queries are close and
     // the previous closest point is a useful first bound; small inputs keep every warp busy instead
     unsigned chunk = (unsigned)kQueryChunk;
     if(const char* e = getenv("AXB_SD_CHUNK")) chunk = (unsigned)std::max(32, atoi(e));
-    if(s->nv == 3)
+    if(s->kernel == 2)
+    {
+      // phase 1 (exact minimum + in-window leaves per query slot), phase 2 (state machine in the reference's order)
+      AXB_TRY(B.cand.reserve(sizeof(int32_t) * kCandCap * (size_t)npts, ctx.stream));
+      AXB_TRY(B.cand_n.reserve((size_t)npts, ctx.stream));
+      AXB_TRY(B.seed.reserve(sizeof(double) * (size_t)npts, ctx.stream));
+      const int grid2 = blocks_for(npts, kSd2Threads);
+      if(s->nv == 3)
+      {
+        AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
+                        B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk);
+        AXB_LAUNCH(ctx, sd_resolve_kernel<3>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
+                   s->bvh->leaf_parent.as<int32_t>(), s->soup.as<double>(), s->prm, q, npts, perm, B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(),
+                   B.seed.as<double>(), d_phi, d_cp, d_n, d_work);
+      }
+      else
+      {
+        AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
+                        B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk);
+        AXB_LAUNCH(ctx, sd_resolve_kernel<4>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
+                   s->bvh->leaf_parent.as<int32_t>(), s->soup.as<double>(), s->prm, q, npts, perm, B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(),
+                   B.seed.as<double>(), d_phi, d_cp, d_n, d_work);
+      }
+    }
+    else if(s->nv == 3)
       AXB_LAUNCH_SMEM(ctx, sd_fast_kernel<3>, grid, 128, kSdFastSmem, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->soup.as<double>(), s->prm, q,
                       npts, perm, d_phi, d_cp, d_n, d_work, B.cursor.as<unsigned int>(), chunk);
     else

@@ -60,12 +60,15 @@ static_assert(sizeof(SdCen) == 64, "SdCen is 2 x 32 B");
 // |M v|^2 <= (1 + 5e-7) |v|^2 for the rows M of a float-rounded frame: scale the bound down accordingly
 constexpr double kBoundScale = 1.0 - 1.0e-6;
 
-// the frame in double from the stored floats; the build and the query MUST agree bit for bit on t2
+// the frame in double from the stored floats; the build and the queries MUST agree bit for bit on t2, which is the
+// BINARY32 cross product of the two stored axes (separately rounded products and differences) so that the binary32
+// bound of sd_two.cuh sees exactly the frame the extents were measured in
 __device__ __forceinline__ void obb_axes(const float* f, V3* A)
 {
   A[0] = {(double)f[0], (double)f[1], (double)f[2]};
   A[1] = {(double)f[3], (double)f[4], (double)f[5]};
-  A[2] = v3cross(A[0], A[1]);
+  A[2] = {(double)__fsub_rn(__fmul_rn(f[1], f[5]), __fmul_rn(f[4], f[2])), (double)__fsub_rn(__fmul_rn(f[3], f[2]), __fmul_rn(f[0], f[5])),
+          (double)__fsub_rn(__fmul_rn(f[0], f[4]), __fmul_rn(f[3], f[1]))};
 }
 
 // extent [lo, hi] of a child along axis k, stored as centre c (float, nearest) and half extent h (float, rounded UP
@@ -76,7 +79,9 @@ __device__ __forceinline__ void store_extent(float* out, int k, double lo, doubl
   const float c = __double2float_rn(0.5 * (lo + hi));
   const double cd = (double)c;
   out[6 + k] = c;
-  out[9 + k] = __double2float_ru(fmax(hi - cd, cd - lo));
+  // the relative pad covers the two binary32 subtractions of obb_sqdist_f32 (2^-23 (|c| + h))
+  const double h = fmax(hi - cd, cd - lo);
+  out[9 + k] = __double2float_ru(h + 2.4e-7 * (fabs(cd) + h));
 }
 
 constexpr int kObbMaxRange = 262144;  // subtrees with more leaves keep only their AABB (an orientation no longer helps)

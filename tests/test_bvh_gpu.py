@@ -93,6 +93,25 @@ def test_build_1m(oracle):
     _check_build(oracle, boxes, 3)
 
 
+def test_build_c4_20m_surface(oracle, have_ref):
+    """BASELINE config 4's surface (20 M leaves): the only size at which build_radix_tree.hpp:336-339's float32(l)
+    rounding (above 2^24 leaves) and the 30-deep Morton tie chains of a sphere quantised to 10 bits per axis are
+    reachable.  Compared with the UNMODIFIED reference (oracle/_ref) when it is present, else with the port."""
+    x, y, z, conn = synth.icosphere(1000)
+    P = np.stack([x, y, z], axis=1)
+    t = P[conn]
+    boxes = np.ascontiguousarray(np.concatenate([t.min(axis=1), t.max(axis=1)], axis=1))
+    del t
+    assert len(boxes) == 20_000_000 > (1 << 24)
+    ref = oracle.Bvh(boxes, ndims=3, kind="reference" if have_ref else "port")
+    gpu = _gpu_bvh(boxes, 3)
+    A, G = ref.arrays(), gpu.arrays()
+    # heavy ties: this is what makes the case interesting
+    assert np.unique(A["mcodes"]).size < 0.5 * len(boxes)
+    for k in ("mcodes", "leafs", "inner_children", "bounds", "inner_nodes"):
+        assert np.array_equal(A[k], G[k]), k
+
+
 def test_soa_and_device_inputs(oracle):
     import torch
     boxes = synth.triangle_aabbs(5000, seed=9)

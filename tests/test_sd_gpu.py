@@ -130,6 +130,74 @@ def test_fast_mode_large_sorted_queries(oracle):
     assert np.array_equal(ref[1], cp)
 
 
+def _degenerate_mesh():
+    """icosphere(10) + what a dirty STL holds: triangles collapsed to a point or to a segment, slivers of area
+    ~1e-13 and ~1e-17, unwelded (coincident) vertex copies, a duplicated triangle and a 1e-16-thin triangle of
+    the kind primal_closest_point.cpp:239-372 uses"""
+    x, y, z, conn = synth.icosphere(10)
+    P = np.stack([x, y, z], 1)
+    nv = len(P)
+    extra_pts, extra_tris = [], []
+
+    def add(p):
+        extra_pts.append(np.asarray(p, np.float64))
+        return nv + len(extra_pts) - 1
+    # collapsed to a point (three equal ids) and to a segment (two equal ids)
+    extra_tris += [[5, 5, 5], [7, 9, 9], [11, 11, 40]]
+    # unwelded copies of existing vertices: a triangle on copies of a real triangle's vertices
+    a, b, c = conn[17]
+    extra_tris.append([add(P[a]), add(P[b]), add(P[c])])
+    # a duplicated triangle (same ids) and one with reversed winding
+    extra_tris.append(list(conn[33]))
+    extra_tris.append(list(conn[34][::-1]))
+    # slivers on an edge: third vertex 1e-12 / 1e-16 off the edge's midpoint -> area ~1e-13 / ~1e-17
+    for t, off in ((50, 1e-12), (51, 1e-16), (52, 0.0)):
+        a, b, c = conn[t]
+        m = 0.5 * (P[a] + P[b])
+        n = np.cross(P[b] - P[a], P[c] - P[a])
+        n /= np.linalg.norm(n)
+        extra_tris.append([a, b, add(m + off * n)])
+    # a needle: two vertices 1e-13 apart
+    a, b, c = conn[70]
+    extra_tris.append([a, add(P[a] + np.array([1e-13, 0, 0])), c])
+    # the reference KAT's thin triangle, scaled into the mesh's neighbourhood
+    extra_tris.append([add([0.6, 0.0, 0.0]), add([0.6, 1e-16, 0.0]), add([0.7, 0.0, 0.1])])
+    P2 = np.concatenate([P, np.array(extra_pts)])
+    conn2 = np.concatenate([conn, np.array(extra_tris, np.int32)]).astype(np.int32)
+    return P2[:, 0].copy(), P2[:, 1].copy(), P2[:, 2].copy(), conn2, len(conn)
+
+
+def test_degenerate_and_sliver_triangles(oracle, have_ref):
+    """A16 / A18: degenerate, sliver and coincident-vertex triangles reach closest_point(Point,Triangle), the
+    !degenerate() guard of the vertex pseudo-normal (quest/SignedDistance.hpp:722-728) and Triangle::angle on the
+    GPU, and must come out as in the reference (both kernels; watertight on/off)"""
+    from axom_b200 import SignedDistance
+    x, y, z, conn, nclean = _degenerate_mesh()
+    P = np.stack([x, y, z], 1)
+    rng = np.random.default_rng(21)
+    dirty = conn[nclean:]
+    qs = [synth.uniform_grid_points(-0.8, 0.8, 14)]
+    for t in dirty:                                   # on / next to every dirty triangle's vertices, edges, centroid
+        V = P[t]
+        cen = V.mean(axis=0)
+        qs += [V, V * 1.05, V * 0.95, V + rng.normal(0, 1e-7, (3, 3)), V + rng.normal(0, 1e-13, (3, 3)),
+               0.5 * (V + np.roll(V, 1, axis=0)), cen[None], cen[None] * 1.2, cen[None] + rng.normal(0, 1e-3, (8, 3))]
+    q = np.concatenate(qs)
+    kinds = (["reference"] if have_ref else []) + ["port"]
+    for wt in (True, False):
+        gpu = SignedDistance(x, y, z, conn, isWatertight=wt)
+        for kind in kinds:
+            rphi, rcp, rn = oracle.SignedDistance(x, y, z, conn, watertight=wt, kind=kind).compute(q, True, True)
+            for mode in (0, 1):
+                gpu.setMode(mode)
+                gphi, gcp, gn = gpu.computeDistances(q, True, True)
+                assert np.array_equal(rphi, gphi), (kind, wt, mode, int((rphi != gphi).sum()))
+                assert np.array_equal(rcp, gcp), (kind, wt, mode)
+                ok = np.isfinite(rn).all(axis=1)
+                assert np.array_equal(ok, np.isfinite(gn).all(axis=1))
+                assert np.allclose(rn[ok], gn[ok], rtol=0, atol=1e-12), (kind, wt, mode)
+
+
 def _mixed_sheet():
     """wavy 8x8 sheet: quads on the even squares, two triangles on the odd ones (MIXED_SHAPE mesh)"""
     g = np.linspace(-1, 1, 9)

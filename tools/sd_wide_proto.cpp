@@ -457,6 +457,143 @@ static QRes run_query(const double* q, int mode, const QRes* hint, double perfec
   return best;
 }
 
+
+// ---- packet simulation: 32 Morton-consecutive queries share the upper part of the walk (binary nodes, LEVELS must be 1) ----
+struct PStats
+{
+  double packet_leaf = 0, packet_nodes = 0, packet_lane_tests = 0, private_visits = 0, leaf_tests = 0, private_pushes = 0, maxpriv = 0, queries = 0;
+};
+static void run_packet(const double* Q /*32 x 3*/, const QRes* hints /*32 or null*/, QRes* out, int T, bool recheck, PStats& S)
+{
+  double thr[32], best[32];
+  int bpos[32];
+  for(int l = 0; l < 32; ++l)
+  {
+    best[l] = DBL_MAX;
+    bpos[l] = -1;
+    thr[l] = DBL_MAX;
+    if(hints && hints[l].pos >= 0)
+    {
+      V3 qv = {Q[3 * l], Q[3 * l + 1], Q[3 * l + 2]};
+      double s = tri_sqdist(qv, soup[3 * (size_t)hints[l].pos], soup[3 * (size_t)hints[l].pos + 1], soup[3 * (size_t)hints[l].pos + 2]);
+      thr[l] = thr_of(s);
+      S.leaf_tests += 1;
+    }
+  }
+  auto leaf = [&](int l, int pos) {
+    V3 qv = {Q[3 * l], Q[3 * l + 1], Q[3 * l + 2]};
+    double s = tri_sqdist(qv, soup[3 * (size_t)pos], soup[3 * (size_t)pos + 1], soup[3 * (size_t)pos + 2]);
+    S.leaf_tests += 1;
+    if(s < best[l])
+    {
+      best[l] = s;
+      bpos[l] = pos;
+    }
+    thr[l] = std::min(thr[l], thr_of(best[l]));
+  };
+  struct PE
+  {
+    int node;
+    unsigned mask;
+  };
+  const bool defer = getenv("DEFER_LEAF") && hints;
+  if(!hints) T = 33;
+  std::vector<PE> ws;
+  struct LE
+  {
+    int node;
+    double lb;
+  };
+  std::vector<LE> priv[32];
+  ws.push_back({0, 0xffffffffu});
+  while(!ws.empty())
+  {
+    PE e = ws.back();
+    ws.pop_back();
+    const Wide& wd = wide[e.node];
+    S.packet_nodes += 1;
+    unsigned m[2] = {0, 0};
+    double lbs[2][32];
+    for(int l = 0; l < 32; ++l)
+      if(e.mask >> l & 1)
+      {
+        S.packet_lane_tests += 1;
+        double r[3] = {Q[3 * l] - wd.org[0], Q[3 * l + 1] - wd.org[1], Q[3 * l + 2] - wd.org[2]};
+        for(int s = 0; s < 2; ++s)
+          if(wd.child[s] != INT32_MIN)
+          {
+            lbs[s][l] = obb_lb2(wd.ob[s], r, 0.0);
+            if(lbs[s][l] <= thr[l]) m[s] |= 1u << l;
+          }
+      }
+    // visit the child most lanes want last-pushed (first popped)
+    int order[2] = {0, 1};
+    if(__builtin_popcount(m[0]) > __builtin_popcount(m[1])) std::swap(order[0], order[1]);
+    for(int k = 0; k < 2; ++k)
+    {
+      int s = order[k];
+      if(!m[s]) continue;
+      int c = wd.child[s];
+      if(c < 0 && !defer)
+      {
+        for(int l = 0; l < 32; ++l)
+          if(m[s] >> l & 1)
+            if(lbs[s][l] <= thr[l]) { leaf(l, -c - 1); S.packet_leaf += 1; }
+      }
+      else if(c >= 0 && __builtin_popcount(m[s]) >= T)
+        ws.push_back({c, m[s]});
+      else
+        for(int l = 0; l < 32; ++l)
+          if(m[s] >> l & 1)
+          {
+            priv[l].push_back({c, lbs[s][l]});
+            S.private_pushes += 1;
+          }
+    }
+  }
+  for(int l = 0; l < 32; ++l)
+  {
+    S.maxpriv = std::max(S.maxpriv, (double)priv[l].size());
+    std::vector<LE>& st = priv[l];
+    if(getenv("BEST_FIRST") && st.size() > 1)
+    {
+      if(atoi(getenv("BEST_FIRST")) == 2)
+        std::sort(st.begin(), st.end(), [](const LE& a, const LE& b) { return a.lb > b.lb; });
+      else
+      {
+        size_t bi = 0;
+        for(size_t k = 1; k < st.size(); ++k)
+          if(st[k].lb < st[bi].lb) bi = k;
+        std::swap(st[bi], st.back());
+      }
+    }
+    while(!st.empty())
+    {
+      LE e = st.back();
+      st.pop_back();
+      if(recheck && e.lb > thr[l]) continue;
+      if(e.node < 0)
+      {
+        leaf(l, -e.node - 1);
+        continue;
+      }
+      const Wide& wd = wide[e.node];
+      S.private_visits += 1;
+      double r[3] = {Q[3 * l] - wd.org[0], Q[3 * l + 1] - wd.org[1], Q[3 * l + 2] - wd.org[2]};
+      double lb[2] = {DBL_MAX, DBL_MAX};
+      for(int s = 0; s < 2; ++s)
+        if(wd.child[s] != INT32_MIN) lb[s] = obb_lb2(wd.ob[s], r, 0.0);
+      int first = lb[0] <= lb[1] ? 0 : 1;  // nearer first: push the farther one
+      int second = 1 - first;
+      if(lb[second] <= thr[l]) st.push_back({wd.child[second], lb[second]});
+      if(lb[first] <= thr[l]) st.push_back({wd.child[first], lb[first]});
+    }
+    out[l].sq = best[l];
+    out[l].pos = bpos[l];
+    S.queries += 1;
+  }
+}
+
 static inline uint32_t compact3(uint32_t v)
 {
   v &= 0x09249249;
@@ -594,6 +731,46 @@ int main(int argc, char** argv)
            tot.maxv, tot.greedy_visits / nq, tot.slot_tests / nq, tot.leaf_tests / nq, tot.multi / nq);
     for(int k = 0; k < 12; ++k) printf(" %d", tot.hist[k]);
     printf("\n");
+  }
+  if(LEVELS == 1)
+  {
+    for(int T : {8, 12, 16, 20, 24})
+      for(int recheck = 1; recheck < 2; ++recheck)
+      {
+        PStats tot;
+        long mism = 0;
+#pragma omp parallel
+        {
+          PStats S;
+          long mm = 0;
+#pragma omp for schedule(dynamic, 1)
+          for(int r = 0; r < RUNS; ++r)
+          {
+            std::vector<QRes> res(RUNLEN);
+            for(int p = 0; p < RUNLEN / 32; ++p)
+            {
+              const double* q = &Q[3 * ((size_t)r * RUNLEN + 32 * p)];
+              run_packet(q, p ? &res[32 * (p - 1)] : nullptr, &res[32 * p], T, recheck != 0, S);
+              for(int l = 0; l < 32; ++l)
+                if(res[32 * p + l].sq != exact[(size_t)r * RUNLEN + 32 * p + l].sq) ++mm;
+            }
+          }
+#pragma omp critical
+          {
+            tot.packet_nodes += S.packet_nodes; tot.packet_leaf += S.packet_leaf;
+            tot.packet_lane_tests += S.packet_lane_tests;
+            tot.private_visits += S.private_visits;
+            tot.leaf_tests += S.leaf_tests;
+            tot.private_pushes += S.private_pushes;
+            tot.maxpriv = std::max(tot.maxpriv, S.maxpriv);
+            tot.queries += S.queries;
+            mism += mm;
+          }
+        }
+        printf("packet T=%2d recheck=%d: packet nodes/packet %.1f (lanes active %.1f), private visits/query %.1f, pushes/query %.1f (max %g), leaf tests/query %.2f (in packet phase %.2f), mismatches %ld\n",
+               T, recheck, tot.packet_nodes / (tot.queries / 32), tot.packet_lane_tests / std::max(1.0, tot.packet_nodes), tot.private_visits / tot.queries,
+               tot.private_pushes / tot.queries, tot.maxpriv, tot.leaf_tests / tot.queries, tot.packet_leaf / tot.queries, mism);
+      }
   }
   return 0;
 }
