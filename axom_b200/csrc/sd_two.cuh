@@ -56,13 +56,16 @@ __global__ void __launch_bounds__(256) sd_up_kernel(const Node<double, 3>* __res
   #define AXB_SD2_SMEM_STACK 16
 #endif
 #ifndef AXB_SD2_CAND_CAP
-  #define AXB_SD2_CAND_CAP 12
+  #define AXB_SD2_CAND_CAP 15
 #endif
 #ifndef AXB_SD2_LEAF_VOTE
   #define AXB_SD2_LEAF_VOTE 16
 #endif
 #ifndef AXB_SD2_FINISH_VOTE
   #define AXB_SD2_FINISH_VOTE 8
+#endif
+#ifndef AXB_SD2_BATCH_MIN
+  #define AXB_SD2_BATCH_MIN 32  // leaves waiting in the warp's pool that trigger a leaf batch
 #endif
 #ifndef AXB_SD2_FULL_VOTE
   #define AXB_SD2_FULL_VOTE 4
@@ -77,8 +80,27 @@ constexpr int kCandCap = AXB_SD2_CAND_CAP;     // remembered leaves per query
 // three-term dot product with FMAs 3 * 2^-24 |r|_1, the two subtractions 2^-24 (2 |r|_1 + 2 |c| + h): at most
 // 3.6e-7 |r|_1 (covered by m) + 2.4e-7 (|c| + h) (covered by the pad store_extent adds to h).  The third axis is
 // the binary32 cross product of the stored two, bit-identical in the build (obb_axes); the sum of three squares
-// loses 3 * 2^-24 relative and the frame is orthonormal to ~2e-7: kBoundScaleF.
-constexpr float kBoundScaleF = 1.0f - 3.0e-6f;
+// loses 4 * 2^-24 = 2.4e-7 relative and the frame is orthonormal to ~2e-7 (|M v|^2 <= (1 + 5e-7) |v|^2): kBoundScaleF.
+constexpr float kBoundScaleF = 1.0f - 1.0e-6f;
+#ifndef AXB_SD2_NORMAL_F64
+  #define AXB_SD2_NORMAL_F64 1
+#endif
+// the same with the first axis (the patch normal: the thin extent, where a margin of 5e-7 |r| is comparable to the
+// extent itself for far queries) evaluated in double: no margin on that axis, the result rounded DOWN to binary32
+__device__ __forceinline__ float obb_sqdist_mixed(const float* f, double qrx, double qry, double qrz, float rx, float ry, float rz, float m)
+{
+  const float t2x = __fsub_rn(__fmul_rn(f[1], f[5]), __fmul_rn(f[4], f[2]));
+  const float t2y = __fsub_rn(__fmul_rn(f[3], f[2]), __fmul_rn(f[0], f[5]));
+  const float t2z = __fsub_rn(__fmul_rn(f[0], f[4]), __fmul_rn(f[3], f[1]));
+  const double d0 = fma((double)f[0], qrx, fma((double)f[1], qry, (double)f[2] * qrz));
+  const float d1 = __fmaf_rn(f[3], rx, __fmaf_rn(f[4], ry, __fmul_rn(f[5], rz)));
+  const float d2 = __fmaf_rn(t2x, rx, __fmaf_rn(t2y, ry, __fmul_rn(t2z, rz)));
+  const double t0 = fabs(d0 - (double)f[6]) - (double)f[9];
+  const float g0 = t0 > 0.0 ? __double2float_rd(t0 * (1.0 - 1e-12)) : 0.f;
+  const float g1 = fmaxf(__fsub_rn(__fsub_rn(fabsf(__fsub_rn(d1, f[7])), f[10]), m), 0.f);
+  const float g2 = fmaxf(__fsub_rn(__fsub_rn(fabsf(__fsub_rn(d2, f[8])), f[11]), m), 0.f);
+  return __fmul_rn(__fmaf_rn(g0, g0, __fmaf_rn(g1, g1, __fmul_rn(g2, g2))), kBoundScaleF);
+}
 __device__ __forceinline__ float obb_sqdist_f32(const float* f, float rx, float ry, float rz, float m)
 {
   const float t2x = __fsub_rn(__fmul_rn(f[1], f[5]), __fmul_rn(f[4], f[2]));
@@ -114,6 +136,16 @@ __device__ __forceinline__ double leaf_min_sq(const double* __restrict__ soup, c
   return sq;
 }
 
+// prune_threshold with the tie window as a parameter: sqrt(EPS) + head-room when the pseudo-normal state machine
+// runs (computeSign), 0 when it does not -- then only the strict-< minimum and its exact ties can matter
+__device__ __forceinline__ double prune_threshold_w(double minSq, double window)
+{
+  if(minSq >= 1e300) return DBL_MAX;
+  const double d = sqrt(minSq) + window;
+  return d * d * (1.0 + 1e-12) + 1e-300;
+}
+constexpr double kTieWindow = 1.0000001e-6;  // prune_threshold's
+
 __device__ __forceinline__ void mincand_reset(MinCand& m)
 {
   m.minSq = DBL_MAX;
@@ -136,7 +168,8 @@ __device__ __noinline__ void sd_ordered_query(const SdNode* __restrict__ nodes, 
   Contribs cl;
   cl.n = 0;
   mincand_reset(m);
-  double thr = prune_threshold(seed_sq);
+  const double window = cn ? kTieWindow : 0.0;
+  double thr = prune_threshold_w(seed_sq, window);
   const double qp[3] = {q.x, q.y, q.z};
   int32_t cur = 0;
   float cur_lb = 0.f;
@@ -193,7 +226,7 @@ __device__ __noinline__ void sd_ordered_query(const SdNode* __restrict__ nodes, 
     {
       ++nleaf;
       check_leaf_lazy<NV>(soup, q, m, cl, -cur - 1, cn);
-      thr = fmin(thr, prune_threshold(m.minSq));
+      thr = fmin(thr, prune_threshold_w(m.minSq, window));
     }
     // next entry of the stack that can still matter
     bool got = false;
@@ -353,7 +386,7 @@ template <int NV>
 __global__ void __launch_bounds__(kSd2Threads, AXB_SD2_MIN_BLOCKS)
 sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup, Desc<3> qpts, int npts, const int32_t* __restrict__ perm,
               int32_t* __restrict__ cand, uint8_t* __restrict__ cand_n, double* __restrict__ seed, unsigned long long* __restrict__ work,
-              unsigned int* __restrict__ cursor, unsigned chunk)
+              unsigned int* __restrict__ cursor, unsigned chunk, double window)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned lane = lane_id();
@@ -442,7 +475,7 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
           {
             // the closest point of the lane's previous query (a Morton neighbour) is a point of the surface
             const double hx = minPt.x - qx, hy = minPt.y - qy, hz = minPt.z - qz;
-            thr = prune_threshold(hx * hx + hy * hy + hz * hz);
+            thr = prune_threshold_w(hx * hx + hy * hy + hz * hz, window);
             thr_f = thr < 3.0e38 ? __double2float_ru(thr) : inf_f;
           }
           ncand = 0;
@@ -464,7 +497,7 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
       continue;  // lanes just stored / were just refilled
     }
 
-    if(pool_n >= 32u || minner == 0u)
+    if(pool_n >= (unsigned)AXB_SD2_BATCH_MIN || minner == 0u)
     {
       // ---- leaf batch ----
       const unsigned nb = min(pool_n, 32u);
@@ -522,7 +555,7 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
         {
           if(rsq < minSq)
           {
-            const double nthr = prune_threshold(rsq);
+            const double nthr = prune_threshold_w(rsq, window);
             if(minSq > nthr) ncand = 0;  // everything remembered so far is outside the new window
             minSq = rsq;
             minPt = rcp;
@@ -563,7 +596,8 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
         const D4 r0 = ldg256(rec), r1 = ldg256(rec + 1), r2 = ldg256(rec + 2), r3 = ldg256(rec + 3);
         const long long ids = __double_as_longlong(r0.x);
         const int32_t child0 = (int32_t)(ids & 0xffffffffll), child1 = (int32_t)(ids >> 32);
-        const float rx = __double2float_rn(qx - r0.y), ry = __double2float_rn(qy - r0.z), rz = __double2float_rn(qz - r0.w);
+        const double qrx = qx - r0.y, qry = qy - r0.z, qrz = qz - r0.w;
+        const float rx = __double2float_rn(qrx), ry = __double2float_rn(qry), rz = __double2float_rn(qrz);
         const float r1n = fabsf(rx) + fabsf(ry) + fabsf(rz);
         const float mg = 5.0e-7f * r1n;
         float f[24];
@@ -576,7 +610,11 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
             f[2 * k + 1] = __int_as_float(__double2hiint(w[k]));
           }
         }
+#if AXB_SD2_NORMAL_F64
+        float s0 = obb_sqdist_mixed(f, qrx, qry, qrz, rx, ry, rz, mg), s1 = obb_sqdist_mixed(f + 12, qrx, qry, qrz, rx, ry, rz, mg);
+#else
         float s0 = obb_sqdist_f32(f, rx, ry, rz, mg), s1 = obb_sqdist_f32(f + 12, rx, ry, rz, mg);
+#endif
         // queries farther than binary32 squares can hold: no pruning by bound (valid children only)
         const bool huge = !(r1n < 1.0e18f);
         s0 = huge ? 0.f : s0;
@@ -782,99 +820,107 @@ __global__ void __launch_bounds__(kSd2Threads) sd_resolve_kernel(const SdNode* _
         e_sq[NSUB - 1] = v3dot(dq2, dq2);
       }
     }
-    // (b) pass 1: the exact minimum, and the first (sub-)triangle in list order that attains it
-    const int kmax = __reduce_max_sync(FULL, sel ? (unsigned)kk : 0u);
-    double msq = DBL_MAX;
-    int first_i = 0, first_u = 0;
-    for(int i = 0; i < kmax; ++i)
+    // (b) on the candidate lanes, in parallel; an owner's candidates are the lanes [base, base + kk): reductions over
+    // that segment are 4 shuffle steps (kk <= kCandCap < 16), flags travel by ballot
+    const int okk = __shfl_sync(FULL, sel ? kk : 0, fs.owner);
+    const int li = (int)lane - fs.obase;  // list index of this lane's candidate
+    const int seg_end = fs.obase + okk;
+    // the exact minimum and the first (sub-)triangle in list order that attains it
+    int lu = 0;
+    double lsq = e_sq[0];
+    if(NSUB == 2 && e_sq[NSUB - 1] < lsq)
     {
-      const int src = min(base + i, 31);
+      lsq = e_sq[NSUB - 1];
+      lu = 1;
+    }
+    double r_sq = (int)lane < fs.total ? lsq : DBL_MAX;
+    int r_li = li;
 #pragma unroll
-      for(int u = 0; u < NSUB; ++u)
+    for(int o = 1; o < 16; o <<= 1)
+    {
+      const double v2 = shfl_f64(r_sq, min((int)lane + o, 31));
+      const int i2 = __shfl_sync(FULL, r_li, min((int)lane + o, 31));
+      if((int)lane + o < seg_end && v2 < r_sq)  // ties keep the lower list index
       {
-        const double sq = shfl_f64(e_sq[u], src);
-        if(i < kk && sq < msq)
-        {
-          msq = sq;
-          first_i = i;
-          first_u = u;
-        }
+        r_sq = v2;
+        r_li = i2;
       }
     }
-    V3 cp0 = {0.0, 0.0, 0.0};
-    int type0 = 2;
+    const int head = min(max(fs.obase, 0), 31);
+    const double c_msq = shfl_f64(r_sq, head);
+    const int c_first = __shfl_sync(FULL, r_li, head);
+    const int first_lane = min(max(fs.obase + c_first, 0), 31);
+    const V3 bcp = lu == 0 ? e_cp[0] : e_cp[NSUB - 1];
+    const int btype = loc_type(lu == 0 ? e_loc[0] : e_loc[NSUB - 1]);
+    const V3 cp0 {shfl_f64(bcp.x, first_lane), shfl_f64(bcp.y, first_lane), shfl_f64(bcp.z, first_lane)};
+    const int type0 = __shfl_sync(FULL, btype, first_lane);
+    const int first_u = __shfl_sync(FULL, lu, first_lane);
+    // The in-window (sub-)triangles in two classes relative to the first minimum c0: G, the same feature (same
+    // location type, closest point within sqrt(EPS)/2), and O, clearly another one (other type, or closest point
+    // farther than 2 sqrt(EPS)).  If nothing falls in between and every O member is farther from the query than every
+    // G member, an O member can only be the running minimum BEFORE the first G member arrives, which then clears
+    // whatever it left: the final state is that of the G members alone, whatever the interleaving.
+    bool l_in = false, l_inG = false, l_gap = false, l_tie = false, l_G2 = false;
+    double l_maxG = 0.0, l_minO = DBL_MAX;
+    if((int)lane < fs.total)
     {
-      const int src = min(base + first_i, 31);
+      const double wthr = prune_threshold_w(c_msq, cn ? kTieWindow : 0.0);
+      int ng = 0;
 #pragma unroll
       for(int u = 0; u < NSUB; ++u)
       {
-        const V3 cp {shfl_f64(e_cp[u].x, src), shfl_f64(e_cp[u].y, src), shfl_f64(e_cp[u].z, src)};
-        const int loc = __shfl_sync(FULL, e_loc[u], src);
-        if(u == first_u)
+        const double sq = e_sq[u];
+        if(sq <= wthr)
         {
-          cp0 = cp;
-          type0 = loc_type(loc);
-        }
-      }
-    }
-    // pass 2: the in-window (sub-)triangles in two classes relative to the first minimum c0: G, the same feature
-    // (same location type, closest point within sqrt(EPS)/2), and O, clearly another one (other type, or closest
-    // point farther than 2 sqrt(EPS)).  If nothing falls in between and every O member is farther from the query than
-    // every G member, an O member can only be the running minimum BEFORE the first G member arrives, which then
-    // clears whatever it left: the final state is that of the G members alone, whatever the interleaving.
-    const double wthr = prune_threshold(msq);
-    unsigned long long pm = 0, pmG = 0;  // list indices of the in-window leaves / of those with a G member, 4 bits each
-    int nord = 0, nG = 0, ninG = 0;
-    bool gap = false, tie_hard = false;
-    double maxG = 0.0, minO = DBL_MAX;
-    for(int i = 0; i < kmax; ++i)
-    {
-      const int src = min(base + i, 31);
-      bool in = false, inG = false;
-#pragma unroll
-      for(int u = 0; u < NSUB; ++u)
-      {
-        const double sq = shfl_f64(e_sq[u], src);
-        const V3 cp {shfl_f64(e_cp[u].x, src), shfl_f64(e_cp[u].y, src), shfl_f64(e_cp[u].z, src)};
-        const int loc = __shfl_sync(FULL, e_loc[u], src);
-        if(i < kk && sq <= wthr)
-        {
-          in = true;
-          const V3 d = v3sub(cp, cp0);
+          l_in = true;
+          const V3 d = v3sub(e_cp[u], cp0);
           const double d2 = v3dot(d, d);
-          const bool same_type = loc_type(loc) == type0;
+          const bool same_type = loc_type(e_loc[u]) == type0;
           const bool isG = same_type && d2 <= 0.25 * EPS, isO = !same_type || d2 > 4.0 * EPS;
-          gap = gap || (!isG && !isO);
+          l_gap = l_gap || (!isG && !isO);
           if(isG)
           {
-            inG = true;
-            ++ninG;
-            maxG = fmax(maxG, sq);
-            if(sq == msq && !(i == first_i && u == first_u))
-              tie_hard = tie_hard || type0 == 2 || cp.x != cp0.x || cp.y != cp0.y || cp.z != cp0.z;
+            ++ng;
+            l_maxG = fmax(l_maxG, sq);
+            if(sq == c_msq && !(li == c_first && u == first_u))
+              l_tie = l_tie || type0 == 2 || e_cp[u].x != cp0.x || e_cp[u].y != cp0.y || e_cp[u].z != cp0.z;
           }
           else if(isO)
-            minO = fmin(minO, sq);
+            l_minO = fmin(l_minO, sq);
         }
       }
-      if(in)
+      l_inG = ng > 0;
+      l_G2 = ng > 1;
+    }
+    const unsigned m_in = __ballot_sync(FULL, l_in), m_G = __ballot_sync(FULL, l_inG), m_G2 = __ballot_sync(FULL, l_G2);
+    const unsigned m_gap = __ballot_sync(FULL, l_gap), m_tie = __ballot_sync(FULL, l_tie);
+#pragma unroll
+    for(int o = 1; o < 16; o <<= 1)
+    {
+      const double g2 = shfl_f64(l_maxG, min((int)lane + o, 31)), o2 = shfl_f64(l_minO, min((int)lane + o, 31));
+      if((int)lane + o < seg_end)
       {
-        pm |= (unsigned long long)i << (4 * nord);
-        ++nord;
-      }
-      if(inG)
-      {
-        pmG |= (unsigned long long)i << (4 * nG);
-        ++nG;
+        l_maxG = fmax(l_maxG, g2);
+        l_minO = fmin(l_minO, o2);
       }
     }
+    // back on the owner lanes
+    const int obl = min(max(base, 0), 31);
+    const double maxG = shfl_f64(l_maxG, obl), minO = shfl_f64(l_minO, obl);
+    const unsigned seg = sel ? (((kk >= 32 ? 0u : (1u << kk)) - 1u) << base) : 0u;
+    const bool gap = (m_gap & seg) != 0u, tie_hard = (m_tie & seg) != 0u;
     const bool g_only = !gap && minO > maxG;
-    int nin = nord;  // (sub-)triangles whose normal terms may be summed
-    if(g_only)
+    const unsigned bits = ((g_only ? m_G : m_in) & seg) >> base;  // list indices that go through the state machine
+    int nord = __popc(bits);
+    const int nin = g_only ? __popc(m_G & seg) + __popc(m_G2 & seg) : nord * NSUB;  // (sub-)triangles whose normal terms may be summed
+    unsigned long long pm = 0;  // those list indices, 4 bits each
     {
-      pm = pmG;
-      nord = nG;
-      nin = ninG;
+      unsigned bb = bits;
+      for(int i = 0; i < nord; ++i)
+      {
+        pm |= (unsigned long long)(__ffs(bb) - 1) << (4 * i);
+        bb &= bb - 1u;
+      }
     }
     const bool order_matters =
       nord >= 2 && (!g_only || tie_hard || (nrms != nullptr && cn && nin >= 3) || nin > kContribCap);
