@@ -38,6 +38,7 @@ _DESC = C.POINTER(ArrayDesc)
 _PD = C.POINTER(C.c_double)
 SYMBOLS = [
     ("axb_version", C.c_char_p, []),
+    ("axb_trim_pool", C.c_int, [C.c_int, C.c_uint64]),
     ("axb_last_error", C.c_char_p, []),
     ("axb_device_count", C.c_int, []),
     ("axb_status_string", C.c_char_p, [C.c_int]),

@@ -212,18 +212,29 @@ class BVH:
             if t:
                 # device-to-device copy into a tensor torch owns, then release the library buffer
                 _cudart_memcpy_d2d(candidates.data_ptr(), cand.value, 4 * t, self)
+        elif t == 0 or not cand.value:
+            candidates = np.empty(0, np.int32)  # no query, or no hit: the library hands back a null buffer
         else:
-            candidates = np.ctypeslib.as_array(C.cast(cand, C.POINTER(C.c_int32)), shape=(max(t, 1),))[:t].copy()
+            candidates = np.ctypeslib.as_array(C.cast(cand, C.POINTER(C.c_int32)), shape=(t,)).copy()
         check(self._L.axb_bvh_free_candidates(self._h, cand, space))
         return offsets, counts, candidates
 
+    @staticmethod
+    def _count(k, n, what):
+        if n is None:
+            return k.count
+        n = int(n)
+        if n < 0 or n > k.count:
+            raise ValueError("%s = %d but the array holds %d" % (what, n, k.count))
+        return n
+
     def findPoints(self, points, numPts=None):
         k = make_desc(points, self.ndims, self.dtype)
-        return self._find("points", k, k.count if numPts is None else int(numPts))
+        return self._find("points", k, self._count(k, numPts, "numPts"))
 
     def findBoundingBoxes(self, boxes, numBoxes=None):
         k = make_desc(boxes, 2 * self.ndims, self.dtype)
-        return self._find("boxes", k, k.count if numBoxes is None else int(numBoxes))
+        return self._find("boxes", k, self._count(k, numBoxes, "numBoxes"))
 
     def findRays(self, origins, directions=None, numRays=None, normalized=False):
         """rays as (origins, directions) AoS pairs or a 2*D-tuple of SoA components.
@@ -237,7 +248,7 @@ class BVH:
         else:
             k = make_desc(np.concatenate([np.asarray(origins, self.dtype).reshape(-1, D),
                                           np.asarray(directions, self.dtype).reshape(-1, D)], axis=1), 2 * D, self.dtype)
-        return self._find("rays", k, k.count if numRays is None else int(numRays), extra=(int(bool(normalized)),))
+        return self._find("rays", k, self._count(k, numRays, "numRays"), extra=(int(bool(normalized)),))
 
     # ---- traverser / parity views ----
     def getTraverser(self):

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,53 @@ static int fail(int status, const std::string& msg)
 }
 
 //------------------------------------------------------------------------------------------
+// The library's own stream-ordered memory pool, one per device.  Freed blocks stay in it (the per-call candidate
+// arrays are hundreds of MB: handing them back to the driver at every synchronisation, the default, turns each call
+// into a fresh allocation) up to a bounded release threshold (AXB_POOL_KEEP_MB, default 16384) -- the device's DEFAULT
+// pool, which other allocators in the process share, is left alone.  axb_trim_pool() gives the cached blocks back.
+//------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+static cudaMemPool_t g_pool[kMaxDevices] = {};
+static std::mutex g_pool_mutex;
+
+static cudaError_t pool_for_current_device(cudaMemPool_t* out)
+{
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if(e != cudaSuccess) return e;
+  if(dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if(!g_pool[dev])
+  {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    e = cudaMemPoolCreate(&g_pool[dev], &props);
+    if(e != cudaSuccess)
+    {
+      g_pool[dev] = nullptr;
+      return e;
+    }
+    unsigned long long keep = 16384ull << 20;
+    if(const char* env = getenv("AXB_POOL_KEEP_MB")) keep = (unsigned long long)std::max(0ll, atoll(env)) << 20;
+    cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  *out = g_pool[dev];
+  return cudaSuccess;
+}
+
+static cudaError_t axb_malloc_async(void** p, size_t bytes, cudaStream_t s)
+{
+  cudaMemPool_t pool = nullptr;
+  cudaError_t e = pool_for_current_device(&pool);
+  if(e != cudaSuccess) return e;
+  return cudaMallocFromPoolAsync(p, bytes, pool, s);
+}
+
+//------------------------------------------------------------------------------------------
 // stream-ordered device buffer (grow-only, reused across calls)
 //------------------------------------------------------------------------------------------
 struct DevBuf
@@ -47,7 +95,7 @@ struct DevBuf
     p = nullptr;
     cap = 0;
     const size_t want = bytes ? bytes : 16;
-    AXB_CUDA_TRY(cudaMallocAsync(&p, want, s));
+    AXB_CUDA_TRY(axb_malloc_async(&p, want, s));
     cap = want;
     return AXB_OK;
   }
@@ -104,16 +152,8 @@ struct Ctx
     AXB_CUDA_TRY(cudaSetDevice(device));
     AXB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     own_stream = true;
-    // keep freed blocks in the device's stream-ordered pool: by default the pool hands memory back to the
-    // driver at every synchronisation, which turns the per-call candidate array into a fresh
-    // multi-hundred-MB allocation each time
     cudaMemPool_t pool = nullptr;
-    if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool)
-    {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
+    AXB_CUDA_TRY(pool_for_current_device(&pool));  // the library's own pool (see above); the default pool is not touched
     return AXB_OK;
   }
   void drop_phases()
@@ -547,8 +587,8 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
     AXB_TRY(ctx.sync());
     if(htotal > 2147483647LL)
       return fail(AXB_ERR_OVERFLOW, "candidate total " + std::to_string(htotal) + " overflows int32 offsets: split the query batch");
-    AXB_CUDA_TRY(cudaMallocAsync((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
-    if(firsts) AXB_CUDA_TRY(cudaMallocAsync((void**)&d_first, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+    AXB_CUDA_TRY(axb_malloc_async((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+    if(firsts) AXB_CUDA_TRY(axb_malloc_async((void**)&d_first, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
     {
       ScopedPhase ph(ctx, "find.fill");
       AXB_LAUNCH(ctx, (fill_kernel<T, D, Query, Filter>), blocks_for(nq, 256), 256, nodes, leaf_nodes, q, nq, tol, flags,
@@ -633,8 +673,8 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
     if(htotal > 2147483647LL)
       return fail(AXB_ERR_OVERFLOW, "candidate total " + std::to_string(htotal) + " overflows int32 offsets: split the query batch");
     h->pair_hint[kind] = htotal;
-    AXB_CUDA_TRY(cudaMallocAsync((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
-    if(firsts) AXB_CUDA_TRY(cudaMallocAsync((void**)&d_first, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+    AXB_CUDA_TRY(axb_malloc_async((void**)&d_cand, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+    if(firsts) AXB_CUDA_TRY(axb_malloc_async((void**)&d_first, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
     ScopedPhase ph(ctx, "find.fill");
     if(hcur[2] == 0u)
     {
@@ -691,6 +731,19 @@ bool valid_bvh(const axb_bvh* b) { return b != nullptr; }
 extern "C" {
 
 const char* axb_version(void) { return AXB_VERSION_STRING; }
+
+int axb_trim_pool(int device, uint64_t keep_bytes)
+{
+  if(device < 0 || device >= kMaxDevices) return fail(AXB_ERR_BAD_ARG, "device ordinal out of range");
+  cudaMemPool_t pool = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    pool = g_pool[device];
+  }
+  if(!pool) return AXB_OK;  // nothing was ever allocated on this device
+  AXB_CUDA_TRY(cudaMemPoolTrimTo(pool, (size_t)keep_bytes));
+  return AXB_OK;
+}
 const char* axb_last_error(void) { return g_last_error.c_str(); }
 
 int axb_device_count(void)
@@ -1640,7 +1693,7 @@ int axb_meshtester_get_degenerate(axb_meshtester* m, int out_memspace, int32_t**
   AXB_CUDA_TRY(cudaMemcpyAsync(&htotal, d_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx.stream));
   AXB_TRY(ctx.sync());
   int32_t* d_idx = nullptr;
-  AXB_CUDA_TRY(cudaMallocAsync((void**)&d_idx, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
+  AXB_CUDA_TRY(axb_malloc_async((void**)&d_idx, sizeof(int32_t) * (size_t)std::max<long long>(htotal, 1), ctx.stream));
   AXB_LAUNCH(ctx, compact_flagged_kernel, blocks_for(m->ncells, 256), 256, m->degflag.as<int32_t>(), m->off.as<int32_t>(), m->ncells, d_idx);
   if(out_memspace == AXB_MEM_HOST)
   {

@@ -51,85 +51,93 @@ double s_lo[3], s_hi[3];  // compute_mesh_bounds of the surface mesh
 
 bool initialized() { return s_query != nullptr; }
 
-// STLReader::isAsciiFormat (:44-87)
-bool stl_is_ascii(const std::string& file)
+// The whole file in one read; the format test and both parsers work on the buffer.
+bool stl_slurp(const std::string& file, std::vector<char>& buf)
 {
-  std::ifstream ifs(file.c_str(), std::ios::in | std::ios::binary);
-  if(!ifs.is_open())
+  FILE* f = std::fopen(file.c_str(), "rb");
+  if(!f)
   {
     quest_warning("Cannot open the provided STL file [" + file + "]");
     return false;
   }
-  ifs.seekg(0, ifs.end);
-  const std::int32_t fileSize = static_cast<std::int32_t>(ifs.tellg());
-  const int totalHeaderSize = 80 + (int)sizeof(std::int32_t);
-  if(fileSize < totalHeaderSize) return true;
-  int numTris = 0;
-  ifs.seekg(80, ifs.beg);
-  ifs.read((char*)&numTris, sizeof(std::int32_t));
-  const int expectedBinarySize = totalHeaderSize + numTris * 50;
-  return fileSize != expectedBinarySize;
+  std::fseek(f, 0, SEEK_END);
+  const long size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  buf.resize(size > 0 ? (size_t)size : 0);
+  const size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
+  std::fclose(f);
+  buf.resize(got);
+  return true;
 }
 
-// STLReader::readAsciiSTL (:90-128): every "vertex x y z" token sequence is a node
-int stl_read_ascii(const std::string& file, std::vector<double>& nodes)
+// The reader's format rule (quest/readers/STLReader.cpp, isAsciiFormat): a file is binary exactly when its size is the
+// 84-byte header plus 50 bytes per face of the count stored at offset 80; anything shorter than a header is ASCII.
+bool stl_buffer_is_binary(const std::vector<char>& buf, std::int32_t& nfaces)
 {
-  std::ifstream ifs(file.c_str());
-  if(!ifs.is_open())
+  constexpr size_t kHeader = 80 + sizeof(std::int32_t);
+  nfaces = 0;
+  if(buf.size() < kHeader) return false;
+  std::memcpy(&nfaces, buf.data() + 80, sizeof(nfaces));
+  // the reader compares in 32-bit arithmetic (an int32 file size against header + 50 * count)
+  return static_cast<std::int32_t>(buf.size()) == static_cast<std::int32_t>(kHeader) + nfaces * 50;
+}
+
+// ASCII: every whitespace-delimited token "vertex" is followed by three numbers, one node (readAsciiSTL); the rest
+// of the grammar (solid / facet / normal / outer loop ...) is skipped.  A pointer scan with strtod instead of
+// formatted stream extraction.
+void stl_parse_ascii(std::vector<char>& buf, std::vector<double>& nodes)
+{
+  buf.push_back('\0');  // strtod needs a terminator
+  const char* p = buf.data();
+  const char* const end = p + buf.size() - 1;
+  auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; };
+  while(p < end)
   {
-    quest_warning("Cannot open the provided STL file [" + file + "]");
-    return -1;
-  }
-  std::string junk;
-  double x, y, z;
-  while(true)
-  {
-    do
+    while(p < end && is_space(*p)) ++p;
+    const char* tok = p;
+    while(p < end && !is_space(*p)) ++p;
+    if(p - tok != 6 || std::memcmp(tok, "vertex", 6) != 0) continue;
+    double v[3] = {0.0, 0.0, 0.0};
+    bool ok = true;
+    for(int k = 0; k < 3 && ok; ++k)
     {
-      ifs >> junk;
-    } while(ifs.good() && junk != "vertex");
-    if(ifs.fail()) break;
-    ifs >> x >> y >> z;
-    nodes.push_back(x);
-    nodes.push_back(y);
-    nodes.push_back(z);
+      char* next = nullptr;
+      v[k] = std::strtod(p, &next);
+      ok = next != p && next <= end;
+      if(ok) p = next;
+    }
+    nodes.insert(nodes.end(), v, v + 3);
+    if(!ok) break;  // a malformed vertex ends the read (the stream reader stops at its first failed extraction)
   }
-  return 0;
 }
 
-// STLReader::readBinarySTL (:131-191): 80-byte header, int32 face count, 50-byte records
-// (float normal[3], float vert[9], uint16 attr); vertices are widened to double
-int stl_read_binary(const std::string& file, std::vector<double>& nodes)
+// Binary: 50-byte face records after the header -- float normal[3] (ignored), float vertex[3][3], uint16 attribute --
+// vertices widened to double (readBinarySTL)
+void stl_parse_binary(const std::vector<char>& buf, std::int32_t nfaces, std::vector<double>& nodes)
 {
-  std::ifstream ifs(file.c_str(), std::ios::in | std::ios::binary);
-  if(!ifs.is_open())
+  if(nfaces <= 0) return;
+  nodes.resize((size_t)nfaces * 9);
+  const char* rec = buf.data() + 84;
+  for(std::int32_t i = 0; i < nfaces; ++i, rec += 50)
   {
-    quest_warning("Cannot open the provided STL file [" + file + "]");
-    return -1;
-  }
-  ifs.seekg(80);
-  std::int32_t nfaces = 0;
-  ifs.read((char*)&nfaces, sizeof(std::int32_t));
-  if(nfaces < 0) return -1;
-  nodes.reserve((size_t)nfaces * 9);
-  unsigned char raw[50];
-  for(std::int32_t i = 0; i < nfaces; ++i)
-  {
-    ifs.read((char*)raw, 50);
     float v[9];
-    std::memcpy(v, raw + 12, sizeof(v));
-    for(int j = 0; j < 9; ++j) nodes.push_back(static_cast<double>(v[j]));
+    std::memcpy(v, rec + 12, sizeof(v));
+    for(int j = 0; j < 9; ++j) nodes[(size_t)i * 9 + j] = static_cast<double>(v[j]);
   }
-  return 0;
 }
 
 // STLReader::read + getMesh (:194-259): SoA coordinates, implicit connectivity 3i, 3i+1, 3i+2
 int stl_read(const std::string& file, std::vector<double>& x, std::vector<double>& y, std::vector<double>& z, std::vector<int32_t>& conn)
 {
   if(file.empty()) return -1;
+  std::vector<char> buf;
+  if(!stl_slurp(file, buf)) return -1;
   std::vector<double> nodes;
-  const int rc = stl_is_ascii(file) ? stl_read_ascii(file, nodes) : stl_read_binary(file, nodes);
-  if(rc != 0) return rc;
+  std::int32_t nfaces = 0;
+  if(stl_buffer_is_binary(buf, nfaces))
+    stl_parse_binary(buf, nfaces, nodes);
+  else
+    stl_parse_ascii(buf, nodes);
   const size_t nn = nodes.size() / 3;
   const size_t nf = nn / 3;
   x.resize(nn);

@@ -239,13 +239,21 @@ class MarchingCubes:
             torch.cuda.current_stream(self.device).synchronize()  # the library works on its own stream
         check(self._L.axb_mc_set_mesh(self._h, arr, len(views), space))
         self._keep = keep if space == MEM_DEVICE else []  # device arrays are used in place: keep them alive
-        self._dirty = False
+        # The reference reads its views of the field and mask live on every computeIsocontour (m_fcnView / m_maskView).
+        # Device arrays are read in place here, so they behave the same; HOST arrays are staged by set_mesh, so the
+        # staging is repeated before every contour (an in-place update of the field between contours is then seen).
+        self._dirty = space != MEM_DEVICE
 
     # -- compute -------------------------------------------------------------------------
     def computeIsocontour(self, contourVal=0.0):
         """adds the contour at contourVal to the contour mesh computed so far (MarchingCubes.cpp:107-147)"""
         if self._dirty or self._h is None:
             self._push_mesh()
+        elif self._keep:
+            # device-resident inputs are read in place on the library's own stream: whatever torch has queued on its
+            # current stream (an in-place update of the field) must have finished first
+            import torch
+            torch.cuda.current_stream(self.device).synchronize()
         self._cache = None
         check(self._L.axb_mc_set_mask_value(self._h, self._mask_val))
         check(self._L.axb_mc_compute_isocontour(self._h, float(contourVal)))

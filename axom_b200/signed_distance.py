@@ -23,6 +23,14 @@ class SignedDistance:
         po = None
         if _is_torch(x):
             import torch
+            dev = torch.device("cuda", device)
+            for name, a, want in (("x", x, torch.float64), ("y", y, torch.float64), ("z", z, torch.float64),
+                                  ("cells_to_nodes", cells_to_nodes, torch.int32), ("cell_node_offsets", cell_node_offsets, torch.int32)):
+                if a is None:
+                    continue
+                if not _is_torch(a) or not a.is_cuda or a.device != dev or a.dtype != want:
+                    raise TypeError("%s must be a %s tensor on %s (got %s on %s): the library reads the device arrays in place"
+                                    % (name, want, dev, getattr(a, "dtype", type(a)), getattr(a, "device", "host")))
             xs = [a.contiguous() for a in (x, y, z)]
             conn = cells_to_nodes.contiguous().reshape(-1)
             torch.cuda.current_stream(xs[0].device).synchronize()  # the library works on its own stream

@@ -99,6 +99,9 @@ typedef struct axb_dcp axb_dcp;
 
 /* ---- library ------------------------------------------------------------------------ */
 const char* axb_version(void);
+/* Device memory the library frees stays cached in its OWN stream-ordered pool (not the device's default pool), up to
+ * AXB_POOL_KEEP_MB (environment, default 16384); this returns everything above keep_bytes to the driver. */
+int axb_trim_pool(int device, uint64_t keep_bytes);
 const char* axb_last_error(void);
 int axb_device_count(void);
 const char* axb_status_string(int status);

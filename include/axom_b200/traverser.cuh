@@ -3,7 +3,8 @@
 // (spin/policy/LinearBVH.hpp:57-109) used by callers that fuse their own leaf action into the walk
 // (quest::SignedDistance, DistributedClosestPoint, mir::TopologyMapper).  Include from CUDA code only.
 //
-//   traverse_tree(traverser, p, leafAction, predicate)            children entered left first
+//   traverse_tree(traverser, p, leafAction, predicate)            children entered left first -- EXCEPT when p is a
+//                                                                  primal::Point: nearer box centroid first (below)
 //   traverse_tree(traverser, p, leafAction, predicate, comp)      comp(leftBox, rightBox, p) == true
 //                                                                  enters the right child first
 //   leafAction(sorted_pos, leaf_nodes)   predicate(p, box) -> bool
@@ -100,6 +101,48 @@ __host__ __device__ inline void traverse_tree(const LinearBVHTraverser<T, D>& tr
                                               Predicate&& predicate)
 {
   traverse_tree(tr, p, leafAction, predicate, NoTraversePreference {});
+}
+
+// The POINT overload (spin/policy/LinearBVH.hpp:72-85): when the primitive is a primal::Point of the tree's own
+// type and dimension, overload resolution in the reference picks the version that enters the child whose box
+// CENTROID is nearer to the point first (an invalid right box counts as infinitely far).  Nearest-neighbour callers
+// (quest::SignedDistance, DistributedClosestPoint) depend on that order: with a strict < in the leaf action it decides
+// which of several equidistant items is reported.
+template <typename T, int D>
+struct NearerCentroidFirst
+{
+  __host__ __device__ bool operator()(const primal::BoundingBox<T, D>& l, const primal::BoundingBox<T, D>& r, const primal::Point<T, D>& p) const
+  {
+    // squared_distance(Point, Point) in double (primal/operators/squared_distance.hpp:62-75), centroid = 0.5 * (min + max)
+    double dl = 0.0, dr = 0.0;
+    for(int d = 0; d < D; ++d)
+    {
+      const T c = static_cast<T>(0.5) * (l.m_min.m_components[d] + l.m_max.m_components[d]);
+      const double v = static_cast<double>(c) - static_cast<double>(p.m_components[d]);
+      dl += v * v;
+    }
+    if(detail::box_is_valid(r))
+    {
+      for(int d = 0; d < D; ++d)
+      {
+        const T c = static_cast<T>(0.5) * (r.m_min.m_components[d] + r.m_max.m_components[d]);
+        const double v = static_cast<double>(c) - static_cast<double>(p.m_components[d]);
+        dr += v * v;
+      }
+    }
+    else
+    {
+      dr = 1.7976931348623157e308;
+    }
+    return dl > dr;
+  }
+};
+
+template <typename T, int D, typename LeafAction, typename Predicate>
+__host__ __device__ inline void traverse_tree(const LinearBVHTraverser<T, D>& tr, const primal::Point<T, D>& p, LeafAction&& leafAction,
+                                              Predicate&& predicate)
+{
+  traverse_tree(tr, p, leafAction, predicate, NearerCentroidFirst<T, D> {});
 }
 
 }  // namespace spin

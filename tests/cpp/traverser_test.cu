@@ -11,6 +11,7 @@
 // findBoundingBoxes' candidate lists in their order.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -46,7 +47,7 @@ __global__ void user_kernel(ab::spin::LinearBVHTraverser<double, 3> tr, const Pt
     return true;
   };
   auto leaf = [&](std::int32_t pos, const std::int32_t* leaf_nodes) { out[base + k++] = leaf_nodes[pos]; };
-  ab::spin::traverse_tree(tr, p, leaf, pred);
+  ab::spin::traverse_tree(tr, p, leaf, pred, ab::spin::NoTraversePreference {});  // findPoints' own order (LinearBVH.hpp:302-364)
   counts[i] = k;
 }
 
@@ -176,8 +177,100 @@ static int test_topology_mapper_pattern()
   return bad == 0 && worst_sum < 1e-12 ? 0 : 1;
 }
 
-int main()
+// The nearest-neighbour pattern of spin_bvh.cpp:1401-1554 (borrowed there from DistributedClosestPoint): a BVH over
+// zero-size boxes of 2-D points, one thread per query point, traverse_tree with the POINT overload, a strict-<
+// leaf action and a <= predicate on the running minimum.  Which of several equidistant points is reported depends on
+// the visiting order, i.e. on the centroid rule.  Results go to a file; tests/test_cpp_shim.py compares them with the
+// unmodified reference's own traverser on the same input.
+using Box2 = ab::primal::BoundingBox<double, 2>;
+using Pt2 = ab::primal::Point<double, 2>;
+__global__ void nearest_point_kernel(ab::spin::LinearBVHTraverser<double, 2> tr, const Pt2* src, const Pt2* qpts, int nq, int* min_elem,
+                                     double* min_sq)
 {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= nq) return;
+  const Pt2 q = qpts[i];
+  double best = 1.7976931348623157e308;
+  int elem = -1;
+  auto checkMinDist = [&](std::int32_t pos, const std::int32_t* leaf_nodes) {
+    const int c = leaf_nodes[pos];
+    double s = 0.0;
+    for(int d = 0; d < 2; ++d)
+    {
+      const double v = src[c].m_components[d] - q.m_components[d];
+      s += v * v;
+    }
+    if(s < best)
+    {
+      best = s;
+      elem = c;
+    }
+  };
+  auto traversePredicate = [&](const Pt2& p, const Box2& bb) -> bool {
+    double s = 0.0;  // squared_distance(Point, BoundingBox): clamp, then sum of squares
+    for(int d = 0; d < 2; ++d)
+    {
+      const double x = p.m_components[d], lo = bb.m_min.m_components[d], hi = bb.m_max.m_components[d];
+      const double c = x < lo ? lo : (x > hi ? hi : x);
+      const double v = c - x;
+      s += v * v;
+    }
+    return s <= best;
+  };
+  ab::spin::traverse_tree(tr, q, checkMinDist, traversePredicate);
+  min_elem[i] = elem;
+  min_sq[i] = best;
+}
+
+static int run_nearest_2d(const char* src_file, const char* query_file, const char* out_file)
+{
+  auto slurp = [](const char* f, std::vector<double>& v) {
+    FILE* fp = std::fopen(f, "rb");
+    if(!fp) return false;
+    std::fseek(fp, 0, SEEK_END);
+    const long n = std::ftell(fp);
+    std::fseek(fp, 0, SEEK_SET);
+    v.resize((size_t)n / sizeof(double));
+    const bool ok = v.empty() || std::fread(v.data(), 1, (size_t)n, fp) == (size_t)n;
+    std::fclose(fp);
+    return ok;
+  };
+  std::vector<double> s, q;
+  if(!slurp(src_file, s) || !slurp(query_file, q)) return 3;
+  const int ns = (int)(s.size() / 2), nq = (int)(q.size() / 2);
+  std::vector<Box2> boxes(ns > 0 ? ns : 1);
+  for(int i = 0; i < ns; ++i) boxes[i] = Box2(Pt2 {s[2 * i], s[2 * i + 1]}, Pt2 {s[2 * i], s[2 * i + 1]});  // BoxType(point)
+  ab::spin::BVH<2> bvh;
+  bvh.initialize(boxes.data(), ns);
+  Pt2 *d_src, *d_q;
+  int* d_elem;
+  double* d_sq;
+  CK(cudaMalloc(&d_src, sizeof(Pt2) * (ns > 0 ? ns : 1)));
+  CK(cudaMalloc(&d_q, sizeof(Pt2) * nq));
+  CK(cudaMalloc(&d_elem, sizeof(int) * nq));
+  CK(cudaMalloc(&d_sq, sizeof(double) * nq));
+  if(ns) CK(cudaMemcpy(d_src, s.data(), sizeof(double) * 2 * ns, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_q, q.data(), sizeof(double) * 2 * nq, cudaMemcpyHostToDevice));
+  nearest_point_kernel<<<(nq + 127) / 128, 128>>>(bvh.getTraverser(), d_src, d_q, nq, d_elem, d_sq);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<int> elem(nq);
+  std::vector<double> sq(nq);
+  CK(cudaMemcpy(elem.data(), d_elem, sizeof(int) * nq, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sq.data(), d_sq, sizeof(double) * nq, cudaMemcpyDeviceToHost));
+  FILE* fo = std::fopen(out_file, "wb");
+  if(!fo) return 3;
+  std::fwrite(elem.data(), sizeof(int), nq, fo);
+  std::fwrite(sq.data(), sizeof(double), nq, fo);
+  std::fclose(fo);
+  std::printf("traverser_test nearest2d: %d source points, %d queries\n", ns, nq);
+  return 0;
+}
+
+int main(int argc, char** argv)
+{
+  if(argc == 5 && std::string(argv[1]) == "--nearest2d") return run_nearest_2d(argv[2], argv[3], argv[4]);
+
   const int N = 20000, Q = 5000;
   std::vector<Box3> boxes;
   std::vector<Pt3> pts;

@@ -331,6 +331,43 @@ def test_gpu_accumulate_clear_relinquish(oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_field_updated_in_place_between_contours(oracle):
+    """the reference re-reads its live field / mask views on every computeIsocontour (m_fcnView, m_maskView): an
+    in-place update of the field followed by clearOutput() + computeIsocontour() must contour the NEW field, for host
+    arrays (re-staged per contour) and for device tensors (read in place, after torch's stream has drained)"""
+    import copy
+    import torch
+    mesh, mask_field, mask_val, _ = mc_cases.build("mc3d_row_domains")
+    for on_device in (False, True):
+        ref = copy.deepcopy(mesh)  # host twin for the oracle
+        m = copy.deepcopy(mesh)
+        if on_device:
+            m = synth.blueprint_to_device(m)
+        mc = MarchingCubes(device=0)
+        mc.setMesh(m, "mesh", mask_field)
+        mc.setFunctionField("dist")
+        mc.setMaskValue(mask_val)
+        mc.computeIsocontour(0.5)
+        first = (mc.getContourFacetCorners().copy(), mc.getContourNodeCoords().copy())
+        for name in m:
+            v = m[name]["fields"]["dist"]["values"]
+            if on_device:
+                v.mul_(0.5).add_(0.1)  # queued on torch's stream, not synchronised by the caller
+            else:
+                v *= 0.5
+                v += 0.1
+            r = ref[name]["fields"]["dist"]["values"]
+            r *= 0.5
+            r += 0.1
+        mc.clearOutput()
+        mc.computeIsocontour(0.5)
+        want = oracle.mc_isocontour(domain_views(ref, "mesh", "dist", mask_field), 0.5, mask_val=mask_val)
+        got = (mc.getContourFacetCorners(), mc.getContourNodeCoords(), mc.getContourFacetParents(), mc.getContourFacetDomainIds())
+        assert _same(got, want), on_device
+        assert got[1].shape != first[1].shape or not np.array_equal(got[1], first[1])  # the contour did move
+
+
+@pytest.mark.gpu
 def test_gpu_rejects_non_unique_strides():
     from axom_b200 import _lib
     mesh = synth.blueprint_structured_mesh(cells=(4, 4, 4))
