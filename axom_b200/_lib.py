@@ -98,6 +98,16 @@ SYMBOLS = [
     ("axb_dcp_get_bvh", C.c_int, [_P, _PP]),
     ("axb_dcp_compute_local_closest_points", C.c_int, [_P, C.c_int, _P, C.c_int32, C.c_int, _P, _P, _P, _P, _P, C.c_int]),
     ("axb_dcp_compute_bounded_closest_points", C.c_int, [_P, C.c_int, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    # the exchange steps (NCCL inside the library)
+    ("axb_comm_get_unique_id", C.c_int, [_P]),
+    ("axb_comm_create", C.c_int, [_PP, C.c_int, C.c_int, _P, C.c_int]),
+    ("axb_comm_destroy", C.c_int, [_P]),
+    ("axb_comm_get_rank", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("axb_comm_get_traffic", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("axb_comm_library", C.c_char_p, []),
+    ("axb_comm_allreduce_f64", C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
+    ("axb_sd_compute_distances_minreduce", C.c_int, [_P, _P, _DESC, C.c_int32, _P, C.c_int]),
+    ("axb_dcp_compute_closest_points", C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P, _P, _P, _P]),
     # quest::MarchingCubes
     ("axb_mc_create", C.c_int, [_PP, C.c_int, C.c_int]),
     ("axb_mc_destroy", C.c_int, [_P]),

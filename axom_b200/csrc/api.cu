@@ -321,6 +321,8 @@ static int stage_desc(Ctx& ctx, const axb_array_desc* in, long long count, size_
 
 }  // namespace axb
 
+#include "comm.cuh"
+
 using namespace axb;
 
 //==========================================================================================
@@ -1891,6 +1893,8 @@ struct axb_dcp
   Ctx& ctx() { return bvh->ctx; }
 };
 
+static void dcpx_release(axb_dcp* h, cudaStream_t st);
+
 extern "C" {
 
 int axb_dcp_set_mode(axb_dcp* h, int mode)
@@ -1928,6 +1932,7 @@ int axb_dcp_destroy(axb_dcp* h)
     for(DevBuf* b : {&h->pts, &h->dom, &h->boxes, &h->q_stage, &h->st_idx, &h->st_dom, &h->st_rank, &h->st_coords, &h->st_dist, &h->keys_a,
                      &h->keys_b, &h->scratch, &h->perm})
       b->release(st);
+    dcpx_release(h, st);
     axb_bvh_destroy(h->bvh);
   }
   delete h;
@@ -2135,6 +2140,434 @@ static int dcp_compute(axb_dcp* h, int rank, const double* query_coords, int32_t
     AXB_CUDA_TRY(cudaMemcpyAsync(cp_rank, d_rank, ib, cudaMemcpyDeviceToHost, ctx.stream));
     AXB_CUDA_TRY(cudaMemcpyAsync(cp_coords, d_coords, cb, cudaMemcpyDeviceToHost, ctx.stream));
     if(cp_distance) AXB_CUDA_TRY(cudaMemcpyAsync(cp_distance, d_dist, db, cudaMemcpyDeviceToHost, ctx.stream));
+  }
+  return ctx.finish_call();
+}
+
+}  // extern "C"
+
+//==========================================================================================
+// The exchange steps of the distributed cases (comm.cuh): NCCL communicator, partitioned-surface MIN,
+// DistributedClosestPoint::computeClosestPoints (quest/detail/DistributedClosestPointImpl.hpp:687-693, :737-851)
+//==========================================================================================
+struct DcpxScratch
+{
+  DevBuf counts, offs, boxes, Q, mine, nearest, slot, list, listn, q_pack, b_pack, st_idx, st_dom, st_rank, st_coords, st_dist, sq, smin, bound,
+    pos, win, cnt, send_off, send, recv, o_idx, o_dom, o_rank, o_coords, o_dist, q_own;
+  void release(cudaStream_t st)
+  {
+    for(DevBuf* b : {&counts, &offs, &boxes, &Q, &mine, &nearest, &slot, &list, &listn, &q_pack, &b_pack, &st_idx, &st_dom, &st_rank, &st_coords,
+                     &st_dist, &sq, &smin, &bound, &pos, &win, &cnt, &send_off, &send, &recv, &o_idx, &o_dom, &o_rank, &o_coords, &o_dist, &q_own})
+      b->release(st);
+  }
+};
+static std::map<axb_dcp*, DcpxScratch> g_dcpx;  // per-handle scratch of the collective path (released by axb_dcp_destroy)
+static std::mutex g_dcpx_mutex;
+
+static void dcpx_release(axb_dcp* h, cudaStream_t st)
+{
+  std::lock_guard<std::mutex> lock(g_dcpx_mutex);
+  auto it = g_dcpx.find(h);
+  if(it == g_dcpx.end()) return;
+  it->second.release(st);
+  g_dcpx.erase(it);
+}
+
+extern "C" {
+
+int axb_comm_get_unique_id(uint8_t* id_bytes)
+{
+  if(!id_bytes) return fail(AXB_ERR_BAD_ARG, "null id buffer");
+  NcclApi* api = nullptr;
+  AXB_TRY(nccl_api(&api));
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == AXB_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  AXB_NCCL_TRY(api, api->GetUniqueId(&id));
+  memcpy(id_bytes, &id, sizeof(id));
+  return AXB_OK;
+}
+
+int axb_comm_create(axb_comm** out, int nranks, int rank, const uint8_t* id_bytes, int device)
+{
+  if(!out) return fail(AXB_ERR_BAD_ARG, "null output handle");
+  *out = nullptr;
+  if(nranks < 1 || rank < 0 || rank >= nranks || !id_bytes) return fail(AXB_ERR_BAD_ARG, "bad communicator arguments");
+  int count = 0;
+  if(cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+  {
+    cudaGetLastError();
+    return fail(AXB_ERR_NO_DEVICE, "no CUDA device available (libaxb200 has no CPU fallback)");
+  }
+  if(device < 0 || device >= count) return fail(AXB_ERR_BAD_ARG, "device ordinal out of range");
+  NcclApi* api = nullptr;
+  AXB_TRY(nccl_api(&api));
+  AXB_CUDA_TRY(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof(id));
+  ncclComm_t c = nullptr;
+  AXB_NCCL_TRY(api, api->CommInitRank(&c, nranks, id, rank));
+  axb_comm* h = new axb_comm();
+  h->api = api;
+  h->comm = c;
+  h->nranks = nranks;
+  h->rank = rank;
+  h->device = device;
+  *out = h;
+  return AXB_OK;
+}
+
+int axb_comm_destroy(axb_comm* c)
+{
+  if(!c) return AXB_OK;
+  if(c->comm)
+  {
+    cudaSetDevice(c->device);
+    c->api->CommDestroy(c->comm);
+  }
+  delete c;
+  return AXB_OK;
+}
+
+int axb_comm_get_rank(const axb_comm* c, int* rank, int* nranks)
+{
+  if(!c) return fail(AXB_ERR_BAD_ARG, "null communicator");
+  if(rank) *rank = c->rank;
+  if(nranks) *nranks = c->nranks;
+  return AXB_OK;
+}
+
+int axb_comm_get_traffic(const axb_comm* c, int64_t* bytes, int64_t* collectives)
+{
+  if(!c) return fail(AXB_ERR_BAD_ARG, "null communicator");
+  if(bytes) *bytes = c->bytes;
+  if(collectives) *collectives = c->calls;
+  return AXB_OK;
+}
+
+const char* axb_comm_library(void)
+{
+  NcclApi* api = nullptr;
+  if(nccl_api(&api) != AXB_OK) return "";
+  static thread_local std::string s;
+  int v = 0;
+  api->GetVersion(&v);
+  s = api->where + " version " + std::to_string(v);
+  return s.c_str();
+}
+
+// elementwise MIN / MAX / SUM of a device array of doubles over the ranks, in place, on `cuda_stream`
+int axb_comm_allreduce_f64(axb_comm* c, double* device_buf, int64_t n, int op, void* cuda_stream)
+{
+  if(!c) return fail(AXB_ERR_BAD_ARG, "null communicator");
+  if(n < 0 || (n > 0 && !device_buf)) return fail(AXB_ERR_BAD_ARG, "null or negative buffer");
+  if(op < 0 || op > 2) return fail(AXB_ERR_BAD_ARG, "op must be 0 (min), 1 (max) or 2 (sum)");
+  AXB_CUDA_TRY(cudaSetDevice(c->device));
+  const ncclRedOp_t ops[3] = {ncclMin, ncclMax, ncclSum};
+  AXB_NCCL_TRY(c->api, c->api->AllReduce(device_buf, device_buf, (size_t)n, ncclDouble, ops[op], c->comm, (cudaStream_t)cuda_stream));
+  c->bytes += 8 * n;
+  c->calls += 1;
+  return AXB_OK;
+}
+
+// C5: every rank holds ONE PART of the surface in `s` (built with compute_sign = 0) and the SAME query points; the result on
+// every rank is the distance to the whole surface = the elementwise MIN of the ranks' partial distances.  The query kernel
+// writes into the buffer the reduction then runs on, in place, on the same stream: no copy, no host round trip between.
+int axb_sd_compute_distances_minreduce(axb_sd* s, axb_comm* c, const axb_array_desc* qpts, int32_t npts, double* dist, int out_memspace)
+{
+  if(!s || !c) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(npts < 0) return fail(AXB_ERR_BAD_ARG, "negative point count");
+  if(npts > 0 && (!dist || !qpts)) return fail(AXB_ERR_BAD_ARG, "null query descriptor or output");
+  if(s->prm.compute_sign) return fail(AXB_ERR_BAD_ARG, "the MIN over surface parts is defined for unsigned distances: create the handle with compute_sign = 0");
+  if(c->device != s->ctx().device) return fail(AXB_ERR_BAD_ARG, "communicator and SignedDistance handle live on different devices");
+  out_memspace = resolve_memspace(out_memspace, dist);
+  if(out_memspace != AXB_MEM_HOST && out_memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown output memspace");
+  if(!s->bvh->built) return fail(AXB_ERR_NOT_BUILT, "SignedDistance query before setMesh()");
+  Ctx& ctx = s->ctx();
+  AXB_TRY(ctx.bind());
+  ctx.begin_call();
+  if(npts == 0) return AXB_OK;  // (every rank passes the same count, so every rank returns here)
+  const int tot = ctx.phase_begin("query.total");
+  axb_sd::QBufs& B = s->qb[0];
+  double* d_out = dist;
+  if(out_memspace == AXB_MEM_HOST)
+  {
+    AXB_TRY(B.out_phi.reserve(sizeof(double) * (size_t)npts, ctx.stream));
+    d_out = B.out_phi.as<double>();
+  }
+  AXB_TRY(sd_query_range(s, B, qpts, npts, d_out, nullptr, nullptr, AXB_MEM_DEVICE, nullptr));
+  {
+    ScopedPhase ph(ctx, "query.minreduce");
+    AXB_NCCL_TRY(c->api, c->api->AllReduce(d_out, d_out, (size_t)npts, ncclDouble, ncclMin, c->comm, ctx.stream));
+    c->bytes += 8ll * npts;
+    c->calls += 1;
+  }
+  if(out_memspace == AXB_MEM_HOST) AXB_CUDA_TRY(cudaMemcpyAsync(dist, d_out, sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.phase_end(tot);
+  if(out_memspace == AXB_MEM_HOST) AXB_TRY(ctx.sync());
+  return ctx.finish_call();
+}
+
+}  // extern "C"
+
+// computeClosestPoints (:737-851) as collectives; see comm.cuh for the protocol
+template <int D>
+static int dcpx_compute(axb_dcp* h, axb_comm* c, DcpxScratch& S, const double* d_q, int32_t nq, int32_t* o_idx, int32_t* o_dom, int32_t* o_rank,
+                        double* o_coords, double* o_dist)
+{
+  Ctx& ctx = h->ctx();
+  NcclApi* api = c->api;
+  const int N = c->nranks, rank = c->rank;
+  cudaStream_t st = ctx.stream;
+  const bool was_async = ctx.async;
+  // ---- 1: counts, query blocks, object boxes ----
+  std::vector<long long> counts(N), offs(N + 1, 0);
+  {
+    ScopedPhase ph(ctx, "dcpx.counts");
+    AXB_TRY(S.counts.reserve(sizeof(long long) * (size_t)(N + 1), st));
+    const long long mine = nq;
+    AXB_CUDA_TRY(cudaMemcpyAsync(S.counts.as<long long>() + N, &mine, sizeof(long long), cudaMemcpyHostToDevice, st));
+    AXB_NCCL_TRY(api, api->AllGather(S.counts.as<long long>() + N, S.counts.p, 1, ncclInt64, c->comm, st));
+    AXB_CUDA_TRY(cudaMemcpyAsync(counts.data(), S.counts.p, sizeof(long long) * (size_t)N, cudaMemcpyDeviceToHost, st));
+    AXB_TRY(ctx.sync());
+    c->bytes += 8;
+    c->calls += 1;
+  }
+  for(int r = 0; r < N; ++r) offs[r + 1] = offs[r] + counts[r];
+  const long long ntot = offs[N];
+  if(counts[rank] != nq) return fail(AXB_ERR_CUDA, "the gathered query count of this rank differs from the one passed in");
+  if(ntot > 2147483647LL) return fail(AXB_ERR_OVERFLOW, "more than 2^31-1 query points in one computeClosestPoints: split the call");
+  if(ntot == 0) return AXB_OK;
+  const size_t nt = (size_t)ntot;
+  {
+    ScopedPhase ph(ctx, "dcpx.gather");
+    AXB_TRY(S.offs.reserve(sizeof(long long) * (size_t)(N + 1), st));
+    AXB_CUDA_TRY(cudaMemcpyAsync(S.offs.p, offs.data(), sizeof(long long) * (size_t)(N + 1), cudaMemcpyHostToDevice, st));
+    AXB_TRY(S.Q.reserve(sizeof(double) * D * nt, st));
+    AXB_NCCL_TRY(api, api->GroupStart());
+    for(int r = 0; r < N; ++r)
+      if(counts[r] > 0)
+        AXB_NCCL_TRY(api, api->Broadcast(r == rank ? (const void*)d_q : (const void*)(S.Q.as<double>() + (size_t)offs[r] * D),
+                                         S.Q.as<double>() + (size_t)offs[r] * D, (size_t)counts[r] * D, ncclDouble, r, c->comm, st));
+    AXB_NCCL_TRY(api, api->GroupEnd());
+    c->bytes += 8ll * D * nq;
+    c->calls += 1;
+    // gatherBVHRoots (:671-693): every rank's object bounding box (invalid = no object points)
+    double hb[6] = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
+    if(h->npts > 0)
+    {
+      double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+      AXB_TRY(axb_bvh_get_bounds(h->bvh, lo, hi));
+      for(int d = 0; d < 3; ++d)
+      {
+        hb[d] = d < D ? lo[d] : 0.0;
+        hb[3 + d] = d < D ? hi[d] : 0.0;
+      }
+    }
+    AXB_TRY(S.boxes.reserve(sizeof(double) * 6 * (size_t)(N + 1), st));
+    AXB_CUDA_TRY(cudaMemcpyAsync(S.boxes.as<double>() + 6 * (size_t)N, hb, sizeof(hb), cudaMemcpyHostToDevice, st));
+    AXB_NCCL_TRY(api, api->AllGather(S.boxes.as<double>() + 6 * (size_t)N, S.boxes.p, 6, ncclDouble, c->comm, st));
+    AXB_TRY(ctx.sync());  // hb and offs leave scope / are reused
+    c->bytes += 48;
+    c->calls += 1;
+  }
+  DcpxRanks R;
+  R.offs = S.offs.as<long long>();
+  R.boxes = S.boxes.as<double>();
+  R.nranks = N;
+  R.rank = rank;
+  // ---- 2: first search (the rank whose box centre is nearest), bound = MIN over ranks ----
+  AXB_TRY(S.mine.reserve(sizeof(double) * nt, st));
+  AXB_TRY(S.nearest.reserve(sizeof(int32_t) * nt, st));
+  AXB_TRY(S.slot.reserve(sizeof(int32_t) * nt, st));
+  AXB_TRY(S.list.reserve(sizeof(int32_t) * nt, st));
+  AXB_TRY(S.listn.reserve(sizeof(unsigned int) * 2, st));
+  AXB_TRY(S.q_pack.reserve(sizeof(double) * D * nt, st));
+  AXB_TRY(S.b_pack.reserve(sizeof(double) * nt, st));
+  AXB_TRY(S.st_idx.reserve(sizeof(int32_t) * nt, st));
+  AXB_TRY(S.st_dom.reserve(sizeof(int32_t) * nt, st));
+  AXB_TRY(S.st_rank.reserve(sizeof(int32_t) * nt, st));
+  AXB_TRY(S.st_coords.reserve(sizeof(double) * D * nt, st));
+  AXB_TRY(S.st_dist.reserve(sizeof(double) * nt, st));
+  AXB_TRY(S.bound.reserve(sizeof(double) * nt, st));
+  AXB_TRY(S.sq.reserve(sizeof(double) * nt, st));
+  AXB_TRY(S.smin.reserve(sizeof(double) * nt, st));
+  AXB_TRY(S.pos.reserve(nt, st));
+  AXB_TRY(S.win.reserve(nt, st));
+  unsigned int hn[2] = {0u, 0u};
+  int n1 = 0, n2 = 0;
+  {
+    ScopedPhase ph(ctx, "dcpx.search1");
+    AXB_CUDA_TRY(cudaMemsetAsync(S.listn.p, 0, sizeof(unsigned int) * 2, st));
+    AXB_LAUNCH(ctx, dcpx_classify_kernel<D>, blocks_for(ntot, 256), 256, S.Q.as<double>(), ntot, R, h->sq_thresh, S.mine.as<double>(),
+               S.nearest.as<int32_t>(), S.slot.as<int32_t>(), S.list.as<int32_t>(), S.listn.as<unsigned int>());
+    AXB_CUDA_TRY(cudaMemcpyAsync(hn, S.listn.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    AXB_TRY(ctx.sync());
+    n1 = (int)hn[0];
+    if(n1 > 0)
+    {
+      AXB_LAUNCH(ctx, dcpx_gather_kernel<D>, blocks_for(n1, 256), 256, S.Q.as<double>(), S.list.as<int32_t>(), n1, 0, (const double*)nullptr,
+                 S.q_pack.as<double>(), (double*)nullptr, S.slot.as<int32_t>());
+      ctx.async = true;  // stay on the stream: the collectives below are ordered behind the search
+      const int rc = axb_dcp_compute_local_closest_points(h, rank, S.q_pack.as<double>(), n1, 1, S.st_idx.as<int32_t>(), S.st_dom.as<int32_t>(),
+                                                          S.st_rank.as<int32_t>(), S.st_coords.as<double>(), S.st_dist.as<double>(), AXB_MEM_DEVICE);
+      ctx.async = was_async;
+      AXB_TRY(rc);
+    }
+    AXB_LAUNCH(ctx, dcpx_sq_kernel<D>, blocks_for(ntot, 256), 256, S.Q.as<double>(), ntot, S.slot.as<int32_t>(), S.st_rank.as<int32_t>(),
+               S.st_coords.as<double>(), S.bound.as<double>(), (double*)nullptr);
+  }
+  {
+    ScopedPhase ph(ctx, "dcpx.bound_allreduce");
+    AXB_NCCL_TRY(api, api->AllReduce(S.bound.p, S.bound.p, nt, ncclDouble, ncclMin, c->comm, st));
+    c->bytes += 8ll * ntot;
+    c->calls += 1;
+  }
+  // ---- 3: bounded search on the other ranks (the ring prunes with the same two tests, per block: :762-775, :859-878, :1037-1040) ----
+  {
+    ScopedPhase ph(ctx, "dcpx.search2");
+    AXB_LAUNCH(ctx, dcpx_classify2_kernel, blocks_for(ntot, 256), 256, ntot, rank, h->sq_thresh, S.mine.as<double>(), S.nearest.as<int32_t>(),
+               S.bound.as<double>(), S.list.as<int32_t>(), S.listn.as<unsigned int>() + 1);
+    AXB_CUDA_TRY(cudaMemcpyAsync(hn + 1, S.listn.as<unsigned int>() + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    AXB_TRY(ctx.sync());
+    n2 = (int)hn[1];
+    if(n2 > 0)
+    {
+      AXB_LAUNCH(ctx, dcpx_gather_kernel<D>, blocks_for(n2, 256), 256, S.Q.as<double>(), S.list.as<int32_t>(), n2, n1, S.bound.as<double>(),
+                 S.q_pack.as<double>(), S.b_pack.as<double>(), S.slot.as<int32_t>());
+      ctx.async = true;
+      const int rc = axb_dcp_compute_bounded_closest_points(h, rank, S.q_pack.as<double>(), n2, S.b_pack.as<double>(), S.st_idx.as<int32_t>() + n1,
+                                                            S.st_dom.as<int32_t>() + n1, S.st_rank.as<int32_t>() + n1,
+                                                            S.st_coords.as<double>() + (size_t)n1 * D, S.st_dist.as<double>() + n1);
+      ctx.async = was_async;
+      AXB_TRY(rc);
+    }
+  }
+  // ---- 4: the winner of every query, exactly as the ring would pick it ----
+  std::vector<unsigned int> hc(2 * (size_t)N, 0u);
+  {
+    ScopedPhase ph(ctx, "dcpx.combine");
+    AXB_LAUNCH(ctx, dcpx_sq_kernel<D>, blocks_for(ntot, 256), 256, S.Q.as<double>(), ntot, S.slot.as<int32_t>(), S.st_rank.as<int32_t>(),
+               S.st_coords.as<double>(), S.sq.as<double>(), S.smin.as<double>());
+    AXB_NCCL_TRY(api, api->AllReduce(S.smin.p, S.smin.p, nt, ncclDouble, ncclMin, c->comm, st));
+    AXB_LAUNCH(ctx, dcpx_pos_kernel, blocks_for(ntot, 256), 256, ntot, R, S.sq.as<double>(), S.smin.as<double>(), S.pos.as<uint8_t>(),
+               S.win.as<uint8_t>());
+    AXB_NCCL_TRY(api, api->AllReduce(S.win.p, S.win.p, nt, ncclUint8, ncclMin, c->comm, st));
+    c->bytes += 9ll * ntot;
+    c->calls += 2;
+    AXB_TRY(S.cnt.reserve(sizeof(unsigned int) * 3 * (size_t)N, st));
+    AXB_CUDA_TRY(cudaMemsetAsync(S.cnt.p, 0, sizeof(unsigned int) * 3 * (size_t)N, st));
+    AXB_LAUNCH(ctx, dcpx_count_kernel, capped_grid(ntot, 256), 256, ntot, R, S.pos.as<uint8_t>(), S.win.as<uint8_t>(), S.cnt.as<unsigned int>(),
+               S.cnt.as<unsigned int>() + N);
+    AXB_CUDA_TRY(cudaMemcpyAsync(hc.data(), S.cnt.p, sizeof(unsigned int) * 2 * (size_t)N, cudaMemcpyDeviceToHost, st));
+    AXB_TRY(ctx.sync());
+  }
+  // ---- 5: every winner sends its record to the query's home rank ----
+  {
+    ScopedPhase ph(ctx, "dcpx.exchange");
+    std::vector<long long> soff(N + 1, 0), roff(N + 1, 0);
+    for(int r = 0; r < N; ++r)
+    {
+      soff[r + 1] = soff[r] + hc[r];
+      roff[r + 1] = roff[r] + hc[N + r];
+    }
+    if(roff[N] > nq) return fail(AXB_ERR_CUDA, "internal error: more winners than query points");
+    AXB_TRY(S.send_off.reserve(sizeof(long long) * (size_t)(N + 1), st));
+    AXB_CUDA_TRY(cudaMemcpyAsync(S.send_off.p, soff.data(), sizeof(long long) * (size_t)(N + 1), cudaMemcpyHostToDevice, st));
+    AXB_TRY(S.send.reserve(sizeof(DcpxRecord) * (size_t)std::max<long long>(soff[N], 1), st));
+    AXB_TRY(S.recv.reserve(sizeof(DcpxRecord) * (size_t)std::max<long long>(roff[N], 1), st));
+    if(soff[N] > 0)
+      AXB_LAUNCH(ctx, dcpx_pack_kernel<D>, blocks_for(ntot, 256), 256, ntot, R, S.pos.as<uint8_t>(), S.win.as<uint8_t>(), S.slot.as<int32_t>(),
+                 S.st_idx.as<int32_t>(), S.st_dom.as<int32_t>(), S.st_rank.as<int32_t>(), S.st_coords.as<double>(), S.st_dist.as<double>(),
+                 S.send_off.as<long long>(), S.cnt.as<unsigned int>() + 2 * N, S.send.as<DcpxRecord>());
+    constexpr size_t W = sizeof(DcpxRecord) / sizeof(long long);
+    AXB_NCCL_TRY(api, api->GroupStart());
+    for(int r = 0; r < N; ++r)
+    {
+      if(r == rank) continue;
+      if(hc[r] > 0) AXB_NCCL_TRY(api, api->Send(S.send.as<DcpxRecord>() + soff[r], (size_t)hc[r] * W, ncclInt64, r, c->comm, st));
+      if(hc[N + r] > 0) AXB_NCCL_TRY(api, api->Recv(S.recv.as<DcpxRecord>() + roff[r], (size_t)hc[N + r] * W, ncclInt64, r, c->comm, st));
+    }
+    AXB_NCCL_TRY(api, api->GroupEnd());
+    if(hc[rank] != hc[N + rank]) return fail(AXB_ERR_CUDA, "internal error: this rank's own send / receive counts differ");
+    if(hc[rank] > 0)
+      AXB_CUDA_TRY(cudaMemcpyAsync(S.recv.as<DcpxRecord>() + roff[rank], S.send.as<DcpxRecord>() + soff[rank], sizeof(DcpxRecord) * (size_t)hc[rank],
+                                   cudaMemcpyDeviceToDevice, st));
+    c->bytes += (long long)sizeof(DcpxRecord) * (soff[N] - hc[rank]);
+    c->calls += 1;
+    if(nq > 0)
+    {
+      AXB_LAUNCH(ctx, dcpx_init_outputs_kernel<D>, blocks_for(nq, 256), 256, nq, o_idx, o_dom, o_rank, o_coords, o_dist);
+      if(roff[N] > 0)
+        AXB_LAUNCH(ctx, dcpx_unpack_kernel<D>, blocks_for(roff[N], 256), 256, S.recv.as<DcpxRecord>(), roff[N], o_idx, o_dom, o_rank, o_coords, o_dist);
+    }
+    AXB_TRY(ctx.sync());  // soff / roff were read by asynchronous copies
+  }
+  return AXB_OK;
+}
+
+extern "C" {
+
+int axb_dcp_compute_closest_points(axb_dcp* h, axb_comm* c, const double* query_coords, int32_t nq, int memspace, int32_t* cp_index,
+                                   int32_t* cp_domain_index, int32_t* cp_rank, double* cp_coords, double* cp_distance)
+{
+  if(!h) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(nq < 0) return fail(AXB_ERR_BAD_ARG, "negative query count");
+  if(nq > 0 && !query_coords) return fail(AXB_ERR_BAD_ARG, "null query array");
+  if(!h->tree_built) return fail(AXB_ERR_NOT_BUILT, "BVH tree must be initialized before calling 'computeClosestPoints");
+  if(c && c->nranks > kDcpxMaxRanks) return fail(AXB_ERR_UNSUPPORTED, "more than 254 ranks");
+  if(c && c->device != h->ctx().device) return fail(AXB_ERR_BAD_ARG, "communicator and DistributedClosestPoint handle live on different devices");
+  if(c && h->mode != 1) return fail(AXB_ERR_UNSUPPORTED, "the collective path needs the nearest-first mode (axb_dcp_set_mode 1)");
+  memspace = resolve_memspace(memspace, nq > 0 ? (const void*)query_coords : (const void*)cp_index);
+  if(memspace != AXB_MEM_HOST && memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  Ctx& ctx = h->ctx();
+  AXB_TRY(ctx.bind());
+  const int D = h->ndims;
+  DcpxScratch* S = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_dcpx_mutex);
+    S = &g_dcpx[h];
+  }
+  cudaStream_t st = ctx.stream;
+  const size_t n = (size_t)std::max(nq, 1);
+  // outputs the caller did not ask for still exist on the device (the records carry all five fields)
+  const bool host = memspace == AXB_MEM_HOST;
+  int32_t *d_idx = cp_index, *d_dom = cp_domain_index, *d_rank = cp_rank;
+  double *d_coords = cp_coords, *d_dist = cp_distance;
+  if(host || !d_idx) { AXB_TRY(S->o_idx.reserve(sizeof(int32_t) * n, st)); d_idx = S->o_idx.as<int32_t>(); }
+  if(host || !d_dom) { AXB_TRY(S->o_dom.reserve(sizeof(int32_t) * n, st)); d_dom = S->o_dom.as<int32_t>(); }
+  if(host || !d_rank) { AXB_TRY(S->o_rank.reserve(sizeof(int32_t) * n, st)); d_rank = S->o_rank.as<int32_t>(); }
+  if(host || !d_coords) { AXB_TRY(S->o_coords.reserve(sizeof(double) * D * n, st)); d_coords = S->o_coords.as<double>(); }
+  if(host || !d_dist) { AXB_TRY(S->o_dist.reserve(sizeof(double) * n, st)); d_dist = S->o_dist.as<double>(); }
+  const double* d_q = query_coords;
+  if(host && nq > 0)
+  {
+    AXB_TRY(S->q_own.reserve(sizeof(double) * D * n, st));
+    AXB_CUDA_TRY(cudaMemcpyAsync(S->q_own.p, query_coords, sizeof(double) * D * (size_t)nq, cudaMemcpyHostToDevice, st));
+    d_q = S->q_own.as<double>();
+  }
+  const int tot = ctx.phase_begin("dcpx.total");
+  if(!c)
+  {
+    // one rank, no exchange: the ring of one
+    const bool was_async = ctx.async;
+    ctx.async = true;
+    const int rc = nq > 0 ? axb_dcp_compute_local_closest_points(h, 0, d_q, nq, 1, d_idx, d_dom, d_rank, d_coords, d_dist, AXB_MEM_DEVICE) : AXB_OK;
+    ctx.async = was_async;
+    AXB_TRY(rc);
+  }
+  else if(D == 3)
+    AXB_TRY(dcpx_compute<3>(h, c, *S, d_q, nq, d_idx, d_dom, d_rank, d_coords, d_dist));
+  else
+    AXB_TRY(dcpx_compute<2>(h, c, *S, d_q, nq, d_idx, d_dom, d_rank, d_coords, d_dist));
+  ctx.phase_end(tot);
+  if(host && nq > 0)
+  {
+    if(cp_index) AXB_CUDA_TRY(cudaMemcpyAsync(cp_index, d_idx, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    if(cp_domain_index) AXB_CUDA_TRY(cudaMemcpyAsync(cp_domain_index, d_dom, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    if(cp_rank) AXB_CUDA_TRY(cudaMemcpyAsync(cp_rank, d_rank, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    if(cp_coords) AXB_CUDA_TRY(cudaMemcpyAsync(cp_coords, d_coords, sizeof(double) * D * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    if(cp_distance) AXB_CUDA_TRY(cudaMemcpyAsync(cp_distance, d_dist, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    AXB_TRY(ctx.sync());
   }
   return ctx.finish_call();
 }

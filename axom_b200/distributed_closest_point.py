@@ -125,6 +125,32 @@ class _GpuBackend:
                                                                  st["cp_coords"].data_ptr(), st["cp_distance"].data_ptr()))
         return st
 
+    def compute_all(self, comm, q):
+        """computeClosestPoints as a whole, inside the library (axb_dcp_compute_closest_points): q is this rank's (n, D)
+        float64 CUDA tensor, comm an axom_b200.comm.Comm or None (one rank)"""
+        import torch
+        torch.cuda.current_stream(q.device).synchronize()
+        n, dev = q.shape[0], q.device
+        st = {"cp_index": torch.empty(n, dtype=torch.int32, device=dev), "cp_domain_index": torch.empty(n, dtype=torch.int32, device=dev),
+              "cp_rank": torch.empty(n, dtype=torch.int32, device=dev), "cp_coords": torch.empty((n, self.ndims), dtype=torch.float64, device=dev),
+              "cp_distance": torch.empty(n, dtype=torch.float64, device=dev)}
+        check(self._L.axb_dcp_compute_closest_points(self._h, comm._h if comm is not None else None, q.data_ptr() if n else None, n, MEM_DEVICE,
+                                                     st["cp_index"].data_ptr(), st["cp_domain_index"].data_ptr(), st["cp_rank"].data_ptr(),
+                                                     st["cp_coords"].data_ptr(), st["cp_distance"].data_ptr()))
+        return st
+
+    def phase_ms(self, name):
+        b = C.c_void_p()
+        check(self._L.axb_dcp_get_bvh(self._h, C.byref(b)))
+        v = C.c_double()
+        check(self._L.axb_bvh_get_phase_ms(b, name.encode(), C.byref(v)))
+        return v.value
+
+    def set_profiling(self, on):
+        b = C.c_void_p()
+        check(self._L.axb_dcp_get_bvh(self._h, C.byref(b)))
+        check(self._L.axb_bvh_set_profiling(b, int(bool(on))))
+
     def compute_local(self, rank, q, state=None):
         """q: (n, D) float64 CUDA tensor.  state None = is_first.  Returns the state dict (updated in place)."""
         import torch
@@ -154,6 +180,12 @@ class DistributedClosestPoint:
         self._outputs = {f: True for f in OUTPUT_FIELDS}
         self._tree = False
         self._have_mesh = False
+        self._comm = None
+
+    def setComm(self, comm):
+        """the axom_b200.comm.Comm the exchange runs on (the reference takes an MPI_Comm, DistributedClosestPoint.hpp:95-100).
+        Without one, a communicator is made from the initialised torch.distributed group at the first query."""
+        self._comm = comm
 
     # ---- configuration (DistributedClosestPoint.hpp:66-118) ----
     def setDistanceThreshold(self, threshold):
@@ -202,6 +234,14 @@ class DistributedClosestPoint:
         q = torch.as_tensor(query_coords, dtype=torch.float64).reshape(-1, self.ndims).to(dev).contiguous()
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank() if world > 1 else 0
+        if isinstance(self._b, _GpuBackend):
+            # the product path: the whole exchange runs inside the library, over its own NCCL communicator
+            if self._comm is None and world > 1:
+                from .comm import Comm
+                self._comm = Comm.from_torch(self._b.device)
+            return self._select(self._b.compute_all(self._comm, q))
+        # An injected backend (the CPU tests run a host per-rank step under gloo): the same protocol written with
+        # torch.distributed, kept as the executable description of what csrc/comm.cuh does on the device.
         if world == 1:
             return self._select(self._b.compute_local(rank, q))
 

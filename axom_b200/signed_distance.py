@@ -126,6 +126,24 @@ class SignedDistance:
         check(self._L.axb_sd_compute_distances(self._h, C.byref(k.desc), n, ptr(phi), ptr(cp), ptr(nr), space))
         return phi, cp, nr
 
+    def computeDistancesMinReduce(self, comm, queryPts, out=None):
+        """BASELINE config C5: this handle holds ONE PART of the surface (computeSign=False), every rank passes the same
+        query points, every rank gets the distance to the whole surface (kernel + ncclAllReduce(MIN) on one stream, inside
+        the library: axb_sd_compute_distances_minreduce).  comm: axom_b200.comm.Comm."""
+        k = make_desc(queryPts, 3)
+        n = k.count
+        if k.device:
+            import torch
+            if getattr(self, "_own_stream", True):
+                torch.cuda.current_stream(self.device).synchronize()
+            d = out if out is not None else torch.empty(n, dtype=torch.float64, device=torch.device("cuda", self.device))
+            ptr, space = d.data_ptr(), MEM_DEVICE
+        else:
+            d = out if out is not None else np.empty(n, np.float64)
+            ptr, space = d.ctypes.data, MEM_HOST
+        check(self._L.axb_sd_compute_distances_minreduce(self._h, comm._h, C.byref(k.desc), n, ptr, space))
+        return d
+
     def computeDistance(self, x, y=None, z=0.0):
         """computeDistance(x,y,z) / computeDistance(Point) (:243-266)"""
         p = np.array([[x, y, z]], np.float64) if y is not None else np.asarray(x, np.float64).reshape(1, 3)

@@ -273,6 +273,43 @@ int axb_dcp_compute_bounded_closest_points(axb_dcp* dcp, int rank, const double*
                                            const double* bound_sq, int32_t* cp_index, int32_t* cp_domain_index, int32_t* cp_rank,
                                            double* cp_coords, double* cp_distance);
 
+/* ---- the exchange steps of the distributed cases: NCCL over NVLink / NVSwitch, inside the library ---------------- */
+/* One communicator per rank (= per process = per GPU).  Rank 0 obtains an id and hands it to the other ranks by any
+ * means the host code has (MPI_Bcast, a file, a socket); every rank then calls axb_comm_create -- collectively, like
+ * ncclCommInitRank, which it wraps.  NCCL is bound at run time: the copy already mapped into the process (a torch
+ * process has one) or libnccl.so.2 on the loader path, or the file AXB_NCCL_LIB names.  What this replaces: the
+ * MPI_Comm the reference's DistributedClosestPoint is given (quest/DistributedClosestPoint.hpp:95-100) and the
+ * MPI_Allgather / Isend / Irecv traffic of quest/detail/DistributedClosestPointImpl.hpp:687-693, :737-851. */
+#define AXB_COMM_ID_BYTES 128
+typedef struct axb_comm axb_comm;
+int axb_comm_get_unique_id(uint8_t id[AXB_COMM_ID_BYTES]);
+int axb_comm_create(axb_comm** out, int nranks, int rank, const uint8_t id[AXB_COMM_ID_BYTES], int device);
+int axb_comm_destroy(axb_comm* comm);
+int axb_comm_get_rank(const axb_comm* comm, int* rank, int* nranks);
+/* payload bytes this rank has contributed to collectives and the number of collectives issued, since creation */
+int axb_comm_get_traffic(const axb_comm* comm, int64_t* bytes, int64_t* collectives);
+const char* axb_comm_library(void); /* which NCCL was bound, and its version ("" if none) */
+/* in-place elementwise reduction of a DEVICE array over the ranks on `cuda_stream`; op 0 = MIN, 1 = MAX, 2 = SUM */
+int axb_comm_allreduce_f64(axb_comm* comm, double* device_buf, int64_t n, int op, void* cuda_stream);
+
+/* BASELINE config C5 -- the surface is PARTITIONED over the ranks (each rank's axb_sd holds one part, created with
+ * compute_sign = 0), every rank passes the SAME query points, and every rank receives the distance to the whole surface:
+ * the query kernel writes its partial (unsigned) distances into the buffer an ncclAllReduce(MIN, double) then reduces in
+ * place on the handle's stream.  Phase timers: "query.kernel", "query.minreduce". */
+int axb_sd_compute_distances_minreduce(axb_sd* sd, axb_comm* comm, const axb_array_desc* query_pts, int32_t npts, double* dist,
+                                       int out_memspace);
+
+/* DistributedClosestPoint::computeClosestPoints (quest/DistributedClosestPoint.hpp:157-166, DistributedClosestPointImpl.hpp
+ * :737-851), the whole of it: every rank passes ITS OWN query points (num_queries may be 0 and differ per rank) and gets,
+ * for each, the nearest object point of the whole machine -- the five xferDom fields, with the reference's tie rule (first
+ * rank in ring order from the query's owner; inside a rank the first point in traversal order) and -1 / signalling NaN where
+ * no rank holds a point within the distance threshold.  Collective: every rank of `comm` must call it.  comm == NULL is the
+ * single-rank case (no exchange).  Any output pointer may be NULL; arrays live in `memspace`.
+ * Phase timers (axb_bvh_get_phase_ms on axb_dcp_get_bvh's handle): "dcpx.total" "dcpx.gather" "dcpx.search1"
+ * "dcpx.bound_allreduce" "dcpx.search2" "dcpx.combine" "dcpx.exchange". */
+int axb_dcp_compute_closest_points(axb_dcp* dcp, axb_comm* comm, const double* query_coords_interleaved, int32_t num_queries, int memspace,
+                                   int32_t* cp_index, int32_t* cp_domain_index, int32_t* cp_rank, double* cp_coords, double* cp_distance);
+
 /* ---- quest::MarchingCubes (the consumer of the distance field: iso-contour of a nodal function) ------------- */
 /* One structured domain, as MarchingCubesImpl::setDomain / setFunctionField see it through MeshViewUtil
  * (quest/detail/MarchingCubesImpl.hpp:100-145, quest/MeshViewUtil.hpp:454-482,560-607): ghost-free views, i.e. every
