@@ -1399,18 +1399,26 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
       const int grid2 = blocks_for(npts, kSd2Threads);
       if(s->nv == 3)
       {
-        AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
-                        B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
-                        s->prm.compute_sign ? kTieWindow : 0.0);
+        {
+          ScopedPhase p1(ctx, "query.min");
+          AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
+                          B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
+                          s->prm.compute_sign ? kTieWindow : 0.0);
+        }
+        ScopedPhase p2(ctx, "query.resolve");
         AXB_LAUNCH(ctx, sd_resolve_kernel<3>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
                    s->bvh->leaf_parent.as<int32_t>(), s->soup.as<double>(), s->prm, q, npts, perm, B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(),
                    B.seed.as<double>(), d_phi, d_cp, d_n, d_work);
       }
       else
       {
-        AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
-                        B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
-                        s->prm.compute_sign ? kTieWindow : 0.0);
+        {
+          ScopedPhase p1(ctx, "query.min");
+          AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
+                          B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
+                          s->prm.compute_sign ? kTieWindow : 0.0);
+        }
+        ScopedPhase p2(ctx, "query.resolve");
         AXB_LAUNCH(ctx, sd_resolve_kernel<4>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
                    s->bvh->leaf_parent.as<int32_t>(), s->soup.as<double>(), s->prm, q, npts, perm, B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(),
                    B.seed.as<double>(), d_phi, d_cp, d_n, d_work);

@@ -460,6 +460,14 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
       }
       if(wcount != 0u)
       {
+        // A second source for the first bound: the running closest point of the lane that holds the LATEST query with a
+        // leaf evaluated.  Right after the warp moves on to a new chunk the lane's own previous query is far away (the
+        // chunks of one warp are grid-size * 32 queries apart), but a lane that is already working on the new chunk is
+        // a Morton neighbour.  Any point of the surface gives a valid upper bound; the smaller of the two is used.
+        const int hkey = (qt >= 0 && minSq < 1e300) ? qt : -1;
+        const int hbest = __reduce_max_sync(FULL, hkey);
+        const int hsrc = max(__ffs(__ballot_sync(FULL, hkey == hbest)) - 1, 0);
+        const V3 wpt {shfl_f64(minPt.x, hsrc), shfl_f64(minPt.y, hsrc), shfl_f64(minPt.z, hsrc)};
         const unsigned rank = __popc(freem & lt_mask);
         if(qt < 0 && rank < wcount)
         {
@@ -471,11 +479,21 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
           minSq = DBL_MAX;
           thr = DBL_MAX;
           thr_f = inf_f;
+          double hsq = DBL_MAX;
           if(have_hint)
           {
             // the closest point of the lane's previous query (a Morton neighbour) is a point of the surface
             const double hx = minPt.x - qx, hy = minPt.y - qy, hz = minPt.z - qz;
-            thr = prune_threshold_w(hx * hx + hy * hy + hz * hz, window);
+            hsq = hx * hx + hy * hy + hz * hz;
+          }
+          if(hbest >= 0)
+          {
+            const double hx = wpt.x - qx, hy = wpt.y - qy, hz = wpt.z - qz;
+            hsq = fmin(hsq, hx * hx + hy * hy + hz * hz);
+          }
+          if(hsq < 1e300)
+          {
+            thr = prune_threshold_w(hsq, window);
             thr_f = thr < 3.0e38 ? __double2float_ru(thr) : inf_f;
           }
           ncand = 0;

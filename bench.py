@@ -547,23 +547,23 @@ def c5_leg(ctx, surface):
             sd.setAsync(True)
     except Exception as e:
         err = "%s: %s" % (type(e).__name__, e)
+    comm = None
+    if world > 1:
+        comm = ctx["comm"]()  # the library's own NCCL communicator (axb_comm): the MIN runs inside libaxb200.so
     ok_all = ctx["sum_over_ranks"](0.0 if err else 1.0) == world
     if not ok_all:
         return {"error": err or "setup failed on another rank"} if rank == 0 else None
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
-    def step(timed=False):
+    def step():
+        if world > 1:
+            sds[0].computeDistancesMinReduce(comm, qd, out=out)  # kernel -> ncclAllReduce(MIN) in place, one stream, one C call
+            return
         for k, sd in enumerate(sds):
             sd.computeDistances(qd, out=(out if k == 0 else tmp))
             if k:
                 torch.minimum(out, tmp, out=out)
-        if world > 1:
-            if timed:
-                ev[2].record()
-            ctx["dist"].all_reduce(out, op=ctx["dist"].ReduceOp.MIN)
-            if timed:
-                ev[3].record()
 
     step()
     ctx["barrier"]()
@@ -573,21 +573,31 @@ def c5_leg(ctx, surface):
     ev[1].record()
     ctx["barrier"]()
     ms = ctx["max_over_ranks"](ev[0].elapsed_time(ev[1]) / args.config_steps)
+    kern_min = kern_max = None
     if world > 1:
-        step(timed=True)
-        torch.cuda.synchronize()
-        coll_ms = ctx["max_over_ranks"](ev[2].elapsed_time(ev[3]))
+        sds[0].setProfiling(1)
+        step()
+        sds[0].synchronize()
+        mine_coll, mine_kern = sds[0].phase_ms("query.minreduce"), sds[0].phase_ms("query.kernel")
+        sds[0].setProfiling(0)
+        # the all-reduce starts when this rank's kernel ends and ends when the SLOWEST rank's data has arrived: the shortest
+        # one over the ranks is the transfer itself, the longest one includes waiting for the slowest kernel
+        coll_ms = -ctx["max_over_ranks"](-mine_coll)
+        coll_max = ctx["max_over_ranks"](mine_coll)
+        kern_min, kern_max = -ctx["max_over_ranks"](-mine_kern), ctx["max_over_ranks"](mine_kern)
     if rank != 0:
         return None
     leg = {"workload": "C5: %d-triangle icosphere in %d Morton ranges (one BVH per %s), %d queries in [-1,1]^3 on every rank, unsigned distance, elementwise MIN"
                        % (len(conn), parts_total, "rank" if world > 1 else "part, evaluated in turn on one GPU", q),
            "metric": "distributed closest point queries/s", "value": q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
            "steps": args.config_steps, "queries": q, "partitions": parts_total,
-           "collective": ("ncclAllReduce(MIN, f64), %d B per rank" % (8 * q)) if world > 1 else "none (one GPU)"}
+           "collective": ("ncclAllReduce(MIN, f64), %d B per rank, issued by axb_sd_compute_distances_minreduce on the kernel's stream" % (8 * q))
+                         if world > 1 else "none (one GPU)"}
     if world > 1:
         bus = 2.0 * (world - 1) / world * 8.0 * q
-        leg["nccl"] = {"allreduce_ms": coll_ms, "bus_bytes": bus, "bus_gbs": bus / (coll_ms * 1e-3) / 1e9 if coll_ms > 0 else None,
-                       "nvlink5_peak_gbs_per_direction": 900.0}
+        leg["nccl"] = {"allreduce_ms": coll_ms, "allreduce_ms_incl_wait_for_slowest_rank": coll_max, "bus_bytes": bus,
+                       "bus_gbs": bus / (coll_ms * 1e-3) / 1e9 if coll_ms > 0 else None, "nvlink5_peak_gbs_per_direction": 900.0,
+                       "library": comm.library(), "kernel_ms_per_rank": {"min": kern_min, "max": kern_max}}
     if not args.no_cpu_baseline:
         try:
             from oracle import oracle as O
@@ -618,6 +628,92 @@ def c5_leg(ctx, surface):
     return leg
 
 
+def dcp_leg(ctx, surface):
+    """quest::DistributedClosestPoint proper (SURVEY 8(f) rank 3): the object is a POINT CLOUD (the vertices of the C4
+    icosphere) in one Morton range per rank; every rank owns 1/N of the 50 M query points; one call =
+    axb_dcp_compute_closest_points (gather, two searches, MIN all-reduces of 8 + 8 + 1 B/query, one all-to-all of 48-byte
+    winner records -- all inside the library over its own NCCL communicator).  Checked against the unmodified reference's
+    traversal of the WHOLE cloud on a sample of rank 0's queries (coordinates and distances; rank / index are
+    partition-relative and are checked against the partition)."""
+    import torch
+    from axom_b200 import DistributedClosestPoint
+    from axom_b200 import dist as D
+    rank, world, dev, local, args = ctx["rank"], ctx["world"], ctx["dev"], ctx["local"], ctx["args"]
+    x, y, z, _ = surface
+    q_total = max(1000, int(50_000_000 * args.config_scale))
+    err, d, myq, got = None, None, None, None
+    try:
+        P = np.stack([x, y, z], 1)
+        parts = D.morton_partition(P, world)
+        lo, hi = D.slab_range(q_total, rank, world)
+        myq = _points_device(q_total, 999, -1.0, 1.0, dev)[lo:hi].contiguous()
+        d = DistributedClosestPoint(3, device=local)
+        d.setObjectMesh([P[parts[rank]]])
+        d.generateBVHTree()
+    except Exception as e:
+        err = "%s: %s" % (type(e).__name__, e)
+    comm = ctx["comm"]() if world > 1 else None
+    ok_all = ctx["sum_over_ranks"](0.0 if err else 1.0) == world
+    if not ok_all:
+        return {"error": err or "setup failed on another rank"} if rank == 0 else None
+    d.setComm(comm)
+    got = d.computeClosestPoints(myq)
+    ctx["barrier"]()
+    b0 = comm.traffic()[0] if comm else 0
+    t0 = time.perf_counter()
+    for _ in range(args.config_steps):
+        got = d.computeClosestPoints(myq)  # synchronous: results complete on return
+    torch.cuda.synchronize()
+    ms = ctx["max_over_ranks"]((time.perf_counter() - t0) * 1e3 / args.config_steps)
+    sent = (comm.traffic()[0] - b0) / args.config_steps if comm else 0
+    phases = None
+    if world > 1:
+        d._b.set_profiling(True)
+        d.computeClosestPoints(myq)
+        names = ("counts", "gather", "search1", "bound_allreduce", "search2", "combine", "exchange", "total")
+        mine = [d._b.phase_ms("dcpx." + n) for n in names]
+        d._b.set_profiling(False)
+        phases = {n: ctx["max_over_ranks"](v) for n, v in zip(names, mine)}
+    sent_total = ctx["sum_over_ranks"](float(sent))
+    if rank != 0:
+        return None
+    leg = {"workload": "DistributedClosestPoint: %d object points (icosphere vertices) in %d Morton ranges, %d queries in [-1,1]^3 split over the ranks"
+                       % (len(P), world, q_total),
+           "metric": "DistributedClosestPoint queries/s", "value": q_total / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+           "steps": args.config_steps, "queries": q_total,
+           "timing": "host wall clock around the synchronous C call, max over ranks (the call contains four host round trips)",
+           "collective": ("axb_dcp_compute_closest_points over axb_comm: broadcast-gather 24 B/query, MIN f64 x2 + MIN u8 (17 B/query), "
+                          "grouped send/recv of 48-byte winner records") if world > 1 else "none (one GPU)"}
+    if world > 1:
+        leg["nccl"] = {"payload_bytes_per_step_all_ranks": sent_total, "phases_ms_max_over_ranks": phases, "library": comm.library(),
+                       "payload_gbs": sent_total / (ms * 1e-3) / 1e9}
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as O
+            kind_ref = "reference" if O.have_reference() else "port"
+            ns = min(hi - lo, 200_000)
+            r = O.DistributedClosestPointRank(P, None, 3, kind_ref)
+            qs = myq[:ns].cpu().numpy()
+            t0 = time.perf_counter()
+            want = r.compute_local(0, qs)
+            dt = time.perf_counter() - t0
+            g = {k: v[:ns].cpu().numpy() for k, v in got.items()}
+            match = bool(np.array_equal(g["cp_coords"], want["cp_coords"]) and np.array_equal(g["cp_distance"], want["cp_distance"]))
+            # rank / index against the partition: the winner's point is where it says it is
+            back = np.full((ns, 3), np.nan)
+            for rk in range(world):
+                m = g["cp_rank"] == rk
+                back[m] = P[parts[rk][g["cp_index"][m]]]
+            match = match and bool(np.array_equal(back, g["cp_coords"]))
+            leg["cpu_baseline"] = {"value": ns / dt, "unit": "queries/s", "cores": 1, "kind": kind_ref,
+                                   "sample": "the first %d of rank 0's queries against the whole %d-point cloud, %s BVH traversal, one thread, %.1f s"
+                                             % (ns, len(P), kind_ref, dt), "matches_gpu_bit_exact": match}
+            leg["matches_reference_bit_exact"] = match
+        except Exception as e:
+            leg["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return leg
+
+
 def config_legs(ctx):
     """C1, C3, C4, C5 -> {"C1": {...}, ...} on rank 0"""
     from axom_b200 import synth
@@ -627,13 +723,15 @@ def config_legs(ctx):
     for name in ("C1", "C3"):
         if name in want:
             out[name] = find_leg(name, ctx)
-    if "C4" in want or "C5" in want:
+    if "C4" in want or "C5" in want or "DCP" in want:
         freq = max(2, int(round(1000 * args.config_scale ** 0.5)))
         surface = synth.icosphere(freq)
         if "C4" in want:
             out["C4"] = find_leg("C4", ctx, surface)
         if "C5" in want:
             out["C5"] = c5_leg(ctx, surface)
+        if "DCP" in want:
+            out["DCP"] = dcp_leg(ctx, surface)
     return out if ctx["rank"] == 0 else None
 
 
@@ -773,8 +871,17 @@ def run_ours(args):
     cfg = None
     if args.configs:
         host_phi = phi_d.cpu().numpy() if (world == 1 and not args.no_cpu_baseline) else None
+        _comm = []
+
+        def lib_comm():
+            # the library's own NCCL communicator, made once (collective: every rank calls it at the same point)
+            if not _comm:
+                from axom_b200.comm import Comm
+                _comm.append(Comm.from_torch(local))
+            return _comm[0]
+
         ctx = {"rank": rank, "world": world, "dev": dev, "local": local, "args": args, "dist": dist, "barrier": barrier,
-               "max_over_ranks": max_over_ranks, "sum_over_ranks": sum_over_ranks}
+               "max_over_ranks": max_over_ranks, "sum_over_ranks": sum_over_ranks, "comm": lib_comm}
         cfg = config_legs(ctx)
 
     if rank != 0:
@@ -865,7 +972,7 @@ def main():
     ap.add_argument("--sharding", default="slabs", choices=["slabs", "planes"], help="how the 256 z-planes are split over ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default="small", choices=["small", "large"])
-    ap.add_argument("--configs", default="C1,C3,C4,C5", help="the other BASELINE configs to run after the headline (C2); '' = none")
+    ap.add_argument("--configs", default="C1,C3,C4,C5,DCP", help="the other BASELINE configs to run after the headline (C2), and DCP = the full DistributedClosestPoint; '' = none")
     ap.add_argument("--config-scale", type=float, default=1.0, help="shrink C1/C3/C4/C5 (0.1 -> 10x fewer boxes and queries); 1.0 = BASELINE sizes")
     ap.add_argument("--config-steps", type=int, default=3)
     args = ap.parse_args()
