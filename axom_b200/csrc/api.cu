@@ -1036,10 +1036,12 @@ struct axb_sd
   // that the upload of chunk i+1 and the download of chunk i-1 overlap the kernel of chunk i
   struct QBufs
   {
-    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor, cand, cand_n, seed;
+    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor, cand, cand_n, seed, solo, solo_scratch;
     void release(cudaStream_t st)
     {
-      for(DevBuf* b : {&q_stage, &out_phi, &out_cp, &out_n, &qkeys_a, &qkeys_b, &qscratch, &qperm, &qbounds, &cursor, &cand, &cand_n, &seed}) b->release(st);
+      for(DevBuf* b : {&q_stage, &out_phi, &out_cp, &out_n, &qkeys_a, &qkeys_b, &qscratch, &qperm, &qbounds, &cursor, &cand, &cand_n, &seed, &solo,
+                       &solo_scratch})
+        b->release(st);
     }
   } qb[2];
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
@@ -1397,6 +1399,20 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
       AXB_TRY(B.cand_n.reserve((size_t)npts, ctx.stream));
       AXB_TRY(B.seed.reserve(sizeof(double) * (size_t)npts, ctx.stream));
       const int grid2 = blocks_for(npts, kSd2Threads);
+      // heavy queries (list overflow, sign too close to call) are listed by the resolve kernel and finished one WARP each
+      const unsigned solo_cap = (unsigned)std::min<long long>(npts, 1 << 20);
+      const int solo_grid = std::min(2 * sms, blocks_for(npts, 32));
+      unsigned int* solo_ctr = nullptr;
+      int32_t* solo_list = nullptr;
+      const bool solo_on = getenv("AXB_SD_NO_SOLO") == nullptr;  // (a test hook: the serial walk in the resolve lane)
+      if(solo_on)
+      {
+        AXB_TRY(B.solo.reserve(16 + sizeof(int32_t) * (size_t)solo_cap, ctx.stream));
+        AXB_TRY(B.solo_scratch.reserve(sizeof(unsigned long long) * kSoloCap * (size_t)solo_grid * (kSoloThreads / 32), ctx.stream));
+        AXB_CUDA_TRY(cudaMemsetAsync(B.solo.p, 0, 16, ctx.stream));
+        solo_ctr = B.solo.as<unsigned int>();
+        solo_list = reinterpret_cast<int32_t*>(B.solo.as<char>() + 16);
+      }
       if(s->nv == 3)
       {
         {
@@ -1408,7 +1424,10 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
         ScopedPhase p2(ctx, "query.resolve");
         AXB_LAUNCH(ctx, sd_resolve_kernel<3>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
                    s->bvh->leaf_parent.as<int32_t>(), s->soup.as<double>(), s->prm, q, npts, perm, B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(),
-                   B.seed.as<double>(), d_phi, d_cp, d_n, d_work);
+                   B.seed.as<double>(), d_phi, d_cp, d_n, d_work, solo_ctr, solo_cap, solo_list);
+        if(solo_on)
+          AXB_LAUNCH(ctx, sd_solo_kernel<3>, solo_grid, kSoloThreads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->soup.as<double>(), s->prm, q,
+                     perm, B.seed.as<double>(), solo_ctr, solo_cap, solo_list, B.solo_scratch.as<unsigned long long>(), d_phi, d_cp, d_n, d_work);
       }
       else
       {
@@ -1421,7 +1440,10 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
         ScopedPhase p2(ctx, "query.resolve");
         AXB_LAUNCH(ctx, sd_resolve_kernel<4>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
                    s->bvh->leaf_parent.as<int32_t>(), s->soup.as<double>(), s->prm, q, npts, perm, B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(),
-                   B.seed.as<double>(), d_phi, d_cp, d_n, d_work);
+                   B.seed.as<double>(), d_phi, d_cp, d_n, d_work, solo_ctr, solo_cap, solo_list);
+        if(solo_on)
+          AXB_LAUNCH(ctx, sd_solo_kernel<4>, solo_grid, kSoloThreads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->soup.as<double>(), s->prm, q,
+                     perm, B.seed.as<double>(), solo_ctr, solo_cap, solo_list, B.solo_scratch.as<unsigned long long>(), d_phi, d_cp, d_n, d_work);
       }
     }
     else if(s->nv == 3)

@@ -764,9 +764,10 @@ __global__ void __launch_bounds__(kSd2Threads) sd_resolve_kernel(const SdNode* _
                                                                  const SdUp* __restrict__ up, const int32_t* __restrict__ leaf_parent,
                                                                  const double* __restrict__ soup, SdParams prm, Desc<3> qpts, int npts,
                                                                  const int32_t* __restrict__ perm, const int32_t* __restrict__ cand,
-                                                                 const uint8_t* __restrict__ cand_n, const double* __restrict__ seed,
+                                                                 const uint8_t* __restrict__ cand_n, double* __restrict__ seed,
                                                                  double* __restrict__ phi, double* __restrict__ cps, double* __restrict__ nrms,
-                                                                 unsigned long long* __restrict__ work)
+                                                                 unsigned long long* __restrict__ work, unsigned int* __restrict__ solo_ctr,
+                                                                 unsigned int solo_cap, int32_t* __restrict__ solo_list)
 {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int NSUB = NV == 4 ? 2 : 1;
@@ -1038,8 +1039,318 @@ __global__ void __launch_bounds__(kSd2Threads) sd_resolve_kernel(const SdNode* _
       const double slack = 1e-13 * (fabs(r.x) + fabs(r.y) + fabs(r.z)) * term_abs;
       solo = !(fabs(dotv) > slack);
     }
-    if(solo) sd_ordered_query<NV>(nodes, cens, soup, q, cand_n[t] == kCandOverflow ? seed[t] : m.minSq, cn, m, nleaf, ninner);
-    sd_finish<NV>(soup, prm, q, m, qi, phi, cps, nrms);
+    bool handed = false;
+    if(solo && solo_list)
+    {
+      // a heavy query: listed for sd_solo_kernel (one warp each) instead of a serial walk in this lane
+      const unsigned at = atomicAdd(solo_ctr, 1u);
+      if(at < solo_cap)
+      {
+        solo_list[at] = t;
+        if(cand_n[t] != kCandOverflow) seed[t] = m.minSq;
+        handed = true;
+      }
+    }
+    if(!handed)
+    {
+      if(solo) sd_ordered_query<NV>(nodes, cens, soup, q, cand_n[t] == kCandOverflow ? seed[t] : m.minSq, cn, m, nleaf, ninner);
+      sd_finish<NV>(soup, prm, q, m, qi, phi, cps, nrms);
+    }
+  }
+  if(work)
+  {
+    unsigned long long a = nleaf, b = ninner;
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+      a += __shfl_xor_sync(FULL, a, o);
+      b += __shfl_xor_sync(FULL, b, o);
+    }
+    if(lane == 0)
+    {
+      atomicAdd(&work[0], a);
+      atomicAdd(&work[1], b);
+    }
+  }
+}
+
+//------------------------------------------------------------------------------------------
+// The heavy queries, one WARP each.  A query whose remembered-leaf list overflowed (dozens of triangles within 1e-6 of
+// each other: the neighbourhood of a sphere's centre), or whose sign test needs the reference's exact summation order,
+// used to walk the tree alone in its resolve lane: ~2500 dependent node visits at ~2 us each, a 5 ms serial chain that
+// set the tail of every launch (and 70 % of the 8-GPU efficiency).  Here the resolve kernel only lists such queries;
+// this kernel, launched behind it, hands them to warps one by one:
+//   stage A  the exact minimum d*: a warp-wide search over a shared stack in global memory (32 nodes per step, children
+//            pushed farther-first, leaves evaluated on the spot, the bound shrinking with every batch);
+//   stage B  every leaf whose oriented bound is within the window of d*, IN THE REFERENCE'S VISITING ORDER: the
+//            frontier is an ordered list, each level replaces every inner node by its surviving children in the order
+//            LinearBVHTraverser enters them (nearer AABB centroid first, LinearBVH.hpp:72-85) -- a level-synchronous
+//            expansion keeps the depth-first order, leaves are carried along in place;
+//   replay   the unchanged state machine over that list (closest points evaluated 32 at a time), then sign and store.
+// With the threshold fixed at thr(d*) from the start, the leaves visited are exactly those sd_ordered_query ends up
+// visiting once its own bound has converged, in the same order.  A frontier that outgrows the scratch (kSoloCap) falls
+// back to sd_ordered_query.
+//------------------------------------------------------------------------------------------
+constexpr int kSoloCap = 8192;  // scratch entries (8 B) per warp: stage A's stack, then two int32 lists of kSoloCap
+constexpr int kSoloThreads = 128;
+
+__device__ __forceinline__ int warp_excl_scan(int v, int& total)
+{
+  const unsigned lane = lane_id();
+  int incl = v;
+#pragma unroll
+  for(int o = 1; o < 32; o <<= 1)
+  {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if((int)lane >= o) incl += u;
+  }
+  total = __shfl_sync(0xffffffffu, incl, 31);
+  return incl - v;
+}
+
+// the two children of inner node `cur` as the ordered walk sees them: ids and double-precision oriented bounds
+__device__ __forceinline__ void solo_visit(const SdNode* __restrict__ nodes, int32_t cur, const double* qp, int32_t& child0, int32_t& child1,
+                                           double& d20, double& d21)
+{
+  const D4* rec = reinterpret_cast<const D4*>(nodes + cur);
+  const D4 r0 = ldg256(rec), r1 = ldg256(rec + 1), r2 = ldg256(rec + 2), r3 = ldg256(rec + 3);
+  const long long ids = __double_as_longlong(r0.x);
+  child0 = (int32_t)(ids & 0xffffffffll);
+  child1 = (int32_t)(ids >> 32);
+  const double rq[3] = {qp[0] - r0.y, qp[1] - r0.z, qp[2] - r0.w};
+  float f[24];
+  const double w[12] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+#pragma unroll
+  for(int k = 0; k < 12; ++k)
+  {
+    f[2 * k] = __int_as_float(__double2loint(w[k]));
+    f[2 * k + 1] = __int_as_float(__double2hiint(w[k]));
+  }
+  d20 = obb_sqdist(f, rq);
+  d21 = obb_sqdist(f + 12, rq);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kSoloThreads) sd_solo_kernel(const SdNode* __restrict__ nodes, const SdCen* __restrict__ cens,
+                                                               const double* __restrict__ soup, SdParams prm, Desc<3> qpts,
+                                                               const int32_t* __restrict__ perm, const double* __restrict__ seed,
+                                                               unsigned int* __restrict__ ctr, unsigned int cap, const int32_t* __restrict__ list,
+                                                               unsigned long long* __restrict__ scratch, double* __restrict__ phi,
+                                                               double* __restrict__ cps, double* __restrict__ nrms, unsigned long long* __restrict__ work)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NSUB = NV == 4 ? 2 : 1;
+  constexpr double EPS = 1e-12;
+  const unsigned lane = lane_id();
+  const bool cn = prm.compute_sign != 0;
+  const double window = cn ? kTieWindow : 0.0;
+  unsigned long long* const buf = scratch + (size_t)(blockIdx.x * (kSoloThreads / 32) + (threadIdx.x >> 5)) * kSoloCap;
+  const unsigned total = min(ctr[0], cap);
+  unsigned nleaf = 0, ninner = 0;
+  while(true)
+  {
+    unsigned item = 0;
+    if(lane == 0) item = atomicAdd(ctr + 1, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if(item >= total) break;
+    const int t = list[item];
+    const int qi = perm ? perm[t] : t;
+    const double qp[3] = {ld_comp<double>(qpts, 0, qi), ld_comp<double>(qpts, 1, qi), ld_comp<double>(qpts, 2, qi)};
+    const V3 q {qp[0], qp[1], qp[2]};
+    bool fail = false;
+    // ---- stage A: the exact minimum ----
+    double minSq = seed[t];  // the squared distance of SOME surface point (exact already for a sign re-run)
+    int sp = 1;
+    if(lane == 0) buf[0] = 0ull;  // (bound 0, root)
+    __syncwarp();
+    while(sp > 0)
+    {
+      const int n = min(sp, 32);
+      sp -= n;
+      const bool have = (int)lane < n;
+      const unsigned long long en = have ? buf[sp + (int)lane] : 0ull;
+      __syncwarp();
+      int32_t push[2] = {kBarrier, kBarrier};
+      float push_lb[2] = {0.f, 0.f};
+      int cnt = 0;
+      double best = DBL_MAX;
+      if(have && (double)__uint_as_float((unsigned)(en >> 32)) <= minSq)
+      {
+        ++ninner;
+        int32_t c0, c1;
+        double d0, d1;
+        solo_visit(nodes, (int32_t)(unsigned)(en & 0xffffffffull), qp, c0, c1, d0, d1);
+        // farther child first: the nearer one ends up on top of the stack
+        const bool swap = d0 < d1;
+        const int32_t ca = swap ? c1 : c0, cb = swap ? c0 : c1;
+        const double da = swap ? d1 : d0, db = swap ? d0 : d1;
+        const int32_t cc[2] = {ca, cb};
+        const double dd[2] = {da, db};
+#pragma unroll
+        for(int k = 0; k < 2; ++k)
+        {
+          if(!(dd[k] <= minSq)) continue;
+          if(cc[k] < 0)
+          {
+            ++nleaf;
+            best = fmin(best, leaf_min_sq<NV>(soup, q, -cc[k] - 1));
+          }
+          else
+          {
+            push[cnt] = cc[k];
+            push_lb[cnt] = __double2float_rd(dd[k]);
+            ++cnt;
+          }
+        }
+      }
+      int tot = 0;
+      const int at = warp_excl_scan(cnt, tot);
+      if(sp + tot > kSoloCap)
+      {
+        fail = true;
+        break;
+      }
+      for(int k = 0; k < cnt; ++k) buf[sp + at + k] = ((unsigned long long)__float_as_uint(push_lb[k]) << 32) | (unsigned)push[k];
+      sp += tot;
+      minSq = fmin(minSq, warp_min(best));
+      __syncwarp();
+    }
+    // ---- stage B: the leaves within the window of d*, in the reference's visiting order ----
+    const double thr = prune_threshold_w(minSq, window);
+    int32_t* la = reinterpret_cast<int32_t*>(buf);
+    int32_t* lb = la + kSoloCap;
+    int na = 1;
+    __syncwarp();
+    if(lane == 0) la[0] = 0;
+    __syncwarp();
+    bool any_inner = !fail;
+    while(any_inner && !fail)
+    {
+      any_inner = false;
+      int nb = 0;
+      for(int base = 0; base < na; base += 32)
+      {
+        const int32_t e = base + (int)lane < na ? la[base + (int)lane] : kBarrier;
+        int32_t o[2] = {kBarrier, kBarrier};
+        int cnt = 0;
+        if(e != kBarrier)
+        {
+          if(e < 0)
+          {
+            o[0] = e;
+            cnt = 1;
+          }
+          else
+          {
+            ++ninner;
+            int32_t c0, c1;
+            double d0, d1;
+            solo_visit(nodes, e, qp, c0, c1, d0, d1);
+            const bool in0 = d0 <= thr, in1 = d1 <= thr;
+            if(in0 && in1)
+            {
+              const D4* cr = reinterpret_cast<const D4*>(cens + e);
+              const D4 k0 = ldg256(cr), k1 = ldg256(cr + 1);
+              const double cl3[3] = {k0.x, k0.y, k0.z}, cr3[3] = {k0.w, k1.x, k1.y};
+              double dl = 0.0, dr = 0.0;
+#pragma unroll
+              for(int d = 0; d < 3; ++d)
+              {
+                const double a = cl3[d] - qp[d];
+                dl += a * a;
+                const double b = cr3[d] - qp[d];
+                dr += b * b;
+              }
+              const bool right_first = dl > dr;
+              o[0] = right_first ? c1 : c0;
+              o[1] = right_first ? c0 : c1;
+              cnt = 2;
+            }
+            else if(in0 || in1)
+            {
+              o[0] = in0 ? c0 : c1;
+              cnt = 1;
+            }
+          }
+        }
+        int tot = 0;
+        const int at = warp_excl_scan(cnt, tot);
+        if(nb + tot > kSoloCap)
+        {
+          fail = true;
+          break;
+        }
+        for(int k = 0; k < cnt; ++k) lb[nb + at + k] = o[k];
+        any_inner = any_inner || __ballot_sync(FULL, (cnt > 0 && o[0] >= 0) || (cnt > 1 && o[1] >= 0)) != 0u;
+        nb += tot;
+      }
+      __syncwarp();
+      int32_t* const tmp = la;
+      la = lb;
+      lb = tmp;
+      na = nb;
+    }
+    // ---- replay: the state machine over the ordered leaves ----
+    MinCand m;
+    mincand_reset(m);
+    if(fail)
+    {
+      if(lane == 0)
+      {
+        sd_ordered_query<NV>(nodes, cens, soup, q, minSq, cn, m, nleaf, ninner);
+        sd_finish<NV>(soup, prm, q, m, qi, phi, cps, nrms);
+      }
+      __syncwarp();
+      continue;
+    }
+    Contribs cl;
+    cl.n = 0;
+    for(int base = 0; base < na; base += 32)
+    {
+      const int nin = min(32, na - base);
+      double e_sq[NSUB];
+      V3 e_cp[NSUB];
+      int e_loc[NSUB];
+      int e_pos = 0;
+#pragma unroll
+      for(int u = 0; u < NSUB; ++u)
+      {
+        e_sq[u] = DBL_MAX;
+        e_cp[u] = {0.0, 0.0, 0.0};
+        e_loc[u] = 3;
+      }
+      if((int)lane < nin)
+      {
+        ++nleaf;
+        e_pos = -la[base + (int)lane] - 1;
+        V3 v[NV];
+        load_leaf<NV>(soup, e_pos, v);
+        e_cp[0] = closest_point_tri(q, v[0], v[1], v[2], e_loc[0], EPS);
+        const V3 dq = v3sub(e_cp[0], q);
+        e_sq[0] = v3dot(dq, dq);
+        if(NV == 4 && has_fourth(v[NV - 1]))
+        {
+          e_cp[NSUB - 1] = closest_point_tri(q, v[0], v[2], v[NV - 1], e_loc[NSUB - 1], EPS);
+          const V3 dq2 = v3sub(e_cp[NSUB - 1], q);
+          e_sq[NSUB - 1] = v3dot(dq2, dq2);
+        }
+      }
+      for(int i = 0; i < nin; ++i)
+      {
+        const int pos = __shfl_sync(FULL, e_pos, i);
+#pragma unroll
+        for(int u = 0; u < NSUB; ++u)
+        {
+          const double sq = shfl_f64(e_sq[u], i);
+          const V3 cp {shfl_f64(e_cp[u].x, i), shfl_f64(e_cp[u].y, i), shfl_f64(e_cp[u].z, i)};
+          const int loc = __shfl_sync(FULL, e_loc[u], i);
+          if(sq < 1e300) apply_candidate<NV>(soup, m, cl, cp, sq, loc, pos, u, cn);  // warp-uniform: every lane keeps the same state
+        }
+      }
+    }
+    if(cl.n) m.sumN = contrib_flush<NV>(soup, cl, m.sumN);
+    if(lane == 0) sd_finish<NV>(soup, prm, q, m, qi, phi, cps, nrms);
+    __syncwarp();
   }
   if(work)
   {

@@ -260,3 +260,30 @@ def test_host_to_host_query_is_pipelined_in_chunks(oracle, monkeypatch):
     monkeypatch.setenv("AXB_SD_PIPE_CHUNK", "0")  # pipeline off: same answer
     phi3, cp3, nrm3 = sd.computeDistances(q, True, True)
     assert np.array_equal(phi3, want_phi) and np.array_equal(cp3, cp) and np.array_equal(nrm3, nrm)
+
+
+def test_heavy_queries_take_the_warp_cooperative_path(oracle, monkeypatch):
+    """Queries at and around the centre of a sphere: hundreds to thousands of triangles within the 1e-6 tie window, the
+    remembered-leaf list of phase 1 overflows and the query is finished by sd_solo_kernel (exact minimum, then the
+    in-window leaves in the reference's visiting order, one warp per query).  icosphere(20): 4000 triangles, the ordered
+    frontier fits the scratch; icosphere(32): 10240 triangles, at the exact centre it does not and the warp falls back to
+    the serial ordered walk.  Both must match the oracle bit for bit, with and without the cooperative kernel."""
+    from axom_b200 import SignedDistance
+    rng = np.random.default_rng(3)
+    for freq in (20, 32):
+        x, y, z, conn = synth.icosphere(freq)
+        q = np.concatenate([np.zeros((1, 3)), rng.normal(0, 1e-9, (8, 3)), rng.normal(0, 1e-6, (16, 3)), rng.normal(0, 1e-3, (40, 3)),
+                            rng.normal(0, 0.02, (200, 3)), synth.uniform_grid_points(-0.05, 0.05, 12)])
+        q = np.concatenate([q, rng.uniform(-1.2, 1.2, (4096, 3))])  # enough for the Morton-sorted path
+        for cs in (True, False):
+            rphi, rcp, rn = oracle.SignedDistance(x, y, z, conn, 3, True, cs).compute(q, True, True, nthreads=0)
+            for solo_off in (False, True):
+                if solo_off:
+                    monkeypatch.setenv("AXB_SD_NO_SOLO", "1")
+                else:
+                    monkeypatch.delenv("AXB_SD_NO_SOLO", raising=False)
+                sd = SignedDistance(x, y, z, conn, 3, True, cs)
+                phi, cp, nr = sd.computeDistances(q, True, True)
+                assert np.array_equal(rphi, phi), (freq, cs, solo_off, int((rphi != phi).sum()))
+                assert np.array_equal(rcp, cp), (freq, cs, solo_off)
+                assert np.allclose(rn, nr, rtol=0, atol=1e-12), (freq, cs, solo_off)
