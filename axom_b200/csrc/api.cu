@@ -1036,11 +1036,11 @@ struct axb_sd
   // that the upload of chunk i+1 and the download of chunk i-1 overlap the kernel of chunk i
   struct QBufs
   {
-    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor, cand, cand_n, seed, solo, solo_scratch;
+    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor, cand, cand_n, seed, solo, solo_scratch, hint;
     void release(cudaStream_t st)
     {
       for(DevBuf* b : {&q_stage, &out_phi, &out_cp, &out_n, &qkeys_a, &qkeys_b, &qscratch, &qperm, &qbounds, &cursor, &cand, &cand_n, &seed, &solo,
-                       &solo_scratch})
+                       &solo_scratch, &hint})
         b->release(st);
     }
   } qb[2];
@@ -1208,7 +1208,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
                    s->sdnodes.as<SdNode>(), big_list, big_count);
       }
       big.release(ctx.stream);
-      for(int k = 0; k < 2; ++k) AXB_TRY(s->qb[k].cursor.reserve(sizeof(unsigned int), ctx.stream));
+      for(int k = 0; k < 2; ++k) AXB_TRY(s->qb[k].cursor.reserve(sizeof(unsigned int) * 4, ctx.stream));
       int bps = 0;
       if(s->nv == 3)
       {
@@ -1327,6 +1327,8 @@ int axb_sd_get_work_counters(const axb_sd* s, int64_t* leaf_tests, int64_t* inne
   return AXB_OK;
 }
 
+static bool solo_on_env() { return getenv("AXB_SD_NO_SOLO") == nullptr; }
+
 // One contiguous range of queries, enqueued on ctx.stream with the scratch set B: stage (host inputs), Morton
 // order, the query kernel, and -- for host outputs -- the copies back.  Does not synchronise.
 static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpts, int32_t npts, double* phi, double* cps, double* nrms,
@@ -1384,7 +1386,7 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
     }
     ScopedPhase ph(ctx, "query.kernel");
     // persistent warps: one resident wave, queries pulled from a device-side cursor
-    AXB_CUDA_TRY(cudaMemsetAsync(B.cursor.p, 0, sizeof(unsigned int), ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(B.cursor.p, 0, sizeof(unsigned int) * 4, ctx.stream));
     int sms = kNumSMsB200;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
     const int grid = (int)std::min<long long>(blocks_for(npts, 128), (long long)sms * (s->kernel == 2 ? s->two_blocks_per_sm : s->fast_blocks_per_sm));
@@ -1399,12 +1401,27 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
       AXB_TRY(B.cand_n.reserve((size_t)npts, ctx.stream));
       AXB_TRY(B.seed.reserve(sizeof(double) * (size_t)npts, ctx.stream));
       const int grid2 = blocks_for(npts, kSd2Threads);
+      // the sample pass: one query in 2^hint_shift (Morton order) searched first, its closest point is the first bound of
+      // its neighbours in the search proper
+      int hint_shift = 5;
+      if(const char* e = getenv("AXB_SD_HINT_SHIFT")) hint_shift = atoi(e);
+      double* hint_tab = nullptr;
+      int hint_n = 0, hint_grid = 0;
+      if(perm && hint_shift >= 3 && hint_shift <= 16 && npts >= (64 << hint_shift))
+      {
+        hint_n = (int)(((long long)npts + (1ll << hint_shift) - 1) >> hint_shift);
+        hint_grid = (int)std::min<long long>(blocks_for(hint_n, 128), (long long)sms * s->two_blocks_per_sm);
+        AXB_TRY(B.hint.reserve(sizeof(double) * 3 * (size_t)hint_n, ctx.stream));
+        hint_tab = B.hint.as<double>();
+      }
+      unsigned heavy_visits = solo_on_env() ? 384u : 0xffffffffu;
+      if(const char* e = getenv("AXB_SD_HEAVY")) heavy_visits = (unsigned)std::max(1, atoi(e));
       // heavy queries (list overflow, sign too close to call) are listed by the resolve kernel and finished one WARP each
       const unsigned solo_cap = (unsigned)std::min<long long>(npts, 1 << 20);
       const int solo_grid = std::min(2 * sms, blocks_for(npts, 32));
       unsigned int* solo_ctr = nullptr;
       int32_t* solo_list = nullptr;
-      const bool solo_on = getenv("AXB_SD_NO_SOLO") == nullptr;  // (a test hook: the serial walk in the resolve lane)
+      const bool solo_on = solo_on_env();  // (off: a test hook, the serial walk in the resolve lane)
       if(solo_on)
       {
         AXB_TRY(B.solo.reserve(16 + sizeof(int32_t) * (size_t)solo_cap, ctx.stream));
@@ -1417,9 +1434,15 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
       {
         {
           ScopedPhase p1(ctx, "query.min");
+          if(hint_tab)
+          {
+            AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, hint_grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, hint_n, perm,
+                            (int32_t*)nullptr, (uint8_t*)nullptr, (double*)nullptr, d_work, B.cursor.as<unsigned int>() + 1, 32u,
+                            s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits);
+          }
           AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
                           B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
-                          s->prm.compute_sign ? kTieWindow : 0.0);
+                          s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits);
         }
         ScopedPhase p2(ctx, "query.resolve");
         AXB_LAUNCH(ctx, sd_resolve_kernel<3>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
@@ -1433,9 +1456,15 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
       {
         {
           ScopedPhase p1(ctx, "query.min");
+          if(hint_tab)
+          {
+            AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, hint_grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, hint_n, perm,
+                            (int32_t*)nullptr, (uint8_t*)nullptr, (double*)nullptr, d_work, B.cursor.as<unsigned int>() + 1, 32u,
+                            s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits);
+          }
           AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
                           B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
-                          s->prm.compute_sign ? kTieWindow : 0.0);
+                          s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits);
         }
         ScopedPhase p2(ctx, "query.resolve");
         AXB_LAUNCH(ctx, sd_resolve_kernel<4>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),

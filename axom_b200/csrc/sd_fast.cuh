@@ -478,7 +478,7 @@ constexpr size_t kSdFastSmem = (size_t)kSmemStack * 128 * sizeof(unsigned long l
 constexpr int kPend = AXB_SD_PEND;                // queued leaves per lane
 constexpr int kLeafVote = AXB_SD_LEAF_VOTE;       // lanes with a queued leaf that trigger a leaf step
 constexpr int kFinishVote = AXB_SD_FINISH_VOTE;   // finished lanes that trigger a finalisation step
-constexpr int kQueryChunk = 512;  // queries a warp takes from the cursor at a time (a run of Morton neighbours)
+constexpr int kQueryChunk = 128;  // queries a warp takes from the cursor at a time (a run of Morton neighbours)
 
 template <int NV>
 __global__ void __launch_bounds__(128, AXB_SD_MIN_BLOCKS) sd_fast_kernel(const SdNode* __restrict__ nodes, const SdCen* __restrict__ cens, const double* __restrict__ soup, SdParams prm,

@@ -386,8 +386,15 @@ template <int NV>
 __global__ void __launch_bounds__(kSd2Threads, AXB_SD2_MIN_BLOCKS)
 sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup, Desc<3> qpts, int npts, const int32_t* __restrict__ perm,
               int32_t* __restrict__ cand, uint8_t* __restrict__ cand_n, double* __restrict__ seed, unsigned long long* __restrict__ work,
-              unsigned int* __restrict__ cursor, unsigned chunk, double window)
+              unsigned int* __restrict__ cursor, unsigned chunk, double window, const double* __restrict__ hint_tab, int hint_shift,
+              double* __restrict__ hint_out, int nfull, unsigned heavy_visits)
 {
+  // Two uses.  hint_out == nullptr: the search proper over the npts query slots.  hint_out != nullptr: the SAMPLE pass
+  // that runs first -- work item k is the query of Morton rank k * 2^hint_shift + 2^(hint_shift-1) (of nfull), and all
+  // that is kept of it is its closest point, hint_out[k].  The search proper then starts every query with the bound
+  // |q - hint_tab[rank >> hint_shift]|^2: a point of the surface found for a query at most 2^(hint_shift-1) ranks away,
+  // whatever the cursor hands to this lane before and after (small launches, chunk starts, the first query of a lane).
+  const bool sampling = hint_out != nullptr;
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned lane = lane_id();
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -423,6 +430,7 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
   int pending = 0;         // the lane's leaves waiting in the pool
   bool have_hint = false;
   unsigned nleaf = 0, ninner = 0;
+  unsigned visits0 = 0;  // ninner when the lane's query started
   unsigned wbase = 0, wcount = 0;
   bool exhausted = false;
   unsigned pool_head = 0, pool_n = 0;  // warp-uniform
@@ -433,8 +441,19 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
     // ---- lanes whose walk is over and whose leaves have all come back: store, free the lane ----
     if(qt >= 0 && cur == kBarrier && sp == 0 && pending == 0)
     {
-      cand_n[qt] = overflow ? kCandOverflow : (uint8_t)ncand;
-      seed[qt] = minSq;
+      if(sampling)
+      {
+        const bool got = minSq < 1e300;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        hint_out[3 * (size_t)qt + 0] = got ? minPt.x : nan;
+        hint_out[3 * (size_t)qt + 1] = got ? minPt.y : nan;
+        hint_out[3 * (size_t)qt + 2] = got ? minPt.z : nan;
+      }
+      else
+      {
+        cand_n[qt] = overflow ? kCandOverflow : (uint8_t)ncand;
+        seed[qt] = minSq;
+      }
       have_hint = have_hint || minSq < 1e300;
       qt = -1;
     }
@@ -472,7 +491,8 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
         if(qt < 0 && rank < wcount)
         {
           qt = (int)(wbase + rank);
-          const int qi = perm ? perm[qt] : qt;
+          const int qrank = sampling ? min((int)(((unsigned)qt << hint_shift) + ((1u << hint_shift) >> 1)), nfull - 1) : qt;
+          const int qi = perm ? perm[qrank] : qrank;
           qx = ld_comp<double>(qpts, 0, qi);
           qy = ld_comp<double>(qpts, 1, qi);
           qz = ld_comp<double>(qpts, 2, qi);
@@ -491,6 +511,16 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
             const double hx = wpt.x - qx, hy = wpt.y - qy, hz = wpt.z - qz;
             hsq = fmin(hsq, hx * hx + hy * hy + hz * hz);
           }
+          if(hint_tab)
+          {
+            const double* hp = hint_tab + 3 * (size_t)(qt >> hint_shift);
+            const double tx = __ldg(hp), ty = __ldg(hp + 1), tz = __ldg(hp + 2);
+            if(tx == tx)  // NaN: the sample query found nothing
+            {
+              const double hx = tx - qx, hy = ty - qy, hz = tz - qz;
+              hsq = fmin(hsq, hx * hx + hy * hy + hz * hz);
+            }
+          }
           if(hsq < 1e300)
           {
             thr = prune_threshold_w(hsq, window);
@@ -500,6 +530,7 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
           overflow = false;
           sp = 0;
           cur = 0;
+          visits0 = ninner;
         }
         const unsigned taken = min((unsigned)__popc(freem), wcount);
         wbase += taken;
@@ -585,7 +616,7 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
           }
           if(ncand < kCandCap)
           {
-            cand[(size_t)qt * kCandCap + ncand] = rpos;
+            if(!sampling) cand[(size_t)qt * kCandCap + ncand] = rpos;
             ++ncand;
           }
           else
@@ -607,6 +638,14 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
     float next_lb = 0.f;
     if(want_inner)
     {
+      if(cur >= 0 && ninner - visits0 >= heavy_visits)
+      {
+        // A heavy query (the neighbourhood of a centre of curvature: hundreds of near-equidistant patches).  Its serial
+        // chain would outlast everybody else's: the lane gives it up, and one whole warp of sd_solo_kernel redoes it.
+        overflow = true;
+        cur = kBarrier;
+        sp = 0;
+      }
       if(cur >= 0)
       {
         ++ninner;
