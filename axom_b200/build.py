@@ -42,7 +42,8 @@ def build(force=False, verbose=False):
             return LIB
         raise RuntimeError("nvcc not found at %s and no prebuilt %s" % (nvcc, LIB))
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("AXB_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-ccbin", os.environ.get("AXB_HOST_CXX", "/usr/bin/g++"), "-o", LIB] + [s for s in sources() if s.endswith(".cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:

@@ -1518,8 +1518,8 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
   unsigned long long* d_work = nullptr;
   if(s->count_work)
   {
-    AXB_TRY(s->work.reserve(sizeof(unsigned long long) * 2, ctx.stream));
-    AXB_CUDA_TRY(cudaMemsetAsync(s->work.p, 0, sizeof(unsigned long long) * 2, ctx.stream));
+    AXB_TRY(s->work.reserve(sizeof(unsigned long long) * 80, ctx.stream));
+    AXB_CUDA_TRY(cudaMemsetAsync(s->work.p, 0, sizeof(unsigned long long) * 80, ctx.stream));
     d_work = s->work.as<unsigned long long>();
   }
   // Opt-in (AXB_SD_PIPE_CHUNK = points per chunk): with host inputs AND host outputs, cut the call into chunks that
@@ -1571,6 +1571,24 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
     AXB_TRY(ctx.sync());
     s->last_leaf_tests = (int64_t)hw[0];
     s->last_inner_visits = (int64_t)hw[1];
+#ifdef AXB_SD_DEBUG_MISS
+    {
+      unsigned long long dbg[80];
+      AXB_CUDA_TRY(cudaMemcpy(dbg, d_work, sizeof(dbg), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[sd debug] queries that found nothing: %llu\n", dbg[2]);
+      for(unsigned long long k = 0; k < std::min<unsigned long long>(dbg[2], 4); ++k)
+      {
+        const unsigned long long* w = dbg + 4 + 18 * k;
+        auto D = [](unsigned long long b) { double v; memcpy(&v, &b, 8); return v; };
+        unsigned ml = (unsigned)w[8];
+        float mlf;
+        memcpy(&mlf, &ml, 4);
+        fprintf(stderr, "   slot %llu lane %llu: visits %llu, leaves pushed %llu returned %llu, h_own %.17g h_warp %.17g h_tab %.17g thr0 %.17g thr %.17g min leaf bound %.9g\n",
+                w[0], w[9], w[1], w[2] >> 32, w[2] & 0xffffffffull, D(w[3]), D(w[4]), D(w[5]), D(w[6]), D(w[7]), (double)mlf);
+        fprintf(stderr, "   MISS q %.17g %.17g %.17g hint %.17g %.17g %.17g\n", D(w[10]), D(w[11]), D(w[12]), D(w[13]), D(w[14]), D(w[15]));
+      }
+    }
+#endif
   }
   return ctx.finish_call();
 }

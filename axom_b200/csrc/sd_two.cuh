@@ -429,8 +429,13 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
   int32_t cur = kBarrier;  // >= 0 inner node in hand, kBarrier: none
   int pending = 0;         // the lane's leaves waiting in the pool
   bool have_hint = false;
+  bool hinted = false;  // the lane's query started with a first bound
   unsigned nleaf = 0, ninner = 0;
   unsigned visits0 = 0;  // ninner when the lane's query started
+#ifdef AXB_SD_DEBUG_MISS
+  double dbg_h0 = 0, dbg_h1 = 0, dbg_h2 = 0, dbg_thr0 = 0, dbg_px = 0, dbg_py = 0, dbg_pz = 0;
+  unsigned dbg_back = 0, dbg_pushed = 0, dbg_minlb = 0x7f800000u;
+#endif
   unsigned wbase = 0, wcount = 0;
   bool exhausted = false;
   unsigned pool_head = 0, pool_n = 0;  // warp-uniform
@@ -439,6 +444,21 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
   while(true)
   {
     // ---- lanes whose walk is over and whose leaves have all come back: store, free the lane ----
+    if(qt >= 0 && cur == kBarrier && sp == 0 && pending == 0 && hinted && !overflow && minSq >= 1e300)
+    {
+      // Nothing within the first bound.  That bound is the distance to a POINT of the surface, and the search minimises
+      // what the reference's closest_point(q, triangle, loc, EPS = 1e-12) returns per triangle -- which is not always the
+      // triangle's nearest point: on triangles whose squared area is below EPS (a 20 M-triangle sphere of radius 0.5:
+      // 1e-14) its fuzzy region tests pick an edge where a vertex is nearer, 3e-6 off in the squared distance.  A point
+      // found through one query can therefore be nearer than anything the reference arithmetic yields for its neighbour.
+      // Every leaf was rejected, so the miss is total and detectable: search again with no first bound (the bounds are
+      // lower bounds of the TRUE distance, hence of the reference's value too).  About 3 queries per million on C5.
+      hinted = false;
+      thr = DBL_MAX;
+      thr_f = inf_f;
+      cur = 0;
+      visits0 = ninner;
+    }
     if(qt >= 0 && cur == kBarrier && sp == 0 && pending == 0)
     {
       if(sampling)
@@ -453,6 +473,32 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
       {
         cand_n[qt] = overflow ? kCandOverflow : (uint8_t)ncand;
         seed[qt] = minSq;
+#ifdef AXB_SD_DEBUG_MISS
+        if(work && minSq >= 1e300 && !overflow)
+        {
+          const unsigned long long k = atomicAdd(&work[2], 1ull);
+          if(k < 4)
+          {
+            unsigned long long* w = work + 4 + 18 * k;
+            w[10] = __double_as_longlong(qx);
+            w[11] = __double_as_longlong(qy);
+            w[12] = __double_as_longlong(qz);
+            w[13] = __double_as_longlong(dbg_px);
+            w[14] = __double_as_longlong(dbg_py);
+            w[15] = __double_as_longlong(dbg_pz);
+            w[0] = (unsigned long long)qt;
+            w[1] = ninner - visits0;
+            w[2] = ((unsigned long long)dbg_pushed << 32) | dbg_back;
+            w[3] = __double_as_longlong(dbg_h0);
+            w[4] = __double_as_longlong(dbg_h1);
+            w[5] = __double_as_longlong(dbg_h2);
+            w[6] = __double_as_longlong(dbg_thr0);
+            w[7] = __double_as_longlong(thr);
+            w[8] = dbg_minlb;
+            w[9] = lane;
+          }
+        }
+#endif
       }
       have_hint = have_hint || minSq < 1e300;
       qt = -1;
@@ -500,16 +546,36 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
           thr = DBL_MAX;
           thr_f = inf_f;
           double hsq = DBL_MAX;
+#ifdef AXB_SD_DEBUG_MISS
+          dbg_h0 = dbg_h1 = dbg_h2 = -1.0;
+          dbg_back = dbg_pushed = 0;
+          dbg_minlb = 0x7f800000u;
+#endif
           if(have_hint)
           {
             // the closest point of the lane's previous query (a Morton neighbour) is a point of the surface
             const double hx = minPt.x - qx, hy = minPt.y - qy, hz = minPt.z - qz;
             hsq = hx * hx + hy * hy + hz * hz;
+#ifdef AXB_SD_DEBUG_MISS
+            dbg_h0 = hsq;
+            dbg_px = minPt.x;
+            dbg_py = minPt.y;
+            dbg_pz = minPt.z;
+#endif
           }
           if(hbest >= 0)
           {
             const double hx = wpt.x - qx, hy = wpt.y - qy, hz = wpt.z - qz;
             hsq = fmin(hsq, hx * hx + hy * hy + hz * hz);
+#ifdef AXB_SD_DEBUG_MISS
+            dbg_h1 = hx * hx + hy * hy + hz * hz;
+            if(dbg_h1 <= hsq)
+            {
+              dbg_px = wpt.x;
+              dbg_py = wpt.y;
+              dbg_pz = wpt.z;
+            }
+#endif
           }
           if(hint_tab)
           {
@@ -519,13 +585,26 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
             {
               const double hx = tx - qx, hy = ty - qy, hz = tz - qz;
               hsq = fmin(hsq, hx * hx + hy * hy + hz * hz);
+#ifdef AXB_SD_DEBUG_MISS
+              dbg_h2 = hx * hx + hy * hy + hz * hz;
+              if(dbg_h2 <= hsq)
+              {
+                dbg_px = tx;
+                dbg_py = ty;
+                dbg_pz = tz;
+              }
+#endif
             }
           }
-          if(hsq < 1e300)
+          hinted = hsq < 1e300;
+          if(hinted)
           {
             thr = prune_threshold_w(hsq, window);
             thr_f = thr < 3.0e38 ? __double2float_ru(thr) : inf_f;
           }
+#ifdef AXB_SD_DEBUG_MISS
+          dbg_thr0 = thr;
+#endif
           ncand = 0;
           overflow = false;
           sp = 0;
@@ -599,6 +678,9 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
         mine &= mine - 1u;
         const double rsq = shfl_f64(sq, src);
         const int rpos = __shfl_sync(FULL, pos, src);
+#ifdef AXB_SD_DEBUG_MISS
+        if(on) ++dbg_back;
+#endif
         const V3 rcp {shfl_f64(cp.x, src), shfl_f64(cp.y, src), shfl_f64(cp.z, src)};
         if(on && !overflow && rsq <= thr)
         {
@@ -715,6 +797,10 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
       // bound truncated to 27 bits (toward zero: never larger than the bound itself)
       pool[slot] = ((unsigned long long)(unsigned)(-next - 1) << 32) | ((unsigned long long)lane << 27) | (unsigned long long)(__float_as_uint(next_lb) >> 5);
       ++pending;
+#ifdef AXB_SD_DEBUG_MISS
+      ++dbg_pushed;
+      dbg_minlb = min(dbg_minlb, __float_as_uint(next_lb));
+#endif
       next = kBarrier;
     }
     pool_n += __popc(mpush);

@@ -287,3 +287,46 @@ def test_heavy_queries_take_the_warp_cooperative_path(oracle, monkeypatch):
                 assert np.array_equal(rphi, phi), (freq, cs, solo_off, int((rphi != phi).sum()))
                 assert np.array_equal(rcp, cp), (freq, cs, solo_off)
                 assert np.allclose(rn, nr, rtol=0, atol=1e-12), (freq, cs, solo_off)
+
+
+def test_first_bound_from_a_point_the_reference_arithmetic_cannot_reach(oracle, have_ref):
+    """One Morton part (2.5 M triangles, an open patch) of the 20 M-triangle sphere of BASELINE config C5, unsigned
+    distance, queries on the far side of the patch so that every closest point lies on the patch boundary.  Triangle
+    areas are 1e-7: their square is below the EPS = 1e-12 of the reference's closest_point(Point, Triangle, loc, EPS)
+    (primal/operators/closest_point.hpp:162-290), whose fuzzy region tests then return an edge point where a vertex is
+    nearer (3e-6 off in the squared distance).  A first bound taken from a neighbouring query's closest point (a vertex,
+    reached exactly from there) is then BELOW every value the reference arithmetic yields: the search must notice the
+    total miss and start over without a bound.  Truth: the reference-order kernel (mode 0, no bounds from hints), itself
+    pinned to the unmodified reference on a sample here."""
+    import torch
+    from axom_b200 import SignedDistance
+    from axom_b200 import dist as D
+    x, y, z, conn = synth.icosphere(1000)
+    P = np.stack([x, y, z], 1)
+    cen = (P[conn[:, 0]] + P[conn[:, 1]] + P[conn[:, 2]]) / 3.0
+    c = conn[D.morton_partition(cen, 8)[7]]
+    pc = cen[D.morton_partition(cen, 8)[7]].mean(axis=0)
+    rng = np.random.default_rng(11)
+    q = rng.uniform(-1.0, 1.0, (6_000_000, 3))
+    q = q[(q * np.sign(pc)).max(axis=1) < 0.0][:3_000_000]  # the octant opposite to the patch
+    assert len(q) > 500_000
+    qd = torch.from_numpy(np.ascontiguousarray(q)).cuda()
+    sd = SignedDistance(x, y, z, c, 3, False, False)
+    sd.setMode(0)
+    truth = sd.computeDistances(qd)[0]
+    sd.setMode(1)
+    got = sd.computeDistances(qd)[0]
+    assert int((got > 1e100).sum()) == 0
+    assert torch.equal(got, truth), int((got != truth).sum())
+    kind = "reference" if have_ref else "port"
+    want, _, _ = oracle.SignedDistance(x, y, z, c, 3, False, False, kind=kind).compute(q[:100_000], nthreads=0)
+    assert np.array_equal(want, truth[:100_000].cpu().numpy())
+    # the quirk itself, on one triangle of this mesh: EPS = 1e-12 picks edge AB, the exact tests pick vertex C
+    tri = np.array([[0.42520727074501397, 0.00068895192447202, 0.263055701802531, 0.42494387910357284, 0.00052631214548544, 0.2634813515373215,
+                     4.2513491742628706e-01, 2.6301083961343877e-04, 2.6317338925172956e-01]])
+    qq = np.array([[0.7702697736345363, -0.0036593517992807856, 0.47534102216064422]])
+    from axom_b200 import primal
+    for eps, loc_want in ((1e-12, -1), (1e-50, 2)):
+        cp_r, loc_r = oracle.closest_point_tri(qq, tri, eps, kind)
+        cp_g, loc_g = primal.closest_point(qq, tri.reshape(-1, 3, 3), eps)
+        assert loc_r[0] == loc_want and loc_g[0] == loc_want and np.array_equal(cp_r, cp_g)
