@@ -1050,6 +1050,7 @@ struct axb_sd
   int two_blocks_per_sm = 0;   // same for sd_two_phase_kernel
   int kernel = 2;              // mode 1 kernel: 2 = sd_two_phase_kernel (default), 1 = sd_fast_kernel (AXB_SD_KERNEL=fast)
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
+  std::map<std::string, double> setmesh_ms;  // device time of the phases of setMesh ("setmesh.*", "build.*")
   Ctx& ctx() { return bvh->ctx; }
 };
 
@@ -1080,8 +1081,15 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
   s->nnodes = nnodes;
   s->prm.watertight = is_watertight != 0;
   s->prm.compute_sign = compute_sign != 0;
+  cudaEvent_t tot0 = nullptr, tot1 = nullptr;
+  ctx.set_profiling(true);  // setMesh always times its phases (a dozen events): "setmesh.*" of axb_sd_get_phase_ms
   auto body = [&]() -> int {
     ctx.begin_call();
+    // (the total is timed with its own event pair: the BVH build inside resolves and drops the context's pending phases)
+    AXB_CUDA_TRY(cudaEventCreate(&tot0));
+    AXB_CUDA_TRY(cudaEventCreate(&tot1));
+    AXB_CUDA_TRY(cudaEventRecord(tot0, ctx.stream));
+    const int up = ctx.phase_begin("setmesh.upload");
     const cudaMemcpyKind kind = mesh_memspace == AXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     size_t conn_len = (size_t)ncells * (mixed ? 0 : nodes_per_cell);
     if(mixed)
@@ -1109,6 +1117,8 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       AXB_CUDA_TRY(cudaMemcpyAsync(s->z.p, z, nb, kind, ctx.stream));
     }
     if(cb) AXB_CUDA_TRY(cudaMemcpyAsync(s->conn.p, conn, cb, kind, ctx.stream));
+    ctx.phase_end(up);
+    const int cbx = ctx.phase_begin("setmesh.cell_boxes");
     // mesh node bounds (m_boxDomain)
     AXB_TRY(s->obounds.reserve(sizeof(unsigned long long) * 6, ctx.stream));
     unsigned long long init[6];
@@ -1147,6 +1157,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
         AXB_LAUNCH(ctx, cell_boxes_kernel<4>, blocks_for(ncells, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
                    s->conn.as<int32_t>(), ncells, s->cell_boxes.as<Box<double, 3>>());
     }
+    ctx.phase_end(cbx);
     AXB_TRY(ctx.sync());
     for(int d = 0; d < 3; ++d)
     {
@@ -1160,9 +1171,10 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
     bd.stride_bytes = 48;
     bd.ncomp = 6;
     bd.memspace = AXB_MEM_DEVICE;
-    AXB_TRY(axb_bvh_initialize(s->bvh, &bd, ncells));
+    AXB_TRY(axb_bvh_initialize(s->bvh, &bd, ncells));  // (its own phases: "build.*")
     // leaf geometry in sorted-leaf order
     const int nl = s->bvh->n;
+    const int gs = ctx.phase_begin("setmesh.gather_soup");
     AXB_TRY(s->soup.reserve(sizeof(double) * kLeafDoubles * (size_t)nl, ctx.stream));
     if(mixed)
       AXB_LAUNCH(ctx, gather_soup_mixed_kernel, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
@@ -1174,6 +1186,8 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       AXB_LAUNCH(ctx, gather_soup_kernel<4>, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
                  s->conn.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
     s->cell_boxes.release(ctx.stream);
+    ctx.phase_end(gs);
+    const int ob = ctx.phase_begin("setmesh.obb_build");
     // traversal records of the fast query mode (sd_fast.cuh): child AABBs + oriented bounds + ids,
     // one warp per tree entity
     {
@@ -1208,6 +1222,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
                    s->sdnodes.as<SdNode>(), big_list, big_count);
       }
       big.release(ctx.stream);
+      ctx.phase_end(ob);
       for(int k = 0; k < 2; ++k) AXB_TRY(s->qb[k].cursor.reserve(sizeof(unsigned int) * 4, ctx.stream));
       int bps = 0;
       if(s->nv == 3)
@@ -1240,9 +1255,22 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       if(const char* e = getenv("AXB_SD_KERNEL"))
         if(!strcmp(e, "fast")) s->kernel = 1;
     }
+    AXB_CUDA_TRY(cudaEventRecord(tot1, ctx.stream));
     return ctx.sync();
   };
   st = body();
+  if(st == AXB_OK)
+  {
+    ctx.resolve();
+    float tms = 0.f;
+    if(tot0 && tot1 && cudaEventElapsedTime(&tms, tot0, tot1) == cudaSuccess) s->setmesh_ms["setmesh.total"] = tms;
+    cudaGetLastError();
+    for(const auto& kv : ctx.acc)
+      if(kv.second.calls) s->setmesh_ms[kv.first] = kv.second.sum / (double)kv.second.calls;
+  }
+  ctx.set_profiling(false);
+  if(tot0) cudaEventDestroy(tot0);
+  if(tot1) cudaEventDestroy(tot1);
   if(st != AXB_OK)
   {
     axb_sd_destroy(s);
@@ -1289,7 +1317,18 @@ int axb_sd_set_profiling(axb_sd* s, int e)
 }
 int axb_sd_get_phase_ms(const axb_sd* s, const char* name, double* ms)
 {
-  return s ? axb_bvh_get_phase_ms(s->bvh, name, ms) : fail(AXB_ERR_BAD_ARG, "null handle");
+  if(!s || !name || !ms) return fail(AXB_ERR_BAD_ARG, "null argument");
+  if(!strncmp(name, "setmesh.", 8) || !strncmp(name, "setmesh_build.", 14))
+  {
+    // the phases of setMesh, always recorded: "setmesh.total|upload|cell_boxes|gather_soup|obb_build", and the BVH build inside it
+    // as "setmesh_build.total|bounds|morton|sort|agglo"
+    const std::string key = !strncmp(name, "setmesh_build.", 14) ? std::string("build.") + (name + 14) : std::string(name);
+    auto it = s->setmesh_ms.find(key);
+    if(it == s->setmesh_ms.end()) return fail(AXB_ERR_BAD_ARG, std::string("no timing recorded for phase ") + name);
+    *ms = it->second;
+    return AXB_OK;
+  }
+  return axb_bvh_get_phase_ms(s->bvh, name, ms);
 }
 int axb_sd_launch_count(const axb_sd* s, int64_t* n) { return s ? axb_bvh_launch_count(s->bvh, n) : fail(AXB_ERR_BAD_ARG, "null handle"); }
 

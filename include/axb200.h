@@ -194,7 +194,10 @@ int axb_sd_get_mesh_bounds(const axb_sd* sd, double* lo, double* hi);
  * points bit-identical, normals may differ in the last ulp by summation order) */
 int axb_sd_set_mode(axb_sd* sd, int mode);
 int axb_sd_set_profiling(axb_sd* sd, int level); /* 0 off, 1 phase timers, 2 + work counters (adds a sync per call) */
-int axb_sd_get_phase_ms(const axb_sd* sd, const char* name, double* ms); /* "setmesh.total" "query.total" "query.kernel" "query.sortq" */
+/* query phases (profiling on): "query.total" "query.sortq" "query.kernel" (= "query.min" + "query.resolve") "query.minreduce";
+ * setMesh phases (always recorded at creation): "setmesh.total" "setmesh.upload" "setmesh.cell_boxes" "setmesh.gather_soup"
+ * "setmesh.obb_build" and the BVH build inside it "setmesh_build.total|bounds|morton|sort|agglo" */
+int axb_sd_get_phase_ms(const axb_sd* sd, const char* name, double* ms);
 int axb_sd_launch_count(const axb_sd* sd, int64_t* n);
 /* work counters of the last query when profiling is enabled (device-side atomics in a
  * profiling build of the kernel): leaf tests and inner nodes visited */
