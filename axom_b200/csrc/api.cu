@@ -1031,7 +1031,7 @@ struct axb_sd
   bool count_work = false;
   SdParams prm;
   DevBuf x, y, z, conn, offsets, soup, cell_boxes, obounds, work;
-  DevBuf sdnodes, sdcens, sdup;
+  DevBuf sdnodes, sdcens, sdup, sdnodes64;
   // per-query scratch, two sets: a host-to-host query is cut into chunks that alternate between two streams so
   // that the upload of chunk i+1 and the download of chunk i-1 overlap the kernel of chunk i
   struct QBufs
@@ -1194,6 +1194,7 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       const long long entities = 2LL * nl - 1;
       AXB_TRY(s->sdnodes.reserve(sizeof(SdNode) * (size_t)(nl - 1), ctx.stream));
       AXB_TRY(s->sdcens.reserve(sizeof(SdCen) * (size_t)(nl - 1), ctx.stream));
+      AXB_TRY(s->sdnodes64.reserve(sizeof(SdNode64) * (size_t)(nl - 1), ctx.stream));
       const int blocks = blocks_for(entities * 32, 256);
       const Node<double, 3>* bn = s->bvh->nodes.as<Node<double, 3>>();
       int obb_max = kObbMaxRange;
@@ -1210,16 +1211,18 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       if(s->nv == 3)
       {
         AXB_LAUNCH(ctx, obb_build_kernel<3>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, big_list, big_count);
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdnodes64.as<SdNode64>(), obb_max, big_list,
+                   big_count);
         AXB_LAUNCH(ctx, obb_build_big_kernel<3>, 2 * sms, 512, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
-                   s->sdnodes.as<SdNode>(), big_list, big_count);
+                   s->sdnodes.as<SdNode>(), s->sdnodes64.as<SdNode64>(), big_list, big_count);
       }
       else
       {
         AXB_LAUNCH(ctx, obb_build_kernel<4>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, big_list, big_count);
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdnodes64.as<SdNode64>(), obb_max, big_list,
+                   big_count);
         AXB_LAUNCH(ctx, obb_build_big_kernel<4>, 2 * sms, 512, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
-                   s->sdnodes.as<SdNode>(), big_list, big_count);
+                   s->sdnodes.as<SdNode>(), s->sdnodes64.as<SdNode64>(), big_list, big_count);
       }
       big.release(ctx.stream);
       ctx.phase_end(ob);
@@ -1287,7 +1290,7 @@ int axb_sd_destroy(axb_sd* s)
   {
     cudaSetDevice(s->ctx().device);
     cudaStream_t st = s->ctx().stream;
-    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->offsets, &s->soup, &s->cell_boxes, &s->obounds, &s->work, &s->sdnodes, &s->sdcens, &s->sdup})
+    for(DevBuf* b : {&s->x, &s->y, &s->z, &s->conn, &s->offsets, &s->soup, &s->cell_boxes, &s->obounds, &s->work, &s->sdnodes, &s->sdcens, &s->sdup, &s->sdnodes64})
       b->release(st);
     for(int k = 0; k < 2; ++k)
     {
@@ -1475,11 +1478,11 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
           ScopedPhase p1(ctx, "query.min");
           if(hint_tab)
           {
-            AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, hint_grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, hint_n, perm,
+            AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, hint_grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, hint_n, perm,
                             (int32_t*)nullptr, (uint8_t*)nullptr, (double*)nullptr, d_work, B.cursor.as<unsigned int>() + 1, 32u,
                             s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits);
           }
-          AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
+          AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, npts, perm,
                           B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
                           s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits);
         }
@@ -1497,11 +1500,11 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
           ScopedPhase p1(ctx, "query.min");
           if(hint_tab)
           {
-            AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, hint_grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, hint_n, perm,
+            AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, hint_grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, hint_n, perm,
                             (int32_t*)nullptr, (uint8_t*)nullptr, (double*)nullptr, d_work, B.cursor.as<unsigned int>() + 1, 32u,
                             s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits);
           }
-          AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes.as<SdNode>(), s->soup.as<double>(), q, npts, perm,
+          AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, npts, perm,
                           B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
                           s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits);
         }

@@ -23,6 +23,8 @@
 // Queries are processed in Morton order of their position (one thread per query), so the threads of a
 // warp walk the same few nodes and their loads coalesce into L1-resident lines.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "sd.cuh"
 
@@ -57,8 +59,69 @@ struct alignas(32) SdCen
 };
 static_assert(sizeof(SdCen) == 64, "SdCen is 2 x 32 B");
 
+// The same bounds in HALF the bytes, for the order-free search of sd_two.cuh, which is bound by the L1 data pipe (every
+// lane reads its own record: one wavefront per 32-byte sector per lane).  2 x LDG.256 per visit instead of 4:
+//   frame    the first axis n as three 16-bit integers (direction only; decoded = normalised in binary32); the second
+//            axis is not stored: t1 = normalise(n x e_k), e_k the coordinate axis least aligned with n, t2 = n x t1, all
+//            in binary32 by sd_frame() -- the ONE function the build and the queries both call, so the extents are
+//            measured in exactly the frame the query evaluates (SdNode stores the same frame as floats);
+//   centres  16-bit integers in units of `step` (>= the node's half diagonal / 16000), decoded c = float(ci) * step;
+//   extents  binary16 in units of `step`, rounded UP against the DECODED centre (-inf marks an invalid child);
+//   origin   three floats (the node's AABB centre rounded to binary32; SdNode carries the same value as doubles).
+// Everything lossy happens in the build, before the extents are measured: the bound stays conservative and merely a
+// little looser (centre quantum = node size / 32000).
+struct alignas(32) SdNode64
+{
+  int32_t child[2];
+  float org[3];
+  float step;
+  int16_t nq[2][3];
+  int16_t cq[2][3];
+  uint16_t hq[2][3];
+  uint32_t pad_;
+};
+static_assert(sizeof(SdNode64) == 64, "SdNode64 is 2 x 32 B");
+
+// MUFU.RSQ: one instruction, 2 ulp, and -- what matters here -- a pure function of its input on a given GPU: the build
+// and the queries run on the same device and get the same bits
+__device__ __forceinline__ float sd_rsqrt(float x)
+{
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// frame from the 16-bit code of its first axis: fr[0..2] = n, fr[3..5] = t1 (t2 is obb_axes' binary32 cross product);
+// the axes are unit to 3e-7
+__device__ __forceinline__ void sd_frame(int cx, int cy, int cz, float* fr)
+{
+  const float vx = (float)cx, vy = (float)cy, vz = (float)cz;
+  const float inv = sd_rsqrt(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+  const float nx = __fmul_rn(vx, inv), ny = __fmul_rn(vy, inv), nz = __fmul_rn(vz, inv);
+  const float ax = fabsf(nx), ay = fabsf(ny), az = fabsf(nz);
+  // n x e_k for the axis k least aligned with n
+  const bool kx = ax <= ay && ax <= az, ky = !kx && ay <= az;
+  const float ux = kx ? 0.f : (ky ? -nz : ny), uy = kx ? nz : (ky ? 0.f : -nx), uz = kx ? -ny : (ky ? nx : 0.f);
+  const float iu = sd_rsqrt(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
+  fr[0] = nx;
+  fr[1] = ny;
+  fr[2] = nz;
+  fr[3] = __fmul_rn(ux, iu);
+  fr[4] = __fmul_rn(uy, iu);
+  fr[5] = __fmul_rn(uz, iu);
+}
+// 16-bit code of a unit vector (any scaling of the direction will do; the largest component uses the full range)
+__device__ __forceinline__ void sd_frame_code(const V3& n, int* code)
+{
+  const double m = fmax(fabs(n.x), fmax(fabs(n.y), fabs(n.z)));
+  const double s = m > 0.0 ? 32767.0 / m : 0.0;
+  code[0] = (int)rint(n.x * s);
+  code[1] = (int)rint(n.y * s);
+  code[2] = (int)rint(n.z * s);
+  if(code[0] == 0 && code[1] == 0 && code[2] == 0) code[2] = 32767;
+}
+
 // |M v|^2 <= (1 + 5e-7) |v|^2 for the rows M of a float-rounded frame: scale the bound down accordingly
-constexpr double kBoundScale = 1.0 - 1.0e-6;
+constexpr double kBoundScale = 1.0 - 2.0e-6;
 
 // the frame in double from the stored floats; the build and the queries MUST agree bit for bit on t2, which is the
 // BINARY32 cross product of the two stored axes (separately rounded products and differences) so that the binary32
@@ -108,12 +171,47 @@ __device__ __forceinline__ double warp_max(double v)
 // One warp per tree entity e: e < inner -> inner node e (leaves node_range[e]), else leaf e - inner.
 // The oriented bound of entity e is stored in its PARENT's record (slot = which child it is); the warp
 // of an inner entity also writes that node's child ids and origin into its own record.
-__device__ __forceinline__ void node_origin(const Node<double, 3>& nd, double* org)
+// origin of a node's records: the centre of its AABB rounded to binary32 (both record formats carry the same value),
+// and the quantum of the compact record's centres / extents
+__device__ __forceinline__ void node_origin(const Node<double, 3>& nd, double* org, float* step = nullptr)
 {
   Box<double, 3> u = nd.box[0];
   box_add(u, nd.box[1]);
+  const bool ok = box_valid(u);
+  double diag2 = 0.0, off = 0.0;
 #pragma unroll
-  for(int d = 0; d < 3; ++d) org[d] = box_valid(u) ? 0.5 * (u.lo[d] + u.hi[d]) : 0.0;
+  for(int d = 0; d < 3; ++d)
+  {
+    const double c = ok ? 0.5 * (u.lo[d] + u.hi[d]) : 0.0;
+    const float cf = (float)c;
+    org[d] = (fabsf(cf) <= 3.0e38f) ? (double)cf : 0.0;
+    const double e = ok ? fmax(u.hi[d] - org[d], org[d] - u.lo[d]) : 0.0;  // half extent seen from the rounded origin
+    diag2 += e * e;
+    off += fabs(c - org[d]);
+  }
+  if(step)
+  {
+    const double q = (sqrt(diag2) * (1.0 + 1e-6) + off) / 16000.0;
+    *step = (q > 1e-37 && q < 1e37) ? __double2float_ru(q) : (q >= 1e37 ? 3.0e38f : 1e-37f);
+  }
+}
+
+// one axis of a child's extent in the compact record: centre on the 16-bit grid, half extent in binary16 units of step,
+// rounded up against the decoded centre (pads as in store_extent)
+__device__ __forceinline__ void store_extent64(int16_t* cq, uint16_t* hq, int k, float step, double lo, double hi)
+{
+  const double mid = 0.5 * (lo + hi);
+  double t = rint(mid / (double)step);
+  t = fmin(fmax(t, -32767.0), 32767.0);
+  const int ci = (int)t;
+  const double cd = (double)__fmul_rn((float)ci, step);  // what the query decodes
+  const double h = fmax(hi - cd, cd - lo);
+  const double need = (h + 2.4e-7 * (fabs(cd) + h)) * (1.0 + 2.0e-7) / (double)step;  // decoded h = half * step, one rounding
+  cq[k] = (int16_t)ci;
+  const float nf = need < 6.0e4 ? __double2float_ru(need) : 6.0e4f;
+  __half hh = __float2half_ru(nf);
+  if(!(need < 6.0e4)) hh = __ushort_as_half((unsigned short)0x7c00);  // +inf: never prunes (cannot happen for |c|, h within the node)
+  hq[k] = __half_as_ushort(hh);
 }
 
 // Reductions over the threads that share one entity: a warp (small subtrees) or a whole block (big ones)
@@ -148,7 +246,7 @@ struct BlockGroup
 // oriented bound of the leaves [first, last] written into slot `link` of the parent's record
 template <int NV, typename Group>
 __device__ __forceinline__ void obb_of_range(const Group& g, const double* __restrict__ soup, int first, int last, const double* org,
-                                             float* __restrict__ out)
+                                             float* __restrict__ out, SdNode64* __restrict__ rec64, int slot, float step)
 {
   const int t = g.rank(), nt = g.size();
   const double omag = fabs(org[0]) + fabs(org[1]) + fabs(org[2]);
@@ -178,16 +276,12 @@ __device__ __forceinline__ void obb_of_range(const Group& g, const double* __res
   {
     n = {0.0, 0.0, 1.0};
   }
-  // tangent frame: t1 = normalise(n x e_k) with e_k the coordinate axis least aligned with n
-  const double ax = fabs(n.x), ay = fabs(n.y), az = fabs(n.z);
-  V3 ek = (ax <= ay && ax <= az) ? V3 {1.0, 0.0, 0.0} : ((ay <= az) ? V3 {0.0, 1.0, 0.0} : V3 {0.0, 0.0, 1.0});
-  V3 t1 = v3cross(n, ek);
-  {
-    const double s = 1.0 / sqrt(v3dot(t1, t1));
-    t1 = v3mul(t1, s);
-  }
-  // the stored frame: axes rounded to float, then everything below uses exactly what the query will see
-  float fr[6] = {(float)n.x, (float)n.y, (float)n.z, (float)t1.x, (float)t1.y, (float)t1.z};
+  // the stored frame: the normal on the 16-bit grid, the tangents derived from it in binary32 (sd_frame): everything
+  // below uses exactly what the queries will see, in either record format
+  int code[3];
+  sd_frame_code(n, code);
+  float fr[6];
+  sd_frame(code[0], code[1], code[2], fr);
   V3 A[3];
   obb_axes(fr, A);
   // pass 2: extents of all vertices along the frame, relative to the parent's origin
@@ -226,6 +320,8 @@ __device__ __forceinline__ void obb_of_range(const Group& g, const double* __res
       // pad by the rounding of the projections (a few ulp of the coordinate magnitude), then round outward
       const double pad = 1e-14 * (fabs(lo[k]) + fabs(hi[k]) + omag) + 1e-300;
       store_extent(out, k, lo[k] - pad, hi[k] + pad);
+      store_extent64(rec64->cq[slot], rec64->hq[slot], k, step, lo[k] - pad, hi[k] + pad);
+      rec64->nq[slot][k] = (int16_t)code[k];
     }
   }
 }
@@ -235,8 +331,8 @@ constexpr int kObbWarpRange = 4096;  // subtrees up to this many leaves are boun
 template <int NV>
 __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
                                                          const int32_t* __restrict__ leaf_parent, const int2* __restrict__ node_range,
-                                                         int nleaves, SdNode* __restrict__ sdn, SdCen* __restrict__ sdc, int obb_max_range,
-                                                         int32_t* __restrict__ big_list, unsigned int* __restrict__ big_count)
+                                                         int nleaves, SdNode* __restrict__ sdn, SdCen* __restrict__ sdc, SdNode64* __restrict__ sdn64,
+                                                         int obb_max_range, int32_t* __restrict__ big_list, unsigned int* __restrict__ big_count)
 {
   const int inner = nleaves - 1;
   const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -249,10 +345,20 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     first = r.x;
     last = r.y;
     link = nodes[e].parent;
-    if(lane < 2) sdn[e].child[lane] = nodes[e].child[lane];
+    if(lane < 2) sdn[e].child[lane] = sdn64[e].child[lane] = nodes[e].child[lane];
     double o[3];
-    node_origin(nodes[e], o);
-    if(lane < 3) sdn[e].org[lane] = o[lane];
+    float st;
+    node_origin(nodes[e], o, &st);
+    if(lane < 3)
+    {
+      sdn[e].org[lane] = o[lane];
+      sdn64[e].org[lane] = (float)o[lane];  // exact: the origin is a binary32 value
+    }
+    if(lane == 0)
+    {
+      sdn64[e].step = st;
+      sdn64[e].pad_ = 0u;
+    }
   }
   else
   {
@@ -261,30 +367,50 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
   }
   if(link < 0) return;  // the root is nobody's child
   float* out = sdn[link >> 1].cb[link & 1];
+  SdNode64* const rec64 = sdn64 + (link >> 1);
+  const int slot = link & 1;
   double org[3];
-  node_origin(nodes[link >> 1], org);
+  float step;
+  node_origin(nodes[link >> 1], org, &step);
   const Box<double, 3> bb = nodes[link >> 1].box[link & 1];  // this entity's AABB as the reference has it
   const bool valid = box_valid(bb);
   if(lane < 3) sdc[link >> 1].cen[link & 1][lane] = 0.5 * (bb.lo[lane] + bb.hi[lane]);
   const int count = last - first + 1;
   if(!valid || count > obb_max_range)
   {
-    // coordinate axes: the bound is the AABB itself (an invalid box is infinitely far)
+    // coordinate axes: the bound is the AABB itself (an invalid box is infinitely far).  The frame is the one sd_frame
+    // derives from the code (32767, 0, 0): n = e_x, t1 = e_z, t2 = -e_y.
     if(lane < 3)
     {
       const double omag = fabs(org[0]) + fabs(org[1]) + fabs(org[2]);
-      out[lane] = lane == 0 ? 1.f : 0.f;
-      out[3 + lane] = lane == 1 ? 1.f : 0.f;
+      float fr[6];
+      sd_frame(32767, 0, 0, fr);
+      out[lane] = fr[lane];
+      out[3 + lane] = fr[3 + lane];
+      rec64->nq[slot][lane] = lane == 0 ? (int16_t)32767 : (int16_t)0;
       if(valid)
       {
-        const double lo = bb.lo[lane] - org[lane], hi = bb.hi[lane] - org[lane];
+        V3 A[3];
+        obb_axes(fr, A);
+        const double a[3] = {A[lane].x, A[lane].y, A[lane].z};
+        double lo = 0.0, hi = 0.0;  // extent of the box's corners along axis `lane` of the frame (exact for signed unit axes)
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+        {
+          const double u = a[d] * (bb.lo[d] - org[d]), v = a[d] * (bb.hi[d] - org[d]);
+          lo += fmin(u, v);
+          hi += fmax(u, v);
+        }
         const double pad = 1e-14 * (fabs(lo) + fabs(hi) + omag) + 1e-300;
         store_extent(out, lane, lo - pad, hi + pad);
+        store_extent64(rec64->cq[slot], rec64->hq[slot], lane, step, lo - pad, hi + pad);
       }
       else
       {
         out[6 + lane] = 0.f;
         out[9 + lane] = __int_as_float(0xff800000);  // half extent -inf: |d - c| - h = +inf, infinitely far
+        rec64->cq[slot][lane] = 0;
+        rec64->hq[slot][lane] = (uint16_t)0xfc00;  // binary16 -inf
       }
     }
     return;
@@ -294,13 +420,13 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     if(lane == 0) big_list[atomicAdd(big_count, 1u)] = e;  // left to obb_build_big_kernel
     return;
   }
-  obb_of_range<NV>(WarpGroup {}, soup, first, last, org, out);
+  obb_of_range<NV>(WarpGroup {}, soup, first, last, org, out, rec64, slot, step);
 }
 
 // the big subtrees queued by obb_build_kernel: one block per entity
 template <int NV>
 __global__ void __launch_bounds__(512) obb_build_big_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
-                                                             const int2* __restrict__ node_range, SdNode* __restrict__ sdn,
+                                                             const int2* __restrict__ node_range, SdNode* __restrict__ sdn, SdNode64* __restrict__ sdn64,
                                                              const int32_t* __restrict__ big_list, const unsigned int* __restrict__ big_count)
 {
   __shared__ double sh[32];
@@ -311,8 +437,9 @@ __global__ void __launch_bounds__(512) obb_build_big_kernel(const double* __rest
     const int2 r = node_range[e];
     const int link = nodes[e].parent;
     double org[3];
-    node_origin(nodes[link >> 1], org);
-    obb_of_range<NV>(BlockGroup {sh}, soup, r.x, r.y, org, sdn[link >> 1].cb[link & 1]);
+    float step;
+    node_origin(nodes[link >> 1], org, &step);
+    obb_of_range<NV>(BlockGroup {sh}, soup, r.x, r.y, org, sdn[link >> 1].cb[link & 1], sdn64 + (link >> 1), link & 1, step);
   }
 }
 

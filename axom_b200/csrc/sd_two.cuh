@@ -81,7 +81,7 @@ constexpr int kCandCap = AXB_SD2_CAND_CAP;     // remembered leaves per query
 // 3.6e-7 |r|_1 (covered by m) + 2.4e-7 (|c| + h) (covered by the pad store_extent adds to h).  The third axis is
 // the binary32 cross product of the stored two, bit-identical in the build (obb_axes); the sum of three squares
 // loses 4 * 2^-24 = 2.4e-7 relative and the frame is orthonormal to ~2e-7 (|M v|^2 <= (1 + 5e-7) |v|^2): kBoundScaleF.
-constexpr float kBoundScaleF = 1.0f - 1.0e-6f;
+constexpr float kBoundScaleF = 1.0f - 2.0e-6f;
 #ifndef AXB_SD2_NORMAL_F64
   #define AXB_SD2_NORMAL_F64 1
 #endif
@@ -384,7 +384,7 @@ constexpr size_t kSd2SmemMin = (size_t)kSd2Threads * (size_t)kSd2Stack * sizeof(
 
 template <int NV>
 __global__ void __launch_bounds__(kSd2Threads, AXB_SD2_MIN_BLOCKS)
-sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup, Desc<3> qpts, int npts, const int32_t* __restrict__ perm,
+sd_min_kernel(const SdNode64* __restrict__ nodes, const double* __restrict__ soup, Desc<3> qpts, int npts, const int32_t* __restrict__ perm,
               int32_t* __restrict__ cand, uint8_t* __restrict__ cand_n, double* __restrict__ seed, unsigned long long* __restrict__ work,
               unsigned int* __restrict__ cursor, unsigned chunk, double window, const double* __restrict__ hint_tab, int hint_shift,
               double* __restrict__ hint_out, int nfull, unsigned heavy_visits)
@@ -731,23 +731,41 @@ sd_min_kernel(const SdNode* __restrict__ nodes, const double* __restrict__ soup,
       if(cur >= 0)
       {
         ++ninner;
+        // the compact record (SdNode64): two sectors, decoded into the layout obb_sqdist_mixed expects
         const D4* rec = reinterpret_cast<const D4*>(nodes + cur);
-        const D4 r0 = ldg256(rec), r1 = ldg256(rec + 1), r2 = ldg256(rec + 2), r3 = ldg256(rec + 3);
-        const long long ids = __double_as_longlong(r0.x);
-        const int32_t child0 = (int32_t)(ids & 0xffffffffll), child1 = (int32_t)(ids >> 32);
-        const double qrx = qx - r0.y, qry = qy - r0.z, qrz = qz - r0.w;
+        const D4 r0 = ldg256(rec), r1 = ldg256(rec + 1);
+        const int32_t child0 = __double2loint(r0.x), child1 = __double2hiint(r0.x);
+        const float ox = __int_as_float(__double2loint(r0.y)), oy = __int_as_float(__double2hiint(r0.y));
+        const float oz = __int_as_float(__double2loint(r0.z)), step = __int_as_float(__double2hiint(r0.z));
+        const unsigned w6 = (unsigned)__double2loint(r0.w), w7 = (unsigned)__double2hiint(r0.w);
+        const unsigned w8 = (unsigned)__double2loint(r1.x), w9 = (unsigned)__double2hiint(r1.x);
+        const unsigned w10 = (unsigned)__double2loint(r1.y), w11 = (unsigned)__double2hiint(r1.y);
+        const unsigned w12 = (unsigned)__double2loint(r1.z), w13 = (unsigned)__double2hiint(r1.z);
+        const unsigned w14 = (unsigned)__double2loint(r1.w);
+        const double qrx = qx - (double)ox, qry = qy - (double)oy, qrz = qz - (double)oz;
         const float rx = __double2float_rn(qrx), ry = __double2float_rn(qry), rz = __double2float_rn(qrz);
         const float r1n = fabsf(rx) + fabsf(ry) + fabsf(rz);
         const float mg = 5.0e-7f * r1n;
         float f[24];
         {
-          const double w[12] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-#pragma unroll
-          for(int k = 0; k < 12; ++k)
-          {
-            f[2 * k] = __int_as_float(__double2loint(w[k]));
-            f[2 * k + 1] = __int_as_float(__double2hiint(w[k]));
-          }
+          auto lo16 = [](unsigned w) { return (int)(short)(w & 0xffffu); };
+          auto hi16 = [](unsigned w) { return (int)(short)(w >> 16); };
+          auto hlo = [](unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); };
+          auto hhi = [](unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); };
+          sd_frame(lo16(w6), hi16(w6), lo16(w7), f);
+          sd_frame(hi16(w7), lo16(w8), hi16(w8), f + 12);
+          f[6] = __fmul_rn((float)lo16(w9), step);
+          f[7] = __fmul_rn((float)hi16(w9), step);
+          f[8] = __fmul_rn((float)lo16(w10), step);
+          f[18] = __fmul_rn((float)hi16(w10), step);
+          f[19] = __fmul_rn((float)lo16(w11), step);
+          f[20] = __fmul_rn((float)hi16(w11), step);
+          f[9] = __fmul_rn(hlo(w12), step);
+          f[10] = __fmul_rn(hhi(w12), step);
+          f[11] = __fmul_rn(hlo(w13), step);
+          f[21] = __fmul_rn(hhi(w13), step);
+          f[22] = __fmul_rn(hlo(w14), step);
+          f[23] = __fmul_rn(hhi(w14), step);
         }
 #if AXB_SD2_NORMAL_F64
         float s0 = obb_sqdist_mixed(f, qrx, qry, qrz, rx, ry, rz, mg), s1 = obb_sqdist_mixed(f + 12, qrx, qry, qrz, rx, ry, rz, mg);
