@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) sd_up_kernel(const Node<double, 3>* __res
 }
 
 #ifndef AXB_SD2_MIN_BLOCKS
-  #define AXB_SD2_MIN_BLOCKS 4
+  #define AXB_SD2_MIN_BLOCKS 5
 #endif
 #ifndef AXB_SD2_SMEM_STACK
   #define AXB_SD2_SMEM_STACK 16
