@@ -1211,20 +1211,20 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       if(s->nv == 3)
       {
         AXB_LAUNCH(ctx, obb_build_kernel<3>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdnodes64.as<SdNode64>(), obb_max, big_list,
-                   big_count);
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, big_list, big_count);
         AXB_LAUNCH(ctx, obb_build_big_kernel<3>, 2 * sms, 512, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
-                   s->sdnodes.as<SdNode>(), s->sdnodes64.as<SdNode64>(), big_list, big_count);
+                   s->sdnodes.as<SdNode>(), big_list, big_count);
       }
       else
       {
         AXB_LAUNCH(ctx, obb_build_kernel<4>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdnodes64.as<SdNode64>(), obb_max, big_list,
-                   big_count);
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, big_list, big_count);
         AXB_LAUNCH(ctx, obb_build_big_kernel<4>, 2 * sms, 512, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
-                   s->sdnodes.as<SdNode>(), s->sdnodes64.as<SdNode64>(), big_list, big_count);
+                   s->sdnodes.as<SdNode>(), big_list, big_count);
       }
       big.release(ctx.stream);
+      // the same bounds as 64-byte records for the order-free search (sd_two.cuh)
+      if(nl > 1) AXB_LAUNCH(ctx, sd64_pack_kernel, blocks_for(nl - 1, 256), 256, s->sdnodes.as<SdNode>(), bn, nl - 1, s->sdnodes64.as<SdNode64>());
       ctx.phase_end(ob);
       for(int k = 0; k < 2; ++k) AXB_TRY(s->qb[k].cursor.reserve(sizeof(unsigned int) * 4, ctx.stream));
       int bps = 0;

@@ -246,7 +246,7 @@ struct BlockGroup
 // oriented bound of the leaves [first, last] written into slot `link` of the parent's record
 template <int NV, typename Group>
 __device__ __forceinline__ void obb_of_range(const Group& g, const double* __restrict__ soup, int first, int last, const double* org,
-                                             float* __restrict__ out, SdNode64* __restrict__ rec64, int slot, float step)
+                                             float* __restrict__ out)
 {
   const int t = g.rank(), nt = g.size();
   const double omag = fabs(org[0]) + fabs(org[1]) + fabs(org[2]);
@@ -320,8 +320,6 @@ __device__ __forceinline__ void obb_of_range(const Group& g, const double* __res
       // pad by the rounding of the projections (a few ulp of the coordinate magnitude), then round outward
       const double pad = 1e-14 * (fabs(lo[k]) + fabs(hi[k]) + omag) + 1e-300;
       store_extent(out, k, lo[k] - pad, hi[k] + pad);
-      store_extent64(rec64->cq[slot], rec64->hq[slot], k, step, lo[k] - pad, hi[k] + pad);
-      rec64->nq[slot][k] = (int16_t)code[k];
     }
   }
 }
@@ -331,8 +329,8 @@ constexpr int kObbWarpRange = 4096;  // subtrees up to this many leaves are boun
 template <int NV>
 __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
                                                          const int32_t* __restrict__ leaf_parent, const int2* __restrict__ node_range,
-                                                         int nleaves, SdNode* __restrict__ sdn, SdCen* __restrict__ sdc, SdNode64* __restrict__ sdn64,
-                                                         int obb_max_range, int32_t* __restrict__ big_list, unsigned int* __restrict__ big_count)
+                                                         int nleaves, SdNode* __restrict__ sdn, SdCen* __restrict__ sdc, int obb_max_range,
+                                                         int32_t* __restrict__ big_list, unsigned int* __restrict__ big_count)
 {
   const int inner = nleaves - 1;
   const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -345,20 +343,10 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     first = r.x;
     last = r.y;
     link = nodes[e].parent;
-    if(lane < 2) sdn[e].child[lane] = sdn64[e].child[lane] = nodes[e].child[lane];
+    if(lane < 2) sdn[e].child[lane] = nodes[e].child[lane];
     double o[3];
-    float st;
-    node_origin(nodes[e], o, &st);
-    if(lane < 3)
-    {
-      sdn[e].org[lane] = o[lane];
-      sdn64[e].org[lane] = (float)o[lane];  // exact: the origin is a binary32 value
-    }
-    if(lane == 0)
-    {
-      sdn64[e].step = st;
-      sdn64[e].pad_ = 0u;
-    }
+    node_origin(nodes[e], o);
+    if(lane < 3) sdn[e].org[lane] = o[lane];
   }
   else
   {
@@ -367,11 +355,8 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
   }
   if(link < 0) return;  // the root is nobody's child
   float* out = sdn[link >> 1].cb[link & 1];
-  SdNode64* const rec64 = sdn64 + (link >> 1);
-  const int slot = link & 1;
   double org[3];
-  float step;
-  node_origin(nodes[link >> 1], org, &step);
+  node_origin(nodes[link >> 1], org);
   const Box<double, 3> bb = nodes[link >> 1].box[link & 1];  // this entity's AABB as the reference has it
   const bool valid = box_valid(bb);
   if(lane < 3) sdc[link >> 1].cen[link & 1][lane] = 0.5 * (bb.lo[lane] + bb.hi[lane]);
@@ -387,7 +372,6 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
       sd_frame(32767, 0, 0, fr);
       out[lane] = fr[lane];
       out[3 + lane] = fr[3 + lane];
-      rec64->nq[slot][lane] = lane == 0 ? (int16_t)32767 : (int16_t)0;
       if(valid)
       {
         V3 A[3];
@@ -403,14 +387,11 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
         }
         const double pad = 1e-14 * (fabs(lo) + fabs(hi) + omag) + 1e-300;
         store_extent(out, lane, lo - pad, hi + pad);
-        store_extent64(rec64->cq[slot], rec64->hq[slot], lane, step, lo - pad, hi + pad);
       }
       else
       {
         out[6 + lane] = 0.f;
         out[9 + lane] = __int_as_float(0xff800000);  // half extent -inf: |d - c| - h = +inf, infinitely far
-        rec64->cq[slot][lane] = 0;
-        rec64->hq[slot][lane] = (uint16_t)0xfc00;  // binary16 -inf
       }
     }
     return;
@@ -420,13 +401,13 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     if(lane == 0) big_list[atomicAdd(big_count, 1u)] = e;  // left to obb_build_big_kernel
     return;
   }
-  obb_of_range<NV>(WarpGroup {}, soup, first, last, org, out, rec64, slot, step);
+  obb_of_range<NV>(WarpGroup {}, soup, first, last, org, out);
 }
 
 // the big subtrees queued by obb_build_kernel: one block per entity
 template <int NV>
 __global__ void __launch_bounds__(512) obb_build_big_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
-                                                             const int2* __restrict__ node_range, SdNode* __restrict__ sdn, SdNode64* __restrict__ sdn64,
+                                                             const int2* __restrict__ node_range, SdNode* __restrict__ sdn,
                                                              const int32_t* __restrict__ big_list, const unsigned int* __restrict__ big_count)
 {
   __shared__ double sh[32];
@@ -437,10 +418,49 @@ __global__ void __launch_bounds__(512) obb_build_big_kernel(const double* __rest
     const int2 r = node_range[e];
     const int link = nodes[e].parent;
     double org[3];
-    float step;
-    node_origin(nodes[link >> 1], org, &step);
-    obb_of_range<NV>(BlockGroup {sh}, soup, r.x, r.y, org, sdn[link >> 1].cb[link & 1], sdn64 + (link >> 1), link & 1, step);
+    node_origin(nodes[link >> 1], org);
+    obb_of_range<NV>(BlockGroup {sh}, soup, r.x, r.y, org, sdn[link >> 1].cb[link & 1]);
   }
+}
+
+// SdNode -> SdNode64, one thread per inner node (a stream: 128 B in, 64 B out).  The frame code is recovered exactly from
+// the stored first axis (n = normalise(code): code_k = rint(32767 n_k / max|n|)); the extent [c - h, c + h] of the full
+// record (already padded outward) is re-expressed on the compact record's grid, rounded outward again.
+__global__ void __launch_bounds__(256) sd64_pack_kernel(const SdNode* __restrict__ sdn, const Node<double, 3>* __restrict__ nodes, int inner,
+                                                         SdNode64* __restrict__ out)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if(e >= inner) return;
+  const SdNode a = sdn[e];
+  SdNode64 r;
+  double org[3];
+  float step;
+  node_origin(nodes[e], org, &step);
+  r.child[0] = a.child[0];
+  r.child[1] = a.child[1];
+#pragma unroll
+  for(int d = 0; d < 3; ++d) r.org[d] = (float)a.org[d];  // exact: the origin is a binary32 value
+  r.step = step;
+  r.pad_ = 0u;
+#pragma unroll
+  for(int s = 0; s < 2; ++s)
+  {
+    const float* f = a.cb[s];
+    const float m = fmaxf(fabsf(f[0]), fmaxf(fabsf(f[1]), fabsf(f[2])));
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
+    {
+      r.nq[s][k] = (int16_t)(int)rintf(32767.0f * (f[k] / m));
+      if(f[9 + k] >= 0.f)
+        store_extent64(r.cq[s], r.hq[s], k, step, (double)f[6 + k] - (double)f[9 + k], (double)f[6 + k] + (double)f[9 + k]);
+      else
+      {
+        r.cq[s][k] = 0;
+        r.hq[s][k] = (uint16_t)0xfc00;  // binary16 -inf: an invalid child is infinitely far
+      }
+    }
+  }
+  out[e] = r;
 }
 
 // squared distance lower bound from the query to the oriented box of a child: f = the 12 floats of the
