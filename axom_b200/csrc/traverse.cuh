@@ -178,6 +178,37 @@ struct RayQuery
 #pragma unroll
     for(int k = 0; k < D; ++k) c[k] = o[k];
   }
+  // where the ray ENTERS the tree's bounds (its origin if inside): rays that enter near each other walk the same nodes,
+  // whereas their origins say nothing (an origin outside the bounds would be clamped to the boundary of the Morton grid
+  // -- every origin beyond a corner to the same cell).  false: the ray misses the bounds and has no candidates.
+  // Processing order only; the candidates come from operator() below.
+  __device__ __forceinline__ bool sort_point(const T* bmin, const T* bmax, T* c) const
+  {
+    T t0 = (T)0, t1 = Lim<T>::max();
+    bool hit = true;
+#pragma unroll
+    for(int k = 0; k < D; ++k)
+    {
+      if(dir[k] == (T)0)
+        hit = hit && !(o[k] < bmin[k] || o[k] > bmax[k]);
+      else
+      {
+        T a = (bmin[k] - o[k]) * inv[k], b = (bmax[k] - o[k]) * inv[k];
+        if(a > b)
+        {
+          const T t = a;
+          a = b;
+          b = t;
+        }
+        t0 = a > t0 ? a : t0;
+        t1 = b < t1 ? b : t1;
+      }
+    }
+    hit = hit && t0 <= t1 * ((T)1 + (T)1e-5) + (T)1e-30;  // generous: a grazing ray is merely sorted with the hits
+#pragma unroll
+    for(int k = 0; k < D; ++k) c[k] = o[k] + t0 * dir[k];
+    return hit;
+  }
   __device__ __forceinline__ bool operator()(const Box<T, D>& bb) const
   {
     T tmin = Lim<T>::min();
@@ -575,8 +606,21 @@ __global__ void __launch_bounds__(256) scatter_pairs_kernel(const int4* __restri
   if(firsts) firsts[o] = p.x;
 }
 
-// Morton keys of the queries' reference points over the BVH bounds (centroid of a box, origin of a ray):
-// (code << 32) | index, for radix_sort.cuh.  Only the processing ORDER depends on it.
+template <typename T, int D, class Query>
+__device__ __forceinline__ bool query_sort_point(const Query& q, const T*, const T*, T* c)
+{
+  q.center(c);
+  return true;
+}
+template <typename T, int D>
+__device__ __forceinline__ bool query_sort_point(const RayQuery<T, D>& q, const T* bmin, const T* bmax, T* c)
+{
+  return q.sort_point(bmin, bmax, c);
+}
+
+// Morton keys of the queries' reference points over the BVH bounds (centroid of a box, entry point of a ray):
+// (code << 32) | index, for radix_sort.cuh.  Only the processing ORDER depends on it.  The digit histograms are
+// aggregated per warp first (match.any): clustered queries would otherwise serialise on one shared-memory counter.
 template <typename T, int D, class Query, class State>
 __global__ void __launch_bounds__(256) find_query_keys_kernel(Desc<Query::NCOMP> prims, int nq, const State* __restrict__ st,
                                                                unsigned long long* __restrict__ keys, uint32_t* __restrict__ ghist)
@@ -584,37 +628,52 @@ __global__ void __launch_bounds__(256) find_query_keys_kernel(Desc<Query::NCOMP>
   __shared__ uint32_t sh[rsort::MAX_PASSES * rsort::RADIX];
   for(int i = threadIdx.x; i < rsort::MAX_PASSES * rsort::RADIX; i += blockDim.x) sh[i] = 0;
   __syncthreads();
-  T mn[D], inv[D];
+  T mn[D], mx[D], inv[D];
 #pragma unroll
   for(int d = 0; d < D; ++d)
   {
     mn[d] = st->bmin[d];
+    mx[d] = st->bmax[d];
     inv[d] = st->inv_extent[d];
   }
-  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x)
+  const unsigned lane = lane_id();
+  for(long long base = (long long)blockIdx.x * blockDim.x; base < nq; base += (long long)gridDim.x * blockDim.x)
   {
-    Query q;
-    q.load(prims, i, (T)0, 1);
-    T c[D];
-    q.center(c);
-    uint32_t qd[D];
-    constexpr int bits = 32 / D;
-#pragma unroll
-    for(int d = 0; d < D; ++d)
+    const long long i = base + threadIdx.x;  // whole warps stay in the loop: match.any needs every lane
+    const bool valid = i < nq;
+    uint32_t code = 0xffffffffu;
+    if(valid)
     {
-      T v = (c[d] - mn[d]) * inv[d] * (T)(1 << bits);
-      v = v > (T)0 ? v : (T)0;  // also maps NaN to 0
-      v = v < (T)((1 << bits) - 1) ? v : (T)((1 << bits) - 1);
-      qd[d] = (uint32_t)(int32_t)v;
-    }
-    uint32_t code;
-    if(D == 2)
-      code = spread_bits_2d(qd[0]) | (spread_bits_2d(qd[1]) << 1);
-    else
-      code = spread_bits_3d(qd[0]) | (spread_bits_3d(qd[1]) << 1) | (spread_bits_3d(qd[D - 1]) << 2);
-    keys[i] = ((unsigned long long)code << 32) | (unsigned long long)(uint32_t)i;
+      Query q;
+      q.load(prims, i, (T)0, 1);
+      T c[D];
+      if(query_sort_point<T, D>(q, mn, mx, c))
+      {
+        uint32_t qd[D];
+        constexpr int bits = 32 / D;
 #pragma unroll
-    for(int p = 0; p < rsort::MAX_PASSES; ++p) atomicAdd(&sh[p * rsort::RADIX + ((code >> (p * 8)) & 255u)], 1u);
+        for(int d = 0; d < D; ++d)
+        {
+          T v = (c[d] - mn[d]) * inv[d] * (T)(1 << bits);
+          v = v > (T)0 ? v : (T)0;  // also maps NaN to 0
+          v = v < (T)((1 << bits) - 1) ? v : (T)((1 << bits) - 1);
+          qd[d] = (uint32_t)(int32_t)v;
+        }
+        if(D == 2)
+          code = spread_bits_2d(qd[0]) | (spread_bits_2d(qd[1]) << 1);
+        else
+          code = spread_bits_3d(qd[0]) | (spread_bits_3d(qd[1]) << 1) | (spread_bits_3d(qd[D - 1]) << 2);
+      }
+      keys[i] = ((unsigned long long)code << 32) | (unsigned long long)(uint32_t)i;
+    }
+    // lanes with the same code add once, together
+    const unsigned grp = __match_any_sync(0xffffffffu, code) & __ballot_sync(0xffffffffu, valid);
+    if(valid && (grp & ((1u << lane) - 1u)) == 0u)
+    {
+      const unsigned n = (unsigned)__popc(grp);
+#pragma unroll
+      for(int p = 0; p < rsort::MAX_PASSES; ++p) atomicAdd(&sh[p * rsort::RADIX + ((code >> (p * 8)) & 255u)], n);
+    }
   }
   __syncthreads();
   for(int i = threadIdx.x; i < rsort::MAX_PASSES * rsort::RADIX; i += blockDim.x)
