@@ -925,8 +925,8 @@ def run_ours(args):
                 "traffic": None, "kernel": "sd_min_kernel (exact-minimum search: sample pass + search proper, 2 launches)", "kernel_ms": min_ms,
                 "all_kernels_ms": kernel_ms, "resolve_and_heavy_ms": resolve_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "not HBM-bound: every lane reads its own 128-byte node record per step, so the limiter is the L1 data pipe "
-                        "(one wavefront per 128-byte line per lane) -- see l1; the HBM fraction is reported because the contract asks for it"}
+                "note": "not HBM-bound: a tree search, every lane reads its own 64-byte node record per step; the limiter is instruction "
+                        "issue (68 % of cycles) and step latency -- see l1; the HBM fraction is reported because the contract asks for it"}
     if prof:
         roofline["traffic"] = prof.get("dram_bytes_per_launch")
         roofline["traffic_source"] = prof.get("source")
@@ -936,18 +936,18 @@ def run_ours(args):
             "frac_of_nominal_fp64_peak": flops / (kernel_ms * 1e-3) / 37.2e12,
             "nominal_fp64_peak": "37.2 TFLOP/s = 148 SMs x 64 DFMA/clk x 1.965 GHz (not in MEASURED_PEAKS.json)",
             "note": "phase 1 evaluates the oriented bounds in binary32 (conservatively) and only the normal axis and the leaves in binary64"}
-    # the L1 side: every lane reads its own 128-byte node record (4 sectors = 4 wavefronts per visit) and 96-byte leaf
+    # the L1 side: every lane reads its own 64-byte node record (2 sectors = 2 wavefronts per visit) and 96-byte leaf
     # record (3 per test); nothing coalesces across lanes.  1 wavefront per clock per SM at best.
-    sectors = 4.0 * inner_visits + 3.0 * leaf_tests
-    l1 = {"bound": "l1 data pipe (LSU wavefronts)", "wavefronts_per_launch_modelled": sectors,
-          "achieved_gwavefronts_per_s": sectors / (min_ms * 1e-3) / 1e9, "peak_gwavefronts_per_s": 148 * 1.965,
-          "frac_modelled": sectors / (min_ms * 1e-3) / 1e9 / (148 * 1.965),
+    sectors = 2.0 * inner_visits + 3.0 * leaf_tests
+    l1 = {"wavefronts_per_launch_modelled": sectors, "achieved_gwavefronts_per_s": sectors / (min_ms * 1e-3) / 1e9,
+          "peak_gwavefronts_per_s": 148 * 1.965, "frac_modelled": sectors / (min_ms * 1e-3) / 1e9 / (148 * 1.965),
           "frac_ncu": (pk.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") or 0.0) / 100.0 or None,
           "lanes_active_ncu": pk.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
           "issue_slots_ncu": pk.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-          "note": "ncu (profiles/r2w_sd_two_phase_ncu_full.txt): sd_min_kernel keeps the L1 data pipe 88.6 % busy (global loads 7.9 G "
-                  "sectors + the shared-memory stack and leaf pool), 21.9 of 32 lanes active, issue slots 45 %, FP64 pipe 13 %, L2 hit "
-                  "95 %, DRAM 3.4 GB per launch; the modelled figure counts the node and leaf records only"}
+          "note": "ncu (profiles/r2za_sd_two_phase_ncu_full.txt): sd_min_kernel issues in 68 % of its cycles (33.8 G warp instructions, "
+                  "22.6 of 32 lanes active, 5 blocks of 93 registers per SM), L1 data pipe 55 % busy (4.4 G sectors of global loads with "
+                  "the 64-byte records; 89 % with the 128-byte ones, profiles/r2w), FP64 pipe 15 %, L2 hit 94 %, DRAM 3.0 GB per "
+                  "launch: bound by instruction issue and the dependent latency of a traversal step, not by any memory level"}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample, checked against the GPU result ----
     cpu = None
