@@ -1427,6 +1427,47 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
       perm = B.qperm.as<int32_t>();
     }
     ScopedPhase ph(ctx, "query.kernel");
+    // Opt-in (AXB_SD_L2_PERSIST=<fraction of L2 to set aside, e.g. 0.5>): an L2 persisting access-policy window over the
+    // compact node records for the duration of the query kernels.  Measured on C2 (profiles/r2zc_*): no gain -- the
+    // search is not bound by any memory level and its L2 hit rate is 94 % without it -- so it is off by default.
+    bool l2_window = false;
+    if(const char* e = getenv("AXB_SD_L2_PERSIST"))
+    {
+      const double frac = atof(e);
+      int l2 = 0, maxwin = 0;
+      cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx.device);
+      cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, ctx.device);
+      if(frac > 0.0 && l2 > 0 && maxwin > 0 && s->kernel == 2)
+      {
+        const size_t carve = (size_t)(frac * (double)l2);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        const size_t bytes = std::min<size_t>(s->sdnodes64.cap, (size_t)maxwin);
+        av.accessPolicyWindow.base_ptr = s->sdnodes64.p;
+        av.accessPolicyWindow.num_bytes = bytes;
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)std::max<size_t>(bytes, 1));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        l2_window = cudaStreamSetAttribute(ctx.stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+        cudaGetLastError();
+      }
+    }
+    struct WindowOff
+    {
+      cudaStream_t st;
+      bool on;
+      ~WindowOff()
+      {
+        if(!on) return;
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+      }
+    } window_off {ctx.stream, l2_window};
     // persistent warps: one resident wave, queries pulled from a device-side cursor
     AXB_CUDA_TRY(cudaMemsetAsync(B.cursor.p, 0, sizeof(unsigned int) * 4, ctx.stream));
     int sms = kNumSMsB200;
