@@ -1605,12 +1605,13 @@ int axb_sd_compute_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts
     AXB_CUDA_TRY(cudaMemsetAsync(s->work.p, 0, sizeof(unsigned long long) * 80, ctx.stream));
     d_work = s->work.as<unsigned long long>();
   }
-  // Opt-in (AXB_SD_PIPE_CHUNK = points per chunk): with host inputs AND host outputs, cut the call into chunks that
+  // With host inputs AND host outputs, cut the call into chunks (AXB_SD_PIPE_CHUNK = points per chunk, 0 = off) that
   // alternate between two streams, so the PCIe traffic of neighbouring chunks hides behind the kernel (pinned host
-  // buffers).  The result does not depend on the chunking: queries are independent.  Off by default: measured on the
-  // C2 workload (tools/pipe_probe.py) the copies do overlap, but a persistent kernel per chunk loses as much in
-  // start-up and tail (8 x 2 M points: 110.9 ms, 2 x 8 M: 105.8 ms, unchunked: 107.0 ms of which 96.3 ms kernel).
-  long long pipe_chunk = 0;
+  // buffers).  The result does not depend on the chunking: queries are independent.
+  // Default: three chunks once the call is large (>= 4 M points).  Measured on C2 with pinned buffers (profiles/r2zd_*):
+  // unchunked 69.4 ms, 2 chunks 66.9, 3 chunks 66.1, 4 chunks 67.1, 8 chunks 69.0 (58.6 ms of it kernels): since the
+  // sample pass and the cooperative heavy-query kernel, a 5.6 M-point launch costs little more per point than a 16.8 M one.
+  long long pipe_chunk = npts >= (4 << 20) ? ((long long)npts + 2) / 3 : 0;
   if(const char* e = getenv("AXB_SD_PIPE_CHUNK")) pipe_chunk = atoll(e);
   const bool host_in = resolve_memspace(qpts->memspace, qpts->comp[0]) == AXB_MEM_HOST;
   if(host_in && out_memspace == AXB_MEM_HOST && !ctx.async && pipe_chunk > 0 && (long long)npts >= 2 * pipe_chunk)
