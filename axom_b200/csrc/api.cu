@@ -1195,34 +1195,56 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       AXB_TRY(s->sdnodes.reserve(sizeof(SdNode) * (size_t)(nl - 1), ctx.stream));
       AXB_TRY(s->sdcens.reserve(sizeof(SdCen) * (size_t)(nl - 1), ctx.stream));
       AXB_TRY(s->sdnodes64.reserve(sizeof(SdNode64) * (size_t)(nl - 1), ctx.stream));
-      const int blocks = blocks_for(entities * 32, 256);
+      const int blocks = blocks_for(entities, 256);  // one thread per entity; larger subtrees are queued for a warp / a block
       const Node<double, 3>* bn = s->bvh->nodes.as<Node<double, 3>>();
       int obb_max = kObbMaxRange;
       if(const char* e = getenv("AXB_SD_OBB_MAX")) obb_max = atoi(e);
       // subtrees of more than kObbWarpRange leaves are queued and bounded by whole blocks
       DevBuf big;
       const size_t big_cap = (size_t)std::max(nl - 1, 1);
-      AXB_TRY(big.reserve(sizeof(int32_t) * (big_cap + 1), ctx.stream));
+      AXB_TRY(big.reserve(sizeof(int32_t) * 2 * (big_cap + 1), ctx.stream));
       unsigned int* big_count = big.as<unsigned int>();
-      int32_t* big_list = big.as<int32_t>() + 1;
-      AXB_CUDA_TRY(cudaMemsetAsync(big_count, 0, sizeof(unsigned int), ctx.stream));
+      unsigned int* mid_count = big_count + 1;
+      int32_t* big_list = big.as<int32_t>() + 2;
+      int32_t* mid_list = big_list + big_cap;
+      AXB_CUDA_TRY(cudaMemsetAsync(big_count, 0, 2 * sizeof(unsigned int), ctx.stream));
       int sms = kNumSMsB200;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
+      // the subtrees' area-weighted normal sums, bottom-up in one sweep (child_sum[2 * node + side][3]; freed below)
+      DevBuf nsum, narr;
+      AXB_TRY(nsum.reserve(sizeof(double) * 6 * (size_t)std::max(nl - 1, 1), ctx.stream));
+      AXB_TRY(narr.reserve(sizeof(unsigned int) * (size_t)std::max(nl - 1, 1), ctx.stream));
+      AXB_CUDA_TRY(cudaMemsetAsync(narr.p, 0, sizeof(unsigned int) * (size_t)std::max(nl - 1, 1), ctx.stream));
+      if(s->nv == 3)
+        AXB_LAUNCH(ctx, normal_sums_kernel<3>, blocks_for(nl, 256), 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(), nl,
+                   nsum.as<double>(), narr.as<unsigned int>());
+      else
+        AXB_LAUNCH(ctx, normal_sums_kernel<4>, blocks_for(nl, 256), 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(), nl,
+                   nsum.as<double>(), narr.as<unsigned int>());
+      const double* child_sum = nsum.as<double>();
       if(s->nv == 3)
       {
         AXB_LAUNCH(ctx, obb_build_kernel<3>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, big_list, big_count);
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, mid_list, mid_count, big_list,
+                   big_count, child_sum);
+        AXB_LAUNCH(ctx, obb_build_mid_kernel<3>, 8 * sms, 256, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
+                   s->sdnodes.as<SdNode>(), mid_list, mid_count, child_sum);
         AXB_LAUNCH(ctx, obb_build_big_kernel<3>, 2 * sms, 512, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
-                   s->sdnodes.as<SdNode>(), big_list, big_count);
+                   s->sdnodes.as<SdNode>(), big_list, big_count, child_sum);
       }
       else
       {
         AXB_LAUNCH(ctx, obb_build_kernel<4>, blocks, 256, s->soup.as<double>(), bn, s->bvh->leaf_parent.as<int32_t>(),
-                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, big_list, big_count);
+                   s->bvh->node_range.as<int2>(), nl, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), obb_max, mid_list, mid_count, big_list,
+                   big_count, child_sum);
+        AXB_LAUNCH(ctx, obb_build_mid_kernel<4>, 8 * sms, 256, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
+                   s->sdnodes.as<SdNode>(), mid_list, mid_count, child_sum);
         AXB_LAUNCH(ctx, obb_build_big_kernel<4>, 2 * sms, 512, s->soup.as<double>(), bn, s->bvh->node_range.as<int2>(),
-                   s->sdnodes.as<SdNode>(), big_list, big_count);
+                   s->sdnodes.as<SdNode>(), big_list, big_count, child_sum);
       }
       big.release(ctx.stream);
+      nsum.release(ctx.stream);
+      narr.release(ctx.stream);
       // the same bounds as 64-byte records for the order-free search (sd_two.cuh)
       if(nl > 1) AXB_LAUNCH(ctx, sd64_pack_kernel, blocks_for(nl - 1, 256), 256, s->sdnodes.as<SdNode>(), bn, nl - 1, s->sdnodes64.as<SdNode64>());
       ctx.phase_end(ob);

@@ -223,6 +223,14 @@ struct WarpGroup
   __device__ __forceinline__ double min(double v) const { return warp_min(v); }
   __device__ __forceinline__ double max(double v) const { return warp_max(v); }
 };
+struct SerialGroup  // one thread does the whole entity (subtrees of a few leaves: three quarters of all entities)
+{
+  __device__ __forceinline__ int rank() const { return 0; }
+  __device__ __forceinline__ int size() const { return 1; }
+  __device__ __forceinline__ double sum(double v) const { return v; }
+  __device__ __forceinline__ double min(double v) const { return v; }
+  __device__ __forceinline__ double max(double v) const { return v; }
+};
 struct BlockGroup
 {
   double* sh;  // 32 doubles of shared memory
@@ -243,28 +251,74 @@ struct BlockGroup
   __device__ __forceinline__ double max(double v) const { return reduce(v, -DBL_MAX, [](double x) { return warp_max(x); }); }
 };
 
+template <int NV>
+__device__ __forceinline__ V3 leaf_area_normal(const double* __restrict__ soup, int p)
+{
+  V3 v[NV];
+  load_leaf<NV>(soup, p, v);
+  V3 c = v3cross(v3sub(v[1], v[0]), v3sub(v[2], v[0]));
+  if(NV == 4 && has_fourth(v[NV - 1])) c = v3add(c, v3cross(v3sub(v[2], v[0]), v3sub(v[NV - 1], v[0])));
+  return c;
+}
+
+// Area-weighted normal sums of every subtree in ONE bottom-up sweep (they are additive): one thread per leaf climbs the
+// parent links; at every node the first child to arrive parks its sum and retires, the second adds LEFT + RIGHT (a fixed
+// order: the result does not depend on who arrives first) and carries on.  child_sum[2 * node + side] ends up holding the
+// sum of the subtree hanging on that side -- what obb_of_range needs for the entity stored in that slot.
+template <int NV>
+__global__ void __launch_bounds__(256) normal_sums_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
+                                                           const int32_t* __restrict__ leaf_parent, int nleaves, double* __restrict__ child_sum,
+                                                           unsigned int* __restrict__ arrived)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p >= nleaves) return;
+  V3 c = leaf_area_normal<NV>(soup, p);
+  int link = leaf_parent[p];
+  while(link >= 0)
+  {
+    const int node = link >> 1, side = link & 1;
+    double* mine = child_sum + 3 * (size_t)link;
+    mine[0] = c.x;
+    mine[1] = c.y;
+    mine[2] = c.z;
+    __threadfence();
+    if(atomicAdd(arrived + node, 1u) == 0u) return;
+    __threadfence();
+    const volatile double* other = child_sum + 3 * (size_t)(link ^ 1);
+    const V3 o {other[0], other[1], other[2]};
+    c = side == 0 ? v3add(c, o) : v3add(o, c);
+    link = nodes[node].parent;
+  }
+}
+
 // oriented bound of the leaves [first, last] written into slot `link` of the parent's record
 template <int NV, typename Group>
 __device__ __forceinline__ void obb_of_range(const Group& g, const double* __restrict__ soup, int first, int last, const double* org,
-                                             float* __restrict__ out)
+                                             float* __restrict__ out, const double* __restrict__ nsum = nullptr)
 {
   const int t = g.rank(), nt = g.size();
   const double omag = fabs(org[0]) + fabs(org[1]) + fabs(org[2]);
-  // pass 1: area-weighted normal sum
+  // pass 1: area-weighted normal sum -- additive over the tree, so normally it arrives precomputed (normal_sums_kernel)
   double nx = 0.0, ny = 0.0, nz = 0.0;
-  for(int p = first + t; p <= last; p += nt)
+  if(nsum)
   {
-    V3 v[NV];
-    load_leaf<NV>(soup, p, v);
-    V3 c = v3cross(v3sub(v[1], v[0]), v3sub(v[2], v[0]));
-    if(NV == 4 && has_fourth(v[NV - 1])) c = v3add(c, v3cross(v3sub(v[2], v[0]), v3sub(v[NV - 1], v[0])));
-    nx += c.x;
-    ny += c.y;
-    nz += c.z;
+    nx = nsum[0];
+    ny = nsum[1];
+    nz = nsum[2];
   }
-  nx = g.sum(nx);
-  ny = g.sum(ny);
-  nz = g.sum(nz);
+  else
+  {
+    for(int p = first + t; p <= last; p += nt)
+    {
+      const V3 c = leaf_area_normal<NV>(soup, p);
+      nx += c.x;
+      ny += c.y;
+      nz += c.z;
+    }
+    nx = g.sum(nx);
+    ny = g.sum(ny);
+    nz = g.sum(nz);
+  }
   double len2 = nx * nx + ny * ny + nz * nz;
   V3 n;
   if(len2 > 1e-280 && len2 < 1e280)
@@ -326,16 +380,25 @@ __device__ __forceinline__ void obb_of_range(const Group& g, const double* __res
 
 constexpr int kObbWarpRange = 4096;  // subtrees up to this many leaves are bounded by one warp, larger ones by a block
 
+constexpr int kObbSerialRange = 8;  // subtrees up to this many leaves are bounded by ONE THREAD
+
+// One THREAD per tree entity e: e < inner -> inner node e (leaves node_range[e]), else leaf e - inner.  The thread writes the
+// node's own header (child ids, origin), its centroid in the parent's SdCen, and -- for invalid boxes, huge subtrees (AABB
+// kept) and subtrees of at most kObbSerialRange leaves -- the oriented bound itself.  Larger subtrees are queued: up to
+// kObbWarpRange leaves for a warp each (obb_build_mid_kernel), beyond that for a block each (obb_build_big_kernel).
+// (Round 1 gave every entity a warp: 4 M warps for 2 M triangles, three quarters of them for one or two leaves.)
 template <int NV>
 __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
                                                          const int32_t* __restrict__ leaf_parent, const int2* __restrict__ node_range,
                                                          int nleaves, SdNode* __restrict__ sdn, SdCen* __restrict__ sdc, int obb_max_range,
-                                                         int32_t* __restrict__ big_list, unsigned int* __restrict__ big_count)
+                                                         int32_t* __restrict__ mid_list, unsigned int* __restrict__ mid_count,
+                                                         int32_t* __restrict__ big_list, unsigned int* __restrict__ big_count,
+                                                         const double* __restrict__ child_sum)
 {
   const int inner = nleaves - 1;
-  const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  if(e >= inner + nleaves) return;
-  const int lane = (int)lane_id();
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if(gid >= (long long)inner + nleaves) return;
+  const int e = (int)gid;
   int first, last, link;
   if(e < inner)
   {
@@ -343,10 +406,12 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
     first = r.x;
     last = r.y;
     link = nodes[e].parent;
-    if(lane < 2) sdn[e].child[lane] = nodes[e].child[lane];
+    sdn[e].child[0] = nodes[e].child[0];
+    sdn[e].child[1] = nodes[e].child[1];
     double o[3];
     node_origin(nodes[e], o);
-    if(lane < 3) sdn[e].org[lane] = o[lane];
+#pragma unroll
+    for(int d = 0; d < 3; ++d) sdn[e].org[d] = o[d];
   }
   else
   {
@@ -359,25 +424,27 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
   node_origin(nodes[link >> 1], org);
   const Box<double, 3> bb = nodes[link >> 1].box[link & 1];  // this entity's AABB as the reference has it
   const bool valid = box_valid(bb);
-  if(lane < 3) sdc[link >> 1].cen[link & 1][lane] = 0.5 * (bb.lo[lane] + bb.hi[lane]);
+#pragma unroll
+  for(int d = 0; d < 3; ++d) sdc[link >> 1].cen[link & 1][d] = 0.5 * (bb.lo[d] + bb.hi[d]);
   const int count = last - first + 1;
   if(!valid || count > obb_max_range)
   {
     // coordinate axes: the bound is the AABB itself (an invalid box is infinitely far).  The frame is the one sd_frame
     // derives from the code (32767, 0, 0): n = e_x, t1 = e_z, t2 = -e_y.
-    if(lane < 3)
+    const double omag = fabs(org[0]) + fabs(org[1]) + fabs(org[2]);
+    float fr[6];
+    sd_frame(32767, 0, 0, fr);
+    V3 A[3];
+    obb_axes(fr, A);
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
     {
-      const double omag = fabs(org[0]) + fabs(org[1]) + fabs(org[2]);
-      float fr[6];
-      sd_frame(32767, 0, 0, fr);
-      out[lane] = fr[lane];
-      out[3 + lane] = fr[3 + lane];
+      out[k] = fr[k];
+      out[3 + k] = fr[3 + k];
       if(valid)
       {
-        V3 A[3];
-        obb_axes(fr, A);
-        const double a[3] = {A[lane].x, A[lane].y, A[lane].z};
-        double lo = 0.0, hi = 0.0;  // extent of the box's corners along axis `lane` of the frame (exact for signed unit axes)
+        const double a[3] = {A[k].x, A[k].y, A[k].z};
+        double lo = 0.0, hi = 0.0;  // extent of the box's corners along axis k of the frame
 #pragma unroll
         for(int d = 0; d < 3; ++d)
         {
@@ -386,29 +453,50 @@ __global__ void __launch_bounds__(256) obb_build_kernel(const double* __restrict
           hi += fmax(u, v);
         }
         const double pad = 1e-14 * (fabs(lo) + fabs(hi) + omag) + 1e-300;
-        store_extent(out, lane, lo - pad, hi + pad);
+        store_extent(out, k, lo - pad, hi + pad);
       }
       else
       {
-        out[6 + lane] = 0.f;
-        out[9 + lane] = __int_as_float(0xff800000);  // half extent -inf: |d - c| - h = +inf, infinitely far
+        out[6 + k] = 0.f;
+        out[9 + k] = __int_as_float(0xff800000);  // half extent -inf: |d - c| - h = +inf, infinitely far
       }
     }
     return;
   }
   if(count > kObbWarpRange)
+    big_list[atomicAdd(big_count, 1u)] = e;  // left to obb_build_big_kernel
+  else if(count > kObbSerialRange)
+    mid_list[atomicAdd(mid_count, 1u)] = e;  // left to obb_build_mid_kernel
+  else
+    obb_of_range<NV>(SerialGroup {}, soup, first, last, org, out, child_sum + 3 * (size_t)link);
+}
+
+// the subtrees of kObbSerialRange < leaves <= kObbWarpRange queued by obb_build_kernel: one warp per entity
+template <int NV>
+__global__ void __launch_bounds__(256) obb_build_mid_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
+                                                             const int2* __restrict__ node_range, SdNode* __restrict__ sdn,
+                                                             const int32_t* __restrict__ mid_list, const unsigned int* __restrict__ mid_count,
+                                                             const double* __restrict__ child_sum)
+{
+  const unsigned n = *mid_count;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  for(unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps)
   {
-    if(lane == 0) big_list[atomicAdd(big_count, 1u)] = e;  // left to obb_build_big_kernel
-    return;
+    const int e = mid_list[i];
+    const int2 r = node_range[e];
+    const int link = nodes[e].parent;
+    double org[3];
+    node_origin(nodes[link >> 1], org);
+    obb_of_range<NV>(WarpGroup {}, soup, r.x, r.y, org, sdn[link >> 1].cb[link & 1], child_sum + 3 * (size_t)link);
   }
-  obb_of_range<NV>(WarpGroup {}, soup, first, last, org, out);
 }
 
 // the big subtrees queued by obb_build_kernel: one block per entity
 template <int NV>
 __global__ void __launch_bounds__(512) obb_build_big_kernel(const double* __restrict__ soup, const Node<double, 3>* __restrict__ nodes,
                                                              const int2* __restrict__ node_range, SdNode* __restrict__ sdn,
-                                                             const int32_t* __restrict__ big_list, const unsigned int* __restrict__ big_count)
+                                                             const int32_t* __restrict__ big_list, const unsigned int* __restrict__ big_count,
+                                                             const double* __restrict__ child_sum)
 {
   __shared__ double sh[32];
   const unsigned n = *big_count;
@@ -419,7 +507,7 @@ __global__ void __launch_bounds__(512) obb_build_big_kernel(const double* __rest
     const int link = nodes[e].parent;
     double org[3];
     node_origin(nodes[link >> 1], org);
-    obb_of_range<NV>(BlockGroup {sh}, soup, r.x, r.y, org, sdn[link >> 1].cb[link & 1]);
+    obb_of_range<NV>(BlockGroup {sh}, soup, r.x, r.y, org, sdn[link >> 1].cb[link & 1], child_sum + 3 * (size_t)link);
   }
 }
 
