@@ -330,3 +330,23 @@ def test_first_bound_from_a_point_the_reference_arithmetic_cannot_reach(oracle, 
         cp_r, loc_r = oracle.closest_point_tri(qq, tri, eps, kind)
         cp_g, loc_g = primal.closest_point(qq, tri.reshape(-1, 3, 3), eps)
         assert loc_r[0] == loc_want and loc_g[0] == loc_want and np.array_equal(cp_r, cp_g)
+
+
+@pytest.mark.parametrize("scale,shift", [(1e-3, (1.0e5, -3.0e5, 7.0e5)), (1.0e7, (0.0, 0.0, 0.0)), (1e-6, (0.0, 0.0, 0.0)), (1.0, (2.0e9, 2.0e9, -2.0e9))])
+def test_compact_records_far_from_the_origin_and_at_extreme_scales(oracle, scale, shift):
+    """The 64-byte node records keep the node origin in binary32 and centres / extents on a per-node 16-bit grid.  A tiny mesh
+    far from the origin (the rounded origin is then farther from the node than the node is wide), a huge one and a
+    microscopic one must still give the reference's distances bit for bit: the quantisation only loosens the bounds."""
+    from axom_b200 import SignedDistance
+    x, y, z, conn = synth.icosphere(14)
+    s = np.array(shift)
+    x, y, z = x * scale + s[0], y * scale + s[1], z * scale + s[2]
+    rng = np.random.default_rng(21)
+    q = rng.uniform(-1.3, 1.3, (6000, 3)) * scale * 0.5 + s
+    q = np.concatenate([q, np.stack([x, y, z], 1)[:200], rng.uniform(-40.0, 40.0, (500, 3)) * scale + s])
+    for cs in (True, False):
+        rphi, rcp, _ = oracle.SignedDistance(x, y, z, conn, 3, True, cs).compute(q, True, False, nthreads=0)
+        sd = SignedDistance(x, y, z, conn, 3, True, cs)
+        phi, cp, _ = sd.computeDistances(q, True, False)
+        assert np.array_equal(rphi, phi), (scale, shift, cs, int((rphi != phi).sum()))
+        assert np.array_equal(rcp, cp), (scale, shift, cs)
