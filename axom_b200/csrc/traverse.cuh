@@ -617,6 +617,21 @@ __device__ __forceinline__ bool query_sort_point(const RayQuery<T, D>& q, const 
 {
   return q.sort_point(bmin, bmax, c);
 }
+// the top D bits of a ray's key: its direction octant (rays entering at the same place but heading apart share nothing below
+// the first few levels); other queries: none
+template <typename T, int D, class Query>
+__device__ __forceinline__ uint32_t query_sort_prefix(const Query&, uint32_t code)
+{
+  return code;
+}
+template <typename T, int D>
+__device__ __forceinline__ uint32_t query_sort_prefix(const RayQuery<T, D>& q, uint32_t code)
+{
+  uint32_t oct = 0;
+#pragma unroll
+  for(int k = 0; k < D; ++k) oct |= (q.dir[k] < (T)0 ? 1u : 0u) << k;
+  return (oct << (32 - D)) | (code >> D);
+}
 
 // Morton keys of the queries' reference points over the BVH bounds (centroid of a box, entry point of a ray):
 // (code << 32) | index, for radix_sort.cuh.  Only the processing ORDER depends on it.  The digit histograms are
@@ -663,6 +678,7 @@ __global__ void __launch_bounds__(256) find_query_keys_kernel(Desc<Query::NCOMP>
           code = spread_bits_2d(qd[0]) | (spread_bits_2d(qd[1]) << 1);
         else
           code = spread_bits_3d(qd[0]) | (spread_bits_3d(qd[1]) << 1) | (spread_bits_3d(qd[D - 1]) << 2);
+        code = query_sort_prefix<T, D>(q, code);
       }
       keys[i] = ((unsigned long long)code << 32) | (unsigned long long)(uint32_t)i;
     }
