@@ -62,6 +62,7 @@ SYMBOLS = [
     ("axb_bvh_set_find_strategy", C.c_int, [_P, C.c_int]),
     ("axb_bvh_num_leaves", C.c_int, [_P, C.POINTER(C.c_int32)]),
     ("axb_bvh_copy_arrays", C.c_int, [_P, _P, _P, _P, _P]),
+    ("axb_bvh_write_vtk_file", C.c_int, [_P, C.c_char_p]),
     ("axb_bvh_set_profiling", C.c_int, [_P, C.c_int]),
     ("axb_bvh_get_phase_ms", C.c_int, [_P, C.c_char_p, _PD]),
     ("axb_bvh_launch_count", C.c_int, [_P, C.POINTER(C.c_int64)]),

@@ -9,6 +9,7 @@ spin/tests/spin_bvh.cpp.  Inputs may be
 Everything is executed by libaxb200.so; nothing is computed in Python.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -134,6 +135,10 @@ class BVH:
 
     def synchronize(self):
         check(self._L.axb_bvh_synchronize(self._h))
+
+    def writeVtkFile(self, fileName):
+        """writeVtkFile(fileName) (spin/BVH.hpp:405): the reference's ASCII VTK dump of the tree, byte for byte"""
+        check(self._L.axb_bvh_write_vtk_file(self._h, os.fsencode(fileName)))
 
     def setProfiling(self, enabled):
         check(self._L.axb_bvh_set_profiling(self._h, int(bool(enabled))))

@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <map>
+#include <sstream>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -982,6 +984,108 @@ int axb_bvh_copy_arrays(axb_bvh* h, uint32_t* mcodes, int32_t* leaf_nodes, void*
                                    ctx.stream));
   }
   return ctx.sync();
+}
+
+}  // extern "C"
+
+// writeVtkFile (spin/BVH.hpp:405, policy/LinearBVH.hpp:404-458, internal/linear_bvh/bvh_vtkio.hpp): a debugging aid, host
+// code over the reference-layout arrays.  Same traversal (root box, then both child boxes of every inner node, left
+// subtree first), same stream formatting, so the file is the reference's byte for byte.
+template <typename T>
+static void vtk_box(int D, const T* b, int32_t& numPoints, int32_t& numBins, std::ostringstream& nodes, std::ostringstream& cells)
+{
+  const T* lo = b;
+  const T* hi = b + D;
+  if(D == 2)
+  {
+    nodes << lo[0] << " " << lo[1] << " 0.0\n";
+    nodes << hi[0] << " " << lo[1] << " 0.0\n";
+    nodes << hi[0] << " " << hi[1] << " 0.0\n";
+    nodes << lo[0] << " " << hi[1] << " 0.0\n";
+  }
+  else
+  {
+    for(int k = 0; k < 2; ++k)
+    {
+      const T z = k == 0 ? lo[2] : hi[2];
+      nodes << lo[0] << " " << lo[1] << " " << z << std::endl;
+      nodes << hi[0] << " " << lo[1] << " " << z << std::endl;
+      nodes << hi[0] << " " << hi[1] << " " << z << std::endl;
+      nodes << lo[0] << " " << hi[1] << " " << z << std::endl;
+    }
+  }
+  const int32_t nn = D == 2 ? 4 : 8;
+  cells << nn << " ";
+  for(int32_t i = 0; i < nn; ++i) cells << (numPoints + i) << " ";
+  cells << "\n";
+  numBins += 1;
+  numPoints += nn;
+}
+
+template <typename T>
+static int write_vtk_impl(axb_bvh* h, const char* file_name)
+{
+  const int D = h->ndims, inner = h->n - 1;
+  std::vector<T> boxes((size_t)2 * inner * 2 * D);
+  std::vector<int32_t> children((size_t)2 * inner);
+  AXB_TRY(axb_bvh_copy_arrays(h, nullptr, nullptr, boxes.data(), children.data()));
+  double lo[3], hi[3];
+  AXB_TRY(axb_bvh_get_bounds(h, lo, hi));
+  T root[6];
+  for(int d = 0; d < D; ++d)
+  {
+    root[d] = (T)lo[d];
+    root[D + d] = (T)hi[d];
+  }
+  std::ofstream ofs(file_name);
+  if(!ofs) return fail(AXB_ERR_BAD_ARG, std::string("cannot open ") + file_name);
+  std::ostringstream nodes, cells, levels;
+  ofs << "# vtk DataFile Version 3.0\n";
+  ofs << " BVHTree \n";
+  ofs << "ASCII\n";
+  ofs << "DATASET UNSTRUCTURED_GRID\n";
+  int32_t numPoints = 0, numBins = 0;
+  vtk_box<T>(D, root, numPoints, numBins, nodes, cells);
+  levels << "0\n";
+  // write_recursive (:155-207) with an explicit stack: (first entry of the node's pair in the flat arrays, level)
+  std::vector<std::pair<int32_t, int32_t>> todo;
+  todo.emplace_back(0, 1);
+  while(!todo.empty())
+  {
+    const int32_t cur = todo.back().first, level = todo.back().second;
+    todo.pop_back();
+    vtk_box<T>(D, boxes.data() + (size_t)cur * 2 * D, numPoints, numBins, nodes, cells);
+    levels << level << std::endl;
+    vtk_box<T>(D, boxes.data() + (size_t)(cur + 1) * 2 * D, numPoints, numBins, nodes, cells);
+    levels << level << std::endl;
+    const int32_t l = children[cur], r = children[cur + 1];
+    if(r > -1) todo.emplace_back(r, level + 1);  // popped after the whole left subtree
+    if(l > -1) todo.emplace_back(l, level + 1);
+  }
+  ofs << "POINTS " << numPoints << " double\n";
+  ofs << nodes.str() << std::endl;
+  const int32_t nn = D == 2 ? 4 : 8;
+  ofs << "CELLS " << numBins << " " << numBins * (nn + 1) << std::endl;
+  ofs << cells.str() << std::endl;
+  ofs << "CELL_TYPES " << numBins << std::endl;
+  const int32_t cellType = D == 2 ? 9 : 12;
+  for(int32_t i = 0; i < numBins; ++i) ofs << cellType << std::endl;
+  ofs << "CELL_DATA " << numBins << std::endl;
+  ofs << "SCALARS level int\n";
+  ofs << "LOOKUP_TABLE default\n";
+  ofs << levels.str() << std::endl;
+  ofs << std::endl;
+  ofs.close();
+  return AXB_OK;
+}
+
+extern "C" {
+
+int axb_bvh_write_vtk_file(axb_bvh* h, const char* file_name)
+{
+  if(!valid_bvh(h) || !file_name) return fail(AXB_ERR_BAD_ARG, "null argument");
+  if(!h->built) return fail(AXB_ERR_NOT_BUILT, "BVH not initialized");
+  return h->fp_bytes == 4 ? write_vtk_impl<float>(h, file_name) : write_vtk_impl<double>(h, file_name);
 }
 
 int axb_bvh_set_find_strategy(axb_bvh* h, int strategy)

@@ -158,6 +158,10 @@ int axb_bvh_set_find_strategy(axb_bvh* bvh, int strategy);
 int axb_bvh_num_leaves(const axb_bvh* bvh, int32_t* n);
 int axb_bvh_copy_arrays(axb_bvh* bvh, uint32_t* mcodes, int32_t* leaf_nodes, void* inner_nodes /* FloatType */, int32_t* inner_children);
 
+/* writeVtkFile(fileName) :405 -- the tree's boxes as an ASCII VTK unstructured grid with a "level" cell field; the file is
+ * the reference's byte for byte (policy/LinearBVH.hpp:404-458).  A debugging aid: host code, O(N) text. */
+int axb_bvh_write_vtk_file(axb_bvh* bvh, const char* file_name);
+
 /* Device time (ms, CUDA events on the handle's stream) of the phases of the calls made since
  * profiling was (re-)enabled: the MEAN over those calls.  Enabling profiling resets the record.
  * names: "build.total" "build.bounds" "build.morton" "build.sort" "build.tree" "build.refit"

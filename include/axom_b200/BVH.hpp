@@ -385,6 +385,9 @@ public:
     return b;
   }
 
+  // writeVtkFile(fileName) (spin/BVH.hpp:405): the tree's boxes as an ASCII VTK file, for debugging
+  void writeVtkFile(const std::string& fileName) const { check(axb_bvh_write_vtk_file(m_bvh, fileName.c_str())); }
+
   TraverserType getTraverser() const
   {
     axb_traverser t;

@@ -140,6 +140,13 @@ class Bvh:
                                        ("mcodes", "leafs", "lchild", "rchild", "parents", "inner_nodes", "inner_children", "bounds")])
         return out
 
+    def write_vtk(self, file_name):
+        """BVH::writeVtkFile of the unmodified reference (kind "reference" / "reference_f32" only)"""
+        f = self.L.fn("bvh_write_vtk")
+        f.argtypes = [C.c_void_p, C.c_char_p]
+        f.restype = None
+        f(self.h, os.fsencode(file_name))
+
     def _collect(self, total, cand_p):
         cand = np.ctypeslib.as_array(C.cast(cand_p, C.POINTER(C.c_int32)), shape=(max(int(total), 1),))[:int(total)].copy()
         self.L.fn("free")(cand_p)

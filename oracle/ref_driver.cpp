@@ -258,6 +258,22 @@ void axref_bvh_get(const AxrefBvh* h, uint32_t* mcodes, int32_t* leafs, int32_t*
     get_arrays(*(RefBvh<double, 3>*)h->impl, mcodes, leafs, lchild, rchild, parents, inner_nodes, inner_children, bounds);
 }
 
+// BVH::writeVtkFile (spin/BVH.hpp:405) of the unmodified reference
+void axref_bvh_write_vtk(const AxrefBvh* h, const char* file_name)
+{
+  if(h->ndims == 2)
+    ((RefBvh<double, 2>*)h->impl)->bvh.writeVtkFile(file_name);
+  else
+    ((RefBvh<double, 3>*)h->impl)->bvh.writeVtkFile(file_name);
+}
+void axreff_bvh_write_vtk(const AxrefBvh* h, const char* file_name)
+{
+  if(h->ndims == 2)
+    ((RefBvh<float, 2>*)h->impl)->bvh.writeVtkFile(file_name);
+  else
+    ((RefBvh<float, 3>*)h->impl)->bvh.writeVtkFile(file_name);
+}
+
 void axref_free(void* p) { free(p); }
 
 int64_t axref_bvh_find_points(const AxrefBvh* h, const double* pts_aos, int q, int32_t* offsets, int32_t* counts, int32_t** cand)

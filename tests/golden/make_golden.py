@@ -109,8 +109,17 @@ def mc_cases(name):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+def vtk_case():
+    """BVH::writeVtkFile of the reference for the small trees of tests/kats.vtk_boxes -> bvh_vtk_{3d,2d}.vtk"""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import kats
+    for nd in (3, 2):
+        O.Bvh(kats.vtk_boxes(nd), ndims=nd, kind="reference").write_vtk(os.path.join(HERE, "bvh_vtk_%dd.vtk" % nd))
+
+
 if __name__ == "__main__":
     assert O.have_reference(), "build the reference first: python oracle/build_ref.py"
+    vtk_case()
     bvh_case("bvh3d_n600", 600, 3, 41)
     bvh_case("bvh2d_n400", 400, 2, 43)
     sd_case("sd_icosphere5", 5, 9)

@@ -257,3 +257,14 @@ def sliver_triangle_cloud(n, seed=5):
     q = np.where((pk == 4)[:, None], rng.uniform(-3, 3, (n, 3)), q)                         # anywhere
     q = np.where((pk == 5)[:, None], A + 1e-13 * rng.uniform(-1, 1, (n, 3)), q)             # within 1e-13 of A
     return np.ascontiguousarray(q), np.ascontiguousarray(tri.reshape(n, 9))
+
+
+def vtk_boxes(ndims):
+    """a small tree for the writeVtkFile golden: 7 boxes with awkward decimals (exercises the stream formatting)"""
+    rng = np.random.default_rng(17 + ndims)
+    lo = rng.uniform(-3.0, 3.0, (7, ndims))
+    ext = rng.uniform(0.01, 1.5, (7, ndims))
+    b = np.concatenate([lo, lo + ext], axis=1)
+    b[2] = np.concatenate([np.full(ndims, 1.0 / 3.0), np.full(ndims, 2.0 / 3.0)])
+    b[5] = np.concatenate([np.full(ndims, -1.0e-7), np.full(ndims, 1234567.891)])
+    return b

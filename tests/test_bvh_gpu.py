@@ -303,3 +303,28 @@ def test_float_bvh_bit_exact(oracle, have_ref, ndims, n):
             assert _same(ref.find_boxes(qb), gpu.findBoundingBoxes(qb))
             assert _same(ref.find_rays(o, d * np.float32(1.7), True), gpu.findRays(o, d * np.float32(1.7), normalized=False))
             assert _same(ref.find_rays(o, d, False), gpu.findRays(o, d, normalized=True))
+
+
+@pytest.mark.parametrize("nd", [3, 2])
+def test_write_vtk_file_matches_the_reference_byte_for_byte(oracle, have_ref, tmp_path, nd):
+    """BVH::writeVtkFile (spin/BVH.hpp:405, policy/LinearBVH.hpp:404-458): same boxes, same order, same stream formatting as the
+    unmodified reference (golden: tests/golden/bvh_vtk_*.vtk, made by tests/golden/make_golden.py; compared with the
+    reference itself when it is present), double and float trees."""
+    import os
+    import kats
+    from axom_b200 import BVH
+    boxes = kats.vtk_boxes(nd)
+    b = BVH(nd, device=0)
+    assert b.initialize(boxes) == 0
+    f = str(tmp_path / "gpu.vtk")
+    b.writeVtkFile(f)
+    want = open(os.path.join(os.path.dirname(__file__), "golden", "bvh_vtk_%dd.vtk" % nd)).read()
+    assert open(f).read() == want
+    if have_ref:
+        for kind, dt in (("reference", np.float64), ("reference_f32", np.float32)):
+            r = str(tmp_path / (kind + ".vtk"))
+            oracle.Bvh(boxes, ndims=nd, kind=kind).write_vtk(r)
+            g = BVH(nd, device=0, dtype=dt)
+            assert g.initialize(boxes.astype(dt)) == 0
+            g.writeVtkFile(f)
+            assert open(f).read() == open(r).read(), kind

@@ -221,3 +221,16 @@ def test_find_tri_mesh_intersections_port_equals_real_reference(oracle, have_ref
     t1, t2 = g["t1"].astype(np.float64), g["t2"].astype(np.float64)
     assert np.array_equal(oracle.tri_tri_intersect(t1, t2, False, 1e-8), g["hit_open"])
     assert np.array_equal(oracle.tri_tri_intersect(t1, t2, True, 1e-8), g["hit_closed"])
+
+
+def test_reference_vtk_dump_matches_the_committed_golden(oracle, have_ref, tmp_path):
+    """BVH::writeVtkFile (spin/BVH.hpp:405): the unmodified reference's file for the two small trees of tests/kats.vtk_boxes is
+    the committed golden (tests/golden/bvh_vtk_{3d,2d}.vtk), which the GPU library must reproduce byte for byte."""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libaxom_ref.so not present (needs /root/reference to build)")
+    import kats
+    for nd in (3, 2):
+        f = str(tmp_path / ("ref_%dd.vtk" % nd))
+        oracle.Bvh(kats.vtk_boxes(nd), ndims=nd, kind="reference").write_vtk(f)
+        want = open(os.path.join(os.path.dirname(__file__), "golden", "bvh_vtk_%dd.vtk" % nd)).read()
+        assert open(f).read() == want
