@@ -631,7 +631,9 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
     {
       int bps = 0;
       AXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, find_walk_kernel<T, D, Query, Filter>, 128, 0));
-      h->walk_blocks_per_sm[kind] = std::max(1, std::min(bps, 8));
+      int cap = 16;  // as many resident blocks as the registers allow (10-11 for the point / box walks): C1 and C3 +6 % over 8
+      if(const char* e = getenv("AXB_FIND_BLOCKS")) cap = std::max(1, atoi(e));
+      h->walk_blocks_per_sm[kind] = std::max(1, std::min(bps, cap));
     }
     int sms = kNumSMsB200;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx.device);
