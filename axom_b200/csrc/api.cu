@@ -371,11 +371,13 @@ struct axb_bvh
 namespace
 {
 // LSD radix sort of the 64-bit keys on bits [32, 64): 4 onesweep passes.
+// first_pass = 1 skips the lowest digit: the order of QUERIES only decides who is processed next to whom, and 24 bits of
+// Morton code (8 per dimension) are as coherent as 32 -- queries that share them stay in index order (the sort is stable).
 int sort_keys_generic(Ctx& ctx, unsigned long long* src, unsigned long long* dst, int n, uint32_t* ghist /* 4*256, filled */,
-                      uint32_t* tile_counters, uint32_t* lookback, unsigned long long** sorted)
+                      uint32_t* tile_counters, uint32_t* lookback, unsigned long long** sorted, int first_pass = 0)
 {
   const int tiles = rsort::num_tiles(n);
-  for(int p = 0; p < rsort::MAX_PASSES; ++p)
+  for(int p = first_pass; p < rsort::MAX_PASSES; ++p)
   {
     AXB_LAUNCH(ctx, rsort::onesweep_kernel, tiles, rsort::BLOCK, src, dst, (long long)n, 32 + p * rsort::RADIX_BITS,
                ghist + p * rsort::RADIX, lookback + (size_t)p * tiles * rsort::RADIX, tile_counters + p);
@@ -620,7 +622,7 @@ int find_impl(axb_bvh* h, int kind, const axb_array_desc* prims, int flags, int3
                  h->state.as<BuildState<T, D>>(), h->f_keys_a.as<unsigned long long>(), ghist);
       unsigned long long* sorted = nullptr;
       AXB_TRY(sort_keys_generic(ctx, h->f_keys_a.as<unsigned long long>(), h->f_keys_b.as<unsigned long long>(), nq, ghist, tile_counters,
-                                lookback, &sorted));
+                                lookback, &sorted, 1));
       AXB_LAUNCH(ctx, keys_to_perm_kernel, blocks_for(nq, 256), 256, sorted, nq, h->f_perm.as<int32_t>());
       perm = h->f_perm.as<int32_t>();
     }
@@ -1550,7 +1552,7 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
                  B.qkeys_a.as<unsigned long long>(), ghist);
       unsigned long long* sorted = nullptr;
       AXB_TRY(sort_keys_generic(ctx, B.qkeys_a.as<unsigned long long>(), B.qkeys_b.as<unsigned long long>(), npts, ghist,
-                                tile_counters, lookback, &sorted));
+                                tile_counters, lookback, &sorted, 1));
       AXB_LAUNCH(ctx, keys_to_perm_kernel, blocks_for(npts, 256), 256, sorted, npts, B.qperm.as<int32_t>());
       perm = B.qperm.as<int32_t>();
     }
@@ -2384,7 +2386,7 @@ static int dcp_compute(axb_dcp* h, int rank, const double* query_coords, int32_t
                  h->bvh->state.as<BuildState<double, 2>>(), h->keys_a.as<unsigned long long>(), ghist);
     unsigned long long* sorted = nullptr;
     AXB_TRY(sort_keys_generic(ctx, h->keys_a.as<unsigned long long>(), h->keys_b.as<unsigned long long>(), nq, ghist, tile_counters, lookback,
-                              &sorted));
+                              &sorted, 1));
     AXB_LAUNCH(ctx, keys_to_perm_kernel, blocks_for(nq, 256), 256, sorted, nq, h->perm.as<int32_t>());
     perm = h->perm.as<int32_t>();
   }
