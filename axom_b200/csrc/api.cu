@@ -1148,11 +1148,11 @@ struct axb_sd
   // that the upload of chunk i+1 and the download of chunk i-1 overlap the kernel of chunk i
   struct QBufs
   {
-    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor, cand, cand_n, seed, solo, solo_scratch, hint;
+    DevBuf q_stage, out_phi, out_cp, out_n, qkeys_a, qkeys_b, qscratch, qperm, qbounds, cursor, cand, cand_n, seed, solo, solo_scratch, hint, ext;
     void release(cudaStream_t st)
     {
       for(DevBuf* b : {&q_stage, &out_phi, &out_cp, &out_n, &qkeys_a, &qkeys_b, &qscratch, &qperm, &qbounds, &cursor, &cand, &cand_n, &seed, &solo,
-                       &solo_scratch, &hint})
+                       &solo_scratch, &hint, &ext})
         b->release(st);
     }
   } qb[2];
@@ -1163,6 +1163,7 @@ struct axb_sd
   int kernel = 2;              // mode 1 kernel: 2 = sd_two_phase_kernel (default), 1 = sd_fast_kernel (AXB_SD_KERNEL=fast)
   int64_t last_leaf_tests = 0, last_inner_visits = 0;
   std::map<std::string, double> setmesh_ms;  // device time of the phases of setMesh ("setmesh.*", "build.*")
+  double max_diam = 0.0;                     // largest triangle diameter of the mesh (slack of the partitioned-surface bound)
   Ctx& ctx() { return bvh->ctx; }
 };
 
@@ -1298,6 +1299,21 @@ int axb_sd_create(axb_sd** out, int device, const double* x, const double* y, co
       AXB_LAUNCH(ctx, gather_soup_kernel<4>, blocks_for(nl, 256), 256, s->x.as<double>(), s->y.as<double>(), s->z.as<double>(),
                  s->conn.as<int32_t>(), s->bvh->leaf_nodes.as<int32_t>(), nl, ncells, s->soup.as<double>());
     s->cell_boxes.release(ctx.stream);
+    {
+      // largest triangle diameter (reuses the mesh-bounds scratch word 0 as an ordered-uint maximum)
+      DevBuf md;
+      AXB_TRY(md.reserve(sizeof(unsigned long long), ctx.stream));
+      AXB_CUDA_TRY(cudaMemsetAsync(md.p, 0, sizeof(unsigned long long), ctx.stream));
+      if(s->nv == 3)
+        AXB_LAUNCH(ctx, sd_max_diam_kernel<3>, blocks_for(nl, 256), 256, s->soup.as<double>(), nl, md.as<unsigned long long>());
+      else
+        AXB_LAUNCH(ctx, sd_max_diam_kernel<4>, blocks_for(nl, 256), 256, s->soup.as<double>(), nl, md.as<unsigned long long>());
+      unsigned long long hmd = 0;
+      AXB_CUDA_TRY(cudaMemcpyAsync(&hmd, md.p, sizeof(hmd), cudaMemcpyDeviceToHost, ctx.stream));
+      AXB_TRY(ctx.sync());
+      md.release(ctx.stream);
+      s->max_diam = hmd ? sqrt(ordered_to_f64(hmd)) * (1.0 + 1e-12) : 0.0;
+    }
     ctx.phase_end(gs);
     const int ob = ctx.phase_begin("setmesh.obb_build");
     // traversal records of the fast query mode (sd_fast.cuh): child AABBs + oriented bounds + ids,
@@ -1507,8 +1523,15 @@ static bool solo_on_env() { return getenv("AXB_SD_NO_SOLO") == nullptr; }
 
 // One contiguous range of queries, enqueued on ctx.stream with the scratch set B: stage (host inputs), Morton
 // order, the query kernel, and -- for host outputs -- the copies back.  Does not synchronise.
+// What a partitioned-surface query exchanges between the sample pass and the search proper (sd_query_range calls it with
+// the per-query distances to this part's sample points; it returns them MIN-reduced over the ranks, and the slack)
+struct SdBoundExchange
+{
+  axb_comm* comm;
+  double slack;  // largest triangle diameter over ALL parts
+};
 static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpts, int32_t npts, double* phi, double* cps, double* nrms,
-                          int out_memspace, unsigned long long* d_work)
+                          int out_memspace, unsigned long long* d_work, SdBoundExchange* ex = nullptr)
 {
   Ctx& ctx = s->ctx();
   Desc<3> q;
@@ -1631,6 +1654,22 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
         AXB_TRY(B.hint.reserve(sizeof(double) * 3 * (size_t)hint_n, ctx.stream));
         hint_tab = B.hint.as<double>();
       }
+      // partitioned surface: after the sample pass the ranks agree on a bound per query (MIN over the ranks of the distance
+      // to each part's sample point); a part far from the query then prunes it at the root
+      const double* ext_bound = nullptr;
+      double ext_slack = 0.0;
+      auto exchange_bounds = [&]() -> int {
+        if(!ex || !hint_tab) return AXB_OK;
+        AXB_TRY(B.ext.reserve(sizeof(double) * (size_t)npts, ctx.stream));
+        AXB_LAUNCH(ctx, sd_ext_bound_kernel, blocks_for(npts, 256), 256, q, perm, npts, (const double*)hint_tab, hint_shift, B.ext.as<double>());
+        ScopedPhase pe(ctx, "query.bound_exchange");
+        AXB_NCCL_TRY(ex->comm->api, ex->comm->api->AllReduce(B.ext.p, B.ext.p, (size_t)npts, ncclDouble, ncclMin, ex->comm->comm, ctx.stream));
+        ex->comm->bytes += 8ll * npts;
+        ex->comm->calls += 1;
+        ext_bound = B.ext.as<double>();
+        ext_slack = ex->slack;
+        return AXB_OK;
+      };
       unsigned heavy_visits = solo_on_env() ? 384u : 0xffffffffu;
       if(const char* e = getenv("AXB_SD_HEAVY")) heavy_visits = (unsigned)std::max(1, atoi(e));
       // heavy queries (list overflow, sign too close to call) are listed by the resolve kernel and finished one WARP each
@@ -1655,11 +1694,12 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
           {
             AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, hint_grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, hint_n, perm,
                             (int32_t*)nullptr, (uint8_t*)nullptr, (double*)nullptr, d_work, B.cursor.as<unsigned int>() + 1, 32u,
-                            s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits);
+                            s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits, (const double*)nullptr, 0.0);
+            AXB_TRY(exchange_bounds());
           }
           AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, npts, perm,
                           B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
-                          s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits);
+                          s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits, ext_bound, ext_slack);
         }
         ScopedPhase p2(ctx, "query.resolve");
         AXB_LAUNCH(ctx, sd_resolve_kernel<3>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
@@ -1677,11 +1717,12 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
           {
             AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, hint_grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, hint_n, perm,
                             (int32_t*)nullptr, (uint8_t*)nullptr, (double*)nullptr, d_work, B.cursor.as<unsigned int>() + 1, 32u,
-                            s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits);
+                            s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits, (const double*)nullptr, 0.0);
+            AXB_TRY(exchange_bounds());
           }
           AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, npts, perm,
                           B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
-                          s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits);
+                          s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits, ext_bound, ext_slack);
         }
         ScopedPhase p2(ctx, "query.resolve");
         AXB_LAUNCH(ctx, sd_resolve_kernel<4>, grid2, kSd2Threads, s->sdnodes.as<SdNode>(), s->sdcens.as<SdCen>(), s->sdup.as<SdUp>(),
@@ -2589,7 +2630,20 @@ int axb_sd_compute_distances_minreduce(axb_sd* s, axb_comm* c, const axb_array_d
     AXB_TRY(B.out_phi.reserve(sizeof(double) * (size_t)npts, ctx.stream));
     d_out = B.out_phi.as<double>();
   }
-  AXB_TRY(sd_query_range(s, B, qpts, npts, d_out, nullptr, nullptr, AXB_MEM_DEVICE, nullptr));
+  // the slack of the exchanged bound: the largest triangle diameter over ALL parts (8 bytes, MAX)
+  SdBoundExchange ex {c, s->max_diam};
+  const bool bounded = c->nranks > 1 && getenv("AXB_SD_NO_BOUND_EXCHANGE") == nullptr;
+  if(bounded)
+  {
+    AXB_TRY(B.ext.reserve(sizeof(double) * (size_t)std::max(npts, 1), ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(B.ext.p, &s->max_diam, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    AXB_NCCL_TRY(c->api, c->api->AllReduce(B.ext.p, B.ext.p, 1, ncclDouble, ncclMax, c->comm, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(&ex.slack, B.ext.p, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    AXB_TRY(ctx.sync());
+    c->bytes += 8;
+    c->calls += 1;
+  }
+  AXB_TRY(sd_query_range(s, B, qpts, npts, d_out, nullptr, nullptr, AXB_MEM_DEVICE, nullptr, bounded ? &ex : nullptr));
   {
     ScopedPhase ph(ctx, "query.minreduce");
     AXB_NCCL_TRY(c->api, c->api->AllReduce(d_out, d_out, (size_t)npts, ncclDouble, ncclMin, c->comm, ctx.stream));

@@ -366,6 +366,47 @@ __device__ __forceinline__ double shfl_f64(double v, int src)
   return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
 }
 
+// distance (not squared) from every query to the closest point the sample pass found for its group of Morton neighbours
+// (DBL_MAX where it found nothing): this rank's contribution to the bound the ranks of a partitioned surface exchange
+__global__ void __launch_bounds__(256) sd_ext_bound_kernel(Desc<3> qpts, const int32_t* __restrict__ perm, int npts,
+                                                            const double* __restrict__ hint_tab, int hint_shift, double* __restrict__ ext)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= npts) return;
+  const int qi = perm ? perm[t] : t;
+  const double* hp = hint_tab + 3 * (size_t)(t >> hint_shift);
+  const double tx = hp[0], ty = hp[1], tz = hp[2];
+  double e = DBL_MAX;
+  if(tx == tx)
+  {
+    const double hx = tx - ld_comp<double>(qpts, 0, qi), hy = ty - ld_comp<double>(qpts, 1, qi), hz = tz - ld_comp<double>(qpts, 2, qi);
+    e = sqrt(hx * hx + hy * hy + hz * hz) * (1.0 + 1e-15);
+  }
+  ext[qi] = e;
+}
+
+// the largest triangle diameter of the mesh (quads: all four vertices), as an ordered-encoded running maximum
+template <int NV>
+__global__ void __launch_bounds__(256) sd_max_diam_kernel(const double* __restrict__ soup, int nleaves, unsigned long long* __restrict__ out)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if(p < nleaves)
+  {
+    V3 v[NV];
+    load_leaf<NV>(soup, p, v);
+    const int nv = (NV == 4 && !has_fourth(v[NV - 1])) ? 3 : NV;
+    for(int a = 0; a < nv; ++a)
+      for(int b = a + 1; b < nv; ++b)
+      {
+        const V3 d = v3sub(v[a], v[b]);
+        m = fmax(m, v3dot(d, d));
+      }
+  }
+  m = warp_max(m);
+  if(lane_id() == 0 && m > 0.0) atomicMax(out, f64_to_ordered(m));
+}
+
 //------------------------------------------------------------------------------------------
 // PHASE 1 kernel.  Persistent warps pull Morton-ordered queries from a device cursor, one query per lane, a lane that
 // finishes is refilled at once.  A warp iteration is either
@@ -390,7 +431,7 @@ __global__ void __launch_bounds__(kSd2Threads, AXB_SD2_MIN_BLOCKS)
 sd_min_kernel(const SdNode64* __restrict__ nodes, const double* __restrict__ soup, Desc<3> qpts, int npts, const int32_t* __restrict__ perm,
               int32_t* __restrict__ cand, uint8_t* __restrict__ cand_n, double* __restrict__ seed, unsigned long long* __restrict__ work,
               unsigned int* __restrict__ cursor, unsigned chunk, double window, const double* __restrict__ hint_tab, int hint_shift,
-              double* __restrict__ hint_out, int nfull, unsigned heavy_visits)
+              double* __restrict__ hint_out, int nfull, unsigned heavy_visits, const double* __restrict__ ext_bound, double ext_slack)
 {
   // Two uses.  hint_out == nullptr: the search proper over the npts query slots.  hint_out != nullptr: the SAMPLE pass
   // that runs first -- work item k is the query of Morton rank k * 2^hint_shift + 2^(hint_shift-1) (of nfull), and all
@@ -433,6 +474,7 @@ sd_min_kernel(const SdNode64* __restrict__ nodes, const double* __restrict__ sou
   int pending = 0;         // the lane's leaves waiting in the pool
   bool have_hint = false;
   bool hinted = false;  // the lane's query started with a first bound
+  double ext_sq = DBL_MAX;  // the never-retracted bound from outside (see the refill)
   unsigned nleaf = 0, ninner = 0;
   unsigned visits0 = 0;  // ninner when the lane's query started
 #ifdef AXB_SD_DEBUG_MISS
@@ -457,8 +499,8 @@ sd_min_kernel(const SdNode64* __restrict__ nodes, const double* __restrict__ sou
       // Every leaf was rejected, so the miss is total and detectable: search again with no first bound (the bounds are
       // lower bounds of the TRUE distance, hence of the reference's value too).  About 3 queries per million on C5.
       hinted = false;
-      thr = DBL_MAX;
-      thr_f = inf_f;
+      thr = ext_sq < 1e300 ? prune_threshold_w(ext_sq, window) : DBL_MAX;
+      thr_f = thr < 3.0e38 ? __double2float_ru(thr) : inf_f;
       cur = 0;
       visits0 = ninner;
     }
@@ -599,8 +641,25 @@ sd_min_kernel(const SdNode64* __restrict__ nodes, const double* __restrict__ sou
 #endif
             }
           }
-          hinted = hsq < 1e300;
-          if(hinted)
+          // A bound from OUTSIDE (partitioned surface: the distance from q to a point of some OTHER part, MIN over the
+          // ranks): the value the reference arithmetic yields for that point's own triangle is at most this distance plus
+          // the triangle's diameter (closest_point returns a point OF the triangle, even where its fuzzy region tests pick
+          // a poor one), so with ext_slack = the largest triangle diameter of the whole surface nothing that can be the
+          // global minimum is cut.  Unlike the lane's own first bounds it is never retracted: a part that has nothing
+          // within it reports nothing for this query, and another part owns the answer.
+          ext_sq = DBL_MAX;
+          if(ext_bound)
+          {
+            const double e = ext_bound[qi];
+            if(e < 1e150)
+            {
+              const double dd = e + ext_slack;
+              ext_sq = dd * dd * (1.0 + 1e-12);
+            }
+          }
+          hinted = hsq < ext_sq;  // a bound of the lane's own that is tighter than the safe one: retried on a total miss
+          hsq = fmin(hsq, ext_sq);
+          if(hsq < 1e300)
           {
             thr = prune_threshold_w(hsq, window);
             thr_f = thr < 3.0e38 ? __double2float_ru(thr) : inf_f;

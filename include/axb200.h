@@ -301,8 +301,11 @@ int axb_comm_allreduce_f64(axb_comm* comm, double* device_buf, int64_t n, int op
 
 /* BASELINE config C5 -- the surface is PARTITIONED over the ranks (each rank's axb_sd holds one part, created with
  * compute_sign = 0), every rank passes the SAME query points, and every rank receives the distance to the whole surface:
- * the query kernel writes its partial (unsigned) distances into the buffer an ncclAllReduce(MIN, double) then reduces in
- * place on the handle's stream.  Phase timers: "query.kernel", "query.minreduce". */
+ * the query kernels write the partial (unsigned) distances into the buffer an ncclAllReduce(MIN, double) then reduces in
+ * place on the handle's stream.  Between the sample pass and the search proper the ranks also MIN-reduce a per-query bound
+ * (the distance to each part's sample point, + the largest triangle diameter), so a part far from a query prunes it at
+ * once; the result is unchanged.  Every rank must pass the same points.  Phase timers: "query.kernel",
+ * "query.bound_exchange", "query.minreduce". */
 int axb_sd_compute_distances_minreduce(axb_sd* sd, axb_comm* comm, const axb_array_desc* query_pts, int32_t npts, double* dist,
                                        int out_memspace);
 
