@@ -18,9 +18,13 @@
 //            leaves is decided at their lowest common ancestor by the centroid comparison, so a walk from that
 //            ancestor that enters only subtrees containing remembered positions reproduces it -- and feeds
 //            them to the unchanged state machine (check_leaf_lazy), then signs and stores (sd_finish).
-// A query whose list overflows (kCandCap leaves within 1e-6 of each other: the centre of a sphere) is handed, by
-// its own lane, to sd_ordered_query: the reference-order walk of sd_fast.cuh for one query, seeded with the bound
-// phase 1 found.
+// A query whose list overflows (kCandCap leaves within 1e-6 of each other: the centre of a sphere), or that phase 1 gives
+// up after heavy_visits node visits, is only LISTED by phase 2 and finished by one whole warp of sd_solo_kernel (exact
+// minimum over a shared stack, then the in-window leaves by an order-preserving level expansion, then the state machine).
+// Launches of one call: sd_min_kernel on a SAMPLE (one query in 32 of the Morton order: its closest point is the first
+// bound of its neighbours), [partitioned surface: the ranks MIN-reduce a per-query bound], sd_min_kernel proper,
+// sd_resolve_kernel, sd_solo_kernel.  Phase 1 reads the 64-byte records (SdNode64, sd_fast.cuh); the ordered walks read
+// the full ones in binary64.
 #pragma once
 #include "sd_fast.cuh"
 
