@@ -108,6 +108,7 @@ SYMBOLS = [
     ("axb_comm_library", C.c_char_p, []),
     ("axb_comm_allreduce_f64", C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     ("axb_sd_compute_distances_minreduce", C.c_int, [_P, _P, _DESC, C.c_int32, _P, C.c_int]),
+    ("axb_sd_update_min_distances", C.c_int, [_P, _DESC, C.c_int32, _P, C.c_int]),
     ("axb_dcp_compute_closest_points", C.c_int, [_P, _P, _P, C.c_int32, C.c_int, _P, _P, _P, _P, _P]),
     # quest::MarchingCubes
     ("axb_mc_create", C.c_int, [_PP, C.c_int, C.c_int]),

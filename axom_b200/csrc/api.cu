@@ -1528,7 +1528,8 @@ static bool solo_on_env() { return getenv("AXB_SD_NO_SOLO") == nullptr; }
 struct SdBoundExchange
 {
   axb_comm* comm;
-  double slack;  // largest triangle diameter over ALL parts
+  double slack;                   // largest triangle diameter over ALL parts
+  const double* given = nullptr;  // no exchange: the caller's own per-query bounds (distances, device memory)
 };
 static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpts, int32_t npts, double* phi, double* cps, double* nrms,
                           int out_memspace, unsigned long long* d_work, SdBoundExchange* ex = nullptr)
@@ -1659,7 +1660,14 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
       const double* ext_bound = nullptr;
       double ext_slack = 0.0;
       auto exchange_bounds = [&]() -> int {
-        if(!ex || !hint_tab) return AXB_OK;
+        if(!ex) return AXB_OK;
+        if(ex->given)
+        {
+          ext_bound = ex->given;
+          ext_slack = ex->slack;
+          return AXB_OK;
+        }
+        if(!hint_tab) return AXB_OK;
         AXB_TRY(B.ext.reserve(sizeof(double) * (size_t)npts, ctx.stream));
         AXB_LAUNCH(ctx, sd_ext_bound_kernel, blocks_for(npts, 256), 256, q, perm, npts, (const double*)hint_tab, hint_shift, B.ext.as<double>());
         ScopedPhase pe(ctx, "query.bound_exchange");
@@ -1697,6 +1705,8 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
                             s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits, (const double*)nullptr, 0.0);
             AXB_TRY(exchange_bounds());
           }
+          else if(ex && ex->given)
+            AXB_TRY(exchange_bounds());
           AXB_LAUNCH_SMEM(ctx, sd_min_kernel<3>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, npts, perm,
                           B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
                           s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits, ext_bound, ext_slack);
@@ -1720,6 +1730,8 @@ static int sd_query_range(axb_sd* s, axb_sd::QBufs& B, const axb_array_desc* qpt
                             s->prm.compute_sign ? kTieWindow : 0.0, (const double*)nullptr, hint_shift, hint_tab, npts, heavy_visits, (const double*)nullptr, 0.0);
             AXB_TRY(exchange_bounds());
           }
+          else if(ex && ex->given)
+            AXB_TRY(exchange_bounds());
           AXB_LAUNCH_SMEM(ctx, sd_min_kernel<4>, grid, kSd2Threads, kSd2SmemMin, s->sdnodes64.as<SdNode64>(), s->soup.as<double>(), q, npts, perm,
                           B.cand.as<int32_t>(), B.cand_n.as<uint8_t>(), B.seed.as<double>(), d_work, B.cursor.as<unsigned int>(), chunk,
                           s->prm.compute_sign ? kTieWindow : 0.0, (const double*)hint_tab, hint_shift, (double*)nullptr, npts, heavy_visits, ext_bound, ext_slack);
@@ -2653,6 +2665,52 @@ int axb_sd_compute_distances_minreduce(axb_sd* s, axb_comm* c, const axb_array_d
   if(out_memspace == AXB_MEM_HOST) AXB_CUDA_TRY(cudaMemcpyAsync(dist, d_out, sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
   ctx.phase_end(tot);
   if(out_memspace == AXB_MEM_HOST) AXB_TRY(ctx.sync());
+  return ctx.finish_call();
+}
+
+}  // extern "C"
+
+__global__ void __launch_bounds__(256) min_update_kernel(double* __restrict__ inout, const double* __restrict__ v, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) inout[i] = fmin(inout[i], v[i]);
+}
+
+extern "C" {
+
+// The same partitioned-surface query on ONE GPU: the parts are evaluated in turn and `dist` is in/out -- on entry the
+// distance to the parts evaluated so far (DBL_MAX: none), on exit min(entry, distance to this handle's part).  The entry
+// value bounds the search (a part farther than it cannot change the minimum: values computed by the same arithmetic are
+// compared, so no slack is needed), which prunes far parts at the root.
+int axb_sd_update_min_distances(axb_sd* s, const axb_array_desc* qpts, int32_t npts, double* dist, int memspace)
+{
+  if(!s) return fail(AXB_ERR_BAD_ARG, "null handle");
+  if(npts < 0) return fail(AXB_ERR_BAD_ARG, "negative point count");
+  if(npts > 0 && (!dist || !qpts)) return fail(AXB_ERR_BAD_ARG, "null query descriptor or distance array");
+  if(s->prm.compute_sign) return fail(AXB_ERR_BAD_ARG, "a running minimum over surface parts is defined for unsigned distances: create the handle with compute_sign = 0");
+  memspace = resolve_memspace(memspace, dist);
+  if(memspace != AXB_MEM_HOST && memspace != AXB_MEM_DEVICE) return fail(AXB_ERR_BAD_ARG, "unknown memspace");
+  if(!s->bvh->built) return fail(AXB_ERR_NOT_BUILT, "SignedDistance query before setMesh()");
+  Ctx& ctx = s->ctx();
+  AXB_TRY(ctx.bind());
+  ctx.begin_call();
+  if(npts == 0) return AXB_OK;
+  const int tot = ctx.phase_begin("query.total");
+  axb_sd::QBufs& B = s->qb[0];
+  AXB_TRY(B.out_phi.reserve(sizeof(double) * (size_t)npts, ctx.stream));
+  double* d_io = dist;
+  if(memspace == AXB_MEM_HOST)
+  {
+    AXB_TRY(B.ext.reserve(sizeof(double) * (size_t)npts, ctx.stream));
+    AXB_CUDA_TRY(cudaMemcpyAsync(B.ext.p, dist, sizeof(double) * (size_t)npts, cudaMemcpyHostToDevice, ctx.stream));
+    d_io = B.ext.as<double>();
+  }
+  SdBoundExchange ex {nullptr, 0.0, d_io};
+  AXB_TRY(sd_query_range(s, B, qpts, npts, B.out_phi.as<double>(), nullptr, nullptr, AXB_MEM_DEVICE, nullptr, &ex));
+  AXB_LAUNCH(ctx, min_update_kernel, blocks_for(npts, 256), 256, d_io, B.out_phi.as<double>(), npts);
+  if(memspace == AXB_MEM_HOST) AXB_CUDA_TRY(cudaMemcpyAsync(dist, d_io, sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.phase_end(tot);
+  if(memspace == AXB_MEM_HOST) AXB_TRY(ctx.sync());
   return ctx.finish_call();
 }
 

@@ -144,6 +144,23 @@ class SignedDistance:
         check(self._L.axb_sd_compute_distances_minreduce(self._h, comm._h, C.byref(k.desc), n, ptr, space))
         return d
 
+    def updateMinDistances(self, queryPts, dist):
+        """one GPU, partitioned surface: dist (float64 tensor / array, in place) becomes min(dist, distance to this handle's
+        part); the entry values bound the search (axb_sd_update_min_distances).  computeSign=False handles."""
+        k = make_desc(queryPts, 3)
+        n = k.count
+        if k.device:
+            import torch
+            if getattr(self, "_own_stream", True):
+                torch.cuda.current_stream(self.device).synchronize()
+            assert dist.is_cuda and dist.dtype == torch.float64 and dist.is_contiguous() and dist.numel() == n
+            ptr, space = dist.data_ptr(), MEM_DEVICE
+        else:
+            assert dist.dtype == np.float64 and dist.flags["C_CONTIGUOUS"] and dist.size == n
+            ptr, space = dist.ctypes.data, MEM_HOST
+        check(self._L.axb_sd_update_min_distances(self._h, C.byref(k.desc), n, ptr, space))
+        return dist
+
     def computeDistance(self, x, y=None, z=0.0):
         """computeDistance(x,y,z) / computeDistance(Point) (:243-266)"""
         p = np.array([[x, y, z]], np.float64) if y is not None else np.asarray(x, np.float64).reshape(1, 3)

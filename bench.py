@@ -522,8 +522,8 @@ def c5_leg(ctx, surface):
     """BASELINE config 5: the surface split into G spatially coherent parts (Morton ranges of the triangle centroids), one
     per rank with its own BVH; every rank evaluates ALL queries unsigned against its part; one elementwise MIN over the
     ranks (NCCL all-reduce over NVLink) gives the distance to the whole surface -- bit-identical, a min of exact
-    per-triangle values.  On one GPU the 8 parts are evaluated in turn and folded with a device-side minimum (no
-    collective).  Checked against the unmodified reference's SignedDistance over the WHOLE surface on a query sample."""
+    per-triangle values.  On one GPU the 8 parts are evaluated in turn into a running minimum that also bounds the
+    search of the next part (axb_sd_update_min_distances; no collective).  Checked against the unmodified reference's SignedDistance over the WHOLE surface on a query sample."""
     import torch
     from axom_b200 import SignedDistance
     from axom_b200 import dist as D
@@ -561,9 +561,10 @@ def c5_leg(ctx, surface):
             sds[0].computeDistancesMinReduce(comm, qd, out=out)  # kernel -> ncclAllReduce(MIN) in place, one stream, one C call
             return
         for k, sd in enumerate(sds):
-            sd.computeDistances(qd, out=(out if k == 0 else tmp))
-            if k:
-                torch.minimum(out, tmp, out=out)
+            if k == 0:
+                sd.computeDistances(qd, out=out)
+            else:
+                sd.updateMinDistances(qd, out)  # out = min(out, distance to part k); out bounds the search of part k
 
     step()
     ctx["barrier"]()

@@ -309,6 +309,11 @@ int axb_comm_allreduce_f64(axb_comm* comm, double* device_buf, int64_t n, int op
 int axb_sd_compute_distances_minreduce(axb_sd* sd, axb_comm* comm, const axb_array_desc* query_pts, int32_t npts, double* dist,
                                        int out_memspace);
 
+/* The same partitioned-surface query on ONE GPU, parts evaluated in turn: `dist` is in/out -- on entry the distance to the
+ * parts evaluated so far (DBL_MAX where none), on exit min(entry, distance to this handle's part).  The entry value bounds the
+ * search, so a part that is farther than what is already known costs a few node visits per query.  compute_sign = 0 handles. */
+int axb_sd_update_min_distances(axb_sd* sd, const axb_array_desc* query_pts, int32_t npts, double* dist_inout, int memspace);
+
 /* DistributedClosestPoint::computeClosestPoints (quest/DistributedClosestPoint.hpp:157-166, DistributedClosestPointImpl.hpp
  * :737-851), the whole of it: every rank passes ITS OWN query points (num_queries may be 0 and differ per rank) and gets,
  * for each, the nearest object point of the whole machine -- the five xferDom fields, with the reference's tie rule (first

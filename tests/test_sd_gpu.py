@@ -350,3 +350,38 @@ def test_compact_records_far_from_the_origin_and_at_extreme_scales(oracle, scale
         phi, cp, _ = sd.computeDistances(q, True, False)
         assert np.array_equal(rphi, phi), (scale, shift, cs, int((rphi != phi).sum()))
         assert np.array_equal(rcp, cp), (scale, shift, cs)
+
+
+def test_update_min_distances_over_surface_parts_equals_the_whole_surface(oracle):
+    """axb_sd_update_min_distances: the parts of a partitioned surface evaluated in turn on one GPU into a running minimum that
+    also bounds the next part's search; the result is the distance to the whole surface, bit for bit (device and host
+    arrays, parts taken in two different orders, DBL_MAX entries)."""
+    import torch
+    from axom_b200 import SignedDistance
+    from axom_b200 import dist as D
+    x, y, z, conn = synth.icosphere(24)
+    P = np.stack([x, y, z], 1)
+    cen = (P[conn[:, 0]] + P[conn[:, 1]] + P[conn[:, 2]]) / 3.0
+    parts = D.morton_partition(cen, 5)
+    rng = np.random.default_rng(31)
+    q = np.concatenate([rng.uniform(-1.2, 1.2, (40000, 3)), P[:500], rng.normal(0, 1e-3, (200, 3))])
+    want, _, _ = oracle.SignedDistance(x, y, z, conn, 3, False, False).compute(q, nthreads=0)
+    sds = [SignedDistance(x, y, z, conn[p], 3, False, False) for p in parts]
+    qd = torch.from_numpy(q).cuda()
+    for order in ([0, 1, 2, 3, 4], [3, 0, 4, 2, 1]):
+        out = torch.full((len(q),), float(np.finfo(np.float64).max), dtype=torch.float64, device="cuda")
+        for k in order:
+            sds[k].updateMinDistances(qd, out)
+        assert np.array_equal(out.cpu().numpy(), want), order
+        outh = np.full(len(q), np.finfo(np.float64).max)
+        for k in order:
+            sds[k].updateMinDistances(q, outh)
+        assert np.array_equal(outh, want), order
+    small = np.ascontiguousarray(q[:100])  # below the sorted / sampled path
+    o = np.full(100, np.finfo(np.float64).max)
+    for sd in sds:
+        sd.updateMinDistances(small, o)
+    assert np.array_equal(o, want[:100])
+    from axom_b200._lib import AxbError
+    with pytest.raises(AxbError):
+        SignedDistance(x, y, z, conn, 3, True, True).updateMinDistances(small, o)
