@@ -108,6 +108,27 @@ public:
                                    reinterpret_cast<double*>(outNormals), AXB_MEM_AUTO));
   }
 
+  // ---- a surface PARTITIONED over handles (BASELINE config 5; no counterpart in the reference class, which holds one mesh:
+  // its distributed query is quest::DistributedClosestPoint).  Handles built with computeSign = false. ----
+  // One GPU, parts evaluated in turn: dist (in/out, the caller's memory space) becomes min(dist, distance to this part);
+  // the entry values bound the search.  Start from DBL_MAX.
+  template <typename PointIndexable>
+  void updateMinDistances(int npts, PointIndexable queryPts, double* dist) const
+  {
+    detail::Resolved<double> r;
+    detail::indexable_traits<PointType, PointIndexable>::resolve(queryPts, npts, r);
+    check(axb_sd_update_min_distances(m_sd, &r.desc, npts, dist, AXB_MEM_AUTO));
+  }
+  // One part per rank, the same query points on every rank: query kernels + ncclAllReduce(MIN) on one stream, inside the
+  // library (comm: axom_b200::quest::Communicator::handle(), DistributedClosestPoint.hpp).  Collective.
+  template <typename PointIndexable>
+  void computeDistancesMinReduce(axb_comm* comm, int npts, PointIndexable queryPts, double* outDist) const
+  {
+    detail::Resolved<double> r;
+    detail::indexable_traits<PointType, PointIndexable>::resolve(queryPts, npts, r);
+    check(axb_sd_compute_distances_minreduce(m_sd, comm, &r.desc, npts, outDist, AXB_MEM_AUTO));
+  }
+
   const BVHTreeType& getBVHTree() const { return m_bvh; }
 
   // bounding box of the mesh nodes (m_boxDomain, :455-487)

@@ -9,6 +9,7 @@
 #define AXOM_B200_ALIAS_AXOM
 #include <algorithm>
 #include <cstring>
+#include <limits>
 #include <stdexcept>
 #include <vector>
 
@@ -217,6 +218,16 @@ static void test_signed_distance()
   EXPECT(c[2] == 0.0 && n[2] == 1.0);
   const Box3 mb = sd.getMeshBounds();
   EXPECT(mb.getMin()[0] == -5.0 && mb.getMax()[1] == 5.0 && mb.getMax()[2] == 0.0);
+  // the same plane partitioned over two unsigned handles, evaluated in turn into a running minimum: |z| exactly
+  axom::quest::SurfaceMesh half[2] = {mesh, mesh};
+  half[0].num_cells = 2;
+  half[1].cells_to_nodes = tris + 6;
+  half[1].num_cells = 2;
+  axom::quest::SignedDistance<3> part0(&half[0], false, /*computeSign*/ false), part1(&half[1], false, false);
+  std::vector<double> dmin(q.size(), std::numeric_limits<double>::max());
+  part0.updateMinDistances((int)q.size(), q.data(), dmin.data());
+  part1.updateMinDistances((int)q.size(), q.data(), dmin.data());
+  for(std::size_t i = 0; i < q.size(); ++i) EXPECT(dmin[i] == std::fabs(q[i][2]));
 }
 
 static void test_mesh_tester()
